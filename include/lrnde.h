@@ -1,0 +1,197 @@
+/*
+ * libLRNDE.so -- C ABI of the B200-native LocalRegNeuralDE hot path.
+ *
+ * This is the boundary a Julia maintainer binds with `ccall` from the unchanged
+ * layer constructors.  Plain C: pointers, sizes, PODs.  No
+ * torch / CUDA types in any signature (a CUDA stream is passed as `void*`).
+ *
+ * Citations are into the reference tree (avik-pal/LocalRegNeuralDE.jl):
+ *   lrnde_ode_forward   replaces the body of (n::NeuralODE)(x, ps, st)
+ *                       src/layers/neural_ode.jl:62-100, i.e. solve (:42-54),
+ *                       _get_ode_integrator (:33-38) and _perform_step
+ *                       (src/perform_step.jl:3-47).
+ *   lrnde_ode_backward  replaces the Zygote pullback through that functor:
+ *                       SciMLSensitivity InterpolatingAdjoint(ZygoteVJP) selected at
+ *                       neural_ode.jl:11 / experiments/src/construct.jl:197, plus the
+ *                       reverse pass of _perform_step w.r.t. ps only (neural_ode.jl:40,
+ *                       src/utils.jl:60; pinned by test/runtests.jl:127-131).
+ *   lrnde_model_create  describes the dynamics net the reference passes as `model`:
+ *                       Lux Chain of Dense layers, optionally a TDChain
+ *                       (src/layers/common.jl:2-45) -- time row appended before every
+ *                       layer -- as built in experiments/src/construct.jl:180-189,235-243.
+ *   lrnde_sosri_step    replaces _perform_step(::FourStageSRIConstantCache)
+ *                       src/perform_step.jl:49-106 for diagonal noise.
+ *
+ * Layout everywhere is the reference's: column-major [features, batch] Float32, `ps`
+ * in ComponentArray order (layer_1.weight[out x in(+1)], layer_1.bias[out], ...).
+ *
+ * Return value: 0 on success, negative LRNDE_E* otherwise; lrnde_last_error() gives a
+ * thread-local message.  Solver outcomes (MaxIters, DtLessThanMin, Unstable) are NOT
+ * errors: like the reference they are reported in stats.retcode and the call returns 0.
+ *
+ * Threading: one ctx <-> one device + one stream; a ctx is not thread-safe, different
+ * ctxs are independent.  The library never calls back into the host language.
+ */
+#ifndef LRNDE_H
+#define LRNDE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LRNDE_OK 0
+#define LRNDE_EINVAL (-1)   /* bad argument; mirrors ArgumentError of src/utils.jl:53-58 */
+#define LRNDE_ECUDA (-2)    /* CUDA runtime failure */
+#define LRNDE_ENOMEM (-3)   /* dense tape does not fit the configured budget */
+#define LRNDE_ESTATE (-4)   /* tape/ctx used out of order */
+
+/* activations (Lux/NNlib names) */
+enum { LRNDE_ACT_IDENTITY = 0, LRNDE_ACT_TANH = 1, LRNDE_ACT_GELU = 2, LRNDE_ACT_SIGMOID = 3,
+       LRNDE_ACT_RELU = 4, LRNDE_ACT_NONE = -1 };
+/* regularize (src/layers/neural_ode.jl:14-18) */
+enum { LRNDE_REG_NONE = 0, LRNDE_REG_UNBIASED = 1, LRNDE_REG_BIASED = 2 };
+/* regularize_type (src/perform_step.jl:34,40) */
+enum { LRNDE_REGTYPE_ERROR = 0, LRNDE_REGTYPE_STIFFNESS = 1 };
+/* arithmetic of the dense contractions */
+enum { LRNDE_PREC_AUTO = 0, LRNDE_PREC_FP32_SIMT = 1, LRNDE_PREC_TF32X3 = 2, LRNDE_PREC_TF32 = 3 };
+/* solver retcodes (OrdinaryDiffEq ReturnCode subset the loop can produce) */
+enum { LRNDE_RET_SUCCESS = 0, LRNDE_RET_MAXITERS = 1, LRNDE_RET_DTMIN = 2, LRNDE_RET_UNSTABLE = 3,
+       LRNDE_RET_TAPEFULL = 4 };
+/* controller power function */
+enum { LRNDE_POW_FASTPOW2023 = 0, LRNDE_POW_EXACT = 1 };
+
+typedef struct lrnde_ctx lrnde_ctx;
+typedef struct lrnde_model lrnde_model;
+typedef struct lrnde_tape lrnde_tape;
+
+/* One Lux Dense(in => out, act).  in_dims EXCLUDES the TDChain time row. */
+typedef struct {
+  int32_t in_dims;
+  int32_t out_dims;
+  int32_t act; /* LRNDE_ACT_* */
+} lrnde_layer_desc;
+
+/* kwargs of NeuralODE(...) / solve(...) that reach the hot path. */
+typedef struct {
+  float t0, t2;          /* tspan (neural_ode.jl:12) */
+  float abstol, reltol;  /* splatted kwargs (neural_ode.jl:51) */
+  int32_t maxiters;      /* neural_ode.jl:13 */
+  int32_t reg_mode;      /* LRNDE_REG_*; eval mode => pass LRNDE_REG_NONE (neural_ode.jl:66) */
+  int32_t reg_type;      /* LRNDE_REGTYPE_* */
+  float t1;              /* unbiased: host-sampled t1 (neural_ode.jl:71) */
+  float u01;             /* biased: host-sampled uniform [0,1) picking a step time (:92) */
+  const float* saveat;   /* HOST pointer, nsave sorted times in [t0,t2]; NULL => see nsave */
+  int32_t nsave;         /* >0: save at saveat[]; 0: save only t2; -1: every accepted step */
+  int32_t save_start;    /* with nsave==-1: include t0 */
+  int32_t precision;     /* LRNDE_PREC_* */
+  int32_t pow_mode;      /* LRNDE_POW_* */
+  int32_t host_buffers;  /* 1: ps/x/u_save/d_* are HOST pointers (Julia Array); staged inside */
+  int32_t keep_tape;     /* 1: return a tape for lrnde_ode_backward (training) */
+  int32_t loop_mode;     /* 0: CUDA-graph WHILE node; 1: host-chunked replay (diagnostic) */
+  int32_t reserved[7];
+} lrnde_opts;
+
+typedef struct {
+  int32_t nfe;        /* st'.nfe: sol.destats.nf (+ 6 + 3 when regularised), neural_ode.jl:79 */
+  int32_t naccept, nreject;
+  int32_t retcode;    /* LRNDE_RET_* of the main solve */
+  float reg_val;      /* st'.reg_val */
+  float t1_used;      /* the sampled time actually used (biased: a step time) */
+  float dt_reg;       /* auto-selected initial dt of the regulariser integrator */
+  int32_t nsave_out;  /* number of [D,B] blocks written to u_save */
+  int32_t nf_bwd, naccept_bwd, nreject_bwd, retcode_bwd; /* filled by lrnde_ode_backward */
+  int32_t gpu_launches; /* kernels this call launched (graph nodes x iterations included) */
+  int32_t reserved[7];
+} lrnde_stats;
+
+const char* lrnde_last_error(void);
+int lrnde_version(void);
+
+/* stream: a cudaStream_t, or NULL for a private non-blocking stream. */
+int lrnde_ctx_create(lrnde_ctx** out, int device, void* stream);
+int lrnde_ctx_destroy(lrnde_ctx* ctx);
+/* Blocks until everything this ctx enqueued has finished. */
+int lrnde_ctx_sync(lrnde_ctx* ctx);
+/* Upper bound (bytes) for the dense-tape arena; default 0 = 60% of free HBM at first use. */
+int lrnde_ctx_set_tape_budget(lrnde_ctx* ctx, uint64_t bytes);
+/* Data-parallel group: this ctx is `rank` of `nranks`; the per-step error norm (and every
+ * other norm the step-size logic takes) is summed over ranks through peer-mapped mailboxes.
+ * mailboxes[r] is the DEVICE-visible address of rank r's mailbox (lrnde_ctx_mailbox on r,
+ * exchanged by the host through CUDA IPC).  total_batch = sum of all ranks' B. */
+int lrnde_ctx_mailbox(lrnde_ctx* ctx, void** dev_ptr, uint64_t* bytes);
+int lrnde_ctx_set_dist(lrnde_ctx* ctx, int rank, int nranks, void* const* mailboxes,
+                       int64_t total_batch);
+
+int lrnde_model_create(lrnde_ctx* ctx, const lrnde_layer_desc* layers, int nlayers,
+                       int time_dependent, int input_act, lrnde_model** out);
+int lrnde_model_destroy(lrnde_model* m);
+int64_t lrnde_model_nparams(const lrnde_model* m);
+int64_t lrnde_model_state_dims(const lrnde_model* m);
+
+/* One f(u, ps, t) evaluation (the `dudt` closure, neural_ode.jl:45-48); parity hook. */
+int lrnde_dynamics_eval(lrnde_ctx* ctx, const lrnde_model* m, const lrnde_opts* o,
+                        const float* ps, const float* u, float t, int64_t B, float* du);
+
+/* Forward functor.  u_save receives stats->nsave_out blocks of [D,B]; capacity must be
+ * nsave (or 1 when nsave==0; when nsave==-1 pass u_save_cap blocks, the LAST accepted
+ * states are written oldest-first and nsave_out reports how many exist).  In unbiased mode
+ * with nsave==0 the reference returns [u(t1), u(t2)] (neural_ode.jl:108): two blocks.
+ * save_times (HOST, nullable) receives the corresponding times. */
+int lrnde_ode_forward(lrnde_ctx* ctx, const lrnde_model* m, const lrnde_opts* o,
+                      const float* ps, const float* x, int64_t B, float* u_save,
+                      int64_t u_save_cap, float* save_times, lrnde_stats* stats,
+                      lrnde_tape** tape);
+
+/* Pullback.  d_u_save: cotangent blocks matching what forward wrote (NULL = all zero),
+ * d_reg: cotangent of st'.reg_val.  Outputs d_ps [P] and d_x [D,B] (d reg/d x == 0,
+ * test/runtests.jl:129).  Consumes nothing: call lrnde_tape_free when done. */
+int lrnde_ode_backward(lrnde_ctx* ctx, const lrnde_model* m, lrnde_tape* tape,
+                       const float* d_u_save, float d_reg, float* d_ps, float* d_x,
+                       lrnde_stats* stats);
+int lrnde_tape_free(lrnde_tape* tape);
+
+/* Parity/diagnostics: every ATTEMPTED step of the last solve recorded on `tape`
+ * (which = 0 forward, 1 adjoint).  HOST arrays of capacity cap; *n = number of steps. */
+int lrnde_step_log(const lrnde_tape* tape, int which, float* t, float* dt, float* eest,
+                   uint8_t* accepted, int cap, int* n);
+
+/* _perform_step(::FourStageSRIConstantCache) for diagonal noise (perform_step.jl:49-106):
+ * one SOSRI step from (uprev, t, dt) with injected Wiener increments dW, dZ [D,B].
+ * drift / diffusion are two models over the same state; ps_drift / ps_diffusion their
+ * flat parameters.  Writes u [D,B] and *reg_val = EEst*dt.  delta = integrator.opts.delta. */
+int lrnde_sosri_step(lrnde_ctx* ctx, const lrnde_model* drift, const lrnde_model* diffusion,
+                     const lrnde_opts* o, const float* ps_drift, const float* ps_diffusion,
+                     const float* uprev, const float* dW, const float* dZ, float t, float dt,
+                     float delta, int64_t B, float* u, float* reg_val);
+
+/* Next row of the path: classifier Dense(D => C) + logitcrossentropy,
+ * experiments/src/construct.jl:199 and experiments/src/utils.jl:88, with its pullback.
+ * Wc: flat [C x D] weight then [C] bias; u: [D,B]; labels: class index per sample.
+ * Writes *loss (HOST), d_u [D,B] and d_Wc [C*D + C] (either may be NULL). */
+int lrnde_head_ce(lrnde_ctx* ctx, const float* Wc, const float* u, const int32_t* labels,
+                  int64_t B, int32_t D, int32_t C, int32_t host_buffers, float* loss, float* d_u,
+                  float* d_Wc);
+
+/* Adam update on device buffers (Optimisers.jl Adam as built in
+ * experiments/src/construct.jl:104-152); step >= 1 is the 1-based iteration count. */
+int lrnde_adam_step(lrnde_ctx* ctx, float* p, const float* g, float* m, float* v, int64_t n,
+                    float lr, float beta1, float beta2, float eps, int32_t step);
+
+/* Roofline probe: times `iters` back-to-back f(u, ps, t) evaluations (DEVICE pointers) with
+ * CUDA events on the ctx stream; *ms_per_eval is the mean, *launches_per_eval the kernels one
+ * evaluation launches. */
+int lrnde_profile_feval(lrnde_ctx* ctx, const lrnde_model* m, const lrnde_opts* o,
+                        const float* ps, const float* u, int64_t B, int32_t iters, float* du,
+                        float* ms_per_eval, int32_t* launches_per_eval);
+
+/* CUDA IPC plumbing for lrnde_ctx_set_dist when every rank is its own process: export a
+ * device allocation of this ctx as a 64-byte handle / map a peer's handle. */
+int lrnde_ipc_export(lrnde_ctx* ctx, void* dev_ptr, void* handle64_out);
+int lrnde_ipc_open(lrnde_ctx* ctx, const void* handle64, void** dev_ptr_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LRNDE_H */

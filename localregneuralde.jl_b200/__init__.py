@@ -1,0 +1,15 @@
+"""B200-native hot path of LocalRegNeuralDE.jl behind the reference's Lux-style layer API.
+
+The directory name contains a dot, so it is loaded through ``__graft_entry__.load_package()``
+(importlib) under the module name ``lrnde_b200``.  Everything numerical lives in
+``libLRNDE.so`` (csrc/, C ABI in include/lrnde.h); there is no CPU fallback.
+"""
+from ._lib import LIB_PATH, LrndeError, lib, SYMBOLS  # noqa: F401
+from .layers import (Chain, Context, Dense, DESolution, NeuralODE, TDChain,  # noqa: F401
+                     default_context, diffeqsol_to_array, diffeqsol_to_timeseries,
+                     glorot_uniform, nparams)
+
+try:
+    from .layers import neural_ode_apply  # noqa: F401
+except ImportError:  # torch missing
+    pass

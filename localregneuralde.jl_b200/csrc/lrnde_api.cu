@@ -1,0 +1,1146 @@
+// libLRNDE.so -- host orchestration + C ABI (include/lrnde.h).
+//
+// The layer logic restated here is the reference's src/layers/neural_ode.jl:56-116 (mode
+// dispatch, saveat resolution, t1, nfe bookkeeping); the solver loop, initial-dt heuristic and
+// continuous adjoint are the un-vendored OrdinaryDiffEq / SciMLSensitivity algorithms of
+// SURVEY App. A.  All arithmetic happens in kernels (lrnde_kernels.cuh, lrnde_umma.cuh); the
+// host only sequences launches and never waits inside a solve.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <cmath>
+#include <functional>
+#include <memory>
+
+#include "lrnde_host.h"
+#include "lrnde_kernels.cuh"
+
+// ------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+void lr_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+extern "C" const char* lrnde_last_error(void) { return g_err; }
+extern "C" int lrnde_version(void) { return 100; }
+
+#define LR_API_BEGIN try {
+#define LR_API_END                                     \
+  }                                                    \
+  catch (const LrError& e) { return e.code; }          \
+  catch (const std::bad_alloc&) {                      \
+    lr_set_error("host out of memory");                \
+    return LRNDE_ENOMEM;                               \
+  }                                                    \
+  return LRNDE_OK;
+
+static void lr_fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  throw LrError(code);
+}
+
+// ------------------------------------------------------------------------------------------
+// ctx: device memory pool (cudaMalloc synchronises; blocks are recycled across calls)
+// ------------------------------------------------------------------------------------------
+void* lrnde_ctx::alloc(size_t bytes) {
+  if (bytes == 0) bytes = 256;
+  bytes = (bytes + 255) & ~(size_t)255;
+  int best = -1;
+  for (size_t i = 0; i < pool.size(); ++i) {
+    if (!pool[i].used && pool[i].bytes >= bytes && pool[i].bytes <= 2 * bytes + (1 << 20)) {
+      if (best < 0 || pool[i].bytes < pool[best].bytes) best = (int)i;
+    }
+  }
+  if (best >= 0) {
+    pool[best].used = true;
+    return pool[best].p;
+  }
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    release_all_unused();
+    e = cudaMalloc(&p, bytes);
+  }
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    lr_fail(LRNDE_ENOMEM, "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+  }
+  pool.push_back({p, bytes, true});
+  return p;
+}
+void lrnde_ctx::release(void* p) {
+  if (!p) return;
+  for (auto& b : pool)
+    if (b.p == p) { b.used = false; return; }
+}
+void lrnde_ctx::release_all_unused() {
+  std::vector<PoolBlock> keep;
+  for (auto& b : pool) {
+    if (b.used) keep.push_back(b);
+    else cudaFree(b.p);
+  }
+  pool.swap(keep);
+}
+
+#define LR_COUNT(ctx) do { if ((ctx)->capturing) (ctx)->captured++; else (ctx)->launches++; } while (0)
+#define LR_CHECK_LAUNCH() LR_CUDA(cudaGetLastError())
+
+static inline int lr_ew_blocks(size_t n) {
+  size_t b = (n + 255) / 256;
+  if (b < 1) b = 1;
+  if (b > 148 * 8) b = 148 * 8;
+  return (int)b;
+}
+
+extern "C" int lrnde_ctx_create(lrnde_ctx** out, int device, void* stream) {
+  LR_API_BEGIN
+  if (!out) lr_fail(LRNDE_EINVAL, "lrnde_ctx_create: out is NULL");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    lr_fail(LRNDE_ECUDA, "libLRNDE needs a CUDA device (sm_100a); none is visible: %s",
+            cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) lr_fail(LRNDE_EINVAL, "device %d out of range", device);
+  LR_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  LR_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    lr_fail(LRNDE_ECUDA, "libLRNDE is built for sm_100a only; device %d is sm_%d%d", device,
+            prop.major, prop.minor);
+  auto* c = new lrnde_ctx();
+  c->device = device;
+  if (stream) c->stream = (cudaStream_t)stream;
+  else {
+    LR_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    c->own_stream = true;
+  }
+  c->pinned_bytes = 1 << 20;
+  LR_CUDA(cudaMallocHost(&c->pinned, c->pinned_bytes));
+  *out = c;
+  LR_API_END
+}
+
+extern "C" int lrnde_ctx_destroy(lrnde_ctx* c) {
+  LR_API_BEGIN
+  if (!c) return LRNDE_OK;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  for (auto& b : c->pool) cudaFree(b.p);
+  if (c->mailbox) cudaFree(c->mailbox);
+  if (c->pinned) cudaFreeHost(c->pinned);
+  if (c->own_stream) cudaStreamDestroy(c->stream);
+  delete c;
+  LR_API_END
+}
+
+extern "C" int lrnde_ctx_sync(lrnde_ctx* c) {
+  LR_API_BEGIN
+  if (!c) lr_fail(LRNDE_EINVAL, "ctx is NULL");
+  LR_CUDA(cudaSetDevice(c->device));
+  LR_CUDA(cudaStreamSynchronize(c->stream));
+  LR_API_END
+}
+
+extern "C" int lrnde_ctx_set_tape_budget(lrnde_ctx* c, uint64_t bytes) {
+  LR_API_BEGIN
+  if (!c) lr_fail(LRNDE_EINVAL, "ctx is NULL");
+  c->tape_budget = bytes;
+  LR_API_END
+}
+
+extern "C" int lrnde_ctx_mailbox(lrnde_ctx* c, void** dev_ptr, uint64_t* bytes) {
+  LR_API_BEGIN
+  if (!c || !dev_ptr) lr_fail(LRNDE_EINVAL, "ctx/dev_ptr is NULL");
+  LR_CUDA(cudaSetDevice(c->device));
+  if (!c->mailbox) {
+    // a dedicated cudaMalloc so the block can be exported with cudaIpcGetMemHandle
+    LR_CUDA(cudaMalloc((void**)&c->mailbox, sizeof(LrMailbox)));
+    LR_CUDA(cudaMemset(c->mailbox, 0, sizeof(LrMailbox)));
+  }
+  *dev_ptr = c->mailbox;
+  if (bytes) *bytes = sizeof(LrMailbox);
+  LR_API_END
+}
+
+extern "C" int lrnde_ctx_set_dist(lrnde_ctx* c, int rank, int nranks, void* const* mailboxes,
+                                  int64_t total_batch) {
+  LR_API_BEGIN
+  if (!c) lr_fail(LRNDE_EINVAL, "ctx is NULL");
+  if (nranks < 1 || nranks > LR_MAX_RANKS || rank < 0 || rank >= nranks)
+    lr_fail(LRNDE_EINVAL, "bad rank/nranks %d/%d (max %d)", rank, nranks, LR_MAX_RANKS);
+  if (nranks > 1 && !mailboxes) lr_fail(LRNDE_EINVAL, "mailboxes is NULL");
+  c->rank = rank;
+  c->nranks = nranks;
+  c->total_batch = total_batch;
+  for (int r = 0; r < nranks && nranks > 1; ++r) c->peer_mbox[r] = (LrMailbox*)mailboxes[r];
+  c->seq = 0;
+  LR_API_END
+}
+
+// ------------------------------------------------------------------------------------------
+// model
+// ------------------------------------------------------------------------------------------
+static int lr_map_act(int a) {
+  switch (a) {
+    case LRNDE_ACT_IDENTITY: case LRNDE_ACT_NONE: return ACT_IDENTITY;
+    case LRNDE_ACT_TANH: return ACT_TANH;
+    case LRNDE_ACT_GELU: return ACT_GELU;
+    case LRNDE_ACT_SIGMOID: return ACT_SIGMOID;
+    case LRNDE_ACT_RELU: return ACT_RELU;
+  }
+  lr_fail(LRNDE_EINVAL, "unknown activation %d", a);
+  return 0;
+}
+
+extern "C" int lrnde_model_create(lrnde_ctx* ctx, const lrnde_layer_desc* layers, int nlayers,
+                                  int time_dependent, int input_act, lrnde_model** out) {
+  LR_API_BEGIN
+  if (!ctx || !layers || !out || nlayers < 1) lr_fail(LRNDE_EINVAL, "lrnde_model_create: bad args");
+  auto m = std::make_unique<lrnde_model>();
+  m->ctx = ctx;
+  m->td = time_dependent ? 1 : 0;
+  m->input_act = lr_map_act(input_act);
+  int64_t off = 0;
+  for (int l = 0; l < nlayers; ++l) {
+    LayerInfo L;
+    L.in = layers[l].in_dims;
+    L.out = layers[l].out_dims;
+    if (L.in < 1 || L.out < 1) lr_fail(LRNDE_EINVAL, "layer %d: bad dims", l);
+    L.act = lr_map_act(layers[l].act);
+    L.w_off = off;
+    off += (int64_t)L.out * (L.in + m->td);
+    L.b_off = off;
+    off += L.out;
+    if (l > 0 && m->layers.back().out != L.in)
+      lr_fail(LRNDE_EINVAL, "layer %d: in_dims %d != previous out_dims %d", l, L.in,
+              m->layers.back().out);
+    m->layers.push_back(L);
+  }
+  if (m->layers.front().in != m->layers.back().out)
+    lr_fail(LRNDE_EINVAL, "dynamics must map R^D -> R^D (got %d -> %d)", m->layers.front().in,
+            m->layers.back().out);
+  m->nparams = off;
+  m->D = m->layers.front().in;
+  *out = m.release();
+  LR_API_END
+}
+extern "C" int lrnde_model_destroy(lrnde_model* m) {
+  delete m;
+  return LRNDE_OK;
+}
+extern "C" int64_t lrnde_model_nparams(const lrnde_model* m) { return m ? m->nparams : -1; }
+extern "C" int64_t lrnde_model_state_dims(const lrnde_model* m) { return m ? m->D : -1; }
+
+// ------------------------------------------------------------------------------------------
+// MLP evaluator: f(u, ps, t) and its VJP as sequences of kernels reading device descriptors
+// ------------------------------------------------------------------------------------------
+struct MlpEval {
+  lrnde_ctx* ctx;
+  const lrnde_model* m;
+  const float* ps;
+  int64_t B;
+  int prec;
+  bool with_vjp;
+  std::vector<float*> act;  // act[l]: [out_l x B]
+  std::vector<float*> pre;  // pre[l]: [out_l x B] (vjp only)
+  std::vector<float*> WT;   // [in_l x out_l] (vjp only)
+  float* ybuf = nullptr;
+  float* delta[2] = {nullptr, nullptr};
+  float* part = nullptr;
+  std::vector<int> wS, wChunk;
+
+  MlpEval(lrnde_ctx* c, const lrnde_model* mm, const float* p, int64_t b, int precision, bool vjp)
+      : ctx(c), m(mm), ps(p), B(b), prec(precision), with_vjp(vjp) {
+    const int L = (int)m->layers.size();
+    act.assign(L, nullptr);
+    for (int l = 0; l < L; ++l) {
+      if (l < L - 1 || vjp) act[l] = (float*)ctx->alloc(sizeof(float) * m->layers[l].out * B);
+    }
+    if (vjp) {
+      pre.assign(L, nullptr);
+      WT.assign(L, nullptr);
+      size_t maxd = 0, maxpart = 0;
+      for (int l = 0; l < L; ++l) {
+        const LayerInfo& Li = m->layers[l];
+        pre[l] = (float*)ctx->alloc(sizeof(float) * Li.out * B);
+        WT[l] = (float*)ctx->alloc(sizeof(float) * (size_t)Li.in * Li.out);
+        maxd = std::max(maxd, (size_t)std::max(Li.in, Li.out) * (size_t)B);
+        int naug = Li.in + m->td + 1;
+        int tiles = ((Li.out + DN_BM - 1) / DN_BM) * ((naug + DN_BN - 1) / DN_BN);
+        int S = std::max(1, std::min(64, (2 * 148 + tiles - 1) / tiles));
+        int chunk = (int)((B + S - 1) / S);
+        chunk = std::max(16, ((chunk + 15) / 16) * 16);
+        S = (int)((B + chunk - 1) / chunk);
+        wS.push_back(S);
+        wChunk.push_back(chunk);
+        maxpart = std::max(maxpart, (size_t)S * Li.out * naug);
+      }
+      ybuf = (float*)ctx->alloc(sizeof(float) * (size_t)m->D * B);
+      delta[0] = (float*)ctx->alloc(sizeof(float) * maxd);
+      delta[1] = (float*)ctx->alloc(sizeof(float) * maxd);
+      part = (float*)ctx->alloc(sizeof(float) * maxpart);
+    }
+  }
+  ~MlpEval() {
+    for (auto p : act) ctx->release(p);
+    for (auto p : pre) ctx->release(p);
+    for (auto p : WT) ctx->release(p);
+    ctx->release(ybuf);
+    ctx->release(delta[0]);
+    ctx->release(delta[1]);
+    ctx->release(part);
+  }
+
+  // once per call: transposed weights for the data-gradient GEMMs
+  void prepare() {
+    if (!with_vjp) return;
+    for (size_t l = 0; l < m->layers.size(); ++l) {
+      const LayerInfo& Li = m->layers[l];
+      dim3 g((Li.out + 31) / 32, (Li.in + 31) / 32), b(32, 8);
+      transpose_kernel<<<g, b, 0, ctx->stream>>>(ps + Li.w_off, Li.out, Li.in, WT[l]);
+      LR_COUNT(ctx);
+    }
+    LR_CHECK_LAUNCH();
+  }
+
+  void dense(const DenseP& p) {
+    dim3 g((p.M + DN_BM - 1) / DN_BM, (p.N + DN_BN - 1) / DN_BN);
+    dense_nn_kernel<<<g, 256, 0, ctx->stream>>>(p);
+    LR_COUNT(ctx);
+  }
+
+  DenseP layer_fwd(int l, const LinComb* in, const float* xplain) const {
+    const LayerInfo& Li = m->layers[l];
+    DenseP p;
+    memset(&p, 0, sizeof(p));
+    p.A = ps + Li.w_off; p.lda = Li.out; p.M = Li.out; p.K = Li.in; p.td = m->td; p.bias = 1;
+    if (l == 0) {
+      if (xplain) p.X = xplain; else p.xdesc = in;
+      p.in_act = m->input_act;
+    } else p.X = act[l - 1];
+    p.ldx = Li.in; p.N = (int)B;
+    p.ldy = Li.out; p.ldpre = Li.out;
+    p.act = Li.act; p.dact = -1; p.out_scale = 1.0f; p.tdesc = in;
+    return p;
+  }
+
+  // in->dst <- f(lincomb(in), ps, in->t)
+  void forward(const LinComb* in, const int* done) {
+    const int L = (int)m->layers.size();
+    for (int l = 0; l < L; ++l) {
+      DenseP p = layer_fwd(l, in, nullptr);
+      if (l == L - 1) { p.ydesc = in; p.y_off = 0; } else p.Y = act[l];
+      p.done = done;
+      dense(p);
+    }
+    LR_CHECK_LAUNCH();
+  }
+
+  // (a, dps) = (J_u^T lam, J_p^T lam) of f at (lincomb(y), y->t), lam = lincomb(lamd) over D*B.
+  //   a   -> a_scale * a   written to out_a, or to out_desc->dst
+  //   dps -> dst = p_beta * dst + p_scale * dps with dst = dps_ptr or dps_desc->dst + dps_off
+  void vjp(const LinComb* y, const LinComb* lamd, float* out_a, const LinComb* out_desc,
+           float a_scale, float* dps_ptr, const LinComb* dps_desc, size_t dps_off, float p_scale,
+           float p_beta, const int* done) {
+    const int L = (int)m->layers.size();
+    const size_t DB = (size_t)m->D * B;
+    cudaStream_t st = ctx->stream;
+    lincomb_kernel<<<lr_ew_blocks(DB), 256, 0, st>>>(y, ybuf, DB, done);
+    LR_COUNT(ctx);
+    const bool last_identity = (m->layers[L - 1].act == ACT_IDENTITY);
+    for (int l = 0; l < L; ++l) {
+      if (l == L - 1 && last_identity) break;  // output itself is not needed
+      DenseP p = layer_fwd(l, y, ybuf);
+      p.Y = act[l];
+      p.pre = pre[l];
+      p.done = done;
+      dense(p);
+    }
+    if (last_identity) lincomb_kernel<<<lr_ew_blocks(DB), 256, 0, st>>>(lamd, delta[0], DB, done);
+    else dact_mul_kernel<<<lr_ew_blocks(DB), 256, 0, st>>>(lamd, pre[L - 1], m->layers[L - 1].act,
+                                                            delta[0], DB, done);
+    LR_COUNT(ctx);
+    int cur = 0;
+    for (int l = L - 1; l >= 0; --l) {
+      const LayerInfo& Li = m->layers[l];
+      const int naug = Li.in + m->td + 1;
+      WgradP w;
+      memset(&w, 0, sizeof(w));
+      w.Dl = delta[cur]; w.ldd = Li.out; w.M = Li.out;
+      w.X = (l == 0) ? ybuf : act[l - 1]; w.ldx = Li.in; w.Nin = Li.in; w.td = m->td; w.bias = 1;
+      w.in_act = (l == 0) ? m->input_act : 0;
+      w.B = (int)B; w.chunk = wChunk[l]; w.part = part; w.tdesc = y; w.done = done;
+      dim3 g((Li.out + DN_BM - 1) / DN_BM, (naug + DN_BN - 1) / DN_BN, wS[l]);
+      wgrad_nt_kernel<<<g, 256, 0, st>>>(w);
+      LR_COUNT(ctx);
+      const size_t nw = (size_t)Li.out * naug;
+      wgrad_reduce_kernel<<<lr_ew_blocks(nw), 256, 0, st>>>(
+          part, wS[l], nw, dps_ptr ? dps_ptr + Li.w_off : nullptr, dps_desc,
+          dps_off + (size_t)Li.w_off, p_scale, p_beta, done);
+      LR_COUNT(ctx);
+      DenseP p;
+      memset(&p, 0, sizeof(p));
+      p.A = WT[l]; p.lda = Li.in; p.M = Li.in; p.K = Li.out; p.td = 0; p.bias = 0;
+      p.X = delta[cur]; p.ldx = Li.out; p.N = (int)B;
+      p.ldy = Li.in; p.act = ACT_IDENTITY; p.dact = -1; p.out_scale = 1.0f; p.done = done;
+      if (l > 0) {
+        p.Y = delta[cur ^ 1];
+        if (m->layers[l - 1].act != ACT_IDENTITY) {
+          p.dact = m->layers[l - 1].act; p.dpre = pre[l - 1]; p.lddpre = Li.in;
+        }
+      } else {
+        if (out_a) p.Y = out_a; else { p.ydesc = out_desc; p.y_off = 0; }
+        if (m->input_act != ACT_IDENTITY) { p.dact = m->input_act; p.dpre = ybuf; p.lddpre = Li.in; }
+        p.out_scale = a_scale;
+      }
+      dense(p);
+      cur ^= 1;
+    }
+    LR_CHECK_LAUNCH();
+  }
+};
+
+// ------------------------------------------------------------------------------------------
+// Solver: one adaptive Tsit5 integration whose state lives on the device
+// ------------------------------------------------------------------------------------------
+struct Solver {
+  lrnde_ctx* ctx;
+  SolveDev h;            // host image used to initialise / read back
+  SolveDev* dev = nullptr;
+  float* tape = nullptr;
+  float* ts = nullptr;
+  float* logbuf = nullptr;
+  unsigned char* logacc = nullptr;
+  double* partials = nullptr;
+  unsigned int* counters = nullptr;
+  cudaGraph_t while_graph = nullptr, body_graph = nullptr;
+  cudaGraphExec_t while_exec = nullptr, body_exec = nullptr;
+  long body_nodes = 0;
+  std::function<void()> body;
+
+  Solver(lrnde_ctx* c, size_t len, size_t lam_len, int cap, int ring, int logcap) : ctx(c) {
+    memset(&h, 0, sizeof(h));
+    h.len = len;
+    h.lam_len = lam_len;
+    h.cap = cap;
+    h.ring = ring;
+    h.logcap = logcap;
+    dev = (SolveDev*)ctx->alloc(sizeof(SolveDev));
+    tape = (float*)ctx->alloc(sizeof(float) * 7 * len * (size_t)cap);
+    if (!ring) ts = (float*)ctx->alloc(sizeof(float) * ((size_t)cap + 1));
+    logbuf = (float*)ctx->alloc(sizeof(float) * 3 * (size_t)std::max(logcap, 1));
+    logacc = (unsigned char*)ctx->alloc((size_t)std::max(logcap, 1));
+    partials = (double*)ctx->alloc(sizeof(double) * 4 * LR_ERR_BLOCKS);
+    counters = (unsigned int*)ctx->alloc(sizeof(unsigned int) * 4);
+    h.tape = tape;
+    h.ts = ts;
+    h.log_t = logbuf;
+    h.log_dt = logbuf + std::max(logcap, 1);
+    h.log_eest = logbuf + 2 * (size_t)std::max(logcap, 1);
+    h.log_acc = logacc;
+    h.partials = partials;
+    h.counters = counters;
+    h.rank = ctx->rank;
+    h.nranks = ctx->nranks;
+    h.total_len = len;
+    for (int r = 0; r < LR_MAX_RANKS; ++r) h.mbox[r] = ctx->peer_mbox[r];
+  }
+  ~Solver() {
+    if (while_exec) cudaGraphExecDestroy(while_exec);
+    if (body_exec) cudaGraphExecDestroy(body_exec);
+    if (while_graph) cudaGraphDestroy(while_graph);
+    if (body_graph) cudaGraphDestroy(body_graph);
+    ctx->release(dev);
+    ctx->release(tape);
+    ctx->release(ts);
+    ctx->release(logbuf);
+    ctx->release(logacc);
+    ctx->release(partials);
+    ctx->release(counters);
+  }
+
+  void upload() {
+    h.seq = ctx->seq;
+    LR_CUDA(cudaMemsetAsync(counters, 0, sizeof(unsigned int) * 4, ctx->stream));
+    LR_CUDA(cudaMemcpyAsync(dev, &h, sizeof(SolveDev), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  void download() {
+    SolveDev* pin = (SolveDev*)ctx->pinned;
+    LR_CUDA(cudaMemcpyAsync(pin, dev, sizeof(SolveDev), cudaMemcpyDeviceToHost, ctx->stream));
+    LR_CUDA(cudaStreamSynchronize(ctx->stream));
+    h = *pin;
+    ctx->seq = h.seq;
+  }
+
+  void init_ctrl(float t0, float tend, float first_stop, int maxiters, int pow_mode,
+                 float abstol, float reltol) {
+    float dtmin = std::max(lr_spacing(t0), lr_spacing(tend));
+    lr_ctrl_init(h.c, t0, tend, 0.0f, dtmin, maxiters, pow_mode);
+    h.c.tstop = first_stop;
+    h.abstol = abstol;
+    h.reltol = reltol;
+    h.slot = 0;
+    h.done = 0;
+    h.failed = 0;
+    h.tape_full = 0;
+  }
+
+  // one step attempt = body(); captured once, then looped on the device
+  void build_graphs(int loop_mode) {
+    cudaStream_t st = ctx->stream;
+    if (loop_mode == 0) {
+      LR_CUDA(cudaGraphCreate(&while_graph, 0));
+      cudaGraphConditionalHandle handle;
+      LR_CUDA(cudaGraphConditionalHandleCreate(&handle, while_graph, 0, 0));
+      h.cond_handle = (unsigned long long)handle;
+      h.use_cond = 1;
+      cudaGraphNode_t prime;
+      cudaKernelNodeParams kp;
+      memset(&kp, 0, sizeof(kp));
+      SolveDev* d = dev;
+      void* args[] = {&d};
+      kp.func = (void*)cond_prime_kernel_entry();
+      kp.gridDim = dim3(1);
+      kp.blockDim = dim3(32);
+      kp.kernelParams = args;
+      LR_CUDA(cudaGraphAddKernelNode(&prime, while_graph, nullptr, 0, &kp));
+      cudaGraphNodeParams cp = {cudaGraphNodeTypeConditional};
+      cp.type = cudaGraphNodeTypeConditional;
+      cp.conditional.handle = handle;
+      cp.conditional.type = cudaGraphCondTypeWhile;
+      cp.conditional.size = 1;
+      cudaGraphNode_t cond;
+      LR_CUDA(cudaGraphAddNode(&cond, while_graph, &prime, 1, &cp));
+      cudaGraph_t bodyg = cp.conditional.phGraph_out[0];
+      ctx->capturing = true;
+      long before = ctx->captured;
+      cudaError_t e = cudaStreamBeginCaptureToGraph(st, bodyg, nullptr, nullptr, 0,
+                                                    cudaStreamCaptureModeThreadLocal);
+      if (e != cudaSuccess) { ctx->capturing = false; LR_CUDA(e); }
+      try { body(); } catch (...) {
+        cudaGraph_t dummy; cudaStreamEndCapture(st, &dummy); ctx->capturing = false; throw;
+      }
+      cudaGraph_t outg = nullptr;
+      e = cudaStreamEndCapture(st, &outg);
+      ctx->capturing = false;
+      LR_CUDA(e);
+      body_nodes = ctx->captured - before;
+      LR_CUDA(cudaGraphInstantiate(&while_exec, while_graph, 0));
+    } else {
+      h.use_cond = 0;
+      ctx->capturing = true;
+      long before = ctx->captured;
+      cudaError_t e = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
+      if (e != cudaSuccess) { ctx->capturing = false; LR_CUDA(e); }
+      try { body(); } catch (...) {
+        cudaGraph_t dummy; cudaStreamEndCapture(st, &dummy); ctx->capturing = false; throw;
+      }
+      e = cudaStreamEndCapture(st, &body_graph);
+      ctx->capturing = false;
+      LR_CUDA(e);
+      body_nodes = ctx->captured - before;
+      LR_CUDA(cudaGraphInstantiate(&body_exec, body_graph, 0));
+    }
+  }
+  static void* cond_prime_kernel_entry();
+
+  // run attempts until the device says done.  WHILE mode: no host involvement at all.
+  // Chunked mode (diagnostic): replay the body in groups of 8 and poll the flag.
+  void run_segment() {
+    cudaStream_t st = ctx->stream;
+    if (while_exec) {
+      LR_CUDA(cudaGraphLaunch(while_exec, st));
+      ctx->launches += 1;
+    } else {
+      int* pin = (int*)((char*)ctx->pinned + sizeof(SolveDev) + 64);
+      for (;;) {
+        for (int i = 0; i < 8; ++i) LR_CUDA(cudaGraphLaunch(body_exec, st));
+        LR_CUDA(cudaMemcpyAsync(pin, &dev->done, sizeof(int), cudaMemcpyDeviceToHost, st));
+        LR_CUDA(cudaStreamSynchronize(st));
+        if (*pin) break;
+      }
+    }
+  }
+};
+
+__global__ void cond_prime_kernel(SolveDev* S) {
+  if (threadIdx.x == 0) lr_set_cond(S);
+}
+void* Solver::cond_prime_kernel_entry() { return (void*)cond_prime_kernel; }
+
+// ------------------------------------------------------------------------------------------
+// tape: everything the pullback needs
+// ------------------------------------------------------------------------------------------
+struct lrnde_tape {
+  lrnde_ctx* ctx;
+  const lrnde_model* model;
+  lrnde_opts opts;
+  int64_t B;
+  float* ps = nullptr;  // device copy of the parameters the forward used
+  std::unique_ptr<Solver> fwd;
+  std::unique_ptr<Solver> reg;  // regulariser integrator (2-slot ring), reg modes only
+  std::vector<float> fts;       // host copy of accepted times
+  std::vector<float> save_ts;   // times of the FULL saved solution (incl. t1 when appended)
+  std::vector<int> save_out;    // index of the output block for each save_ts entry, -1 if dropped
+  int reg_mode = 0;
+  float t1 = 0.f;
+  // step logs (host copies)
+  std::vector<float> log_t[2], log_dt[2], log_eest[2];
+  std::vector<unsigned char> log_acc[2];
+  ~lrnde_tape() { ctx->release(ps); }
+};
+
+static void lr_copy_log(Solver& S, lrnde_tape* T, int which) {
+  int n = std::min(S.h.nlog, S.h.logcap);
+  T->log_t[which].resize(n);
+  T->log_dt[which].resize(n);
+  T->log_eest[which].resize(n);
+  T->log_acc[which].resize(n);
+  if (n == 0) return;
+  cudaStream_t st = S.ctx->stream;
+  LR_CUDA(cudaMemcpyAsync(T->log_t[which].data(), S.h.log_t, 4 * (size_t)n, cudaMemcpyDeviceToHost, st));
+  LR_CUDA(cudaMemcpyAsync(T->log_dt[which].data(), S.h.log_dt, 4 * (size_t)n, cudaMemcpyDeviceToHost, st));
+  LR_CUDA(cudaMemcpyAsync(T->log_eest[which].data(), S.h.log_eest, 4 * (size_t)n, cudaMemcpyDeviceToHost, st));
+  LR_CUDA(cudaMemcpyAsync(T->log_acc[which].data(), S.h.log_acc, (size_t)n, cudaMemcpyDeviceToHost, st));
+  LR_CUDA(cudaStreamSynchronize(st));
+}
+
+// fsalfirst + initial dt of a freshly initialised solver (OrdinaryDiffEq __init: initialize!
+// then auto_dt_reset!), then the header of the first attempt when `begin`.
+template <class EvalFn>
+static void lr_solver_start(Solver& S, EvalFn&& eval, int begin) {
+  lrnde_ctx* ctx = S.ctx;
+  cudaStream_t st = ctx->stream;
+  k1_desc_kernel<<<1, 32, 0, st>>>(S.dev);
+  LR_COUNT(ctx);
+  eval(&S.dev->st[6], &S.dev->yint[6], &S.dev->failed);
+  initdt_norm1_kernel<<<LR_ERR_BLOCKS, 256, 0, st>>>(S.dev);
+  LR_COUNT(ctx);
+  initdt_a_kernel<<<1, 32, 0, st>>>(S.dev);
+  LR_COUNT(ctx);
+  eval(&S.dev->st[0], &S.dev->yint[1], &S.dev->failed);
+  initdt_norm2_kernel<<<LR_ERR_BLOCKS, 256, 0, st>>>(S.dev);
+  LR_COUNT(ctx);
+  initdt_b_kernel<<<1, 32, 0, st>>>(S.dev, begin);
+  LR_COUNT(ctx);
+  LR_CHECK_LAUNCH();
+}
+
+// the kernels of one step attempt (perform_step! + loopfooter! + next loopheader!)
+template <class EvalFn>
+static void lr_step_body(Solver& S, EvalFn&& eval) {
+  lrnde_ctx* ctx = S.ctx;
+  cudaStream_t st = ctx->stream;
+  for (int j = 0; j < 5; ++j) eval(&S.dev->st[j], &S.dev->yint[j + 1], &S.dev->done);
+  lincomb_kernel<<<lr_ew_blocks(S.h.len), 256, 0, st>>>(&S.dev->st[5], nullptr, S.h.len, &S.dev->done);
+  LR_COUNT(ctx);
+  eval(&S.dev->st[6], &S.dev->yint[6], &S.dev->done);
+  err_norm_kernel<<<LR_ERR_BLOCKS, 256, 0, st>>>(S.dev);
+  LR_COUNT(ctx);
+  controller_kernel<<<1, 32, 0, st>>>(S.dev);
+  LR_COUNT(ctx);
+  LR_CHECK_LAUNCH();
+}
+
+static void lr_grow_tape(Solver& S) {
+  lrnde_ctx* ctx = S.ctx;
+  cudaStream_t st = ctx->stream;
+  int newcap = S.h.cap * 2;
+  size_t slot_bytes = sizeof(float) * 7 * S.h.len;
+  float* nt = (float*)ctx->alloc(slot_bytes * (size_t)newcap);
+  float* nts = (float*)ctx->alloc(sizeof(float) * ((size_t)newcap + 1));
+  LR_CUDA(cudaMemcpyAsync(nt, S.tape, slot_bytes * (size_t)(S.h.slot + 1), cudaMemcpyDeviceToDevice, st));
+  LR_CUDA(cudaMemcpyAsync(nts, S.ts, sizeof(float) * (size_t)(S.h.slot + 1), cudaMemcpyDeviceToDevice, st));
+  LR_CUDA(cudaStreamSynchronize(st));
+  ctx->release(S.tape);
+  ctx->release(S.ts);
+  S.tape = nt;
+  S.ts = nts;
+  S.h.tape = nt;
+  S.h.ts = nts;
+  S.h.cap = newcap;
+  // patch the three fields in the device image
+  LR_CUDA(cudaMemcpyAsync(&S.dev->tape, &S.h.tape, sizeof(float*), cudaMemcpyHostToDevice, st));
+  LR_CUDA(cudaMemcpyAsync(&S.dev->ts, &S.h.ts, sizeof(float*), cudaMemcpyHostToDevice, st));
+  LR_CUDA(cudaMemcpyAsync(&S.dev->cap, &S.h.cap, sizeof(int), cudaMemcpyHostToDevice, st));
+}
+
+static size_t lr_tape_budget(lrnde_ctx* ctx) {
+  if (ctx->tape_budget) return (size_t)ctx->tape_budget;
+  size_t fr = 0, tot = 0;
+  LR_CUDA(cudaMemGetInfo(&fr, &tot));
+  size_t pooled = 0;
+  for (auto& b : ctx->pool)
+    if (!b.used) pooled += b.bytes;
+  return (size_t)(0.6 * (double)(fr + pooled));
+}
+
+// host-side evaluation of "sol(t)" on the dense forward tape: descriptor of the interpolant
+// (or of the stored state on an exact hit), oracle ODESolution.__call__(exact_hit_stored=True)
+static LinComb lr_host_interp(const Solver& F, const std::vector<float>& fts, float tval) {
+  LinComb d;
+  memset(&d, 0, sizeof(d));
+  const int nsteps = (int)fts.size() - 1;
+  for (int n = 0; n <= nsteps; ++n) {
+    if (fts[n] == tval) {
+      d.base = F.tape + (size_t)n * 7 * F.h.len;
+      d.t = tval;
+      return d;
+    }
+  }
+  if (nsteps < 1) {
+    d.base = F.tape;
+    d.t = tval;
+    return d;
+  }
+  int n = lr_locate(fts.data(), nsteps, 1, tval);
+  float dt = lr_sub(fts[n + 1], fts[n]);
+  float th = lr_div(lr_sub(tval, fts[n]), dt);
+  float b[7];
+  lr_tsit5_interp(th, b);
+  const float* slot = F.tape + (size_t)n * 7 * F.h.len;
+  d.base = slot;
+  for (int k = 0; k < 6; ++k) d.src[k] = slot + (size_t)(k + 1) * F.h.len;
+  d.src[6] = slot + (size_t)8 * F.h.len;
+  for (int k = 0; k < 7; ++k) d.coef[k] = b[k];
+  d.scale = dt;
+  d.n = 7;
+  d.t = tval;
+  return d;
+}
+
+static void lr_validate_opts(const lrnde_opts* o) {
+  if (!o) lr_fail(LRNDE_EINVAL, "opts is NULL");
+  if (o->reg_mode < LRNDE_REG_NONE || o->reg_mode > LRNDE_REG_BIASED)
+    lr_fail(LRNDE_EINVAL, "regularize must be one of (:none, :unbiased, :biased)");
+  if (o->reg_type != LRNDE_REGTYPE_ERROR && o->reg_type != LRNDE_REGTYPE_STIFFNESS)
+    lr_fail(LRNDE_EINVAL, "regularize must be one of (:error_estimate, :stiffness_estimate)");
+  if (!(o->t2 > o->t0)) lr_fail(LRNDE_EINVAL, "tspan must satisfy t0 < t2");
+  if (o->maxiters < 1) lr_fail(LRNDE_EINVAL, "maxiters must be >= 1");
+  if (o->nsave > 0 && !o->saveat) lr_fail(LRNDE_EINVAL, "saveat is NULL but nsave > 0");
+  if (o->precision < LRNDE_PREC_AUTO || o->precision > LRNDE_PREC_TF32)
+    lr_fail(LRNDE_EINVAL, "unknown precision %d", o->precision);
+}
+
+struct DevBuf {  // pooled device scratch with RAII
+  lrnde_ctx* ctx;
+  float* p;
+  DevBuf(lrnde_ctx* c, size_t nfloat) : ctx(c), p((float*)c->alloc(sizeof(float) * nfloat)) {}
+  ~DevBuf() { ctx->release(p); }
+};
+
+// ------------------------------------------------------------------------------------------
+// f(u, ps, t) once (parity hook)
+// ------------------------------------------------------------------------------------------
+extern "C" int lrnde_dynamics_eval(lrnde_ctx* ctx, const lrnde_model* m, const lrnde_opts* o,
+                                   const float* ps, const float* u, float t, int64_t B,
+                                   float* du) {
+  LR_API_BEGIN
+  if (!ctx || !m || !ps || !u || !du || B < 1) lr_fail(LRNDE_EINVAL, "lrnde_dynamics_eval: bad args");
+  LR_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const int host = o ? o->host_buffers : 0;
+  const size_t DB = (size_t)m->D * B;
+  DevBuf dps(ctx, host ? m->nparams : 1), dun(ctx, host ? DB : 1), dout(ctx, host ? DB : 1);
+  DevBuf ddesc(ctx, sizeof(LinComb) / 4 + 1);
+  const float* psd = ps;
+  const float* ud = u;
+  float* outd = du;
+  if (host) {
+    LR_CUDA(cudaMemcpyAsync(dps.p, ps, 4 * m->nparams, cudaMemcpyHostToDevice, st));
+    LR_CUDA(cudaMemcpyAsync(dun.p, u, 4 * DB, cudaMemcpyHostToDevice, st));
+    psd = dps.p; ud = dun.p; outd = dout.p;
+  }
+  LinComb d;
+  memset(&d, 0, sizeof(d));
+  d.base = ud; d.t = t; d.dst = outd;
+  LR_CUDA(cudaMemcpyAsync(ddesc.p, &d, sizeof(d), cudaMemcpyHostToDevice, st));
+  MlpEval ev(ctx, m, psd, B, o ? o->precision : 0, false);
+  ev.forward((const LinComb*)ddesc.p, nullptr);
+  if (host) LR_CUDA(cudaMemcpyAsync(du, outd, 4 * DB, cudaMemcpyDeviceToHost, st));
+  LR_CUDA(cudaStreamSynchronize(st));
+  LR_API_END
+}
+
+// ------------------------------------------------------------------------------------------
+// forward functor
+// ------------------------------------------------------------------------------------------
+extern "C" int lrnde_ode_forward(lrnde_ctx* ctx, const lrnde_model* m, const lrnde_opts* o,
+                                 const float* ps, const float* x, int64_t B, float* u_save,
+                                 int64_t u_save_cap, float* save_times, lrnde_stats* stats,
+                                 lrnde_tape** tape_out) {
+  LR_API_BEGIN
+  if (!ctx || !m || !ps || !x || !stats || B < 1) lr_fail(LRNDE_EINVAL, "lrnde_ode_forward: bad args");
+  lr_validate_opts(o);
+  if (o->keep_tape && !tape_out) lr_fail(LRNDE_EINVAL, "keep_tape set but tape is NULL");
+  LR_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  memset(stats, 0, sizeof(*stats));
+  const long launches0 = ctx->launches;
+  const int D = m->D;
+  const size_t DB = (size_t)D * B;
+  const int64_t P = m->nparams;
+  const int host = o->host_buffers;
+  const cudaMemcpyKind in_kind = host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+
+  auto T = std::make_unique<lrnde_tape>();
+  T->ctx = ctx;
+  T->model = m;
+  T->opts = *o;
+  T->opts.saveat = nullptr;
+  T->B = B;
+  T->reg_mode = o->reg_mode;
+  T->ps = (float*)ctx->alloc(sizeof(float) * P);
+  LR_CUDA(cudaMemcpyAsync(T->ps, ps, sizeof(float) * P, in_kind, st));
+
+  // ---- dense tape
+  size_t slot_bytes = sizeof(float) * 7 * DB;
+  size_t budget_slots = std::max<size_t>(3, lr_tape_budget(ctx) / slot_bytes);
+  int cap = (int)std::min<size_t>({(size_t)o->maxiters + 2, (size_t)96, budget_slots});
+  cap = std::max(cap, 3);
+  T->fwd = std::make_unique<Solver>(ctx, DB, DB, cap, 0, o->maxiters + 1);
+  Solver& F = *T->fwd;
+  if (ctx->nranks > 1) F.h.total_len = (unsigned long long)D * (unsigned long long)ctx->total_batch;
+  F.init_ctrl(o->t0, o->t2, o->t2, o->maxiters, o->pow_mode, o->abstol, o->reltol);
+  LR_CUDA(cudaMemcpyAsync(F.tape, x, sizeof(float) * DB, in_kind, st));
+  LR_CUDA(cudaMemcpyAsync(F.ts, &o->t0, sizeof(float), cudaMemcpyHostToDevice, st));
+
+  const bool need_vjp = false;
+  MlpEval ev(ctx, m, T->ps, B, o->precision, need_vjp);
+  auto eval = [&](const LinComb* in, const LinComb*, const int* done) { ev.forward(in, done); };
+  F.body = [&]() { lr_step_body(F, eval); };
+  F.build_graphs(o->loop_mode);
+  F.upload();
+  lr_solver_start(F, eval, 1);
+  for (;;) {
+    F.run_segment();
+    F.download();
+    if (!F.h.tape_full) break;
+    if ((size_t)F.h.cap * 2 > budget_slots) {
+      F.h.c.retcode = LR_RET_TAPEFULL;
+      break;
+    }
+    lr_grow_tape(F);
+    segment_begin_kernel<<<1, 32, 0, st>>>(F.dev, 0.0f, 0);
+    LR_COUNT(ctx);
+  }
+  const int naccept = F.h.c.naccept, nreject = F.h.c.nreject;
+  T->fts.resize(naccept + 1);
+  LR_CUDA(cudaMemcpyAsync(T->fts.data(), F.ts, sizeof(float) * (naccept + 1), cudaMemcpyDeviceToHost, st));
+  LR_CUDA(cudaStreamSynchronize(st));
+  lr_copy_log(F, T.get(), 0);
+  const float t_last = T->fts.back();
+
+  // ---- which times the returned solution holds (neural_ode.jl:102-116)
+  std::vector<float> times;      // full saved solution
+  std::vector<int> out_index;    // output block per entry, -1 = dropped (_CorrectedDESolution)
+  float t1 = o->t1;
+  const int mode = o->reg_mode;
+  if (o->nsave > 0) {
+    for (int i = 0; i < o->nsave; ++i) times.push_back(o->saveat[i]);
+    if (o->save_start && std::find(times.begin(), times.end(), o->t0) == times.end())
+      times.insert(times.begin(), o->t0);
+    for (size_t i = 0; i < times.size(); ++i) out_index.push_back((int)i);
+    if (mode == LRNDE_REG_UNBIASED) { times.push_back(t1); out_index.push_back(-1); }
+  } else if (o->nsave == 0 && mode != LRNDE_REG_BIASED) {
+    if (mode == LRNDE_REG_UNBIASED) { times.push_back(t1); out_index.push_back(0); }
+    times.push_back(o->t2);
+    out_index.push_back((int)out_index.size());
+  } else {  // every accepted step (saveat = [] of the :biased path, or nsave == -1)
+    int start = o->save_start ? 0 : 1;
+    for (int n = start; n <= naccept; ++n) { times.push_back(T->fts[n]); out_index.push_back(n - start); }
+  }
+  if (mode == LRNDE_REG_BIASED) {  // t1 = rand(rng, sol.t[1:end-1])   (neural_ode.jl:92)
+    int ncand = (int)times.size() - 1;
+    if (ncand > 0) {
+      int idx = std::min(ncand - 1, std::max(0, (int)std::floor(o->u01 * (float)ncand)));
+      t1 = times[idx];
+    } else t1 = o->t0;
+  }
+  int nout = 0;
+  for (int v : out_index) nout = std::max(nout, v + 1);
+  if (u_save && nout > u_save_cap)
+    lr_fail(LRNDE_EINVAL, "u_save holds %lld blocks but the solution has %d", (long long)u_save_cap, nout);
+
+  // ---- write the saved states
+  std::vector<LinComb> descs;
+  std::vector<int> desc_out;
+  for (size_t i = 0; i < times.size(); ++i) {
+    if (out_index[i] < 0) continue;
+    float tq = std::min(times[i], t_last);
+    descs.push_back(lr_host_interp(F, T->fts, tq));
+    desc_out.push_back(out_index[i]);
+    if (save_times) save_times[out_index[i]] = times[i];
+  }
+  if (u_save && !descs.empty()) {
+    DevBuf dd(ctx, descs.size() * (sizeof(LinComb) / 4 + 1));
+    LR_CUDA(cudaMemcpyAsync(dd.p, descs.data(), sizeof(LinComb) * descs.size(), cudaMemcpyHostToDevice, st));
+    DevBuf stage(ctx, host ? DB * descs.size() : 1);
+    for (size_t i = 0; i < descs.size(); ++i) {
+      float* dst = host ? stage.p + i * DB : u_save + (size_t)desc_out[i] * DB;
+      lincomb_kernel<<<lr_ew_blocks(DB), 256, 0, st>>>(((const LinComb*)dd.p) + i, dst, DB, nullptr);
+      LR_COUNT(ctx);
+      if (host)
+        LR_CUDA(cudaMemcpyAsync(u_save + (size_t)desc_out[i] * DB, dst, sizeof(float) * DB,
+                                cudaMemcpyDeviceToHost, st));
+    }
+    LR_CHECK_LAUNCH();
+    LR_CUDA(cudaStreamSynchronize(st));
+  }
+  T->save_ts = times;
+  T->save_out = out_index;
+  T->t1 = t1;
+
+  // ---- local regulariser: integrator at t1 + one differentiable step (neural_ode.jl:75-78)
+  int nf_reg = 0;
+  float reg_val = 0.0f, dt_reg = 0.0f;
+  if (mode != LRNDE_REG_NONE) {
+    T->reg = std::make_unique<Solver>(ctx, DB, DB, 2, 1, 1);
+    Solver& R = *T->reg;
+    if (ctx->nranks > 1) R.h.total_len = F.h.total_len;
+    R.init_ctrl(t1, o->t2, o->t2, o->maxiters, o->pow_mode, o->abstol, o->reltol);
+    R.upload();
+    LinComb u1 = lr_host_interp(F, T->fts, std::min(t1, t_last));
+    DevBuf dd(ctx, sizeof(LinComb) / 4 + 1);
+    LR_CUDA(cudaMemcpyAsync(dd.p, &u1, sizeof(LinComb), cudaMemcpyHostToDevice, st));
+    lincomb_kernel<<<lr_ew_blocks(DB), 256, 0, st>>>((const LinComb*)dd.p, R.tape, DB, nullptr);
+    LR_COUNT(ctx);
+    lr_solver_start(R, eval, 0);
+    for (int j = 0; j < 5; ++j) eval(&R.dev->st[j], nullptr, &R.dev->failed);
+    lincomb_kernel<<<lr_ew_blocks(DB), 256, 0, st>>>(&R.dev->st[5], nullptr, DB, &R.dev->failed);
+    LR_COUNT(ctx);
+    eval(&R.dev->st[6], nullptr, &R.dev->failed);
+    err_norm_kernel<<<LR_ERR_BLOCKS, 256, 0, st>>>(R.dev);
+    LR_COUNT(ctx);
+    if (o->reg_type == LRNDE_REGTYPE_STIFFNESS) {
+      reg_stiff_sums_kernel<<<LR_ERR_BLOCKS, 256, 0, st>>>(R.dev);
+      LR_COUNT(ctx);
+    }
+    reg_value_kernel<<<1, 32, 0, st>>>(R.dev, o->reg_type);
+    LR_COUNT(ctx);
+    LR_CHECK_LAUNCH();
+    R.download();
+    reg_val = R.h.reg_val;
+    dt_reg = R.h.c.dt;
+    nf_reg = 9;  // 6 + integrator.sol.destats.nf (perform_step.jl:31)
+  }
+
+  stats->naccept = naccept;
+  stats->nreject = nreject;
+  stats->retcode = F.h.c.retcode;
+  stats->nfe = 3 + 6 * (naccept + nreject) + nf_reg;
+  stats->reg_val = reg_val;
+  stats->t1_used = t1;
+  stats->dt_reg = dt_reg;
+  stats->nsave_out = nout;
+  stats->gpu_launches = (int)((ctx->launches - launches0) + F.body_nodes * (long)F.h.nlog);
+  if (o->keep_tape) *tape_out = T.release();
+  else if (tape_out) *tape_out = nullptr;
+  LR_API_END
+}
+
+extern "C" int lrnde_tape_free(lrnde_tape* t) {
+  LR_API_BEGIN
+  if (t) {
+    cudaSetDevice(t->ctx->device);
+    cudaStreamSynchronize(t->ctx->stream);
+    delete t;
+  }
+  LR_API_END
+}
+
+extern "C" int lrnde_step_log(const lrnde_tape* t, int which, float* tt, float* dt, float* eest,
+                              uint8_t* accepted, int cap, int* n) {
+  LR_API_BEGIN
+  if (!t || which < 0 || which > 1 || !n) lr_fail(LRNDE_EINVAL, "lrnde_step_log: bad args");
+  int cnt = (int)t->log_t[which].size();
+  *n = cnt;
+  int k = std::min(cnt, cap);
+  for (int i = 0; i < k; ++i) {
+    if (tt) tt[i] = t->log_t[which][i];
+    if (dt) dt[i] = t->log_dt[which][i];
+    if (eest) eest[i] = t->log_eest[which][i];
+    if (accepted) accepted[i] = t->log_acc[which][i];
+  }
+  LR_API_END
+}
+
+// ------------------------------------------------------------------------------------------
+// pullback: continuous adjoint over z = [lambda; mu] + reverse pass of the regulariser step
+// ------------------------------------------------------------------------------------------
+extern "C" int lrnde_ode_backward(lrnde_ctx* ctx, const lrnde_model* m, lrnde_tape* T,
+                                  const float* d_u_save, float d_reg, float* d_ps, float* d_x,
+                                  lrnde_stats* stats) {
+  LR_API_BEGIN
+  if (!ctx || !m || !T || !d_ps || !d_x) lr_fail(LRNDE_EINVAL, "lrnde_ode_backward: bad args");
+  if (T->ctx != ctx || T->model != m) lr_fail(LRNDE_ESTATE, "tape belongs to another ctx/model");
+  LR_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const lrnde_opts& o = T->opts;
+  const int64_t B = T->B;
+  const int D = m->D;
+  const size_t DB = (size_t)D * B;
+  const size_t P = (size_t)m->nparams;
+  const size_t len = DB + P;
+  const int host = o.host_buffers;
+  const long launches0 = ctx->launches;
+  Solver& F = *T->fwd;
+  const int nsteps = (int)T->fts.size() - 1;
+  const float t0 = T->fts.front(), t2 = T->fts.back();
+
+  // cotangent blocks on the device
+  int nout = 0;
+  for (int v : T->save_out) nout = std::max(nout, v + 1);
+  DevBuf dstage(ctx, (host && d_u_save) ? DB * (size_t)std::max(nout, 1) : 1);
+  const float* dU = d_u_save;
+  if (host && d_u_save) {
+    LR_CUDA(cudaMemcpyAsync(dstage.p, d_u_save, sizeof(float) * DB * nout, cudaMemcpyHostToDevice, st));
+    dU = dstage.p;
+  }
+  auto cot_blocks = [&](float tval, std::vector<const float*>& out) {
+    out.clear();
+    if (!dU) return;
+    for (size_t i = 0; i < T->save_ts.size(); ++i)
+      if (T->save_out[i] >= 0 && std::min(T->save_ts[i], t2) == tval)
+        out.push_back(dU + (size_t)T->save_out[i] * DB);
+  };
+
+  MlpEval ev(ctx, m, T->ps, B, o.precision, true);
+  ev.prepare();
+
+  DevBuf out_dx(ctx, host ? DB : 1), out_dps(ctx, host ? P : 1);
+  float* dx_dev = host ? out_dx.p : d_x;
+  float* dps_dev = host ? out_dps.p : d_ps;
+
+  int nbwd_stops = 0;
+  int retcode_bwd = 0, nacc_b = 0, nrej_b = 0;
+  long body_launches = 0;
+  if (nsteps >= 1) {
+    Solver A(ctx, len, DB, 2, 1, o.maxiters + 1);
+    A.h.is_adjoint = 1;
+    A.h.fts = F.ts;
+    A.h.ftape = F.tape;
+    A.h.flen = DB;
+    A.h.fnsteps = nsteps;
+    A.h.ftdir = 1;
+    if (ctx->nranks > 1) {
+      A.h.total_len = (unsigned long long)D * (unsigned long long)ctx->total_batch + P;
+      A.h.reduce_mu = 1;
+    }
+    // interior tstops: saved times strictly inside (t0, t2), descending, unique
+    std::vector<float> stops;
+    for (float s : T->save_ts) {
+      float sc = std::min(s, t2);
+      if (sc > t0 && sc < t2 && std::find(stops.begin(), stops.end(), sc) == stops.end()) stops.push_back(sc);
+    }
+    std::sort(stops.begin(), stops.end(), [](float a, float b) { return a > b; });
+    stops.push_back(t0);
+    A.init_ctrl(t2, t0, stops[0], o.maxiters, o.pow_mode, o.abstol, o.reltol);
+    auto rhs = [&](const LinComb* in, const LinComb* y, const int* done) {
+      ev.vjp(y, in, nullptr, in, -1.0f, nullptr, in, DB, -1.0f, 0.0f, done);
+    };
+    A.body = [&]() { lr_step_body(A, rhs); };
+    A.build_graphs(o.loop_mode);
+    A.upload();
+    // z(t2) = [dL/du(t2); 0]
+    LR_CUDA(cudaMemsetAsync(A.tape, 0, sizeof(float) * len, st));
+    std::vector<const float*> blocks;
+    cot_blocks(t2, blocks);
+    for (auto b : blocks) {
+      axpy_kernel<<<lr_ew_blocks(DB), 256, 0, st>>>(A.tape, b, 1.0f, DB);
+      LR_COUNT(ctx);
+    }
+    lr_solver_start(A, rhs, 1);
+    for (size_t si = 0; si < stops.size(); ++si) {
+      A.run_segment();
+      if (si + 1 < stops.size()) {
+        cot_blocks(stops[si], blocks);
+        for (auto b : blocks) {
+          jump_kernel<<<lr_ew_blocks(DB), 256, 0, st>>>(A.dev, b, DB);
+          LR_COUNT(ctx);
+        }
+        k1_desc_kernel<<<1, 32, 0, st>>>(A.dev);
+        LR_COUNT(ctx);
+        rhs(&A.dev->st[6], &A.dev->yint[6], &A.dev->failed);
+        segment_begin_kernel<<<1, 32, 0, st>>>(A.dev, stops[si + 1], 1);
+        LR_COUNT(ctx);
+        nbwd_stops++;
+      }
+    }
+    LR_CHECK_LAUNCH();
+    A.download();
+    lr_copy_log(A, T, 1);
+    const float* z = A.tape + (size_t)A.h.slot * 7 * len;
+    LR_CUDA(cudaMemcpyAsync(dx_dev, z, sizeof(float) * DB, cudaMemcpyDeviceToDevice, st));
+    LR_CUDA(cudaMemcpyAsync(dps_dev, z + DB, sizeof(float) * P, cudaMemcpyDeviceToDevice, st));
+    cot_blocks(t0, blocks);
+    for (auto b : blocks) {
+      axpy_kernel<<<lr_ew_blocks(DB), 256, 0, st>>>(dx_dev, b, 1.0f, DB);
+      LR_COUNT(ctx);
+    }
+    retcode_bwd = A.h.c.retcode;
+    nacc_b = A.h.c.naccept;
+    nrej_b = A.h.c.nreject;
+    body_launches = A.body_nodes * (long)A.h.nlog;
+    LR_CUDA(cudaStreamSynchronize(st));
+  } else {
+    LR_CUDA(cudaMemsetAsync(dx_dev, 0, sizeof(float) * DB, st));
+    LR_CUDA(cudaMemsetAsync(dps_dev, 0, sizeof(float) * P, st));
+  }
+
+  // ---- reverse pass of the regulariser step: gradient w.r.t. ps only
+  if (T->reg && d_reg != 0.0f) {
+    Solver& R = *T->reg;
+    DevBuf work(ctx, 9 * DB);
+    RegSeedP sp;
+    sp.R = R.dev; sp.reg_type = o.reg_type; sp.d_reg = d_reg;
+    for (int k = 0; k < 6; ++k) sp.dk[k] = work.p + (size_t)k * DB;
+    sp.du = work.p + 6 * DB;
+    sp.dg6 = work.p + 7 * DB;
+    float* abuf = work.p + 8 * DB;
+    reg_seed_kernel<<<lr_ew_blocks(DB), 256, 0, st>>>(sp);
+    LR_COUNT(ctx);
+    std::vector<LinComb> lam(6);
+    for (int k = 0; k < 6; ++k) { memset(&lam[k], 0, sizeof(LinComb)); lam[k].base = sp.dk[k]; }
+    DevBuf dl(ctx, 6 * (sizeof(LinComb) / 4 + 1));
+    LR_CUDA(cudaMemcpyAsync(dl.p, lam.data(), sizeof(LinComb) * 6, cudaMemcpyHostToDevice, st));
+    const LinComb* lamd = (const LinComb*)dl.p;
+    for (int row = 5; row >= 0; --row) {
+      const LinComb* y = (row == 5) ? &R.dev->st[6] : &R.dev->st[row];
+      ev.vjp(y, lamd + row, abuf, nullptr, 1.0f, dps_dev, nullptr, 0, 1.0f, 1.0f, nullptr);
+      if (row == 0) break;  // k2's input depends on k1 only (constant)
+      RegBwdP bp;
+      bp.R = R.dev; bp.row = row; bp.a = abuf; bp.du = sp.du; bp.dg6 = sp.dg6;
+      for (int k = 0; k < 6; ++k) bp.dk[k] = sp.dk[k];
+      reg_bwd_stage_kernel<<<lr_ew_blocks(DB), 256, 0, st>>>(bp);
+      LR_COUNT(ctx);
+    }
+    LR_CHECK_LAUNCH();
+    LR_CUDA(cudaStreamSynchronize(st));
+  }
+  if (host) {
+    LR_CUDA(cudaMemcpyAsync(d_x, dx_dev, sizeof(float) * DB, cudaMemcpyDeviceToHost, st));
+    LR_CUDA(cudaMemcpyAsync(d_ps, dps_dev, sizeof(float) * P, cudaMemcpyDeviceToHost, st));
+  }
+  LR_CUDA(cudaStreamSynchronize(st));
+  if (stats) {
+    stats->nf_bwd = (nsteps >= 1) ? 3 + 6 * (nacc_b + nrej_b) + nbwd_stops : 0;
+    stats->naccept_bwd = nacc_b;
+    stats->nreject_bwd = nrej_b;
+    stats->retcode_bwd = retcode_bwd;
+    stats->gpu_launches = (int)((ctx->launches - launches0) + body_launches);
+  }
+  LR_API_END
+}
+
+#include "lrnde_extra.cuh"

@@ -1,0 +1,93 @@
+// Device-resident descriptors of the solve.  Everything a kernel needs that depends on the
+// step size (stage coefficients dt*a_ij, stage times, which tape slot is current) lives in
+// device memory and is rewritten by the on-device controller, so a captured CUDA graph of one
+// step attempt can be replayed (or looped by a WHILE node) with no host round trip.
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+
+#include "lrnde_controller.h"
+
+#define LR_MAXSRC 7
+#define LR_ERR_BLOCKS 296  // 2 x 148 SMs: partial sums of every norm, summed in fixed order
+#define LR_MAX_RANKS 8
+
+// x[i] = base[i] + scale * sum_{k<n} coef[k] * src[k][i]; the f-evaluation that consumes x
+// runs at time `t` and writes its result to `dst`.
+struct LinComb {
+  const float* base;
+  const float* src[LR_MAXSRC];
+  float* dst;
+  float coef[LR_MAXSRC];
+  float scale;
+  float t;
+  int n;
+  int pad_;
+};
+
+// Mailbox of the data-parallel group (one per rank, peer-mapped on every other rank).
+// slot[seq & 1][r][0..3]: the four partial sums rank r published for sequence number seq,
+// flag[seq & 1][r]: seq + 1 once they are visible.
+struct LrMailbox {
+  double val[2][LR_MAX_RANKS][4];
+  unsigned long long flag[2][LR_MAX_RANKS];
+};
+
+struct SolveDev {
+  LrCtrl c;
+  int done;       // segment finished, solve failed, or tape full: step kernels become no-ops
+  int failed;     // retcode != SUCCESS
+  int tape_full;  // forward only: host must grow the tape and resume
+  int u_nan;
+  int slot;  // current slot: U(slot)=uprev, K(slot,1)=fsalfirst
+  int cap;   // number of slots
+  int ring;  // 1: slot index wraps (adjoint / regulariser integrator), 0: dense tape
+  int nlog, logcap;
+  int nf;  // f evaluations so far
+  int reduce_mu;  // adjoint, multi-rank: the mu block of z is a partial batch sum
+  float abstol, reltol;
+  unsigned long long cond_handle;
+  int use_cond;
+  int is_adjoint;
+  size_t len;      // elements per array of this solve (D*B, or D*B + P for the adjoint)
+  size_t lam_len;  // D*B
+  float* tape;     // slot s at tape + s * 7 * len : [u, k1, ..., k6]; k7 == k1 of slot s+1
+  float* ts;       // accepted times, ts[0] = t0 (dense tape only)
+  float* log_t;
+  float* log_dt;
+  float* log_eest;
+  unsigned char* log_acc;
+  double* partials;  // [4][LR_ERR_BLOCKS]
+  unsigned int* counters;  // [4] order-independent integer flags (non-finite count, f0!=f1 count)
+  LinComb st[7];   // [0..4] inputs of stages 2..6 (dst = K(slot, j)); [5] u_new (dst U(slot+1));
+                   // [6] input of stage 7 (base = U(slot+1), dst = K(slot+1, 1))
+  LinComb err;     // src = k1..k7, coef = btilde, scale = dt, base = uprev, dst = u_new
+  LinComb yint[7]; // adjoint: forward-solution interpolants for the RHS evaluations;
+                   // [0] at the current time (fsalfirst refresh), [j] for st[j-1] ... see api
+  // dense forward solution the adjoint interpolates
+  const float* fts;
+  const float* ftape;
+  size_t flen;
+  int fnsteps;
+  int ftdir;
+  // initdt scratch
+  float d0, d1, dt0;
+  float reg_ss_root;  // regulariser integrator: sqrt(ss/n) kept for the reverse pass
+  float reg_val;
+  float reg_aux[3];
+  // data-parallel group
+  int rank, nranks;
+  unsigned long long seq;  // collective sequence number
+  unsigned long long total_len;  // elements of the GLOBAL array (norm denominators)
+  LrMailbox* mbox[LR_MAX_RANKS];
+};
+
+__host__ __device__ inline float* lr_slot_u(const SolveDev* S, int s) {
+  return S->tape + (size_t)s * 7 * S->len;
+}
+__host__ __device__ inline float* lr_slot_k(const SolveDev* S, int s, int j) {  // j = 1..6
+  return S->tape + ((size_t)s * 7 + j) * S->len;
+}
+__host__ __device__ inline int lr_next_slot(const SolveDev* S, int s) {
+  return S->ring ? ((s + 1) % S->cap) : (s + 1);
+}

@@ -1,0 +1,68 @@
+// Host-side objects behind the C ABI of include/lrnde.h.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/lrnde.h"
+#include "lrnde_device.h"
+
+void lr_set_error(const char* fmt, ...);
+
+#define LR_CUDA(expr)                                                                   \
+  do {                                                                                  \
+    cudaError_t e__ = (expr);                                                           \
+    if (e__ != cudaSuccess) {                                                           \
+      lr_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e__)); \
+      throw LrError(LRNDE_ECUDA);                                                       \
+    }                                                                                   \
+  } while (0)
+
+struct LrError {
+  int code;
+  explicit LrError(int c) : code(c) {}
+};
+
+struct PoolBlock {
+  void* p;
+  size_t bytes;
+  bool used;
+};
+
+struct lrnde_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  uint64_t tape_budget = 0;
+  std::vector<PoolBlock> pool;
+  void* pinned = nullptr;  // small host mirror for state read-back
+  size_t pinned_bytes = 0;
+  long launches = 0;       // kernels launched directly (outside capture)
+  long captured = 0;       // kernel nodes recorded while capturing
+  bool capturing = false;
+  // data-parallel group
+  int rank = 0, nranks = 1;
+  int64_t total_batch = 0;
+  LrMailbox* mailbox = nullptr;               // this rank's mailbox (device memory)
+  LrMailbox* peer_mbox[LR_MAX_RANKS] = {nullptr};
+  unsigned long long seq = 0;                 // next collective sequence number
+
+  void* alloc(size_t bytes);
+  void release(void* p);
+  void release_all_unused();
+};
+
+struct LayerInfo {
+  int in, out, act;
+  int64_t w_off, b_off;  // offsets into the flat parameter vector
+};
+
+struct lrnde_model {
+  lrnde_ctx* ctx;
+  std::vector<LayerInfo> layers;
+  int td;
+  int input_act;  // LRNDE_ACT_NONE (-1) when absent
+  int64_t nparams;
+  int D;
+};

@@ -1,0 +1,435 @@
+"""Host-side mirror of the reference's Lux layer interface for the hot path.
+
+    layer(x, ps, st) -> (sol, st')          src/layers/neural_ode.jl:62
+
+with ``st`` carrying ``nfe`` / ``reg_val`` / ``rng`` / ``training`` exactly as the reference
+does (neural_ode.jl:27-31, :83).  All arithmetic happens in libLRNDE.so on the GPU; this file
+only resolves keyword arguments, samples the host-side scalar ``t1`` (neural_ode.jl:71) and
+passes pointers.  Inputs may be numpy arrays (host buffers, staged inside the library) or torch
+CUDA tensors (device pointers, zero-copy).
+"""
+from __future__ import annotations
+
+import copy
+import ctypes as C
+import math
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import LayerDesc, Opts, Stats, check, lib
+
+try:  # torch is plumbing only (device memory / streams)
+    import torch
+except Exception:  # pragma: no cover
+    torch = None
+
+
+# ------------------------------------------------------------------ dynamics descriptors
+@dataclass(frozen=True)
+class Dense:
+    """Lux ``Dense(in => out, act)``."""
+    in_dims: int
+    out_dims: int
+    activation: str = "identity"
+
+
+class Chain:
+    """Lux ``Chain(Dense...)`` (parameters named layer_1..layer_N, flattened in that order)."""
+
+    def __init__(self, *layers: Dense, input_activation: Optional[str] = None):
+        self.layers: List[Dense] = list(layers)
+        self.input_activation = input_activation  # Base.Fix1(broadcast, act) (construct.jl:235)
+        self.time_dependent = False
+
+
+class TDChain(Chain):
+    """``TDChain(chain)``: the scalar t is appended as an extra input row before EVERY layer
+    (src/layers/common.jl:19-33)."""
+
+    def __init__(self, chain: Chain):
+        super().__init__(*chain.layers, input_activation=chain.input_activation)
+        self.time_dependent = True
+
+
+def nparams(model: Chain) -> int:
+    td = 1 if model.time_dependent else 0
+    return sum(L.out_dims * (L.in_dims + td) + L.out_dims for L in model.layers)
+
+
+def glorot_uniform(model: Chain, rng: np.random.Generator) -> np.ndarray:
+    """Lux default init (Glorot-uniform weights, zero bias), flat ComponentArray order."""
+    td = 1 if model.time_dependent else 0
+    out = []
+    for L in model.layers:
+        fan_in, fan_out = L.in_dims + td, L.out_dims
+        a = math.sqrt(6.0 / (fan_in + fan_out))
+        W = rng.uniform(-a, a, size=(fan_out, fan_in)).astype(np.float32)
+        out.append(W.ravel(order="F"))
+        out.append(np.zeros(fan_out, np.float32))
+    return np.concatenate(out)
+
+
+# ------------------------------------------------------------------ context
+class Context:
+    """One device + one stream (include/lrnde.h: a ctx is not thread-safe)."""
+
+    def __init__(self, device: int = 0, stream: Optional[int] = None):
+        self._h = C.c_void_p()
+        check(lib().lrnde_ctx_create(C.byref(self._h), int(device), C.c_void_p(stream or 0)))
+        self.device = device
+        self._models = {}
+
+    def sync(self):
+        check(lib().lrnde_ctx_sync(self._h))
+
+    def set_tape_budget(self, nbytes: int):
+        check(lib().lrnde_ctx_set_tape_budget(self._h, int(nbytes)))
+
+    def close(self):
+        if self._h:
+            for m in self._models.values():
+                lib().lrnde_model_destroy(m)
+            self._models.clear()
+            lib().lrnde_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def model_handle(self, model: Chain):
+        key = id(model)
+        if key not in self._models:
+            arr = (LayerDesc * len(model.layers))()
+            for i, L in enumerate(model.layers):
+                arr[i] = LayerDesc(L.in_dims, L.out_dims, _lib.ACT[L.activation])
+            h = C.c_void_p()
+            check(lib().lrnde_model_create(self._h, arr, len(model.layers),
+                                           1 if model.time_dependent else 0,
+                                           _lib.ACT[model.input_activation], C.byref(h)))
+            self._models[key] = h
+        return self._models[key]
+
+    # ---- data-parallel group (one process per GPU): mailboxes exchanged through CUDA IPC
+    def setup_group(self, rank: int, nranks: int, total_batch: int, allgather_bytes):
+        """``allgather_bytes(b: bytes) -> list[bytes]`` gathers one blob per rank (e.g. via
+        torch.distributed.all_gather_object)."""
+        if nranks == 1:
+            check(lib().lrnde_ctx_set_dist(self._h, 0, 1, None, int(total_batch)))
+            return
+        ptr = C.c_void_p()
+        nb = C.c_uint64()
+        check(lib().lrnde_ctx_mailbox(self._h, C.byref(ptr), C.byref(nb)))
+        handle = (C.c_ubyte * 64)()
+        check(lib().lrnde_ipc_export(self._h, ptr, handle))
+        blobs = allgather_bytes(bytes(handle))
+        boxes = (C.c_void_p * nranks)()
+        for r, blob in enumerate(blobs):
+            if r == rank:
+                boxes[r] = ptr
+            else:
+                buf = (C.c_ubyte * 64).from_buffer_copy(blob)
+                p = C.c_void_p()
+                check(lib().lrnde_ipc_open(self._h, buf, C.byref(p)))
+                boxes[r] = p
+        check(lib().lrnde_ctx_set_dist(self._h, rank, nranks, boxes, int(total_batch)))
+
+
+_default_ctx = {}
+
+
+def default_context(device: int = 0) -> Context:
+    if device not in _default_ctx:
+        stream = None
+        if torch is not None and torch.cuda.is_available():
+            stream = torch.cuda.current_stream(device).cuda_stream
+        _default_ctx[device] = Context(device, stream)
+    return _default_ctx[device]
+
+
+# ------------------------------------------------------------------ array plumbing
+def _is_torch(a):
+    return torch is not None and isinstance(a, torch.Tensor)
+
+
+def _ptr(a):
+    if a is None:
+        return C.c_void_p(0)
+    if _is_torch(a):
+        return C.c_void_p(a.data_ptr())
+    return C.c_void_p(a.ctypes.data)
+
+
+def _as_input(a, like_torch: bool, device):
+    """Column-major (features, batch) -> the flat buffer the C ABI takes."""
+    if _is_torch(a):
+        if not a.is_cuda:
+            raise ValueError("torch inputs must be CUDA tensors (or pass numpy arrays)")
+        # (D, B) logical, stored batch-major == column-major flat buffer
+        return a.detach().to(torch.float32).t().contiguous()
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float32).T)
+
+
+class DESolution:
+    """What the functor returns as ``sol``: ``sol.u`` (list of (D,B) arrays at ``sol.t``)."""
+
+    def __init__(self, t, u, tape, layer, ctx, stats, host):
+        self.t, self.u = t, u
+        self._tape, self._layer, self._ctx, self.stats, self._host = tape, layer, ctx, stats, host
+        self.retcode = _lib.RETCODES.get(stats.retcode, "?")
+
+    def step_log(self, which: int = 0):
+        """(t, dt, EEst, accepted) of every attempted step of the forward (0) / adjoint (1)."""
+        if not self._tape:
+            raise _lib.LrndeError(-4, "no tape (forward ran with keep_tape=False)")
+        n = C.c_int32()
+        check(lib().lrnde_step_log(self._tape, which, None, None, None, None, 0, C.byref(n)))
+        k = n.value
+        t = np.zeros(k, np.float32); dt = np.zeros(k, np.float32)
+        e = np.zeros(k, np.float32); a = np.zeros(k, np.uint8)
+        check(lib().lrnde_step_log(self._tape, which, _ptr(t), _ptr(dt), _ptr(e), _ptr(a), k,
+                                   C.byref(n)))
+        return t, dt, e, a.astype(bool)
+
+    def free(self):
+        if self._tape:
+            lib().lrnde_tape_free(self._tape)
+            self._tape = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def diffeqsol_to_array(sol):                      # src/utils.jl:37
+    return sol.u[-1]
+
+
+def diffeqsol_to_timeseries(sol):                 # src/utils.jl:43-45
+    if _is_torch(sol.u[0]):
+        return torch.stack(sol.u, dim=1)
+    return np.stack(sol.u, axis=1)
+
+
+# ------------------------------------------------------------------ the layer
+class NeuralODE:
+    """``NeuralODE(model; solver=Tsit5(), sensealg=InterpolatingAdjoint(autojacvec=ZygoteVJP()),
+    tspan=(0f0,1f0), regularize=true, maxiters=1000, regularize_type=:error_estimate,
+    kwargs...)`` (src/layers/neural_ode.jl:10-22).  kwargs: abstol, reltol, saveat, save_start
+    (splatted into solve/init, :51/:36).  Extra, GPU-side only: ``precision`` ("auto", "fp32",
+    "tf32x3", "tf32"), ``pow_mode``, ``loop_mode``."""
+
+    VALID_MODES = ("none", "unbiased", "biased")
+    VALID_TYPES = ("error_estimate", "stiffness_estimate")
+
+    def __init__(self, model: Chain, *, solver="Tsit5", sensealg="InterpolatingAdjoint",
+                 tspan=(0.0, 1.0), regularize=True, maxiters: int = 1000,
+                 regularize_type: str = "error_estimate", precision: str = "auto",
+                 pow_mode: str = "fastpow_2023", loop_mode: int = 0, ctx: Optional[Context] = None,
+                 **kwargs):
+        if isinstance(regularize, bool):
+            regularize = "unbiased" if regularize else "none"          # :14-16
+        if regularize not in self.VALID_MODES:                          # utils.jl:53-58
+            raise ValueError(f"regularize must be one of {self.VALID_MODES}")
+        if regularize_type not in self.VALID_TYPES:
+            raise ValueError(f"regularize must be one of {self.VALID_TYPES}")
+        if solver != "Tsit5":
+            raise ValueError("the B200 path implements solver=Tsit5() (the reference default)")
+        if sensealg != "InterpolatingAdjoint":
+            raise ValueError("the B200 path implements sensealg=InterpolatingAdjoint(ZygoteVJP)")
+        self.model, self.tspan, self.regularize = model, tuple(tspan), regularize
+        self.regularize_type, self.maxiters = regularize_type, int(maxiters)
+        self.abstol = float(kwargs.pop("abstol", 1e-6))     # OrdinaryDiffEq defaults
+        self.reltol = float(kwargs.pop("reltol", 1e-3))
+        self.saveat = kwargs.pop("saveat", None)
+        self.save_start = kwargs.pop("save_start", None)
+        if kwargs:
+            raise TypeError(f"unsupported solve kwargs {sorted(kwargs)}")
+        self.precision, self.pow_mode, self.loop_mode = precision, pow_mode, loop_mode
+        self._ctx = ctx
+
+    # Lux.initialparameters / initialstates (neural_ode.jl:27-31)
+    def initialparameters(self, rng: np.random.Generator) -> np.ndarray:
+        return glorot_uniform(self.model, rng)
+
+    def initialstates(self, rng: np.random.Generator):
+        rng.standard_normal()
+        return dict(model={}, nfe=-1, reg_val=np.float32(0), rng=copy.deepcopy(rng), training=True)
+
+    @property
+    def ctx(self) -> Context:
+        if self._ctx is None:
+            self._ctx = default_context(0)
+        return self._ctx
+
+    def _opts(self, mode, t1, u01, keep_tape, host):
+        o = Opts()
+        o.t0, o.t2 = self.tspan
+        o.abstol, o.reltol, o.maxiters = self.abstol, self.reltol, self.maxiters
+        o.reg_mode = _lib.REG[mode]
+        o.reg_type = _lib.REGTYPE[self.regularize_type]
+        o.t1, o.u01 = float(t1), float(u01)
+        keep = None
+        if self.saveat is not None:
+            keep = np.asarray(self.saveat, dtype=np.float32)
+            o.saveat = keep.ctypes.data_as(C.POINTER(C.c_float))
+            o.nsave = keep.size
+        elif mode == "biased":
+            o.nsave = -1
+        else:
+            o.nsave = 0
+        # OrdinaryDiffEq: save_start defaults to true only for the save-everything case
+        if self.save_start is None:
+            o.save_start = 1 if (self.saveat is None and mode == "biased") else 0
+        else:
+            o.save_start = 1 if self.save_start else 0
+        o.precision = _lib.PREC[self.precision]
+        o.pow_mode = _lib.POW[self.pow_mode]
+        o.host_buffers = 1 if host else 0
+        o.keep_tape = 1 if keep_tape else 0
+        o.loop_mode = int(self.loop_mode)
+        return o, keep
+
+    def __call__(self, x, ps, st, keep_tape: Optional[bool] = None):
+        """(n::NeuralODE)(x, ps, st) -> (sol, st')."""
+        T = np.float32
+        t0, t2 = T(self.tspan[0]), T(self.tspan[1])
+        training = bool(st["training"])
+        mode = self.regularize if training else "none"                  # :66, :86
+        rng = st["rng"]
+        t1, u01 = t0, 0.0
+        if mode != "none":
+            rng = copy.deepcopy(st["rng"])                              # Lux.replicate (:69)
+            if mode == "unbiased":
+                t1 = T(rng.random(dtype=np.float32)) * (t2 - t0) + t0   # :71
+            else:
+                u01 = float(rng.random(dtype=np.float32))               # :92 (index sampled in C)
+        host = not _is_torch(x)
+        if keep_tape is None:
+            keep_tape = training
+        o, _keep = self._opts(mode, t1, u01, keep_tape, host)
+        xb = _as_input(x, not host, None)
+        B, D = xb.shape
+        if D != self.model.layers[0].in_dims:
+            raise ValueError(f"x has {D} features, the dynamics expect {self.model.layers[0].in_dims}")
+        psb = ps.detach().to(torch.float32).contiguous() if _is_torch(ps) else \
+            np.ascontiguousarray(np.asarray(ps, dtype=np.float32))
+        if (not host) != _is_torch(psb):
+            raise ValueError("x and ps must both be numpy arrays or both be CUDA tensors")
+        n_ps = psb.size if host else psb.numel()
+        if n_ps != nparams(self.model):
+            raise ValueError("ps has the wrong length for this model")
+        if o.nsave > 0:
+            cap = o.nsave + 1
+        elif o.nsave == 0:
+            cap = 2
+        else:
+            cap = self.maxiters + 2
+        if host:
+            usave = np.empty((cap, B, D), np.float32)
+        else:
+            usave = torch.empty((cap, B, D), dtype=torch.float32, device=xb.device)
+        times = np.zeros(cap, np.float32)
+        stats = Stats()
+        tape = C.c_void_p()
+        ctx = self.ctx
+        mh = ctx.model_handle(self.model)
+        check(lib().lrnde_ode_forward(ctx._h, mh, C.byref(o), _ptr(psb), _ptr(xb), B, _ptr(usave),
+                                      cap, _ptr(times), C.byref(stats), C.byref(tape)))
+        n = stats.nsave_out
+        us = [usave[i].T for i in range(n)]        # back to (D, B) views
+        sol = DESolution([T(t) for t in times[:n]], us, tape if keep_tape else None, self, ctx,
+                         stats, host)
+        sol._shape = (B, D)
+        st2 = dict(model=st["model"], nfe=int(stats.nfe), reg_val=T(stats.reg_val), rng=rng,
+                   training=st["training"])                             # :79-83
+        return sol, st2
+
+    def backward(self, sol: DESolution, d_us: Sequence, d_reg: float = 0.0):
+        """Pullback of the functor: cotangents on each ``sol.u[i]`` (None = zero) and on
+        ``st'.reg_val``.  Returns (d_x, d_ps); d reg / d x == 0 (test/runtests.jl:129)."""
+        if not sol._tape:
+            raise _lib.LrndeError(-4, "no tape: call the layer with training=True / keep_tape=True")
+        B, D = sol._shape
+        n = len(sol.u)
+        if len(d_us) != n:
+            raise ValueError(f"expected {n} cotangent blocks, got {len(d_us)}")
+        host = sol._host
+        P = nparams(self.model)
+        if all(d is None for d in d_us):
+            dU = None
+        elif host:
+            dU = np.zeros((n, B, D), np.float32)
+            for i, d in enumerate(d_us):
+                if d is not None:
+                    dU[i] = np.asarray(d, np.float32).T
+        else:
+            dev = sol.u[0].device
+            dU = torch.zeros((n, B, D), dtype=torch.float32, device=dev)
+            for i, d in enumerate(d_us):
+                if d is not None:
+                    dU[i] = d.to(torch.float32).t()
+        if host:
+            d_x = np.empty((B, D), np.float32)
+            d_ps = np.empty(P, np.float32)
+        else:
+            dev = sol.u[0].device
+            d_x = torch.empty((B, D), dtype=torch.float32, device=dev)
+            d_ps = torch.empty(P, dtype=torch.float32, device=dev)
+        stats = Stats()
+        ctx = sol._ctx
+        check(lib().lrnde_ode_backward(ctx._h, ctx.model_handle(self.model), sol._tape, _ptr(dU),
+                                       float(d_reg), _ptr(d_ps), _ptr(d_x), C.byref(stats)))
+        sol.bwd_stats = stats
+        return d_x.T, d_ps
+
+    def dynamics(self, u, ps, t: float):
+        """One evaluation of the ``dudt`` closure (neural_ode.jl:45-48) on the GPU."""
+        host = not _is_torch(u)
+        ub = _as_input(u, not host, None)
+        B, D = ub.shape
+        psb = ps.contiguous() if _is_torch(ps) else np.ascontiguousarray(np.asarray(ps, np.float32))
+        out = np.empty((B, D), np.float32) if host else torch.empty_like(ub)
+        o, _ = self._opts("none", 0.0, 0.0, False, host)
+        ctx = self.ctx
+        check(lib().lrnde_dynamics_eval(ctx._h, ctx.model_handle(self.model), C.byref(o), _ptr(psb),
+                                        _ptr(ub), float(t), B, _ptr(out)))
+        return out.T
+
+
+# ------------------------------------------------------------------ torch autograd bridge
+if torch is not None:
+
+    class _NeuralODEFn(torch.autograd.Function):
+        """Stands in for the ChainRules rrule a Julia wrapper would define: differentiable
+        outputs are the stacked saved states and ``reg_val``."""
+
+        @staticmethod
+        def forward(ctx, x, ps, layer, st, box):
+            sol, st2 = layer(x, ps, st, keep_tape=True)
+            box["sol"], box["st"] = sol, st2
+            ctx.layer, ctx.sol = layer, sol
+            u = torch.stack(sol.u, dim=0)
+            reg = torch.tensor(float(st2["reg_val"]), device=x.device, dtype=torch.float32)
+            return u, reg
+
+        @staticmethod
+        def backward(ctx, d_u, d_reg):
+            sol = ctx.sol
+            d_us = [d_u[i] for i in range(d_u.shape[0])] if d_u is not None else [None] * len(sol.u)
+            d_x, d_ps = ctx.layer.backward(sol, d_us, float(d_reg) if d_reg is not None else 0.0)
+            sol.free()
+            return d_x, d_ps, None, None, None
+
+    def neural_ode_apply(layer: NeuralODE, x, ps, st):
+        """Differentiable call: returns (u_stack [nsave, D, B], reg_val, st')."""
+        box = {}
+        u, reg = _NeuralODEFn.apply(x, ps, layer, st, box)
+        return u, reg, box["st"]
