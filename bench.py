@@ -1,0 +1,372 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: one MNIST neural-ODE TRAINING step (forward adaptive Tsit5 solve
+with the randomly-sampled local regulariser, classifier head + cross-entropy, continuous
+adjoint + regulariser pullback, gradient all-reduce, Adam) on synthetic data.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo (libLRNDE.so)
+    python bench.py --impl reference --gpus N --steps K ...  # CPU restatement of the reference
+
+Metric (BASELINE.json): MNIST neural-ODE train samples/s (+ NFE/s).  Workload: the
+"mnist_ode batch-scaling sweep" config at 8192 samples per GPU (weak scaling: 8192 x N, i.e.
+8192 ... 65536 over 1 ... 8 GPUs), reference tolerances abstol = reltol = 1.4e-8, :unbiased
+:error_estimate regulariser, w_reg = 2.5 (experiments/mnist_ode/mlp.yml).
+
+The Julia reference cannot run here (no julia binary in the image), so `--impl reference` and
+the `cpu_baseline` leg time the numpy oracle (oracle/, "port") on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+D, H, NCLS = 784, 100, 10
+TOL = 1.4e-8
+W_REG = 2.5
+LR = 1e-3
+
+
+def flops_per_feval(B):
+    return 2.0 * B * (H * (D + 1) + D * (H + 1))
+
+
+def iteration_flops(B, nfe_fwd, nf_bwd):
+    """forward f-evals cost F_f, adjoint RHS evals ~3 F_f (recompute layer 1, two data GEMMs,
+    two weight-gradient GEMMs; the W2*h product is skipped), regulariser pullback 6 x 3 F_f."""
+    return flops_per_feval(B) * (nfe_fwd + 3.0 * nf_bwd + 18.0)
+
+
+# ---------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.path = index, None, f"/tmp/lrnde_clocks_{os.getpid()}.csv"
+
+    def start(self):
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=self.f,
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        for line in open(self.path):
+            p = [s.strip() for s in line.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1])); mx.append(float(p[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                   "samples": len(sm)}
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+        return out
+
+
+# ---------------------------------------------------------------------------------- reference arm
+def oracle_iteration(B, seed=0, reps=1):
+    """One training iteration (fwd + head + adjoint + reg pullback) of the CPU restatement on a
+    bounded sample of the workload.  Returns (seconds per iteration, nfe, nf_bwd)."""
+    import oracle as orc
+    om = orc.mnist_ode_model(D, H)
+    rng = np.random.default_rng(seed)
+    ps = orc.glorot_uniform_params(om, rng)
+    Wc = (rng.uniform(-1, 1, (NCLS, D)) * np.sqrt(6.0 / (D + NCLS))).astype(np.float32)
+    x = rng.random((D, B), dtype=np.float32)
+    y = rng.integers(0, NCLS, B)
+    node = orc.NeuralODE(om, regularize="unbiased", save_start=False, abstol=TOL, reltol=TOL, maxiters=10000)
+    st = node.initialstates(np.random.default_rng(seed + 1))
+    best, nfe, nfb = None, 0, 0
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        sol, st2, aux = node.forward(x, ps, st)
+        u = sol.u[-1]
+        z = Wc @ u
+        z = z - z.max(0)
+        sm = np.exp(z) / np.exp(z).sum(0)
+        sm[y, np.arange(B)] -= 1
+        d_u = (Wc.T @ (sm / B)).astype(np.float32)
+        d_x, d_ps = node.backward(aux, [None, d_u], W_REG, ps)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+        nfe, nfb = st2["nfe"], aux["bsol"].nf
+    return best, nfe, nfb
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    Bs = args.ref_batch
+    for _ in range(max(args.warmup, 0) and 1):
+        oracle_iteration(Bs)
+    times = []
+    nfe = nfb = 0
+    for _ in range(max(1, args.steps)):
+        dt, nfe, nfb = oracle_iteration(Bs)
+        times.append(dt)
+    ms = 1e3 * float(np.mean(times))
+    val = Bs / (ms / 1e3)
+    cores = os.cpu_count()
+    sample = (f"{Bs} of the {args.batch}-sample per-GPU batch, same model/tolerances/regulariser; numpy "
+              f"float32 oracle (CPU restatement of the reference, not Julia), BLAS threads = all {cores} cores")
+    line = {
+        "impl": "reference", "metric": "mnist_ode_train_samples_per_s", "value": val, "unit": "samples/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "nfe_per_s": nfe / (ms / 1e3),
+        "config": workload_config(args, args.gpus),
+        "cpu_baseline": {"value": val, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args, n):
+    return {"workload": "mnist_ode batch-scaling sweep (BASELINE configs[4]); TD-MLP 785=>100 tanh, 101=>784; "
+                        "Tsit5 + :unbiased :error_estimate local reg; fwd + head + adjoint + Adam",
+            "batch_per_gpu": args.batch, "global_batch": args.batch * n, "abstol": TOL, "reltol": TOL,
+            "w_reg": W_REG, "precision": args.precision,
+            "l2": "per-step working set (tape slot 7 x 25.7 MB at 8192/GPU) exceeds L2 (126 MB); no flush needed"}
+
+
+# ---------------------------------------------------------------------------------- this repo
+def run_native(args):
+    import torch
+    import __graft_entry__ as entry
+    entry.build()
+    pkg = entry.load_package()
+    lib = pkg.lib()
+    chk = pkg._lib.check
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    B = args.batch
+    ctx = pkg.Context(local, torch.cuda.current_stream(dev).cuda_stream)
+    if world > 1:
+        def gather(blob):
+            out = [None] * world
+            dist.all_gather_object(out, blob)
+            return out
+        ctx.setup_group(rank, world, B * world, gather)
+    chain = pkg.TDChain(pkg.Chain(pkg.Dense(D, H, "tanh"), pkg.Dense(H, D)))
+    node = pkg.NeuralODE(chain, regularize="unbiased", save_start=False, abstol=TOL, reltol=TOL,
+                         maxiters=10000, precision=args.precision, loop_mode=args.loop_mode, ctx=ctx)
+    P = pkg.nparams(chain)
+    rng = np.random.default_rng(0)                       # same weights on every rank
+    ps_h = node.initialparameters(rng)
+    Wc_h = np.concatenate([((rng.uniform(-1, 1, (NCLS, D)) * np.sqrt(6.0 / (D + NCLS))).astype(np.float32)).ravel(order="F"),
+                           np.zeros(NCLS, np.float32)])
+    drng = np.random.default_rng(1000 + rank)             # different data per rank
+    xb_h = torch.empty((B, D), dtype=torch.float32).pin_memory()
+    xb_h.numpy()[...] = drng.random((B, D), dtype=np.float32)
+    y_h = drng.integers(0, NCLS, B).astype(np.int32)
+    st0 = node.initialstates(np.random.default_rng(7))    # same t1 stream on every rank
+
+    ps = torch.from_numpy(ps_h).to(dev)
+    Wc = torch.from_numpy(Wc_h).to(dev)
+    xb = xb_h.to(dev)
+    y = torch.from_numpy(y_h).to(dev)
+    opt = {k: torch.zeros_like(v) for k, v in (("m_ps", ps), ("v_ps", ps), ("m_wc", Wc), ("v_wc", Wc))}
+    d_u = torch.empty((B, D), dtype=torch.float32, device=dev)
+    d_Wc = torch.empty_like(Wc)
+    loss = C.c_float()
+    launches = {"n": 0}
+    info = {}
+
+    def step(i, st, resident=True):
+        """One training iteration.  resident=True: device pointers; False: host buffers through
+        the C ABI (the e2e leg)."""
+        if resident:
+            sol, st2 = node(xb.t(), ps, st)
+            u_last = sol.u[-1].t()                           # (B, D) contiguous block of u_save
+            chk(lib.lrnde_head_ce(ctx._h, Wc.data_ptr(), u_last.data_ptr(), y.data_ptr(), B, D, NCLS, 0,
+                                  C.byref(loss), d_u.data_ptr(), d_Wc.data_ptr()))
+            d_x, d_ps = node.backward(sol, [None, d_u.t()], W_REG)
+            launches["n"] += sol.stats.gpu_launches + sol.bwd_stats.gpu_launches + 6
+            gp, gw = d_ps, d_Wc
+        else:
+            x_np = xb_h.numpy()
+            sol, st2 = node(x_np.T, ps_host["ps"], st)
+            u_last = np.ascontiguousarray(sol.u[-1].T)
+            du_np = np.empty((B, D), np.float32)
+            dwc_np = np.empty(NCLS * D + NCLS, np.float32)
+            chk(lib.lrnde_head_ce(ctx._h, ps_host["Wc"].ctypes.data, u_last.ctypes.data, y_h.ctypes.data, B, D,
+                                  NCLS, 1, C.byref(loss), du_np.ctypes.data, dwc_np.ctypes.data))
+            d_x, d_ps = node.backward(sol, [None, du_np.T], W_REG)
+            gp = torch.from_numpy(d_ps).to(dev, non_blocking=False)
+            gw = torch.from_numpy(dwc_np).to(dev)
+        if world > 1:
+            dist.all_reduce(gp)
+            dist.all_reduce(gw)
+            gp /= world
+            gw /= world
+        chk(lib.lrnde_adam_step(ctx._h, ps.data_ptr(), gp.data_ptr(), opt["m_ps"].data_ptr(),
+                                opt["v_ps"].data_ptr(), P, LR, 0.9, 0.999, 1e-8, i + 1))
+        chk(lib.lrnde_adam_step(ctx._h, Wc.data_ptr(), gw.data_ptr(), opt["m_wc"].data_ptr(),
+                                opt["v_wc"].data_ptr(), Wc.numel(), LR, 0.9, 0.999, 1e-8, i + 1))
+        if not resident:
+            ps_host["ps"] = ps.cpu().numpy()
+            ps_host["Wc"] = Wc.cpu().numpy()
+        info.update(nfe=st2["nfe"], nf_bwd=sol.bwd_stats.nf_bwd, reg=float(st2["reg_val"]),
+                    naccept=sol.stats.naccept, nreject=sol.stats.nreject,
+                    nacc_b=sol.bwd_stats.naccept_bwd, nrej_b=sol.bwd_stats.nreject_bwd,
+                    loss=float(loss.value) + W_REG * float(st2["reg_val"]), retcode=sol.retcode)
+        sol.free()
+        return st2
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    def timed(nsteps, st, resident, i0):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sync_all()
+        e0.record()
+        nfe_sum = 0
+        for i in range(nsteps):
+            st = step(i0 + i, st, resident)
+            nfe_sum += info["nfe"]
+        e1.record()
+        sync_all()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, st, nfe_sum
+
+    st = st0
+    for i in range(args.warmup):
+        st = step(i, st, True)
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    launches["n"] = 0
+    ms_total, st, nfe_sum = timed(args.steps, st, True, args.warmup)
+    n_launch = launches["n"]
+    clk = clocks.stop() if rank == 0 else None
+    ms = ms_total / args.steps
+    value = B * world / (ms / 1e3)
+    fwd_info = dict(info)
+
+    # ---- e2e leg: host buffers through the C ABI (H2D / D2H inside the timed region)
+    ps_host = {"ps": ps.cpu().numpy(), "Wc": Wc.cpu().numpy()}
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    st_e = step(0, st, False)                               # warm
+    ms_e, _, _ = timed(e2e_steps, st_e, False, 1)
+    ms_e /= e2e_steps
+    h2d = 4 * (B * D + P + B * D + (NCLS * D + NCLS) + B + 2 * B * D + P + (NCLS * D + NCLS))
+    d2h = 4 * (2 * B * D + B * D + (NCLS * D + NCLS) + 1 + B * D + P + P + (NCLS * D + NCLS))
+    e2e = {"value": B * world / (ms_e / 1e3), "unit": "samples/s", "h2d_bytes_per_step": h2d,
+           "d2h_bytes_per_step": d2h, "ms_per_step": ms_e, "steps": e2e_steps}
+
+    # ---- roofline of the dominant unit: one stage f-evaluation (both layer GEMMs + epilogues)
+    du = torch.empty((B, D), dtype=torch.float32, device=dev)
+    o, _k = node._opts("none", 0.0, 0.0, False, False)
+    msf, lp = C.c_float(), C.c_int32()
+    chk(lib.lrnde_profile_feval(ctx._h, ctx.model_handle(chain), C.byref(o), ps.data_ptr(), xb.data_ptr(), B,
+                                50, du.data_ptr(), C.byref(msf), C.byref(lp)))
+    peaks = {}
+    pk_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk_path):
+        peaks = json.load(open(pk_path))
+    bf16 = peaks.get("bf16_tflops", 1590.0)
+    tf32_peak = bf16 / 2.0
+    ach = flops_per_feval(B) / (msf.value * 1e-3) / 1e12
+    roof = {"bound": "tensor", "kernel": "stage f-evaluation (layer-1 + layer-2 GEMMs with fused prologue/epilogue)",
+            "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s", "frac": ach / tf32_peak, "traffic": None,
+            "peak_source": ("measured bf16 burst / 2 (TF32 dense = half the bf16 rate)" if peaks else
+                            "fallback 1590 bf16 / 2"),
+            "ms_per_feval": msf.value, "launches_per_feval": lp.value,
+            "step_flops_frac": iteration_flops(B, fwd_info["nfe"], fwd_info["nf_bwd"]) / (ms * 1e-3) / 1e12 / tf32_peak}
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            Bs = args.ref_batch
+            dt, nfe_c, nfb_c = oracle_iteration(Bs)
+            cpu = {"value": Bs / dt, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
+                   "sample": f"1 iteration on {Bs} of the {B} samples ({dt:.1f} s), numpy float32 oracle, all host cores via BLAS",
+                   "nfe": int(nfe_c)}
+        line = {
+            "metric": "mnist_ode_train_samples_per_s", "value": value, "unit": "samples/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "tf32x3",
+            "data": "synthetic", "config": workload_config(args, world),
+            "nfe_per_s": nfe_sum / (ms_total / 1e3) * world, "nfe_per_step": fwd_info["nfe"],
+            "nf_bwd_per_step": fwd_info["nf_bwd"], "steps_fwd": [fwd_info["naccept"], fwd_info["nreject"]],
+            "steps_bwd": [fwd_info["nacc_b"], fwd_info["nrej_b"]], "loss": fwd_info["loss"],
+            "retcode": fwd_info["retcode"],
+            "e2e": e2e, "gpu_launches": int(n_launch), "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--batch", type=int, default=8192, help="samples per GPU")
+    ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "tf32x3", "tf32"])
+    ap.add_argument("--loop-mode", type=int, default=0)
+    ap.add_argument("--ref-batch", type=int, default=512, help="bounded sample for the CPU reference")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -90,8 +90,8 @@ class Context:
 
     def close(self):
         if self._h:
-            for m in self._models.values():
-                lib().lrnde_model_destroy(m)
+            for _m, h in self._models.values():
+                lib().lrnde_model_destroy(h)
             self._models.clear()
             lib().lrnde_ctx_destroy(self._h)
             self._h = C.c_void_p()
@@ -104,6 +104,8 @@ class Context:
 
     def model_handle(self, model: Chain):
         key = id(model)
+        if key in self._models and self._models[key][0] is not model:
+            lib().lrnde_model_destroy(self._models.pop(key)[1])    # id() reuse of a dead object
         if key not in self._models:
             arr = (LayerDesc * len(model.layers))()
             for i, L in enumerate(model.layers):
@@ -112,8 +114,8 @@ class Context:
             check(lib().lrnde_model_create(self._h, arr, len(model.layers),
                                            1 if model.time_dependent else 0,
                                            _lib.ACT[model.input_activation], C.byref(h)))
-            self._models[key] = h
-        return self._models[key]
+            self._models[key] = (model, h)       # the strong reference keeps id(model) unique
+        return self._models[key][1]
 
     # ---- data-parallel group (one process per GPU): mailboxes exchanged through CUDA IPC
     def setup_group(self, rank: int, nranks: int, total_batch: int, allgather_bytes):

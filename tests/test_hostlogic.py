@@ -208,7 +208,8 @@ def test_layer_constructor_validation_mirrors_reference():
 
 
 @pytest.mark.parametrize("name", ["tiny_td_gelu", "tiny_plain_biased", "mid_tanh_stiff",
-                                  "latent_saveat", "eval_mode"])
+                                  "latent_saveat", "eval_mode", "mid_x3_err", "mid_x3_stiff",
+                                  "gelu3_x3_biased"])
 def test_oracle_reproduces_golden(name):
     import importlib.util
     spec = importlib.util.spec_from_file_location("make_golden", os.path.join(GOLD, "make_golden.py"))
