@@ -47,6 +47,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if force or not _newer(LIB, srcs):
         cus = [s for s in srcs if s.endswith(".cu")]
         cmd = [nvcc, *NVCC_FLAGS, "-o", LIB, *cus, "-lcuda"]
+        if os.environ.get("LRNDE_TRACE"):
+            cmd.insert(1, "-DLRNDE_UMMA_TRACE")
         if verbose:
             cmd.insert(1, "-Xptxas")
             cmd.insert(2, "-v")

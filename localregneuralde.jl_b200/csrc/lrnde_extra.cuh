@@ -156,6 +156,8 @@ extern "C" int lrnde_sosri_step(lrnde_ctx* ctx, const lrnde_model* drift,
   const LinComb* dd = (const LinComb*)descs.p;
   MlpEval evf(ctx, drift, psd.p, B, o->precision, false);
   MlpEval evg(ctx, diffusion, psg.p, B, o->precision, false);
+  evf.prepare();
+  evg.prepare();
   for (int s = 0; s < 4; ++s) {
     if (s > 0) {
       sosri_stage_kernel<<<lr_ew_blocks(DB), 256, 0, st>>>(p, s);
@@ -370,3 +372,10 @@ extern "C" int lrnde_profile_feval(lrnde_ctx* ctx, const lrnde_model* m, const l
   if (launches_per_eval) *launches_per_eval = (int32_t)per;
   LR_API_END
 }
+
+#ifdef LRNDE_UMMA_TRACE
+extern "C" int lrnde_debug_trace(long long* out, int n) {
+  cudaMemcpyFromSymbol(out, g_umma_trace, sizeof(long long) * (size_t)n);
+  return 0;
+}
+#endif

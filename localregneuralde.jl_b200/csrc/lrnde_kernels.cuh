@@ -850,6 +850,7 @@ __global__ void __launch_bounds__(256) reg_seed_kernel(RegSeedP p) {
 struct RegBwdP {
   SolveDev* R; int row;
   const float* a; float* du; const float* dg6; float* dk[6];
+  float coef[6];  // tableau row a_{row+2, .} (host-filled: no local-memory table in the loop)
 };
 __global__ void __launch_bounds__(256) reg_bwd_stage_kernel(RegBwdP p) {
   const float dt = p.R->c.dt;
@@ -860,7 +861,9 @@ __global__ void __launch_bounds__(256) reg_bwd_stage_kernel(RegBwdP p) {
     if (p.row == 5) { a += p.du[i]; p.du[i] = a; nk = 5; }
     else { if (p.row == 4) a += p.dg6[i]; nk = p.row; }
     // k index i+1 (i>=1) receives dt * a[row][i] * a ; dk[] starts at k2
-    for (int k = 1; k <= nk; ++k) p.dk[k - 1][i] = fmaf(dt * lr_tsit5_a(p.row, k), a, p.dk[k - 1][i]);
+#pragma unroll
+    for (int k = 1; k <= 5; ++k)
+      if (k <= nk) p.dk[k - 1][i] = fmaf(dt * p.coef[k], a, p.dk[k - 1][i]);
   }
 }
 

@@ -1,0 +1,538 @@
+// tcgen05 / TMEM dense layer for sm_100a: the GEMM of one Lux Dense (or of its transposed
+// data-gradient) in TF32 or 3xTF32, drop-in for dense_nn_kernel (same DenseP contract).
+//
+//   D[128 x NT] (TMEM, fp32)  +=  A[128 x 8] (smem, K-major, SWIZZLE_128B)  x  B[NT x 8]^T
+//
+//   A = weight tile (output features on the 128 TMEM lanes).  Weights are constant during a
+//       solve, so they are split once per call into tf32 hi / lo parts and stored in global
+//       memory as ready-made shared-memory images (swizzle applied); a single elected thread
+//       streams them with cp.async.bulk (TMA engine) onto an mbarrier ring.
+//   B = activations [NT samples x 32 features] per K-chunk.  The stage combination
+//       uprev + dt * sum a_ij k_j (or the dense-output interpolant, or the TDChain time row /
+//       bias row) is formed by the producer warps WHILE the tile is written to shared memory
+//       -- the "linear combination in the operand prologue" of BASELINE.json's north star --
+//       and split hi / lo on the fly.
+//   3xTF32: D += A_lo*B_hi + A_hi*B_lo + A_hi*B_hi  (three tcgen05.mma per K-step).
+//   Epilogue: tcgen05.ld -> activation / activation-derivative -> coalesced global stores
+//       (lane = output feature => 32 consecutive floats per sample per warp).
+//
+// Two schedules:
+//   RING      one 128-row weight tile per CTA (grid.y = M tiles); A and B chunks share the
+//             mbarrier ring.  Used when K is long (layer 1: K = 786).
+//   RESIDENT  all K-chunks of the activation tile stay in shared memory, the CTA loops over
+//             every weight tile (up to 512 TMEM columns).  Used when K is short (layer 2:
+//             K = 102, 7 weight tiles).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <type_traits>
+
+#include "lrnde_kernels.cuh"
+
+#ifdef LRNDE_UMMA_TRACE
+__device__ long long g_umma_trace[8192];
+#define UMMA_TRACE(slot, it) do { if (blockIdx.x == 1 && blockIdx.y == 0 && (it) < 64) g_umma_trace[(slot) * 64 + (it)] = clock64(); } while (0)
+#else
+#define UMMA_TRACE(slot, it) do { } while (0)
+#endif
+
+namespace umma {
+
+constexpr int kChunkK = 32;                 // floats per K-chunk = one 128-byte swizzle row
+constexpr int kAChunkFloats = 128 * kChunkK;  // 4096 floats = 16 KB (hi), same again for lo
+constexpr int kAChunkBytes = 2 * kAChunkFloats * 4;  // 32 KB: [hi | lo]
+constexpr int kProducerWarps = 16;          // many warps: the operand prologue is load-latency bound
+constexpr int kThreads = 64 + kProducerWarps * 32;  // warp 0: bulk-copy producer, warp 1: MMA
+                                                    // issuer, the rest: operand producers, then
+                                                    // the epilogue
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  const uint32_t addr = smem_u32(bar);
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
+//   start address >> 4 | LBO (ignored for swizzled K-major; 1) | SBO = 1024 B (8 rows x 128 B)
+//   | version 1 (Blackwell) | layout type 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// kind::tf32 instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32,
+// both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// one lane of a converged warp (the pattern the compiler maps to ELECT + uniform-register operands;
+// a divergent `if (lane == 0)` region makes every tcgen05 operand go through an R2UR waterfall loop)
+__device__ __forceinline__ uint32_t elect_one_sync() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, %1;\n\t"
+      "@px mov.s32 %0, 1;\n\t}"
+      : "+r"(pred)
+      : "r"(0xFFFFFFFFu));
+  return pred;
+}
+// descriptor = {lo: start address >> 4 | LBO << 16, hi: SBO | version | layout}
+constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr >> 4) & 0x3FFFu) | (1u << 16); }
+__device__ __forceinline__ void mma_tf32_lo(uint32_t d_tmem, uint32_t a_lo32, uint32_t b_lo32, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_lo32), "r"(b_lo32), "r"(idesc), "r"(accumulate), "r"(kDescHi)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+// byte offset of (row, 16-byte chunk c) inside a K-major SWIZZLE_128B tile of 128-byte rows
+__device__ __forceinline__ uint32_t swz_off(int row, int c) {
+  return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((c ^ (row & 7)) << 4));
+}
+
+// ---- weights -> ready-made shared-memory images:  out[(mt*KC + kc)] = [hi 16 KB | lo 16 KB]
+__global__ void pack_weights_kernel(const float* __restrict__ A, long lda, int M, int Kaug, int KC,
+                                    float* __restrict__ out, int passes) {
+  // blockIdx.y = replica: every CTA of a GEMM reads the same weight images at the same time, so
+  // the images are replicated (and the chunk order rotated per CTA) to spread the L2 slices
+  const int chunk = blockIdx.x;
+  const int mt = chunk / KC, kc = chunk % KC;
+  float* dst = out + ((size_t)blockIdx.y * gridDim.x + chunk) * (2 * kAChunkFloats);
+  for (int e = threadIdx.x; e < kAChunkFloats; e += blockDim.x) {
+    const int r = e & 127, kk = e >> 7;
+    const int m = mt * 128 + r, k = kc * kChunkK + kk;
+    float v = (m < M && k < Kaug) ? A[(size_t)k * lda + m] : 0.0f;
+    float hi = (passes == 1) ? v : tf32_rna(v);
+    float lo = (passes == 1) ? 0.0f : tf32_rna(v - hi);  // rounded, not left to the MMA's truncation
+    const int c = kk >> 2;
+    const int pos = (r >> 3) * 256 + (r & 7) * 32 + ((c ^ (r & 7)) << 2) + (kk & 3);
+    dst[pos] = hi;
+    dst[kAChunkFloats + pos] = lo;
+  }
+}
+
+struct UmmaP {
+  DenseP d;
+  const float* Apack;  // packed weight images
+  int n_mt;            // number of 128-row weight tiles
+  int KC;              // number of 32-float K chunks (covers K + td + bias)
+  int passes;          // 3 = 3xTF32, 1 = TF32
+  int replicas;        // copies of the packed images (stride n_mt * KC chunks)
+};
+constexpr int kReplicas = 4;
+constexpr int kBulkParts = 2;
+constexpr int kPrefetchAhead = 4;  // K-chunks of L2 prefetch distance for the activation operand
+
+template <int NT>
+struct Cfg {
+  static constexpr int kBChunkBytes = NT * 128 * 2;  // [hi | lo]
+  static constexpr int kRingStage = kAChunkBytes + kBChunkBytes;
+  static constexpr int kRingStages = (NT == 64) ? 4 : 3;
+  static constexpr int kResStages = (NT == 64) ? 5 : 3;
+  static constexpr int kMaxResKC = 4;
+  static constexpr int ring_smem() { return kRingStages * kRingStage + 1024; }
+  static constexpr int res_smem(int KC) { return kResStages * kAChunkBytes + KC * kBChunkBytes + 1024; }
+};
+
+// One float4 group (row, 16-byte chunk c) of the activation operand: loads are issued by
+// load_group() and consumed later by store_group(), so that several K-chunks of loads are in
+// flight per thread (the prologue is load-latency bound: ~1 us per dependent global load).
+struct ProdCtx {
+  const DenseP* p;
+  const LinComb* sd;
+  int n0, nsrc, passes;
+  bool vec;
+  float tval;
+};
+
+template <int NS1>  // NS1 = 1 + number of lincomb sources held in registers
+__device__ __forceinline__ void load_group(const ProdCtx& c, int row, int cch, int kc, float4 (&buf)[NS1]) {
+  const DenseP& p = *c.p;
+  const int n = c.n0 + row, k = kc * kChunkK + cch * 4;
+  if (n < p.N && c.vec && k + 3 < p.K) {
+    const size_t off = (size_t)n * p.ldx + k;
+    buf[0] = c.sd->base ? *reinterpret_cast<const float4*>(c.sd->base + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int s = 0; s < NS1 - 1; ++s)
+      if (s < c.nsrc) buf[s + 1] = *reinterpret_cast<const float4*>(c.sd->src[s] + off);
+  }
+}
+
+template <int NS1, int NT>
+__device__ __forceinline__ void store_group(const ProdCtx& c, int row, int cch, int kc, const float4 (&buf)[NS1],
+                                            uint8_t* dst) {
+  const DenseP& p = *c.p;
+  const LinComb& sd = *c.sd;
+  const int n = c.n0 + row, k = kc * kChunkK + cch * 4;
+  float v[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+  if (n < p.N) {
+    const size_t off = (size_t)n * p.ldx + k;
+    if (c.vec && k + 3 < p.K) {
+      float4 inner = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int s = 0; s < NS1 - 1; ++s)
+        if (s < c.nsrc) {
+          const float cf = sd.coef[s];
+          inner.x = fmaf(cf, buf[s + 1].x, inner.x); inner.y = fmaf(cf, buf[s + 1].y, inner.y);
+          inner.z = fmaf(cf, buf[s + 1].z, inner.z); inner.w = fmaf(cf, buf[s + 1].w, inner.w);
+        }
+      if (c.nsrc) {
+        v[0] = fmaf(sd.scale, inner.x, buf[0].x); v[1] = fmaf(sd.scale, inner.y, buf[0].y);
+        v[2] = fmaf(sd.scale, inner.z, buf[0].z); v[3] = fmaf(sd.scale, inner.w, buf[0].w);
+      } else { v[0] = buf[0].x; v[1] = buf[0].y; v[2] = buf[0].z; v[3] = buf[0].w; }
+      if (p.in_act) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[e] = lr_act(p.in_act, v[e]);
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int kk = k + e;
+        if (kk < p.K) {
+          float x = lr_lincomb_at(sd, off + e);
+          v[e] = p.in_act ? lr_act(p.in_act, x) : x;
+        } else if (p.td && kk == p.K) v[e] = c.tval;
+        else if (p.bias && kk == p.K + p.td) v[e] = 1.0f;
+      }
+    }
+  }
+  float4 hi, lo;
+  if (c.passes == 3) {
+    hi = make_float4(tf32_rna(v[0]), tf32_rna(v[1]), tf32_rna(v[2]), tf32_rna(v[3]));
+    lo = make_float4(tf32_rna(v[0] - hi.x), tf32_rna(v[1] - hi.y), tf32_rna(v[2] - hi.z), tf32_rna(v[3] - hi.w));
+  } else {
+    hi = make_float4(v[0], v[1], v[2], v[3]);
+    lo = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const uint32_t o = swz_off(row, cch);
+  *reinterpret_cast<float4*>(dst + o) = hi;
+  *reinterpret_cast<float4*>(dst + NT * 128 + o) = lo;
+}
+
+template <int NT, bool RESIDENT>
+__global__ void __launch_bounds__(kThreads, 1) dense_kernel(UmmaP q) {
+  const DenseP& p = q.d;
+  if (p.done && *p.done) return;
+  using C = Cfg<NT>;
+  constexpr int NS = RESIDENT ? C::kResStages : C::kRingStages;
+  constexpr int PT = kProducerWarps * 32;  // producer / epilogue threads
+  constexpr int GPT = NT * 8 / PT;         // float4 groups per producer thread per K-chunk
+  static_assert(NT * 8 % PT == 0 && GPT >= 1, "producer mapping");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t full_bar[8], empty_bar[8], tile_bar[8], bres_bar;
+  __shared__ uint32_t tmem_slot;
+  __shared__ LinComb sdesc;
+  __shared__ float s_t;
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform for the compiler
+  const int lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * NT;
+  const int KC = q.KC;
+  const int mt_begin = RESIDENT ? 0 : blockIdx.y;
+  const int mt_count = RESIDENT ? q.n_mt : 1;
+  const int nchunks = mt_count * KC;
+  // RING: the K loop is split over several TMEM accumulators that the epilogue adds in fp32
+  // (the tensor core accumulates with truncation; shorter chains keep 3xTF32 at fp32 level)
+  const int nacc = RESIDENT ? 1 : min(512 / NT, KC);
+  const int ncols_used = RESIDENT ? mt_count * NT : nacc * NT;
+  // chunk order rotated per CTA (accumulation order is free): de-synchronises the CTAs.
+  // RESIDENT rotates whole weight tiles so that tiles finish one after the other and the
+  // epilogue of a finished tile overlaps the MMAs of the next.
+  const int rot = RESIDENT ? (int)((blockIdx.x * 3u) % (unsigned)mt_count) * KC
+                           : (int)((blockIdx.x * 7u + blockIdx.y * 3u) % (unsigned)nchunks);
+
+  auto a_stage = [&](int s) -> uint8_t* {
+    return RESIDENT ? smem + (size_t)s * kAChunkBytes : smem + (size_t)s * C::kRingStage;
+  };
+  auto b_slot = [&](int s_or_kc) -> uint8_t* {
+    return RESIDENT ? smem + (size_t)NS * kAChunkBytes + (size_t)s_or_kc * C::kBChunkBytes
+                    : smem + (size_t)s_or_kc * C::kRingStage + kAChunkBytes;
+  };
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NS; ++s) {
+      mbar_init(&full_bar[s], RESIDENT ? 1u : (uint32_t)(kProducerWarps + 1));  // one arrival per warp
+      mbar_init(&empty_bar[s], 1u);
+    }
+    for (int t = 0; t < 8; ++t) mbar_init(&tile_bar[t], 1u);
+    mbar_init(&bres_bar, (uint32_t)kProducerWarps);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (p.xdesc) sdesc = *p.xdesc;
+    else { sdesc.base = p.X; sdesc.n = 0; sdesc.scale = 0.0f; }
+    s_t = p.tdesc ? p.tdesc->t : 0.0f;
+  }
+  uint32_t ncols = 32;
+  while (ncols < (uint32_t)ncols_used) ncols <<= 1;
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)),
+                 "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  if (threadIdx.x == 0) UMMA_TRACE(7, 0);
+
+  if (warp == 0) {
+    // ------------------------------------------------ weight images: bulk copies onto the ring
+    // (converged warp + one elected lane, same reason as the MMA warp)
+    const float* src = q.Apack + (size_t)(blockIdx.x % q.replicas) * q.n_mt * KC * (2 * kAChunkFloats);
+    for (int it = 0; it < nchunks; ++it) {
+      const int s = it % NS, ph = (it / NS) & 1;
+      const int j = (it + rot) % nchunks;
+      const int mt = mt_begin + j / KC, kc = j % KC;
+      mbar_wait(&empty_bar[s], ph ^ 1);
+      const uint8_t* g = (const uint8_t*)(src + (size_t)(mt * KC + kc) * (2 * kAChunkFloats));
+      uint8_t* d = a_stage(s);
+      if (elect_one_sync()) {
+        UMMA_TRACE(0, it);
+        mbar_arrive_expect_tx(&full_bar[s], kAChunkBytes);
+#pragma unroll
+        for (int part = 0; part < kBulkParts; ++part)
+          bulk_g2s(d + part * (kAChunkBytes / kBulkParts), g + part * (kAChunkBytes / kBulkParts),
+                   kAChunkBytes / kBulkParts, &full_bar[s]);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------ tcgen05.mma issue: the whole warp runs the
+    // loop converged (uniform registers), one elected lane issues the MMAs and the commits
+    constexpr uint32_t idesc = make_idesc(128, NT);
+    if (RESIDENT) mbar_wait(&bres_bar, 0);
+    for (int it = 0; it < nchunks; ++it) {
+      const int s = it % NS, ph = (it / NS) & 1;
+      const int j = (it + rot) % nchunks;
+      const int mi = j / KC, kc = j % KC;
+      mbar_wait(&full_bar[s], ph);
+      tc_fence_after();
+      if (lane == 0) UMMA_TRACE(1, it);
+      const uint32_t a_hi = desc_lo(smem_u32(a_stage(s)));
+      const uint32_t a_lo = desc_lo(smem_u32(a_stage(s)) + kAChunkFloats * 4);
+      const uint32_t b_hi = desc_lo(smem_u32(b_slot(RESIDENT ? kc : s)));
+      const uint32_t b_lo = desc_lo(smem_u32(b_slot(RESIDENT ? kc : s)) + NT * 128);
+      int acc = 0;
+      bool group_start, group_end;
+      if (!RESIDENT) {
+        acc = (it * nacc) / KC;
+        group_start = (it == 0) || (((it - 1) * nacc) / KC != acc);
+        group_end = (it == nchunks - 1);
+      } else {
+        group_start = (kc == 0);      // whole tiles are rotated: a tile's chunks are contiguous
+        group_end = (kc == KC - 1);
+      }
+      const uint32_t d = tmem_base + (uint32_t)((RESIDENT ? mi : acc) * NT);
+      if (elect_one_sync()) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t ko = (uint32_t)k * 2;  // 8 tf32 = 32 bytes = 2 x 16 B along K in the swizzle row
+          const uint32_t first = (group_start && k == 0) ? 0u : 1u;
+          if (q.passes == 3) {
+            mma_tf32_lo(d, a_lo + ko, b_hi + ko, idesc, first);
+            mma_tf32_lo(d, a_hi + ko, b_lo + ko, idesc, 1u);
+            mma_tf32_lo(d, a_hi + ko, b_hi + ko, idesc, 1u);
+          } else {
+            mma_tf32_lo(d, a_hi + ko, b_hi + ko, idesc, first);
+          }
+        }
+        mma_commit(&empty_bar[s]);  // frees the stage once these MMAs have read it
+        if (group_end) mma_commit(&tile_bar[RESIDENT ? mi : 0]);  // accumulator(s) complete
+        UMMA_TRACE(2, it);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ------------------------------------------------ warps 2..: operand producers
+    const int tid = threadIdx.x - 64;
+    ProdCtx pc;
+    pc.p = &p; pc.sd = &sdesc; pc.n0 = n0; pc.nsrc = sdesc.n; pc.passes = q.passes; pc.tval = s_t;
+    pc.vec = (p.ldx % 4 == 0) && ((((uintptr_t)sdesc.base) & 15) == 0);
+    for (int k = 0; k < sdesc.n; ++k) pc.vec = pc.vec && ((((uintptr_t)sdesc.src[k]) & 15) == 0);
+
+    // software-pipelined producer: DEPTH chunks of loads in flight per thread, about 8 float4
+    // registers of load buffers whatever the number of lincomb sources
+    auto run = [&](auto ns1_tag, auto depth_tag) {
+      constexpr int NS1 = decltype(ns1_tag)::value;
+      constexpr int DEPTH = decltype(depth_tag)::value;
+      float4 buf[DEPTH][GPT][NS1];
+      const int total = RESIDENT ? KC : nchunks;
+      auto chunk_of = [&](int it) { return RESIDENT ? it : (it + rot) % KC; };
+#pragma unroll
+      for (int d = 0; d < DEPTH; ++d)
+        if (d < total) {
+#pragma unroll
+          for (int g = 0; g < GPT; ++g) {
+            const int gi = tid + g * PT;
+            load_group<NS1>(pc, gi >> 3, gi & 7, chunk_of(d), buf[d][g]);
+          }
+        }
+      for (int it0 = 0; it0 < total; it0 += DEPTH) {
+#pragma unroll
+        for (int d = 0; d < DEPTH; ++d) {
+          const int it = it0 + d;
+          if (it < total) {
+            const int s = it % NS, ph = (it / NS) & 1;
+            uint8_t* dst = RESIDENT ? b_slot(it) : b_slot(s);
+            if (!RESIDENT) mbar_wait(&empty_bar[s], ph ^ 1);
+            if (tid == 0) UMMA_TRACE(3, it);
+#pragma unroll
+            for (int g = 0; g < GPT; ++g) {
+              const int gi = tid + g * PT;
+              store_group<NS1, NT>(pc, gi >> 3, gi & 7, chunk_of(it), buf[d][g], dst);
+            }
+            if (tid == 0) UMMA_TRACE(4, it);
+            if (it + DEPTH < total) {
+#pragma unroll
+              for (int g = 0; g < GPT; ++g) {
+                const int gi = tid + g * PT;
+                load_group<NS1>(pc, gi >> 3, gi & 7, chunk_of(it + DEPTH), buf[d][g]);
+              }
+            }
+            if (!RESIDENT) {
+              fence_proxy_async();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&full_bar[s]);  // 512 arrivals on one word would serialise
+            }
+          }
+        }
+      }
+      if (RESIDENT) {
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bres_bar);
+      }
+    };
+    using I1 = std::integral_constant<int, 1>;
+    using I2 = std::integral_constant<int, 2>;
+    using I3 = std::integral_constant<int, 3>;
+    using I4 = std::integral_constant<int, 4>;
+    using I8 = std::integral_constant<int, 8>;
+    if (pc.nsrc == 0) run(I1{}, I4{});
+    else if (pc.nsrc == 1) run(I2{}, I4{});
+    else if (pc.nsrc <= 3) run(I4{}, I2{});
+    else run(I8{}, I1{});
+
+    // ------------------------------------------------ epilogue: TMEM -> registers -> global
+    // warps sharing a TMEM lane quarter split the 16-column blocks; tiles are drained in the
+    // order the MMA warp finishes them
+    const int quarter = (warp & 3) * 32;     // the TMEM lanes this warp may read
+    const int wgroup = (warp - 2) >> 2;
+    constexpr int kGroups = kProducerWarps / 4;
+    const int row = quarter + lane;
+    float* Y = p.ydesc ? (p.ydesc->dst + p.y_off) : p.Y;
+    for (int t = 0; t < mt_count; ++t) {
+      const int mi = RESIDENT ? (t + rot / KC) % mt_count : 0;
+      if (tid == 0) UMMA_TRACE(6, 0);
+      mbar_wait(&tile_bar[mi], 0);
+      tc_fence_after();
+      if (tid == 0) UMMA_TRACE(6, 1);
+      const int m = (mt_begin + mi) * 128 + row;
+      for (int cb = wgroup; cb < NT / 16; cb += kGroups) {
+        const int c0 = cb * 16;
+        float accv[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) accv[j] = 0.0f;
+        for (int a = 0; a < nacc; ++a) {
+          uint32_t r[16];
+          const uint32_t taddr =
+              tmem_base + ((uint32_t)quarter << 16) + (uint32_t)((RESIDENT ? mi : a) * NT + c0);
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, "
+              "%13, %14, %15}, [%16];\n\t"
+              "tcgen05.wait::ld.sync.aligned;"
+              : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),
+                "=r"(r[15])
+              : "r"(taddr)
+              : "memory");
+#pragma unroll
+          for (int j = 0; j < 16; ++j) accv[j] += __uint_as_float(r[j]);
+        }
+        if (m < p.M) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int n = n0 + c0 + j;
+            if (n < p.N) {
+              float v = accv[j];
+              if (p.pre) p.pre[(size_t)n * p.ldpre + m] = v;
+              if (p.dact >= 0) v = v * lr_dact(p.dact, p.dpre[(size_t)n * p.lddpre + m]);
+              else v = lr_act(p.act, v);
+              Y[(size_t)n * p.ldy + m] = v * p.out_scale;
+            }
+          }
+        }
+      }
+    }
+    tc_fence_before();
+    if (tid == 0) UMMA_TRACE(6, 2);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) UMMA_TRACE(6, 3);
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
+  }
+}
+
+}  // namespace umma

@@ -113,6 +113,7 @@ def build(name):
         step_log=log, bwd_step_log=blog, nf_bwd=np.int64(aux["bsol"].nf),
         t1=np.float32(aux.get("t1", 0.0)), dt_reg=np.float32(aux.get("dt_reg", 0.0)),
         step_log64=log64, reg_val64=np.float64(st64["reg_val"]),
+        n_bwd64=np.int64(len(aux64["bsol"].step_log)),
         u_last64=np.asarray(sol64.u[-1], np.float64), d_x64=d_x64.astype(np.float64),
         d_ps_rel64=np.float64(np.abs(d_ps64 - d_ps).max() / np.abs(d_ps64).max()),
         d_x_rel64=np.float64(np.abs(d_x64 - d_x).max() / (np.abs(d_x64).max() + 1e-300)),
