@@ -224,6 +224,9 @@ def run_native(args):
             u_last = sol.u[-1].t()                           # (B, D) contiguous block of u_save
             chk(lib.lrnde_head_ce(ctx._h, Wc.data_ptr(), u_last.data_ptr(), y.data_ptr(), B, D, NCLS, 0,
                                   C.byref(loss), d_u.data_ptr(), d_Wc.data_ptr()))
+            if world > 1:            # global-mean loss: lambda(t2) = dL/du carries 1 / world
+                d_u.mul_(1.0 / world)
+                d_Wc.mul_(1.0 / world)
             d_x, d_ps = node.backward(sol, [None, d_u.t()], W_REG)
             launches["n"] += sol.stats.gpu_launches + sol.bwd_stats.gpu_launches + 6
             gp, gw = d_ps, d_Wc
@@ -235,14 +238,15 @@ def run_native(args):
             dwc_np = np.empty(NCLS * D + NCLS, np.float32)
             chk(lib.lrnde_head_ce(ctx._h, ps_host["Wc"].ctypes.data, u_last.ctypes.data, y_h.ctypes.data, B, D,
                                   NCLS, 1, C.byref(loss), du_np.ctypes.data, dwc_np.ctypes.data))
+            if world > 1:
+                du_np *= np.float32(1.0 / world)
+                dwc_np *= np.float32(1.0 / world)
             d_x, d_ps = node.backward(sol, [None, du_np.T], W_REG)
             gp = torch.from_numpy(d_ps).to(dev, non_blocking=False)
             gw = torch.from_numpy(dwc_np).to(dev)
-        if world > 1:
+        if world > 1:                # parameter gradients: one NCCL all-reduce per iteration
             dist.all_reduce(gp)
             dist.all_reduce(gw)
-            gp /= world
-            gw /= world
         chk(lib.lrnde_adam_step(ctx._h, ps.data_ptr(), gp.data_ptr(), opt["m_ps"].data_ptr(),
                                 opt["v_ps"].data_ptr(), P, LR, 0.9, 0.999, 1e-8, i + 1))
         chk(lib.lrnde_adam_step(ctx._h, Wc.data_ptr(), gw.data_ptr(), opt["m_wc"].data_ptr(),

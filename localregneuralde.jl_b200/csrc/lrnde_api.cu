@@ -165,11 +165,11 @@ extern "C" int lrnde_ctx_mailbox(lrnde_ctx* c, void** dev_ptr, uint64_t* bytes) 
   LR_CUDA(cudaSetDevice(c->device));
   if (!c->mailbox) {
     // a dedicated cudaMalloc so the block can be exported with cudaIpcGetMemHandle
-    LR_CUDA(cudaMalloc((void**)&c->mailbox, sizeof(LrMailbox)));
-    LR_CUDA(cudaMemset(c->mailbox, 0, sizeof(LrMailbox)));
+    LR_CUDA(cudaMalloc((void**)&c->mailbox, LR_MAILBOX_BYTES));
+    LR_CUDA(cudaMemset(c->mailbox, 0, LR_MAILBOX_BYTES));
   }
   *dev_ptr = c->mailbox;
-  if (bytes) *bytes = sizeof(LrMailbox);
+  if (bytes) *bytes = LR_MAILBOX_BYTES;
   LR_API_END
 }
 
@@ -185,6 +185,7 @@ extern "C" int lrnde_ctx_set_dist(lrnde_ctx* c, int rank, int nranks, void* cons
   c->total_batch = total_batch;
   for (int r = 0; r < nranks && nranks > 1; ++r) c->peer_mbox[r] = (LrMailbox*)mailboxes[r];
   c->seq = 0;
+  c->mseq = 0;
   LR_API_END
 }
 
@@ -484,6 +485,7 @@ struct Solver {
   unsigned char* logacc = nullptr;
   double* partials = nullptr;
   unsigned int* counters = nullptr;
+  float* muglob = nullptr;
   cudaGraph_t while_graph = nullptr, body_graph = nullptr;
   cudaGraphExec_t while_exec = nullptr, body_exec = nullptr;
   long body_nodes = 0;
@@ -502,7 +504,7 @@ struct Solver {
     logbuf = (float*)ctx->alloc(sizeof(float) * 3 * (size_t)std::max(logcap, 1));
     logacc = (unsigned char*)ctx->alloc((size_t)std::max(logcap, 1));
     partials = (double*)ctx->alloc(sizeof(double) * 4 * LR_ERR_BLOCKS);
-    counters = (unsigned int*)ctx->alloc(sizeof(unsigned int) * 4);
+    counters = (unsigned int*)ctx->alloc(sizeof(unsigned int) * 8);
     h.tape = tape;
     h.ts = ts;
     h.log_t = logbuf;
@@ -528,11 +530,25 @@ struct Solver {
     ctx->release(logacc);
     ctx->release(partials);
     ctx->release(counters);
+    ctx->release(muglob);
   }
 
+  // adjoint in a data-parallel group: buffers of the mu-vector exchange
+  void enable_mu_exchange(size_t P) {
+    if (P > (size_t)LR_MU_MAX) {
+      lr_set_error("data-parallel adjoint supports up to %d parameters, model has %zu", LR_MU_MAX, P);
+      throw LrError(LRNDE_EINVAL);
+    }
+    muglob = (float*)ctx->alloc(sizeof(float) * 3 * P);
+    h.muglob = muglob;
+    h.mu_len = P;
+    h.mucounter = counters + 4;
+    h.reduce_mu = 1;
+  }
   void upload() {
     h.seq = ctx->seq;
-    LR_CUDA(cudaMemsetAsync(counters, 0, sizeof(unsigned int) * 4, ctx->stream));
+    h.mseq = ctx->mseq;
+    LR_CUDA(cudaMemsetAsync(counters, 0, sizeof(unsigned int) * 8, ctx->stream));
     LR_CUDA(cudaMemcpyAsync(dev, &h, sizeof(SolveDev), cudaMemcpyHostToDevice, ctx->stream));
   }
   void download() {
@@ -541,6 +557,7 @@ struct Solver {
     LR_CUDA(cudaStreamSynchronize(ctx->stream));
     h = *pin;
     ctx->seq = h.seq;
+    ctx->mseq = h.mseq;
   }
 
   void init_ctrl(float t0, float tend, float first_stop, int maxiters, int pow_mode,
@@ -685,6 +702,19 @@ static void lr_copy_log(Solver& S, lrnde_tape* T, int which) {
   LR_CUDA(cudaStreamSynchronize(st));
 }
 
+// data-parallel adjoint: exchange the mu vectors the next norm reads (no-op otherwise)
+static void lr_mu_exchange(Solver& S, int mode, int nvec, const int* done) {
+  if (!(S.h.reduce_mu && S.h.nranks > 1)) return;
+  lrnde_ctx* ctx = S.ctx;
+  cudaStream_t st = ctx->stream;
+  mu_publish_kernel<<<64, 256, 0, st>>>(S.dev, mode, done);
+  LR_COUNT(ctx);
+  mu_gather_kernel<<<64, 256, 0, st>>>(S.dev, nvec, done);
+  LR_COUNT(ctx);
+  mu_norm_kernel<<<LR_ERR_BLOCKS, 256, 0, st>>>(S.dev, mode, done);
+  LR_COUNT(ctx);
+}
+
 // fsalfirst + initial dt of a freshly initialised solver (OrdinaryDiffEq __init: initialize!
 // then auto_dt_reset!), then the header of the first attempt when `begin`.
 template <class EvalFn>
@@ -696,11 +726,13 @@ static void lr_solver_start(Solver& S, EvalFn&& eval, int begin) {
   eval(&S.dev->st[6], &S.dev->yint[6], &S.dev->failed);
   initdt_norm1_kernel<<<LR_ERR_BLOCKS, 256, 0, st>>>(S.dev);
   LR_COUNT(ctx);
+  lr_mu_exchange(S, 0, 1, &S.dev->failed);
   initdt_a_kernel<<<1, 32, 0, st>>>(S.dev);
   LR_COUNT(ctx);
   eval(&S.dev->st[0], &S.dev->yint[1], &S.dev->failed);
   initdt_norm2_kernel<<<LR_ERR_BLOCKS, 256, 0, st>>>(S.dev);
   LR_COUNT(ctx);
+  lr_mu_exchange(S, 1, 1, &S.dev->failed);
   initdt_b_kernel<<<1, 32, 0, st>>>(S.dev, begin);
   LR_COUNT(ctx);
   LR_CHECK_LAUNCH();
@@ -717,6 +749,7 @@ static void lr_step_body(Solver& S, EvalFn&& eval) {
   eval(&S.dev->st[6], &S.dev->yint[6], &S.dev->done);
   err_norm_kernel<<<LR_ERR_BLOCKS, 256, 0, st>>>(S.dev);
   LR_COUNT(ctx);
+  lr_mu_exchange(S, 2, 3, &S.dev->done);
   controller_kernel<<<1, 32, 0, st>>>(S.dev);
   LR_COUNT(ctx);
   LR_CHECK_LAUNCH();
@@ -1107,7 +1140,7 @@ extern "C" int lrnde_ode_backward(lrnde_ctx* ctx, const lrnde_model* m, lrnde_ta
     A.h.ftdir = 1;
     if (ctx->nranks > 1) {
       A.h.total_len = (unsigned long long)D * (unsigned long long)ctx->total_batch + P;
-      A.h.reduce_mu = 1;
+      A.enable_mu_exchange(P);
     }
     // interior tstops: saved times strictly inside (t0, t2), descending, unique
     std::vector<float> stops;

@@ -31,7 +31,17 @@ struct LinComb {
 struct LrMailbox {
   double val[2][LR_MAX_RANKS][4];
   unsigned long long flag[2][LR_MAX_RANKS];
+  unsigned long long mflag[2][LR_MAX_RANKS];  // vector exchange (adjoint mu block)
+  unsigned long long pad_[16];
 };
+// The exported mailbox allocation = LrMailbox followed by the vector staging area
+// stage[parity][3][LR_MU_MAX] floats: per-rank partial batch sums of the mu block that the
+// adjoint's error norm needs as GLOBAL values.
+#define LR_MU_MAX (1 << 20)
+#define LR_MAILBOX_BYTES (sizeof(LrMailbox) + sizeof(float) * 2 * 3 * (size_t)LR_MU_MAX)
+__host__ __device__ inline float* lr_mbox_stage(LrMailbox* m, int parity, int vec) {
+  return reinterpret_cast<float*>(m + 1) + ((size_t)parity * 3 + vec) * LR_MU_MAX;
+}
 
 struct SolveDev {
   LrCtrl c;
@@ -80,6 +90,10 @@ struct SolveDev {
   unsigned long long seq;  // collective sequence number
   unsigned long long total_len;  // elements of the GLOBAL array (norm denominators)
   LrMailbox* mbox[LR_MAX_RANKS];
+  unsigned long long mseq;       // vector-exchange sequence number
+  float* muglob;                 // [3][mu_len]: globally summed mu vectors of the current exchange
+  unsigned int* mucounter;       // blocks-finished counter of mu_publish_kernel
+  size_t mu_len;                 // P
 };
 
 __host__ __device__ inline float* lr_slot_u(const SolveDev* S, int s) {

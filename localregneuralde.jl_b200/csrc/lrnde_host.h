@@ -47,6 +47,7 @@ struct lrnde_ctx {
   LrMailbox* mailbox = nullptr;               // this rank's mailbox (device memory)
   LrMailbox* peer_mbox[LR_MAX_RANKS] = {nullptr};
   unsigned long long seq = 0;                 // next collective sequence number
+  unsigned long long mseq = 0;                // next vector-exchange sequence number
 
   void* alloc(size_t bytes);
   void release(void* p);

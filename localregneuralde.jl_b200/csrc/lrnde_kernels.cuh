@@ -460,7 +460,8 @@ __global__ void __launch_bounds__(256) initdt_norm1_kernel(SolveDev* S) {
   const float abstol = S->abstol, reltol = S->reltol;
   double a0 = 0.0, a1 = 0.0;
   unsigned int bad = 0;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < S->len;
+  const size_t nloc = (S->reduce_mu && S->nranks > 1) ? S->lam_len : S->len;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nloc;
        i += (size_t)gridDim.x * blockDim.x) {
     float u = u0[i], f = f0[i];
     float sk = abstol + fabsf(u) * reltol;
@@ -487,7 +488,8 @@ __global__ void __launch_bounds__(256) initdt_norm2_kernel(SolveDev* S) {
   const float abstol = S->abstol, reltol = S->reltol;
   double a2 = 0.0;
   unsigned int neq = 0;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < S->len;
+  const size_t nloc = (S->reduce_mu && S->nranks > 1) ? S->lam_len : S->len;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nloc;
        i += (size_t)gridDim.x * blockDim.x) {
     float sk = abstol + fabsf(u0[i]) * reltol;
     float q = (f1[i] - f0[i]) / sk;
@@ -530,6 +532,103 @@ __device__ inline void lr_group_sum(SolveDev* S, double* v) {
     for (int r = 0; r < S->nranks; ++r) s += ((volatile double*)mine->val[par][r])[k];
     v[k] = s;
   }
+}
+
+// ------------------------------------------------------------------------------------------
+// Adjoint in a data-parallel group: z = [lambda_local ; mu_partial].  mu is a batch sum, and the
+// step controller's norms are non-linear in it, so the vectors they read are exchanged:
+// every rank publishes its partial vectors in its peer-mapped staging area, then every rank adds
+// all ranks' vectors in rank order (identical bits everywhere).  mode 0: f0_mu ; mode 1:
+// (f1 - f0)_mu ; mode 2: utilde_mu, mu_prev, mu_new of the attempt.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) mu_publish_kernel(SolveDev* S, int mode, const int* done) {
+  if (done && *done) return;
+  __shared__ LinComb e;
+  if (threadIdx.x == 0) e = S->err;
+  __syncthreads();
+  const size_t P = S->mu_len, off = S->lam_len;
+  const int par = (int)(S->mseq & 1ull);
+  LrMailbox* mine = S->mbox[S->rank];
+  float* v0 = lr_mbox_stage(mine, par, 0);
+  float* v1 = lr_mbox_stage(mine, par, 1);
+  float* v2 = lr_mbox_stage(mine, par, 2);
+  const float* f0 = lr_slot_k(S, S->slot, 1) + off;
+  const float* f1 = lr_slot_k(S, S->slot, 2) + off;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < P; i += (size_t)gridDim.x * blockDim.x) {
+    if (mode == 0) v0[i] = f0[i];
+    else if (mode == 1) v0[i] = f1[i] - f0[i];
+    else {
+      float inner = 0.0f;
+#pragma unroll
+      for (int k = 0; k < 7; ++k) inner = fmaf(e.coef[k], e.src[k][off + i], inner);
+      v0[i] = e.scale * inner;
+      v1[i] = e.base[off + i];
+      v2[i] = e.dst[off + i];
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int prev = atomicAdd(S->mucounter, 1u);
+    if (prev == gridDim.x - 1) {  // last block: everything of this rank is visible, raise the flags
+      *S->mucounter = 0;
+      __threadfence_system();
+      for (int r = 0; r < S->nranks; ++r) {
+        volatile unsigned long long* f = &S->mbox[r]->mflag[par][S->rank];
+        *f = S->mseq + 1;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) mu_gather_kernel(SolveDev* S, int nvec, const int* done) {
+  if (done && *done) return;
+  const int par = (int)(S->mseq & 1ull);
+  LrMailbox* mine = S->mbox[S->rank];
+  if (threadIdx.x == 0) {
+    for (int r = 0; r < S->nranks; ++r) {
+      volatile unsigned long long* f = &mine->mflag[par][r];
+      while (*f != S->mseq + 1) { __nanosleep(40); }
+    }
+    __threadfence_system();
+  }
+  __syncthreads();
+  const size_t P = S->mu_len;
+  for (int v = 0; v < nvec; ++v) {
+    float* out = S->muglob + (size_t)v * P;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < P; i += (size_t)gridDim.x * blockDim.x) {
+      float s = 0.0f;
+      for (int r = 0; r < S->nranks; ++r) {
+        const volatile float* src = lr_mbox_stage(S->mbox[r], par, v);
+        s += src[i];
+      }
+      out[i] = s;
+    }
+  }
+}
+
+// mu part of the norms from the exchanged global vectors -> partials[3 * LR_ERR_BLOCKS + b]
+__global__ void __launch_bounds__(256) mu_norm_kernel(SolveDev* S, int mode, const int* done) {
+  if (done && *done) return;
+  const size_t P = S->mu_len;
+  const float abstol = S->abstol, reltol = S->reltol;
+  const float* g0 = S->muglob;
+  const float* g1 = S->muglob + P;
+  const float* g2 = S->muglob + 2 * P;
+  double acc = 0.0;
+  unsigned int cnt = 0;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < P; i += (size_t)gridDim.x * blockDim.x) {
+    float r;
+    if (mode == 2) r = g0[i] / (abstol + fmaxf(fabsf(g1[i]), fabsf(g2[i])) * reltol);
+    else r = g0[i] / abstol;  // mu(t2) = 0  =>  sk = abstol
+    acc += (double)(r * r);
+    if (mode == 0 && !isfinite(g0[i])) cnt++;
+    if (mode == 1 && !(g0[i] == 0.0f)) cnt++;
+  }
+  double s = lr_block_sum(acc);
+  if (threadIdx.x == 0) S->partials[3 * LR_ERR_BLOCKS + blockIdx.x] = s;
+  if (cnt) atomicAdd(&S->counters[3], cnt);
+  if (blockIdx.x == 0 && threadIdx.x == 0) S->mseq += 1;  // next exchange uses the other parity
 }
 
 // fixed-order sum of LR_ERR_BLOCKS partials by one warp
@@ -644,6 +743,13 @@ __global__ void initdt_a_kernel(SolveDev* S) {
   v[2] = (double)S->counters[0];
   v[3] = 0.0;
   lr_group_sum(S, v);
+  if (S->reduce_mu && S->nranks > 1) {  // mu block from the exchanged global vector
+    double m = 0.0;
+    for (int i = 0; i < LR_ERR_BLOCKS; ++i) m += S->partials[3 * LR_ERR_BLOCKS + i];
+    v[1] += m;
+    v[2] += (double)S->counters[3];
+    S->counters[3] = 0;
+  }
   S->nf += 2;
   const double n = (double)S->total_len;
   float d0 = sqrtf((float)v[0] / (float)n);
@@ -675,6 +781,13 @@ __global__ void initdt_b_kernel(SolveDev* S, int begin) {
   v[1] = (double)S->counters[1];
   v[2] = v[3] = 0.0;
   lr_group_sum(S, v);
+  if (S->reduce_mu && S->nranks > 1) {
+    double m = 0.0;
+    for (int i = 0; i < LR_ERR_BLOCKS; ++i) m += S->partials[3 * LR_ERR_BLOCKS + i];
+    v[0] += m;
+    v[1] += (double)S->counters[3];
+    S->counters[3] = 0;
+  }
   float d2rms = sqrtf((float)v[0] / (float)(double)S->total_len);
   float dt;
   if (S->counters[2]) dt = lr_mul((float)S->c.tdir, S->c.dtmin);
@@ -695,7 +808,7 @@ __global__ void controller_kernel(SolveDev* S) {
   if (S->done) { if (threadIdx.x == 0) lr_set_cond(S); return; }
   double v[4];
   v[0] = lr_sum_partials(S->partials);
-  v[1] = (S->reduce_mu && S->nranks > 1) ? lr_sum_partials(S->partials + LR_ERR_BLOCKS) : 0.0;
+  v[1] = (S->reduce_mu && S->nranks > 1) ? lr_sum_partials(S->partials + 3 * LR_ERR_BLOCKS) : 0.0;
   if (threadIdx.x != 0) return;
   v[2] = v[3] = 0.0;
   if (!(S->reduce_mu && S->nranks > 1)) lr_group_sum(S, v);

@@ -335,7 +335,9 @@ def test_full_size_batch_replication_property(pkg, prec):
     dx2, dps2 = node.backward(sol2, [None, c2], 1.5)
     assert st1["nfe"] == st2["nfe"]
     assert rel(sol2.u[-1][:, :B], sol1.u[-1]) < 1e-5 and rel(sol2.u[-1][:, B:], sol1.u[-1]) < 1e-5
-    assert abs(float(st1["reg_val"]) / float(st2["reg_val"]) - 1) < 1e-4
+    # the K-chunk order of the tcgen05 kernels is rotated per CTA, so a sample and its replica
+    # are summed in different orders: bit-identical in fp32 mode only
+    assert abs(float(st1["reg_val"]) / float(st2["reg_val"]) - 1) < (1e-4 if prec == "fp32" else 5e-3)
     assert rel(dx2[:, :B], dx1) < 1e-3
 
 
