@@ -257,7 +257,10 @@ def run_native(args):
         info.update(nfe=st2["nfe"], nf_bwd=sol.bwd_stats.nf_bwd, reg=float(st2["reg_val"]),
                     naccept=sol.stats.naccept, nreject=sol.stats.nreject,
                     nacc_b=sol.bwd_stats.naccept_bwd, nrej_b=sol.bwd_stats.nreject_bwd,
-                    loss=float(loss.value) + W_REG * float(st2["reg_val"]), retcode=sol.retcode)
+                    loss=float(loss.value) + W_REG * float(st2["reg_val"]), retcode=sol.retcode,
+                    phases_us=dict(fwd_solve=sol.stats.reserved[0], saves=sol.stats.reserved[1],
+                                   reg_step=sol.stats.reserved[2], adjoint=sol.bwd_stats.reserved[3],
+                                   reg_pullback=sol.bwd_stats.reserved[4]))
         sol.free()
         return st2
 
@@ -348,7 +351,7 @@ def run_native(args):
             "nfe_per_s": nfe_sum / (ms_total / 1e3) * world, "nfe_per_step": fwd_info["nfe"],
             "nf_bwd_per_step": fwd_info["nf_bwd"], "steps_fwd": [fwd_info["naccept"], fwd_info["nreject"]],
             "steps_bwd": [fwd_info["nacc_b"], fwd_info["nrej_b"]], "loss": fwd_info["loss"],
-            "retcode": fwd_info["retcode"],
+            "retcode": fwd_info["retcode"], "phases_us": fwd_info["phases_us"],
             "e2e": e2e, "gpu_launches": int(n_launch), "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
         }
         print(json.dumps(line))

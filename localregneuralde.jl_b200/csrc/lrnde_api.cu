@@ -10,6 +10,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <functional>
 #include <memory>
@@ -40,6 +41,11 @@ extern "C" int lrnde_version(void) { return 100; }
     return LRNDE_ENOMEM;                               \
   }                                                    \
   return LRNDE_OK;
+
+static inline long lr_now_us() {
+  return (long)std::chrono::duration_cast<std::chrono::microseconds>(
+             std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 
 static void lr_fail(int code, const char* fmt, ...) {
   va_list ap;
@@ -396,16 +402,41 @@ struct MlpEval {
     return p;
   }
 
-  // in->dst <- f(lincomb(in), ps, in->t)
-  void forward(const LinComb* in, const int* done) {
+  // (out ? out : in)->dst <- f(lincomb(in), ps, in->t); when side_to_in_dst the combined input
+  // itself is also written to in->dst (u_{n+1} of the step, fused into stage 7's prologue)
+  void forward(const LinComb* in, const int* done, const LinComb* out = nullptr,
+               bool side_to_in_dst = false) {
     const int L = (int)m->layers.size();
     for (int l = 0; l < L; ++l) {
       DenseP p = layer_fwd(l, in, nullptr);
-      if (l == L - 1) { p.ydesc = in; p.y_off = 0; } else p.Y = act[l];
+      if (l == L - 1) { p.ydesc = out ? out : in; p.y_off = 0; } else p.Y = act[l];
+      if (l == 0 && side_to_in_dst) p.side_desc = in;
       p.done = done;
       dense(p, use_umma ? packW[l] : nullptr);
     }
     LR_CHECK_LAUNCH();
+  }
+
+  // data-gradient GEMM of layer l: g_{l-1} = W_l[:, :in]^T delta_l (times act'_{l-1}, or the final
+  // scaled output when l == 0)
+  DenseP data_gemm(int l, int cur, float* out_a, const LinComb* out_desc, float a_scale, const int* done) const {
+    const LayerInfo& Li = m->layers[l];
+    DenseP p;
+    memset(&p, 0, sizeof(p));
+    p.A = WT[l]; p.lda = Li.in; p.M = Li.in; p.K = Li.out; p.td = 0; p.bias = 0;
+    p.X = delta[cur]; p.ldx = Li.out; p.N = (int)B;
+    p.ldy = Li.in; p.act = ACT_IDENTITY; p.dact = -1; p.out_scale = 1.0f; p.done = done;
+    if (l > 0) {
+      p.Y = delta[cur ^ 1];
+      if (m->layers[l - 1].act != ACT_IDENTITY) {
+        p.dact = m->layers[l - 1].act; p.dpre = pre[l - 1]; p.lddpre = Li.in;
+      }
+    } else {
+      if (out_a) p.Y = out_a; else { p.ydesc = out_desc; p.y_off = 0; }
+      if (m->input_act != ACT_IDENTITY) { p.dact = m->input_act; p.dpre = ybuf; p.lddpre = Li.in; }
+      p.out_scale = a_scale;
+    }
+    return p;
   }
 
   // (a, dps) = (J_u^T lam, J_p^T lam) of f at (lincomb(y), y->t), lam = lincomb(lamd) over D*B.
@@ -417,25 +448,38 @@ struct MlpEval {
     const int L = (int)m->layers.size();
     const size_t DB = (size_t)m->D * B;
     cudaStream_t st = ctx->stream;
-    lincomb_kernel<<<lr_ew_blocks(DB), 256, 0, st>>>(y, ybuf, DB, done);
-    LR_COUNT(ctx);
     const bool last_identity = (m->layers[L - 1].act == ACT_IDENTITY);
+    const bool fwd_runs = !(L == 1 && last_identity);
+    if (!fwd_runs) {  // nothing will form y(t) in a prologue: materialise it
+      lincomb_kernel<<<lr_ew_blocks(DB), 256, 0, st>>>(y, ybuf, DB, done);
+      LR_COUNT(ctx);
+    }
     for (int l = 0; l < L; ++l) {
       if (l == L - 1 && last_identity) break;  // output itself is not needed
-      DenseP p = layer_fwd(l, y, ybuf);
+      DenseP p = layer_fwd(l, y, nullptr);
+      if (l == 0) p.side = ybuf;               // y(t) formed in the prologue, kept for dW_1 and act'
       p.Y = act[l];
       p.pre = pre[l];
       p.done = done;
       dense(p, use_umma ? packW[l] : nullptr);
     }
-    if (last_identity) lincomb_kernel<<<lr_ew_blocks(DB), 256, 0, st>>>(lamd, delta[0], DB, done);
-    else dact_mul_kernel<<<lr_ew_blocks(DB), 256, 0, st>>>(lamd, pre[L - 1], m->layers[L - 1].act,
-                                                            delta[0], DB, done);
-    LR_COUNT(ctx);
+    if (!last_identity) {
+      dact_mul_kernel<<<lr_ew_blocks(DB), 256, 0, st>>>(lamd, pre[L - 1], m->layers[L - 1].act, delta[0], DB,
+                                                         done);
+      LR_COUNT(ctx);
+    }
     int cur = 0;
     for (int l = L - 1; l >= 0; --l) {
       const LayerInfo& Li = m->layers[l];
       const int naug = Li.in + m->td + 1;
+      // identity output layer: delta_L is the lincomb lambda_g itself; the data-gradient GEMM
+      // of that layer forms it in its prologue and keeps a copy (delta[0]) for dW_L
+      const bool lam_in_prologue = (l == L - 1) && last_identity;
+      if (lam_in_prologue) {
+        DenseP p = data_gemm(l, cur, out_a, out_desc, a_scale, done);
+        p.X = nullptr; p.xdesc = lamd; p.side = delta[0];
+        dense(p, use_umma ? packWT[l] : nullptr);
+      }
       WgradP w;
       memset(&w, 0, sizeof(w));
       w.Dl = delta[cur]; w.ldd = Li.out; w.M = Li.out;
@@ -450,22 +494,10 @@ struct MlpEval {
           part, wS[l], nw, dps_ptr ? dps_ptr + Li.w_off : nullptr, dps_desc,
           dps_off + (size_t)Li.w_off, p_scale, p_beta, done);
       LR_COUNT(ctx);
-      DenseP p;
-      memset(&p, 0, sizeof(p));
-      p.A = WT[l]; p.lda = Li.in; p.M = Li.in; p.K = Li.out; p.td = 0; p.bias = 0;
-      p.X = delta[cur]; p.ldx = Li.out; p.N = (int)B;
-      p.ldy = Li.in; p.act = ACT_IDENTITY; p.dact = -1; p.out_scale = 1.0f; p.done = done;
-      if (l > 0) {
-        p.Y = delta[cur ^ 1];
-        if (m->layers[l - 1].act != ACT_IDENTITY) {
-          p.dact = m->layers[l - 1].act; p.dpre = pre[l - 1]; p.lddpre = Li.in;
-        }
-      } else {
-        if (out_a) p.Y = out_a; else { p.ydesc = out_desc; p.y_off = 0; }
-        if (m->input_act != ACT_IDENTITY) { p.dact = m->input_act; p.dpre = ybuf; p.lddpre = Li.in; }
-        p.out_scale = a_scale;
+      if (!lam_in_prologue) {
+        DenseP p = data_gemm(l, cur, out_a, out_desc, a_scale, done);
+        dense(p, use_umma ? packWT[l] : nullptr);
       }
-      dense(p, use_umma ? packWT[l] : nullptr);
       cur ^= 1;
     }
     LR_CHECK_LAUNCH();
@@ -723,13 +755,13 @@ static void lr_solver_start(Solver& S, EvalFn&& eval, int begin) {
   cudaStream_t st = ctx->stream;
   k1_desc_kernel<<<1, 32, 0, st>>>(S.dev);
   LR_COUNT(ctx);
-  eval(&S.dev->st[6], &S.dev->yint[6], &S.dev->failed);
+  eval(&S.dev->st[6], &S.dev->yint[6], &S.dev->failed, nullptr, false);
   initdt_norm1_kernel<<<LR_ERR_BLOCKS, 256, 0, st>>>(S.dev);
   LR_COUNT(ctx);
   lr_mu_exchange(S, 0, 1, &S.dev->failed);
   initdt_a_kernel<<<1, 32, 0, st>>>(S.dev);
   LR_COUNT(ctx);
-  eval(&S.dev->st[0], &S.dev->yint[1], &S.dev->failed);
+  eval(&S.dev->st[0], &S.dev->yint[1], &S.dev->failed, nullptr, false);
   initdt_norm2_kernel<<<LR_ERR_BLOCKS, 256, 0, st>>>(S.dev);
   LR_COUNT(ctx);
   lr_mu_exchange(S, 1, 1, &S.dev->failed);
@@ -740,13 +772,19 @@ static void lr_solver_start(Solver& S, EvalFn&& eval, int begin) {
 
 // the kernels of one step attempt (perform_step! + loopfooter! + next loopheader!)
 template <class EvalFn>
-static void lr_step_body(Solver& S, EvalFn&& eval) {
+static void lr_step_body(Solver& S, EvalFn&& eval, bool fuse_unew = false) {
   lrnde_ctx* ctx = S.ctx;
   cudaStream_t st = ctx->stream;
-  for (int j = 0; j < 5; ++j) eval(&S.dev->st[j], &S.dev->yint[j + 1], &S.dev->done);
-  lincomb_kernel<<<lr_ew_blocks(S.h.len), 256, 0, st>>>(&S.dev->st[5], nullptr, S.h.len, &S.dev->done);
-  LR_COUNT(ctx);
-  eval(&S.dev->st[6], &S.dev->yint[6], &S.dev->done);
+  for (int j = 0; j < 5; ++j) eval(&S.dev->st[j], &S.dev->yint[j + 1], &S.dev->done, nullptr, false);
+  if (fuse_unew) {
+    // u_{n+1} = uprev + dt * sum a_7i k_i is formed in the prologue of stage 7's first GEMM and
+    // stored from there (perform_step.jl:18-19 in one kernel)
+    eval(&S.dev->st[5], &S.dev->yint[6], &S.dev->done, &S.dev->st[6], true);
+  } else {
+    lincomb_kernel<<<lr_ew_blocks(S.h.len), 256, 0, st>>>(&S.dev->st[5], nullptr, S.h.len, &S.dev->done);
+    LR_COUNT(ctx);
+    eval(&S.dev->st[6], &S.dev->yint[6], &S.dev->done, nullptr, false);
+  }
   err_norm_kernel<<<LR_ERR_BLOCKS, 256, 0, st>>>(S.dev);
   LR_COUNT(ctx);
   lr_mu_exchange(S, 2, 3, &S.dev->done);
@@ -922,10 +960,13 @@ extern "C" int lrnde_ode_forward(lrnde_ctx* ctx, const lrnde_model* m, const lrn
   const bool need_vjp = false;
   MlpEval ev(ctx, m, T->ps, B, o->precision, need_vjp);
   ev.prepare();
-  auto eval = [&](const LinComb* in, const LinComb*, const int* done) { ev.forward(in, done); };
-  F.body = [&]() { lr_step_body(F, eval); };
+  auto eval = [&](const LinComb* in, const LinComb*, const int* done, const LinComb* out, bool side) {
+    ev.forward(in, done, out, side);
+  };
+  F.body = [&]() { lr_step_body(F, eval, /*fuse_unew=*/true); };
   F.build_graphs(o->loop_mode);
   F.upload();
+  const long t_start = lr_now_us();
   lr_solver_start(F, eval, 1);
   for (;;) {
     F.run_segment();
@@ -939,6 +980,7 @@ extern "C" int lrnde_ode_forward(lrnde_ctx* ctx, const lrnde_model* m, const lrn
     segment_begin_kernel<<<1, 32, 0, st>>>(F.dev, 0.0f, 0);
     LR_COUNT(ctx);
   }
+  const long t_solve = lr_now_us();
   const int naccept = F.h.c.naccept, nreject = F.h.c.nreject;
   T->fts.resize(naccept + 1);
   LR_CUDA(cudaMemcpyAsync(T->fts.data(), F.ts, sizeof(float) * (naccept + 1), cudaMemcpyDeviceToHost, st));
@@ -1006,6 +1048,7 @@ extern "C" int lrnde_ode_forward(lrnde_ctx* ctx, const lrnde_model* m, const lrn
   T->save_out = out_index;
   T->t1 = t1;
 
+  const long t_saves = lr_now_us();
   // ---- local regulariser: integrator at t1 + one differentiable step (neural_ode.jl:75-78)
   int nf_reg = 0;
   float reg_val = 0.0f, dt_reg = 0.0f;
@@ -1021,10 +1064,8 @@ extern "C" int lrnde_ode_forward(lrnde_ctx* ctx, const lrnde_model* m, const lrn
     lincomb_kernel<<<lr_ew_blocks(DB), 256, 0, st>>>((const LinComb*)dd.p, R.tape, DB, nullptr);
     LR_COUNT(ctx);
     lr_solver_start(R, eval, 0);
-    for (int j = 0; j < 5; ++j) eval(&R.dev->st[j], nullptr, &R.dev->failed);
-    lincomb_kernel<<<lr_ew_blocks(DB), 256, 0, st>>>(&R.dev->st[5], nullptr, DB, &R.dev->failed);
-    LR_COUNT(ctx);
-    eval(&R.dev->st[6], nullptr, &R.dev->failed);
+    for (int j = 0; j < 5; ++j) eval(&R.dev->st[j], nullptr, &R.dev->failed, nullptr, false);
+    eval(&R.dev->st[5], nullptr, &R.dev->failed, &R.dev->st[6], true);   // u and k7 in one pass
     err_norm_kernel<<<LR_ERR_BLOCKS, 256, 0, st>>>(R.dev);
     LR_COUNT(ctx);
     if (o->reg_type == LRNDE_REGTYPE_STIFFNESS) {
@@ -1049,6 +1090,10 @@ extern "C" int lrnde_ode_forward(lrnde_ctx* ctx, const lrnde_model* m, const lrn
   stats->dt_reg = dt_reg;
   stats->nsave_out = nout;
   stats->gpu_launches = (int)((ctx->launches - launches0) + F.body_nodes * (long)F.h.nlog);
+  // host wall-clock of the phases (each ends on a stream sync), microseconds: diagnostics
+  stats->reserved[0] = (int32_t)(t_solve - t_start);
+  stats->reserved[1] = (int32_t)(t_saves - t_solve);
+  stats->reserved[2] = (int32_t)(lr_now_us() - t_saves);
   if (o->keep_tape) *tape_out = T.release();
   else if (tape_out) *tape_out = nullptr;
   LR_API_END
@@ -1127,6 +1172,7 @@ extern "C" int lrnde_ode_backward(lrnde_ctx* ctx, const lrnde_model* m, lrnde_ta
   float* dx_dev = host ? out_dx.p : d_x;
   float* dps_dev = host ? out_dps.p : d_ps;
 
+  const long tb_start = lr_now_us();
   int nbwd_stops = 0;
   int retcode_bwd = 0, nacc_b = 0, nrej_b = 0;
   long body_launches = 0;
@@ -1151,7 +1197,7 @@ extern "C" int lrnde_ode_backward(lrnde_ctx* ctx, const lrnde_model* m, lrnde_ta
     std::sort(stops.begin(), stops.end(), [](float a, float b) { return a > b; });
     stops.push_back(t0);
     A.init_ctrl(t2, t0, stops[0], o.maxiters, o.pow_mode, o.abstol, o.reltol);
-    auto rhs = [&](const LinComb* in, const LinComb* y, const int* done) {
+    auto rhs = [&](const LinComb* in, const LinComb* y, const int* done, const LinComb*, bool) {
       ev.vjp(y, in, nullptr, in, -1.0f, nullptr, in, DB, -1.0f, 0.0f, done);
     };
     A.body = [&]() { lr_step_body(A, rhs); };
@@ -1176,7 +1222,7 @@ extern "C" int lrnde_ode_backward(lrnde_ctx* ctx, const lrnde_model* m, lrnde_ta
         }
         k1_desc_kernel<<<1, 32, 0, st>>>(A.dev);
         LR_COUNT(ctx);
-        rhs(&A.dev->st[6], &A.dev->yint[6], &A.dev->failed);
+        rhs(&A.dev->st[6], &A.dev->yint[6], &A.dev->failed, nullptr, false);
         segment_begin_kernel<<<1, 32, 0, st>>>(A.dev, stops[si + 1], 1);
         LR_COUNT(ctx);
         nbwd_stops++;
@@ -1203,6 +1249,7 @@ extern "C" int lrnde_ode_backward(lrnde_ctx* ctx, const lrnde_model* m, lrnde_ta
     LR_CUDA(cudaMemsetAsync(dps_dev, 0, sizeof(float) * P, st));
   }
 
+  const long tb_adj = lr_now_us();
   // ---- reverse pass of the regulariser step: gradient w.r.t. ps only
   if (T->reg && d_reg != 0.0f) {
     Solver& R = *T->reg;
@@ -1244,6 +1291,8 @@ extern "C" int lrnde_ode_backward(lrnde_ctx* ctx, const lrnde_model* m, lrnde_ta
     stats->nreject_bwd = nrej_b;
     stats->retcode_bwd = retcode_bwd;
     stats->gpu_launches = (int)((ctx->launches - launches0) + body_launches);
+    stats->reserved[3] = (int32_t)(tb_adj - tb_start);
+    stats->reserved[4] = (int32_t)(lr_now_us() - tb_adj);
   }
   LR_API_END
 }

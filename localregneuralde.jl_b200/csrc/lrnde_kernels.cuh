@@ -61,7 +61,8 @@ __device__ __forceinline__ float lr_lincomb_at(const LinComb& d, size_t i) {
 // ------------------------------------------------------------------------------------------
 struct DenseP {
   const float* A; long lda; int M; int K; int td; int bias;
-  const float* X; const LinComb* xdesc; long ldx; int N; int in_act; size_t xlimit;
+  const float* X; const LinComb* xdesc; long ldx; int N; int in_act;
+  float* side; const LinComb* side_desc;  // optional: also store the (pre-in_act) X tile, fp32
   float* Y; const LinComb* ydesc; long y_off; long ldy;
   float* pre; long ldpre;
   int act;
@@ -94,8 +95,9 @@ __global__ void __launch_bounds__(256) dense_nn_kernel(DenseP p) {
   }
   __syncthreads();
   const float tval = s_t;
+  float* side = p.side_desc ? p.side_desc->dst : p.side;
   const bool a_vec = ((((uintptr_t)p.A) & 15) == 0) && (p.lda % 4 == 0);
-  bool x_vec = (p.ldx % 4 == 0) && ((((uintptr_t)sdesc.base) & 15) == 0);
+  bool x_vec = (p.ldx % 4 == 0) && ((((uintptr_t)sdesc.base) & 15) == 0) && ((((uintptr_t)side) & 15) == 0);
   for (int k = 0; k < sdesc.n; ++k) x_vec = x_vec && ((((uintptr_t)sdesc.src[k]) & 15) == 0);
 
   float acc[8][4];
@@ -149,6 +151,8 @@ __global__ void __launch_bounds__(256) dense_nn_kernel(DenseP p) {
             rx[0] = fmaf(sdesc.scale, inner.x, b.x); rx[1] = fmaf(sdesc.scale, inner.y, b.y);
             rx[2] = fmaf(sdesc.scale, inner.z, b.z); rx[3] = fmaf(sdesc.scale, inner.w, b.w);
           } else { rx[0] = b.x; rx[1] = b.y; rx[2] = b.z; rx[3] = b.w; }
+          if (side && blockIdx.x == 0)
+            *reinterpret_cast<float4*>(side + off) = make_float4(rx[0], rx[1], rx[2], rx[3]);
           if (p.in_act) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) rx[e] = lr_act(p.in_act, rx[e]);
@@ -160,6 +164,7 @@ __global__ void __launch_bounds__(256) dense_nn_kernel(DenseP p) {
             float v = 0.0f;
             if (k < p.K) {
               v = lr_lincomb_at(sdesc, off + e);
+              if (side && blockIdx.x == 0) side[off + e] = v;
               if (p.in_act) v = lr_act(p.in_act, v);
             } else if (p.td && k == p.K) v = tval;
             else if (p.bias && k == p.K + p.td) v = 1.0f;
@@ -371,7 +376,8 @@ __global__ void wgrad_reduce_kernel(const float* part, int S, size_t n, float* d
 // ------------------------------------------------------------------------------------------
 // Elementwise
 // ------------------------------------------------------------------------------------------
-__global__ void lincomb_kernel(const LinComb* dp, float* dst, size_t n, const int* done) {
+// out[off + i] = lincomb(off + i), i < n   (dst == nullptr: out = descriptor's dst)
+__global__ void lincomb_kernel(const LinComb* dp, float* dst, size_t n, const int* done, size_t off = 0) {
   if (done && *done) return;
   __shared__ LinComb d;
   if (threadIdx.x == 0) d = *dp;
@@ -379,7 +385,7 @@ __global__ void lincomb_kernel(const LinComb* dp, float* dst, size_t n, const in
   float* out = dst ? dst : d.dst;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
        i += (size_t)gridDim.x * blockDim.x)
-    out[i] = lr_lincomb_at(d, i);
+    out[off + i] = lr_lincomb_at(d, off + i);
 }
 
 // out[i] = a[i] * act'(pre[i])

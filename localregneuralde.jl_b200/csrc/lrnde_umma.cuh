@@ -202,6 +202,7 @@ struct ProdCtx {
   int n0, nsrc, passes;
   bool vec;
   float tval;
+  float* side;  // optional fp32 copy of the combined tile (only the blockIdx.y == 0 CTAs write it)
 };
 
 template <int NS1>  // NS1 = 1 + number of lincomb sources held in registers
@@ -239,6 +240,7 @@ __device__ __forceinline__ void store_group(const ProdCtx& c, int row, int cch, 
         v[0] = fmaf(sd.scale, inner.x, buf[0].x); v[1] = fmaf(sd.scale, inner.y, buf[0].y);
         v[2] = fmaf(sd.scale, inner.z, buf[0].z); v[3] = fmaf(sd.scale, inner.w, buf[0].w);
       } else { v[0] = buf[0].x; v[1] = buf[0].y; v[2] = buf[0].z; v[3] = buf[0].w; }
+      if (c.side) *reinterpret_cast<float4*>(c.side + off) = make_float4(v[0], v[1], v[2], v[3]);
       if (p.in_act) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) v[e] = lr_act(p.in_act, v[e]);
@@ -249,6 +251,7 @@ __device__ __forceinline__ void store_group(const ProdCtx& c, int row, int cch, 
         const int kk = k + e;
         if (kk < p.K) {
           float x = lr_lincomb_at(sd, off + e);
+          if (c.side) c.side[off + e] = x;
           v[e] = p.in_act ? lr_act(p.in_act, x) : x;
         } else if (p.td && kk == p.K) v[e] = c.tval;
         else if (p.bias && kk == p.K + p.td) v[e] = 1.0f;
@@ -407,7 +410,8 @@ __global__ void __launch_bounds__(kThreads, 1) dense_kernel(UmmaP q) {
     const int tid = threadIdx.x - 64;
     ProdCtx pc;
     pc.p = &p; pc.sd = &sdesc; pc.n0 = n0; pc.nsrc = sdesc.n; pc.passes = q.passes; pc.tval = s_t;
-    pc.vec = (p.ldx % 4 == 0) && ((((uintptr_t)sdesc.base) & 15) == 0);
+    pc.side = (blockIdx.y == 0) ? (p.side_desc ? p.side_desc->dst : p.side) : nullptr;
+    pc.vec = (p.ldx % 4 == 0) && ((((uintptr_t)sdesc.base) & 15) == 0) && ((((uintptr_t)pc.side) & 15) == 0);
     for (int k = 0; k < sdesc.n; ++k) pc.vec = pc.vec && ((((uintptr_t)sdesc.src[k]) & 15) == 0);
 
     // software-pipelined producer: DEPTH chunks of loads in flight per thread, about 8 float4
