@@ -268,7 +268,8 @@ struct MlpEval {
   float* ybuf = nullptr;
   float* delta[2] = {nullptr, nullptr};
   float* part = nullptr;
-  std::vector<int> wS, wChunk;
+  std::vector<int> wS, wChunk;    // SIMT weight-gradient split
+  std::vector<int> uS, uChunk;    // tcgen05 weight-gradient split (0 = layer not eligible)
 
   MlpEval(lrnde_ctx* c, const lrnde_model* mm, const float* p, int64_t b, int precision, bool vjp)
       : ctx(c), m(mm), ps(p), B(b), prec(precision), with_vjp(vjp) {
@@ -307,6 +308,18 @@ struct MlpEval {
         wS.push_back(S);
         wChunk.push_back(chunk);
         maxpart = std::max(maxpart, (size_t)S * Li.out * naug);
+        // tensor-core version: the smaller operand must fit one 128-column accumulator
+        int us = 0, uc = 0;
+        if (use_umma && std::min(Li.out, naug) <= 128) {
+          int n_mt = (std::max(Li.out, naug) + 127) / 128;
+          us = std::max(1, std::min(64, 256 / n_mt));
+          uc = (int)((B + us - 1) / us);
+          uc = std::max(32, ((uc + 31) / 32) * 32);
+          us = (int)((B + uc - 1) / uc);
+          maxpart = std::max(maxpart, (size_t)us * Li.out * naug);
+        }
+        uS.push_back(us);
+        uChunk.push_back(uc);
       }
       ybuf = (float*)ctx->alloc(sizeof(float) * (size_t)m->D * B);
       delta[0] = (float*)ctx->alloc(sizeof(float) * maxd);
@@ -480,18 +493,46 @@ struct MlpEval {
         p.X = nullptr; p.xdesc = lamd; p.side = delta[0];
         dense(p, use_umma ? packWT[l] : nullptr);
       }
-      WgradP w;
-      memset(&w, 0, sizeof(w));
-      w.Dl = delta[cur]; w.ldd = Li.out; w.M = Li.out;
-      w.X = (l == 0) ? ybuf : act[l - 1]; w.ldx = Li.in; w.Nin = Li.in; w.td = m->td; w.bias = 1;
-      w.in_act = (l == 0) ? m->input_act : 0;
-      w.B = (int)B; w.chunk = wChunk[l]; w.part = part; w.tdesc = y; w.done = done;
-      dim3 g((Li.out + DN_BM - 1) / DN_BM, (naug + DN_BN - 1) / DN_BN, wS[l]);
-      wgrad_nt_kernel<<<g, 256, 0, st>>>(w);
-      LR_COUNT(ctx);
       const size_t nw = (size_t)Li.out * naug;
+      const float* xin = (l == 0) ? ybuf : act[l - 1];
+      const int xact = (l == 0) ? m->input_act : 0;
+      int nsplit;
+      if (uS[l] > 0) {
+        // dW_aug = delta [x;t;1]^T on the tensor cores (MN-major operands, 3xTF32)
+        static bool attr_set = false;
+        if (!attr_set) {
+          LR_CUDA(cudaFuncSetAttribute(umma::wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       umma::wgrad_smem()));
+          attr_set = true;
+        }
+        umma::WgradUP w;
+        memset(&w, 0, sizeof(w));
+        umma::WgOperand od = {delta[cur], Li.out, Li.out, 0, 0, 0};
+        umma::WgOperand ox = {xin, Li.in, Li.in, m->td, 1, xact};
+        const bool normal = Li.out >= naug;
+        w.P = normal ? od : ox;
+        w.Q = normal ? ox : od;
+        w.transposed = normal ? 0 : 1;
+        w.ldo = Li.out;
+        w.B = (int)B; w.chunk = uChunk[l]; w.part = part; w.block = nw; w.passes = passes;
+        w.tdesc = y; w.done = done;
+        dim3 g((std::max(Li.out, naug) + 127) / 128, uS[l]);
+        umma::wgrad_kernel<<<g, umma::kThreads, umma::wgrad_smem(), st>>>(w);
+        nsplit = uS[l];
+      } else {
+        WgradP w;
+        memset(&w, 0, sizeof(w));
+        w.Dl = delta[cur]; w.ldd = Li.out; w.M = Li.out;
+        w.X = xin; w.ldx = Li.in; w.Nin = Li.in; w.td = m->td; w.bias = 1;
+        w.in_act = xact;
+        w.B = (int)B; w.chunk = wChunk[l]; w.part = part; w.tdesc = y; w.done = done;
+        dim3 g((Li.out + DN_BM - 1) / DN_BM, (naug + DN_BN - 1) / DN_BN, wS[l]);
+        wgrad_nt_kernel<<<g, 256, 0, st>>>(w);
+        nsplit = wS[l];
+      }
+      LR_COUNT(ctx);
       wgrad_reduce_kernel<<<lr_ew_blocks(nw), 256, 0, st>>>(
-          part, wS[l], nw, dps_ptr ? dps_ptr + Li.w_off : nullptr, dps_desc,
+          part, nsplit, nw, dps_ptr ? dps_ptr + Li.w_off : nullptr, dps_desc,
           dps_off + (size_t)Li.w_off, p_scale, p_beta, done);
       LR_COUNT(ctx);
       if (!lam_in_prologue) {

@@ -539,4 +539,224 @@ __global__ void __launch_bounds__(kThreads, 1) dense_kernel(UmmaP q) {
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Weight gradient on the tensor cores:  part[z][..] = sum_{b in split z} P[:, b] * Q[:, b]^T
+// Both operands are activations stored feature-contiguous per sample ([rows, B] column-major),
+// i.e. MN-major for the MMA.  For tf32 the only MN-major shared-memory layout is
+// SWIZZLE_128B_BASE32B (cute Layout_MN_SW128_32B_Atom): atoms of 4 samples x 128 bytes (32 rows),
+// 32-byte chunks XOR-ed with the sample index (Swizzle<2,5,2>); LBO = stride between 32-row
+// groups, SBO = stride between 4-sample groups; the instruction descriptor carries
+// a_major = b_major = MN.  P = the operand with more rows
+// (128-row tiles on the TMEM lanes), Q = the other one (<= 128 rows).  One operand may be the
+// augmented layer input [x ; t ; 1] (TDChain time row, bias row) with an input activation.
+// ------------------------------------------------------------------------------------------
+struct WgOperand {
+  const float* ptr; long ld; int rows;  // rows read from memory
+  int td, bias, in_act;                 // extra generated rows (augmented input only)
+};
+struct WgradUP {
+  WgOperand P, Q;
+  int B, chunk;      // batch size, samples per split (multiple of 32)
+  int transposed;    // 0: out[m + n * ldo] ; 1: out[n + m * ldo]
+  int ldo;           // leading dimension of the [out x (in+2)] block
+  float* part;       // [S][block] partial sums
+  size_t block;      // floats per partial block
+  int passes;
+  const LinComb* tdesc;
+  const int* done;
+};
+constexpr int kWgStageBytes = 4 * 16384;  // [P_hi | P_lo | Q_hi | Q_lo]
+constexpr int kWgStages = 3;
+constexpr int wgrad_smem() { return kWgStages * kWgStageBytes + 1024; }
+__host__ __device__ constexpr uint32_t make_idesc_mn(int M, int N) {
+  return make_idesc(M, N) | (1u << 15) | (1u << 16);
+}
+// MN-major descriptor: atom (g, k4) of 512 B at ((k4 * 4 + g) * 512): LBO = 512 B between 32-row
+// groups, SBO = 2048 B between 4-sample groups, layout type 1 = SWIZZLE_128B_BASE32B
+constexpr uint32_t kDescHiMN = (2048u >> 4) | (1u << 14) | (1u << 29);
+__device__ __forceinline__ uint32_t desc_lo_mn(uint32_t saddr) { return ((saddr >> 4) & 0x3FFFu) | ((512u >> 4) << 16); }
+__device__ __forceinline__ void mma_tf32_mn(uint32_t d_tmem, uint32_t a_lo32, uint32_t b_lo32, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_lo32), "r"(b_lo32), "r"(idesc), "r"(accumulate), "r"(kDescHiMN)
+      : "memory");
+}
+
+__device__ __forceinline__ float4 wg_load(const WgOperand& o, int row, int b, bool valid, float tval, bool vec) {
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (!valid) return v;
+  const float* p = o.ptr + (size_t)b * o.ld + row;
+  if (vec && row + 3 < o.rows) {
+    v = *reinterpret_cast<const float4*>(p);
+    if (o.in_act) { v.x = lr_act(o.in_act, v.x); v.y = lr_act(o.in_act, v.y); v.z = lr_act(o.in_act, v.z); v.w = lr_act(o.in_act, v.w); }
+  } else {
+    float e[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int r = row + j;
+      float x = 0.0f;
+      if (r < o.rows) { x = p[j]; if (o.in_act) x = lr_act(o.in_act, x); }
+      else if (o.td && r == o.rows) x = tval;
+      else if (o.bias && r == o.rows + o.td) x = 1.0f;
+      e[j] = x;
+    }
+    v = make_float4(e[0], e[1], e[2], e[3]);
+  }
+  return v;
+}
+
+__global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(WgradUP q) {
+  if (q.done && *q.done) return;
+  constexpr int NS = kWgStages;
+  constexpr int PT = kProducerWarps * 32;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t full_bar[NS], empty_bar[NS], done_bar;
+  __shared__ uint32_t tmem_slot;
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * 128;
+  const int b_begin = blockIdx.y * q.chunk;
+  const int b_end = min(q.B, b_begin + q.chunk);
+  const int nchunks = (b_end - b_begin + 31) / 32;
+  const float tval = q.tdesc ? q.tdesc->t : 0.0f;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NS; ++s) {
+      mbar_init(&full_bar[s], (uint32_t)kProducerWarps);
+      mbar_init(&empty_bar[s], 1u);
+    }
+    mbar_init(&done_bar, 1u);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)),
+                 "r"(128u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 1) {
+    constexpr uint32_t idesc = make_idesc_mn(128, 128);
+    for (int it = 0; it < nchunks; ++it) {
+      const int s = it % NS, ph = (it / NS) & 1;
+      mbar_wait(&full_bar[s], ph);
+      tc_fence_after();
+      const uint32_t base = smem_u32(smem + (size_t)s * kWgStageBytes);
+      const uint32_t p_hi = desc_lo_mn(base), p_lo = desc_lo_mn(base + 16384);
+      const uint32_t q_hi = desc_lo_mn(base + 32768), q_lo = desc_lo_mn(base + 49152);
+      if (elect_one_sync()) {
+#pragma unroll
+        for (int kg = 0; kg < 4; ++kg) {
+          const uint32_t ko = (uint32_t)kg * (4096u >> 4);
+          const uint32_t first = (it == 0 && kg == 0) ? 0u : 1u;
+          if (q.passes == 3) {
+            mma_tf32_mn(tmem_base, p_lo + ko, q_hi + ko, idesc, first);
+            mma_tf32_mn(tmem_base, p_hi + ko, q_lo + ko, idesc, 1u);
+            mma_tf32_mn(tmem_base, p_hi + ko, q_hi + ko, idesc, 1u);
+          } else {
+            mma_tf32_mn(tmem_base, p_hi + ko, q_hi + ko, idesc, first);
+          }
+        }
+        mma_commit(&empty_bar[s]);
+        if (it == nchunks - 1) mma_commit(&done_bar);
+      }
+      __syncwarp();
+    }
+    if (nchunks == 0 && elect_one_sync()) mbar_arrive(&done_bar);
+  } else if (warp >= 2) {
+    const int tid = threadIdx.x - 64;
+    const bool pvec = ((((uintptr_t)q.P.ptr) & 15) == 0) && (q.P.ld % 4 == 0);
+    const bool qvec = ((((uintptr_t)q.Q.ptr) & 15) == 0) && (q.Q.ld % 4 == 0);
+    for (int it = 0; it < nchunks; ++it) {
+      const int s = it % NS, ph = (it / NS) & 1;
+      uint8_t* stage = smem + (size_t)s * kWgStageBytes;
+      float4 v[4];
+      // 2048 float4 groups per chunk: [0,1024) operand P, [1024,2048) operand Q; group = (sample
+      // bl, float4 index c4 along the rows) so that a warp reads 512 contiguous bytes of a sample
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int gi = tid + g * PT;
+        const bool isq = gi >= 1024;
+        const int li = gi & 1023;
+        const int bl = li >> 5, c4 = li & 31;
+        const int b = b_begin + it * 32 + bl;
+        if (!isq) v[g] = wg_load(q.P, m0 + c4 * 4, b, b < b_end, tval, pvec);
+        else v[g] = wg_load(q.Q, c4 * 4, b, b < b_end, tval, qvec);
+      }
+      mbar_wait(&empty_bar[s], ph ^ 1);
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int gi = tid + g * PT;
+        const bool isq = gi >= 1024;
+        const int li = gi & 1023;
+        const int bl = li >> 5, c4 = li & 31;
+        const int grp = c4 >> 3, c32 = (c4 & 7) >> 1, half = c4 & 1, k4 = bl >> 2, r = bl & 3;
+        const uint32_t o = (uint32_t)((k4 * 4 + grp) * 512 + r * 128 + ((c32 ^ r) << 5) + half * 16);
+        float4 hi, lo;
+        if (q.passes == 3) {
+          hi = make_float4(tf32_rna(v[g].x), tf32_rna(v[g].y), tf32_rna(v[g].z), tf32_rna(v[g].w));
+          lo = make_float4(tf32_rna(v[g].x - hi.x), tf32_rna(v[g].y - hi.y), tf32_rna(v[g].z - hi.z),
+                           tf32_rna(v[g].w - hi.w));
+        } else { hi = v[g]; lo = make_float4(0.f, 0.f, 0.f, 0.f); }
+        uint8_t* img = stage + (isq ? 32768 : 0);
+        *reinterpret_cast<float4*>(img + o) = hi;
+        *reinterpret_cast<float4*>(img + 16384 + o) = lo;
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full_bar[s]);
+    }
+    // epilogue: lane = row of P's tile, 128 columns = rows of Q
+    mbar_wait(&done_bar, 0);
+    tc_fence_after();
+    const int quarter = (warp & 3) * 32;
+    const int wgroup = (warp - 2) >> 2;
+    const int m = m0 + quarter + lane;
+    const int mrows = q.P.rows + q.P.td + q.P.bias;
+    const int nrows = q.Q.rows + q.Q.td + q.Q.bias;
+    float* out = q.part + (size_t)blockIdx.y * q.block;
+    for (int cb = wgroup; cb < 8; cb += kProducerWarps / 4) {
+      const int c0 = cb * 16;
+      uint32_t r[16];
+      const uint32_t taddr = tmem_base + ((uint32_t)quarter << 16) + (uint32_t)c0;
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, "
+          "%13, %14, %15}, [%16];\n\t"
+          "tcgen05.wait::ld.sync.aligned;"
+          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+            "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+          : "r"(taddr)
+          : "memory");
+      if (m < mrows) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int n = c0 + j;
+          if (n < nrows) {
+            const float val = (nchunks > 0) ? __uint_as_float(r[j]) : 0.0f;
+            if (q.transposed) out[(size_t)m * q.ldo + n] = val;
+            else out[(size_t)n * q.ldo + m] = val;
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128u) : "memory");
+  }
+}
+
 }  // namespace umma
