@@ -7,6 +7,7 @@
 // host only sequences launches and never waits inside a solve.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -264,6 +265,7 @@ struct MlpEval {
   std::vector<float*> WT;   // [in_l x out_l] (vjp only)
   std::vector<float*> packW, packWT;  // tcgen05 path: tf32 hi/lo shared-memory images of the weights
   bool use_umma = false;
+  bool use_cluster = true;
   int passes = 3;
   float* ybuf = nullptr;
   float* delta[2] = {nullptr, nullptr};
@@ -275,6 +277,7 @@ struct MlpEval {
       : ctx(c), m(mm), ps(p), B(b), prec(precision), with_vjp(vjp) {
     const int L = (int)m->layers.size();
     use_umma = (precision != LRNDE_PREC_FP32_SIMT);
+    use_cluster = (getenv("LRNDE_NO_CLUSTER") == nullptr);
     passes = (precision == LRNDE_PREC_TF32) ? 1 : 3;
     act.assign(L, nullptr);
     packW.assign(L, nullptr);
@@ -375,13 +378,14 @@ struct MlpEval {
       return;
     }
     constexpr int NT = 64;
+    constexpr int CL = 4;
     using C = umma::Cfg<NT>;
     static bool attr_set = false;
     if (!attr_set) {
-      LR_CUDA(cudaFuncSetAttribute(umma::dense_kernel<NT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   C::ring_smem()));
-      LR_CUDA(cudaFuncSetAttribute(umma::dense_kernel<NT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   C::res_smem(C::kMaxResKC)));
+      LR_CUDA(cudaFuncSetAttribute(umma::dense_kernel<NT, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::ring_smem()));
+      LR_CUDA(cudaFuncSetAttribute(umma::dense_kernel<NT, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::res_smem(C::kMaxResKC)));
+      LR_CUDA(cudaFuncSetAttribute(umma::dense_kernel<NT, false, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::ring_smem()));
+      LR_CUDA(cudaFuncSetAttribute(umma::dense_kernel<NT, true, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::res_smem(C::kMaxResKC)));
       attr_set = true;
     }
     umma::UmmaP q;
@@ -391,11 +395,29 @@ struct MlpEval {
     q.KC = chunks_k(p.K + p.td + p.bias);
     q.passes = passes;
     q.replicas = umma::kReplicas;
-    const unsigned ntile = (unsigned)((p.N + NT - 1) / NT);
-    if (q.n_mt > 1 && q.n_mt * NT <= 512 && q.KC <= C::kMaxResKC) {
-      umma::dense_kernel<NT, true><<<dim3(ntile), umma::kThreads, C::res_smem(q.KC), ctx->stream>>>(q);
+    unsigned ntile = (unsigned)((p.N + NT - 1) / NT);
+    const bool resident = q.n_mt > 1 && q.n_mt * NT <= 512 && q.KC <= C::kMaxResKC;
+    const bool cluster = ntile >= (unsigned)CL && use_cluster;
+    if (cluster) ntile = ((ntile + CL - 1) / CL) * CL;  // padded CTAs produce zeros and store nothing
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = resident ? dim3(ntile) : dim3(ntile, q.n_mt);
+    cfg.blockDim = dim3(umma::kThreads);
+    cfg.dynamicSmemBytes = resident ? C::res_smem(q.KC) : C::ring_smem();
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = cluster ? CL : 1;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    if (resident) {
+      if (cluster) LR_CUDA(cudaLaunchKernelEx(&cfg, umma::dense_kernel<NT, true, CL>, q));
+      else LR_CUDA(cudaLaunchKernelEx(&cfg, umma::dense_kernel<NT, true, 1>, q));
     } else {
-      umma::dense_kernel<NT, false><<<dim3(ntile, q.n_mt), umma::kThreads, C::ring_smem(), ctx->stream>>>(q);
+      if (cluster) LR_CUDA(cudaLaunchKernelEx(&cfg, umma::dense_kernel<NT, false, CL>, q));
+      else LR_CUDA(cudaLaunchKernelEx(&cfg, umma::dense_kernel<NT, false, 1>, q));
     }
     LR_COUNT(ctx);
   }

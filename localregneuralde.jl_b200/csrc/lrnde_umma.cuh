@@ -32,7 +32,7 @@
 
 #ifdef LRNDE_UMMA_TRACE
 __device__ long long g_umma_trace[8192];
-#define UMMA_TRACE(slot, it) do { if (blockIdx.x == 1 && blockIdx.y == 0 && (it) < 64) g_umma_trace[(slot) * 64 + (it)] = clock64(); } while (0)
+#define UMMA_TRACE(slot, it) do { if (blockIdx.x == 1 && blockIdx.y == 0 && (it) < 64) g_umma_trace[(RESIDENT ? 512 : 0) + (slot) * 64 + (it)] = clock64(); } while (0)
 #else
 #define UMMA_TRACE(slot, it) do { } while (0)
 #endif
@@ -78,6 +78,23 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
                    smem_u32(smem_dst)),
                "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
+}
+// multicast variants (thread-block cluster): the copy lands at the same shared-memory offset of
+// every CTA in ctaMask and signals the mbarrier at the same offset there
+__device__ __forceinline__ void bulk_g2s_mc(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar,
+                                            uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+      ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -138,6 +155,12 @@ __device__ __forceinline__ void mma_tf32_lo(uint32_t d_tmem, uint32_t a_lo32, ui
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
+}
+__device__ __forceinline__ void mma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(smem_u32(bar)), "h"(mask)
+      : "memory");
 }
 __device__ __forceinline__ float tf32_rna(float x) {
   uint32_t r;
@@ -271,10 +294,15 @@ __device__ __forceinline__ void store_group(const ProdCtx& c, int row, int cch, 
   *reinterpret_cast<float4*>(dst + NT * 128 + o) = lo;
 }
 
-template <int NT, bool RESIDENT>
+// CL = thread-block cluster size along the sample tiles (1 or 4): the CTAs of a cluster read the
+// same weight chunks, so each loads a 1/CL slice and multicasts it to all of them (L2 -> SM
+// traffic of the weight images / CL); stages are released cluster-wide by multicast commits.
+template <int NT, bool RESIDENT, int CL>
 __global__ void __launch_bounds__(kThreads, 1) dense_kernel(UmmaP q) {
   const DenseP& p = q.d;
   if (p.done && *p.done) return;
+  const uint32_t crank = (CL > 1) ? cluster_ctarank() : 0u;
+  constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1u);
   using C = Cfg<NT>;
   constexpr int NS = RESIDENT ? C::kResStages : C::kRingStages;
   constexpr int PT = kProducerWarps * 32;  // producer / epilogue threads
@@ -282,7 +310,7 @@ __global__ void __launch_bounds__(kThreads, 1) dense_kernel(UmmaP q) {
   static_assert(NT * 8 % PT == 0 && GPT >= 1, "producer mapping");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  __shared__ uint64_t full_bar[8], empty_bar[8], tile_bar[8], bres_bar;
+  __shared__ uint64_t full_bar[8], empty_bar[8], bempty_bar[8], tile_bar[8], bres_bar;
   __shared__ uint32_t tmem_slot;
   __shared__ LinComb sdesc;
   __shared__ float s_t;
@@ -301,8 +329,9 @@ __global__ void __launch_bounds__(kThreads, 1) dense_kernel(UmmaP q) {
   // chunk order rotated per CTA (accumulation order is free): de-synchronises the CTAs.
   // RESIDENT rotates whole weight tiles so that tiles finish one after the other and the
   // epilogue of a finished tile overlaps the MMAs of the next.
-  const int rot = RESIDENT ? (int)((blockIdx.x * 3u) % (unsigned)mt_count) * KC
-                           : (int)((blockIdx.x * 7u + blockIdx.y * 3u) % (unsigned)nchunks);
+  const unsigned cid = blockIdx.x / CL;  // identical order inside a cluster
+  const int rot = RESIDENT ? (int)((cid * 3u) % (unsigned)mt_count) * KC
+                           : (int)((cid * 7u + blockIdx.y * 3u) % (unsigned)nchunks);
 
   auto a_stage = [&](int s) -> uint8_t* {
     return RESIDENT ? smem + (size_t)s * kAChunkBytes : smem + (size_t)s * C::kRingStage;
@@ -315,7 +344,8 @@ __global__ void __launch_bounds__(kThreads, 1) dense_kernel(UmmaP q) {
   if (threadIdx.x == 0) {
     for (int s = 0; s < NS; ++s) {
       mbar_init(&full_bar[s], RESIDENT ? 1u : (uint32_t)(kProducerWarps + 1));  // one arrival per warp
-      mbar_init(&empty_bar[s], 1u);
+      mbar_init(&empty_bar[s], (uint32_t)CL);  // weight stage free in every CTA of the cluster
+      mbar_init(&bempty_bar[s], 1u);           // activation stage (local)
     }
     for (int t = 0; t < 8; ++t) mbar_init(&tile_bar[t], 1u);
     mbar_init(&bres_bar, (uint32_t)kProducerWarps);
@@ -334,6 +364,7 @@ __global__ void __launch_bounds__(kThreads, 1) dense_kernel(UmmaP q) {
   }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();  // every CTA's barriers are initialised before any remote arrive
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
   if (threadIdx.x == 0) UMMA_TRACE(7, 0);
@@ -341,7 +372,7 @@ __global__ void __launch_bounds__(kThreads, 1) dense_kernel(UmmaP q) {
   if (warp == 0) {
     // ------------------------------------------------ weight images: bulk copies onto the ring
     // (converged warp + one elected lane, same reason as the MMA warp)
-    const float* src = q.Apack + (size_t)(blockIdx.x % q.replicas) * q.n_mt * KC * (2 * kAChunkFloats);
+    const float* src = q.Apack + (size_t)(cid % q.replicas) * q.n_mt * KC * (2 * kAChunkFloats);
     for (int it = 0; it < nchunks; ++it) {
       const int s = it % NS, ph = (it / NS) & 1;
       const int j = (it + rot) % nchunks;
@@ -352,10 +383,15 @@ __global__ void __launch_bounds__(kThreads, 1) dense_kernel(UmmaP q) {
       if (elect_one_sync()) {
         UMMA_TRACE(0, it);
         mbar_arrive_expect_tx(&full_bar[s], kAChunkBytes);
+        if (CL > 1) {
+          constexpr uint32_t slice = kAChunkBytes / CL;
+          bulk_g2s_mc(d + crank * slice, g + crank * slice, slice, &full_bar[s], kMask);
+        } else {
 #pragma unroll
-        for (int part = 0; part < kBulkParts; ++part)
-          bulk_g2s(d + part * (kAChunkBytes / kBulkParts), g + part * (kAChunkBytes / kBulkParts),
-                   kAChunkBytes / kBulkParts, &full_bar[s]);
+          for (int part = 0; part < kBulkParts; ++part)
+            bulk_g2s(d + part * (kAChunkBytes / kBulkParts), g + part * (kAChunkBytes / kBulkParts),
+                     kAChunkBytes / kBulkParts, &full_bar[s]);
+        }
       }
       __syncwarp();
     }
@@ -399,7 +435,10 @@ __global__ void __launch_bounds__(kThreads, 1) dense_kernel(UmmaP q) {
             mma_tf32_lo(d, a_hi + ko, b_hi + ko, idesc, first);
           }
         }
-        mma_commit(&empty_bar[s]);  // frees the stage once these MMAs have read it
+        // frees the stage once these MMAs have read it: weights cluster-wide, activations locally
+        if (CL > 1) mma_commit_mc(&empty_bar[s], kMask);
+        else mma_commit(&empty_bar[s]);
+        if (!RESIDENT) mma_commit(&bempty_bar[s]);
         if (group_end) mma_commit(&tile_bar[RESIDENT ? mi : 0]);  // accumulator(s) complete
         UMMA_TRACE(2, it);
       }
@@ -438,7 +477,7 @@ __global__ void __launch_bounds__(kThreads, 1) dense_kernel(UmmaP q) {
           if (it < total) {
             const int s = it % NS, ph = (it / NS) & 1;
             uint8_t* dst = RESIDENT ? b_slot(it) : b_slot(s);
-            if (!RESIDENT) mbar_wait(&empty_bar[s], ph ^ 1);
+            if (!RESIDENT) mbar_wait(&bempty_bar[s], ph ^ 1);
             if (tid == 0) UMMA_TRACE(3, it);
 #pragma unroll
             for (int g = 0; g < GPT; ++g) {
@@ -532,6 +571,7 @@ __global__ void __launch_bounds__(kThreads, 1) dense_kernel(UmmaP q) {
     if (tid == 0) UMMA_TRACE(6, 2);
   }
   __syncthreads();
+  if (CL > 1) cluster_sync_all();  // nobody exits while peers may still signal its barriers
   if (threadIdx.x == 0) UMMA_TRACE(6, 3);
   if (warp == 1) {
     tc_fence_after();

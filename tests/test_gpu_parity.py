@@ -341,6 +341,42 @@ def test_full_size_batch_replication_property(pkg, prec):
     assert rel(dx2[:, :B], dx1) < 1e-3
 
 
+@pytest.mark.parametrize("prec", PRECS)
+def test_physionet_latent_ode_shape(pkg, prec):
+    """BASELINE configs[2] shape on the path: the latent-ODE decoder dynamics
+    (experiments/src/construct.jl:235-243: tanh.(u) then 8 x Dense(20<->40, tanh), not time
+    dependent), 49 observation times as saveat, batch 256, unbiased regulariser; cotangents
+    arrive at every saved time (49 lambda jumps in the adjoint).  Weights x2 keep the case
+    truncation-dominated so the oracle comparison is meaningful."""
+    layers = [(20, 40, "tanh"), (40, 20, "tanh")] * 4
+    om = _omodel(layers, False, "tanh")
+    rng = np.random.default_rng(5)
+    ps = (orc.glorot_uniform_params(om, rng) * 2 + 0.05 * rng.standard_normal(om.nparams)).astype(np.float32)
+    B = 256
+    x = rng.standard_normal((20, B)).astype(np.float32)
+    saveat = np.sort(np.concatenate([[0.0], rng.uniform(0.02, 1.0, 47), [1.0]])).astype(np.float32)
+    kw = dict(regularize="unbiased", abstol=1e-4, reltol=1e-4, maxiters=10000, saveat=list(saveat))
+    node = pkg.NeuralODE(_chain(pkg, layers, False, "tanh"), precision=prec, **kw)
+    on = orc.NeuralODE(om, **kw)
+    st = node.initialstates(np.random.default_rng(2))
+    sol, st2 = node(x, ps, st)
+    osol, ost2, aux = on.forward(x, ps, on.initialstates(np.random.default_rng(2)))
+    assert len(sol.u) == 49 and np.allclose(np.array(sol.t), saveat)
+    ts = pkg.diffeqsol_to_timeseries(sol)
+    assert ts.shape == (20, 49, B)                                  # src/utils.jl:43-45
+    assert st2["nfe"] == ost2["nfe"]
+    for i in (0, 1, 17, 48):
+        assert rel(sol.u[i], osol.u[i]) < 1e-4
+    assert abs(float(st2["reg_val"]) / float(ost2["reg_val"]) - 1) < (1e-3 if prec == "fp32" else 2e-2)
+    cots = [(rng.standard_normal((20, B)) / B).astype(np.float32) for _ in range(49)]
+    d_x, d_ps = node.backward(sol, cots, 0.0)
+    o_dx, o_dps = on.backward(aux, cots, 0.0, ps)
+    assert rel(d_x, o_dx) < 1e-3 and rel(d_ps, o_dps) < 1e-3
+    bt, bdt, bee, bacc = sol.step_log(1)
+    for s in saveat[1:-1]:
+        assert np.any(np.abs(bt + bdt - s) < 1e-6) or np.any(np.abs(bt - s) < 1e-6)   # jumps are tstops
+
+
 # ------------------------------------------------------------------ SOSRI step + head
 def test_sosri_step_matches_oracle(pkg):
     import ctypes as C
