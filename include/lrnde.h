@@ -166,6 +166,67 @@ int lrnde_sosri_step(lrnde_ctx* ctx, const lrnde_model* drift, const lrnde_model
                      const float* uprev, const float* dW, const float* dZ, float t, float dt,
                      float delta, int64_t B, float* u, float* reg_val);
 
+/* ---------------------------------------------------------------------------------------
+ * Neural SDE (diagonal noise): replaces (n::NeuralDSDE)(x, ps, st), src/layers/neural_sde.jl:82-123
+ *   lrnde_sde_forward   solve(SDEProblem(dudt, g, x, tspan, ps), SOSRI(); saveat, maxiters, abstol,
+ *                       reltol) (neural_sde.jl:44-72) + _get_dsde_integrator (:35-40) +
+ *                       _perform_step(::FourStageSRIConstantCache) (src/perform_step.jl:49-106)
+ *   lrnde_sde_backward  the TrackerAdjoint pullback selected at neural_sde.jl:12
+ * drift / diffusion: two lrnde_model over the same state (ps.drift / ps.diffusion, :57,:63).
+ * The reference's Wiener process is unseeded (neural_sde.jl:68-69); here the increments come
+ * from Philox4x32-10 keyed by `seed` (counter = element, draw, stream), reproducible on CPU.
+ * --------------------------------------------------------------------------------------- */
+typedef struct lrnde_sde_tape lrnde_sde_tape;
+
+typedef struct {
+  float t0, t2;          /* tspan (neural_sde.jl:13) */
+  float abstol, reltol;  /* splatted kwargs (neural_sde.jl:69) */
+  int32_t maxiters;      /* neural_sde.jl:14 */
+  int32_t reg_mode;      /* LRNDE_REG_*; eval mode => LRNDE_REG_NONE (neural_sde.jl:86,108) */
+  float t1;              /* unbiased: host-sampled t1 (:89); must be one of saveat[] (:90-91) */
+  float u01;             /* biased: uniform [0,1) picking sol.t[1:end-1] (:112) */
+  const float* saveat;   /* HOST pointer, nsave sorted times in [t0,t2] */
+  int32_t nsave;         /* >0: save at saveat[] (linear interpolation inside a step); 0: only t2;
+                            -1: every accepted step (fetch with lrnde_sde_states) */
+  int32_t save_start;    /* with nsave==-1: include t0 */
+  uint64_t seed;         /* Wiener process seed */
+  int32_t pow_mode;      /* LRNDE_POW_* */
+  int32_t host_buffers;  /* 1: ps / x / u_save / d_* are HOST pointers */
+  int32_t keep_tape;     /* 1: return a tape for lrnde_sde_backward */
+  float qmax, gamma, qmin, delta; /* controller constants; 0 => StochasticDiffEq defaults for
+                                     SOSRI (9/8, 9/10, 1/5, 1/6) */
+  int32_t reserved[8];
+} lrnde_sde_opts;
+
+typedef struct {
+  int32_t nfe_drift, nfe_diffusion; /* st'.nfe_drift / nfe_diffusion (neural_sde.jl:44-65) */
+  int32_t naccept, nreject;
+  int32_t retcode;      /* LRNDE_RET_* */
+  float reg_val;        /* st'.reg_val = EEst*dt (perform_step.jl:105) */
+  float t1_used, dt_reg;
+  int32_t nsave_out;    /* blocks written to u_save (nsave==-1: states available) */
+  int32_t ndraws;       /* Philox draws consumed (next free draw index) */
+  int32_t gpu_launches;
+  int32_t reserved[8];
+} lrnde_sde_stats;
+
+/* x: [D,B]; u_save: [D,B,nsave] (ignored for nsave==-1). */
+int lrnde_sde_forward(lrnde_ctx* ctx, const lrnde_model* drift, const lrnde_model* diffusion,
+                      const lrnde_sde_opts* o, const float* ps_drift, const float* ps_diffusion,
+                      const float* x, int64_t B, float* u_save, lrnde_sde_stats* stats,
+                      lrnde_sde_tape** tape);
+/* d_u_save: one [D,B] cotangent block per returned state (NULL = zeros); d_reg: cotangent of
+ * reg_val.  Writes d_ps_drift, d_ps_diffusion (flat parameter layouts) and d_x (may be NULL). */
+int lrnde_sde_backward(lrnde_ctx* ctx, lrnde_sde_tape* tape, const float* d_u_save, float d_reg,
+                       float* d_ps_drift, float* d_ps_diffusion, float* d_x);
+int lrnde_sde_tape_free(lrnde_sde_tape* tape);
+/* accepted states first .. first+count-1 of the last solve (state 0 = x) and their times (HOST). */
+int lrnde_sde_states(lrnde_ctx* ctx, const lrnde_sde_tape* tape, int32_t first, int32_t count,
+                     int32_t host_buffers, float* u_out, float* t_out);
+/* every ATTEMPTED step (t, dt, EEst, accepted); HOST arrays of capacity cap. */
+int lrnde_sde_step_log(const lrnde_sde_tape* tape, float* t, float* dt, float* eest,
+                       uint8_t* accepted, int32_t cap, int32_t* n);
+
 /* Next row of the path: classifier Dense(D => C) + logitcrossentropy,
  * experiments/src/construct.jl:199 and experiments/src/utils.jl:88, with its pullback.
  * Wc: flat [C x D] weight then [C] bias; u: [D,B]; labels: class index per sample.

@@ -41,6 +41,26 @@ class Stats(C.Structure):
     ]
 
 
+class SdeOpts(C.Structure):
+    _fields_ = [
+        ("t0", C.c_float), ("t2", C.c_float), ("abstol", C.c_float), ("reltol", C.c_float),
+        ("maxiters", C.c_int32), ("reg_mode", C.c_int32), ("t1", C.c_float), ("u01", C.c_float),
+        ("saveat", C.POINTER(C.c_float)), ("nsave", C.c_int32), ("save_start", C.c_int32),
+        ("seed", C.c_uint64), ("pow_mode", C.c_int32), ("host_buffers", C.c_int32),
+        ("keep_tape", C.c_int32), ("qmax", C.c_float), ("gamma", C.c_float), ("qmin", C.c_float),
+        ("delta", C.c_float), ("reserved", C.c_int32 * 8),
+    ]
+
+
+class SdeStats(C.Structure):
+    _fields_ = [
+        ("nfe_drift", C.c_int32), ("nfe_diffusion", C.c_int32), ("naccept", C.c_int32),
+        ("nreject", C.c_int32), ("retcode", C.c_int32), ("reg_val", C.c_float),
+        ("t1_used", C.c_float), ("dt_reg", C.c_float), ("nsave_out", C.c_int32),
+        ("ndraws", C.c_int32), ("gpu_launches", C.c_int32), ("reserved", C.c_int32 * 8),
+    ]
+
+
 class LrndeError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"libLRNDE error {code}: {msg}")
@@ -57,6 +77,8 @@ SYMBOLS = [
     "lrnde_model_state_dims", "lrnde_dynamics_eval", "lrnde_ode_forward", "lrnde_ode_backward",
     "lrnde_tape_free", "lrnde_step_log", "lrnde_sosri_step", "lrnde_ipc_export",
     "lrnde_ipc_open", "lrnde_head_ce", "lrnde_adam_step", "lrnde_profile_feval",
+    "lrnde_sde_forward", "lrnde_sde_backward", "lrnde_sde_tape_free", "lrnde_sde_states",
+    "lrnde_sde_step_log",
 ]
 
 
@@ -98,6 +120,12 @@ def lib():
     L.lrnde_adam_step.argtypes = [vp, vp, vp, vp, vp, i64, f32, f32, f32, f32, i32]
     L.lrnde_profile_feval.argtypes = [vp, vp, C.POINTER(Opts), vp, vp, i64, i32, vp,
                                       C.POINTER(f32), C.POINTER(i32)]
+    L.lrnde_sde_forward.argtypes = [vp, vp, vp, C.POINTER(SdeOpts), vp, vp, vp, i64, vp,
+                                    C.POINTER(SdeStats), C.POINTER(vp)]
+    L.lrnde_sde_backward.argtypes = [vp, vp, vp, f32, vp, vp, vp]
+    L.lrnde_sde_tape_free.argtypes = [vp]
+    L.lrnde_sde_states.argtypes = [vp, vp, i32, i32, i32, vp, vp]
+    L.lrnde_sde_step_log.argtypes = [vp, vp, vp, vp, vp, i32, C.POINTER(i32)]
     for name in SYMBOLS:
         fn = getattr(L, name)
         if name not in ("lrnde_last_error", "lrnde_model_nparams", "lrnde_model_state_dims"):

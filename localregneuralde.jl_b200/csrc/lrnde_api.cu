@@ -1361,3 +1361,4 @@ extern "C" int lrnde_ode_backward(lrnde_ctx* ctx, const lrnde_model* m, lrnde_ta
 }
 
 #include "lrnde_extra.cuh"
+#include "lrnde_sde.cuh"

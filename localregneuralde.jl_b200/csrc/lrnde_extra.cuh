@@ -351,6 +351,17 @@ extern "C" int lrnde_profile_feval(lrnde_ctx* ctx, const lrnde_model* m, const l
   LinComb d;
   memset(&d, 0, sizeof(d));
   d.base = u; d.t = 0.5f; d.dst = du;
+  // LRNDE_PROFILE_NSRC=n: time the evaluation with an n-source stage combination in the operand
+  // prologue (the HBM-bound shape of the later Tsit5 stages) instead of a plain input
+  const char* ns_env = getenv("LRNDE_PROFILE_NSRC");
+  const int nsrc = ns_env ? std::max(0, std::min(7, atoi(ns_env))) : 0;
+  const size_t len = (size_t)m->D * (size_t)B;
+  DevBuf srcs(ctx, nsrc ? len * (size_t)nsrc : 1);
+  if (nsrc) {
+    LR_CUDA(cudaMemsetAsync(srcs.p, 0, len * (size_t)nsrc * sizeof(float), st));
+    d.n = nsrc; d.scale = 0.01f;
+    for (int i = 0; i < nsrc; ++i) { d.src[i] = srcs.p + (size_t)i * len; d.coef[i] = 0.1f * (float)(i + 1); }
+  }
   LR_CUDA(cudaMemcpyAsync(ddesc.p, &d, sizeof(d), cudaMemcpyHostToDevice, st));
   MlpEval ev(ctx, m, ps, B, o ? o->precision : 0, false);
   ev.prepare();

@@ -141,16 +141,41 @@ __device__ __forceinline__ uint32_t elect_one_sync() {
 // descriptor = {lo: start address >> 4 | LBO << 16, hi: SBO | version | layout}
 constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
 __device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr >> 4) & 0x3FFFu) | (1u << 16); }
+// COLL: A-operand collector usage: 0 = discard, 1 = fill (keep A for the next MMA), 2 = lastuse
+// (take A from the collector instead of shared memory).  In 3xTF32 the two MMAs that share
+// A_hi are issued back to back as fill / lastuse: one 4 KB shared-memory read less per K-step
+// (the kernels are shared-memory-bandwidth bound at N = 64).
+template <int COLL = 0>
 __device__ __forceinline__ void mma_tf32_lo(uint32_t d_tmem, uint32_t a_lo32, uint32_t b_lo32, uint32_t idesc,
                                             uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "mov.b64 da, {%1, %5};\n\t"
-      "mov.b64 db, {%2, %5};\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %3, p;\n\t}"
-      ::"r"(d_tmem), "r"(a_lo32), "r"(b_lo32), "r"(idesc), "r"(accumulate), "r"(kDescHi)
-      : "memory");
+  if (COLL == 1) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "mov.b64 da, {%1, %5};\n\t"
+        "mov.b64 db, {%2, %5};\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32.collector::a::fill [%0], da, db, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_lo32), "r"(b_lo32), "r"(idesc), "r"(accumulate), "r"(kDescHi)
+        : "memory");
+  } else if (COLL == 2) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "mov.b64 da, {%1, %5};\n\t"
+        "mov.b64 db, {%2, %5};\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32.collector::a::lastuse [%0], da, db, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_lo32), "r"(b_lo32), "r"(idesc), "r"(accumulate), "r"(kDescHi)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "mov.b64 da, {%1, %5};\n\t"
+        "mov.b64 db, {%2, %5};\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_lo32), "r"(b_lo32), "r"(idesc), "r"(accumulate), "r"(kDescHi)
+        : "memory");
+  }
 }
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -428,9 +453,9 @@ __global__ void __launch_bounds__(kThreads, 1) dense_kernel(UmmaP q) {
           const uint32_t ko = (uint32_t)k * 2;  // 8 tf32 = 32 bytes = 2 x 16 B along K in the swizzle row
           const uint32_t first = (group_start && k == 0) ? 0u : 1u;
           if (q.passes == 3) {
-            mma_tf32_lo(d, a_lo + ko, b_hi + ko, idesc, first);
-            mma_tf32_lo(d, a_hi + ko, b_lo + ko, idesc, 1u);
-            mma_tf32_lo(d, a_hi + ko, b_hi + ko, idesc, 1u);
+            mma_tf32_lo<0>(d, a_lo + ko, b_hi + ko, idesc, first);
+            mma_tf32_lo<1>(d, a_hi + ko, b_lo + ko, idesc, 1u);
+            mma_tf32_lo<2>(d, a_hi + ko, b_hi + ko, idesc, 1u);
           } else {
             mma_tf32_lo(d, a_hi + ko, b_hi + ko, idesc, first);
           }
@@ -514,7 +539,7 @@ __global__ void __launch_bounds__(kThreads, 1) dense_kernel(UmmaP q) {
     if (pc.nsrc == 0) run(I1{}, I4{});
     else if (pc.nsrc == 1) run(I2{}, I4{});
     else if (pc.nsrc <= 3) run(I4{}, I2{});
-    else run(I8{}, I1{});
+    else run(I8{}, I2{});
 
     // ------------------------------------------------ epilogue: TMEM -> registers -> global
     // warps sharing a TMEM lane quarter split the 16-column blocks; tiles are drained in the
@@ -615,16 +640,22 @@ __host__ __device__ constexpr uint32_t make_idesc_mn(int M, int N) {
 // groups, SBO = 2048 B between 4-sample groups, layout type 1 = SWIZZLE_128B_BASE32B
 constexpr uint32_t kDescHiMN = (2048u >> 4) | (1u << 14) | (1u << 29);
 __device__ __forceinline__ uint32_t desc_lo_mn(uint32_t saddr) { return ((saddr >> 4) & 0x3FFFu) | ((512u >> 4) << 16); }
+template <int COLL = 0>
 __device__ __forceinline__ void mma_tf32_mn(uint32_t d_tmem, uint32_t a_lo32, uint32_t b_lo32, uint32_t idesc,
                                             uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "mov.b64 da, {%1, %5};\n\t"
-      "mov.b64 db, {%2, %5};\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %3, p;\n\t}"
-      ::"r"(d_tmem), "r"(a_lo32), "r"(b_lo32), "r"(idesc), "r"(accumulate), "r"(kDescHiMN)
-      : "memory");
+#define LR_MMA_MN(QUAL)                                                                              \
+  asm volatile(                                                                                      \
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"                                                \
+      "setp.ne.b32 p, %4, 0;\n\t"                                                                    \
+      "mov.b64 da, {%1, %5};\n\t"                                                                    \
+      "mov.b64 db, {%2, %5};\n\t"                                                                    \
+      "tcgen05.mma.cta_group::1.kind::tf32" QUAL " [%0], da, db, %3, p;\n\t}"                         \
+      ::"r"(d_tmem), "r"(a_lo32), "r"(b_lo32), "r"(idesc), "r"(accumulate), "r"(kDescHiMN)           \
+      : "memory")
+  if (COLL == 1) LR_MMA_MN(".collector::a::fill");
+  else if (COLL == 2) LR_MMA_MN(".collector::a::lastuse");
+  else LR_MMA_MN("");
+#undef LR_MMA_MN
 }
 
 __device__ __forceinline__ float4 wg_load(const WgOperand& o, int row, int b, bool valid, float tval, bool vec) {
@@ -701,9 +732,9 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(WgradUP q) {
           const uint32_t ko = (uint32_t)kg * (4096u >> 4);
           const uint32_t first = (it == 0 && kg == 0) ? 0u : 1u;
           if (q.passes == 3) {
-            mma_tf32_mn(tmem_base, p_lo + ko, q_hi + ko, idesc, first);
-            mma_tf32_mn(tmem_base, p_hi + ko, q_lo + ko, idesc, 1u);
-            mma_tf32_mn(tmem_base, p_hi + ko, q_hi + ko, idesc, 1u);
+            mma_tf32_mn<0>(tmem_base, p_lo + ko, q_hi + ko, idesc, first);
+            mma_tf32_mn<1>(tmem_base, p_hi + ko, q_lo + ko, idesc, 1u);
+            mma_tf32_mn<2>(tmem_base, p_hi + ko, q_hi + ko, idesc, 1u);
           } else {
             mma_tf32_mn(tmem_base, p_hi + ko, q_hi + ko, idesc, first);
           }

@@ -406,6 +406,201 @@ class NeuralODE:
         return out.T
 
 
+# ------------------------------------------------------------------ neural SDE layer
+class SDESolution:
+    """``sol`` of the NeuralDSDE functor: ``sol.u`` (list of (D,B) arrays at ``sol.t``)."""
+
+    def __init__(self, t, u, tape, layer, ctx, stats, host, shape, dev_times, t1_block):
+        self.t, self.u = t, u
+        self._tape, self._layer, self._ctx, self.stats, self._host = tape, layer, ctx, stats, host
+        self._shape, self._dev_times, self._t1_block = shape, dev_times, t1_block
+        self.retcode = _lib.RETCODES.get(stats.retcode, "?")
+
+    def step_log(self):
+        if not self._tape:
+            raise _lib.LrndeError(-4, "no tape (forward ran with keep_tape=False)")
+        n = C.c_int32()
+        check(lib().lrnde_sde_step_log(self._tape, None, None, None, None, 0, C.byref(n)))
+        k = n.value
+        t = np.zeros(k, np.float32); dt = np.zeros(k, np.float32)
+        e = np.zeros(k, np.float32); a = np.zeros(k, np.uint8)
+        check(lib().lrnde_sde_step_log(self._tape, _ptr(t), _ptr(dt), _ptr(e), _ptr(a), k, C.byref(n)))
+        return t, dt, e, a.astype(bool)
+
+    def free(self):
+        if self._tape:
+            lib().lrnde_sde_tape_free(self._tape)
+            self._tape = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class NeuralDSDE:
+    """``NeuralDSDE(drift, diffusion; solver=SOSRI(), sensealg=TrackerAdjoint(), tspan=(0f0,1f0),
+    regularize=:unbiased, maxiters=1000, kwargs...)`` (src/layers/neural_sde.jl:11-19); kwargs:
+    abstol, reltol, saveat, save_start.  Parameters are ``[ps.drift; ps.diffusion]`` flat.
+    ``seed`` keys the Philox Wiener process (the reference's is unseeded, :68-69)."""
+
+    VALID_MODES = ("none", "unbiased", "biased")
+
+    def __init__(self, drift: Chain, diffusion: Chain, *, solver="SOSRI", sensealg="TrackerAdjoint",
+                 tspan=(0.0, 1.0), regularize: str = "unbiased", maxiters: int = 1000,
+                 pow_mode: str = "fastpow_2023", seed: int = 0, ctx: Optional[Context] = None,
+                 controller: Optional[dict] = None, **kwargs):
+        if regularize not in self.VALID_MODES:                          # utils.jl:53-58
+            raise ValueError(f"regularize must be one of {self.VALID_MODES}")
+        if solver != "SOSRI":
+            raise ValueError("the B200 path implements solver=SOSRI() (the reference default)")
+        if sensealg != "TrackerAdjoint":
+            raise ValueError("the B200 path implements sensealg=TrackerAdjoint()")
+        self.drift, self.diffusion, self.tspan, self.regularize = drift, diffusion, tuple(tspan), regularize
+        self.maxiters, self.pow_mode, self.seed = int(maxiters), pow_mode, int(seed)
+        self.abstol = float(kwargs.pop("abstol", 1e-2))     # StochasticDiffEq defaults
+        self.reltol = float(kwargs.pop("reltol", 1e-2))
+        self.saveat = kwargs.pop("saveat", None)
+        self.save_start = kwargs.pop("save_start", None)
+        if kwargs:
+            raise TypeError(f"unsupported solve kwargs {sorted(kwargs)}")
+        self.controller = dict(controller or {})
+        self._ctx = ctx
+
+    def initialparameters(self, rng: np.random.Generator) -> np.ndarray:
+        return np.concatenate([glorot_uniform(self.drift, rng), glorot_uniform(self.diffusion, rng)])
+
+    def initialstates(self, rng: np.random.Generator):                   # neural_sde.jl:22-27
+        rng.standard_normal()
+        return dict(drift={}, diffusion={}, nfe_drift=-1, nfe_diffusion=-1, reg_val=np.float32(0),
+                    rng=copy.deepcopy(rng), training=True)
+
+    @property
+    def ctx(self) -> Context:
+        if self._ctx is None:
+            self._ctx = default_context(0)
+        return self._ctx
+
+    def __call__(self, x, ps, st, keep_tape: Optional[bool] = None):
+        """(n::NeuralDSDE)(x, ps, st) -> (sol, st') (neural_sde.jl:82-123)."""
+        T = np.float32
+        t0, t2 = T(self.tspan[0]), T(self.tspan[1])
+        training = bool(st["training"])
+        mode = self.regularize if training else "none"                   # :86, :108
+        rng = st["rng"]
+        t1, u01 = t0, 0.0
+        if mode != "none":
+            rng = copy.deepcopy(st["rng"])                               # Lux.replicate (:87)
+            if mode == "unbiased":
+                t1 = T(rng.random(dtype=np.float32)) * (t2 - t0) + t0    # :89
+            else:
+                u01 = float(rng.random(dtype=np.float32))                # :112 (index picked in C)
+        host = not _is_torch(x)
+        if keep_tape is None:
+            keep_tape = training
+        # ---- the save times the device sees (sorted) and how they map back to sol.u
+        user = None if self.saveat is None else [T(s) for s in self.saveat]
+        if user is not None and self.save_start and t0 not in user:
+            user = [t0] + user
+        all_steps = False
+        if mode == "unbiased":
+            ret_times = [t1, t2] if user is None else list(user)         # :90-91, utils.jl:31-33
+            dev_times = sorted(set(ret_times + [t1]))
+        elif mode == "biased" and user is None:
+            all_steps, ret_times, dev_times = True, None, []
+        else:
+            ret_times = [t2] if user is None else list(user)
+            dev_times = sorted(set(ret_times))
+        o = _lib.SdeOpts()
+        o.t0, o.t2, o.abstol, o.reltol, o.maxiters = t0, t2, self.abstol, self.reltol, self.maxiters
+        o.reg_mode, o.t1, o.u01 = _lib.REG[mode], float(t1), u01
+        keep = np.asarray(dev_times, dtype=np.float32)
+        if all_steps:
+            o.nsave = -1
+            o.save_start = 1 if (self.save_start is None or self.save_start) else 0
+        else:
+            o.saveat = keep.ctypes.data_as(C.POINTER(C.c_float))
+            o.nsave = keep.size
+        o.seed, o.pow_mode = self.seed, _lib.POW[self.pow_mode]
+        o.host_buffers, o.keep_tape = (1 if host else 0), (1 if keep_tape else 0)
+        for k in ("qmax", "gamma", "qmin", "delta"):
+            setattr(o, k, float(self.controller.get(k, 0.0)))
+        xb = _as_input(x, not host, None)
+        B, D = xb.shape
+        psb = ps.detach().to(torch.float32).contiguous() if _is_torch(ps) else \
+            np.ascontiguousarray(np.asarray(ps, dtype=np.float32))
+        nf, ng = nparams(self.drift), nparams(self.diffusion)
+        if (psb.size if host else psb.numel()) != nf + ng:
+            raise ValueError("ps has the wrong length for [drift; diffusion]")
+        pf, pg = psb[:nf], psb[nf:]
+        nblk = max(1, len(dev_times))
+        usave = np.empty((nblk, B, D), np.float32) if host else \
+            torch.empty((nblk, B, D), dtype=torch.float32, device=xb.device)
+        stats = _lib.SdeStats()
+        tape = C.c_void_p()
+        ctx = self.ctx
+        check(lib().lrnde_sde_forward(ctx._h, ctx.model_handle(self.drift), ctx.model_handle(self.diffusion),
+                                      C.byref(o), _ptr(pf), _ptr(pg), _ptr(xb), B, _ptr(usave),
+                                      C.byref(stats), C.byref(tape)))
+        try:
+            if all_steps:
+                n = stats.nsave_out
+                first = 0 if o.save_start else 1
+                states = np.empty((max(n, 1), B, D), np.float32) if host else \
+                    torch.empty((max(n, 1), B, D), dtype=torch.float32, device=xb.device)
+                times = np.zeros(max(n, 1), np.float32)
+                if not tape:
+                    raise _lib.LrndeError(-4, "regularize=:biased without saveat needs keep_tape=True")
+                check(lib().lrnde_sde_states(ctx._h, tape, first, n, 1 if host else 0, _ptr(states), _ptr(times)))
+                ts, us = [T(t) for t in times[:n]], [states[i].T for i in range(n)]
+                t1_block = None
+            else:
+                index = {float(s): i for i, s in enumerate(dev_times)}
+                ts = [T(s) for s in ret_times]
+                us = [usave[index[float(s)]].T for s in ret_times]
+                t1_block = index.get(float(t1)) if (mode == "unbiased" and user is not None) else None
+        except Exception:
+            if tape:
+                lib().lrnde_sde_tape_free(tape)
+            raise
+        sol = SDESolution(ts, us, tape if keep_tape else None, self, ctx, stats, host, (B, D),
+                          [float(s) for s in dev_times], t1_block)
+        st2 = dict(st, nfe_drift=int(stats.nfe_drift), nfe_diffusion=int(stats.nfe_diffusion),
+                   reg_val=T(stats.reg_val), rng=rng)                     # :103-105
+        return sol, st2
+
+    def backward(self, sol: SDESolution, d_us: Sequence, d_reg: float = 0.0):
+        """TrackerAdjoint pullback: cotangents on each ``sol.u[i]`` (None = zero) and on
+        ``st'.reg_val``.  Returns (d_x, d_ps) with d_ps = [d_drift; d_diffusion]."""
+        if not sol._tape:
+            raise _lib.LrndeError(-4, "no tape: call the layer with training=True / keep_tape=True")
+        B, D = sol._shape
+        if len(d_us) != len(sol.u):
+            raise ValueError(f"expected {len(sol.u)} cotangent blocks, got {len(d_us)}")
+        host = sol._host
+        nblk = len(sol._dev_times) if sol._dev_times else len(sol.u)
+        dev = None if host else sol.u[0].device
+        dU = np.zeros((max(nblk, 1), B, D), np.float32) if host else \
+            torch.zeros((max(nblk, 1), B, D), dtype=torch.float32, device=dev)
+        index = {s: i for i, s in enumerate(sol._dev_times)}
+        for i, d in enumerate(d_us):
+            if d is None:
+                continue
+            k = index[float(sol.t[i])] if sol._dev_times else i
+            dU[k] += (np.asarray(d, np.float32).T if host else d.to(torch.float32).t())
+        nf, ng = nparams(self.drift), nparams(self.diffusion)
+        if host:
+            d_x, d_ps = np.empty((B, D), np.float32), np.empty(nf + ng, np.float32)
+        else:
+            d_x = torch.empty((B, D), dtype=torch.float32, device=dev)
+            d_ps = torch.empty(nf + ng, dtype=torch.float32, device=dev)
+        ctx = sol._ctx
+        check(lib().lrnde_sde_backward(ctx._h, sol._tape, _ptr(dU), float(d_reg), _ptr(d_ps[:nf]),
+                                       _ptr(d_ps[nf:]), _ptr(d_x)))
+        return d_x.T, d_ps
+
+
 # ------------------------------------------------------------------ torch autograd bridge
 if torch is not None:
 

@@ -10,3 +10,4 @@ tests hold no golden vectors (test/runtests.jl:21-29,118-131 assert only
 finiteness / non-zeroness).  See oracle/lrnde_oracle.py's header.
 """
 from .lrnde_oracle import *  # noqa: F401,F403
+from .lrnde_sde_oracle import *  # noqa: F401,F403,E402
