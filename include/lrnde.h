@@ -227,6 +227,17 @@ int lrnde_sde_states(lrnde_ctx* ctx, const lrnde_sde_tape* tape, int32_t first, 
 int lrnde_sde_step_log(const lrnde_sde_tape* tape, float* t, float* dt, float* eest,
                        uint8_t* accepted, int32_t cap, int32_t* n);
 
+/* The other in-tree SDE local-reg steps for diagonal noise with injected increments dW [D,B]:
+ * _perform_step(::RKMilCommuteConstantCache) src/perform_step.jl:108-170 (quirk kept: the
+ * error computed at :162-163 is overwritten at :165, EEst = RMS relative change) and
+ * _perform_step(::LambaEulerHeunConstantCache) :172-206.  Writes u [D,B], *reg_val = EEst*dt. */
+enum { LRNDE_SDESTEP_RKMIL = 0, LRNDE_SDESTEP_LAMBA_EULER_HEUN = 1 };
+int lrnde_sde_aux_step(lrnde_ctx* ctx, const lrnde_model* drift, const lrnde_model* diffusion,
+                       int32_t kind, const float* ps_drift, const float* ps_diffusion,
+                       const float* uprev, const float* dW, float t, float dt, float abstol,
+                       float reltol, float delta, int64_t B, int32_t host_buffers, float* u,
+                       float* reg_val);
+
 /* Next row of the path: classifier Dense(D => C) + logitcrossentropy,
  * experiments/src/construct.jl:199 and experiments/src/utils.jl:88, with its pullback.
  * Wc: flat [C x D] weight then [C] bias; u: [D,B]; labels: class index per sample.

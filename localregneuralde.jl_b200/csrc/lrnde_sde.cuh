@@ -983,6 +983,97 @@ __global__ void sde_grad_reduce_kernel(SdeNet n, const float* gpart, int stride,
   }
 }
 
+// ---------------------------------------------------------------- the other in-tree SDE steps
+// _perform_step(::RKMilCommuteConstantCache) (perform_step.jl:108-170) and
+// _perform_step(::LambaEulerHeunConstantCache) (:172-206), diagonal noise, Ito, injected dW.
+// kind 0 = RKMilCommute (quirk kept: the drift/noise error of :162-163 is overwritten at :165 and
+// EEst is the RMS of the relative CHANGE), kind 1 = LambaEulerHeun.
+struct SdeAuxP {
+  SdeNet nf, ng;
+  const float* psf; const float* psg;
+  int B, S, SP, tiles_per_cta, kind;
+  float t, dt, abstol, reltol, delta;
+  const float* uprev; const float* dW; float* u; double* partials;
+};
+
+__global__ void __launch_bounds__(SDE_THREADS, 1) sde_aux_step_kernel(SdeAuxP p) {
+  extern __shared__ __align__(16) float sde_sm[];
+  __shared__ double red[32];
+  float *Wf, *Wg, *Gf, *Gg;
+  SdeBufs b;
+  const int D = p.nf.D;
+  sde_carve(sde_sm, p.nf, p.ng, D, p.SP, false, Wf, Wg, Gf, Gg, b);
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  sde_load_weights(p.nf, p.psf, Wf, tid, nthr);
+  sde_load_weights(p.ng, p.psg, Wg, tid, nthr);
+  __syncthreads();
+  SdeTile T{p.S, p.SP, D, 0, nthr, tid};
+  const float t = p.t, dt = p.dt, sqdt = sqrtf(fabsf(dt));
+  double part = 0.0;
+  for (int ti = 0; ti < p.tiles_per_cta; ++ti) {
+    const int b0 = (blockIdx.x * p.tiles_per_cta + ti) * p.S;
+    if (b0 >= p.B) break;
+    T.nvalid = min(p.S, p.B - b0);
+    sde_tile_load(b.U, p.uprev, b0, T);
+    sde_tile_load(b.dW, p.dW, b0, T);
+    __syncthreads();
+    sde_mlp_fwd(p.nf, Wf, b.U, t, b.k[0], b.pre, b.post, T);   // du1
+    sde_mlp_fwd(p.ng, Wg, b.U, t, b.g[0], b.pre, b.post, T);   // L
+    for (int idx = tid; idx < D * T.S; idx += nthr) {
+      const int a = (idx / T.S) * T.SP + (idx % T.S);
+      const float K = b.U[a] + dt * b.k[0][a];
+      b.H0[a] = K;
+      b.H1[a] = (p.kind == 0) ? K + sqdt * b.g[0][a] : K + b.g[0][a] * b.dW[a];
+    }
+    __syncthreads();
+    if (p.kind == 0) {
+      sde_mlp_fwd(p.ng, Wg, b.H1, t, b.g[1], b.pre, b.post, T);        // gtmp
+      sde_mlp_fwd(p.nf, Wf, b.H0, t + dt, b.k[1], b.pre, b.post, T);   // du2 (evaluated, unused: quirk)
+      for (int idx = tid; idx < D * T.S; idx += nthr) {
+        const int s = idx % T.S, a = (idx / T.S) * T.SP + s;
+        const float dW = b.dW[a], L = b.g[0][a];
+        const float J = dW * dW / 2.0f - 0.5f * fabsf(dt);
+        const float Dgj = (b.g[1][a] - L) / sqdt;
+        const float u = b.H0[a] + L * dW + Dgj * J;
+        b.un[a] = u;
+        if (s < T.nvalid) {
+          const float up = b.U[a];
+          const float r = (u - up) / (p.abstol + fmaxf(fabsf(up), fabsf(u)) * p.reltol);
+          part += (double)r * r;
+        }
+      }
+    } else {
+      sde_mlp_fwd(p.ng, Wg, b.H1, t + dt, b.g[1], b.pre, b.post, T);   // g(tmp, t+dt)
+      sde_mlp_fwd(p.nf, Wf, b.H1, t + dt, b.k[1], b.pre, b.post, T);   // f(tmp, t+dt)
+      sde_mlp_fwd(p.nf, Wf, b.H0, t + dt, b.k[2], b.pre, b.post, T);   // du2
+      for (int idx = tid; idx < D * T.S; idx += nthr) {
+        const int a = (idx / T.S) * T.SP + (idx % T.S);
+        b.H1[a] = b.U[a] + b.g[0][a] * sqdt;                           // utilde
+      }
+      __syncthreads();
+      sde_mlp_fwd(p.ng, Wg, b.H1, t, b.g[2], b.pre, b.post, T);
+      for (int idx = tid; idx < D * T.S; idx += nthr) {
+        const int s = idx % T.S, a = (idx / T.S) * T.SP + s;
+        const float dW = b.dW[a], L = b.g[0][a], up = b.U[a];
+        const float gtmp2 = 0.5f * (L + b.g[1][a]);
+        const float u = up + (dt / 2.0f) * (b.k[0][a] + b.k[1][a]) + gtmp2 * dW;
+        b.un[a] = u;
+        if (s < T.nvalid) {
+          const float Ed = dt * (b.k[2][a] - b.k[0][a]) / 2.0f;
+          const float En = ((b.g[2][a] - L) / sqdt) * (dW * dW) / 2.0f;
+          const float r = (p.delta * Ed + En) / (p.abstol + fmaxf(fabsf(up), fabsf(u)) * p.reltol);
+          part += (double)r * r;
+        }
+      }
+    }
+    __syncthreads();
+    sde_tile_store(p.u, b.un, b0, T);
+    __syncthreads();
+  }
+  part = sde_block_sum(part, red);
+  if (tid == 0) p.partials[blockIdx.x] = part;
+}
+
 // ==========================================================================================
 // Host side: C ABI (include/lrnde.h, "Neural SDE" section)
 // ==========================================================================================
@@ -1332,5 +1423,63 @@ extern "C" int lrnde_sde_backward(lrnde_ctx* ctx, lrnde_sde_tape* T, const float
 extern "C" int lrnde_sde_tape_free(lrnde_sde_tape* T) {
   LR_API_BEGIN
   delete T;
+  LR_API_END
+}
+
+extern "C" int lrnde_sde_aux_step(lrnde_ctx* ctx, const lrnde_model* drift, const lrnde_model* diffusion,
+                                  int32_t kind, const float* ps_drift, const float* ps_diffusion,
+                                  const float* uprev, const float* dW, float t, float dt, float abstol,
+                                  float reltol, float delta, int64_t B, int32_t host_buffers, float* u,
+                                  float* reg_val) {
+  LR_API_BEGIN
+  if (!ctx || !drift || !diffusion || !ps_drift || !ps_diffusion || !uprev || !dW || !u || !reg_val || B < 1)
+    lr_fail(LRNDE_EINVAL, "lrnde_sde_aux_step: bad args");
+  if (kind != LRNDE_SDESTEP_RKMIL && kind != LRNDE_SDESTEP_LAMBA_EULER_HEUN)
+    lr_fail(LRNDE_EINVAL, "kind must be LRNDE_SDESTEP_RKMIL or LRNDE_SDESTEP_LAMBA_EULER_HEUN");
+  if (drift->D != diffusion->D) lr_fail(LRNDE_EINVAL, "drift and diffusion act on different state sizes");
+  LR_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  SdeAuxP p;
+  memset(&p, 0, sizeof(p));
+  p.nf = sde_make_net(drift, "drift");
+  p.ng = sde_make_net(diffusion, "diffusion");
+  const int D = drift->D;
+  const size_t DB = (size_t)D * (size_t)B;
+  cudaDeviceProp prop;
+  LR_CUDA(cudaGetDeviceProperties(&prop, ctx->device));
+  int S = 32;
+  while (S > 8 && ((B + S - 1) / S) < prop.multiProcessorCount / 2) S >>= 1;
+  size_t smem = 0;
+  for (;; S >>= 1) {
+    smem = sde_smem_bytes(p.nf, p.ng, D, S + 1, false);
+    if (smem <= (size_t)prop.sharedMemPerBlockOptin) break;
+    if (S <= 4) lr_fail(LRNDE_EINVAL, "SDE networks / state too large for the shared-memory resident path");
+  }
+  const int ntiles = (int)((B + S - 1) / S);
+  const int max_grid = 4 * prop.multiProcessorCount;
+  p.S = S; p.SP = S + 1; p.B = (int)B; p.kind = kind;
+  p.tiles_per_cta = (ntiles + max_grid - 1) / max_grid;
+  const int grid = (ntiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
+  p.t = t; p.dt = dt; p.abstol = abstol; p.reltol = reltol; p.delta = delta;
+  const cudaMemcpyKind in_kind = host_buffers ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+  DevBuf psf(ctx, drift->nparams), psg(ctx, diffusion->nparams), up(ctx, DB), dw(ctx, DB), un(ctx, DB);
+  DevBuf parts(ctx, 2 * (size_t)grid + 2);
+  LR_CUDA(cudaMemcpyAsync(psf.p, ps_drift, sizeof(float) * drift->nparams, in_kind, st));
+  LR_CUDA(cudaMemcpyAsync(psg.p, ps_diffusion, sizeof(float) * diffusion->nparams, in_kind, st));
+  LR_CUDA(cudaMemcpyAsync(up.p, uprev, sizeof(float) * DB, in_kind, st));
+  LR_CUDA(cudaMemcpyAsync(dw.p, dW, sizeof(float) * DB, in_kind, st));
+  p.psf = psf.p; p.psg = psg.p; p.uprev = up.p; p.dW = dw.p; p.u = un.p; p.partials = (double*)parts.p;
+  LR_CUDA(cudaFuncSetAttribute(sde_aux_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  sde_aux_step_kernel<<<grid, SDE_THREADS, smem, st>>>(p);
+  LR_COUNT(ctx);
+  LR_CUDA(cudaGetLastError());
+  std::vector<double> hp(grid);
+  LR_CUDA(cudaMemcpyAsync(hp.data(), parts.p, sizeof(double) * grid, cudaMemcpyDeviceToHost, st));
+  LR_CUDA(cudaMemcpyAsync(u, un.p, sizeof(float) * DB, host_buffers ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, st));
+  LR_CUDA(cudaStreamSynchronize(st));
+  double tot = 0.0;
+  for (double v : hp) tot += v;
+  const float eest = sqrtf((float)(tot / (double)DB));
+  *reg_val = eest * dt;   // perform_step.jl:169,205: EEst * dt
   LR_API_END
 }

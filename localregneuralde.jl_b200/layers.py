@@ -600,6 +600,26 @@ class NeuralDSDE:
                                        _ptr(d_ps[nf:]), _ptr(d_x)))
         return d_x.T, d_ps
 
+    def perform_step(self, kind: str, ps, uprev, dW, t: float, dt: float, delta: float = 1.0 / 6.0):
+        """``_perform_step`` of the alternative SDE caches (src/perform_step.jl:108-206) with injected
+        increments: kind "RKMilCommute" or "LambaEulerHeun".  Returns (u, reg_val = EEst*dt)."""
+        kinds = {"RKMilCommute": 0, "LambaEulerHeun": 1}
+        if kind not in kinds:
+            raise ValueError(f"kind must be one of {sorted(kinds)}")
+        host = not _is_torch(uprev)
+        ub, wb = _as_input(uprev, not host, None), _as_input(dW, not host, None)
+        B, D = ub.shape
+        psb = ps.contiguous() if _is_torch(ps) else np.ascontiguousarray(np.asarray(ps, np.float32))
+        nf = nparams(self.drift)
+        out = np.empty((B, D), np.float32) if host else torch.empty_like(ub)
+        reg = C.c_float()
+        ctx = self.ctx
+        check(lib().lrnde_sde_aux_step(ctx._h, ctx.model_handle(self.drift), ctx.model_handle(self.diffusion),
+                                       kinds[kind], _ptr(psb[:nf]), _ptr(psb[nf:]), _ptr(ub), _ptr(wb),
+                                       float(t), float(dt), self.abstol, self.reltol, float(delta), B,
+                                       1 if host else 0, _ptr(out), C.byref(reg)))
+        return out.T, np.float32(reg.value)
+
 
 # ------------------------------------------------------------------ torch autograd bridge
 if torch is not None:

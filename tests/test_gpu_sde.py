@@ -176,3 +176,29 @@ def test_sde_argument_errors(pkg):
     with pytest.raises(pkg.LrndeError):
         bad(np.zeros((4, 3), np.float32), np.zeros(4 * 6 + 6 + 6 * 4 + 4 + 12, np.float32),
             bad.initialstates(np.random.default_rng(0)))
+
+
+@pytest.mark.parametrize("kind", ["RKMilCommute", "LambaEulerHeun"])
+@pytest.mark.parametrize("B", [1, 77, 4096])
+def test_other_in_tree_sde_steps(pkg, kind, B):
+    """perform_step.jl:108-170 / :172-206 (diagonal noise, injected dW) against the oracle."""
+    D, H = 12, 20
+    dl, gl = [(D, H, "tanh"), (H, D, "identity")], [(D, D, "tanh")]
+    od = orc.MLP([orc.Dense(*l) for l in dl], time_dependent=False)
+    og = orc.MLP([orc.Dense(*l) for l in gl], time_dependent=False)
+    rng = np.random.default_rng(B)
+    ps = np.concatenate([2 * orc.glorot_uniform_params(od, rng), orc.glorot_uniform_params(og, rng)]).astype(np.float32)
+    x = rng.standard_normal((D, B)).astype(np.float32)
+    t, dt = np.float32(0.3), np.float32(0.02)
+    dW = (np.sqrt(dt) * rng.standard_normal((D, B))).astype(np.float32)
+    layer = pkg.NeuralDSDE(pkg.Chain(*[pkg.Dense(*l) for l in dl]), pkg.Chain(*[pkg.Dense(*l) for l in gl]),
+                           regularize="none", abstol=1e-2, reltol=1e-2)
+    u, reg = layer.perform_step(kind, ps, x, dW, t, dt)
+    nf = od.nparams
+    fd = lambda v, tt: od.f(v, ps[:nf], tt)
+    gd = lambda v, tt: og.f(v, ps[nf:], tt)
+    if kind == "RKMilCommute":
+        ou, oreg, _, _ = so.perform_step_rkmil_reg(fd, gd, x, t, dt, dW, np.zeros_like(dW), 1e-2, 1e-2)
+    else:
+        ou, oreg, _, _ = so.perform_step_lamba_eulerheun_reg(fd, gd, x, t, dt, dW, np.zeros_like(dW), 1e-2, 1e-2)
+    assert rel(u, ou) < 1e-5 and abs(float(reg) / float(oreg) - 1) < 1e-4
