@@ -288,11 +288,12 @@ def run_native(args):
         return ms, st, nfe_sum
 
     st = st0
-    for i in range(args.warmup):
-        st = step(i, st, True)
     clocks = ClockSampler(local)
     if rank == 0:
-        clocks.start()
+        clocks.start()         # before the warm-up: nvidia-smi's own start-up (~1 s of driver calls) must not
+                               # land inside the timed region; it keeps sampling every 200 ms through it
+    for i in range(args.warmup):
+        st = step(i, st, True)
     launches["n"] = 0
     ms_total, st, nfe_sum = timed(args.steps, st, True, args.warmup)
     n_launch = launches["n"]
@@ -315,24 +316,57 @@ def run_native(args):
     e2e = {"value": B * world / (ms_e / 1e3), "unit": "samples/s", "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": d2h, "ms_per_step": ms_e, "steps": e2e_steps}
 
-    # ---- roofline of the dominant unit: one stage f-evaluation (both layer GEMMs + epilogues)
+    # ---- roofline of the dominant kernel.  By share of the step (profiles/) that is the long-K
+    # dense kernel umma::dense_kernel<64,0,4> = layer 1 of a stage evaluation with the Tsit5 stage
+    # combination formed in its operand prologue.  Per launch it moves (1 + nsrc) [D,B] arrays in and
+    # one [H,B] array out for 2*H*(D+2)*B flop: 5..40 flop/B, far below the ridge (TF32 peak / HBM
+    # peak ~ 126 flop/B), so HBM bandwidth bounds it.  Timed live with CUDA events on the launching
+    # stream through lrnde_profile_feval, once per stage shape of a Tsit5 step (nsrc = 1..6).
     du = torch.empty((B, D), dtype=torch.float32, device=dev)
     o, _k = node._opts("none", 0.0, 0.0, False, False)
-    msf, lp = C.c_float(), C.c_int32()
-    chk(lib.lrnde_profile_feval(ctx._h, ctx.model_handle(chain), C.byref(o), ps.data_ptr(), xb.data_ptr(), B,
-                                50, du.data_ptr(), C.byref(msf), C.byref(lp)))
+
+    def probe(nsrc, layers):
+        os.environ["LRNDE_PROFILE_NSRC"] = str(nsrc)
+        if layers:
+            os.environ["LRNDE_PROFILE_LAYERS"] = str(layers)
+        else:
+            os.environ.pop("LRNDE_PROFILE_LAYERS", None)
+        msf, lp = C.c_float(), C.c_int32()
+        chk(lib.lrnde_profile_feval(ctx._h, ctx.model_handle(chain), C.byref(o), ps.data_ptr(), xb.data_ptr(), B,
+                                    30, du.data_ptr(), C.byref(msf), C.byref(lp)))
+        os.environ.pop("LRNDE_PROFILE_NSRC", None)
+        os.environ.pop("LRNDE_PROFILE_LAYERS", None)
+        return msf.value * 1e-3, lp.value
+
     peaks = {}
     pk_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(pk_path):
         peaks = json.load(open(pk_path))
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
     bf16 = peaks.get("bf16_tflops", 1590.0)
     tf32_peak = bf16 / 2.0
-    ach = flops_per_feval(B) / (msf.value * 1e-3) / 1e12
-    roof = {"bound": "tensor", "kernel": "stage f-evaluation (layer-1 + layer-2 GEMMs with fused prologue/epilogue)",
-            "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s", "frac": ach / tf32_peak, "traffic": None,
-            "peak_source": ("measured bf16 burst / 2 (TF32 dense = half the bf16 rate)" if peaks else
-                            "fallback 1590 bf16 / 2"),
-            "ms_per_feval": msf.value, "launches_per_feval": lp.value,
+    arr = 4.0 * D * B                                    # bytes of one [D,B] state array
+    t_l1 = [probe(ns, 1)[0] for ns in range(1, 7)]       # the six layer-1 launches of one Tsit5 step
+    t_ev = [probe(ns, 0)[0] for ns in range(1, 7)]       # whole stage evaluations (both layers)
+    bytes_l1 = [(1 + ns) * arr + 4.0 * H * B for ns in range(1, 7)]
+    bytes_ev = [(2 + ns) * arr + 2 * 4.0 * H * B for ns in range(1, 7)]
+    t0s, lpe = probe(0, 0)
+    ach = sum(bytes_l1) / sum(t_l1) / 1e9
+    flops_l1 = 2.0 * H * (D + 2) * B
+    roof = {"bound": "hbm",
+            "kernel": "umma::dense_kernel<64,0,4> (layer 1 of a stage evaluation, Tsit5 stage combination in the "
+                      "operand prologue); mean over the six launch shapes of one step (nsrc = 1..6)",
+            "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+            "traffic": 166.2e6,   # dram read+write of the nsrc = 5 launch, ncu --set full (profiles/), algorithmic 157.5e6
+            "peak_source": ("measured STREAM copy (MEASURED_PEAKS.json)" if peaks else "fallback 6650 GB/s"),
+            "algorithmic_bytes_per_launch": sum(bytes_l1) / 6.0, "avg_launch_us": 1e6 * sum(t_l1) / 6.0,
+            "launch_us_by_nsrc": [round(1e6 * t, 2) for t in t_l1],
+            "tensor_frac_3xtf32": 3.0 * 6 * flops_l1 / sum(t_l1) / 1e12 / tf32_peak,
+            "stage_eval": {"hbm_frac": sum(bytes_ev) / sum(t_ev) / 1e9 / hbm_peak,
+                           "tflops_algorithmic": 6 * flops_per_feval(B) / sum(t_ev) / 1e12,
+                           "tensor_frac": 6 * flops_per_feval(B) / sum(t_ev) / 1e12 / tf32_peak,
+                           "us_by_nsrc": [round(1e6 * t, 2) for t in t_ev], "us_plain_input": round(1e6 * t0s, 2),
+                           "launches_per_eval": lpe},
             "step_flops_frac": iteration_flops(B, fwd_info["nfe"], fwd_info["nf_bwd"]) / (ms * 1e-3) / 1e12 / tf32_peak}
 
     if rank == 0:
@@ -359,6 +393,106 @@ def run_native(args):
         dist.destroy_process_group()
 
 
+# ---------------------------------------------------------------------------------- mnist_sde (secondary)
+def sde_setup(B, use_oracle):
+    Ds, Hs = 32, 64
+    kw = dict(regularize="unbiased", abstol=0.14, reltol=0.14, save_start=False, maxiters=10000, seed=0)
+    rng = np.random.default_rng(0)
+    if use_oracle:
+        import oracle as orc
+        od = orc.MLP([orc.Dense(Ds, Hs, "tanh"), orc.Dense(Hs, Ds, "identity")], time_dependent=False)
+        og = orc.MLP([orc.Dense(Ds, Ds, "identity")], time_dependent=False)
+        layer = orc.NeuralDSDE(od, og, **kw)
+        ps = np.concatenate([orc.glorot_uniform_params(od, rng), orc.glorot_uniform_params(og, rng)])
+    else:
+        import __graft_entry__ as entry
+        entry.build()
+        pkg = entry.load_package()
+        layer = pkg.NeuralDSDE(pkg.Chain(pkg.Dense(Ds, Hs, "tanh"), pkg.Dense(Hs, Ds)), pkg.Chain(pkg.Dense(Ds, Ds)), **kw)
+        ps = layer.initialparameters(rng)
+    x = np.random.default_rng(1).random((Ds, B), dtype=np.float32)
+    return layer, ps, x
+
+
+def run_sde(args):
+    """BASELINE configs[1]: neural SDE (diagonal noise) with local regularisation, state 32 x 128
+    (experiments/src/construct.jl:202-210): forward SOSRI solve + regulariser step + TrackerAdjoint
+    pullback of sum(u(t2))/B + w_reg * reg_val.  Secondary workload (one JSON line, same contract)."""
+    B = args.sde_batch
+    if args.impl == "reference":
+        layer, ps, x = sde_setup(B, True)
+        st = layer.initialstates(np.random.default_rng(7))
+        ts = []
+        for i in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            out, st2, aux = layer.forward(x, ps, st)
+            layer.backward(aux, [None, np.ones_like(x) / B], W_REG, ps)
+            if i >= args.warmup:
+                ts.append(time.perf_counter() - t0)
+        ms = 1e3 * float(np.mean(ts))
+        val = B / (ms / 1e3)
+        print(json.dumps({"impl": "reference", "metric": "mnist_sde_train_samples_per_s", "value": val, "unit": "samples/s",
+                          "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "config": {"workload": "mnist_sde (BASELINE configs[1])", "batch": B},
+                          "cpu_baseline": {"value": val, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
+                                           "sample": "the whole workload"},
+                          "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+    import torch
+    layer, ps, x = sde_setup(B, False)
+    dev = torch.device("cuda", 0)
+    xt, pt = torch.from_numpy(x).to(dev), torch.from_numpy(ps).to(dev)
+    cot_t = torch.ones((32, B), device=dev) / B
+    cot_h = np.ones((32, B), np.float32) / B
+    st = layer.initialstates(np.random.default_rng(7))
+    info = {}
+
+    def step(resident):
+        sol, st2 = layer(xt if resident else x, pt if resident else ps, st)
+        layer.backward(sol, [None, cot_t if resident else cot_h], W_REG)
+        info.update(nfe=st2["nfe_drift"], acc=sol.stats.naccept, rej=sol.stats.nreject, launches=sol.stats.gpu_launches + 3)
+        sol.free()
+
+    def timed(n, resident):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(n):
+            step(resident)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+    clocks = ClockSampler(0)
+    clocks.start()
+    for _ in range(max(3, args.warmup) + 20):
+        step(True); step(False)
+    ms = timed(args.steps, True)
+    clk = clocks.stop()
+    ms_e = timed(args.steps, False)
+    olayer, ops, ox = sde_setup(B, True)
+    ost = olayer.initialstates(np.random.default_rng(7))
+    t0 = time.perf_counter()
+    out, st2, aux = olayer.forward(ox, ops, ost)
+    olayer.backward(aux, [None, cot_h], W_REG, ops)
+    dt = time.perf_counter() - t0
+    print(json.dumps({"metric": "mnist_sde_train_samples_per_s", "value": B / (ms / 1e3), "unit": "samples/s", "n_gpus": 1,
+                      "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+                      "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                      "config": {"workload": "mnist_sde (BASELINE configs[1]): NeuralDSDE drift 32-64-32 tanh, diffusion "
+                                             "Dense(32=>32), SOSRI + RSwM3, :unbiased local reg, tol 0.14; fwd + TrackerAdjoint",
+                                 "batch": B, "l2": "working set 16 KB per array: cache resident by construction"},
+                      "nfe_per_step": info["nfe"], "steps_fwd": [info["acc"], info["rej"]],
+                      "e2e": {"value": B / (ms_e / 1e3), "unit": "samples/s", "ms_per_step": ms_e,
+                              "h2d_bytes_per_step": 4 * (32 * B * 2 + ps.size), "d2h_bytes_per_step": 4 * (32 * B * 3 + ps.size)},
+                      "gpu_launches": int(info["launches"] * args.steps), "clocks": clk,
+                      "roofline": {"bound": "latency", "kernel": "sde_solve_kernel (persistent cooperative kernel, one grid.sync "
+                                   "per attempt)", "achieved": None, "peak": None, "unit": None, "frac": None, "traffic": None,
+                                   "us_per_attempt": 1e3 * ms / max(1, info["acc"] + info["rej"])},
+                      "cpu_baseline": {"value": B / dt, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
+                                       "sample": f"the whole workload, 1 iteration ({dt:.2f} s), numpy float32 oracle"}}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -371,8 +505,13 @@ def main():
     ap.add_argument("--ref-batch", type=int, default=512, help="bounded sample for the CPU reference")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="mnist_ode", choices=["mnist_ode", "mnist_sde"],
+                    help="mnist_ode (default, the headline metric) or the secondary mnist_sde config")
+    ap.add_argument("--sde-batch", type=int, default=128)
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.workload == "mnist_sde":
+        run_sde(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_native(args)

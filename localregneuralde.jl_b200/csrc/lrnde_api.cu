@@ -266,6 +266,7 @@ struct MlpEval {
   std::vector<float*> packW, packWT;  // tcgen05 path: tf32 hi/lo shared-memory images of the weights
   bool use_umma = false;
   bool use_cluster = true;
+  int max_layers = 1 << 30;  // profiling probe: evaluate only the first layers
   int passes = 3;
   float* ybuf = nullptr;
   float* delta[2] = {nullptr, nullptr};
@@ -442,7 +443,7 @@ struct MlpEval {
   void forward(const LinComb* in, const int* done, const LinComb* out = nullptr,
                bool side_to_in_dst = false) {
     const int L = (int)m->layers.size();
-    for (int l = 0; l < L; ++l) {
+    for (int l = 0; l < std::min(L, max_layers); ++l) {
       DenseP p = layer_fwd(l, in, nullptr);
       if (l == L - 1) { p.ydesc = out ? out : in; p.y_off = 0; } else p.Y = act[l];
       if (l == 0 && side_to_in_dst) p.side_desc = in;

@@ -365,6 +365,9 @@ extern "C" int lrnde_profile_feval(lrnde_ctx* ctx, const lrnde_model* m, const l
   LR_CUDA(cudaMemcpyAsync(ddesc.p, &d, sizeof(d), cudaMemcpyHostToDevice, st));
   MlpEval ev(ctx, m, ps, B, o ? o->precision : 0, false);
   ev.prepare();
+  // LRNDE_PROFILE_LAYERS=k: only the first k layers (k = 1 isolates the layer-1 kernel with the
+  // stage combination in its operand prologue)
+  if (const char* nl_env = getenv("LRNDE_PROFILE_LAYERS")) ev.max_layers = std::max(1, atoi(nl_env));
   long l0 = ctx->launches;
   ev.forward((const LinComb*)ddesc.p, nullptr);  // warm
   long per = ctx->launches - l0;

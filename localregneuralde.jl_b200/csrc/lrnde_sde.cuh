@@ -97,6 +97,7 @@ __device__ void sde_mlp_fwd(const SdeNet& n, const float* W, const float* x, flo
         const float4 w = *reinterpret_cast<const float4*>(Wl + in * outp + r0);
         acc.x = fmaf(w.x, t, acc.x); acc.y = fmaf(w.y, t, acc.y); acc.z = fmaf(w.z, t, acc.z); acc.w = fmaf(w.w, t, acc.w);
       }
+#pragma unroll 8
       for (int i = 0; i < in; ++i) {
         const float xv = cur[i * T.SP + s];
         const float4 w = *reinterpret_cast<const float4*>(Wl + i * outp + r0);
@@ -143,6 +144,7 @@ __device__ void sde_mlp_vjp(const SdeNet& n, const float* W, float* G, const flo
       if (r >= out) continue;
       float acc = 0.0f;
       if (i < in) {
+#pragma unroll 8
         for (int s = 0; s < T.S; ++s) acc = fmaf(xin[i * T.SP + s], dcur[r * T.SP + s], acc);
       } else {
         for (int s = 0; s < T.S; ++s) acc += dcur[r * T.SP + s];
@@ -157,6 +159,7 @@ __device__ void sde_mlp_vjp(const SdeNet& n, const float* W, float* G, const flo
       for (int item = T.tid; item < nb * T.S; item += T.nthr) {
         const int s = item % T.S, i0 = (item / T.S) << 2;
         float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
         for (int r = 0; r < out; ++r) {
           const float d = dcur[r * T.SP + s];
 #pragma unroll
@@ -354,6 +357,16 @@ __device__ double sde_block_sum(double v, double* red) {
   return tot;
 }
 
+
+// Sum of slot `k` of every CTA's partial record, identical on every CTA: lane l adds the records
+// l, l + 32, ... in order, then a fixed shuffle tree.  Call from all threads of warp 0.
+__device__ __forceinline__ double sde_partials_sum(const double* base, int nblk, int k) {
+  double v = 0.0;
+  for (int i = threadIdx.x & 31; i < nblk; i += 32) v += base[(size_t)i * 4 + k];
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
 // ---------------------------------------------------------------- kernel parameters
 struct SdeShared {  // controller state, identical in every CTA
   float t, dt, qold, tnew;
@@ -460,11 +473,15 @@ __device__ float sde_initdt_coop(const SdeSolveP& p, const float* Wf, const floa
   double* mine = p.partials + ((size_t)(parity_base & 1) * gridDim.x + blockIdx.x) * 4;
   if (threadIdx.x == 0) { mine[0] = s0; mine[1] = s1; }
   grid.sync();
-  double t0s = 0.0, t1s = 0.0;
-  for (unsigned i = 0; i < gridDim.x; ++i) {
-    const double* q = p.partials + ((size_t)(parity_base & 1) * gridDim.x + i) * 4;
-    t0s += q[0]; t1s += q[1];
+  __shared__ double s_tot[2];
+  if (threadIdx.x < 32) {
+    const double* q = p.partials + (size_t)(parity_base & 1) * gridDim.x * 4;
+    const double a = sde_partials_sum(q, gridDim.x, 0), c = sde_partials_sum(q, gridDim.x, 1);
+    if (threadIdx.x == 0) { s_tot[0] = a; s_tot[1] = c; }
   }
+  __syncthreads();
+  const double t0s = s_tot[0], t1s = s_tot[1];
+  __syncthreads();
   const float d0 = sqrtf((float)(t0s / (double)n_total)), d1 = sqrtf((float)(t1s / (double)n_total));
   float dt0 = (d0 < 1e-5f || d1 < 1e-5f) ? 1e-6f : 0.01f * (d0 / d1);
   dt0 = fminf(dt0, dtmax);
@@ -500,8 +517,13 @@ __device__ float sde_initdt_coop(const SdeSolveP& p, const float* Wf, const floa
   double* mine2 = p.partials + ((size_t)((parity_base + 1) & 1) * gridDim.x + blockIdx.x) * 4;
   if (threadIdx.x == 0) mine2[0] = s2;
   grid.sync();
-  double t2s = 0.0;
-  for (unsigned i = 0; i < gridDim.x; ++i) t2s += p.partials[((size_t)((parity_base + 1) & 1) * gridDim.x + i) * 4];
+  if (threadIdx.x < 32) {
+    const double a = sde_partials_sum(p.partials + (size_t)((parity_base + 1) & 1) * gridDim.x * 4, gridDim.x, 0);
+    if (threadIdx.x == 0) s_tot[0] = a;
+  }
+  __syncthreads();
+  const double t2s = s_tot[0];
+  __syncthreads();
   const float d2 = sqrtf((float)(t2s / (double)n_total)) / dt0;
   const float mx = fmaxf(d1, d2);
   float dt1;
@@ -595,9 +617,13 @@ __global__ void __launch_bounds__(SDE_THREADS, 1) sde_solve_kernel(SdeSolveP p) 
     if (tid == 0) p.partials[((size_t)parity * gridDim.x + blockIdx.x) * 4] = part;
     grid.sync();
     // ---- controller (thread 0 of every CTA, identical arithmetic)
+    if (tid < 32) {
+      const double a = sde_partials_sum(p.partials + (size_t)parity * gridDim.x * 4, gridDim.x, 0);
+      if (tid == 0) red[0] = a;
+    }
+    __syncthreads();
     if (tid == 0) {
-      double tot = 0.0;
-      for (unsigned i = 0; i < gridDim.x; ++i) tot += p.partials[((size_t)parity * gridDim.x + i) * 4];
+      const double tot = red[0];
       const float eest = sqrtf((float)(tot / (double)DB));
       C.iter++;
       const int li = C.natt++;
@@ -841,7 +867,7 @@ __global__ void __launch_bounds__(SDE_THREADS, 1) sde_reg_kernel(SdeSolveP p) {
   grid.sync();
   if (blockIdx.x == 0 && tid == 0) {
     double tot = 0.0;
-    for (unsigned i = 0; i < gridDim.x; ++i) tot += p.partials[((size_t)0 * gridDim.x + i) * 4 + 2];
+    for (unsigned i = 0; i < gridDim.x; ++i) tot += p.partials[(size_t)i * 4 + 2];
     p.out_f[1] = dt;
     p.out_f[2] = sqrtf((float)(tot / (double)DB));
   }
@@ -1106,6 +1132,18 @@ struct lrnde_sde_tape {
   ~lrnde_sde_tape() { for (void* p : owned) ctx->release(p); }
 };
 
+// device limits, queried once per device (cudaGetDeviceProperties is a slow, lock-taking call)
+static void sde_device_limits(int device, int* n_sm, size_t* smem_optin) {
+  static int cached_dev = -1, c_sm = 0, c_smem = 0;
+  if (cached_dev != device) {
+    LR_CUDA(cudaDeviceGetAttribute(&c_sm, cudaDevAttrMultiProcessorCount, device));
+    LR_CUDA(cudaDeviceGetAttribute(&c_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    cached_dev = device;
+  }
+  *n_sm = c_sm;
+  *smem_optin = (size_t)c_smem;
+}
+
 static SdeNet sde_make_net(const lrnde_model* m, const char* what) {
   SdeNet n;
   memset(&n, 0, sizeof(n));
@@ -1189,24 +1227,23 @@ extern "C" int lrnde_sde_forward(lrnde_ctx* ctx, const lrnde_model* drift, const
   const cudaMemcpyKind out_kind = host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
 
   // ---- launch shape: S samples per tile, one CTA per SM at most (cooperative launch)
-  cudaDeviceProp prop;
-  LR_CUDA(cudaGetDeviceProperties(&prop, ctx->device));
+  int n_sm = 0;
+  size_t smem_optin = 0;
+  sde_device_limits(ctx->device, &n_sm, &smem_optin);
   int S = 32;
-  while (S > 8 && ((B + S - 1) / S) < prop.multiProcessorCount / 2) S >>= 1;
+  while (S > 8 && ((B + S - 1) / S) < n_sm / 2) S >>= 1;
   size_t smem_f = 0, smem_b = 0;
   for (;; S >>= 1) {
     smem_f = sde_smem_bytes(T->nf, T->ng, D, S + 1, false);
     smem_b = sde_smem_bytes(T->nf, T->ng, D, S + 1, true);
-    if (smem_b <= (size_t)prop.sharedMemPerBlockOptin) break;
+    if (smem_b <= smem_optin) break;
     if (S <= 4) lr_fail(LRNDE_EINVAL, "SDE networks / state too large for the shared-memory resident path (%zu bytes)", smem_b);
   }
   T->S = S; T->SP = S + 1;
   const int ntiles = (int)((B + S - 1) / S);
   LR_CUDA(cudaFuncSetAttribute(sde_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f));
   LR_CUDA(cudaFuncSetAttribute(sde_reg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f));
-  int occ = 0;
-  LR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sde_solve_kernel, SDE_THREADS, smem_f));
-  const int max_grid = std::max(1, occ) * prop.multiProcessorCount;
+  const int max_grid = n_sm;   // __launch_bounds__(SDE_THREADS, 1): one CTA per SM is always co-resident
   T->tiles_per_cta = (ntiles + max_grid - 1) / max_grid;
   T->grid = (ntiles + T->tiles_per_cta - 1) / T->tiles_per_cta;
 
@@ -1445,18 +1482,19 @@ extern "C" int lrnde_sde_aux_step(lrnde_ctx* ctx, const lrnde_model* drift, cons
   p.ng = sde_make_net(diffusion, "diffusion");
   const int D = drift->D;
   const size_t DB = (size_t)D * (size_t)B;
-  cudaDeviceProp prop;
-  LR_CUDA(cudaGetDeviceProperties(&prop, ctx->device));
+  int n_sm = 0;
+  size_t smem_optin = 0;
+  sde_device_limits(ctx->device, &n_sm, &smem_optin);
   int S = 32;
-  while (S > 8 && ((B + S - 1) / S) < prop.multiProcessorCount / 2) S >>= 1;
+  while (S > 8 && ((B + S - 1) / S) < n_sm / 2) S >>= 1;
   size_t smem = 0;
   for (;; S >>= 1) {
     smem = sde_smem_bytes(p.nf, p.ng, D, S + 1, false);
-    if (smem <= (size_t)prop.sharedMemPerBlockOptin) break;
+    if (smem <= smem_optin) break;
     if (S <= 4) lr_fail(LRNDE_EINVAL, "SDE networks / state too large for the shared-memory resident path");
   }
   const int ntiles = (int)((B + S - 1) / S);
-  const int max_grid = 4 * prop.multiProcessorCount;
+  const int max_grid = 4 * n_sm;
   p.S = S; p.SP = S + 1; p.B = (int)B; p.kind = kind;
   p.tiles_per_cta = (ntiles + max_grid - 1) / max_grid;
   const int grid = (ntiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
