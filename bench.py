@@ -55,6 +55,8 @@ class ClockSampler:
         self.index, self.proc, self.path = index, None, f"/tmp/lrnde_clocks_{os.getpid()}.csv"
 
     def start(self):
+        if os.environ.get("LRNDE_NO_CLOCKS"):      # diagnostic: measure the sampler's own perturbation
+            return
         try:
             self.f = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
@@ -260,7 +262,8 @@ def run_native(args):
                     loss=float(loss.value) + W_REG * float(st2["reg_val"]), retcode=sol.retcode,
                     phases_us=dict(fwd_solve=sol.stats.reserved[0], saves=sol.stats.reserved[1],
                                    reg_step=sol.stats.reserved[2], adjoint=sol.bwd_stats.reserved[3],
-                                   reg_pullback=sol.bwd_stats.reserved[4]))
+                                   reg_pullback=sol.bwd_stats.reserved[4], fwd_setup=sol.stats.reserved[5],
+                                   bwd_setup=sol.bwd_stats.reserved[5]))
         sol.free()
         return st2
 

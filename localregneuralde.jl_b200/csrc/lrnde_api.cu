@@ -267,6 +267,8 @@ struct MlpEval {
   bool use_umma = false;
   bool use_cluster = true;
   int max_layers = 1 << 30;  // profiling probe: evaluate only the first layers
+  int nacc_max = 8;
+  bool use_lean = true;
   int passes = 3;
   float* ybuf = nullptr;
   float* delta[2] = {nullptr, nullptr};
@@ -279,6 +281,8 @@ struct MlpEval {
     const int L = (int)m->layers.size();
     use_umma = (precision != LRNDE_PREC_FP32_SIMT);
     use_cluster = (getenv("LRNDE_NO_CLUSTER") == nullptr);
+    if (const char* e = getenv("LRNDE_NACC")) nacc_max = std::max(1, std::min(8, atoi(e)));
+    use_lean = (getenv("LRNDE_NO_LEAN") == nullptr);
     passes = (precision == LRNDE_PREC_TF32) ? 1 : 3;
     act.assign(L, nullptr);
     packW.assign(L, nullptr);
@@ -316,7 +320,7 @@ struct MlpEval {
         int us = 0, uc = 0;
         if (use_umma && std::min(Li.out, naug) <= 128) {
           int n_mt = (std::max(Li.out, naug) + 127) / 128;
-          us = std::max(1, std::min(64, 256 / n_mt));
+          us = std::max(1, std::min(64, 148 / n_mt));  // one CTA per SM (196 KB of shared memory): a single wave
           uc = (int)((B + us - 1) / us);
           uc = std::max(32, ((uc + 31) / 32) * 32);
           us = (int)((B + uc - 1) / uc);
@@ -383,10 +387,14 @@ struct MlpEval {
     using C = umma::Cfg<NT>;
     static bool attr_set = false;
     if (!attr_set) {
-      LR_CUDA(cudaFuncSetAttribute(umma::dense_kernel<NT, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::ring_smem()));
-      LR_CUDA(cudaFuncSetAttribute(umma::dense_kernel<NT, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::res_smem(C::kMaxResKC)));
-      LR_CUDA(cudaFuncSetAttribute(umma::dense_kernel<NT, false, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::ring_smem()));
-      LR_CUDA(cudaFuncSetAttribute(umma::dense_kernel<NT, true, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::res_smem(C::kMaxResKC)));
+      LR_CUDA(cudaFuncSetAttribute(umma::dense_kernel<NT, false, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::ring_smem()));
+      LR_CUDA(cudaFuncSetAttribute(umma::dense_kernel<NT, true, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::res_smem(C::kMaxResKC)));
+      LR_CUDA(cudaFuncSetAttribute(umma::dense_kernel<NT, false, CL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::ring_smem()));
+      LR_CUDA(cudaFuncSetAttribute(umma::dense_kernel<NT, true, CL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::res_smem(C::kMaxResKC)));
+      LR_CUDA(cudaFuncSetAttribute(umma::dense_kernel<NT, false, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::ring_smem()));
+      LR_CUDA(cudaFuncSetAttribute(umma::dense_kernel<NT, true, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::res_smem(C::kMaxResKC)));
+      LR_CUDA(cudaFuncSetAttribute(umma::dense_kernel<NT, false, CL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::ring_smem()));
+      LR_CUDA(cudaFuncSetAttribute(umma::dense_kernel<NT, true, CL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::res_smem(C::kMaxResKC)));
       attr_set = true;
     }
     umma::UmmaP q;
@@ -396,6 +404,7 @@ struct MlpEval {
     q.KC = chunks_k(p.K + p.td + p.bias);
     q.passes = passes;
     q.replicas = umma::kReplicas;
+    q.nacc_max = nacc_max;
     unsigned ntile = (unsigned)((p.N + NT - 1) / NT);
     const bool resident = q.n_mt > 1 && q.n_mt * NT <= 512 && q.KC <= C::kMaxResKC;
     const bool cluster = ntile >= (unsigned)CL && use_cluster;
@@ -413,13 +422,22 @@ struct MlpEval {
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
+    // lean instantiation (no scalar fallback / activation switch in the hot loops) when the shape allows:
+    // K % 4 == 0, rows 16-byte aligned (library buffers are 256-byte aligned and D*B % 4 == 0 follows from
+    // ldx % 4 == 0), no input activation, tanh / identity epilogues
+    const bool lean = use_lean && (p.K % 4 == 0) && (p.ldx % 4 == 0) && p.in_act == ACT_IDENTITY &&
+                      (p.act == ACT_IDENTITY || p.act == ACT_TANH) &&
+                      (p.dact < 0 || p.dact == ACT_IDENTITY || p.dact == ACT_TANH) &&
+                      (!p.X || (((uintptr_t)p.X) & 15) == 0) && (!p.side || (((uintptr_t)p.side) & 15) == 0);
+#define LR_LAUNCH_DENSE(RES, CLV, GENV) LR_CUDA(cudaLaunchKernelEx(&cfg, umma::dense_kernel<NT, RES, CLV, GENV>, q))
     if (resident) {
-      if (cluster) LR_CUDA(cudaLaunchKernelEx(&cfg, umma::dense_kernel<NT, true, CL>, q));
-      else LR_CUDA(cudaLaunchKernelEx(&cfg, umma::dense_kernel<NT, true, 1>, q));
+      if (cluster) { if (lean) LR_LAUNCH_DENSE(true, CL, false); else LR_LAUNCH_DENSE(true, CL, true); }
+      else { if (lean) LR_LAUNCH_DENSE(true, 1, false); else LR_LAUNCH_DENSE(true, 1, true); }
     } else {
-      if (cluster) LR_CUDA(cudaLaunchKernelEx(&cfg, umma::dense_kernel<NT, false, CL>, q));
-      else LR_CUDA(cudaLaunchKernelEx(&cfg, umma::dense_kernel<NT, false, 1>, q));
+      if (cluster) { if (lean) LR_LAUNCH_DENSE(false, CL, false); else LR_LAUNCH_DENSE(false, CL, true); }
+      else { if (lean) LR_LAUNCH_DENSE(false, 1, false); else LR_LAUNCH_DENSE(false, 1, true); }
     }
+#undef LR_LAUNCH_DENSE
     LR_COUNT(ctx);
   }
 
@@ -882,12 +900,17 @@ static void lr_grow_tape(Solver& S) {
 
 static size_t lr_tape_budget(lrnde_ctx* ctx) {
   if (ctx->tape_budget) return (size_t)ctx->tape_budget;
+  // cudaMemGetInfo takes a driver lock (measured 0.08 ... 60 ms per call on a shared host), so the
+  // automatic budget is computed once per ctx; a failing allocation still falls back to
+  // release_all_unused() + retry in lrnde_ctx::alloc
+  if (ctx->auto_budget) return ctx->auto_budget;
   size_t fr = 0, tot = 0;
   LR_CUDA(cudaMemGetInfo(&fr, &tot));
   size_t pooled = 0;
   for (auto& b : ctx->pool)
     if (!b.used) pooled += b.bytes;
-  return (size_t)(0.6 * (double)(fr + pooled));
+  ctx->auto_budget = (size_t)(0.6 * (double)(fr + pooled));
+  return ctx->auto_budget;
 }
 
 // host-side evaluation of "sol(t)" on the dense forward tape: descriptor of the interpolant
@@ -992,6 +1015,7 @@ extern "C" int lrnde_ode_forward(lrnde_ctx* ctx, const lrnde_model* m, const lrn
   LR_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   memset(stats, 0, sizeof(*stats));
+  const long t_call = lr_now_us();
   const long launches0 = ctx->launches;
   const int D = m->D;
   const size_t DB = (size_t)D * B;
@@ -1008,10 +1032,13 @@ extern "C" int lrnde_ode_forward(lrnde_ctx* ctx, const lrnde_model* m, const lrn
   T->reg_mode = o->reg_mode;
   T->ps = (float*)ctx->alloc(sizeof(float) * P);
   LR_CUDA(cudaMemcpyAsync(T->ps, ps, sizeof(float) * P, in_kind, st));
+  const bool timing = getenv("LRNDE_TIMING") != nullptr;
+  const long tq0 = lr_now_us();
 
   // ---- dense tape
   size_t slot_bytes = sizeof(float) * 7 * DB;
   size_t budget_slots = std::max<size_t>(3, lr_tape_budget(ctx) / slot_bytes);
+  const long tq1 = lr_now_us();
   int cap = (int)std::min<size_t>({(size_t)o->maxiters + 2, (size_t)96, budget_slots});
   cap = std::max(cap, 3);
   T->fwd = std::make_unique<Solver>(ctx, DB, DB, cap, 0, o->maxiters + 1);
@@ -1020,10 +1047,12 @@ extern "C" int lrnde_ode_forward(lrnde_ctx* ctx, const lrnde_model* m, const lrn
   F.init_ctrl(o->t0, o->t2, o->t2, o->maxiters, o->pow_mode, o->abstol, o->reltol);
   LR_CUDA(cudaMemcpyAsync(F.tape, x, sizeof(float) * DB, in_kind, st));
   LR_CUDA(cudaMemcpyAsync(F.ts, &o->t0, sizeof(float), cudaMemcpyHostToDevice, st));
+  const long tq2 = lr_now_us();
 
   const bool need_vjp = false;
   MlpEval ev(ctx, m, T->ps, B, o->precision, need_vjp);
   ev.prepare();
+  const long tq3 = lr_now_us();
   auto eval = [&](const LinComb* in, const LinComb*, const int* done, const LinComb* out, bool side) {
     ev.forward(in, done, out, side);
   };
@@ -1031,6 +1060,9 @@ extern "C" int lrnde_ode_forward(lrnde_ctx* ctx, const lrnde_model* m, const lrn
   F.build_graphs(o->loop_mode);
   F.upload();
   const long t_start = lr_now_us();
+  if (timing)
+    fprintf(stderr, "[lrnde] fwd setup us: stage_ps %ld budget %ld tape_alloc %ld prepare %ld graphs %ld (pool %zu blocks)\n",
+            tq0 - t_call, tq1 - tq0, tq2 - tq1, tq3 - tq2, t_start - tq3, ctx->pool.size());
   lr_solver_start(F, eval, 1);
   for (;;) {
     F.run_segment();
@@ -1158,6 +1190,7 @@ extern "C" int lrnde_ode_forward(lrnde_ctx* ctx, const lrnde_model* m, const lrn
   stats->reserved[0] = (int32_t)(t_solve - t_start);
   stats->reserved[1] = (int32_t)(t_saves - t_solve);
   stats->reserved[2] = (int32_t)(lr_now_us() - t_saves);
+  stats->reserved[5] = (int32_t)(t_start - t_call);   // setup: staging, weight images, graph capture + instantiation
   if (o->keep_tape) *tape_out = T.release();
   else if (tape_out) *tape_out = nullptr;
   LR_API_END
@@ -1208,6 +1241,7 @@ extern "C" int lrnde_ode_backward(lrnde_ctx* ctx, const lrnde_model* m, lrnde_ta
   const size_t len = DB + P;
   const int host = o.host_buffers;
   const long launches0 = ctx->launches;
+  const long tb_call = lr_now_us();
   Solver& F = *T->fwd;
   const int nsteps = (int)T->fts.size() - 1;
   const float t0 = T->fts.front(), t2 = T->fts.back();
@@ -1356,6 +1390,7 @@ extern "C" int lrnde_ode_backward(lrnde_ctx* ctx, const lrnde_model* m, lrnde_ta
     stats->retcode_bwd = retcode_bwd;
     stats->gpu_launches = (int)((ctx->launches - launches0) + body_launches);
     stats->reserved[3] = (int32_t)(tb_adj - tb_start);
+    stats->reserved[5] = (int32_t)(tb_start - tb_call);
     stats->reserved[4] = (int32_t)(lr_now_us() - tb_adj);
   }
   LR_API_END

@@ -35,6 +35,7 @@ struct lrnde_ctx {
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   uint64_t tape_budget = 0;
+  size_t auto_budget = 0;  // 60% of free HBM at first use (when tape_budget == 0)
   std::vector<PoolBlock> pool;
   void* pinned = nullptr;  // small host mirror for state read-back
   size_t pinned_bytes = 0;

@@ -33,8 +33,10 @@
 #ifdef LRNDE_UMMA_TRACE
 __device__ long long g_umma_trace[8192];
 #define UMMA_TRACE(slot, it) do { if (blockIdx.x == 1 && blockIdx.y == 0 && (it) < 64) g_umma_trace[(RESIDENT ? 512 : 0) + (slot) * 64 + (it)] = clock64(); } while (0)
+#define WG_TRACE(slot, it) do { if (blockIdx.x == 1 && blockIdx.y == 1 && (it) < 64) g_umma_trace[1024 + (slot) * 64 + (it)] = clock64(); } while (0)
 #else
 #define UMMA_TRACE(slot, it) do { } while (0)
+#define WG_TRACE(slot, it) do { } while (0)
 #endif
 
 namespace umma {
@@ -225,6 +227,7 @@ struct UmmaP {
   int KC;              // number of 32-float K chunks (covers K + td + bias)
   int passes;          // 3 = 3xTF32, 1 = TF32
   int replicas;        // copies of the packed images (stride n_mt * KC chunks)
+  int nacc_max;        // RING: upper bound on the number of split TMEM accumulators
 };
 constexpr int kReplicas = 4;
 constexpr int kBulkParts = 2;
@@ -253,27 +256,55 @@ struct ProdCtx {
   float* side;  // optional fp32 copy of the combined tile (only the blockIdx.y == 0 CTAs write it)
 };
 
-template <int NS1>  // NS1 = 1 + number of lincomb sources held in registers
+// GEN = false is the lean instantiation for the common case (K % 4 == 0, 16-byte aligned operands, no
+// input activation): no scalar fallback in the hot loop -- the TDChain time row and the bias row are the
+// first elements of the float4 group that starts at k == K.  The host picks it (MlpEval::dense).
+template <int NS1, bool GEN>  // NS1 = 1 + number of lincomb sources held in registers
 __device__ __forceinline__ void load_group(const ProdCtx& c, int row, int cch, int kc, float4 (&buf)[NS1]) {
   const DenseP& p = *c.p;
   const int n = c.n0 + row, k = kc * kChunkK + cch * 4;
-  if (n < p.N && c.vec && k + 3 < p.K) {
+  if (n < p.N && (GEN ? (c.vec && k + 3 < p.K) : (k < p.K))) {
     const size_t off = (size_t)n * p.ldx + k;
-    buf[0] = c.sd->base ? *reinterpret_cast<const float4*>(c.sd->base + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+    // streaming loads (L2 only): every byte is used exactly once by this CTA, and the L1 data array is
+    // the shared-memory array the MMA operands and the bulk copies already saturate
+    buf[0] = c.sd->base ? __ldcg(reinterpret_cast<const float4*>(c.sd->base + off)) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int s = 0; s < NS1 - 1; ++s)
-      if (s < c.nsrc) buf[s + 1] = *reinterpret_cast<const float4*>(c.sd->src[s] + off);
+      if (s < c.nsrc) buf[s + 1] = __ldcg(reinterpret_cast<const float4*>(c.sd->src[s] + off));
   }
 }
 
-template <int NS1, int NT>
+template <int NS1, int NT, bool GEN>
 __device__ __forceinline__ void store_group(const ProdCtx& c, int row, int cch, int kc, const float4 (&buf)[NS1],
                                             uint8_t* dst) {
   const DenseP& p = *c.p;
   const LinComb& sd = *c.sd;
   const int n = c.n0 + row, k = kc * kChunkK + cch * 4;
   float v[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-  if (n < p.N) {
+  if (!GEN) {
+    if (n < p.N) {
+      if (k < p.K) {
+        float4 x = buf[0];
+        if (NS1 > 1 && c.nsrc) {
+          float4 inner = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int s = 0; s < NS1 - 1; ++s)
+            if (s < c.nsrc) {
+              const float cf = sd.coef[s];
+              inner.x = fmaf(cf, buf[s + 1].x, inner.x); inner.y = fmaf(cf, buf[s + 1].y, inner.y);
+              inner.z = fmaf(cf, buf[s + 1].z, inner.z); inner.w = fmaf(cf, buf[s + 1].w, inner.w);
+            }
+          x.x = fmaf(sd.scale, inner.x, x.x); x.y = fmaf(sd.scale, inner.y, x.y);
+          x.z = fmaf(sd.scale, inner.z, x.z); x.w = fmaf(sd.scale, inner.w, x.w);
+        }
+        if (c.side) *reinterpret_cast<float4*>(c.side + (size_t)n * p.ldx + k) = x;
+        v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w;
+      } else if (k == p.K) {
+        if (p.td) { v[0] = c.tval; if (p.bias) v[1] = 1.0f; }
+        else if (p.bias) v[0] = 1.0f;
+      }
+    }
+  } else if (n < p.N) {
     const size_t off = (size_t)n * p.ldx + k;
     if (c.vec && k + 3 < p.K) {
       float4 inner = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -322,7 +353,7 @@ __device__ __forceinline__ void store_group(const ProdCtx& c, int row, int cch, 
 // CL = thread-block cluster size along the sample tiles (1 or 4): the CTAs of a cluster read the
 // same weight chunks, so each loads a 1/CL slice and multicasts it to all of them (L2 -> SM
 // traffic of the weight images / CL); stages are released cluster-wide by multicast commits.
-template <int NT, bool RESIDENT, int CL>
+template <int NT, bool RESIDENT, int CL, bool GEN>
 __global__ void __launch_bounds__(kThreads, 1) dense_kernel(UmmaP q) {
   const DenseP& p = q.d;
   if (p.done && *p.done) return;
@@ -349,7 +380,7 @@ __global__ void __launch_bounds__(kThreads, 1) dense_kernel(UmmaP q) {
   const int nchunks = mt_count * KC;
   // RING: the K loop is split over several TMEM accumulators that the epilogue adds in fp32
   // (the tensor core accumulates with truncation; shorter chains keep 3xTF32 at fp32 level)
-  const int nacc = RESIDENT ? 1 : min(512 / NT, KC);
+  const int nacc = RESIDENT ? 1 : min(min(512 / NT, KC), q.nacc_max);
   const int ncols_used = RESIDENT ? mt_count * NT : nacc * NT;
   // chunk order rotated per CTA (accumulation order is free): de-synchronises the CTAs.
   // RESIDENT rotates whole weight tiles so that tiles finish one after the other and the
@@ -477,6 +508,7 @@ __global__ void __launch_bounds__(kThreads, 1) dense_kernel(UmmaP q) {
     pc.side = (blockIdx.y == 0) ? (p.side_desc ? p.side_desc->dst : p.side) : nullptr;
     pc.vec = (p.ldx % 4 == 0) && ((((uintptr_t)sdesc.base) & 15) == 0) && ((((uintptr_t)pc.side) & 15) == 0);
     for (int k = 0; k < sdesc.n; ++k) pc.vec = pc.vec && ((((uintptr_t)sdesc.src[k]) & 15) == 0);
+    if (!GEN && !pc.vec) asm volatile("trap;");   // the host selected the lean kernel for a misaligned operand
 
     // software-pipelined producer: DEPTH chunks of loads in flight per thread, about 8 float4
     // registers of load buffers whatever the number of lincomb sources
@@ -492,7 +524,7 @@ __global__ void __launch_bounds__(kThreads, 1) dense_kernel(UmmaP q) {
 #pragma unroll
           for (int g = 0; g < GPT; ++g) {
             const int gi = tid + g * PT;
-            load_group<NS1>(pc, gi >> 3, gi & 7, chunk_of(d), buf[d][g]);
+            load_group<NS1, GEN>(pc, gi >> 3, gi & 7, chunk_of(d), buf[d][g]);
           }
         }
       for (int it0 = 0; it0 < total; it0 += DEPTH) {
@@ -507,14 +539,14 @@ __global__ void __launch_bounds__(kThreads, 1) dense_kernel(UmmaP q) {
 #pragma unroll
             for (int g = 0; g < GPT; ++g) {
               const int gi = tid + g * PT;
-              store_group<NS1, NT>(pc, gi >> 3, gi & 7, chunk_of(it), buf[d][g], dst);
+              store_group<NS1, NT, GEN>(pc, gi >> 3, gi & 7, chunk_of(it), buf[d][g], dst);
             }
             if (tid == 0) UMMA_TRACE(4, it);
             if (it + DEPTH < total) {
 #pragma unroll
               for (int g = 0; g < GPT; ++g) {
                 const int gi = tid + g * PT;
-                load_group<NS1>(pc, gi >> 3, gi & 7, chunk_of(it + DEPTH), buf[d][g]);
+                load_group<NS1, GEN>(pc, gi >> 3, gi & 7, chunk_of(it + DEPTH), buf[d][g]);
               }
             }
             if (!RESIDENT) {
@@ -578,15 +610,50 @@ __global__ void __launch_bounds__(kThreads, 1) dense_kernel(UmmaP q) {
           for (int j = 0; j < 16; ++j) accv[j] += __uint_as_float(r[j]);
         }
         if (m < p.M) {
+          if (GEN) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int n = n0 + c0 + j;
-            if (n < p.N) {
-              float v = accv[j];
-              if (p.pre) p.pre[(size_t)n * p.ldpre + m] = v;
-              if (p.dact >= 0) v = v * lr_dact(p.dact, p.dpre[(size_t)n * p.lddpre + m]);
-              else v = lr_act(p.act, v);
-              Y[(size_t)n * p.ldy + m] = v * p.out_scale;
+            for (int j = 0; j < 16; ++j) {
+              const int n = n0 + c0 + j;
+              if (n < p.N) {
+                float v = accv[j];
+                if (p.pre) p.pre[(size_t)n * p.ldpre + m] = v;
+                if (p.dact >= 0) v = v * lr_dact(p.dact, p.dpre[(size_t)n * p.lddpre + m]);
+                else v = lr_act(p.act, v);
+                Y[(size_t)n * p.ldy + m] = v * p.out_scale;
+              }
+            }
+          } else {
+            // lean: act in {identity, tanh}, dact in {none, identity, tanh}; the mode is chosen once
+            const int mode = (p.dact == ACT_TANH) ? 2 : ((p.dact < 0 && p.act == ACT_TANH) ? 1 : 0);
+            const float os = p.out_scale;
+            if (mode == 0) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const int n = n0 + c0 + j;
+                if (n < p.N) {
+                  if (p.pre) p.pre[(size_t)n * p.ldpre + m] = accv[j];
+                  Y[(size_t)n * p.ldy + m] = accv[j] * os;
+                }
+              }
+            } else if (mode == 1) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const int n = n0 + c0 + j;
+                if (n < p.N) {
+                  if (p.pre) p.pre[(size_t)n * p.ldpre + m] = accv[j];
+                  Y[(size_t)n * p.ldy + m] = tanhf(accv[j]) * os;
+                }
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const int n = n0 + c0 + j;
+                if (n < p.N) {
+                  if (p.pre) p.pre[(size_t)n * p.ldpre + m] = accv[j];
+                  const float y = tanhf(p.dpre[(size_t)n * p.lddpre + m]);
+                  Y[(size_t)n * p.ldy + m] = accv[j] * (1.0f - y * y) * os;
+                }
+              }
             }
           }
         }
@@ -716,6 +783,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(WgradUP q) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
+  if (threadIdx.x == 0) WG_TRACE(7, 0);
 
   if (warp == 1) {
     constexpr uint32_t idesc = make_idesc_mn(128, 128);
@@ -723,6 +791,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(WgradUP q) {
       const int s = it % NS, ph = (it / NS) & 1;
       mbar_wait(&full_bar[s], ph);
       tc_fence_after();
+      if (lane == 0) WG_TRACE(1, it);
       const uint32_t base = smem_u32(smem + (size_t)s * kWgStageBytes);
       const uint32_t p_hi = desc_lo_mn(base), p_lo = desc_lo_mn(base + 16384);
       const uint32_t q_hi = desc_lo_mn(base + 32768), q_lo = desc_lo_mn(base + 49152);
@@ -741,6 +810,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(WgradUP q) {
         }
         mma_commit(&empty_bar[s]);
         if (it == nchunks - 1) mma_commit(&done_bar);
+        WG_TRACE(2, it);
       }
       __syncwarp();
     }
@@ -749,12 +819,13 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(WgradUP q) {
     const int tid = threadIdx.x - 64;
     const bool pvec = ((((uintptr_t)q.P.ptr) & 15) == 0) && (q.P.ld % 4 == 0);
     const bool qvec = ((((uintptr_t)q.Q.ptr) & 15) == 0) && (q.Q.ld % 4 == 0);
-    for (int it = 0; it < nchunks; ++it) {
-      const int s = it % NS, ph = (it / NS) & 1;
-      uint8_t* stage = smem + (size_t)s * kWgStageBytes;
-      float4 v[4];
-      // 2048 float4 groups per chunk: [0,1024) operand P, [1024,2048) operand Q; group = (sample
-      // bl, float4 index c4 along the rows) so that a warp reads 512 contiguous bytes of a sample
+    // software-pipelined producer: kWgDepth chunks of loads in flight per thread (the loop is
+    // load-latency bound: one dependent global load per chunk otherwise)
+    constexpr int kWgDepth = 3;
+    float4 v[kWgDepth][4];
+    // 2048 float4 groups per chunk: [0,1024) operand P, [1024,2048) operand Q; group = (sample
+    // bl, float4 index c4 along the rows) so that a warp reads 512 contiguous bytes of a sample
+    auto load_chunk = [&](int it, float4 (&dst)[4]) {
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         const int gi = tid + g * PT;
@@ -762,35 +833,54 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(WgradUP q) {
         const int li = gi & 1023;
         const int bl = li >> 5, c4 = li & 31;
         const int b = b_begin + it * 32 + bl;
-        if (!isq) v[g] = wg_load(q.P, m0 + c4 * 4, b, b < b_end, tval, pvec);
-        else v[g] = wg_load(q.Q, c4 * 4, b, b < b_end, tval, qvec);
+        if (!isq) dst[g] = wg_load(q.P, m0 + c4 * 4, b, b < b_end, tval, pvec);
+        else dst[g] = wg_load(q.Q, c4 * 4, b, b < b_end, tval, qvec);
       }
-      mbar_wait(&empty_bar[s], ph ^ 1);
+    };
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const int gi = tid + g * PT;
-        const bool isq = gi >= 1024;
-        const int li = gi & 1023;
-        const int bl = li >> 5, c4 = li & 31;
-        const int grp = c4 >> 3, c32 = (c4 & 7) >> 1, half = c4 & 1, k4 = bl >> 2, r = bl & 3;
-        const uint32_t o = (uint32_t)((k4 * 4 + grp) * 512 + r * 128 + ((c32 ^ r) << 5) + half * 16);
-        float4 hi, lo;
-        if (q.passes == 3) {
-          hi = make_float4(tf32_rna(v[g].x), tf32_rna(v[g].y), tf32_rna(v[g].z), tf32_rna(v[g].w));
-          lo = make_float4(tf32_rna(v[g].x - hi.x), tf32_rna(v[g].y - hi.y), tf32_rna(v[g].z - hi.z),
-                           tf32_rna(v[g].w - hi.w));
-        } else { hi = v[g]; lo = make_float4(0.f, 0.f, 0.f, 0.f); }
-        uint8_t* img = stage + (isq ? 32768 : 0);
-        *reinterpret_cast<float4*>(img + o) = hi;
-        *reinterpret_cast<float4*>(img + 16384 + o) = lo;
+    for (int d = 0; d < kWgDepth; ++d)
+      if (d < nchunks) load_chunk(d, v[d]);
+    for (int it0 = 0; it0 < nchunks; it0 += kWgDepth) {
+#pragma unroll
+      for (int d = 0; d < kWgDepth; ++d) {
+        const int it = it0 + d;
+        if (it < nchunks) {
+          const int s = it % NS, ph = (it / NS) & 1;
+          uint8_t* stage = smem + (size_t)s * kWgStageBytes;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          if (tid == 0) WG_TRACE(3, it);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int gi = tid + g * PT;
+            const bool isq = gi >= 1024;
+            const int li = gi & 1023;
+            const int bl = li >> 5, c4 = li & 31;
+            const int grp = c4 >> 3, c32 = (c4 & 7) >> 1, half = c4 & 1, k4 = bl >> 2, r = bl & 3;
+            const uint32_t o = (uint32_t)((k4 * 4 + grp) * 512 + r * 128 + ((c32 ^ r) << 5) + half * 16);
+            const float4 x = v[d][g];
+            float4 hi, lo;
+            if (q.passes == 3) {
+              hi = make_float4(tf32_rna(x.x), tf32_rna(x.y), tf32_rna(x.z), tf32_rna(x.w));
+              lo = make_float4(tf32_rna(x.x - hi.x), tf32_rna(x.y - hi.y), tf32_rna(x.z - hi.z),
+                               tf32_rna(x.w - hi.w));
+            } else { hi = x; lo = make_float4(0.f, 0.f, 0.f, 0.f); }
+            uint8_t* img = stage + (isq ? 32768 : 0);
+            *reinterpret_cast<float4*>(img + o) = hi;
+            *reinterpret_cast<float4*>(img + 16384 + o) = lo;
+          }
+          if (tid == 0) WG_TRACE(4, it);
+          if (it + kWgDepth < nchunks) load_chunk(it + kWgDepth, v[d]);
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&full_bar[s]);
+        }
       }
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&full_bar[s]);
     }
     // epilogue: lane = row of P's tile, 128 columns = rows of Q
+    if (tid == 0) WG_TRACE(6, 0);
     mbar_wait(&done_bar, 0);
     tc_fence_after();
+    if (tid == 0) WG_TRACE(6, 1);
     const int quarter = (warp & 3) * 32;
     const int wgroup = (warp - 2) >> 2;
     const int m = m0 + quarter + lane;
@@ -822,8 +912,10 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(WgradUP q) {
       }
     }
     tc_fence_before();
+    if (tid == 0) WG_TRACE(6, 2);
   }
   __syncthreads();
+  if (threadIdx.x == 0) WG_TRACE(6, 3);
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128u) : "memory");
