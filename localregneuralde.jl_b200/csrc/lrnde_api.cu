@@ -320,7 +320,7 @@ struct MlpEval {
         int us = 0, uc = 0;
         if (use_umma && std::min(Li.out, naug) <= 128) {
           int n_mt = (std::max(Li.out, naug) + 127) / 128;
-          us = std::max(1, std::min(64, 148 / n_mt));  // one CTA per SM (196 KB of shared memory): a single wave
+          us = std::max(1, std::min(64, (getenv("LRNDE_WG_2WAVES") ? 256 : 148) / n_mt));  // one CTA per SM (196 KB of shared memory): a single wave
           uc = (int)((B + us - 1) / us);
           uc = std::max(32, ((uc + 31) / 32) * 32);
           us = (int)((B + uc - 1) / uc);
@@ -542,7 +542,9 @@ struct MlpEval {
         // dW_aug = delta [x;t;1]^T on the tensor cores (MN-major operands, 3xTF32)
         static bool attr_set = false;
         if (!attr_set) {
-          LR_CUDA(cudaFuncSetAttribute(umma::wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+          LR_CUDA(cudaFuncSetAttribute(umma::wgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       umma::wgrad_smem()));
+          LR_CUDA(cudaFuncSetAttribute(umma::wgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        umma::wgrad_smem()));
           attr_set = true;
         }
@@ -558,7 +560,11 @@ struct MlpEval {
         w.B = (int)B; w.chunk = uChunk[l]; w.part = part; w.block = nw; w.passes = passes;
         w.tdesc = y; w.done = done;
         dim3 g((std::max(Li.out, naug) + 127) / 128, uS[l]);
-        umma::wgrad_kernel<<<g, umma::kThreads, umma::wgrad_smem(), st>>>(w);
+        const bool wlean = use_lean && w.P.rows % 4 == 0 && w.Q.rows % 4 == 0 && w.P.ld % 4 == 0 && w.Q.ld % 4 == 0 &&
+                           w.P.in_act == ACT_IDENTITY && w.Q.in_act == ACT_IDENTITY &&
+                           (((uintptr_t)w.P.ptr) & 15) == 0 && (((uintptr_t)w.Q.ptr) & 15) == 0;
+        if (wlean) umma::wgrad_kernel<false><<<g, umma::kThreads, umma::wgrad_smem(), st>>>(w);
+        else umma::wgrad_kernel<true><<<g, umma::kThreads, umma::wgrad_smem(), st>>>(w);
         nsplit = uS[l];
       } else {
         WgradP w;

@@ -725,10 +725,21 @@ __device__ __forceinline__ void mma_tf32_mn(uint32_t d_tmem, uint32_t a_lo32, ui
 #undef LR_MMA_MN
 }
 
+// GEN = false: lean instantiation (rows % 4 == 0, aligned, no input activation): the time / bias rows are the
+// first elements of the float4 group starting at row == rows (same idea as the lean dense kernel)
+template <bool GEN>
 __device__ __forceinline__ float4 wg_load(const WgOperand& o, int row, int b, bool valid, float tval, bool vec) {
   float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
   if (!valid) return v;
   const float* p = o.ptr + (size_t)b * o.ld + row;
+  if (!GEN) {
+    if (row < o.rows) v = __ldcg(reinterpret_cast<const float4*>(p));
+    else if (row == o.rows) {
+      if (o.td) { v.x = tval; if (o.bias) v.y = 1.0f; }
+      else if (o.bias) v.x = 1.0f;
+    }
+    return v;
+  }
   if (vec && row + 3 < o.rows) {
     v = *reinterpret_cast<const float4*>(p);
     if (o.in_act) { v.x = lr_act(o.in_act, v.x); v.y = lr_act(o.in_act, v.y); v.z = lr_act(o.in_act, v.z); v.w = lr_act(o.in_act, v.w); }
@@ -748,6 +759,7 @@ __device__ __forceinline__ float4 wg_load(const WgOperand& o, int row, int b, bo
   return v;
 }
 
+template <bool GEN>
 __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(WgradUP q) {
   if (q.done && *q.done) return;
   constexpr int NS = kWgStages;
@@ -819,6 +831,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(WgradUP q) {
     const int tid = threadIdx.x - 64;
     const bool pvec = ((((uintptr_t)q.P.ptr) & 15) == 0) && (q.P.ld % 4 == 0);
     const bool qvec = ((((uintptr_t)q.Q.ptr) & 15) == 0) && (q.Q.ld % 4 == 0);
+    if (!GEN && !(pvec && qvec)) asm volatile("trap;");
     // software-pipelined producer: kWgDepth chunks of loads in flight per thread (the loop is
     // load-latency bound: one dependent global load per chunk otherwise)
     constexpr int kWgDepth = 3;
@@ -833,8 +846,8 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(WgradUP q) {
         const int li = gi & 1023;
         const int bl = li >> 5, c4 = li & 31;
         const int b = b_begin + it * 32 + bl;
-        if (!isq) dst[g] = wg_load(q.P, m0 + c4 * 4, b, b < b_end, tval, pvec);
-        else dst[g] = wg_load(q.Q, c4 * 4, b, b < b_end, tval, qvec);
+        if (!isq) dst[g] = wg_load<GEN>(q.P, m0 + c4 * 4, b, b < b_end, tval, pvec);
+        else dst[g] = wg_load<GEN>(q.Q, c4 * 4, b, b < b_end, tval, qvec);
       }
     };
 #pragma unroll
