@@ -383,6 +383,29 @@ __global__ void lincomb_kernel(const LinComb* dp, float* dst, size_t n, const in
   if (threadIdx.x == 0) d = *dp;
   __syncthreads();
   float* out = dst ? dst : d.dst;
+  // 16-byte path (every operand aligned, which library buffers are): one float4 per source in flight
+  bool vec = ((n & 3) == 0) && ((off & 3) == 0) && ((((uintptr_t)out) & 15) == 0) && ((((uintptr_t)d.base) & 15) == 0);
+  for (int k = 0; k < d.n; ++k) vec = vec && ((((uintptr_t)d.src[k]) & 15) == 0);
+  if (vec) {
+    const size_t n4 = n >> 2, o4 = off >> 2;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+      float4 v[LR_MAXSRC];
+#pragma unroll
+      for (int k = 0; k < LR_MAXSRC; ++k)
+        if (k < d.n) v[k] = __ldcg(reinterpret_cast<const float4*>(d.src[k]) + o4 + i);
+      float4 b = d.base ? __ldcg(reinterpret_cast<const float4*>(d.base) + o4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 in = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < LR_MAXSRC; ++k)
+        if (k < d.n) {
+          in.x = fmaf(d.coef[k], v[k].x, in.x); in.y = fmaf(d.coef[k], v[k].y, in.y);
+          in.z = fmaf(d.coef[k], v[k].z, in.z); in.w = fmaf(d.coef[k], v[k].w, in.w);
+        }
+      if (d.n) { b.x = fmaf(d.scale, in.x, b.x); b.y = fmaf(d.scale, in.y, b.y); b.z = fmaf(d.scale, in.z, b.z); b.w = fmaf(d.scale, in.w, b.w); }
+      reinterpret_cast<float4*>(out)[o4 + i] = b;
+    }
+    return;
+  }
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
        i += (size_t)gridDim.x * blockDim.x)
     out[off + i] = lr_lincomb_at(d, off + i);
@@ -445,14 +468,39 @@ __global__ void __launch_bounds__(256) err_norm_kernel(SolveDev* S) {
   const float* uprev = d.base;
   const float* unew = d.dst;
   double acc = 0.0;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
-       i += (size_t)gridDim.x * blockDim.x) {
-    float inner = 0.0f;
+  bool vec = ((n & 3) == 0) && ((((uintptr_t)uprev) & 15) == 0) && ((((uintptr_t)unew) & 15) == 0);
 #pragma unroll
-    for (int k = 0; k < 7; ++k) inner = fmaf(d.coef[k], d.src[k][i], inner);
-    float ut = d.scale * inner;
-    float r = ut / (abstol + fmaxf(fabsf(uprev[i]), fabsf(unew[i])) * reltol);
-    acc += (double)(r * r);
+  for (int k = 0; k < 7; ++k) vec = vec && ((((uintptr_t)d.src[k]) & 15) == 0);
+  if (vec) {   // nine float4 loads in flight per thread (the kernel is a pure HBM stream: 9 arrays in)
+    const size_t n4 = n >> 2;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+      float4 v[7];
+#pragma unroll
+      for (int k = 0; k < 7; ++k) v[k] = __ldcg(reinterpret_cast<const float4*>(d.src[k]) + i);
+      const float4 up = __ldcg(reinterpret_cast<const float4*>(uprev) + i);
+      const float4 un = __ldcg(reinterpret_cast<const float4*>(unew) + i);
+      float4 in = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < 7; ++k) {
+        in.x = fmaf(d.coef[k], v[k].x, in.x); in.y = fmaf(d.coef[k], v[k].y, in.y);
+        in.z = fmaf(d.coef[k], v[k].z, in.z); in.w = fmaf(d.coef[k], v[k].w, in.w);
+      }
+      const float r0 = (d.scale * in.x) / (abstol + fmaxf(fabsf(up.x), fabsf(un.x)) * reltol);
+      const float r1 = (d.scale * in.y) / (abstol + fmaxf(fabsf(up.y), fabsf(un.y)) * reltol);
+      const float r2 = (d.scale * in.z) / (abstol + fmaxf(fabsf(up.z), fabsf(un.z)) * reltol);
+      const float r3 = (d.scale * in.w) / (abstol + fmaxf(fabsf(up.w), fabsf(un.w)) * reltol);
+      acc += (double)(r0 * r0) + (double)(r1 * r1) + (double)(r2 * r2) + (double)(r3 * r3);
+    }
+  } else {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x) {
+      float inner = 0.0f;
+#pragma unroll
+      for (int k = 0; k < 7; ++k) inner = fmaf(d.coef[k], d.src[k][i], inner);
+      float ut = d.scale * inner;
+      float r = ut / (abstol + fmaxf(fabsf(uprev[i]), fabsf(unew[i])) * reltol);
+      acc += (double)(r * r);
+    }
   }
   double s = lr_block_sum(acc);
   if (threadIdx.x == 0) S->partials[blockIdx.x] = s;
