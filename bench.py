@@ -236,8 +236,7 @@ def run_native(args):
             x_np = xb_h.numpy()
             sol, st2 = node(x_np.T, ps_host["ps"], st)
             u_last = np.ascontiguousarray(sol.u[-1].T)
-            du_np = np.empty((B, D), np.float32)
-            dwc_np = np.empty(NCLS * D + NCLS, np.float32)
+            du_np, dwc_np = e2e_buf["du"], e2e_buf["dwc"]
             chk(lib.lrnde_head_ce(ctx._h, ps_host["Wc"].ctypes.data, u_last.ctypes.data, y_h.ctypes.data, B, D,
                                   NCLS, 1, C.byref(loss), du_np.ctypes.data, dwc_np.ctypes.data))
             if world > 1:
@@ -307,6 +306,8 @@ def run_native(args):
 
     # ---- e2e leg: host buffers through the C ABI (H2D / D2H inside the timed region)
     ps_host = {"ps": ps.cpu().numpy(), "Wc": Wc.cpu().numpy()}
+    e2e_buf = {"du": torch.empty((B, D), dtype=torch.float32).pin_memory().numpy(),       # page-locked host buffers,
+               "dwc": torch.empty(NCLS * D + NCLS, dtype=torch.float32).pin_memory().numpy()}  # as a host application would keep
     e2e_steps = max(0, min(args.steps, args.e2e_steps))
     if e2e_steps:
         st_e = step(0, st, False)                           # warm

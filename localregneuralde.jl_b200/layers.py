@@ -380,10 +380,12 @@ class NeuralODE:
         if all(d is None for d in d_us):
             dU = None
         elif host:
-            dU = np.zeros((n, B, D), np.float32)
+            dU = _host_empty((n, B, D))
             for i, d in enumerate(d_us):
                 if d is not None:
                     dU[i] = np.asarray(d, np.float32).T
+                else:
+                    dU[i] = 0.0
         else:
             dev = sol.u[0].device
             dU = torch.zeros((n, B, D), dtype=torch.float32, device=dev)
