@@ -269,6 +269,7 @@ struct MlpEval {
   int max_layers = 1 << 30;  // profiling probe: evaluate only the first layers
   int nacc_max = 8;
   bool use_lean = true;
+  bool use_wide = true;
   int passes = 3;
   float* ybuf = nullptr;
   float* delta[2] = {nullptr, nullptr};
@@ -283,6 +284,7 @@ struct MlpEval {
     use_cluster = (getenv("LRNDE_NO_CLUSTER") == nullptr);
     if (const char* e = getenv("LRNDE_NACC")) nacc_max = std::max(1, std::min(8, atoi(e)));
     use_lean = (getenv("LRNDE_NO_LEAN") == nullptr);
+    use_wide = (getenv("LRNDE_NO_WIDE") == nullptr);
     passes = (precision == LRNDE_PREC_TF32) ? 1 : 3;
     act.assign(L, nullptr);
     packW.assign(L, nullptr);
@@ -395,6 +397,11 @@ struct MlpEval {
       LR_CUDA(cudaFuncSetAttribute(umma::dense_kernel<NT, true, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::res_smem(C::kMaxResKC)));
       LR_CUDA(cudaFuncSetAttribute(umma::dense_kernel<NT, false, CL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::ring_smem()));
       LR_CUDA(cudaFuncSetAttribute(umma::dense_kernel<NT, true, CL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::res_smem(C::kMaxResKC)));
+      using CW = umma::Cfg<128>;
+      LR_CUDA(cudaFuncSetAttribute(umma::dense_kernel<128, true, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CW::res_smem(CW::kMaxResKC)));
+      LR_CUDA(cudaFuncSetAttribute(umma::dense_kernel<128, true, CL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CW::res_smem(CW::kMaxResKC)));
+      LR_CUDA(cudaFuncSetAttribute(umma::dense_kernel<128, true, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CW::res_smem(CW::kMaxResKC)));
+      LR_CUDA(cudaFuncSetAttribute(umma::dense_kernel<128, true, CL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CW::res_smem(CW::kMaxResKC)));
       attr_set = true;
     }
     umma::UmmaP q;
@@ -405,15 +412,22 @@ struct MlpEval {
     q.passes = passes;
     q.replicas = umma::kReplicas;
     q.nacc_max = nacc_max;
+    q.res_group = q.n_mt;
     unsigned ntile = (unsigned)((p.N + NT - 1) / NT);
     const bool resident = q.n_mt > 1 && q.n_mt * NT <= 512 && q.KC <= C::kMaxResKC;
+    // wide RESIDENT schedule: 128 samples per CTA (N = 128 per MMA runs at the tensor floor, N = 64 is
+    // shared-memory bound), the weight tiles split into groups of 4 (512 TMEM columns) over grid.y
+    const unsigned ntile_w = (unsigned)((p.N + 127) / 128);
+    const unsigned ngroup_w = (unsigned)((q.n_mt + 3) / 4);
+    const bool wide = use_wide && q.n_mt > 1 && q.KC <= umma::Cfg<128>::kMaxResKC && ntile_w * ngroup_w >= 96;
+    if (wide) { ntile = ntile_w; q.res_group = 4; }
     const bool cluster = ntile >= (unsigned)CL && use_cluster;
     if (cluster) ntile = ((ntile + CL - 1) / CL) * CL;  // padded CTAs produce zeros and store nothing
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = resident ? dim3(ntile) : dim3(ntile, q.n_mt);
+    cfg.gridDim = wide ? dim3(ntile, ngroup_w) : (resident ? dim3(ntile) : dim3(ntile, q.n_mt));
     cfg.blockDim = dim3(umma::kThreads);
-    cfg.dynamicSmemBytes = resident ? C::res_smem(q.KC) : C::ring_smem();
+    cfg.dynamicSmemBytes = wide ? umma::Cfg<128>::res_smem(q.KC) : (resident ? C::res_smem(q.KC) : C::ring_smem());
     cfg.stream = ctx->stream;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
@@ -430,7 +444,11 @@ struct MlpEval {
                       (p.dact < 0 || p.dact == ACT_IDENTITY || p.dact == ACT_TANH) &&
                       (!p.X || (((uintptr_t)p.X) & 15) == 0) && (!p.side || (((uintptr_t)p.side) & 15) == 0);
 #define LR_LAUNCH_DENSE(RES, CLV, GENV) LR_CUDA(cudaLaunchKernelEx(&cfg, umma::dense_kernel<NT, RES, CLV, GENV>, q))
-    if (resident) {
+#define LR_LAUNCH_WIDE(CLV, GENV) LR_CUDA(cudaLaunchKernelEx(&cfg, umma::dense_kernel<128, true, CLV, GENV>, q))
+    if (wide) {
+      if (cluster) { if (lean) LR_LAUNCH_WIDE(CL, false); else LR_LAUNCH_WIDE(CL, true); }
+      else { if (lean) LR_LAUNCH_WIDE(1, false); else LR_LAUNCH_WIDE(1, true); }
+    } else if (resident) {
       if (cluster) { if (lean) LR_LAUNCH_DENSE(true, CL, false); else LR_LAUNCH_DENSE(true, CL, true); }
       else { if (lean) LR_LAUNCH_DENSE(true, 1, false); else LR_LAUNCH_DENSE(true, 1, true); }
     } else {
@@ -438,6 +456,7 @@ struct MlpEval {
       else { if (lean) LR_LAUNCH_DENSE(false, 1, false); else LR_LAUNCH_DENSE(false, 1, true); }
     }
 #undef LR_LAUNCH_DENSE
+#undef LR_LAUNCH_WIDE
     LR_COUNT(ctx);
   }
 

@@ -228,6 +228,7 @@ struct UmmaP {
   int passes;          // 3 = 3xTF32, 1 = TF32
   int replicas;        // copies of the packed images (stride n_mt * KC chunks)
   int nacc_max;        // RING: upper bound on the number of split TMEM accumulators
+  int res_group;       // RESIDENT: weight tiles per CTA (grid.y = groups of tiles)
 };
 constexpr int kReplicas = 4;
 constexpr int kBulkParts = 2;
@@ -375,8 +376,8 @@ __global__ void __launch_bounds__(kThreads, 1) dense_kernel(UmmaP q) {
   const int lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * NT;
   const int KC = q.KC;
-  const int mt_begin = RESIDENT ? 0 : blockIdx.y;
-  const int mt_count = RESIDENT ? q.n_mt : 1;
+  const int mt_begin = RESIDENT ? (int)blockIdx.y * q.res_group : (int)blockIdx.y;
+  const int mt_count = RESIDENT ? min(q.res_group, q.n_mt - mt_begin) : 1;
   const int nchunks = mt_count * KC;
   // RING: the K loop is split over several TMEM accumulators that the epilogue adds in fp32
   // (the tensor core accumulates with truncation; shorter chains keep 3xTF32 at fp32 level)
