@@ -440,3 +440,47 @@ def test_head_ce_matches_numpy(pkg):
     assert rel(du.T, want_du) < 1e-4
     assert rel(dWc[:Cn * D].reshape((Cn, D), order="F"), want_dW) < 1e-4
     assert rel(dWc[Cn * D:], want_db) < 1e-4
+
+
+# ------------------------------------------------------------------ kernel instantiations
+def test_lean_wide_and_cluster_instantiations_agree(pkg, monkeypatch):
+    """MlpEval::dense picks, per launch, the lean instantiation (no scalar fallback / activation switch
+    in the hot loops), the wide RESIDENT schedule (128 samples per CTA) and the 4-CTA cluster multicast.
+    Each can be switched off by an environment variable read per call; all combinations must give the
+    same forward states, step sequence and gradients on the mnist_ode shape (tanh / identity, K % 4 == 0,
+    batch large enough for the wide schedule), and the general path is also exercised by the
+    gelu / sigmoid / relu / odd-K cases of this suite."""
+    layers = [(784, 100, "tanh"), (100, 784, "identity")]
+    om = _omodel(layers, True, None)
+    rng = np.random.default_rng(11)
+    ps = (orc.glorot_uniform_params(om, rng) * 2).astype(np.float32)
+    B = 6208                                         # 97 tiles of 64: ragged against 128, above the wide threshold
+    x = rng.random((784, B)).astype(np.float32)
+    # tight tolerances: the adjoint is itself an adaptive solve, so at 1e-3 two summation orders (the
+    # chunk rotation depends on the cluster id) may differ by the discretisation error
+    kw = dict(regularize="unbiased", abstol=1e-6, reltol=1e-6, maxiters=1000, save_start=False)
+    cot = (rng.standard_normal((784, B)) / B).astype(np.float32)
+    res = {}
+    for name, env in [("default", {}), ("general", {"LRNDE_NO_LEAN": "1"}), ("narrow", {"LRNDE_NO_WIDE": "1"}),
+                      ("nocluster", {"LRNDE_NO_CLUSTER": "1"}),
+                      ("plain", {"LRNDE_NO_LEAN": "1", "LRNDE_NO_WIDE": "1", "LRNDE_NO_CLUSTER": "1"})]:
+        for k in ("LRNDE_NO_LEAN", "LRNDE_NO_WIDE", "LRNDE_NO_CLUSTER"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        node = pkg.NeuralODE(_chain(pkg, layers, True, None), precision="tf32x3", **kw)
+        sol, st2 = node(x, ps, node.initialstates(np.random.default_rng(2)))
+        d_x, d_ps = node.backward(sol, [None, cot], 0.0)   # the regulariser's gradient is Float32 noise at this tolerance
+        t, dt, ee, acc = sol.step_log(0)
+        res[name] = (np.array(sol.u[-1]), st2["nfe"], float(st2["reg_val"]), np.array(d_x), np.array(d_ps), acc.copy(), dt.copy())
+        sol.free()
+    ref = res["plain"]
+    for name, r in res.items():
+        assert r[1] == ref[1] and np.array_equal(r[5], ref[5]), name          # same NFE and step sequence
+        assert np.allclose(r[6], ref[6], rtol=1e-2), name          # EEst carries Float32 noise at this tolerance
+        assert rel(r[0], ref[0]) < 1e-5, (name, rel(r[0], ref[0]))
+        assert abs(r[2] / ref[2] - 1) < 1e-3, name
+        assert rel(r[3], ref[3]) < 3e-4 and rel(r[4], ref[4]) < 3e-4, (name, rel(r[3], ref[3]), rel(r[4], ref[4]))
+    # lean vs general and wide vs narrow do the same arithmetic in the same order per output element
+    assert res["default"][0].tobytes() == res["general"][0].tobytes()
+    assert res["default"][0].tobytes() == res["narrow"][0].tobytes()
