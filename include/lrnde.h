@@ -238,6 +238,20 @@ int lrnde_sde_aux_step(lrnde_ctx* ctx, const lrnde_model* drift, const lrnde_mod
                        float reltol, float delta, int64_t B, int32_t host_buffers, float* u,
                        float* reg_val);
 
+/* Latent-ODE encoder: Recurrence(LatentGRUCell(in, h, latent)) of the physionet model,
+ * src/layers/latent_ode.jl:1-48 (both quirks kept: new_y_mean uses new_state_std, :37; the mask sums the
+ * mask rows and the dt row, :40) applied along the time dimension as at experiments/src/construct.jl:231.
+ * F = feature rows of x (2*in + 1); ps = [update_gate; reset_gate; new_state], each Chain(Dense(2L+F => H,
+ * tanh), Dense(H => L | L | 2L, sigmoid | sigmoid | tanh)) in ComponentArray order.  x: [F,T,B] column-major;
+ * y: [2L,B] = vcat(y_mean, y_std) after the last step.  The pullback is w.r.t. the parameters (x is data). */
+typedef struct lrnde_gru_tape lrnde_gru_tape;
+int64_t lrnde_gru_nparams(int32_t F, int32_t H, int32_t L);
+int lrnde_gru_forward(lrnde_ctx* ctx, int32_t F, int32_t H, int32_t L, const float* ps, const float* x,
+                      int32_t T, int64_t B, int32_t host_buffers, int32_t keep_tape, float* y,
+                      lrnde_gru_tape** tape);
+int lrnde_gru_backward(lrnde_ctx* ctx, lrnde_gru_tape* tape, const float* d_y, float* d_ps);
+int lrnde_gru_tape_free(lrnde_gru_tape* tape);
+
 /* Next row of the path: classifier Dense(D => C) + logitcrossentropy,
  * experiments/src/construct.jl:199 and experiments/src/utils.jl:88, with its pullback.
  * Wc: flat [C x D] weight then [C] bias; u: [D,B]; labels: class index per sample.

@@ -78,7 +78,8 @@ SYMBOLS = [
     "lrnde_tape_free", "lrnde_step_log", "lrnde_sosri_step", "lrnde_ipc_export",
     "lrnde_ipc_open", "lrnde_head_ce", "lrnde_adam_step", "lrnde_profile_feval",
     "lrnde_sde_forward", "lrnde_sde_backward", "lrnde_sde_tape_free", "lrnde_sde_states",
-    "lrnde_sde_step_log", "lrnde_sde_aux_step",
+    "lrnde_sde_step_log", "lrnde_sde_aux_step", "lrnde_gru_nparams", "lrnde_gru_forward",
+    "lrnde_gru_backward", "lrnde_gru_tape_free",
 ]
 
 
@@ -128,9 +129,14 @@ def lib():
     L.lrnde_sde_step_log.argtypes = [vp, vp, vp, vp, vp, i32, C.POINTER(i32)]
     L.lrnde_sde_aux_step.argtypes = [vp, vp, vp, i32, vp, vp, vp, vp, f32, f32, f32, f32, f32, i64, i32, vp,
                                      C.POINTER(f32)]
+    L.lrnde_gru_nparams.argtypes = [i32, i32, i32]
+    L.lrnde_gru_nparams.restype = i64
+    L.lrnde_gru_forward.argtypes = [vp, i32, i32, i32, vp, vp, i32, i64, i32, i32, vp, C.POINTER(vp)]
+    L.lrnde_gru_backward.argtypes = [vp, vp, vp, vp]
+    L.lrnde_gru_tape_free.argtypes = [vp]
     for name in SYMBOLS:
         fn = getattr(L, name)
-        if name not in ("lrnde_last_error", "lrnde_model_nparams", "lrnde_model_state_dims"):
+        if name not in ("lrnde_last_error", "lrnde_model_nparams", "lrnde_model_state_dims", "lrnde_gru_nparams"):
             fn.restype = i32
     _lib = L
     return L

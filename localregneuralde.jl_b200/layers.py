@@ -635,6 +635,86 @@ class NeuralDSDE:
         return out.T, np.float32(reg.value)
 
 
+# ------------------------------------------------------------------ latent-ODE encoder
+class LatentGRUCell:
+    """``LatentGRUCell(in_dim, h_dim, latent_dim)`` (src/layers/latent_ode.jl:10-17): three two-layer gate
+    networks on ``vcat(y_mean, y_std, x)`` with ``x`` of ``2*in_dim + 1`` rows (data, mask, dt)."""
+
+    def __init__(self, in_dim: int, h_dim: int, latent_dim: int):
+        self.in_dim, self.h_dim, self.latent_dim = int(in_dim), int(h_dim), int(latent_dim)
+        self.features = 2 * self.in_dim + 1
+
+    def nparams(self) -> int:
+        return int(lib().lrnde_gru_nparams(self.features, self.h_dim, self.latent_dim))
+
+    def initialparameters(self, rng: np.random.Generator) -> np.ndarray:
+        """Lux defaults (Glorot-uniform weights, zero biases) in ComponentArray order
+        update_gate, reset_gate, new_state."""
+        L, H, I = self.latent_dim, self.h_dim, 2 * self.latent_dim + self.features
+        out = []
+        for out2 in (L, L, 2 * L):
+            for (i, o) in ((I, H), (H, out2)):
+                a = math.sqrt(6.0 / (i + o))
+                out.append(rng.uniform(-a, a, size=(o, i)).astype(np.float32).ravel(order="F"))
+                out.append(np.zeros(o, np.float32))
+        return np.concatenate(out)
+
+
+class Recurrence:
+    """``Recurrence(cell)`` as used at experiments/src/construct.jl:231: the cell runs along the time
+    dimension of ``x`` (features, time, batch) and the last output ``vcat(y_mean, y_std)`` is returned.
+    One kernel launch walks the whole series; ``backward`` is back-propagation through time w.r.t. ``ps``."""
+
+    def __init__(self, cell: LatentGRUCell, ctx: Optional[Context] = None):
+        self.cell, self._ctx = cell, ctx
+
+    @property
+    def ctx(self) -> Context:
+        if self._ctx is None:
+            self._ctx = default_context(0)
+        return self._ctx
+
+    def __call__(self, x, ps, st=None, keep_tape: bool = True):
+        c = self.cell
+        host = not _is_torch(x)
+        if x.shape[0] != c.features:
+            raise ValueError(f"x has {x.shape[0]} feature rows, the cell expects {c.features}")
+        F, T, B = x.shape
+        if host:
+            xb = np.ascontiguousarray(np.transpose(np.asarray(x, np.float32), (2, 1, 0)))     # (B, T, F) C order
+            psb = np.ascontiguousarray(np.asarray(ps, np.float32))
+            y = _host_empty((B, 2 * c.latent_dim))
+        else:
+            xb = x.detach().to(torch.float32).permute(2, 1, 0).contiguous()
+            psb = ps.detach().to(torch.float32).contiguous()
+            y = torch.empty((B, 2 * c.latent_dim), dtype=torch.float32, device=x.device)
+        if (psb.size if host else psb.numel()) != c.nparams():
+            raise ValueError("ps has the wrong length for this cell")
+        tape = C.c_void_p()
+        check(lib().lrnde_gru_forward(self.ctx._h, c.features, c.h_dim, c.latent_dim, _ptr(psb), _ptr(xb), T, B,
+                                      1 if host else 0, 1 if keep_tape else 0, _ptr(y), C.byref(tape)))
+        return y.T, dict(st or {}, tape=tape if keep_tape else None, host=host, B=B)
+
+    def backward(self, st, d_y):
+        """d_ps for a cotangent on the returned ``y`` (2*latent, B)."""
+        if not st.get("tape"):
+            raise _lib.LrndeError(-4, "no tape: call the layer with keep_tape=True")
+        host, c = st["host"], self.cell
+        if host:
+            dy = np.ascontiguousarray(np.asarray(d_y, np.float32).T)
+            d_ps = np.empty(c.nparams(), np.float32)
+        else:
+            dy = d_y.to(torch.float32).t().contiguous()
+            d_ps = torch.empty(c.nparams(), dtype=torch.float32, device=d_y.device)
+        check(lib().lrnde_gru_backward(self.ctx._h, st["tape"], _ptr(dy), _ptr(d_ps)))
+        return d_ps
+
+    def free(self, st):
+        if st.get("tape"):
+            lib().lrnde_gru_tape_free(st["tape"])
+            st["tape"] = None
+
+
 # ------------------------------------------------------------------ torch autograd bridge
 if torch is not None:
 
