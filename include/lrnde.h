@@ -252,6 +252,27 @@ int lrnde_gru_forward(lrnde_ctx* ctx, int32_t F, int32_t H, int32_t L, const flo
 int lrnde_gru_backward(lrnde_ctx* ctx, lrnde_gru_tape* tape, const float* d_y, float* d_ps);
 int lrnde_gru_tape_free(lrnde_gru_tape* tape);
 
+/* The small layers either side of the latent ODE (experiments/src/construct.jl:229-247).
+ * lrnde_mlp_*: a Chain of Dense layers (rec_to_gen; gen_to_data applied to the N = T*B saved columns),
+ * x [in,N] -> y [out,N]; the backward recomputes the forward from x and returns d_x (may be NULL), d_ps. */
+int lrnde_mlp_forward(lrnde_ctx* ctx, const lrnde_layer_desc* layers, int32_t nlayers, const float* ps,
+                      const float* x, int64_t N, int32_t host_buffers, float* y);
+int lrnde_mlp_backward(lrnde_ctx* ctx, const lrnde_layer_desc* layers, int32_t nlayers, const float* ps,
+                       const float* x, const float* d_y, int64_t N, int32_t host_buffers, float* d_x,
+                       float* d_ps);
+/* ReparameterizeLayer (src/layers/common.jl:48-77): x [2L,B] = vcat(mu, logsigma2) -> y = mu + exp(logsigma2/2)*eps,
+ * eps from Philox(seed) (the reference uses randn_like(rng, ...)); training == 0: y = mu.  Pass d_x (and any of
+ * d_y, d_mu, d_logsigma2, the latter two being the KL cotangents) to get the pullback in the same call. */
+int lrnde_reparameterize(lrnde_ctx* ctx, const float* x, int32_t L, int64_t B, uint64_t seed, int32_t training,
+                         int32_t host_buffers, float* y, const float* d_y, const float* d_mu,
+                         const float* d_ls, float* d_x);
+/* Latent-ODE loss -mean(log_likelihood - w_kl * kl_div) (experiments/src/construct.jl:36-70 with
+ * log_likelihood_loss / kl_divergence of experiments/src/utils.jl:94-101; w_reg * reg_val is added by the
+ * caller).  pred/data/mask [F,T,B], mu/logsigma2 [L,B]; out3 (HOST) = {loss, -mean(ll), mean(kl)}. */
+int lrnde_latent_loss(lrnde_ctx* ctx, const float* pred, const float* data, const float* mask, const float* mu,
+                      const float* logsigma2, int32_t F, int32_t T, int32_t L, int64_t B, float w_kl,
+                      int32_t host_buffers, float* out3, float* d_pred, float* d_mu, float* d_logsigma2);
+
 /* Next row of the path: classifier Dense(D => C) + logitcrossentropy,
  * experiments/src/construct.jl:199 and experiments/src/utils.jl:88, with its pullback.
  * Wc: flat [C x D] weight then [C] bias; u: [D,B]; labels: class index per sample.

@@ -6,7 +6,7 @@ The directory name contains a dot, so it is loaded through ``__graft_entry__.loa
 """
 from ._lib import LIB_PATH, LrndeError, lib, SYMBOLS  # noqa: F401
 from .layers import (Chain, Context, Dense, DESolution, LatentGRUCell, NeuralDSDE, NeuralODE, Recurrence,  # noqa: F401
-                     SDESolution, TDChain,
+                     ReparameterizeLayer, SDESolution, TDChain, latent_loss, mlp_backward, mlp_forward,
                      default_context, diffeqsol_to_array, diffeqsol_to_timeseries,
                      glorot_uniform, nparams)
 

@@ -79,7 +79,8 @@ SYMBOLS = [
     "lrnde_ipc_open", "lrnde_head_ce", "lrnde_adam_step", "lrnde_profile_feval",
     "lrnde_sde_forward", "lrnde_sde_backward", "lrnde_sde_tape_free", "lrnde_sde_states",
     "lrnde_sde_step_log", "lrnde_sde_aux_step", "lrnde_gru_nparams", "lrnde_gru_forward",
-    "lrnde_gru_backward", "lrnde_gru_tape_free",
+    "lrnde_gru_backward", "lrnde_gru_tape_free", "lrnde_mlp_forward", "lrnde_mlp_backward",
+    "lrnde_reparameterize", "lrnde_latent_loss",
 ]
 
 
@@ -134,6 +135,10 @@ def lib():
     L.lrnde_gru_forward.argtypes = [vp, i32, i32, i32, vp, vp, i32, i64, i32, i32, vp, C.POINTER(vp)]
     L.lrnde_gru_backward.argtypes = [vp, vp, vp, vp]
     L.lrnde_gru_tape_free.argtypes = [vp]
+    L.lrnde_mlp_forward.argtypes = [vp, C.POINTER(LayerDesc), i32, vp, vp, i64, i32, vp]
+    L.lrnde_mlp_backward.argtypes = [vp, C.POINTER(LayerDesc), i32, vp, vp, vp, i64, i32, vp, vp]
+    L.lrnde_reparameterize.argtypes = [vp, vp, i32, i64, C.c_uint64, i32, i32, vp, vp, vp, vp, vp]
+    L.lrnde_latent_loss.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i64, f32, i32, vp, vp, vp, vp]
     for name in SYMBOLS:
         fn = getattr(L, name)
         if name not in ("lrnde_last_error", "lrnde_model_nparams", "lrnde_model_state_dims", "lrnde_gru_nparams"):

@@ -715,6 +715,116 @@ class Recurrence:
             st["tape"] = None
 
 
+def _cols(a):
+    """Julia column-major (rows, d2, ..., dn) -> the flat buffer the C ABI takes (reversed axes, C order)."""
+    if _is_torch(a):
+        return a.detach().to(torch.float32).permute(*reversed(range(a.dim()))).contiguous()
+    a = np.asarray(a, np.float32)
+    return np.ascontiguousarray(a.transpose(tuple(reversed(range(a.ndim)))))
+
+
+def _out_like(shape_cols, like):
+    """Output buffer with C shape ``shape_cols`` (reversed Julia shape) on the side ``like`` lives on."""
+    if _is_torch(like):
+        return torch.empty(tuple(shape_cols), dtype=torch.float32, device=like.device)
+    return np.empty(tuple(shape_cols), np.float32)
+
+
+def _back(a):
+    """Inverse of _cols for outputs: a view with Julia's axis order."""
+    if _is_torch(a):
+        return a.permute(*reversed(range(a.dim())))
+    return a.transpose(tuple(reversed(range(a.ndim))))
+
+
+def _layer_descs(model: Chain):
+    if model.time_dependent or model.input_activation is not None:
+        raise ValueError("mlp_forward/backward take a plain Chain of Dense layers")
+    arr = (LayerDesc * len(model.layers))()
+    for i, L in enumerate(model.layers):
+        arr[i] = LayerDesc(L.in_dims, L.out_dims, _lib.ACT[L.activation])
+    return arr
+
+
+def mlp_forward(model: Chain, ps, x, ctx: Optional[Context] = None):
+    """``Chain(Dense...)`` on ``x`` of shape (in, ...): every trailing index is a column (rec_to_gen on
+    (2L, B); gen_to_data on the stacked saves (N, T, B), experiments/src/construct.jl:232-246)."""
+    ctx = ctx or default_context(0)
+    xb = _cols(x)
+    N = int(np.prod(xb.shape[:-1]))
+    psb = ps.detach().to(torch.float32).contiguous() if _is_torch(ps) else np.ascontiguousarray(np.asarray(ps, np.float32))
+    y = _out_like(tuple(xb.shape[:-1]) + (model.layers[-1].out_dims,), xb)
+    check(lib().lrnde_mlp_forward(ctx._h, _layer_descs(model), len(model.layers), _ptr(psb), _ptr(xb), N,
+                                  0 if _is_torch(x) else 1, _ptr(y)))
+    return _back(y)
+
+
+def mlp_backward(model: Chain, ps, x, d_y, ctx: Optional[Context] = None):
+    """(d_x, d_ps) of mlp_forward (the forward is recomputed from ``x``)."""
+    ctx = ctx or default_context(0)
+    xb, dyb = _cols(x), _cols(d_y)
+    N = int(np.prod(xb.shape[:-1]))
+    psb = ps.detach().to(torch.float32).contiguous() if _is_torch(ps) else np.ascontiguousarray(np.asarray(ps, np.float32))
+    d_x = _out_like(xb.shape, xb)
+    d_ps = _out_like((nparams(model),), xb)
+    check(lib().lrnde_mlp_backward(ctx._h, _layer_descs(model), len(model.layers), _ptr(psb), _ptr(xb), _ptr(dyb), N,
+                                   0 if _is_torch(x) else 1, _ptr(d_x), _ptr(d_ps)))
+    return _back(d_x), d_ps
+
+
+class ReparameterizeLayer:
+    """``ReparameterizeLayer()`` (src/layers/common.jl:48-77): x = vcat(mu0, logsigma2) -> mu0 + exp(logsigma2/2) .* eps;
+    the state keeps mu0 / logsigma2 for the KL term.  eps comes from Philox(seed) instead of randn_like(rng, ...)."""
+
+    def __init__(self, seed: int = 0, ctx: Optional[Context] = None):
+        self.seed, self._ctx = int(seed), ctx
+
+    def initialstates(self, rng: np.random.Generator):
+        rng.standard_normal(1)
+        return dict(rng=rng, training=True, mu0=None, logsigma2=None)
+
+    def __call__(self, x, ps=None, st=None):
+        ctx = self._ctx or default_context(0)
+        st = dict(st or {"training": True})
+        xb = _cols(x)
+        B, L2 = xb.shape
+        L = L2 // 2
+        y = _out_like((B, L), xb)
+        check(lib().lrnde_reparameterize(ctx._h, _ptr(xb), L, B, self.seed, 1 if st.get("training", True) else 0,
+                                         0 if _is_torch(x) else 1, _ptr(y), None, None, None, None))
+        if st.get("training", True):
+            st.update(mu0=x[:L], logsigma2=x[L:])
+        else:
+            st.update(mu0=x[:L], logsigma2=x[:L])                 # common.jl:73-77
+        return _back(y), st
+
+    def backward(self, x, d_y, d_mu=None, d_ls=None, training: bool = True):
+        ctx = self._ctx or default_context(0)
+        xb = _cols(x)
+        B, L2 = xb.shape
+        d_x = _out_like(xb.shape, xb)
+        f = lambda a: None if a is None else _cols(a)
+        bufs = [f(d_y), f(d_mu), f(d_ls)]
+        check(lib().lrnde_reparameterize(ctx._h, _ptr(xb), L2 // 2, B, self.seed, 1 if training else 0,
+                                         0 if _is_torch(x) else 1, None, _ptr(bufs[0]), _ptr(bufs[1]), _ptr(bufs[2]),
+                                         _ptr(d_x)))
+        return _back(d_x)
+
+
+def latent_loss(pred, data, mask, mu, logsigma2, w_kl: float, ctx: Optional[Context] = None):
+    """The latent-ODE objective without the regulariser term (experiments/src/construct.jl:36-70):
+    returns (loss, neg_log_likelihood, kl_div, d_pred, d_mu, d_logsigma2)."""
+    ctx = ctx or default_context(0)
+    pb, db, mb, mub, lsb = _cols(pred), _cols(data), _cols(mask), _cols(mu), _cols(logsigma2)
+    B, T, F = pb.shape
+    L = mub.shape[1]
+    out3 = (C.c_float * 3)()
+    d_pred, d_mu, d_ls = _out_like(pb.shape, pb), _out_like(mub.shape, pb), _out_like(mub.shape, pb)
+    check(lib().lrnde_latent_loss(ctx._h, _ptr(pb), _ptr(db), _ptr(mb), _ptr(mub), _ptr(lsb), F, T, L, B, float(w_kl),
+                                  0 if _is_torch(pred) else 1, out3, _ptr(d_pred), _ptr(d_mu), _ptr(d_ls)))
+    return float(out3[0]), float(out3[1]), float(out3[2]), _back(d_pred), _back(d_mu), _back(d_ls)
+
+
 # ------------------------------------------------------------------ torch autograd bridge
 if torch is not None:
 
