@@ -497,6 +497,157 @@ def run_sde(args):
                                        "sample": f"the whole workload, 1 iteration ({dt:.2f} s), numpy float32 oracle"}}))
 
 
+# ---------------------------------------------------------------------------------- physionet (secondary)
+def physionet_setup(B, T):
+    in_dim, Hh, Lg, Nn = 37, 40, 50, 20                     # experiments/src/config.jl:31-34
+    rng = np.random.default_rng(8)
+    mask = (rng.random((in_dim, T, B)) < 0.2).astype(np.float32)
+    mask[0, 0, :] = 1
+    data = rng.standard_normal((in_dim, T, B)).astype(np.float32) * mask
+    dt = np.zeros((1, T, B), np.float32)
+    dt[0, 1:, :] = np.diff(np.sort(rng.random((T, B)), axis=0), axis=0)
+    x = np.concatenate([data, mask, dt], axis=0)
+    ts = np.sort(np.concatenate([[0.0], rng.uniform(0.02, 1.0, T - 1)])).astype(np.float32)
+    return dict(in_dim=in_dim, H=Hh, Lg=Lg, Nn=Nn, x=x, data=data, mask=mask, ts=ts, rng=rng,
+                dyn=[(Nn, Hh, "tanh"), (Hh, Nn, "tanh")] * 4,
+                kw=dict(regularize="unbiased", abstol=1e-4, reltol=1e-4, maxiters=10000, saveat=list(ts)))
+
+
+def run_physionet(args):
+    """BASELINE configs[2]: latent ODE (GRU encoder + ODE decoder), 37 features, irregular series, batch 256;
+    one training iteration = encoder -> rec_to_gen -> reparameterise -> NeuralODE (saveat = T observation times,
+    :unbiased local reg) -> gen_to_data -> loss, and the whole reverse pass.  Secondary workload."""
+    B, T = args.phys_batch, args.phys_T
+    S = physionet_setup(B, T)
+    w_reg, w_kl = 0.5, 0.1
+    import oracle as orc
+    from oracle.lrnde_latent_oracle import _net_fwd, _net_vjp
+    rng = S["rng"]
+    F = 2 * S["in_dim"] + 1
+    ps_gru = orc.gru_init(rng, F, S["H"], S["Lg"])
+    om = orc.MLP([orc.Dense(*l) for l in S["dyn"]], time_dependent=False, input_act="tanh")
+    ps_node = (orc.glorot_uniform_params(om, rng) * 2).astype(np.float32)
+
+    def chain_ps(dims):
+        out = []
+        for (i, o) in dims:
+            a = np.sqrt(6.0 / (i + o))
+            out += [rng.uniform(-a, a, (o, i)).astype(np.float32).ravel(order="F"), np.zeros(o, np.float32)]
+        return np.concatenate(out)
+    ps_r2g, ps_g2d = chain_ps([(2 * S["Lg"], S["Lg"]), (S["Lg"], 2 * S["Nn"])]), chain_ps([(S["Nn"], S["in_dim"])])
+
+    def oracle_iter():
+        def layers(ps, dims):
+            out, off = [], 0
+            for (i, o, a) in dims:
+                W = ps[off:off + o * i].reshape((o, i), order="F"); wo = off; off += o * i
+                b = ps[off:off + o]; bo = off; off += o
+                out.append((W, b, a, wo, bo))
+            return out
+        x, data, mask = S["x"], S["data"], S["mask"]
+        h, car = orc.gru_recurrence(ps_gru, x, F, S["H"], S["Lg"])
+        Lr = layers(ps_r2g, [(2 * S["Lg"], S["Lg"], "tanh"), (S["Lg"], 2 * S["Nn"], "identity")])
+        Ld = layers(ps_g2d, [(S["Nn"], S["in_dim"], "identity")])
+        z = _net_fwd(Lr, h)
+        eps = orc.philox_normal(13, 2, 0, S["Nn"] * B).reshape((S["Nn"], B), order="F")
+        y0, mu, ls = orc.reparameterize(z, eps, True)
+        on = orc.NeuralODE(om, **S["kw"])
+        sol, st, aux = on.forward(y0, ps_node, on.initialstates(np.random.default_rng(2)))
+        ser = np.stack(sol.u, axis=1)
+        pred = _net_fwd(Ld, ser.reshape(S["Nn"], -1, order="F")).reshape((S["in_dim"], T, B), order="F")
+        msum = mask.sum(axis=(0, 1))
+        dpred = ((pred * mask - data * mask) * mask / 1e-4 / msum / B).astype(np.float32)
+        g = np.zeros_like(ps_g2d)
+        dser = _net_vjp(Ld, ser.reshape(S["Nn"], -1, order="F"), dpred.reshape(S["in_dim"], -1, order="F"), g).reshape(ser.shape, order="F")
+        dy0, _ = on.backward(aux, [dser[:, i, :] for i in range(T)], w_reg, ps_node)
+        dz = np.concatenate([dy0 + w_kl * mu / (S["Nn"] * B), dy0 * eps * np.exp(ls / 2) / 2 + w_kl * (np.exp(ls) - 1) / (2 * S["Nn"] * B)]).astype(np.float32)
+        g2 = np.zeros_like(ps_r2g)
+        dh = _net_vjp(Lr, h, dz, g2)
+        orc.gru_recurrence_backward(ps_gru, x, F, S["H"], S["Lg"], car, dh)
+        return st["nfe"]
+
+    if args.impl == "reference":
+        ts_ = []
+        for i in range(args.warmup + args.steps):
+            t0 = time.perf_counter(); oracle_iter()
+            if i >= args.warmup:
+                ts_.append(time.perf_counter() - t0)
+        ms = 1e3 * float(np.mean(ts_)); val = B / (ms / 1e3)
+        print(json.dumps({"impl": "reference", "metric": "physionet_train_samples_per_s", "value": val, "unit": "samples/s",
+                          "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+                          "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "config": {"workload": "physionet latent ODE (BASELINE configs[2])", "batch": B, "T": T},
+                          "cpu_baseline": {"value": val, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port", "sample": "the whole workload"},
+                          "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+    import torch
+    import __graft_entry__ as entry
+    entry.build()
+    pkg = entry.load_package()
+    dev = torch.device("cuda", 0)
+    cell = pkg.LatentGRUCell(S["in_dim"], S["H"], S["Lg"])
+    rec = pkg.Recurrence(cell)
+    r2g = pkg.Chain(pkg.Dense(2 * S["Lg"], S["Lg"], "tanh"), pkg.Dense(S["Lg"], 2 * S["Nn"]))
+    g2d = pkg.Chain(pkg.Dense(S["Nn"], S["in_dim"]))
+    node = pkg.NeuralODE(pkg.Chain(*[pkg.Dense(*l) for l in S["dyn"]], input_activation="tanh"),
+                         precision=args.precision, **S["kw"])
+    rp = pkg.ReparameterizeLayer(seed=13)
+    to = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    dv = dict(x=to(S["x"]), data=to(S["data"]), mask=to(S["mask"]), gru=to(ps_gru), r2g=to(ps_r2g), g2d=to(ps_g2d), node=to(ps_node))
+    hv = dict(x=S["x"], data=S["data"], mask=S["mask"], gru=ps_gru, r2g=ps_r2g, g2d=ps_g2d, node=ps_node)
+    info = {}
+
+    def step(resident):
+        v = dv if resident else hv
+        h, st_rec = rec(v["x"], v["gru"])
+        z = pkg.mlp_forward(r2g, v["r2g"], h)
+        y0, st_rp = rp(z, None, dict(training=True))
+        y0c = y0.contiguous() if resident else np.ascontiguousarray(y0)
+        sol, st_node = node(y0c, v["node"], node.initialstates(np.random.default_rng(2)))
+        ser = pkg.diffeqsol_to_timeseries(sol)
+        pred = pkg.mlp_forward(g2d, v["g2d"], ser)
+        loss, nll, kl, d_pred, d_mu, d_ls = pkg.latent_loss(pred, v["data"], v["mask"], st_rp["mu0"], st_rp["logsigma2"], w_kl)
+        d_ser, d_g2d = pkg.mlp_backward(g2d, v["g2d"], ser, d_pred)
+        cots = [d_ser[:, i, :].contiguous() if resident else np.ascontiguousarray(d_ser[:, i, :]) for i in range(T)]
+        d_y0, d_node = node.backward(sol, cots, w_reg)
+        d_z = rp.backward(z, d_y0, d_mu, d_ls)
+        d_h, d_r2g = pkg.mlp_backward(r2g, v["r2g"], h, d_z)
+        rec.backward(st_rec, d_h)
+        info.update(nfe=st_node["nfe"], loss=loss + w_reg * float(st_node["reg_val"]),
+                    launches=sol.stats.gpu_launches + sol.bwd_stats.gpu_launches + 16)
+        rec.free(st_rec); sol.free()
+
+    def timed(n, resident):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(); e0.record()
+        for _ in range(n):
+            step(resident)
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+    clocks = ClockSampler(0)
+    clocks.start()
+    for _ in range(max(3, args.warmup)):
+        step(True); step(False)
+    ms = timed(args.steps, True)
+    clk = clocks.stop()
+    ms_e = timed(args.steps, False)
+    t0 = time.perf_counter(); nfe_o = oracle_iter(); dt = time.perf_counter() - t0
+    print(json.dumps({"metric": "physionet_train_samples_per_s", "value": B / (ms / 1e3), "unit": "samples/s", "n_gpus": 1,
+                      "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+                      "vs_baseline": None, "dtype": "tf32x3", "data": "synthetic",
+                      "config": {"workload": "physionet latent ODE (BASELINE configs[2]): GRU encoder 37/40/50, ODE decoder 8 x Dense(20<->40, tanh), "
+                                             "saveat at T irregular times, :unbiased local reg; fwd + full reverse pass", "batch": B, "T": T,
+                                 "l2": "working set a few MB: cache resident by construction"},
+                      "nfe_per_step": info["nfe"], "loss": info["loss"],
+                      "e2e": {"value": B / (ms_e / 1e3), "unit": "samples/s", "ms_per_step": ms_e,
+                              "h2d_bytes_per_step": int(4 * (S["x"].size * 3 + ps_gru.size + ps_node.size)), "d2h_bytes_per_step": int(4 * (S["Nn"] * T * B * 3))},
+                      "gpu_launches": int(info["launches"] * args.steps), "clocks": clk,
+                      "roofline": {"bound": "latency", "kernel": "adjoint solve with T lambda jumps (tiny state 20 x B): launch / latency bound",
+                                   "achieved": None, "peak": None, "unit": None, "frac": None, "traffic": None},
+                      "cpu_baseline": {"value": B / dt, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
+                                       "sample": f"the whole workload, 1 iteration ({dt:.2f} s), numpy float32 oracle", "nfe": int(nfe_o)}}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -509,12 +660,16 @@ def main():
     ap.add_argument("--ref-batch", type=int, default=512, help="bounded sample for the CPU reference")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="mnist_ode", choices=["mnist_ode", "mnist_sde"],
-                    help="mnist_ode (default, the headline metric) or the secondary mnist_sde config")
+    ap.add_argument("--workload", default="mnist_ode", choices=["mnist_ode", "mnist_sde", "physionet"],
+                    help="mnist_ode (default, the headline metric) or a secondary config")
+    ap.add_argument("--phys-batch", type=int, default=256)
+    ap.add_argument("--phys-T", type=int, default=49)
     ap.add_argument("--sde-batch", type=int, default=128)
     args = ap.parse_args()
     if args.workload == "mnist_sde":
         run_sde(args)
+    elif args.workload == "physionet":
+        run_physionet(args)
     elif args.impl == "reference":
         run_reference(args)
     else:
