@@ -14,3 +14,4 @@ try:
     from .layers import neural_ode_apply  # noqa: F401
 except ImportError:  # torch missing
     pass
+from . import trainer  # noqa: F401,E402

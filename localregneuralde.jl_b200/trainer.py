@@ -1,0 +1,190 @@
+"""Host-side training loop pieces next to the hot path: the learning-rate and
+regulariser-weight schedules of experiments/src/utils.jl:1-68 / experiments/src/construct.jl:78-152, the CSV
+metric columns of experiments/src/logging.jl:102-128 and one MNIST neural-ODE training iteration
+(experiments/src/utils.jl:106-115) built from the C-ABI calls (layer forward, head + cross-entropy, adjoint,
+Adam).  Scalars and bookkeeping only: every array operation runs in libLRNDE.so."""
+from __future__ import annotations
+
+import csv
+import ctypes as C
+import math
+import time
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import check, lib
+from .layers import Chain, Context, Dense, NeuralODE, TDChain, nparams
+
+
+# ------------------------------------------------------------------ schedules (experiments/src/utils.jl:1-68)
+class ExponentialDecay:
+    def __init__(self, l0: float, l1: float, nsteps: int):
+        self.l0, self.l1, self.nsteps = float(l0), float(l1), int(nsteps)
+        self.k = math.log(self.l0 / self.l1) / self.nsteps
+
+    def __call__(self, t):
+        return self.l0 * math.exp(-self.k * t)
+
+
+class InverseDecay:
+    def __init__(self, l0: float, gamma: float):
+        self.l0, self.gamma = float(l0), float(gamma)
+
+    def __call__(self, t):
+        return self.l0 / (1 + self.gamma * t)
+
+
+class Step:
+    def __init__(self, l0: float, gamma: float, step_sizes):
+        self.l0, self.gamma = float(l0), float(gamma)
+        self.step_sizes = [step_sizes] if isinstance(step_sizes, int) else list(step_sizes)
+
+    def __call__(self, t):
+        # searchsortedfirst(step_sizes, t - 1) - 1 (1-based index of the first entry >= t - 1, minus one)
+        idx = sum(1 for s in self.step_sizes if s < t - 1)
+        return self.l0 * self.gamma ** idx
+
+
+class Constant:
+    def __init__(self, lam: float):
+        self.lam = float(lam)
+
+    def __call__(self, t):
+        return self.lam
+
+
+class CosineAnneal:
+    def __init__(self, l0: float, l1: float, period: int, restart: bool = False, dampen: float = 1.0):
+        self.range, self.offset = abs(l0 - l1), min(l0, l1)
+        self.dampen, self.period, self.restart = float(dampen), int(period), bool(restart)
+
+    def __call__(self, t):
+        if self.restart:
+            d = self.dampen ** ((t - 1) // self.period)
+            return (self.range * (1 + math.cos(math.pi * ((t - 1) % self.period) / self.period)) / 2 + self.offset) / d
+        return self.range * (1 + math.cos(math.pi * (t - 1) / self.period)) / 2 + self.offset
+
+
+def w_kl_schedule(t):
+    """construct.jl:97: t -> max(0, 1 - 0.99f0^(t - 100))."""
+    return max(0.0, 1.0 - 0.99 ** (t - 100))
+
+
+def lr_scheduler(name: str, lr: float, *, total_steps: int = 1, cosine_lr_div_factor=100.0, cosine_cycle_length=50000,
+                 cosine_dampen=1.0, step_lr_step_decay=0.1, step_lr_steps=(1,), inverse_decay_factor=1e-4,
+                 exponential_lr_div_factor=100.0):
+    """construct.jl:127-148."""
+    if name == "cosine":
+        return CosineAnneal(lr, lr / cosine_lr_div_factor, cosine_cycle_length, restart=True, dampen=cosine_dampen)
+    if name == "constant":
+        return Constant(lr)
+    if name == "step":
+        return Step(lr, step_lr_step_decay, step_lr_steps)
+    if name == "inverse":
+        return InverseDecay(lr, inverse_decay_factor)
+    if name == "exponential":
+        return ExponentialDecay(lr, lr / exponential_lr_div_factor, total_steps)
+    raise ValueError("unknown value for `scheduler` = %s. Supported options are: `constant`, `step`, "
+                     "`exponential`, `inverse` and `cosine`." % name)
+
+
+# ------------------------------------------------------------------ CSV schema (experiments/src/logging.jl:102-128)
+def train_csv_header(latent_ode: bool = False, sde: bool = False) -> List[str]:
+    return (["Step", "Batch Time", "Data Time", "Forward Pass Time", "Backward Pass Time", "Optimizer Time"]
+            + (["Neg Log Likelihood", "KL Divergence"] if latent_ode else ["Cross Entropy Loss"])
+            + ["Regularize Value", "Net Loss"] + (["NFE Drift", "NFE Diffusion"] if sde else ["NFE"])
+            + ([] if latent_ode else ["Accuracy (Top 1)", "Accuracy (Top 5)"]))
+
+
+def eval_csv_header(latent_ode: bool = False, sde: bool = False) -> List[str]:
+    return (["Step", "Batch Time", "Data Time", "Forward Pass Time"] + ([] if latent_ode else ["Cross Entropy Loss"])
+            + ["Regularize Value", "Net Loss"] + (["NFE Drift", "NFE Diffusion"] if sde else ["NFE"])
+            + ([] if latent_ode else ["Accuracy (Top 1)", "Accuracy (Top 5)"]))
+
+
+class CSVLogger:
+    def __init__(self, path: str, header: Sequence[str]):
+        self.path, self.header = path, list(header)
+        with open(path, "w", newline="") as f:
+            csv.writer(f).writerow(self.header)
+
+    def __call__(self, *row):
+        if len(row) != len(self.header):
+            raise ValueError(f"expected {len(self.header)} columns, got {len(row)}")
+        with open(self.path, "a", newline="") as f:
+            csv.writer(f).writerow(row)
+
+
+# ------------------------------------------------------------------ MNIST neural-ODE trainer (torch tensors = device memory)
+class MnistODETrainer:
+    """FlattenLayer -> NeuralODE(TDChain(Dense(785 => H, tanh), Dense(H+1 => 784))) -> sol.u[end] ->
+    Dense(784 => 10) with logitcrossentropy + w_reg * reg_val (experiments/src/construct.jl:180-200, :19-33),
+    Adam (construct.jl:104), scheduled learning rate and w_reg."""
+
+    def __init__(self, *, hidden: int = 100, lr: float = 1e-3, scheduler: str = "inverse", w_reg_start: float = 100.0,
+                 w_reg_end: float = 10.0, w_reg_decay: str = "exponential", total_steps: int = 1000, abstol: float = 1.4e-8,
+                 reltol: float = 1.4e-8, regularize: str = "unbiased", seed: int = 0, ctx: Optional[Context] = None,
+                 device: int = 0):
+        import torch
+        self.torch = torch
+        self.dev = torch.device("cuda", device)
+        self.ctx = ctx or Context(device, torch.cuda.current_stream(self.dev).cuda_stream)
+        self.D, self.C = 784, 10
+        self.chain = TDChain(Chain(Dense(self.D, hidden, "tanh"), Dense(hidden, self.D)))
+        self.node = NeuralODE(self.chain, regularize=regularize, save_start=False, abstol=abstol, reltol=reltol,
+                              maxiters=10_000, ctx=self.ctx)
+        rng = np.random.default_rng(seed)
+        self.ps = torch.from_numpy(self.node.initialparameters(rng)).to(self.dev)
+        a = math.sqrt(6.0 / (self.D + self.C))
+        wc = np.concatenate([rng.uniform(-a, a, (self.C, self.D)).astype(np.float32).ravel(order="F"),
+                             np.zeros(self.C, np.float32)])
+        self.wc = torch.from_numpy(wc).to(self.dev)
+        self.st = self.node.initialstates(rng)
+        self.opt = [torch.zeros_like(self.ps), torch.zeros_like(self.ps), torch.zeros_like(self.wc), torch.zeros_like(self.wc)]
+        self.lr_sched = lr_scheduler(scheduler, lr, total_steps=total_steps)
+        self.w_reg_sched = ExponentialDecay(w_reg_start, w_reg_end, total_steps) if w_reg_decay == "exponential" \
+            else Constant(w_reg_start)
+        self.step = 0
+
+    def train_step(self, x, y, data_time: float = 0.0):
+        """x: (B, 784) float32 CUDA tensor, y: (B,) int32 labels.  Returns the CSV row of this step."""
+        torch, L = self.torch, lib()
+        t_batch = time.perf_counter()
+        self.step += 1
+        w_reg, lr = self.w_reg_sched(self.step), self.lr_sched(self.step)
+        B = x.shape[0]
+        t0 = time.perf_counter()
+        sol, st2 = self.node(x.t(), self.ps, self.st)
+        u_last = sol.u[-1].t()
+        loss = C.c_float()
+        d_u = torch.empty_like(u_last)
+        d_wc = torch.empty_like(self.wc)
+        check(L.lrnde_head_ce(self.ctx._h, self.wc.data_ptr(), u_last.data_ptr(), y.data_ptr(), B, self.D, self.C, 0,
+                              C.byref(loss), d_u.data_ptr(), d_wc.data_ptr()))
+        torch.cuda.synchronize(self.dev)
+        t_fwd = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        d_x, d_ps = self.node.backward(sol, [None] * (len(sol.u) - 1) + [d_u.t()], w_reg)
+        torch.cuda.synchronize(self.dev)
+        t_bwd = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        for p, g, m, v in ((self.ps, d_ps, self.opt[0], self.opt[1]), (self.wc, d_wc, self.opt[2], self.opt[3])):
+            check(L.lrnde_adam_step(self.ctx._h, p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(),
+                                    float(lr), 0.9, 0.999, 1e-8, self.step))
+        torch.cuda.synchronize(self.dev)
+        t_opt = time.perf_counter() - t0
+        # metrics (not on the timed path): logits = W u + b
+        W = self.wc[: self.C * self.D].view(self.D, self.C)       # column-major [C x D]
+        logits = u_last @ W + self.wc[self.C * self.D:]
+        top5 = logits.topk(5, dim=1).indices
+        yl = y.long()
+        acc1 = float((top5[:, 0] == yl).float().mean())
+        acc5 = float((top5 == yl[:, None]).any(dim=1).float().mean())
+        reg = float(st2["reg_val"])
+        nfe = int(st2["nfe"])
+        sol.free()
+        self.st = st2
+        return [self.step, time.perf_counter() - t_batch, data_time, t_fwd, t_bwd, t_opt, float(loss.value), reg,
+                float(loss.value) + w_reg * reg, nfe, acc1, acc5]

@@ -1,0 +1,66 @@
+"""Schedules and CSV schema of the training loop against the reference formulas
+(experiments/src/utils.jl:1-68, experiments/src/logging.jl:102-128); the GPU part runs a few training
+iterations and checks that the loss goes down on a fixed synthetic batch."""
+import math
+
+import numpy as np
+import pytest
+
+import __graft_entry__ as entry
+
+
+@pytest.fixture(scope="module")
+def tr():
+    return entry.load_package().trainer
+
+
+def test_schedules_follow_the_reference_formulas(tr):
+    e = tr.ExponentialDecay(100.0, 10.0, 1000)
+    assert abs(e(0) - 100) < 1e-9 and abs(e(1000) - 10) < 1e-9 and abs(e(500) - math.sqrt(1000)) < 1e-9
+    assert abs(tr.InverseDecay(1e-3, 1e-4)(10000) - 5e-4) < 1e-12
+    s = tr.Step(1.0, 0.1, [10, 20])
+    assert s(1) == 1.0 and s(11) == 1.0 and abs(s(12) - 0.1) < 1e-12 and abs(s(22) - 0.01) < 1e-12
+    assert tr.Step(1.0, 0.5, 5)(7) == 0.5
+    assert tr.Constant(0.3)(99) == 0.3
+    c = tr.CosineAnneal(1.0, 0.0, 10, restart=True, dampen=2.0)
+    assert abs(c(1) - 1.0) < 1e-12 and abs(c(6) - 0.5) < 1e-12 and abs(c(11) - 0.5) < 1e-12      # restart, dampened
+    c2 = tr.CosineAnneal(1.0, 0.0, 10)
+    assert abs(c2(11) - 0.0) < 1e-12
+    assert tr.w_kl_schedule(50) == 0.0 and abs(tr.w_kl_schedule(200) - (1 - 0.99 ** 100)) < 1e-12
+    with pytest.raises(ValueError):
+        tr.lr_scheduler("linear", 1e-3)
+    assert isinstance(tr.lr_scheduler("inverse", 1e-3), tr.InverseDecay)
+
+
+def test_csv_headers_match_the_reference_schema(tr, tmp_path):
+    assert tr.train_csv_header() == ["Step", "Batch Time", "Data Time", "Forward Pass Time", "Backward Pass Time",
+                                     "Optimizer Time", "Cross Entropy Loss", "Regularize Value", "Net Loss", "NFE",
+                                     "Accuracy (Top 1)", "Accuracy (Top 5)"]
+    assert tr.train_csv_header(latent_ode=True)[6:8] == ["Neg Log Likelihood", "KL Divergence"]
+    assert tr.train_csv_header(sde=True)[9:11] == ["NFE Drift", "NFE Diffusion"]
+    assert tr.eval_csv_header()[:5] == ["Step", "Batch Time", "Data Time", "Forward Pass Time", "Cross Entropy Loss"]
+    log = tr.CSVLogger(str(tmp_path / "results_train.csv"), tr.train_csv_header())
+    log(*range(12))
+    with pytest.raises(ValueError):
+        log(1, 2)
+    rows = open(tmp_path / "results_train.csv").read().strip().splitlines()
+    assert rows[0].startswith("Step,Batch Time") and rows[1] == ",".join(str(i) for i in range(12))
+
+
+@pytest.mark.gpu
+def test_training_iterations_reduce_the_loss(tr, tmp_path):
+    import torch
+    t = tr.MnistODETrainer(hidden=100, lr=2e-3, scheduler="constant", w_reg_start=1.0, w_reg_end=0.1, total_steps=10,
+                           abstol=1e-3, reltol=1e-3, seed=0)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.rand((256, 784), device="cuda", generator=g)
+    y = torch.randint(0, 10, (256,), device="cuda", generator=g, dtype=torch.int32)
+    log = tr.CSVLogger(str(tmp_path / "results_train.csv"), tr.train_csv_header())
+    rows = []
+    for _ in range(8):
+        rows.append(t.train_step(x, y))
+        log(*rows[-1])
+    ce = [r[6] for r in rows]
+    assert all(np.isfinite(ce)) and ce[-1] < ce[0] - 0.05, ce            # memorising a fixed batch
+    assert rows[0][0] == 1 and rows[-1][0] == 8 and rows[-1][9] > 0 and 0.0 <= rows[-1][10] <= rows[-1][11] <= 1.0
+    assert len(open(tmp_path / "results_train.csv").read().strip().splitlines()) == 9
