@@ -614,7 +614,11 @@ def run_physionet(args):
         d_h, d_r2g = pkg.mlp_backward(r2g, v["r2g"], h, d_z)
         rec.backward(st_rec, d_h)
         info.update(nfe=st_node["nfe"], loss=loss + w_reg * float(st_node["reg_val"]),
-                    launches=sol.stats.gpu_launches + sol.bwd_stats.gpu_launches + 16)
+                    launches=sol.stats.gpu_launches + sol.bwd_stats.gpu_launches + 16,
+                    phases_us=dict(fwd_solve=sol.stats.reserved[0], saves=sol.stats.reserved[1], reg_step=sol.stats.reserved[2],
+                                   adjoint=sol.bwd_stats.reserved[3], reg_pullback=sol.bwd_stats.reserved[4],
+                                   fwd_setup=sol.stats.reserved[5], bwd_setup=sol.bwd_stats.reserved[5]),
+                    steps_bwd=[sol.bwd_stats.naccept_bwd, sol.bwd_stats.nreject_bwd], nf_bwd=sol.bwd_stats.nf_bwd)
         rec.free(st_rec); sol.free()
 
     def timed(n, resident):
@@ -638,7 +642,8 @@ def run_physionet(args):
                       "config": {"workload": "physionet latent ODE (BASELINE configs[2]): GRU encoder 37/40/50, ODE decoder 8 x Dense(20<->40, tanh), "
                                              "saveat at T irregular times, :unbiased local reg; fwd + full reverse pass", "batch": B, "T": T,
                                  "l2": "working set a few MB: cache resident by construction"},
-                      "nfe_per_step": info["nfe"], "loss": info["loss"],
+                      "nfe_per_step": info["nfe"], "loss": info["loss"], "phases_us": info["phases_us"],
+                      "steps_bwd": info["steps_bwd"], "nf_bwd_per_step": info["nf_bwd"],
                       "e2e": {"value": B / (ms_e / 1e3), "unit": "samples/s", "ms_per_step": ms_e,
                               "h2d_bytes_per_step": int(4 * (S["x"].size * 3 + ps_gru.size + ps_node.size)), "d2h_bytes_per_step": int(4 * (S["Nn"] * T * B * 3))},
                       "gpu_launches": int(info["launches"] * args.steps), "clocks": clk,

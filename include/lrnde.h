@@ -55,7 +55,8 @@ enum { LRNDE_REG_NONE = 0, LRNDE_REG_UNBIASED = 1, LRNDE_REG_BIASED = 2 };
 /* regularize_type (src/perform_step.jl:34,40) */
 enum { LRNDE_REGTYPE_ERROR = 0, LRNDE_REGTYPE_STIFFNESS = 1 };
 /* arithmetic of the dense contractions */
-enum { LRNDE_PREC_AUTO = 0, LRNDE_PREC_FP32_SIMT = 1, LRNDE_PREC_TF32X3 = 2, LRNDE_PREC_TF32 = 3 };
+enum { LRNDE_PREC_AUTO = 0, LRNDE_PREC_FP32_SIMT = 1, LRNDE_PREC_TF32X3 = 2, LRNDE_PREC_TF32 = 3,
+       LRNDE_PREC_SMEM = 4 /* FP32, whole network out of shared memory: one launch per evaluation (small nets) */ };
 /* solver retcodes (OrdinaryDiffEq ReturnCode subset the loop can produce) */
 enum { LRNDE_RET_SUCCESS = 0, LRNDE_RET_MAXITERS = 1, LRNDE_RET_DTMIN = 2, LRNDE_RET_UNSTABLE = 3,
        LRNDE_RET_TAPEFULL = 4 };

@@ -19,6 +19,7 @@
 #include "lrnde_host.h"
 #include "lrnde_kernels.cuh"
 #include "lrnde_umma.cuh"
+#include "lrnde_smem_mlp.cuh"
 
 // ------------------------------------------------------------------------------------------
 // errors
@@ -270,6 +271,11 @@ struct MlpEval {
   int nacc_max = 8;
   bool use_lean = true;
   bool use_wide = true;
+  // small-state engine (lrnde_smem_mlp.cuh): the whole network out of shared memory, one launch per evaluation
+  bool use_small = false;
+  SdeNet snet;
+  int sS = 32, s_tiles = 1, s_grid = 1;
+  float* s_gpart = nullptr;
   int passes = 3;
   float* ybuf = nullptr;
   float* delta[2] = {nullptr, nullptr};
@@ -281,6 +287,8 @@ struct MlpEval {
       : ctx(c), m(mm), ps(p), B(b), prec(precision), with_vjp(vjp) {
     const int L = (int)m->layers.size();
     use_umma = (precision != LRNDE_PREC_FP32_SIMT);
+    setup_small(precision);
+    if (use_small) use_umma = false;
     use_cluster = (getenv("LRNDE_NO_CLUSTER") == nullptr);
     if (const char* e = getenv("LRNDE_NACC")) nacc_max = std::max(1, std::min(8, atoi(e)));
     use_lean = (getenv("LRNDE_NO_LEAN") == nullptr);
@@ -349,11 +357,64 @@ struct MlpEval {
     ctx->release(delta[0]);
     ctx->release(delta[1]);
     ctx->release(part);
+    ctx->release(s_gpart);
   }
 
   // once per call: transposed weights for the data-gradient GEMMs, and (tcgen05 path) the
   // tf32 hi/lo shared-memory images of every weight matrix
+  // Eligibility of the shared-memory engine: the padded network (twice, for the reverse pass) and the tile
+  // buffers fit one SM.  LRNDE_PREC_SMEM asks for it explicitly; LRNDE_PREC_AUTO picks it for batches the
+  // per-layer tcgen05 kernels cannot fill (their cost is per-CTA latency, ~25 us per layer launch).
+  void setup_small(int precision) {
+    use_small = false;
+    if (precision != LRNDE_PREC_SMEM && precision != LRNDE_PREC_AUTO) return;
+    const bool want = (precision == LRNDE_PREC_SMEM);
+    if ((int)m->layers.size() > SDE_MAXL) { if (want) lr_fail(LRNDE_EINVAL, "precision smem: at most %d layers", SDE_MAXL); return; }
+    memset(&snet, 0, sizeof(snet));
+    snet.nl = (int)m->layers.size(); snet.td = m->td; snet.D = m->D; snet.nparams = (int)m->nparams;
+    int woff = 0, hoff = 0, md = m->D;
+    for (int l = 0; l < snet.nl; ++l) {
+      const LayerInfo& L = m->layers[l];
+      snet.in[l] = L.in; snet.out[l] = L.out; snet.outp[l] = (L.out + 3) & ~3; snet.act[l] = L.act;
+      snet.ps_w[l] = L.w_off; snet.ps_b[l] = L.b_off;
+      snet.w_off[l] = woff; woff += (L.in + m->td + 1) * snet.outp[l];
+      snet.hid_off[l] = hoff; hoff += snet.outp[l];
+      md = std::max(md, std::max(L.in, snet.outp[l]));
+    }
+    snet.wfloats = woff; snet.hid_rows = hoff; snet.maxdim = md;
+    int n_sm = 0;
+    size_t smem_optin = 0;
+    sde_device_limits(ctx->device, &n_sm, &smem_optin);
+    int S = 32;
+    while (S > 8 && ((B + S - 1) / S) < n_sm / 2) S >>= 1;
+    for (;; S >>= 1) {
+      if (small_smem_bytes(snet, m->D, S + 1, true) + 2048 <= smem_optin) break;   // 2 KB of static shared memory
+      if (S <= 4) { if (want) lr_fail(LRNDE_EINVAL, "precision smem: the network does not fit shared memory"); return; }
+    }
+    if (!want && (B > 4096 || getenv("LRNDE_NO_SMEM"))) return;
+    use_small = true;
+    sS = S;
+    const int ntiles = (int)((B + S - 1) / S);
+    s_tiles = (ntiles + 4 * n_sm - 1) / (4 * n_sm);
+    s_grid = (ntiles + s_tiles - 1) / s_tiles;
+    if (with_vjp) s_gpart = (float*)ctx->alloc(sizeof(float) * (size_t)s_grid * snet.wfloats);
+    static bool attr_set = false;
+    if (!attr_set) {
+      LR_CUDA(cudaFuncSetAttribute(small_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin - 2048));
+      LR_CUDA(cudaFuncSetAttribute(small_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin - 2048));
+      attr_set = true;
+    }
+  }
+  SmallP small_params(const LinComb* in, const int* done) const {
+    SmallP q;
+    memset(&q, 0, sizeof(q));
+    q.n = snet; q.in_act = m->input_act; q.ps = ps; q.in = in; q.done = done;
+    q.B = (int)B; q.D = m->D; q.S = sS; q.SP = sS + 1; q.tiles_per_cta = s_tiles;
+    return q;
+  }
+
   void prepare() {
+    if (use_small) return;
     for (size_t l = 0; l < m->layers.size(); ++l) {
       const LayerInfo& Li = m->layers[l];
       if (with_vjp) {
@@ -479,6 +540,14 @@ struct MlpEval {
   // itself is also written to in->dst (u_{n+1} of the step, fused into stage 7's prologue)
   void forward(const LinComb* in, const int* done, const LinComb* out = nullptr,
                bool side_to_in_dst = false) {
+    if (use_small) {
+      SmallP q = small_params(in, done);
+      q.out = out; q.side_to_in_dst = side_to_in_dst ? 1 : 0;
+      small_kernel<false><<<s_grid, SDE_THREADS, small_smem_bytes(snet, m->D, sS + 1, false), ctx->stream>>>(q);
+      LR_COUNT(ctx);
+      LR_CHECK_LAUNCH();
+      return;
+    }
     const int L = (int)m->layers.size();
     for (int l = 0; l < std::min(L, max_layers); ++l) {
       DenseP p = layer_fwd(l, in, nullptr);
@@ -518,6 +587,17 @@ struct MlpEval {
   void vjp(const LinComb* y, const LinComb* lamd, float* out_a, const LinComb* out_desc,
            float a_scale, float* dps_ptr, const LinComb* dps_desc, size_t dps_off, float p_scale,
            float p_beta, const int* done) {
+    if (use_small) {
+      SmallP q = small_params(y, done);
+      q.lam = lamd; q.out_a = out_a; q.out_desc = out_desc; q.a_scale = a_scale; q.gpart = s_gpart;
+      small_kernel<true><<<s_grid, SDE_THREADS, small_smem_bytes(snet, m->D, sS + 1, true), ctx->stream>>>(q);
+      LR_COUNT(ctx);
+      small_dps_reduce_kernel<<<(snet.wfloats + 255) / 256, 256, 0, ctx->stream>>>(snet, s_gpart, s_grid, dps_ptr, dps_desc, dps_off, p_scale,
+                                                          p_beta, done);
+      LR_COUNT(ctx);
+      LR_CHECK_LAUNCH();
+      return;
+    }
     const int L = (int)m->layers.size();
     const size_t DB = (size_t)m->D * B;
     cudaStream_t st = ctx->stream;
@@ -981,7 +1061,7 @@ static void lr_validate_opts(const lrnde_opts* o) {
   if (!(o->t2 > o->t0)) lr_fail(LRNDE_EINVAL, "tspan must satisfy t0 < t2");
   if (o->maxiters < 1) lr_fail(LRNDE_EINVAL, "maxiters must be >= 1");
   if (o->nsave > 0 && !o->saveat) lr_fail(LRNDE_EINVAL, "saveat is NULL but nsave > 0");
-  if (o->precision < LRNDE_PREC_AUTO || o->precision > LRNDE_PREC_TF32)
+  if (o->precision < LRNDE_PREC_AUTO || o->precision > LRNDE_PREC_SMEM)
     lr_fail(LRNDE_EINVAL, "unknown precision %d", o->precision);
 }
 

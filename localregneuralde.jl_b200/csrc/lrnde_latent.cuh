@@ -316,9 +316,9 @@ extern "C" int lrnde_gru_backward(lrnde_ctx* ctx, lrnde_gru_tape* Tp, const floa
   LR_CUDA(cudaFuncSetAttribute(gru_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   gru_backward_kernel<<<Tp->grid, SDE_THREADS, smem, st>>>(p);
   LR_COUNT(ctx);
-  sde_grad_reduce_kernel<<<8, 256, 0, st>>>(p.nu, gpart.p, stride, 0, Tp->grid, dps.p);
-  sde_grad_reduce_kernel<<<8, 256, 0, st>>>(p.nr, gpart.p, stride, p.nu.wfloats, Tp->grid, dps.p);
-  sde_grad_reduce_kernel<<<8, 256, 0, st>>>(p.nn, gpart.p, stride, p.nu.wfloats + p.nr.wfloats, Tp->grid, dps.p);
+  sde_grad_reduce_kernel<<<64, 256, 0, st>>>(p.nu, gpart.p, stride, 0, Tp->grid, dps.p);
+  sde_grad_reduce_kernel<<<64, 256, 0, st>>>(p.nr, gpart.p, stride, p.nu.wfloats, Tp->grid, dps.p);
+  sde_grad_reduce_kernel<<<64, 256, 0, st>>>(p.nn, gpart.p, stride, p.nu.wfloats + p.nr.wfloats, Tp->grid, dps.p);
   LR_COUNT(ctx); LR_COUNT(ctx); LR_COUNT(ctx);
   LR_CUDA(cudaGetLastError());
   LR_CUDA(cudaMemcpyAsync(d_ps, dps.p, sizeof(float) * P, Tp->host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, st));
@@ -488,7 +488,7 @@ extern "C" int lrnde_mlp_backward(lrnde_ctx* ctx, const lrnde_layer_desc* layers
   LR_CUDA(cudaFuncSetAttribute(mlpop_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   mlpop_kernel<true><<<grid, SDE_THREADS, smem, st>>>(p);
   LR_COUNT(ctx);
-  sde_grad_reduce_kernel<<<8, 256, 0, st>>>(p.n, gpart.p, p.n.wfloats, 0, grid, dpsd.p);
+  sde_grad_reduce_kernel<<<64, 256, 0, st>>>(p.n, gpart.p, p.n.wfloats, 0, grid, dpsd.p);
   LR_COUNT(ctx);
   LR_CUDA(cudaGetLastError());
   if (d_x) LR_CUDA(cudaMemcpyAsync(d_x, dxd.p, sizeof(float) * p.in0 * N, ok, st));

@@ -28,28 +28,7 @@
 
 namespace cg = cooperative_groups;
 
-#define SDE_MAXL 6
-#define SDE_STK 64
-#define SDE_THREADS 256
-
-struct SdeNet {
-  int nl, td, D;
-  int in[SDE_MAXL], out[SDE_MAXL], outp[SDE_MAXL], act[SDE_MAXL];
-  int w_off[SDE_MAXL];    // float offset of the layer's [(in + td + 1) x outp] block in shared memory
-  int hid_off[SDE_MAXL];  // row offset of the layer's pre / post activation buffers
-  long long ps_w[SDE_MAXL], ps_b[SDE_MAXL];
-  int wfloats;            // shared-memory floats of all blocks
-  int hid_rows;           // total rows of the activation buffers
-  int maxdim;
-  int nparams;
-};
-
-struct SdeConsts {
-  float beta1, beta2, gamma, qmin, qmax, qoldinit, delta, discard, order;
-  int pow_mode;
-};
-
-struct SdeTile { int S, SP, D, nvalid, nthr, tid; };
+#include "lrnde_smem_mlp.cuh"
 
 // ---------------------------------------------------------------- Philox4x32-10
 __device__ __forceinline__ float sde_normal(unsigned long long seed, unsigned stream, unsigned draw,
@@ -66,118 +45,6 @@ __device__ __forceinline__ float sde_normal(unsigned long long seed, unsigned st
   const double u1 = ((double)c0 + 0.5) * 2.3283064365386963e-10;
   const double u2 = ((double)c1 + 0.5) * 2.3283064365386963e-10;
   return (float)(sqrt(-2.0 * log(u1)) * cos(6.283185307179586 * u2));
-}
-
-// ---------------------------------------------------------------- networks in shared memory
-__device__ void sde_load_weights(const SdeNet& n, const float* __restrict__ ps, float* W, int tid, int nthr) {
-  for (int l = 0; l < n.nl; ++l) {
-    const int rows = n.in[l] + n.td + 1, outp = n.outp[l], out = n.out[l];
-    for (int e = tid; e < rows * outp; e += nthr) {
-      const int i = e / outp, r = e % outp;
-      float v = 0.0f;
-      if (r < out) v = (i < rows - 1) ? ps[n.ps_w[l] + (long long)i * out + r] : ps[n.ps_b[l] + r];
-      W[n.w_off[l] + e] = v;
-    }
-  }
-}
-
-// y = net(x, t) for the S samples of the tile; x, y: [D][SP]; pre/post: [hid_rows][SP]
-__device__ void sde_mlp_fwd(const SdeNet& n, const float* W, const float* x, float t, float* y, float* pre,
-                            float* post, const SdeTile& T) {
-  const float* cur = x;
-  for (int l = 0; l < n.nl; ++l) {
-    const int in = n.in[l], out = n.out[l], outp = n.outp[l], act = n.act[l];
-    const float* Wl = W + n.w_off[l];
-    float* pl = pre + n.hid_off[l] * T.SP;
-    float* dst = (l == n.nl - 1) ? y : post + n.hid_off[l] * T.SP;
-    for (int item = T.tid; item < (outp >> 2) * T.S; item += T.nthr) {
-      const int s = item % T.S, r0 = (item / T.S) << 2;
-      float4 acc = *reinterpret_cast<const float4*>(Wl + (in + n.td) * outp + r0);
-      if (n.td) {
-        const float4 w = *reinterpret_cast<const float4*>(Wl + in * outp + r0);
-        acc.x = fmaf(w.x, t, acc.x); acc.y = fmaf(w.y, t, acc.y); acc.z = fmaf(w.z, t, acc.z); acc.w = fmaf(w.w, t, acc.w);
-      }
-#pragma unroll 8
-      for (int i = 0; i < in; ++i) {
-        const float xv = cur[i * T.SP + s];
-        const float4 w = *reinterpret_cast<const float4*>(Wl + i * outp + r0);
-        acc.x = fmaf(w.x, xv, acc.x); acc.y = fmaf(w.y, xv, acc.y); acc.z = fmaf(w.z, xv, acc.z); acc.w = fmaf(w.w, xv, acc.w);
-      }
-      const float a[4] = {acc.x, acc.y, acc.z, acc.w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        if (r0 + j < out) {
-          pl[(r0 + j) * T.SP + s] = a[j];
-          dst[(r0 + j) * T.SP + s] = lr_act(act, a[j]);
-        }
-    }
-    __syncthreads();
-    cur = dst;
-  }
-}
-
-// (J_x^T cot, J_p^T cot) of net at (x, t): xbar += J_x^T cot (when xbar != nullptr), G += J_p^T cot.
-// cot: [D][SP] (read only); dA/dB: scratch [maxdim][SP].  Samples >= nvalid contribute nothing.
-__device__ void sde_mlp_vjp(const SdeNet& n, const float* W, float* G, const float* x, float t, const float* cot,
-                            float* xbar, float* y_scratch, float* pre, float* post, float* dA, float* dB,
-                            const SdeTile& T) {
-  sde_mlp_fwd(n, W, x, t, y_scratch, pre, post, T);
-  const int L = n.nl - 1;
-  {
-    const float* pl = pre + n.hid_off[L] * T.SP;
-    for (int idx = T.tid; idx < n.out[L] * T.S; idx += T.nthr) {
-      const int r = idx / T.S, s = idx % T.S, a = r * T.SP + s;
-      dA[a] = (s < T.nvalid) ? cot[a] * lr_dact(n.act[L], pl[a]) : 0.0f;
-    }
-  }
-  __syncthreads();
-  float* dcur = dA;
-  float* dnext = dB;
-  for (int l = L; l >= 0; --l) {
-    const int in = n.in[l], out = n.out[l], outp = n.outp[l];
-    const float* Wl = W + n.w_off[l];
-    float* Gl = G + n.w_off[l];
-    const float* xin = (l == 0) ? x : post + n.hid_off[l - 1] * T.SP;
-    const int rows = in + n.td + 1;
-    for (int item = T.tid; item < rows * outp; item += T.nthr) {
-      const int i = item / outp, r = item % outp;
-      if (r >= out) continue;
-      float acc = 0.0f;
-      if (i < in) {
-#pragma unroll 8
-        for (int s = 0; s < T.S; ++s) acc = fmaf(xin[i * T.SP + s], dcur[r * T.SP + s], acc);
-      } else {
-        for (int s = 0; s < T.S; ++s) acc += dcur[r * T.SP + s];
-        if (n.td && i == in) acc *= t;
-      }
-      Gl[item] += acc;
-    }
-    if (l > 0 || xbar) {
-      const float* pprev = (l > 0) ? pre + n.hid_off[l - 1] * T.SP : nullptr;
-      const int actprev = (l > 0) ? n.act[l - 1] : 0;
-      const int nb = (in + 3) >> 2;
-      for (int item = T.tid; item < nb * T.S; item += T.nthr) {
-        const int s = item % T.S, i0 = (item / T.S) << 2;
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 4
-        for (int r = 0; r < out; ++r) {
-          const float d = dcur[r * T.SP + s];
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            if (i0 + j < in) acc[j] = fmaf(Wl[(i0 + j) * outp + r], d, acc[j]);
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (i0 + j < in) {
-            const int a = (i0 + j) * T.SP + s;
-            if (l > 0) dnext[a] = acc[j] * lr_dact(actprev, pprev[a]);
-            else xbar[a] += acc[j];
-          }
-      }
-    }
-    __syncthreads();
-    float* tmp = dcur; dcur = dnext; dnext = tmp;
-  }
 }
 
 // ---------------------------------------------------------------- SOSRI step on a tile
@@ -994,18 +861,21 @@ __global__ void __launch_bounds__(SDE_THREADS, 1) sde_backward_kernel(SdeBwdP p)
   for (int e = tid; e < p.ng.wfloats; e += nthr) mine[p.nf.wfloats + e] = Gg[e];
 }
 
-// fixed-order sum of the per-CTA partial gradients, un-padded into the flat parameter layout
+// fixed-order sum of the per-CTA partial gradients, un-padded into the flat parameter layout (one thread per
+// padded element; `stride` = floats per CTA record, `base` = offset of this network inside the record)
 __global__ void sde_grad_reduce_kernel(SdeNet n, const float* gpart, int stride, int base, int nblk, float* d_ps) {
-  for (int l = 0; l < n.nl; ++l) {
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n.wfloats; e += gridDim.x * blockDim.x) {
+    int l = 0;
+    while (l + 1 < n.nl && e >= n.w_off[l + 1]) ++l;
+    const int loc = e - n.w_off[l];
     const int rows = n.in[l] + n.td + 1, outp = n.outp[l], out = n.out[l];
-    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < rows * outp; e += gridDim.x * blockDim.x) {
-      const int i = e / outp, r = e % outp;
-      if (r >= out) continue;
-      float acc = 0.0f;
-      for (int bb = 0; bb < nblk; ++bb) acc += gpart[(size_t)bb * stride + base + n.w_off[l] + e];
-      if (i < rows - 1) d_ps[n.ps_w[l] + (long long)i * out + r] = acc;
-      else d_ps[n.ps_b[l] + r] = acc;
-    }
+    const int i = loc / outp, r = loc % outp;
+    if (r >= out) continue;
+    float acc = 0.0f;
+#pragma unroll 8
+    for (int bb = 0; bb < nblk; ++bb) acc += gpart[(size_t)bb * stride + base + e];
+    if (i < rows - 1) d_ps[n.ps_w[l] + (long long)i * out + r] = acc;
+    else d_ps[n.ps_b[l] + r] = acc;
   }
 }
 
@@ -1131,18 +1001,6 @@ struct lrnde_sde_tape {
   }
   ~lrnde_sde_tape() { for (void* p : owned) ctx->release(p); }
 };
-
-// device limits, queried once per device (cudaGetDeviceProperties is a slow, lock-taking call)
-static void sde_device_limits(int device, int* n_sm, size_t* smem_optin) {
-  static int cached_dev = -1, c_sm = 0, c_smem = 0;
-  if (cached_dev != device) {
-    LR_CUDA(cudaDeviceGetAttribute(&c_sm, cudaDevAttrMultiProcessorCount, device));
-    LR_CUDA(cudaDeviceGetAttribute(&c_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
-    cached_dev = device;
-  }
-  *n_sm = c_sm;
-  *smem_optin = (size_t)c_smem;
-}
 
 static SdeNet sde_make_net(const lrnde_model* m, const char* what) {
   SdeNet n;
@@ -1444,9 +1302,9 @@ extern "C" int lrnde_sde_backward(lrnde_ctx* ctx, lrnde_sde_tape* T, const float
   q.eest_reg = T->eest_reg; q.d_reg = d_reg;
   sde_backward_kernel<<<T->grid, SDE_THREADS, smem_b, st>>>(q);
   LR_COUNT(ctx);
-  sde_grad_reduce_kernel<<<8, 256, 0, st>>>(T->nf, gpart.p, gstride, 0, T->grid, dpf.p);
+  sde_grad_reduce_kernel<<<64, 256, 0, st>>>(T->nf, gpart.p, gstride, 0, T->grid, dpf.p);
   LR_COUNT(ctx);
-  sde_grad_reduce_kernel<<<8, 256, 0, st>>>(T->ng, gpart.p, gstride, T->nf.wfloats, T->grid, dpg.p);
+  sde_grad_reduce_kernel<<<64, 256, 0, st>>>(T->ng, gpart.p, gstride, T->nf.wfloats, T->grid, dpg.p);
   LR_COUNT(ctx);
   LR_CUDA(cudaGetLastError());
   const cudaMemcpyKind out_kind = host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;

@@ -17,6 +17,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLD = os.path.join(ROOT, "tests", "golden")
 PRECS = ["fp32", "tf32x3"]
+PRECS_SMALL = ["fp32", "tf32x3", "smem"]     # "smem": the shared-memory engine (networks that fit one SM)
 
 
 @pytest.fixture(scope="module")
@@ -47,7 +48,7 @@ def rel(a, b):
 
 
 # ------------------------------------------------------------------ f(u, p, t)
-@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("prec", PRECS_SMALL)
 @pytest.mark.parametrize("layers,td,input_act,B", [
     ([(2, 4, "gelu"), (4, 2, "identity")], True, None, 1),
     ([(3, 5, "tanh"), (5, 3, "tanh")], False, "tanh", 7),
@@ -57,6 +58,8 @@ def rel(a, b):
     ([(33, 70, "gelu"), (70, 33, "identity")], True, None, 65),
 ])
 def test_dynamics_matches_oracle(pkg, prec, layers, td, input_act, B):
+    if prec == "smem" and layers[0][0] > 256:
+        pytest.skip("the mnist network (158 K parameters) does not fit shared memory: tcgen05 path only")
     rng = np.random.default_rng(0)
     om = _omodel(layers, td, input_act)
     ps = orc.glorot_uniform_params(om, rng) + (0.05 * rng.standard_normal(om.nparams)).astype(np.float32)
@@ -99,7 +102,7 @@ GOLDEN = ["tiny_td_gelu", "tiny_plain_biased", "mid_tanh_stiff", "latent_saveat"
           "eval_mode", "mid_x3_err", "mid_x3_stiff", "gelu3_x3_biased"]
 
 
-@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("prec", PRECS_SMALL)
 @pytest.mark.parametrize("loop_mode", [0, 1])
 @pytest.mark.parametrize("name", GOLDEN)
 def test_layer_matches_golden(pkg, name, loop_mode, prec):
@@ -112,6 +115,8 @@ def test_layer_matches_golden(pkg, name, loop_mode, prec):
     EEst / reg_val, so a second Float32 implementation is held to: same decisions up to the
     measured Float32-vs-Float64 gap, states 1e-4, adjoint gradients 1e-3."""
     layers, td, input_act, B, kw, seed, d_reg = _cases()[name]
+    if prec == "smem" and name == "mnist_b16":
+        pytest.skip("the mnist network does not fit shared memory: tcgen05 path only")
     g = np.load(os.path.join(GOLD, name + ".npz"))
     want, want64 = g["step_log"], g["step_log64"]
     n64 = min(len(want), len(want64))
@@ -120,7 +125,7 @@ def test_layer_matches_golden(pkg, name, loop_mode, prec):
     strict_bwd = strict and int(g["n_bwd64"]) == len(g["bwd_step_log"])
     # 3xTF32 keeps fp32-level products but drops the lo*lo term and rounds the lo parts: its
     # rounding noise is a few times the FP32 FMA's, so noise-regime allowances scale with it
-    noise = 1.0 if prec == "fp32" else 30.0
+    noise = 1.0 if prec in ("fp32", "smem") else 30.0
     layer = pkg.NeuralODE(_chain(pkg, layers, td, input_act), precision=prec, loop_mode=loop_mode, **kw)
     st = layer.initialstates(np.random.default_rng(seed + 100))
     if name == "eval_mode":
@@ -341,7 +346,7 @@ def test_full_size_batch_replication_property(pkg, prec):
     assert rel(dx2[:, :B], dx1) < 1e-3
 
 
-@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("prec", PRECS_SMALL)
 def test_physionet_latent_ode_shape(pkg, prec):
     """BASELINE configs[2] shape on the path: the latent-ODE decoder dynamics
     (experiments/src/construct.jl:235-243: tanh.(u) then 8 x Dense(20<->40, tanh), not time
@@ -367,7 +372,7 @@ def test_physionet_latent_ode_shape(pkg, prec):
     assert st2["nfe"] == ost2["nfe"]
     for i in (0, 1, 17, 48):
         assert rel(sol.u[i], osol.u[i]) < 1e-4
-    assert abs(float(st2["reg_val"]) / float(ost2["reg_val"]) - 1) < (1e-3 if prec == "fp32" else 2e-2)
+    assert abs(float(st2["reg_val"]) / float(ost2["reg_val"]) - 1) < (1e-3 if prec in ("fp32", "smem") else 2e-2)
     cots = [(rng.standard_normal((20, B)) / B).astype(np.float32) for _ in range(49)]
     d_x, d_ps = node.backward(sol, cots, 0.0)
     o_dx, o_dps = on.backward(aux, cots, 0.0, ps)
