@@ -91,7 +91,10 @@ typedef struct {
   int32_t host_buffers;  /* 1: ps/x/u_save/d_* are HOST pointers (Julia Array); staged inside */
   int32_t keep_tape;     /* 1: return a tape for lrnde_ode_backward (training) */
   int32_t loop_mode;     /* 0: CUDA-graph WHILE node; 1: host-chunked replay (diagnostic) */
-  int32_t reserved[7];
+  int32_t last_only;     /* 1: return only sol.u[end] (the diffeqsol_to_array layer that follows the functor in
+                            every classifier of experiments/src/construct.jl, src/utils.jl:37, fused): u_save and
+                            d_u_save then hold ONE [D,B] block; t1 / the regulariser are unaffected */
+  int32_t reserved[6];
 } lrnde_opts;
 
 typedef struct {

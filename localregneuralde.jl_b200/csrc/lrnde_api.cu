@@ -1215,6 +1215,12 @@ extern "C" int lrnde_ode_forward(lrnde_ctx* ctx, const lrnde_model* m, const lrn
       t1 = times[idx];
     } else t1 = o->t0;
   }
+  if (o->last_only) {   // fused diffeqsol_to_array (src/utils.jl:37): only sol.u[end] leaves the library
+    int last = -1, mx = -1;
+    for (size_t i = 0; i < out_index.size(); ++i)
+      if (out_index[i] > mx) { mx = out_index[i]; last = (int)i; }
+    for (size_t i = 0; i < out_index.size(); ++i) out_index[i] = ((int)i == last) ? 0 : -1;
+  }
   int nout = 0;
   for (int v : out_index) nout = std::max(nout, v + 1);
   if (u_save && nout > u_save_cap)

@@ -247,7 +247,7 @@ class NeuralODE:
                  tspan=(0.0, 1.0), regularize=True, maxiters: int = 1000,
                  regularize_type: str = "error_estimate", precision: str = "auto",
                  pow_mode: str = "fastpow_2023", loop_mode: int = 0, ctx: Optional[Context] = None,
-                 **kwargs):
+                 return_last_only: bool = False, **kwargs):
         if isinstance(regularize, bool):
             regularize = "unbiased" if regularize else "none"          # :14-16
         if regularize not in self.VALID_MODES:                          # utils.jl:53-58
@@ -267,6 +267,7 @@ class NeuralODE:
         if kwargs:
             raise TypeError(f"unsupported solve kwargs {sorted(kwargs)}")
         self.precision, self.pow_mode, self.loop_mode = precision, pow_mode, loop_mode
+        self.return_last_only = bool(return_last_only)   # fused diffeqsol_to_array: sol.u == [u(t2)]
         self._ctx = ctx
 
     # Lux.initialparameters / initialstates (neural_ode.jl:27-31)
@@ -309,6 +310,7 @@ class NeuralODE:
         o.host_buffers = 1 if host else 0
         o.keep_tape = 1 if keep_tape else 0
         o.loop_mode = int(self.loop_mode)
+        o.last_only = 1 if self.return_last_only else 0
         return o, keep
 
     def __call__(self, x, ps, st, keep_tape: Optional[bool] = None):

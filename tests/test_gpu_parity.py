@@ -489,3 +489,26 @@ def test_lean_wide_and_cluster_instantiations_agree(pkg, monkeypatch):
     # lean vs general and wide vs narrow do the same arithmetic in the same order per output element
     assert res["default"][0].tobytes() == res["general"][0].tobytes()
     assert res["default"][0].tobytes() == res["narrow"][0].tobytes()
+
+
+def test_return_last_only_is_the_fused_sol_to_arr(pkg):
+    """lrnde_opts.last_only: only sol.u[end] crosses the boundary (src/utils.jl:37 fused); states, the
+    regulariser, NFE and the gradients are those of the full call with a zero cotangent on u(t1)."""
+    layers = [(16, 12, "tanh"), (12, 16, "identity")]
+    om = _omodel(layers, True, None)
+    rng = np.random.default_rng(4)
+    ps = (orc.glorot_uniform_params(om, rng) * 3).astype(np.float32)
+    x = rng.standard_normal((16, 37)).astype(np.float32)
+    kw = dict(regularize="unbiased", abstol=1e-3, reltol=1e-3, save_start=False)
+    cot = (rng.standard_normal((16, 37)) / 37).astype(np.float32)
+    full = pkg.NeuralODE(_chain(pkg, layers, True, None), precision="tf32x3", **kw)
+    last = pkg.NeuralODE(_chain(pkg, layers, True, None), precision="tf32x3", return_last_only=True, **kw)
+    s1, st1 = full(x, ps, full.initialstates(np.random.default_rng(2)))
+    s2, st2 = last(x, ps, last.initialstates(np.random.default_rng(2)))
+    assert len(s1.u) == 2 and len(s2.u) == 1 and s2.t[0] == np.float32(1.0)
+    assert np.asarray(s2.u[0]).tobytes() == np.asarray(s1.u[1]).tobytes()
+    assert st1["nfe"] == st2["nfe"] and st1["reg_val"] == st2["reg_val"]
+    dx1, dp1 = full.backward(s1, [None, cot], 0.7)
+    dx2, dp2 = last.backward(s2, [cot], 0.7)
+    assert np.asarray(dx1).tobytes() == np.asarray(dx2).tobytes() and np.asarray(dp1).tobytes() == np.asarray(dp2).tobytes()
+    s1.free(); s2.free()
