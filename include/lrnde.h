@@ -74,6 +74,17 @@ typedef struct {
   int32_t act; /* LRNDE_ACT_* */
 } lrnde_layer_desc;
 
+/* One layer of the conv dynamics (experiments/src/construct.jl:212-218):
+ * Conv((3,3), in_ch(+1) => out_ch; pad=(1,1), use_bias=false), optionally wrapped as
+ * Chain(Conv, BatchNorm(out_ch, act)).  in_ch EXCLUDES the TDChain time channel.  Parameters in
+ * ComponentArray order: weight[3,3,in_ch(+1),out_ch], then (batchnorm) scale[out_ch], bias[out_ch]. */
+typedef struct {
+  int32_t in_ch;
+  int32_t out_ch;
+  int32_t batchnorm; /* 0 / 1; training-mode batch statistics over (W,H,B), eps = 1e-5 */
+  int32_t act;       /* LRNDE_ACT_*: BatchNorm's activation (or the conv's own when batchnorm == 0) */
+} lrnde_conv_layer_desc;
+
 /* kwargs of NeuralODE(...) / solve(...) that reach the hot path. */
 typedef struct {
   float t0, t2;          /* tspan (neural_ode.jl:12) */
@@ -130,6 +141,13 @@ int lrnde_ctx_set_dist(lrnde_ctx* ctx, int rank, int nranks, void* const* mailbo
 
 int lrnde_model_create(lrnde_ctx* ctx, const lrnde_layer_desc* layers, int nlayers,
                        int time_dependent, int input_act, lrnde_model** out);
+/* Conv dynamics on a WHCN state [width, height, channels, B] (state dims D = width*height*channels; the
+ * layer functor, solve, regulariser and adjoint entry points below take the model unchanged).  Replaces
+ * TDChain(Chain(Chain(Conv, BatchNorm), ..., Conv)) applied through the `dudt` closure (neural_ode.jl:44-48,
+ * src/layers/common.jl:10-45).  width % 4 == 0, 4 <= width <= 32; the last layer is a plain Conv.  BatchNorm
+ * couples the samples of a batch, so a model with batchnorm layers runs on a single-GPU ctx only. */
+int lrnde_conv_model_create(lrnde_ctx* ctx, const lrnde_conv_layer_desc* layers, int nlayers, int width,
+                            int height, int time_dependent, lrnde_model** out);
 int lrnde_model_destroy(lrnde_model* m);
 int64_t lrnde_model_nparams(const lrnde_model* m);
 int64_t lrnde_model_state_dims(const lrnde_model* m);
@@ -137,6 +155,11 @@ int64_t lrnde_model_state_dims(const lrnde_model* m);
 /* One f(u, ps, t) evaluation (the `dudt` closure, neural_ode.jl:45-48); parity hook. */
 int lrnde_dynamics_eval(lrnde_ctx* ctx, const lrnde_model* m, const lrnde_opts* o,
                         const float* ps, const float* u, float t, int64_t B, float* du);
+
+/* (J_u^T lam, J_p^T lam) of one f evaluation: what Zygote.pullback((u,p) -> dudt(u,p,t)) returns inside
+ * SciMLSensitivity's ZygoteVJP (neural_ode.jl:11); parity hook.  a [D,B], dps [nparams]. */
+int lrnde_dynamics_vjp(lrnde_ctx* ctx, const lrnde_model* m, const lrnde_opts* o, const float* ps,
+                       const float* u, float t, const float* lam, int64_t B, float* a, float* dps);
 
 /* Forward functor.  u_save receives stats->nsave_out blocks of [D,B]; capacity must be
  * nsave (or 1 when nsave==0; when nsave==-1 pass u_save_cap blocks, the LAST accepted

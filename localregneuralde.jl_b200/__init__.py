@@ -5,8 +5,8 @@ The directory name contains a dot, so it is loaded through ``__graft_entry__.loa
 ``libLRNDE.so`` (csrc/, C ABI in include/lrnde.h); there is no CPU fallback.
 """
 from ._lib import LIB_PATH, LrndeError, lib, SYMBOLS  # noqa: F401
-from .layers import (Chain, Context, Dense, DESolution, LatentGRUCell, NeuralDSDE, NeuralODE, Recurrence,  # noqa: F401
-                     ReparameterizeLayer, SDESolution, TDChain, latent_loss, mlp_backward, mlp_forward,
+from .layers import (Chain, Context, Conv, ConvChain, Dense, DESolution, LatentGRUCell, NeuralDSDE, NeuralODE, Recurrence,  # noqa: F401
+                     ReparameterizeLayer, SDESolution, TDChain, TDConvChain, latent_loss, mlp_backward, mlp_forward,
                      default_context, diffeqsol_to_array, diffeqsol_to_timeseries,
                      glorot_uniform, nparams)
 

@@ -20,6 +20,10 @@ class LayerDesc(C.Structure):
     _fields_ = [("in_dims", C.c_int32), ("out_dims", C.c_int32), ("act", C.c_int32)]
 
 
+class ConvLayerDesc(C.Structure):
+    _fields_ = [("in_ch", C.c_int32), ("out_ch", C.c_int32), ("batchnorm", C.c_int32), ("act", C.c_int32)]
+
+
 class Opts(C.Structure):
     _fields_ = [
         ("t0", C.c_float), ("t2", C.c_float), ("abstol", C.c_float), ("reltol", C.c_float),
@@ -80,7 +84,7 @@ SYMBOLS = [
     "lrnde_sde_forward", "lrnde_sde_backward", "lrnde_sde_tape_free", "lrnde_sde_states",
     "lrnde_sde_step_log", "lrnde_sde_aux_step", "lrnde_gru_nparams", "lrnde_gru_forward",
     "lrnde_gru_backward", "lrnde_gru_tape_free", "lrnde_mlp_forward", "lrnde_mlp_backward",
-    "lrnde_reparameterize", "lrnde_latent_loss",
+    "lrnde_reparameterize", "lrnde_latent_loss", "lrnde_conv_model_create", "lrnde_dynamics_vjp",
 ]
 
 
@@ -104,6 +108,8 @@ def lib():
     L.lrnde_ctx_set_dist.argtypes = [vp, i32, i32, C.POINTER(vp), i64]
     L.lrnde_model_create.argtypes = [vp, C.POINTER(LayerDesc), i32, i32, i32, C.POINTER(vp)]
     L.lrnde_model_destroy.argtypes = [vp]
+    L.lrnde_conv_model_create.argtypes = [vp, C.POINTER(ConvLayerDesc), i32, i32, i32, i32, C.POINTER(vp)]
+    L.lrnde_dynamics_vjp.argtypes = [vp, vp, C.POINTER(Opts), vp, vp, f32, vp, i64, vp, vp]
     L.lrnde_model_nparams.argtypes = [vp]
     L.lrnde_model_nparams.restype = i64
     L.lrnde_model_state_dims.argtypes = [vp]

@@ -20,6 +20,7 @@
 #include "lrnde_kernels.cuh"
 #include "lrnde_umma.cuh"
 #include "lrnde_smem_mlp.cuh"
+#include "lrnde_conv.cuh"
 
 // ------------------------------------------------------------------------------------------
 // errors
@@ -244,12 +245,238 @@ extern "C" int lrnde_model_create(lrnde_ctx* ctx, const lrnde_layer_desc* layers
   *out = m.release();
   LR_API_END
 }
+extern "C" int lrnde_conv_model_create(lrnde_ctx* ctx, const lrnde_conv_layer_desc* layers, int nlayers, int width,
+                                       int height, int time_dependent, lrnde_model** out) {
+  LR_API_BEGIN
+  if (!ctx || !layers || !out || nlayers < 1) lr_fail(LRNDE_EINVAL, "lrnde_conv_model_create: bad args");
+  if (width < 4 || width > 32 || (width & 3) || height < 1)
+    lr_fail(LRNDE_EINVAL, "lrnde_conv_model_create: width must be a multiple of 4 in 4..32 (got %d x %d)", width, height);
+  auto m = std::make_unique<lrnde_model>();
+  m->ctx = ctx;
+  m->td = time_dependent ? 1 : 0;
+  m->input_act = ACT_IDENTITY;
+  m->Wd = width; m->Ht = height;
+  int64_t off = 0;
+  for (int l = 0; l < nlayers; ++l) {
+    ConvLayerInfo L;
+    L.cin = layers[l].in_ch; L.cout = layers[l].out_ch; L.bn = layers[l].batchnorm ? 1 : 0;
+    L.act = lr_map_act(layers[l].act);
+    if (L.cin < 1 || L.cout < 1) lr_fail(LRNDE_EINVAL, "conv layer %d: bad channel counts", l);
+    if (l > 0 && m->conv.back().cout != L.cin)
+      lr_fail(LRNDE_EINVAL, "conv layer %d: in_ch %d != previous out_ch %d", l, L.cin, m->conv.back().cout);
+    L.w_off = off; off += (int64_t)9 * (L.cin + m->td) * L.cout;
+    L.g_off = off; if (L.bn) off += 2 * (int64_t)L.cout;
+    m->conv.push_back(L);
+  }
+  if (m->conv.back().bn || m->conv.back().act != ACT_IDENTITY)
+    lr_fail(LRNDE_EINVAL, "the last layer of the conv dynamics must be a plain Conv (no BatchNorm / activation)");
+  if (m->conv.front().cin != m->conv.back().cout)
+    lr_fail(LRNDE_EINVAL, "dynamics must map the state onto itself (got %d -> %d channels)", m->conv.front().cin,
+            m->conv.back().cout);
+  m->nparams = off;
+  m->D = width * height * m->conv.front().cin;
+  *out = m.release();
+  LR_API_END
+}
 extern "C" int lrnde_model_destroy(lrnde_model* m) {
   delete m;
   return LRNDE_OK;
 }
 extern "C" int64_t lrnde_model_nparams(const lrnde_model* m) { return m ? m->nparams : -1; }
 extern "C" int64_t lrnde_model_state_dims(const lrnde_model* m) { return m ? m->D : -1; }
+
+// ------------------------------------------------------------------------------------------
+// Conv evaluator (lrnde_conv.cuh): the same forward / vjp contract as MlpEval below
+// ------------------------------------------------------------------------------------------
+struct ConvEval {
+  lrnde_ctx* ctx;
+  const lrnde_model* m;
+  const float* ps;
+  int64_t B;
+  bool with_vjp;
+  int L, maxC = 0, nblk_max = 0;
+  size_t HW;
+  std::vector<float*> z, ab, stat, pack, packT;
+  float2* spart = nullptr;
+  float* ybuf = nullptr; float* lbuf = nullptr; float* G[2] = {nullptr, nullptr};
+  float* part = nullptr; double2* bpart = nullptr; float* coef = nullptr; float* dgb = nullptr;
+  std::vector<int> wS, wImg, wCic, wChunks;
+  int bnS = 1, bnImg = 1;
+
+  static int tile_rows(int PT, int Wd, int Ht) { return std::min(PT / (Wd >> 2), Ht); }
+  static bool narrow(int cout) { return cout <= 16; }   // <8,8,4> instantiation (whole-image tiles)
+  int conv_nblk(int cout) const {
+    const int TR = tile_rows(narrow(cout) ? 256 : 64, m->Wd, m->Ht);
+    return (int)B * ((m->Ht + TR - 1) / TR);
+  }
+
+  ConvEval(lrnde_ctx* c, const lrnde_model* mm, const float* p, int64_t b, bool vjp)
+      : ctx(c), m(mm), ps(p), B(b), with_vjp(vjp) {
+    if (ctx->nranks > 1)
+      for (auto& Li : m->conv)
+        if (Li.bn) lr_fail(LRNDE_EINVAL, "conv dynamics with BatchNorm: batch statistics are not exchanged across ranks (single-GPU ctx only)");
+    L = (int)m->conv.size();
+    HW = (size_t)m->Wd * m->Ht;
+    z.assign(L, nullptr); ab.assign(L, nullptr); stat.assign(L, nullptr); pack.assign(L, nullptr); packT.assign(L, nullptr);
+    for (int l = 0; l < L; ++l) {
+      const ConvLayerInfo& Li = m->conv[l];
+      maxC = std::max(maxC, std::max(Li.cin, Li.cout));
+      nblk_max = std::max(nblk_max, conv_nblk(Li.cout) * Li.cout);
+      const size_t nw = (size_t)9 * (Li.cin + m->td) * Li.cout;
+      pack[l] = (float*)ctx->alloc(4 * nw);
+      if (l < L - 1) z[l] = (float*)ctx->alloc(4 * HW * Li.cout * B);
+      if (Li.bn) { ab[l] = (float*)ctx->alloc(8 * Li.cout); stat[l] = (float*)ctx->alloc(8 * Li.cout); }
+      if (vjp) packT[l] = (float*)ctx->alloc(4 * (size_t)9 * Li.cin * Li.cout);
+    }
+    spart = (float2*)ctx->alloc(sizeof(float2) * (size_t)nblk_max);
+    if (vjp) {
+      int n_sm = 148;
+      ybuf = (float*)ctx->alloc(4 * (size_t)m->D * B);
+      lbuf = (float*)ctx->alloc(4 * (size_t)m->D * B);
+      G[0] = (float*)ctx->alloc(4 * HW * maxC * B);
+      G[1] = (float*)ctx->alloc(4 * HW * maxC * B);
+      size_t maxpart = 0;
+      for (int l = 0; l < L; ++l) {
+        const ConvLayerInfo& Li = m->conv[l];
+        const int cintot = Li.cin + m->td;
+        const int chunks = (cintot + 15) / 16, cic = (cintot + chunks - 1) / chunks;
+        const int ncob = (Li.cout + 63) / 64;
+        int S = std::max(1, std::min((int)B, (4 * n_sm) / (chunks * ncob)));
+        const int img = (int)((B + S - 1) / S);
+        S = (int)((B + img - 1) / img);
+        wS.push_back(S); wImg.push_back(img); wCic.push_back(cic); wChunks.push_back(chunks);
+        maxpart = std::max(maxpart, (size_t)S * 9 * cintot * Li.cout);
+      }
+      part = (float*)ctx->alloc(4 * maxpart);
+      bnS = std::max(1, std::min((int)B, 16));
+      bnImg = (int)((B + bnS - 1) / bnS);
+      bnS = (int)((B + bnImg - 1) / bnImg);
+      bpart = (double2*)ctx->alloc(sizeof(double2) * (size_t)maxC * bnS);
+      coef = (float*)ctx->alloc(8 * maxC);
+      dgb = (float*)ctx->alloc(8 * maxC);
+    }
+  }
+  ~ConvEval() {
+    for (auto p : z) ctx->release(p);
+    for (auto p : ab) ctx->release(p);
+    for (auto p : stat) ctx->release(p);
+    for (auto p : pack) ctx->release(p);
+    for (auto p : packT) ctx->release(p);
+    ctx->release(spart); ctx->release(ybuf); ctx->release(lbuf); ctx->release(G[0]); ctx->release(G[1]);
+    ctx->release(part); ctx->release(bpart); ctx->release(coef); ctx->release(dgb);
+  }
+
+  void prepare() {
+    for (int l = 0; l < L; ++l) {
+      const ConvLayerInfo& Li = m->conv[l];
+      const int cintot = Li.cin + m->td;
+      conv_pack_kernel<<<lr_ew_blocks((size_t)9 * cintot * Li.cout), 256, 0, ctx->stream>>>(ps + Li.w_off, cintot, Li.cout, 0, 0, pack[l]);
+      LR_COUNT(ctx);
+      if (with_vjp) {
+        conv_pack_kernel<<<lr_ew_blocks((size_t)9 * Li.cin * Li.cout), 256, 0, ctx->stream>>>(ps + Li.w_off, cintot, Li.cout, 1, Li.cin, packT[l]);
+        LR_COUNT(ctx);
+      }
+    }
+    LR_CHECK_LAUNCH();
+  }
+
+  void launch(ConvP& q) {
+    q.Wd = m->Wd; q.Ht = m->Ht; q.B = (int)B;
+    const bool nar = narrow(q.Cout);
+    dim3 g(conv_nblk(q.Cout), (q.Cout + (nar ? 8 : 64) - 1) / (nar ? 8 : 64));
+    if (nar) conv3x3_kernel<8, 8, 4><<<g, 256, 0, ctx->stream>>>(q);
+    else conv3x3_kernel<64, 16, 8><<<g, 256, 0, ctx->stream>>>(q);
+    LR_COUNT(ctx);
+  }
+
+  // layers 0..upto-1 of the dynamics on lincomb(in); `side` / `side_desc`: keep the combined input
+  void run_layers(const LinComb* in, const int* done, int upto, const LinComb* out, bool side_to_in_dst, float* side) {
+    for (int l = 0; l < upto; ++l) {
+      const ConvLayerInfo& Li = m->conv[l];
+      ConvP q;
+      memset(&q, 0, sizeof(q));
+      if (l == 0) {
+        q.xdesc = in; q.side_desc = side_to_in_dst ? in : nullptr; q.side = side; q.in_act = ACT_IDENTITY;
+      } else {
+        q.X = z[l - 1]; q.in_ab = m->conv[l - 1].bn ? ab[l - 1] : nullptr; q.in_act = m->conv[l - 1].act;
+      }
+      q.td = m->td; q.tdesc = in; q.Wp = pack[l]; q.Cin = Li.cin; q.Cout = Li.cout; q.out_scale = 1.0f; q.done = done;
+      if (l == L - 1) q.ydesc = out ? out : in; else q.Y = z[l];
+      if (Li.bn) q.stat_part = spart;
+      launch(q);
+      if (Li.bn) {
+        bn_finalize_kernel<<<Li.cout, 128, 0, ctx->stream>>>(spart, conv_nblk(Li.cout), Li.cout, (double)HW * (double)B,
+                                                           ps + Li.g_off, 1e-5f, ab[l], stat[l], done);
+        LR_COUNT(ctx);
+      }
+    }
+  }
+
+  void forward(const LinComb* in, const int* done, const LinComb* out, bool side_to_in_dst) {
+    run_layers(in, done, L, out, side_to_in_dst, nullptr);
+    LR_CHECK_LAUNCH();
+  }
+
+  void vjp(const LinComb* y, const LinComb* lamd, float* out_a, const LinComb* out_desc, float a_scale,
+           float* dps_ptr, const LinComb* dps_desc, size_t dps_off, float p_scale, float p_beta, const int* done) {
+    cudaStream_t st = ctx->stream;
+    const size_t DB = (size_t)m->D * B;
+    if (L > 1) run_layers(y, done, L - 1, nullptr, false, ybuf);     // recompute; y(t) kept for dW_1
+    else { lincomb_kernel<<<lr_ew_blocks(DB), 256, 0, st>>>(y, ybuf, DB, done); LR_COUNT(ctx); }
+    lincomb_kernel<<<lr_ew_blocks(DB), 256, 0, st>>>(lamd, lbuf, DB, done);
+    LR_COUNT(ctx);
+    const float* delta = lbuf;
+    int cur = 0;
+    for (int l = L - 1; l >= 0; --l) {
+      const ConvLayerInfo& Li = m->conv[l];
+      const int cintot = Li.cin + m->td;
+      const size_t nw = (size_t)9 * cintot * Li.cout;
+      ConvWgP w;
+      memset(&w, 0, sizeof(w));
+      if (l == 0) { w.X = ybuf; w.in_act = ACT_IDENTITY; }
+      else { w.X = z[l - 1]; w.in_ab = m->conv[l - 1].bn ? ab[l - 1] : nullptr; w.in_act = m->conv[l - 1].act; }
+      w.td = m->td; w.tdesc = y; w.Dl = delta; w.Wd = m->Wd; w.Ht = m->Ht; w.Cin = Li.cin; w.Cout = Li.cout; w.B = (int)B;
+      w.cic = wCic[l]; w.img_per_split = wImg[l]; w.part = part; w.block = nw; w.done = done;
+      conv3x3_wgrad_kernel<<<dim3(wChunks[l], wS[l], (Li.cout + 63) / 64), 256, 0, st>>>(w);
+      LR_COUNT(ctx);
+      wgrad_reduce_kernel<<<lr_ew_blocks(nw), 256, 0, st>>>(part, wS[l], nw, dps_ptr ? dps_ptr + Li.w_off : nullptr, dps_desc,
+                                                           dps_off + (size_t)Li.w_off, p_scale, p_beta, done);
+      LR_COUNT(ctx);
+      // data gradient: transposed convolution over the first cin channels (the time channel has no cotangent)
+      ConvP q;
+      memset(&q, 0, sizeof(q));
+      q.X = delta; q.in_act = ACT_IDENTITY; q.td = 0; q.Wp = packT[l]; q.Cin = Li.cout; q.Cout = Li.cin; q.done = done;
+      if (l == 0) {
+        q.out_scale = a_scale;
+        if (out_a) q.Y = out_a; else q.ydesc = out_desc;
+        launch(q);
+      } else {
+        q.out_scale = 1.0f; q.Y = G[cur];
+        launch(q);
+        const ConvLayerInfo& Lp = m->conv[l - 1];
+        const size_t n = HW * Lp.cout * B;
+        if (Lp.bn) {
+          bn_bwd_stats_kernel<<<dim3(Lp.cout, bnS), 256, 0, st>>>(G[cur], z[l - 1], ab[l - 1], stat[l - 1], Lp.act, Lp.cout, HW,
+                                                                (int)B, bnImg, bpart, done);
+          LR_COUNT(ctx);
+          bn_bwd_finalize_kernel<<<(Lp.cout + 63) / 64, 64, 0, st>>>(bpart, bnS, Lp.cout, (double)HW * (double)B, coef, dgb, done);
+          LR_COUNT(ctx);
+          wgrad_reduce_kernel<<<1, 256, 0, st>>>(dgb, 1, (size_t)2 * Lp.cout, dps_ptr ? dps_ptr + Lp.g_off : nullptr, dps_desc,
+                                               dps_off + (size_t)Lp.g_off, p_scale, p_beta, done);
+          LR_COUNT(ctx);
+          bn_bwd_apply_kernel<<<lr_ew_blocks(n), 256, 0, st>>>(G[cur], z[l - 1], ab[l - 1], stat[l - 1], coef, Lp.act, Lp.cout, HW, n, done);
+          LR_COUNT(ctx);
+        } else if (Lp.act != ACT_IDENTITY) {
+          bn_bwd_apply_kernel<<<lr_ew_blocks(n), 256, 0, st>>>(G[cur], z[l - 1], nullptr, nullptr, nullptr, Lp.act, Lp.cout, HW, n, done);
+          LR_COUNT(ctx);
+        }
+        delta = G[cur];
+        cur ^= 1;
+      }
+    }
+    LR_CHECK_LAUNCH();
+  }
+};
 
 // ------------------------------------------------------------------------------------------
 // MLP evaluator: f(u, ps, t) and its VJP as sequences of kernels reading device descriptors
@@ -280,11 +507,16 @@ struct MlpEval {
   float* ybuf = nullptr;
   float* delta[2] = {nullptr, nullptr};
   float* part = nullptr;
+  std::unique_ptr<ConvEval> conv;  // conv dynamics: every call below is forwarded
   std::vector<int> wS, wChunk;    // SIMT weight-gradient split
   std::vector<int> uS, uChunk;    // tcgen05 weight-gradient split (0 = layer not eligible)
 
   MlpEval(lrnde_ctx* c, const lrnde_model* mm, const float* p, int64_t b, int precision, bool vjp)
       : ctx(c), m(mm), ps(p), B(b), prec(precision), with_vjp(vjp) {
+    if (!m->conv.empty()) {
+      conv = std::make_unique<ConvEval>(c, mm, p, b, vjp);
+      return;
+    }
     const int L = (int)m->layers.size();
     use_umma = (precision != LRNDE_PREC_FP32_SIMT);
     setup_small(precision);
@@ -414,6 +646,7 @@ struct MlpEval {
   }
 
   void prepare() {
+    if (conv) { conv->prepare(); return; }
     if (use_small) return;
     for (size_t l = 0; l < m->layers.size(); ++l) {
       const LayerInfo& Li = m->layers[l];
@@ -540,6 +773,7 @@ struct MlpEval {
   // itself is also written to in->dst (u_{n+1} of the step, fused into stage 7's prologue)
   void forward(const LinComb* in, const int* done, const LinComb* out = nullptr,
                bool side_to_in_dst = false) {
+    if (conv) { conv->forward(in, done, out, side_to_in_dst); return; }
     if (use_small) {
       SmallP q = small_params(in, done);
       q.out = out; q.side_to_in_dst = side_to_in_dst ? 1 : 0;
@@ -587,6 +821,7 @@ struct MlpEval {
   void vjp(const LinComb* y, const LinComb* lamd, float* out_a, const LinComb* out_desc,
            float a_scale, float* dps_ptr, const LinComb* dps_desc, size_t dps_off, float p_scale,
            float p_beta, const int* done) {
+    if (conv) { conv->vjp(y, lamd, out_a, out_desc, a_scale, dps_ptr, dps_desc, dps_off, p_scale, p_beta, done); return; }
     if (use_small) {
       SmallP q = small_params(y, done);
       q.lam = lamd; q.out_a = out_a; q.out_desc = out_desc; q.a_scale = a_scale; q.gpart = s_gpart;
@@ -1102,6 +1337,42 @@ extern "C" int lrnde_dynamics_eval(lrnde_ctx* ctx, const lrnde_model* m, const l
   ev.prepare();
   ev.forward((const LinComb*)ddesc.p, nullptr);
   if (host) LR_CUDA(cudaMemcpyAsync(du, outd, 4 * DB, cudaMemcpyDeviceToHost, st));
+  LR_CUDA(cudaStreamSynchronize(st));
+  LR_API_END
+}
+
+extern "C" int lrnde_dynamics_vjp(lrnde_ctx* ctx, const lrnde_model* m, const lrnde_opts* o, const float* ps,
+                                  const float* u, float t, const float* lam, int64_t B, float* a, float* dps) {
+  LR_API_BEGIN
+  if (!ctx || !m || !ps || !u || !lam || !a || !dps || B < 1) lr_fail(LRNDE_EINVAL, "lrnde_dynamics_vjp: bad args");
+  LR_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const int host = o ? o->host_buffers : 0;
+  const size_t DB = (size_t)m->D * B;
+  DevBuf dp(ctx, host ? m->nparams : 1), dun(ctx, host ? DB : 1), dl(ctx, host ? DB : 1), da(ctx, host ? DB : 1),
+      dg(ctx, host ? m->nparams : 1);
+  DevBuf ddesc(ctx, 2 * (sizeof(LinComb) / 4 + 1));
+  const float* psd = ps; const float* ud = u; const float* ld = lam;
+  float* ad = a; float* gd = dps;
+  if (host) {
+    LR_CUDA(cudaMemcpyAsync(dp.p, ps, 4 * m->nparams, cudaMemcpyHostToDevice, st));
+    LR_CUDA(cudaMemcpyAsync(dun.p, u, 4 * DB, cudaMemcpyHostToDevice, st));
+    LR_CUDA(cudaMemcpyAsync(dl.p, lam, 4 * DB, cudaMemcpyHostToDevice, st));
+    psd = dp.p; ud = dun.p; ld = dl.p; ad = da.p; gd = dg.p;
+  }
+  LinComb d[2];
+  memset(d, 0, sizeof(d));
+  d[0].base = ud; d[0].t = t;
+  d[1].base = ld; d[1].t = t;
+  LinComb* dd = (LinComb*)ddesc.p;
+  LR_CUDA(cudaMemcpyAsync(dd, d, sizeof(d), cudaMemcpyHostToDevice, st));
+  MlpEval ev(ctx, m, psd, B, o ? o->precision : 0, true);
+  ev.prepare();
+  ev.vjp(dd, dd + 1, ad, nullptr, 1.0f, gd, nullptr, 0, 1.0f, 0.0f, nullptr);
+  if (host) {
+    LR_CUDA(cudaMemcpyAsync(a, ad, 4 * DB, cudaMemcpyDeviceToHost, st));
+    LR_CUDA(cudaMemcpyAsync(dps, gd, 4 * m->nparams, cudaMemcpyDeviceToHost, st));
+  }
   LR_CUDA(cudaStreamSynchronize(st));
   LR_API_END
 }

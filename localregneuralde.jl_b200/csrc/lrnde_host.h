@@ -60,9 +60,17 @@ struct LayerInfo {
   int64_t w_off, b_off;  // offsets into the flat parameter vector
 };
 
+// conv dynamics: Conv((3,3), cin(+1) => cout; pad=1, use_bias=false) [+ BatchNorm(cout, act)]
+struct ConvLayerInfo {
+  int cin, cout, bn, act;
+  int64_t w_off, g_off;  // weight [3,3,cin+td,cout]; BatchNorm scale[cout] then bias[cout] at g_off
+};
+
 struct lrnde_model {
   lrnde_ctx* ctx;
   std::vector<LayerInfo> layers;
+  std::vector<ConvLayerInfo> conv;  // non-empty: conv dynamics on a [Wd,Ht,C,B] state
+  int Wd = 0, Ht = 0;
   int td;
   int input_act;  // LRNDE_ACT_NONE (-1) when absent
   int64_t nparams;

@@ -54,15 +54,66 @@ class TDChain(Chain):
         self.time_dependent = True
 
 
-def nparams(model: Chain) -> int:
+@dataclass(frozen=True)
+class Conv:
+    """Lux ``Conv((3,3), in_ch => out_ch; pad=(1,1), use_bias=false)``, optionally followed by
+    ``BatchNorm(out_ch, activation)`` as ``Chain(Conv, BatchNorm)`` (experiments/src/construct.jl:213-218).
+    ``in_ch`` excludes the TDChain time channel."""
+    in_ch: int
+    out_ch: int
+    batchnorm: bool = False
+    activation: str = "identity"
+
+
+class ConvChain:
+    """The conv dynamics of the cifar10 config on a WHCN state ``(width, height, channels, B)``, handed to the
+    layer as the flat column-major ``(width*height*channels, B)`` array (a reshape, no copy).  Parameters in
+    ComponentArray order: ``weight[3,3,in(+1),out]`` then BatchNorm ``scale[out]``, ``bias[out]`` per layer."""
+
+    def __init__(self, *layers: Conv, width: int, height: int):
+        self.layers: List[Conv] = list(layers)
+        self.width, self.height = int(width), int(height)
+        self.time_dependent = False
+        self.input_activation = None
+
+    @property
+    def state_dims(self) -> int:
+        return self.width * self.height * self.layers[0].in_ch
+
+
+class TDConvChain(ConvChain):
+    """``TDChain(Chain(...))`` over conv layers: ``t .* ones`` is concatenated as one more input CHANNEL before
+    every outer layer (src/layers/common.jl:19-33)."""
+
+    def __init__(self, chain: ConvChain):
+        super().__init__(*chain.layers, width=chain.width, height=chain.height)
+        self.time_dependent = True
+
+
+def _state_dims(model) -> int:
+    return model.state_dims if isinstance(model, ConvChain) else model.layers[0].in_dims
+
+
+def nparams(model) -> int:
     td = 1 if model.time_dependent else 0
+    if isinstance(model, ConvChain):
+        return sum(9 * (L.in_ch + td) * L.out_ch + (2 * L.out_ch if L.batchnorm else 0) for L in model.layers)
     return sum(L.out_dims * (L.in_dims + td) + L.out_dims for L in model.layers)
 
 
-def glorot_uniform(model: Chain, rng: np.random.Generator) -> np.ndarray:
-    """Lux default init (Glorot-uniform weights, zero bias), flat ComponentArray order."""
+def glorot_uniform(model, rng: np.random.Generator) -> np.ndarray:
+    """Lux default init (Glorot-uniform weights, zero bias; BatchNorm scale 1, bias 0), flat ComponentArray order."""
     td = 1 if model.time_dependent else 0
     out = []
+    if isinstance(model, ConvChain):
+        for L in model.layers:
+            cin = L.in_ch + td
+            a = math.sqrt(6.0 / (9 * cin + 9 * L.out_ch))
+            out.append(rng.uniform(-a, a, size=9 * cin * L.out_ch).astype(np.float32))
+            if L.batchnorm:
+                out.append(np.ones(L.out_ch, np.float32))
+                out.append(np.zeros(L.out_ch, np.float32))
+        return np.concatenate(out)
     for L in model.layers:
         fan_in, fan_out = L.in_dims + td, L.out_dims
         a = math.sqrt(6.0 / (fan_in + fan_out))
@@ -106,6 +157,14 @@ class Context:
         key = id(model)
         if key in self._models and self._models[key][0] is not model:
             lib().lrnde_model_destroy(self._models.pop(key)[1])    # id() reuse of a dead object
+        if key not in self._models and isinstance(model, ConvChain):
+            arr = (_lib.ConvLayerDesc * len(model.layers))()
+            for i, L in enumerate(model.layers):
+                arr[i] = _lib.ConvLayerDesc(L.in_ch, L.out_ch, 1 if L.batchnorm else 0, _lib.ACT[L.activation])
+            h = C.c_void_p()
+            check(lib().lrnde_conv_model_create(self._h, arr, len(model.layers), model.width, model.height,
+                                                1 if model.time_dependent else 0, C.byref(h)))
+            self._models[key] = (model, h)
         if key not in self._models:
             arr = (LayerDesc * len(model.layers))()
             for i, L in enumerate(model.layers):
@@ -333,8 +392,8 @@ class NeuralODE:
         o, _keep = self._opts(mode, t1, u01, keep_tape, host)
         xb = _as_input(x, not host, None)
         B, D = xb.shape
-        if D != self.model.layers[0].in_dims:
-            raise ValueError(f"x has {D} features, the dynamics expect {self.model.layers[0].in_dims}")
+        if D != _state_dims(self.model):
+            raise ValueError(f"x has {D} features, the dynamics expect {_state_dims(self.model)}")
         psb = ps.detach().to(torch.float32).contiguous() if _is_torch(ps) else \
             np.ascontiguousarray(np.asarray(ps, dtype=np.float32))
         if (not host) != _is_torch(psb):
@@ -420,6 +479,21 @@ class NeuralODE:
         check(lib().lrnde_dynamics_eval(ctx._h, ctx.model_handle(self.model), C.byref(o), _ptr(psb),
                                         _ptr(ub), float(t), B, _ptr(out)))
         return out.T
+
+    def dynamics_vjp(self, u, ps, t: float, lam):
+        """``(J_u^T lam, J_p^T lam)`` of one ``dudt`` evaluation: the ZygoteVJP pullback the adjoint calls
+        (neural_ode.jl:11).  Host arrays only (parity hook)."""
+        ub = _as_input(u, False, None)
+        lb = _as_input(lam, False, None)
+        B, D = ub.shape
+        psb = np.ascontiguousarray(np.asarray(ps, np.float32))
+        a = np.empty((B, D), np.float32)
+        dps = np.empty(psb.size, np.float32)
+        o, _ = self._opts("none", 0.0, 0.0, False, True)
+        ctx = self.ctx
+        check(lib().lrnde_dynamics_vjp(ctx._h, ctx.model_handle(self.model), C.byref(o), _ptr(psb), _ptr(ub),
+                                       float(t), _ptr(lb), B, _ptr(a), _ptr(dps)))
+        return a.T, dps
 
 
 # ------------------------------------------------------------------ neural SDE layer

@@ -12,3 +12,4 @@ finiteness / non-zeroness).  See oracle/lrnde_oracle.py's header.
 from .lrnde_oracle import *  # noqa: F401,F403
 from .lrnde_sde_oracle import *  # noqa: F401,F403,E402
 from .lrnde_latent_oracle import *  # noqa: F401,F403,E402
+from .lrnde_conv_oracle import *  # noqa: F401,F403,E402

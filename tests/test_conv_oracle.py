@@ -1,0 +1,82 @@
+"""Self-validation of the conv-dynamics oracle (oracle/lrnde_conv_oracle.py).  CPU only."""
+import numpy as np
+import scipy.signal
+
+import oracle as orc
+from oracle.lrnde_conv_oracle import ConvLayer, ConvNet, cifar10_node_core, glorot_uniform_conv_params
+
+
+def _small(dtype=np.float64, td=True, seed=0, B=3):
+    rng = np.random.default_rng(seed)
+    net = ConvNet([ConvLayer(2, 5, True, "gelu"), ConvLayer(5, 4, True, "gelu"), ConvLayer(4, 2)], 8, 4,
+                  time_dependent=td)
+    ps = glorot_uniform_conv_params(net, rng, dtype, jitter=0.2)
+    u = rng.standard_normal((net.state_dims, B)).astype(dtype)
+    return net, ps, u, rng
+
+
+def test_parameter_count_of_the_cifar10_core():
+    assert cifar10_node_core().nparams == 47560
+    assert cifar10_node_core().state_dims == 32 * 32 * 8
+
+
+def test_conv_is_a_true_convolution_with_zero_padding():
+    """NNlib ``conv`` flips the kernel: the single-channel case equals scipy's convolve2d 'same'."""
+    rng = np.random.default_rng(1)
+    net = ConvNet([ConvLayer(1, 1)], 8, 4, time_dependent=False)
+    w = rng.standard_normal(9)
+    x = rng.standard_normal((4, 8))                        # [h, w]
+    y = net.f(x.reshape(-1, 1), w, 0.0).reshape(4, 8)
+    k = w.reshape((3, 3), order="F").T                     # w[kx, ky] -> k[ky, kx]
+    np.testing.assert_allclose(y, scipy.signal.convolve2d(x, k, mode="same"), rtol=1e-12, atol=1e-12)
+
+
+def test_time_channel_is_not_a_bias_at_the_border():
+    """t * ones is concatenated BEFORE the zero padding (common.jl:19-33): border pixels see fewer time taps."""
+    net = ConvNet([ConvLayer(1, 1)], 4, 4, time_dependent=True)
+    ps = np.zeros(net.nparams)
+    ps[9:] = 1.0                                           # only the time channel's taps
+    y = net.f(np.zeros((16, 1)), ps, 2.0).reshape(4, 4)
+    assert y[1, 1] == 18.0 and y[0, 0] == 8.0 and y[0, 1] == 12.0
+
+
+def test_vjp_matches_finite_differences():
+    net, ps, u, rng = _small()
+    lam = rng.standard_normal(u.shape)
+    a, dps = net.vjp(u, ps, 0.3, lam)
+    eps = 1e-6
+    for i in rng.choice(ps.size, 24, replace=False):
+        p1, p2 = ps.copy(), ps.copy()
+        p1[i] += eps; p2[i] -= eps
+        fd = (np.sum(lam * net.f(u, p1, 0.3)) - np.sum(lam * net.f(u, p2, 0.3))) / (2 * eps)
+        assert abs(dps[i] - fd) < 1e-6 * max(1.0, abs(fd)), (i, dps[i], fd)
+    for i in rng.choice(u.size, 12, replace=False):
+        u1, u2 = u.copy(), u.copy()
+        u1.flat[i] += eps; u2.flat[i] -= eps
+        fd = (np.sum(lam * net.f(u1, ps, 0.3)) - np.sum(lam * net.f(u2, ps, 0.3))) / (2 * eps)
+        assert abs(a.flat[i] - fd) < 1e-6 * max(1.0, abs(fd))
+
+
+def test_batchnorm_couples_the_batch():
+    """Training-mode statistics are taken over the whole batch: changing one sample moves the others' outputs."""
+    net, ps, u, _ = _small()
+    y0 = net.f(u, ps, 0.1)
+    u2 = u.copy(); u2[:, 0] *= 3.0
+    y1 = net.f(u2, ps, 0.1)
+    assert np.abs(y1[:, 1] - y0[:, 1]).max() > 1e-6
+
+
+def test_neural_ode_layer_runs_on_the_conv_dynamics():
+    """The reference's NeuralODE property test (test/runtests.jl:118-131) on the conv core: finite outputs,
+    reg_val > 0, a gradient for every parameter block."""
+    net, ps, u, rng = _small(np.float32, B=2)
+    node = orc.NeuralODE(net, regularize="unbiased", abstol=1e-3, reltol=1e-3, maxiters=1000)
+    st = node.initialstates(np.random.default_rng(0))
+    out, st2, aux = node.forward(u, ps, st)
+    assert all(np.isfinite(x).all() for x in out.u) and st2["reg_val"] > 0 and st2["nfe"] > 0
+    d_us = [np.zeros_like(x) for x in out.u]
+    d_us[-1] = rng.standard_normal(out.u[-1].shape).astype(np.float32)
+    d_x, d_ps = node.backward(aux, d_us, np.float32(1.0), ps)
+    assert np.isfinite(d_ps).all() and np.isfinite(d_x).all()
+    for (wo, go), L in zip(net.offsets, net.layers):
+        assert np.abs(d_ps[wo:go]).max() > 0

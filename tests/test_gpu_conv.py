@@ -1,0 +1,155 @@
+"""GPU parity of the conv dynamics (the cifar10 config's node core) against the CPU oracle,
+through the C ABI: f(u, p, t), its pullback, and the whole layer (solve + local regulariser + adjoint).
+
+Tolerances: states / regulariser 1e-4 relative, gradients 1e-3 relative (BASELINE.json); f itself 2e-5."""
+import numpy as np
+import pytest
+
+import __graft_entry__ as entry
+import oracle as orc
+from oracle.lrnde_conv_oracle import ConvLayer, ConvNet, cifar10_node_core, glorot_uniform_conv_params
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    entry.build()
+    return entry.load_package()
+
+
+def rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-30))
+
+
+def _pair(pkg, layers, W, H, td):
+    onet = ConvNet([ConvLayer(*l) for l in layers], W, H, time_dependent=td)
+    chain = pkg.ConvChain(*[pkg.Conv(*l) for l in layers], width=W, height=H)
+    return onet, (pkg.TDConvChain(chain) if td else chain)
+
+
+SHAPES = [
+    # layers (in, out, batchnorm, act), W, H, td, B
+    ([(1, 1, False, "identity")], 4, 4, False, 1),                                          # bare convolution
+    ([(2, 5, True, "gelu"), (5, 4, True, "gelu"), (4, 2, False, "identity")], 8, 4, True, 3),
+    ([(3, 24, True, "gelu"), (24, 20, False, "tanh"), (20, 3, False, "identity")], 12, 7, True, 5),   # 64-wide tiles, masks
+    ([(8, 64, True, "gelu"), (64, 64, True, "gelu"), (64, 8, False, "identity")], 32, 32, True, 2),  # the cifar10 core
+    ([(2, 17, True, "gelu"), (17, 2, False, "identity")], 16, 40, False, 2),                 # several row tiles
+]
+
+
+@pytest.mark.parametrize("layers,W,H,td,B", SHAPES)
+def test_conv_dynamics_matches_oracle(pkg, layers, W, H, td, B):
+    rng = np.random.default_rng(0)
+    onet, chain = _pair(pkg, layers, W, H, td)
+    ps = glorot_uniform_conv_params(onet, rng, jitter=0.2)
+    assert pkg.nparams(chain) == onet.nparams
+    u = rng.standard_normal((onet.state_dims, B)).astype(np.float32)
+    layer = pkg.NeuralODE(chain)
+    got = layer.dynamics(u, ps, 0.37)
+    want = onet.f(u.astype(np.float64), ps.astype(np.float64), 0.37)
+    assert got.shape == want.shape
+    assert rel(got, want) < 2e-5, rel(got, want)
+
+
+@pytest.mark.parametrize("layers,W,H,td,B", SHAPES)
+def test_conv_vjp_matches_oracle(pkg, layers, W, H, td, B):
+    rng = np.random.default_rng(1)
+    onet, chain = _pair(pkg, layers, W, H, td)
+    ps = glorot_uniform_conv_params(onet, rng, jitter=0.2)
+    u = rng.standard_normal((onet.state_dims, B)).astype(np.float32)
+    lam = rng.standard_normal((onet.state_dims, B)).astype(np.float32)
+    a, dps = pkg.NeuralODE(chain).dynamics_vjp(u, ps, 0.61, lam)
+    wa, wdps = onet.vjp(u.astype(np.float64), ps.astype(np.float64), 0.61, lam.astype(np.float64))
+    assert rel(a, wa) < 1e-4, rel(a, wa)
+    for (wo, go), L in zip(onet.offsets, onet.layers):          # per parameter block: weights, then scale / bias
+        n = 9 * (L.in_ch + (1 if td else 0)) * L.out_ch
+        assert rel(dps[wo:wo + n], wdps[wo:wo + n]) < 1e-4
+        if L.batchnorm:
+            assert rel(dps[go:go + 2 * L.out_ch], wdps[go:go + 2 * L.out_ch]) < 1e-4
+
+
+def test_conv_model_validation(pkg):
+    with pytest.raises(pkg.LrndeError):                          # width not a multiple of 4
+        pkg.NeuralODE(pkg.ConvChain(pkg.Conv(1, 1), width=6, height=6)).dynamics(np.zeros((36, 1), np.float32),
+                                                                              np.zeros(9, np.float32), 0.0)
+    with pytest.raises(pkg.LrndeError):                          # last layer must be a plain Conv
+        pkg.NeuralODE(pkg.ConvChain(pkg.Conv(1, 1, True, "gelu"), width=4, height=4)).dynamics(
+            np.zeros((16, 1), np.float32), np.zeros(11, np.float32), 0.0)
+
+
+@pytest.mark.parametrize("mode,reg_type", [("unbiased", "error_estimate"), ("unbiased", "stiffness_estimate"),
+                                           ("none", "error_estimate")])
+def test_conv_neural_ode_layer_matches_oracle(pkg, mode, reg_type):
+    """The layer functor on conv dynamics: same accepted / rejected step sequence and NFE, states and
+    regulariser 1e-4, gradients 1e-3 (cotangents on u(t2) and on reg_val)."""
+    layers, W, H, B = [(2, 6, True, "gelu"), (6, 6, True, "gelu"), (6, 2, False, "identity")], 8, 8, 4
+    rng = np.random.default_rng(2)
+    onet, chain = _pair(pkg, layers, W, H, True)
+    ps = glorot_uniform_conv_params(onet, rng, jitter=0.1)
+    x = rng.standard_normal((onet.state_dims, B)).astype(np.float32)
+    kw = dict(regularize=mode, regularize_type=reg_type, abstol=1e-3, reltol=1e-3, maxiters=1000)
+    onode = orc.NeuralODE(onet, **kw)
+    gnode = pkg.NeuralODE(chain, **kw)
+    ost = onode.initialstates(np.random.default_rng(5))
+    gst = gnode.initialstates(np.random.default_rng(5))
+    osol, ost2, aux = onode.forward(x, ps, ost)
+    # Float64 twin of the oracle: where the embedded error estimate of the regulariser's step (taken at the
+    # conservative initial dt, perform_step.jl:4) is Float32 rounding noise, two Float32 implementations agree
+    # only up to that noise; the twin measures it
+    o64 = orc.NeuralODE(onet, dtype=np.float64, **kw)
+    osol64, ost64, aux64 = o64.forward(x.astype(np.float64), ps.astype(np.float64),
+                                       o64.initialstates(np.random.default_rng(5)))
+    gsol, gst2 = gnode(x, ps, gst)
+    assert gst2["nfe"] == ost2["nfe"]
+    t, dt, eest, acc = gsol.step_log(0)
+    assert int(acc.sum()) == aux["sol"].naccept and int((~acc).sum()) == aux["sol"].nreject
+    assert len(gsol.u) == len(osol.u)
+    for g, w in zip(gsol.u, osol.u):
+        assert rel(g, w) < 1e-4, rel(g, w)
+    if mode != "none":
+        r32, r64 = float(ost2["reg_val"]), float(ost64["reg_val"])
+        assert abs(float(gst2["reg_val"]) - r32) <= 1e-4 * abs(r32) + 10 * abs(r32 - r64) + 1e-12
+    cot = rng.standard_normal(gsol.u[-1].shape).astype(np.float32)
+    d_us = [None] * len(gsol.u)
+    d_us[-1] = cot
+    od = [np.zeros_like(u) for u in osol.u]
+    od[-1] = cot
+    # adjoint alone (bar: 1e-3), then with the regulariser's cotangent (noise-aware bar from the twin)
+    gdx, gdps = gnode.backward(gsol, d_us, 0.0)
+    odx, odps = onode.backward(aux, od, np.float32(0.0), ps)
+    assert rel(gdx, odx) < 1e-3, rel(gdx, odx)
+    assert rel(gdps, odps) < 1e-3, rel(gdps, odps)
+    if mode != "none":
+        gsol2, _ = gnode(x, ps, gst)
+        gdx2, gdps2 = gnode.backward(gsol2, d_us, 2.5)
+        odx2, odps2 = onode.backward(aux, od, np.float32(2.5), ps)
+        od64 = [np.zeros_like(u) for u in osol64.u]
+        od64[-1] = cot.astype(np.float64)
+        _, odps64 = o64.backward(aux64, od64, np.float64(2.5), ps.astype(np.float64))
+        assert rel(gdx2, odx2) < 1e-3                              # d reg / d x == 0 (test/runtests.jl:129)
+        assert rel(gdps2, odps2) < 1e-3 + 3 * rel(odps2, odps64), (rel(gdps2, odps2), rel(odps2, odps64))
+
+
+def test_cifar10_core_training_iteration_properties(pkg):
+    """Full-size node core (32x32x8 state, 47 560 parameters, batch 16): the reference's NeuralODE property
+    test (test/runtests.jl:118-131) -- finite outputs, reg_val > 0, finite non-zero parameter gradient --
+    plus linearity of the pullback in its cotangent (size-independent)."""
+    rng = np.random.default_rng(3)
+    onet = cifar10_node_core()
+    chain = pkg.TDConvChain(pkg.ConvChain(pkg.Conv(8, 64, True, "gelu"), pkg.Conv(64, 64, True, "gelu"),
+                                          pkg.Conv(64, 8), width=32, height=32))
+    ps = glorot_uniform_conv_params(onet, rng)
+    x = rng.standard_normal((onet.state_dims, 16)).astype(np.float32)
+    node = pkg.NeuralODE(chain, regularize="unbiased", abstol=1e-4, reltol=1e-4, maxiters=10_000)
+    st = node.initialstates(np.random.default_rng(0))
+    sol, st2 = node(x, ps, st)
+    assert sol.retcode == "Success" and st2["nfe"] > 0 and float(st2["reg_val"]) > 0
+    assert all(np.isfinite(u).all() for u in sol.u)
+    cot = rng.standard_normal(sol.u[-1].shape).astype(np.float32)
+    dx1, dps1 = node.backward(sol, [None, cot], 0.0)
+    assert np.isfinite(dps1).all() and np.abs(dps1).max() > 0 and np.isfinite(dx1).all()
+    sol2, _ = node(x, ps, st)
+    dx2, dps2 = node.backward(sol2, [None, 2.0 * cot], 0.0)
+    assert rel(dps2, 2.0 * np.asarray(dps1)) < 1e-3
