@@ -657,6 +657,147 @@ def run_physionet(args):
                                        "sample": f"the whole workload, 1 iteration ({dt:.2f} s), numpy float32 oracle", "nfe": int(nfe_o)}}))
 
 
+# ---------------------------------------------------------------------------------- cifar10 node core (secondary)
+def measured_peaks():
+    pk_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peaks = json.load(open(pk_path)) if os.path.exists(pk_path) else {}
+    return {"hbm": peaks.get("hbm_gbs", 6650.0), "bf16_burst": peaks.get("bf16_tflops", 1590.0),
+            "source": "MEASURED_PEAKS.json" if peaks else "fallback of B200_PROFILING.md"}
+
+
+def cifar10_setup(B, use_oracle, W=32, loop_mode=0):
+    kw = dict(regularize="unbiased", abstol=1e-4, reltol=1e-4, save_start=False, maxiters=10000)
+    rng = np.random.default_rng(0)
+    if use_oracle:
+        import oracle as orc
+        from oracle.lrnde_conv_oracle import cifar10_node_core, glorot_uniform_conv_params
+        net = cifar10_node_core(W, W)
+        layer = orc.NeuralODE(net, **kw)
+        ps = glorot_uniform_conv_params(net, rng)
+        D = net.state_dims
+    else:
+        import __graft_entry__ as entry
+        entry.build()
+        pkg = entry.load_package()
+        chain = pkg.TDConvChain(pkg.ConvChain(pkg.Conv(8, 64, True, "gelu"), pkg.Conv(64, 64, True, "gelu"),
+                                              pkg.Conv(64, 8), width=W, height=W))
+        layer = pkg.NeuralODE(chain, return_last_only=True, loop_mode=loop_mode, **kw)
+        ps = layer.initialparameters(rng)
+        D = chain.state_dims
+    x = np.random.default_rng(1).standard_normal((D, B)).astype(np.float32)
+    return layer, ps, x
+
+
+def run_cifar10(args):
+    """BASELINE configs[3]: conv-dynamics neural ODE, state 32x32x8 (after the AugmenterLayer), batch 256, local
+    regularisation, tol 1e-4 (experiments/src/construct.jl:212-223): forward Tsit5 solve + regulariser step +
+    adjoint pullback of sum(u(t2))/B + w_reg * reg_val.  The augment / BatchNorm(8) / classifier layers either
+    side of the NeuralODE are not part of this workload.  Secondary workload (one JSON line, same contract)."""
+    B = args.cifar_batch
+    F_f = 2.0 * 9 * 1024 * (9 * 64 + 65 * 64 + 65 * 8)          # flop per f evaluation per sample
+    wl = ("cifar10 node core (BASELINE configs[3]): TDChain(Conv 9=>64 + BN gelu, Conv 65=>64 + BN gelu, Conv 65=>8), "
+          "3x3 pad 1, state 32x32x8, Tsit5 + :unbiased local reg, tol 1e-4; fwd + adjoint")
+    if args.impl == "reference":
+        Bs = args.cifar_ref_batch
+        layer, ps, x = cifar10_setup(Bs, True)
+        st = layer.initialstates(np.random.default_rng(7))
+        ts = []
+        for i in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            out, st2, aux = layer.forward(x, ps, st)
+            layer.backward(aux, [np.zeros_like(x), np.ones_like(x) / Bs], np.float32(W_REG), ps)
+            if i >= args.warmup:
+                ts.append(time.perf_counter() - t0)
+        ms = 1e3 * float(np.mean(ts))
+        val = Bs / (ms / 1e3)
+        print(json.dumps({"impl": "reference", "metric": "cifar10_train_samples_per_s", "value": val, "unit": "samples/s",
+                          "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "config": {"workload": wl, "batch": B},
+                          "cpu_baseline": {"value": val, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
+                                           "sample": f"batch {Bs} of the same workload per step"},
+                          "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+    import torch
+    layer, ps, x = cifar10_setup(B, False, loop_mode=args.loop_mode)
+    D = x.shape[0]
+    dev = torch.device("cuda", 0)
+    xt, pt = torch.from_numpy(x).to(dev), torch.from_numpy(ps).to(dev)
+    cot_t = torch.ones((D, B), device=dev) / B
+    x_pin = torch.from_numpy(x).pin_memory().numpy()
+    cot_h = torch.ones((D, B)).div_(B).pin_memory().numpy()
+    st = layer.initialstates(np.random.default_rng(7))
+    info = {}
+
+    def step(resident):
+        sol, st2 = layer(xt if resident else x_pin, pt if resident else ps, st)
+        layer.backward(sol, [cot_t if resident else cot_h], W_REG)
+        b = sol.bwd_stats
+        info.update(nfe=st2["nfe"], acc=sol.stats.naccept, rej=sol.stats.nreject, nf_bwd=b.nf_bwd,
+                    bacc=b.naccept_bwd, brej=b.nreject_bwd, launches=sol.stats.gpu_launches + b.gpu_launches,
+                    reg=float(st2["reg_val"]), retcode=sol.retcode)
+        sol.free()
+
+    def timed(n, resident):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(n):
+            step(resident)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+    clocks = ClockSampler(0)
+    clocks.start()
+    for _ in range(max(3, args.warmup)):
+        step(True)
+    step(False)
+    ms = timed(args.steps, True)
+    clk = clocks.stop()
+    ms_e = timed(max(1, min(args.steps, args.e2e_steps)), False)
+    # roofline probe: one f evaluation (3 convolutions + 2 BatchNorm reductions), CUDA events around 10 calls
+    for _ in range(3):
+        layer.dynamics(xt, pt, 0.5)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(10):
+        layer.dynamics(xt, pt, 0.5)
+    e1.record()
+    torch.cuda.synchronize()
+    us_f = 1e3 * e0.elapsed_time(e1) / 10
+    peaks = measured_peaks()
+    tf32_peak = peaks["bf16_burst"] / 2.0
+    ach = F_f * B / (us_f * 1e-6) / 1e12
+    cpu = None
+    if not args.no_cpu_baseline:
+        Bs = args.cifar_ref_batch
+        olayer, ops, ox = cifar10_setup(Bs, True)
+        ost = olayer.initialstates(np.random.default_rng(7))
+        t0 = time.perf_counter()
+        out, st2, aux = olayer.forward(ox, ops, ost)
+        olayer.backward(aux, [np.zeros_like(ox), np.ones_like(ox) / Bs], np.float32(W_REG), ops)
+        dt = time.perf_counter() - t0
+        cpu = {"value": Bs / dt, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
+               "sample": f"1 iteration at batch {Bs} ({dt:.1f} s), numpy float32 oracle", "nfe": int(st2["nfe"])}
+    print(json.dumps({"metric": "cifar10_train_samples_per_s", "value": B / (ms / 1e3), "unit": "samples/s", "n_gpus": 1,
+                      "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+                      "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                      "config": {"workload": wl, "batch": B,
+                                 "l2": "hidden activations 2 x 67 MB per f evaluation at batch 256: larger than L2"},
+                      "nfe_per_step": info["nfe"], "nfe_per_s": info["nfe"] / (ms / 1e3), "nf_bwd_per_step": info["nf_bwd"],
+                      "steps_fwd": [info["acc"], info["rej"]], "steps_bwd": [info["bacc"], info["brej"]],
+                      "reg_val": info["reg"], "retcode": info["retcode"],
+                      "e2e": {"value": B / (ms_e / 1e3), "unit": "samples/s", "ms_per_step": ms_e,
+                              "h2d_bytes_per_step": 4 * (2 * D * B + ps.size), "d2h_bytes_per_step": 4 * (2 * D * B + ps.size)},
+                      "gpu_launches": int(info["launches"] * args.steps), "clocks": clk,
+                      "roofline": {"bound": "tensor", "kernel": "one f evaluation: conv3x3_kernel x 3 (FP32 SIMT direct convolution, "
+                                   "not yet on the tensor cores) + bn_finalize x 2", "achieved": ach, "peak": tf32_peak,
+                                   "unit": "TFLOP/s", "frac": ach / tf32_peak, "traffic": None, "us_per_feval": us_f,
+                                   "peak_source": peaks["source"] + " (bf16 burst / 2 = TF32 dense)"},
+                      "cpu_baseline": cpu}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -669,16 +810,20 @@ def main():
     ap.add_argument("--ref-batch", type=int, default=512, help="bounded sample for the CPU reference")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="mnist_ode", choices=["mnist_ode", "mnist_sde", "physionet"],
+    ap.add_argument("--workload", default="mnist_ode", choices=["mnist_ode", "mnist_sde", "physionet", "cifar10"],
                     help="mnist_ode (default, the headline metric) or a secondary config")
     ap.add_argument("--phys-batch", type=int, default=256)
     ap.add_argument("--phys-T", type=int, default=49)
     ap.add_argument("--sde-batch", type=int, default=128)
+    ap.add_argument("--cifar-batch", type=int, default=256)
+    ap.add_argument("--cifar-ref-batch", type=int, default=4, help="bounded sample for the CPU oracle")
     args = ap.parse_args()
     if args.workload == "mnist_sde":
         run_sde(args)
     elif args.workload == "physionet":
         run_physionet(args)
+    elif args.workload == "cifar10":
+        run_cifar10(args)
     elif args.impl == "reference":
         run_reference(args)
     else:

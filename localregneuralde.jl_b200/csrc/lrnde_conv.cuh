@@ -152,6 +152,7 @@ __global__ void __launch_bounds__(256) conv3x3_kernel(ConvP p) {
   }
 
   float* out = p.ydesc ? p.ydesc->dst : p.Y;
+  const bool out_vec = (((uintptr_t)out) & 15) == 0;
   if (active) {
 #pragma unroll
     for (int j = 0; j < TC; ++j) {
@@ -160,7 +161,9 @@ __global__ void __launch_bounds__(256) conv3x3_kernel(ConvP p) {
         const size_t idx = pcol + (size_t)Wd * ((row0 + prow) + (size_t)Ht * (co + (size_t)p.Cout * b));
         float4 v = make_float4(acc[0][j] * p.out_scale, acc[1][j] * p.out_scale, acc[2][j] * p.out_scale,
                                acc[3][j] * p.out_scale);
-        *reinterpret_cast<float4*>(out + idx) = v;
+        // the lambda block of the adjoint state sits at a multiple of (D*B + nparams) floats: not always 16-byte aligned
+        if (out_vec) *reinterpret_cast<float4*>(out + idx) = v;
+        else { out[idx] = v.x; out[idx + 1] = v.y; out[idx + 2] = v.z; out[idx + 3] = v.w; }
       }
     }
   }
