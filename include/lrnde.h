@@ -105,7 +105,13 @@ typedef struct {
   int32_t last_only;     /* 1: return only sol.u[end] (the diffeqsol_to_array layer that follows the functor in
                             every classifier of experiments/src/construct.jl, src/utils.jl:37, fused): u_save and
                             d_u_save then hold ONE [D,B] block; t1 / the regulariser are unaffected */
-  int32_t reserved[6];
+  float* model_state;    /* conv dynamics with BatchNorm: st.model of the layer (neural_ode.jl:44-47, :83), per
+                            BatchNorm layer running_mean[C] then running_var[C]; HOST or device pointer as
+                            host_buffers says; NULL = batch statistics, nothing tracked.  Training mode: every f
+                            evaluation of the main solve updates it through the closure exactly as Lux does
+                            (momentum 0.1, unbiased variance) and the buffer holds st'.model on return */
+  int32_t model_testmode; /* 1: Lux.testmode(st.model): BatchNorm normalises with model_state, no update */
+  int32_t reserved[3];
 } lrnde_opts;
 
 typedef struct {

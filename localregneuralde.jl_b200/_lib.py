@@ -31,7 +31,8 @@ class Opts(C.Structure):
         ("t1", C.c_float), ("u01", C.c_float), ("saveat", C.POINTER(C.c_float)),
         ("nsave", C.c_int32), ("save_start", C.c_int32), ("precision", C.c_int32),
         ("pow_mode", C.c_int32), ("host_buffers", C.c_int32), ("keep_tape", C.c_int32),
-        ("loop_mode", C.c_int32), ("last_only", C.c_int32), ("reserved", C.c_int32 * 6),
+        ("loop_mode", C.c_int32), ("last_only", C.c_int32), ("model_state", C.c_void_p),
+        ("model_testmode", C.c_int32), ("reserved", C.c_int32 * 3),
     ]
 
 

@@ -302,6 +302,14 @@ struct ConvEval {
   float* part = nullptr; double2* bpart = nullptr; float* coef = nullptr; float* dgb = nullptr;
   std::vector<int> wS, wImg, wCic, wChunks;
   int bnS = 1, bnImg = 1;
+  // st.model of the layer: running statistics of every BatchNorm (device), see lrnde_opts.model_state
+  float* bn_state = nullptr;
+  std::vector<int64_t> s_off;
+  int64_t nstate = 0;
+  int testmode = 0;
+  bool bn_update = false;
+  bool first_call_twice = false;  // OrdinaryDiffEq calls f(u0, t0) twice (initialize! and the initial-dt heuristic);
+                                  // the library evaluates it once, the running statistics see two closure calls
 
   static int tile_rows(int PT, int Wd, int Ht) { return std::min(PT / (Wd >> 2), Ht); }
   static bool narrow(int cout) { return cout <= 16; }   // <8,8,4> instantiation (whole-image tiles)
@@ -326,6 +334,8 @@ struct ConvEval {
       pack[l] = (float*)ctx->alloc(4 * nw);
       if (l < L - 1) z[l] = (float*)ctx->alloc(4 * HW * Li.cout * B);
       if (Li.bn) { ab[l] = (float*)ctx->alloc(8 * Li.cout); stat[l] = (float*)ctx->alloc(8 * Li.cout); }
+      s_off.push_back(nstate);
+      if (Li.bn) nstate += 2 * (int64_t)Li.cout;
       if (vjp) packT[l] = (float*)ctx->alloc(4 * (size_t)9 * Li.cin * Li.cout);
     }
     spart = (float2*)ctx->alloc(sizeof(float2) * (size_t)nblk_max);
@@ -366,6 +376,28 @@ struct ConvEval {
     ctx->release(part); ctx->release(bpart); ctx->release(coef); ctx->release(dgb);
   }
 
+  // o->model_state (NULL: batch statistics, nothing tracked).  `stage`: device buffer of nstate floats used
+  // when the caller's pointer is a host pointer.  Returns the device pointer in use.
+  float* attach_state(const lrnde_opts* o, float* stage) {
+    bn_state = nullptr; testmode = 0; bn_update = false;
+    if (!o) return nullptr;
+    if (o->model_testmode && !o->model_state && nstate > 0)
+      lr_fail(LRNDE_EINVAL, "model_testmode needs model_state (the running statistics BatchNorm normalises with)");
+    if (!o->model_state || nstate == 0) return nullptr;
+    if (o->host_buffers) {
+      LR_CUDA(cudaMemcpyAsync(stage, o->model_state, 4 * nstate, cudaMemcpyHostToDevice, ctx->stream));
+      bn_state = stage;
+    } else bn_state = o->model_state;
+    testmode = o->model_testmode ? 1 : 0;
+    bn_update = !testmode;
+    return bn_state;
+  }
+  void return_state(const lrnde_opts* o) {   // st'.model back into the caller's buffer (host-pointer case)
+    if (bn_state && o && o->host_buffers && !testmode)
+      LR_CUDA(cudaMemcpyAsync(o->model_state, bn_state, 4 * nstate, cudaMemcpyDeviceToHost, ctx->stream));
+    bn_update = false;
+  }
+
   void prepare() {
     for (int l = 0; l < L; ++l) {
       const ConvLayerInfo& Li = m->conv[l];
@@ -390,7 +422,10 @@ struct ConvEval {
   }
 
   // layers 0..upto-1 of the dynamics on lincomb(in); `side` / `side_desc`: keep the combined input
-  void run_layers(const LinComb* in, const int* done, int upto, const LinComb* out, bool side_to_in_dst, float* side) {
+  void run_layers(const LinComb* in, const int* done, int upto, const LinComb* out, bool side_to_in_dst, float* side,
+                  bool update_state) {
+    const int ncalls = (update_state && first_call_twice) ? 2 : 1;
+    if (update_state) first_call_twice = false;
     for (int l = 0; l < upto; ++l) {
       const ConvLayerInfo& Li = m->conv[l];
       ConvP q;
@@ -402,18 +437,20 @@ struct ConvEval {
       }
       q.td = m->td; q.tdesc = in; q.Wp = pack[l]; q.Cin = Li.cin; q.Cout = Li.cout; q.out_scale = 1.0f; q.done = done;
       if (l == L - 1) q.ydesc = out ? out : in; else q.Y = z[l];
-      if (Li.bn) q.stat_part = spart;
+      if (Li.bn && !testmode) q.stat_part = spart;
       launch(q);
       if (Li.bn) {
         bn_finalize_kernel<<<Li.cout, 128, 0, ctx->stream>>>(spart, conv_nblk(Li.cout), Li.cout, (double)HW * (double)B,
-                                                           ps + Li.g_off, 1e-5f, ab[l], stat[l], done);
+                                                           ps + Li.g_off, 1e-5f, ab[l], stat[l],
+                                                           bn_state ? bn_state + s_off[l] : nullptr, testmode,
+                                                           (update_state && bn_update) ? ncalls : 0, done);
         LR_COUNT(ctx);
       }
     }
   }
 
   void forward(const LinComb* in, const int* done, const LinComb* out, bool side_to_in_dst) {
-    run_layers(in, done, L, out, side_to_in_dst, nullptr);
+    run_layers(in, done, L, out, side_to_in_dst, nullptr, true);
     LR_CHECK_LAUNCH();
   }
 
@@ -421,7 +458,7 @@ struct ConvEval {
            float* dps_ptr, const LinComb* dps_desc, size_t dps_off, float p_scale, float p_beta, const int* done) {
     cudaStream_t st = ctx->stream;
     const size_t DB = (size_t)m->D * B;
-    if (L > 1) run_layers(y, done, L - 1, nullptr, false, ybuf);     // recompute; y(t) kept for dW_1
+    if (L > 1) run_layers(y, done, L - 1, nullptr, false, ybuf, false);     // recompute; y(t) kept for dW_1
     else { lincomb_kernel<<<lr_ew_blocks(DB), 256, 0, st>>>(y, ybuf, DB, done); LR_COUNT(ctx); }
     lincomb_kernel<<<lr_ew_blocks(DB), 256, 0, st>>>(lamd, lbuf, DB, done);
     LR_COUNT(ctx);
@@ -459,7 +496,7 @@ struct ConvEval {
           bn_bwd_stats_kernel<<<dim3(Lp.cout, bnS), 256, 0, st>>>(G[cur], z[l - 1], ab[l - 1], stat[l - 1], Lp.act, Lp.cout, HW,
                                                                 (int)B, bnImg, bpart, done);
           LR_COUNT(ctx);
-          bn_bwd_finalize_kernel<<<(Lp.cout + 63) / 64, 64, 0, st>>>(bpart, bnS, Lp.cout, (double)HW * (double)B, coef, dgb, done);
+          bn_bwd_finalize_kernel<<<(Lp.cout + 63) / 64, 64, 0, st>>>(bpart, bnS, Lp.cout, (double)HW * (double)B, coef, dgb, testmode, done);
           LR_COUNT(ctx);
           wgrad_reduce_kernel<<<1, 256, 0, st>>>(dgb, 1, (size_t)2 * Lp.cout, dps_ptr ? dps_ptr + Lp.g_off : nullptr, dps_desc,
                                                dps_off + (size_t)Lp.g_off, p_scale, p_beta, done);
@@ -1128,6 +1165,7 @@ struct lrnde_tape {
   lrnde_opts opts;
   int64_t B;
   float* ps = nullptr;  // device copy of the parameters the forward used
+  float* bn_state = nullptr;  // conv dynamics: device copy of st.model the forward normalised with (testmode)
   std::unique_ptr<Solver> fwd;
   std::unique_ptr<Solver> reg;  // regulariser integrator (2-slot ring), reg modes only
   std::vector<float> fts;       // host copy of accepted times
@@ -1138,7 +1176,7 @@ struct lrnde_tape {
   // step logs (host copies)
   std::vector<float> log_t[2], log_dt[2], log_eest[2];
   std::vector<unsigned char> log_acc[2];
-  ~lrnde_tape() { ctx->release(ps); }
+  ~lrnde_tape() { ctx->release(ps); ctx->release(bn_state); }
 };
 
 static void lr_copy_log(Solver& S, lrnde_tape* T, int which) {
@@ -1335,7 +1373,10 @@ extern "C" int lrnde_dynamics_eval(lrnde_ctx* ctx, const lrnde_model* m, const l
   LR_CUDA(cudaMemcpyAsync(ddesc.p, &d, sizeof(d), cudaMemcpyHostToDevice, st));
   MlpEval ev(ctx, m, psd, B, o ? o->precision : 0, false);
   ev.prepare();
+  DevBuf dstate(ctx, ev.conv ? std::max<int64_t>(1, ev.conv->nstate) : 1);
+  if (ev.conv) ev.conv->attach_state(o, dstate.p);
   ev.forward((const LinComb*)ddesc.p, nullptr);
+  if (ev.conv) ev.conv->return_state(o);
   if (host) LR_CUDA(cudaMemcpyAsync(du, outd, 4 * DB, cudaMemcpyDeviceToHost, st));
   LR_CUDA(cudaStreamSynchronize(st));
   LR_API_END
@@ -1368,6 +1409,8 @@ extern "C" int lrnde_dynamics_vjp(lrnde_ctx* ctx, const lrnde_model* m, const lr
   LR_CUDA(cudaMemcpyAsync(dd, d, sizeof(d), cudaMemcpyHostToDevice, st));
   MlpEval ev(ctx, m, psd, B, o ? o->precision : 0, true);
   ev.prepare();
+  DevBuf dstate(ctx, ev.conv ? std::max<int64_t>(1, ev.conv->nstate) : 1);
+  if (ev.conv) { ev.conv->attach_state(o, dstate.p); ev.conv->bn_update = false; }
   ev.vjp(dd, dd + 1, ad, nullptr, 1.0f, gd, nullptr, 0, 1.0f, 0.0f, nullptr);
   if (host) {
     LR_CUDA(cudaMemcpyAsync(a, ad, 4 * DB, cudaMemcpyDeviceToHost, st));
@@ -1428,6 +1471,14 @@ extern "C" int lrnde_ode_forward(lrnde_ctx* ctx, const lrnde_model* m, const lrn
   const bool need_vjp = false;
   MlpEval ev(ctx, m, T->ps, B, o->precision, need_vjp);
   ev.prepare();
+  if (ev.conv) {   // st.model: tracked by the main solve's f evaluations only (the closure's st_ at the time
+                   // _solve_neuralode_generic returns, neural_ode.jl:44-53)
+    if (ev.conv->nstate > 0 && o->model_state && (o->host_buffers || o->model_testmode))
+      T->bn_state = (float*)ctx->alloc(4 * ev.conv->nstate);
+    float* used = ev.conv->attach_state(o, T->bn_state);
+    if (used && used != T->bn_state && T->bn_state)
+      LR_CUDA(cudaMemcpyAsync(T->bn_state, used, 4 * ev.conv->nstate, cudaMemcpyDeviceToDevice, st));
+  }
   const long tq3 = lr_now_us();
   auto eval = [&](const LinComb* in, const LinComb*, const int* done, const LinComb* out, bool side) {
     ev.forward(in, done, out, side);
@@ -1439,6 +1490,7 @@ extern "C" int lrnde_ode_forward(lrnde_ctx* ctx, const lrnde_model* m, const lrn
   if (timing)
     fprintf(stderr, "[lrnde] fwd setup us: stage_ps %ld budget %ld tape_alloc %ld prepare %ld graphs %ld (pool %zu blocks)\n",
             tq0 - t_call, tq1 - tq0, tq2 - tq1, tq3 - tq2, t_start - tq3, ctx->pool.size());
+  if (ev.conv) ev.conv->first_call_twice = true;   // after the graphs were captured: applies to the k1 launch only
   lr_solver_start(F, eval, 1);
   for (;;) {
     F.run_segment();
@@ -1453,6 +1505,7 @@ extern "C" int lrnde_ode_forward(lrnde_ctx* ctx, const lrnde_model* m, const lrn
     LR_COUNT(ctx);
   }
   const long t_solve = lr_now_us();
+  if (ev.conv) ev.conv->return_state(o);
   const int naccept = F.h.c.naccept, nreject = F.h.c.nreject;
   T->fts.resize(naccept + 1);
   LR_CUDA(cudaMemcpyAsync(T->fts.data(), F.ts, sizeof(float) * (naccept + 1), cudaMemcpyDeviceToHost, st));
@@ -1647,6 +1700,7 @@ extern "C" int lrnde_ode_backward(lrnde_ctx* ctx, const lrnde_model* m, lrnde_ta
 
   MlpEval ev(ctx, m, T->ps, B, o.precision, true);
   ev.prepare();
+  if (ev.conv && o.model_testmode) { ev.conv->bn_state = T->bn_state; ev.conv->testmode = 1; }
 
   DevBuf out_dx(ctx, host ? DB : 1), out_dps(ctx, host ? P : 1);
   float* dx_dev = host ? out_dx.p : d_x;

@@ -298,10 +298,21 @@ __global__ void __launch_bounds__(256) conv3x3_wgrad_kernel(ConvWgP p) {
 // stat = [mean ; invstd].  grid = C blocks of 128 threads; fixed partition, fixed-order tree => deterministic.
 __global__ void __launch_bounds__(128) bn_finalize_kernel(const float2* part, int nblk, int C, double count,
                                                           const float* gamma_beta, float eps, float* ab,
-                                                          float* stat, const int* done) {
+                                                          float* stat, float* running, int testmode, int update,
+                                                          const int* done) {
   if (done && *done) return;
   __shared__ double s1[128], s2[128];
   const int c = blockIdx.x, tid = threadIdx.x;
+  if (testmode) {   // Lux.testmode: normalise with the running statistics (running = [mean[C] ; var[C]])
+    if (tid == 0) {
+      const float mean = running[c];
+      const float invstd = 1.0f / sqrtf(running[C + c] + eps);
+      const float a = gamma_beta[c] * invstd;
+      ab[c] = a; ab[C + c] = fmaf(-mean, a, gamma_beta[C + c]);
+      stat[c] = mean; stat[C + c] = invstd;
+    }
+    return;
+  }
   double a1 = 0.0, a2 = 0.0;
   for (int i = tid; i < nblk; i += 128) {
     const float2 v = part[(size_t)i * C + c];
@@ -323,6 +334,14 @@ __global__ void __launch_bounds__(128) bn_finalize_kernel(const float2* part, in
     ab[C + c] = fmaf(-(float)mean, a, gamma_beta[C + c]);
     stat[c] = (float)mean;
     stat[C + c] = invstd;
+    if (running) {   // Lux BatchNorm: momentum 0.1, running_var tracks the UNBIASED batch variance; `update` = how
+                     // many closure calls this evaluation stands for (f(u0, t0) is called twice at the start of a solve)
+      const float mom = 0.1f;
+      for (int i = 0; i < update; ++i) {
+        running[c] = (1.0f - mom) * running[c] + mom * (float)mean;
+        running[C + c] = (1.0f - mom) * running[C + c] + mom * (float)(var * (count / (count - 1.0)));
+      }
+    }
   }
 }
 
@@ -365,14 +384,14 @@ __global__ void __launch_bounds__(256) bn_bwd_stats_kernel(const float* g, const
 
 // coef = [mean(ghat) ; mean(ghat xhat)], dgb = [d_gamma ; d_beta]
 __global__ void bn_bwd_finalize_kernel(const double2* part, int S, int C, double count, float* coef, float* dgb,
-                                       const int* done) {
+                                       int testmode, const int* done) {
   if (done && *done) return;
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   double t1 = 0.0, t2 = 0.0;
   for (int s = 0; s < S; ++s) { t1 += part[(size_t)c * S + s].x; t2 += part[(size_t)c * S + s].y; }
-  coef[c] = (float)(t1 / count);
-  coef[C + c] = (float)(t2 / count);
+  coef[c] = testmode ? 0.0f : (float)(t1 / count);          // testmode: the statistics are constants
+  coef[C + c] = testmode ? 0.0f : (float)(t2 / count);
   dgb[c] = (float)t2;
   dgb[C + c] = (float)t1;
 }

@@ -90,6 +90,18 @@ class TDConvChain(ConvChain):
         self.time_dependent = True
 
 
+def initial_model_state(model) -> dict:
+    """``Lux.initialstates`` of the dynamics: BatchNorm running_mean = 0 / running_var = 1 per BatchNorm layer
+    (flat: mean[C] then var[C], layer order) and ``training`` (``Lux.testmode`` flips it); {} for Dense chains."""
+    if not isinstance(model, ConvChain) or not any(L.batchnorm for L in model.layers):
+        return {}
+    blocks = []
+    for L in model.layers:
+        if L.batchnorm:
+            blocks += [np.zeros(L.out_ch, np.float32), np.ones(L.out_ch, np.float32)]
+    return dict(running=np.concatenate(blocks), training=True)
+
+
 def _state_dims(model) -> int:
     return model.state_dims if isinstance(model, ConvChain) else model.layers[0].in_dims
 
@@ -335,7 +347,22 @@ class NeuralODE:
 
     def initialstates(self, rng: np.random.Generator):
         rng.standard_normal()
-        return dict(model={}, nfe=-1, reg_val=np.float32(0), rng=copy.deepcopy(rng), training=True)
+        return dict(model=initial_model_state(self.model), nfe=-1, reg_val=np.float32(0), rng=copy.deepcopy(rng),
+                    training=True)
+
+    def _attach_model_state(self, o, mstate, host, device=None):
+        """st.model -> lrnde_opts.model_state (a fresh copy that the call updates = st'.model)."""
+        if not mstate or mstate.get("running") is None:
+            return None
+        r = mstate["running"]
+        if host:
+            run = np.ascontiguousarray(np.asarray(r.detach().cpu() if _is_torch(r) else r, dtype=np.float32)).copy()
+        else:
+            run = (r.detach().to(device=device, dtype=torch.float32).clone() if _is_torch(r)
+                   else torch.from_numpy(np.asarray(r, np.float32).copy()).to(device))
+        o.model_state = _ptr(run)
+        o.model_testmode = 0 if mstate.get("training", True) else 1
+        return run
 
     @property
     def ctx(self) -> Context:
@@ -416,6 +443,7 @@ class NeuralODE:
         tape = C.c_void_p()
         ctx = self.ctx
         mh = ctx.model_handle(self.model)
+        running = self._attach_model_state(o, st.get("model"), host, None if host else xb.device)
         check(lib().lrnde_ode_forward(ctx._h, mh, C.byref(o), _ptr(psb), _ptr(xb), B, _ptr(usave),
                                       cap, _ptr(times), C.byref(stats), C.byref(tape)))
         n = stats.nsave_out
@@ -423,7 +451,8 @@ class NeuralODE:
         sol = DESolution([T(t) for t in times[:n]], us, tape if keep_tape else None, self, ctx,
                          stats, host)
         sol._shape = (B, D)
-        st2 = dict(model=st["model"], nfe=int(stats.nfe), reg_val=T(stats.reg_val), rng=rng,
+        model_st = st["model"] if running is None else dict(st["model"], running=running)   # st_ of the closure
+        st2 = dict(model=model_st, nfe=int(stats.nfe), reg_val=T(stats.reg_val), rng=rng,
                    training=st["training"])                             # :79-83
         return sol, st2
 
@@ -467,8 +496,9 @@ class NeuralODE:
         sol.bwd_stats = stats
         return d_x.T, d_ps
 
-    def dynamics(self, u, ps, t: float):
-        """One evaluation of the ``dudt`` closure (neural_ode.jl:45-48) on the GPU."""
+    def dynamics(self, u, ps, t: float, model_state: Optional[dict] = None):
+        """One evaluation of the ``dudt`` closure (neural_ode.jl:45-48) on the GPU.  ``model_state`` (st.model of
+        conv dynamics with BatchNorm): returns ``(du, st_model')`` like ``Lux.apply`` does."""
         host = not _is_torch(u)
         ub = _as_input(u, not host, None)
         B, D = ub.shape
@@ -476,11 +506,14 @@ class NeuralODE:
         out = np.empty((B, D), np.float32) if host else torch.empty_like(ub)
         o, _ = self._opts("none", 0.0, 0.0, False, host)
         ctx = self.ctx
+        running = self._attach_model_state(o, model_state, host, None if host else ub.device)
         check(lib().lrnde_dynamics_eval(ctx._h, ctx.model_handle(self.model), C.byref(o), _ptr(psb),
                                         _ptr(ub), float(t), B, _ptr(out)))
+        if model_state is not None:
+            return out.T, (model_state if running is None else dict(model_state, running=running))
         return out.T
 
-    def dynamics_vjp(self, u, ps, t: float, lam):
+    def dynamics_vjp(self, u, ps, t: float, lam, model_state: Optional[dict] = None):
         """``(J_u^T lam, J_p^T lam)`` of one ``dudt`` evaluation: the ZygoteVJP pullback the adjoint calls
         (neural_ode.jl:11).  Host arrays only (parity hook)."""
         ub = _as_input(u, False, None)
@@ -491,6 +524,7 @@ class NeuralODE:
         dps = np.empty(psb.size, np.float32)
         o, _ = self._opts("none", 0.0, 0.0, False, True)
         ctx = self.ctx
+        _running = self._attach_model_state(o, model_state, True)
         check(lib().lrnde_dynamics_vjp(ctx._h, ctx.model_handle(self.model), C.byref(o), _ptr(psb), _ptr(ub),
                                        float(t), _ptr(lb), B, _ptr(a), _ptr(dps)))
         return a.T, dps

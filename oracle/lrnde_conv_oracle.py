@@ -27,7 +27,7 @@ import numpy as np
 
 from .lrnde_oracle import _act, _act_grad
 
-__all__ = ["ConvLayer", "ConvNet", "glorot_uniform_conv_params", "cifar10_node_core"]
+__all__ = ["ConvLayer", "ConvNet", "glorot_uniform_conv_params", "initial_conv_state", "cifar10_node_core"]
 
 
 @dataclass(frozen=True)
@@ -46,6 +46,13 @@ class ConvNet:
     height: int
     time_dependent: bool = True
     eps: float = 1e-5
+    momentum: float = 0.1
+    # st.model of the layer (Lux BatchNorm states): per BatchNorm layer running_mean[C] then running_var[C].
+    # ``running`` set and ``track``: every training-mode f call updates it, as the ``dudt`` closure does through
+    # its captured ``st_`` (neural_ode.jl:44-47); ``testmode``: normalise with it (Lux.testmode).
+    running: Optional[np.ndarray] = None
+    track: bool = False
+    testmode: bool = False
 
     def __post_init__(self):
         td = 1 if self.time_dependent else 0
@@ -59,6 +66,13 @@ class ConvNet:
                 off += 2 * L.out_ch
             self.offsets.append((w_off, g_off))
         self.nparams = off
+        soff = 0
+        self.state_offsets = []
+        for L in self.layers:
+            self.state_offsets.append(soff)
+            if L.batchnorm:
+                soff += 2 * L.out_ch
+        self.nstate = soff
         for a, b in zip(self.layers[:-1], self.layers[1:]):
             assert a.out_ch == b.in_ch
         assert self.layers[0].in_ch == self.layers[-1].out_ch
@@ -124,12 +138,23 @@ class ConvNet:
     def f(self, u, ps, t, cache: Optional[list] = None):
         T = u.dtype.type
         x = self._to_img(u, self.layers[0].in_ch)
-        for L, (W, gamma, beta) in zip(self.layers, self.unpack(ps)):
+        for L, so, (W, gamma, beta) in zip(self.layers, self.state_offsets, self.unpack(ps)):
             xin = self._with_time(x, t)
             z = self._conv(xin, W)
             if L.batchnorm:
-                mu = z.mean(axis=(0, 2, 3), keepdims=True, dtype=z.dtype)
-                var = ((z - mu) ** 2).mean(axis=(0, 2, 3), keepdims=True, dtype=z.dtype)
+                C = L.out_ch
+                if self.testmode:
+                    mu = self.running[so:so + C].astype(z.dtype)[None, :, None, None]
+                    var = self.running[so + C:so + 2 * C].astype(z.dtype)[None, :, None, None]
+                else:
+                    mu = z.mean(axis=(0, 2, 3), keepdims=True, dtype=z.dtype)
+                    var = ((z - mu) ** 2).mean(axis=(0, 2, 3), keepdims=True, dtype=z.dtype)
+                    if self.running is not None and self.track and cache is None:
+                        n = z.size // C                   # Lux: running_var tracks the unbiased batch variance
+                        m = self.running.dtype.type(self.momentum)
+                        self.running[so:so + C] = (1 - m) * self.running[so:so + C] + m * mu.ravel()
+                        self.running[so + C:so + 2 * C] = ((1 - m) * self.running[so + C:so + 2 * C]
+                                                           + m * var.ravel() * (n / (n - 1)))
                 invstd = T(1) / np.sqrt(var + T(self.eps))
                 xhat = (z - mu) * invstd
                 pre = gamma[None, :, None, None] * xhat + beta[None, :, None, None]
@@ -154,13 +179,25 @@ class ConvNet:
             if L.batchnorm:
                 dps[go:go + L.out_ch] = (d * xhat).sum(axis=(0, 2, 3))
                 dps[go + L.out_ch:go + 2 * L.out_ch] = d.sum(axis=(0, 2, 3))
-                m1 = d.mean(axis=(0, 2, 3), keepdims=True, dtype=d.dtype)
-                m2 = (d * xhat).mean(axis=(0, 2, 3), keepdims=True, dtype=d.dtype)
-                d = gamma[None, :, None, None] * invstd * (d - m1 - xhat * m2)
+                if self.testmode:                       # statistics are constants
+                    d = gamma[None, :, None, None] * invstd * d
+                else:
+                    m1 = d.mean(axis=(0, 2, 3), keepdims=True, dtype=d.dtype)
+                    m2 = (d * xhat).mean(axis=(0, 2, 3), keepdims=True, dtype=d.dtype)
+                    d = gamma[None, :, None, None] * invstd * (d - m1 - xhat * m2)
             gx, dW = self._conv_vjp(xin, W, d)
             dps[wo:wo + dW.size] = dW.ravel(order="F")
             g = gx[:, :L.in_ch] if self.time_dependent else gx
         return self._to_flat(g), dps
+
+
+def initial_conv_state(model: ConvNet, dtype=np.float32):
+    """Lux.initialstates of the BatchNorm layers: running_mean = 0, running_var = 1."""
+    st = np.zeros(model.nstate, dtype)
+    for L, so in zip(model.layers, model.state_offsets):
+        if L.batchnorm:
+            st[so + L.out_ch:so + 2 * L.out_ch] = 1
+    return st
 
 
 def glorot_uniform_conv_params(model: ConvNet, rng: np.random.Generator, dtype=np.float32, jitter: float = 0.0):

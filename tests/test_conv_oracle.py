@@ -3,7 +3,8 @@ import numpy as np
 import scipy.signal
 
 import oracle as orc
-from oracle.lrnde_conv_oracle import ConvLayer, ConvNet, cifar10_node_core, glorot_uniform_conv_params
+from oracle.lrnde_conv_oracle import (ConvLayer, ConvNet, cifar10_node_core, glorot_uniform_conv_params,
+                                      initial_conv_state)
 
 
 def _small(dtype=np.float64, td=True, seed=0, B=3):
@@ -80,3 +81,29 @@ def test_neural_ode_layer_runs_on_the_conv_dynamics():
     assert np.isfinite(d_ps).all() and np.isfinite(d_x).all()
     for (wo, go), L in zip(net.offsets, net.layers):
         assert np.abs(d_ps[wo:go]).max() > 0
+
+
+def test_running_statistics_follow_the_closure_and_testmode_uses_them():
+    """Lux BatchNorm inside the ``dudt`` closure (neural_ode.jl:44-47): every training-mode call moves the running
+    statistics by momentum 0.1 (unbiased variance); in testmode they replace the batch statistics and the
+    samples decouple; the testmode pullback matches finite differences."""
+    net, ps, u, rng = _small()
+    net.running = initial_conv_state(net, np.float64)
+    net.track = True
+    z = net._conv(net._with_time(net._to_img(u, 2), 0.1), net.unpack(ps)[0][0])
+    net.f(u, ps, 0.1)
+    n = z.size // 5
+    np.testing.assert_allclose(net.running[:5], 0.1 * z.mean(axis=(0, 2, 3)), rtol=1e-12)
+    np.testing.assert_allclose(net.running[5:10], 0.9 + 0.1 * z.var(axis=(0, 2, 3)) * n / (n - 1), rtol=1e-12)
+    net.track, net.testmode = False, True
+    y0 = net.f(u, ps, 0.1)
+    u2 = u.copy(); u2[:, 0] *= 3.0
+    assert np.array_equal(net.f(u2, ps, 0.1)[:, 1:], y0[:, 1:])
+    lam = rng.standard_normal(u.shape)
+    a, dps = net.vjp(u, ps, 0.3, lam)
+    eps = 1e-6
+    for i in rng.choice(ps.size, 12, replace=False):
+        p1, p2 = ps.copy(), ps.copy()
+        p1[i] += eps; p2[i] -= eps
+        fd = (np.sum(lam * net.f(u, p1, 0.3)) - np.sum(lam * net.f(u, p2, 0.3))) / (2 * eps)
+        assert abs(dps[i] - fd) < 1e-6 * max(1.0, abs(fd))

@@ -153,3 +153,97 @@ def test_cifar10_core_training_iteration_properties(pkg):
     sol2, _ = node(x, ps, st)
     dx2, dps2 = node.backward(sol2, [None, 2.0 * cot], 0.0)
     assert rel(dps2, 2.0 * np.asarray(dps1)) < 1e-3
+
+
+# ------------------------------------------------------------------ st.model: BatchNorm running statistics
+def _bn_case(pkg, seed=4):
+    layers, W, H, B = [(2, 6, True, "gelu"), (6, 20, True, "gelu"), (20, 2, False, "identity")], 8, 8, 4
+    rng = np.random.default_rng(seed)
+    onet, chain = _pair(pkg, layers, W, H, True)
+    ps = glorot_uniform_conv_params(onet, rng, jitter=0.1)
+    x = rng.standard_normal((onet.state_dims, B)).astype(np.float32)
+    return onet, chain, ps, x, rng
+
+
+def test_closure_call_updates_running_statistics(pkg):
+    """One ``dudt`` call = one Lux.apply of the BatchNorm layers in training mode: momentum 0.1, unbiased variance."""
+    from oracle.lrnde_conv_oracle import initial_conv_state
+    onet, chain, ps, x, _ = _bn_case(pkg)
+    node = pkg.NeuralODE(chain)
+    st = node.initialstates(np.random.default_rng(0))
+    assert np.array_equal(st["model"]["running"], initial_conv_state(onet))
+    du, mst = node.dynamics(x, ps, 0.2, model_state=st["model"])
+    onet.running, onet.track = initial_conv_state(onet, np.float64), True
+    want = onet.f(x.astype(np.float64), ps.astype(np.float64), 0.2)
+    assert rel(du, want) < 2e-5
+    assert rel(mst["running"], onet.running) < 1e-5
+    assert np.array_equal(st["model"]["running"], initial_conv_state(onet))     # the input state is not mutated
+
+
+def test_testmode_uses_running_statistics(pkg):
+    onet, chain, ps, x, rng = _bn_case(pkg)
+    running = (np.abs(rng.standard_normal(onet.nstate)) + 0.5).astype(np.float32)
+    node = pkg.NeuralODE(chain)
+    mst = dict(running=running, training=False)
+    du, mst2 = node.dynamics(x, ps, 0.2, model_state=mst)
+    onet.running, onet.testmode = running.astype(np.float64), True
+    assert rel(du, onet.f(x.astype(np.float64), ps.astype(np.float64), 0.2)) < 2e-5
+    assert np.array_equal(mst2["running"], running)
+    lam = rng.standard_normal(x.shape).astype(np.float32)
+    a, dps = node.dynamics_vjp(x, ps, 0.2, lam, model_state=mst)
+    wa, wdps = onet.vjp(x.astype(np.float64), ps.astype(np.float64), 0.2, lam.astype(np.float64))
+    assert rel(a, wa) < 1e-4 and rel(dps, wdps) < 1e-4
+
+
+def test_layer_returns_the_state_of_the_closure(pkg):
+    """st'.model = the closure's st_ when the solve returns (neural_ode.jl:44-53): one update per f evaluation of
+    the MAIN solve -- f(u0, t0) twice (initialize! and the initial-dt heuristic), the initial-dt probe, six per
+    attempt -- and none for the regulariser's evaluations."""
+    from oracle.lrnde_conv_oracle import initial_conv_state
+    onet, chain, ps, x, _ = _bn_case(pkg)
+
+    def oracle_state(maxiters):
+        onet.running, onet.track = initial_conv_state(onet), True
+        sol = orc.solve_tsit5(lambda u, t: onet.f(u, ps, t), x, np.float32(0), np.float32(1), abstol=1e-3,
+                              reltol=1e-3, maxiters=maxiters)
+        return sol, onet.running.copy()
+
+    def gpu_state(mode, maxiters):
+        node = pkg.NeuralODE(chain, regularize=mode, abstol=1e-3, reltol=1e-3, maxiters=maxiters)
+        sol, st2 = node(x, ps, node.initialstates(np.random.default_rng(5)))
+        assert st2["model"]["training"] is True
+        return sol, st2["model"]["running"]
+
+    # exactly one attempt (3 + 6 closure calls): the call counting, to rounding
+    _, want1 = oracle_state(1)
+    gsol1, got1 = gpu_state("none", 1)
+    assert gsol1.retcode == "MaxIters" and rel(got1, want1) < 1e-5, rel(got1, want1)
+    # whole solve: same number of attempts; the step sizes of two Float32 implementations agree to ~1e-3 at
+    # this tolerance (the embedded estimate is a cancellation), and the layer-1 statistics move with the stage
+    # times through the time channel, hence the looser bar
+    osol, want = oracle_state(1000)
+    gsol, got = gpu_state("none", 1000)
+    assert gsol.stats.naccept == osol.naccept and gsol.stats.nreject == osol.nreject
+    assert rel(got, want) < 5e-3, rel(got, want)
+    # the regulariser's integrator evaluates the same closure but AFTER solve returned st_: bitwise the same state
+    _, got_reg = gpu_state("unbiased", 1000)
+    assert np.array_equal(got_reg, got)
+
+
+def test_testmode_layer_matches_oracle(pkg):
+    """Lux.testmode(st): the solve and its adjoint with BatchNorm normalising by the running statistics."""
+    onet, chain, ps, x, rng = _bn_case(pkg)
+    running = (np.abs(rng.standard_normal(onet.nstate)) + 0.5).astype(np.float32)
+    kw = dict(regularize="none", abstol=1e-3, reltol=1e-3, maxiters=1000)
+    onet.running, onet.testmode = running.copy(), True
+    onode, gnode = orc.NeuralODE(onet, **kw), pkg.NeuralODE(chain, **kw)
+    osol, ost2, aux = onode.forward(x, ps, onode.initialstates(np.random.default_rng(5)))
+    gst = gnode.initialstates(np.random.default_rng(5))
+    gst["model"] = dict(running=running, training=False)
+    gsol, gst2 = gnode(x, ps, gst)
+    assert gst2["nfe"] == ost2["nfe"] and rel(gsol.u[-1], osol.u[-1]) < 1e-4
+    assert np.array_equal(gst2["model"]["running"], running)
+    cot = rng.standard_normal(gsol.u[-1].shape).astype(np.float32)
+    gdx, gdps = gnode.backward(gsol, [cot], 0.0)
+    odx, odps = onode.backward(aux, [cot], np.float32(0.0), ps)
+    assert rel(gdx, odx) < 1e-3 and rel(gdps, odps) < 1e-3
