@@ -300,7 +300,7 @@ struct ConvEval {
   float2* spart = nullptr;
   float* ybuf = nullptr; float* lbuf = nullptr; float* G[2] = {nullptr, nullptr};
   float* part = nullptr; double2* bpart = nullptr; float* coef = nullptr; float* dgb = nullptr;
-  std::vector<int> wS, wImg, wCic, wChunks;
+  std::vector<int> wS, wImg, wCic, wChunks, wSwap;
   int bnS = 1, bnImg = 1;
   // st.model of the layer: running statistics of every BatchNorm (device), see lrnde_opts.model_state
   float* bn_state = nullptr;
@@ -349,12 +349,15 @@ struct ConvEval {
       for (int l = 0; l < L; ++l) {
         const ConvLayerInfo& Li = m->conv[l];
         const int cintot = Li.cin + m->td;
-        const int chunks = (cintot + 15) / 16, cic = (cintot + chunks - 1) / chunks;
-        const int ncob = (Li.cout + 63) / 64;
-        int S = std::max(1, std::min((int)B, (4 * n_sm) / (chunks * ncob)));
+        // few output channels (65 => 8): delta takes the patch role and the input the 64-wide tile role
+        const bool swapped = Li.cout <= 16 && cintot > Li.cout;
+        const int pt = swapped ? Li.cout : cintot, qt = swapped ? cintot : Li.cout;
+        const int chunks = (pt + 15) / 16, cic = (pt + chunks - 1) / chunks;
+        const int nqb = (qt + 63) / 64;
+        int S = std::max(1, std::min((int)B, (4 * n_sm) / (chunks * nqb)));
         const int img = (int)((B + S - 1) / S);
         S = (int)((B + img - 1) / img);
-        wS.push_back(S); wImg.push_back(img); wCic.push_back(cic); wChunks.push_back(chunks);
+        wS.push_back(S); wImg.push_back(img); wCic.push_back(cic); wChunks.push_back(chunks); wSwap.push_back(swapped ? 1 : 0);
         maxpart = std::max(maxpart, (size_t)S * 9 * cintot * Li.cout);
       }
       part = (float*)ctx->alloc(4 * maxpart);
@@ -470,11 +473,18 @@ struct ConvEval {
       const size_t nw = (size_t)9 * cintot * Li.cout;
       ConvWgP w;
       memset(&w, 0, sizeof(w));
-      if (l == 0) { w.X = ybuf; w.in_act = ACT_IDENTITY; }
-      else { w.X = z[l - 1]; w.in_ab = m->conv[l - 1].bn ? ab[l - 1] : nullptr; w.in_act = m->conv[l - 1].act; }
-      w.td = m->td; w.tdesc = y; w.Dl = delta; w.Wd = m->Wd; w.Ht = m->Ht; w.Cin = Li.cin; w.Cout = Li.cout; w.B = (int)B;
-      w.cic = wCic[l]; w.img_per_split = wImg[l]; w.part = part; w.block = nw; w.done = done;
-      conv3x3_wgrad_kernel<<<dim3(wChunks[l], wS[l], (Li.cout + 63) / 64), 256, 0, st>>>(w);
+      ConvWgOp ox, od;
+      memset(&ox, 0, sizeof(ox)); memset(&od, 0, sizeof(od));
+      if (l == 0) { ox.ptr = ybuf; ox.act = ACT_IDENTITY; }
+      else { ox.ptr = z[l - 1]; ox.ab = m->conv[l - 1].bn ? ab[l - 1] : nullptr; ox.act = m->conv[l - 1].act; }
+      ox.C = Li.cin; ox.td = m->td;
+      od.ptr = delta; od.act = ACT_IDENTITY; od.C = Li.cout; od.td = 0;
+      w.swapped = wSwap[l];
+      w.P = w.swapped ? od : ox; w.Q = w.swapped ? ox : od;
+      w.tdesc = y; w.Wd = m->Wd; w.Ht = m->Ht; w.B = (int)B; w.CinTot = cintot; w.Cout = Li.cout;
+      w.pcc = wCic[l]; w.img_per_split = wImg[l]; w.part = part; w.block = nw; w.done = done;
+      const int qt = w.Q.C + w.Q.td;
+      conv3x3_wgrad_kernel<<<dim3(wChunks[l], wS[l], (qt + 63) / 64), 256, 0, st>>>(w);
       LR_COUNT(ctx);
       wgrad_reduce_kernel<<<lr_ew_blocks(nw), 256, 0, st>>>(part, wS[l], nw, dps_ptr ? dps_ptr + Li.w_off : nullptr, dps_desc,
                                                            dps_off + (size_t)Li.w_off, p_scale, p_beta, done);

@@ -192,32 +192,53 @@ __global__ void __launch_bounds__(256) conv3x3_kernel(ConvP p) {
 }
 
 // ------------------------------------------------------------------------------------------
-// weight gradient: dW[kx,ky,ci,co] = sum_{b,o} xin[o + d, ci, b] * delta[o, co, b]
-// grid (input-channel chunks, batch splits, 64-wide output-channel blocks); a thread owns one input
-// channel x 4 output channels x the 9 taps and walks the pixels of a row strip with a sliding window
+// weight gradient: dW[kx,ky,ci,co] = sum_{b,o} x[o + d, ci, b] * delta[o, co, b]
+//
+// Two operands: P ("patch", with a one-pixel halo, <= 16 channels per CTA) and Q ("tile", no halo, 64 channels
+// per CTA, stored pixel-major so that a thread reads its 4 channels with one 16-byte load).  A thread owns one P
+// channel x 4 Q channels x the 9 taps and walks the pixels of a row strip with a sliding window over P:
+//   acc[tap][j] = sum_px P[px + d_tap][pc] * Q[px][qc_j]
+// normal : P = x (input, transformed on load), Q = delta           -> dW[2-dx, 2-dy][ci = pc][co = qc]
+// swapped: P = delta, Q = x  (few output channels: 65 => 8)        -> dW[dx, dy][ci = qc][co = pc]
+// grid (P-channel chunks, batch splits, 64-wide Q blocks); fixed-order reduce over the splits afterwards
 // ------------------------------------------------------------------------------------------
+struct ConvWgOp {
+  const float* ptr; const float* ab; int act; int C; int td;   // [Wd,Ht,C,B]; per-channel a,b + activation on load; virtual time channel
+};
 struct ConvWgP {
-  const float* X; const float* in_ab; int in_act; int td; const LinComb* tdesc;
-  const float* Dl;
-  int Wd, Ht, Cin, Cout, B;
-  int cic, img_per_split;
+  ConvWgOp P, Q;
+  int swapped;
+  const LinComb* tdesc;
+  int Wd, Ht, B;
+  int pcc, img_per_split;      // P channels per CTA (<= 16)
+  int CinTot, Cout;            // layout of the result
   float* part; size_t block;   // part[split][block], Lux weight layout
   const int* done;
 };
 
+__device__ __forceinline__ float conv_wg_load(const ConvWgOp& o, int ch, size_t pix, int b, size_t HW, float tval) {
+  if (ch == o.C) return tval;
+  float v = o.ptr[pix + HW * (ch + (size_t)o.C * b)];
+  if (o.ab) v = fmaf(o.ab[ch], v, o.ab[o.C + ch]);
+  if (o.act != ACT_IDENTITY) v = lr_act(o.act, v);
+  return v;
+}
+
+#define CWG_NPX 96
+#define CWG_QS 68     // Q tile row stride (floats): 16-byte aligned rows, 4-way conflict on the (rare) stores only
 __global__ void __launch_bounds__(256) conv3x3_wgrad_kernel(ConvWgP p) {
   if (p.done && *p.done) return;
-  __shared__ float ds[64][129];
-  __shared__ float xs[16][240];
+  __shared__ __align__(16) float qs[CWG_NPX * CWG_QS];
+  __shared__ float xs[16][184];
   __shared__ float tval;
   const int tid = threadIdx.x;
   const int Wd = p.Wd, Ht = p.Ht, RS = Wd + 3, pw = Wd + 2;
-  const int SR = max(1, min(Ht, 128 / Wd)), NPX = SR * Wd;
-  const int CinTot = p.Cin + (p.td ? 1 : 0);
-  const int c0 = blockIdx.x * p.cic;
-  const int ncl = min(p.cic, CinTot - c0);
-  const int co0 = blockIdx.z * 64;
-  const int ci_l = tid >> 4, cog = tid & 15;
+  const int SR = max(1, min(Ht, CWG_NPX / Wd)), NPX = SR * Wd;
+  const int PT = p.P.C + p.P.td, QT = p.Q.C + p.Q.td;
+  const int c0 = blockIdx.x * p.pcc;
+  const int ncl = min(p.pcc, PT - c0);
+  const int q0 = blockIdx.z * 64;
+  const int pc_l = tid >> 4, cog = tid & 15;
   const int b0 = blockIdx.y * p.img_per_split, b1 = min(p.B, b0 + p.img_per_split);
   if (tid == 0) tval = p.tdesc ? p.tdesc->t : 0.0f;
   float acc[9][4];
@@ -226,43 +247,37 @@ __global__ void __launch_bounds__(256) conv3x3_wgrad_kernel(ConvWgP p) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[k][j] = 0.0f;
   const size_t HW = (size_t)Wd * Ht;
+  const bool qactive = q0 + cog * 4 < QT;       // warps whose threads are all idle skip the pixel loop
   for (int b = b0; b < b1; ++b) {
     for (int row0 = 0; row0 < Ht; row0 += SR) {
       __syncthreads();
       for (int e = tid; e < ncl * (SR + 2) * pw; e += 256) {
         const int x = e % pw, r = (e / pw) % (SR + 2), c = e / (pw * (SR + 2));
-        const int gc = c0 + c, gy = row0 + r - 1, gx = x - 1;
+        const int gy = row0 + r - 1, gx = x - 1;
         float v = 0.0f;
-        if (gy >= 0 && gy < Ht && gx >= 0 && gx < Wd) {
-          if (gc == p.Cin) v = tval;
-          else {
-            v = p.X[gx + (size_t)Wd * gy + HW * (gc + (size_t)p.Cin * b)];
-            if (p.in_ab) v = fmaf(p.in_ab[gc], v, p.in_ab[p.Cin + gc]);
-            if (p.in_act != ACT_IDENTITY) v = lr_act(p.in_act, v);
-          }
-        }
+        if (gy >= 0 && gy < Ht && gx >= 0 && gx < Wd) v = conv_wg_load(p.P, c0 + c, gx + (size_t)Wd * gy, b, HW, tval);
         xs[c][r * RS + x] = v;
       }
       for (int e = tid; e < 64 * NPX; e += 256) {
-        const int px = e % NPX, co = e / NPX;
+        const int px = e % NPX, c = e / NPX;
         const int gy = row0 + px / Wd;
         float v = 0.0f;
-        if (co0 + co < p.Cout && gy < Ht) v = p.Dl[(size_t)row0 * Wd + px + HW * (co0 + co + (size_t)p.Cout * b)];
-        ds[co][px] = v;
+        if (q0 + c < QT && gy < Ht) v = conv_wg_load(p.Q, q0 + c, (size_t)row0 * Wd + px, b, HW, tval);
+        qs[px * CWG_QS + c] = v;
       }
       __syncthreads();
-      if (ci_l < ncl) {
+      if (pc_l < ncl && qactive) {
         for (int r = 0; r < SR; ++r) {
           float x0[3], x1[3], x2[3];
 #pragma unroll
-          for (int dy = 0; dy < 3; ++dy) { x0[dy] = xs[ci_l][(r + dy) * RS]; x1[dy] = xs[ci_l][(r + dy) * RS + 1]; }
+          for (int dy = 0; dy < 3; ++dy) { x0[dy] = xs[pc_l][(r + dy) * RS]; x1[dy] = xs[pc_l][(r + dy) * RS + 1]; }
+#pragma unroll 4
           for (int x = 0; x < Wd; ++x) {
-            float d[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) d[j] = ds[cog * 4 + j][r * Wd + x];
+            const float4 d4 = *reinterpret_cast<const float4*>(&qs[(r * Wd + x) * CWG_QS + cog * 4]);
+            const float d[4] = {d4.x, d4.y, d4.z, d4.w};
 #pragma unroll
             for (int dy = 0; dy < 3; ++dy) {
-              x2[dy] = xs[ci_l][(r + dy) * RS + x + 2];
+              x2[dy] = xs[pc_l][(r + dy) * RS + x + 2];
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 acc[dy * 3 + 0][j] = fmaf(x0[dy], d[j], acc[dy * 3 + 0][j]);
@@ -276,16 +291,18 @@ __global__ void __launch_bounds__(256) conv3x3_wgrad_kernel(ConvWgP p) {
       }
     }
   }
-  if (ci_l < ncl) {
+  if (pc_l < ncl) {
     float* out = p.part + (size_t)blockIdx.y * p.block;
+    const int pc = c0 + pc_l;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int co = co0 + cog * 4 + j;
-      if (co >= p.Cout) continue;
+      const int qc = q0 + cog * 4 + j;
+      if (qc >= QT) continue;
+      const int ci = p.swapped ? qc : pc, co = p.swapped ? pc : qc;
 #pragma unroll
       for (int k = 0; k < 9; ++k) {
-        const int kx = 2 - k % 3, ky = 2 - k / 3;
-        out[kx + 3 * (ky + 3 * (c0 + ci_l + (size_t)CinTot * co))] = acc[k][j];
+        const int kx = p.swapped ? (k % 3) : (2 - k % 3), ky = p.swapped ? (k / 3) : (2 - k / 3);
+        out[kx + 3 * (ky + 3 * (ci + (size_t)p.CinTot * co))] = acc[k][j];
       }
     }
   }
