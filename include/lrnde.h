@@ -306,6 +306,25 @@ int lrnde_latent_loss(lrnde_ctx* ctx, const float* pred, const float* data, cons
                       const float* logsigma2, int32_t F, int32_t T, int32_t L, int64_t B, float w_kl,
                       int32_t host_buffers, float* out3, float* d_pred, float* d_mu, float* d_logsigma2);
 
+/* Layers either side of the cifar10 NeuralODE (experiments/src/construct.jl:220-227), WHCN arrays
+ * [width, height, C, B]; backward calls recompute what they need from x (no tape).
+ * lrnde_conv2d_*: Lux Conv((3,3), in_ch => out_ch, act; pad=(1,1)) -- the AugmenterLayer's Conv 3 => 5
+ * (src/layers/common.jl:80-92; the concatenation with x is the caller's) and the classifier's Conv 8 => 1, gelu.
+ * ps = weight[3,3,in_ch,out_ch] then (use_bias) bias[out_ch].  d_x may be NULL. */
+int lrnde_conv2d_forward(lrnde_ctx* ctx, int32_t in_ch, int32_t out_ch, int32_t use_bias, int32_t act, int32_t width,
+                         int32_t height, const float* ps, const float* x, int64_t B, int32_t host_buffers, float* y);
+int lrnde_conv2d_backward(lrnde_ctx* ctx, int32_t in_ch, int32_t out_ch, int32_t use_bias, int32_t act,
+                          int32_t width, int32_t height, const float* ps, const float* x, const float* d_y, int64_t B,
+                          int32_t host_buffers, float* d_x, float* d_ps);
+/* lrnde_batchnorm_*: Lux BatchNorm(C, act) on [HW, C, B]: ps = scale[C] then bias[C]; state (nullable unless
+ * testmode) = running_mean[C] then running_var[C], updated in place in training mode (momentum 0.1, unbiased
+ * variance), used for normalisation when testmode. */
+int lrnde_batchnorm_forward(lrnde_ctx* ctx, int32_t C, int64_t HW, int32_t act, const float* ps, const float* x,
+                            int64_t B, float* state, int32_t testmode, int32_t host_buffers, float* y);
+int lrnde_batchnorm_backward(lrnde_ctx* ctx, int32_t C, int64_t HW, int32_t act, const float* ps, const float* x,
+                             const float* d_y, int64_t B, const float* state, int32_t testmode, int32_t host_buffers,
+                             float* d_x, float* d_ps);
+
 /* Next row of the path: classifier Dense(D => C) + logitcrossentropy,
  * experiments/src/construct.jl:199 and experiments/src/utils.jl:88, with its pullback.
  * Wc: flat [C x D] weight then [C] bias; u: [D,B]; labels: class index per sample.

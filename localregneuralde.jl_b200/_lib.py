@@ -86,6 +86,7 @@ SYMBOLS = [
     "lrnde_sde_step_log", "lrnde_sde_aux_step", "lrnde_gru_nparams", "lrnde_gru_forward",
     "lrnde_gru_backward", "lrnde_gru_tape_free", "lrnde_mlp_forward", "lrnde_mlp_backward",
     "lrnde_reparameterize", "lrnde_latent_loss", "lrnde_conv_model_create", "lrnde_dynamics_vjp",
+    "lrnde_conv2d_forward", "lrnde_conv2d_backward", "lrnde_batchnorm_forward", "lrnde_batchnorm_backward",
 ]
 
 
@@ -111,6 +112,10 @@ def lib():
     L.lrnde_model_destroy.argtypes = [vp]
     L.lrnde_conv_model_create.argtypes = [vp, C.POINTER(ConvLayerDesc), i32, i32, i32, i32, C.POINTER(vp)]
     L.lrnde_dynamics_vjp.argtypes = [vp, vp, C.POINTER(Opts), vp, vp, f32, vp, i64, vp, vp]
+    L.lrnde_conv2d_forward.argtypes = [vp, i32, i32, i32, i32, i32, i32, vp, vp, i64, i32, vp]
+    L.lrnde_conv2d_backward.argtypes = [vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, i64, i32, vp, vp]
+    L.lrnde_batchnorm_forward.argtypes = [vp, i32, i64, i32, vp, vp, i64, vp, i32, i32, vp]
+    L.lrnde_batchnorm_backward.argtypes = [vp, i32, i64, i32, vp, vp, vp, i64, vp, i32, i32, vp, vp]
     L.lrnde_model_nparams.argtypes = [vp]
     L.lrnde_model_nparams.restype = i64
     L.lrnde_model_state_dims.argtypes = [vp]

@@ -1845,3 +1845,4 @@ extern "C" int lrnde_ode_backward(lrnde_ctx* ctx, const lrnde_model* m, lrnde_ta
 #include "lrnde_extra.cuh"
 #include "lrnde_sde.cuh"
 #include "lrnde_latent.cuh"
+#include "lrnde_conv_ops.cuh"

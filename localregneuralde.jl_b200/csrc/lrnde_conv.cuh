@@ -36,6 +36,7 @@ struct ConvP {
   const float* Wp;                       // packed weights [9][CinTot][Cout]
   int Wd, Ht, Cin, Cout, B;
   float* Y; const LinComb* ydesc; float out_scale;
+  const float* bias; int out_act; float* pre;   // standalone Conv layer: y = act(conv + bias), pre-activation kept
   float2* stat_part;                     // [gridDim.x][Cout] (sum, sum of squares) of the raw output
   const int* done;
 };
@@ -161,6 +162,11 @@ __global__ void __launch_bounds__(256) conv3x3_kernel(ConvP p) {
         const size_t idx = pcol + (size_t)Wd * ((row0 + prow) + (size_t)Ht * (co + (size_t)p.Cout * b));
         float4 v = make_float4(acc[0][j] * p.out_scale, acc[1][j] * p.out_scale, acc[2][j] * p.out_scale,
                                acc[3][j] * p.out_scale);
+        if (p.bias) { const float bv = p.bias[co]; v.x += bv; v.y += bv; v.z += bv; v.w += bv; }
+        if (p.pre) *reinterpret_cast<float4*>(p.pre + idx) = v;
+        if (p.out_act != ACT_IDENTITY) {
+          v.x = lr_act(p.out_act, v.x); v.y = lr_act(p.out_act, v.y); v.z = lr_act(p.out_act, v.z); v.w = lr_act(p.out_act, v.w);
+        }
         // the lambda block of the adjoint state sits at a multiple of (D*B + nparams) floats: not always 16-byte aligned
         if (out_vec) *reinterpret_cast<float4*>(out + idx) = v;
         else { out[idx] = v.x; out[idx + 1] = v.y; out[idx + 2] = v.z; out[idx + 3] = v.w; }
@@ -429,5 +435,65 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(float* g, const float
     } else {
       g[i] = g[i] * lr_dact(act, zz);
     }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// standalone BatchNorm layer (the BatchNorm(8) in front of the cifar10 NeuralODE, construct.jl:222)
+// ------------------------------------------------------------------------------------------
+// per-channel (sum, sum of squares) of x [HW, C, B] over a slice of the batch, in the layout bn_finalize_kernel
+// reads: part[split][C].  grid (C, S)
+__global__ void __launch_bounds__(256) bn_stats_kernel(const float* x, int C, size_t HW, int B, int img_per_split,
+                                                       float2* part) {
+  __shared__ double r1[8], r2[8];
+  const int c = blockIdx.x, tid = threadIdx.x;
+  const int b0 = blockIdx.y * img_per_split, b1 = min(B, b0 + img_per_split);
+  double a1 = 0.0, a2 = 0.0;
+  for (int b = b0; b < b1; ++b) {
+    const size_t base = HW * (c + (size_t)C * b);
+    float f1 = 0.0f, f2 = 0.0f;
+    for (size_t i = tid; i < HW; i += 256) { const float v = x[base + i]; f1 += v; f2 = fmaf(v, v, f2); }
+    a1 += (double)f1; a2 += (double)f2;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+    a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+  }
+  if ((tid & 31) == 0) { r1[tid >> 5] = a1; r2[tid >> 5] = a2; }
+  __syncthreads();
+  if (tid == 0) {
+    double t1 = 0.0, t2 = 0.0;
+    for (int w = 0; w < 8; ++w) { t1 += r1[w]; t2 += r2[w]; }
+    part[(size_t)blockIdx.y * C + c] = make_float2((float)t1, (float)t2);
+  }
+}
+
+// y = act(a[c] x + b[c])
+__global__ void __launch_bounds__(256) bn_apply_kernel(const float* x, const float* ab, int act, int C, size_t HW,
+                                                       size_t n, float* y) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)((i / HW) % C);
+    y[i] = lr_act(act, fmaf(ab[c], x[i], ab[C + c]));
+  }
+}
+
+// dst[c] = sum over (HW, B) of g[., c, .]   (bias gradient of a Conv layer); grid C
+__global__ void __launch_bounds__(256) channel_sum_kernel(const float* g, int C, size_t HW, int B, float* dst) {
+  __shared__ double r1[8];
+  const int c = blockIdx.x, tid = threadIdx.x;
+  double a1 = 0.0;
+  for (int b = 0; b < B; ++b) {
+    const size_t base = HW * (c + (size_t)C * b);
+    float f1 = 0.0f;
+    for (size_t i = tid; i < HW; i += 256) f1 += g[base + i];
+    a1 += (double)f1;
+  }
+  for (int o = 16; o > 0; o >>= 1) a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+  if ((tid & 31) == 0) r1[tid >> 5] = a1;
+  __syncthreads();
+  if (tid == 0) {
+    double t1 = 0.0;
+    for (int w = 0; w < 8; ++w) t1 += r1[w];
+    dst[c] = (float)t1;
   }
 }

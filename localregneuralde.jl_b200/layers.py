@@ -964,3 +964,114 @@ if torch is not None:
         box = {}
         u, reg = _NeuralODEFn.apply(x, ps, layer, st, box)
         return u, reg, box["st"]
+
+
+# ------------------------------------------------------------------ layers either side of the cifar10 NeuralODE
+def _whcn(a):
+    """(W, H, C, B) array in the reference's column-major order == C-contiguous (B, C, H, W) memory."""
+    if _is_torch(a):
+        return a.detach().to(torch.float32).permute(3, 2, 1, 0).contiguous()
+    return np.ascontiguousarray(np.asarray(a, np.float32).transpose(3, 2, 1, 0))
+
+
+def _from_bchw(a):
+    return a.permute(3, 2, 1, 0) if _is_torch(a) else a.transpose(3, 2, 1, 0)
+
+
+def conv2d_forward(x, ps, out_ch: int, activation: str = "identity", use_bias: bool = True, ctx: Optional[Context] = None):
+    """Lux ``Conv((3,3), in => out, activation; pad=(1,1))`` on a WHCN array ``(W, H, in, B)``; ``ps`` = weight
+    ``[3,3,in,out]`` (column-major) then bias (experiments/src/construct.jl:220,224)."""
+    ctx = ctx or default_context(0)
+    xb = _whcn(x)
+    B, Cin, H, W = xb.shape
+    host = not _is_torch(x)
+    psb = np.ascontiguousarray(np.asarray(ps, np.float32)) if host else ps.detach().to(torch.float32).contiguous()
+    y = np.empty((B, out_ch, H, W), np.float32) if host else torch.empty((B, out_ch, H, W), dtype=torch.float32, device=xb.device)
+    check(lib().lrnde_conv2d_forward(ctx._h, Cin, out_ch, 1 if use_bias else 0, _lib.ACT[activation], W, H, _ptr(psb),
+                                     _ptr(xb), B, 1 if host else 0, _ptr(y)))
+    return _from_bchw(y)
+
+
+def conv2d_backward(x, ps, d_y, activation: str = "identity", use_bias: bool = True, need_dx: bool = True,
+                    ctx: Optional[Context] = None):
+    """Pullback of :func:`conv2d_forward`: ``(d_x or None, d_ps)``."""
+    ctx = ctx or default_context(0)
+    xb, dyb = _whcn(x), _whcn(d_y)
+    B, Cin, H, W = xb.shape
+    Cout = dyb.shape[1]
+    host = not _is_torch(x)
+    psb = np.ascontiguousarray(np.asarray(ps, np.float32)) if host else ps.detach().to(torch.float32).contiguous()
+    n_ps = 9 * Cin * Cout + (Cout if use_bias else 0)
+    if host:
+        d_x = np.empty(xb.shape, np.float32) if need_dx else None
+        d_ps = np.empty(n_ps, np.float32)
+    else:
+        d_x = torch.empty_like(xb) if need_dx else None
+        d_ps = torch.empty(n_ps, dtype=torch.float32, device=xb.device)
+    check(lib().lrnde_conv2d_backward(ctx._h, Cin, Cout, 1 if use_bias else 0, _lib.ACT[activation], W, H, _ptr(psb),
+                                      _ptr(xb), _ptr(dyb), B, 1 if host else 0, _ptr(d_x), _ptr(d_ps)))
+    return (_from_bchw(d_x) if need_dx else None), d_ps
+
+
+def batchnorm_forward(x, ps, state: Optional[dict] = None, activation: str = "identity", ctx: Optional[Context] = None):
+    """Lux ``BatchNorm(C, activation)`` on a WHCN array; ``ps`` = scale then bias; ``state`` = ``{"running": [mean; var],
+    "training": bool}`` (``Lux.initialstates``: zeros / ones).  Returns ``(y, state')``."""
+    ctx = ctx or default_context(0)
+    xb = _whcn(x)
+    B, Cc, H, W = xb.shape
+    host = not _is_torch(x)
+    psb = np.ascontiguousarray(np.asarray(ps, np.float32)) if host else ps.detach().to(torch.float32).contiguous()
+    y = np.empty(xb.shape, np.float32) if host else torch.empty_like(xb)
+    run, test = None, 0
+    if state is not None and state.get("running") is not None:
+        r = state["running"]
+        run = (np.ascontiguousarray(np.asarray(r, np.float32)).copy() if host
+               else (r.detach().to(device=xb.device, dtype=torch.float32).clone() if _is_torch(r)
+                     else torch.from_numpy(np.asarray(r, np.float32).copy()).to(xb.device)))
+        test = 0 if state.get("training", True) else 1
+    check(lib().lrnde_batchnorm_forward(ctx._h, Cc, H * W, _lib.ACT[activation], _ptr(psb), _ptr(xb), B, _ptr(run), test,
+                                        1 if host else 0, _ptr(y)))
+    st2 = state if run is None else dict(state, running=run)
+    return _from_bchw(y), st2
+
+
+def batchnorm_backward(x, ps, d_y, state: Optional[dict] = None, activation: str = "identity", ctx: Optional[Context] = None):
+    """Pullback of :func:`batchnorm_forward` (training mode: through the batch statistics): ``(d_x, d_ps)``."""
+    ctx = ctx or default_context(0)
+    xb, dyb = _whcn(x), _whcn(d_y)
+    B, Cc, H, W = xb.shape
+    host = not _is_torch(x)
+    psb = np.ascontiguousarray(np.asarray(ps, np.float32)) if host else ps.detach().to(torch.float32).contiguous()
+    d_x = np.empty(xb.shape, np.float32) if host else torch.empty_like(xb)
+    d_ps = np.empty(2 * Cc, np.float32) if host else torch.empty(2 * Cc, dtype=torch.float32, device=xb.device)
+    run, test = None, 0
+    if state is not None and state.get("running") is not None and not state.get("training", True):
+        r = state["running"]
+        run = (np.ascontiguousarray(np.asarray(r, np.float32)) if host
+               else (r.detach().to(device=xb.device, dtype=torch.float32).contiguous() if _is_torch(r)
+                     else torch.from_numpy(np.asarray(r, np.float32).copy()).to(xb.device)))
+        test = 1
+    check(lib().lrnde_batchnorm_backward(ctx._h, Cc, H * W, _lib.ACT[activation], _ptr(psb), _ptr(xb), _ptr(dyb), B,
+                                         _ptr(run), test, 1 if host else 0, _ptr(d_x), _ptr(d_ps)))
+    return _from_bchw(d_x), d_ps
+
+
+class AugmenterLayer:
+    """``AugmenterLayer(Conv((3,3), in => extra; pad=(1,1)), 3)``: ``cat(x, conv(x); dims=3)``
+    (src/layers/common.jl:80-92, experiments/src/construct.jl:220)."""
+
+    def __init__(self, in_ch: int, extra_ch: int):
+        self.in_ch, self.extra_ch = in_ch, extra_ch
+
+    def nparams(self):
+        return 9 * self.in_ch * self.extra_ch + self.extra_ch
+
+    def __call__(self, x, ps, ctx=None):
+        y = conv2d_forward(x, ps, self.extra_ch, "identity", True, ctx)
+        return torch.cat([x, y], dim=2) if _is_torch(x) else np.concatenate([np.asarray(x, np.float32), y], axis=2)
+
+    def backward(self, x, ps, d_out, ctx=None):
+        """(d_x, d_ps): the cotangent of the first ``in_ch`` channels passes through, the rest goes through the conv."""
+        d_pass, d_conv = d_out[:, :, :self.in_ch], d_out[:, :, self.in_ch:]
+        d_x, d_ps = conv2d_backward(x, ps, d_conv, "identity", True, True, ctx)
+        return d_x + d_pass, d_ps

@@ -27,7 +27,8 @@ import numpy as np
 
 from .lrnde_oracle import _act, _act_grad
 
-__all__ = ["ConvLayer", "ConvNet", "glorot_uniform_conv_params", "initial_conv_state", "cifar10_node_core"]
+__all__ = ["ConvLayer", "ConvNet", "glorot_uniform_conv_params", "initial_conv_state", "cifar10_node_core",
+           "conv2d", "conv2d_vjp", "batchnorm", "batchnorm_vjp", "augmenter", "augmenter_vjp"]
 
 
 @dataclass(frozen=True)
@@ -220,3 +221,91 @@ def cifar10_node_core(width=32, height=32) -> ConvNet:
     """experiments/src/construct.jl:212-218 (state 32x32x8 after the AugmenterLayer 3 -> 3+5 channels)."""
     return ConvNet([ConvLayer(8, 64, True, "gelu"), ConvLayer(64, 64, True, "gelu"), ConvLayer(64, 8)],
                    width, height, time_dependent=True)
+
+
+# --------------------------------------------------------------------------
+# Layers either side of the cifar10 NeuralODE (experiments/src/construct.jl:220-227), on WHCN arrays (W, H, C, B)
+# --------------------------------------------------------------------------
+def _split_conv_ps(ps, cin, cout, use_bias):
+    n = 9 * cin * cout
+    W = ps[:n].reshape((3, 3, cin, cout), order="F")
+    return W, (ps[n:n + cout] if use_bias else None)
+
+
+def conv2d(x, ps, out_ch, act="identity", use_bias=True):
+    """Lux ``Conv((3,3), in => out, act; pad=(1,1))``: ``act.(conv(x, W) .+ b)``."""
+    xb = np.ascontiguousarray(x.transpose(3, 2, 1, 0))
+    W, b = _split_conv_ps(ps, xb.shape[1], out_ch, use_bias)
+    z = ConvNet._conv(xb, W)
+    if use_bias:
+        z = z + b[None, :, None, None]
+    return _act(act, z).transpose(3, 2, 1, 0)
+
+
+def conv2d_vjp(x, ps, d_y, act="identity", use_bias=True):
+    xb = np.ascontiguousarray(x.transpose(3, 2, 1, 0))
+    dyb = np.ascontiguousarray(d_y.transpose(3, 2, 1, 0))
+    cout = dyb.shape[1]
+    W, b = _split_conv_ps(ps, xb.shape[1], cout, use_bias)
+    z = ConvNet._conv(xb, W)
+    if use_bias:
+        z = z + b[None, :, None, None]
+    d = dyb * _act_grad(act, z, _act(act, z))
+    gx, dW = ConvNet._conv_vjp(xb, W, d)
+    d_ps = np.concatenate([dW.ravel(order="F")] + ([d.sum(axis=(0, 2, 3))] if use_bias else []))
+    return gx.transpose(3, 2, 1, 0), d_ps.astype(x.dtype)
+
+
+def batchnorm(x, ps, act="identity", running=None, training=True, eps=1e-5, momentum=0.1):
+    """Lux ``BatchNorm(C, act)``: returns ``(y, running')``; ``running`` = [mean; var]."""
+    T = x.dtype.type
+    C = x.shape[2]
+    gamma, beta = ps[:C][None, None, :, None], ps[C:2 * C][None, None, :, None]
+    if training:
+        mu = x.mean(axis=(0, 1, 3), keepdims=True, dtype=x.dtype)
+        var = ((x - mu) ** 2).mean(axis=(0, 1, 3), keepdims=True, dtype=x.dtype)
+        if running is not None:
+            n = x.size // C
+            m = running.dtype.type(momentum)
+            running = np.concatenate([(1 - m) * running[:C] + m * mu.ravel(),
+                                      (1 - m) * running[C:] + m * var.ravel() * (n / (n - 1))]).astype(running.dtype)
+    else:
+        mu = running[:C].astype(x.dtype)[None, None, :, None]
+        var = running[C:].astype(x.dtype)[None, None, :, None]
+    xhat = (x - mu) / np.sqrt(var + T(eps))
+    return _act(act, gamma * xhat + beta), running
+
+
+def batchnorm_vjp(x, ps, d_y, act="identity", running=None, training=True, eps=1e-5):
+    T = x.dtype.type
+    C = x.shape[2]
+    gamma, beta = ps[:C][None, None, :, None], ps[C:2 * C][None, None, :, None]
+    if training:
+        mu = x.mean(axis=(0, 1, 3), keepdims=True, dtype=x.dtype)
+        var = ((x - mu) ** 2).mean(axis=(0, 1, 3), keepdims=True, dtype=x.dtype)
+    else:
+        mu = running[:C].astype(x.dtype)[None, None, :, None]
+        var = running[C:].astype(x.dtype)[None, None, :, None]
+    invstd = T(1) / np.sqrt(var + T(eps))
+    xhat = (x - mu) * invstd
+    pre = gamma * xhat + beta
+    d = d_y * _act_grad(act, pre, _act(act, pre))
+    d_ps = np.concatenate([(d * xhat).sum(axis=(0, 1, 3)), d.sum(axis=(0, 1, 3))]).astype(x.dtype)
+    if training:
+        m1 = d.mean(axis=(0, 1, 3), keepdims=True, dtype=d.dtype)
+        m2 = (d * xhat).mean(axis=(0, 1, 3), keepdims=True, dtype=d.dtype)
+        d_x = gamma * invstd * (d - m1 - xhat * m2)
+    else:
+        d_x = gamma * invstd * d
+    return d_x, d_ps
+
+
+def augmenter(x, ps, extra_ch):
+    """``AugmenterLayer(Conv((3,3), in => extra; pad=1), 3)``: cat(x, conv(x); dims=3) (src/layers/common.jl:80-92)."""
+    return np.concatenate([x, conv2d(x, ps, extra_ch)], axis=2)
+
+
+def augmenter_vjp(x, ps, d_out):
+    cin = x.shape[2]
+    d_x, d_ps = conv2d_vjp(x, ps, d_out[:, :, cin:])
+    return d_x + d_out[:, :, :cin], d_ps

@@ -107,3 +107,41 @@ def test_running_statistics_follow_the_closure_and_testmode_uses_them():
         p1[i] += eps; p2[i] -= eps
         fd = (np.sum(lam * net.f(u, p1, 0.3)) - np.sum(lam * net.f(u, p2, 0.3))) / (2 * eps)
         assert abs(dps[i] - fd) < 1e-6 * max(1.0, abs(fd))
+
+
+def test_side_layers_match_finite_differences():
+    """Conv with bias / activation, BatchNorm (training and testmode) and the AugmenterLayer: pullbacks vs central
+    differences in Float64."""
+    from oracle.lrnde_conv_oracle import augmenter, augmenter_vjp, batchnorm, batchnorm_vjp, conv2d, conv2d_vjp
+    rng = np.random.default_rng(7)
+    x = rng.standard_normal((8, 4, 3, 2))
+    eps = 1e-6
+
+    def check(fun, vjp_out, args, n=10):
+        for k, (arr, grad) in enumerate(args):
+            for i in rng.choice(arr.size, min(n, arr.size), replace=False):
+                a1, a2 = arr.copy(), arr.copy()
+                a1.flat[i] += eps; a2.flat[i] -= eps
+                fd = (fun(*(a1 if j == k else a[0] for j, a in enumerate(args)))
+                      - fun(*(a2 if j == k else a[0] for j, a in enumerate(args)))) / (2 * eps)
+                assert abs(grad.flat[i] - fd) < 1e-6 * max(1.0, abs(fd)), (k, i, grad.flat[i], fd)
+
+    ps = rng.standard_normal(9 * 3 * 5 + 5) * 0.3
+    dy = rng.standard_normal((8, 4, 5, 2))
+    d_x, d_ps = conv2d_vjp(x, ps, dy, "gelu")
+    check(lambda xx, pp: np.sum(dy * conv2d(xx, pp, 5, "gelu")), None, [(x, d_x), (ps, d_ps)])
+    assert augmenter(x, ps, 5).shape == (8, 4, 8, 2)
+    da = rng.standard_normal((8, 4, 8, 2))
+    d_x, d_ps = augmenter_vjp(x, ps, da)
+    check(lambda xx, pp: np.sum(da * augmenter(xx, pp, 5)), None, [(x, d_x), (ps, d_ps)])
+    bps = np.concatenate([1 + 0.2 * rng.standard_normal(3), 0.2 * rng.standard_normal(3)])
+    dyb = rng.standard_normal(x.shape)
+    d_x, d_ps = batchnorm_vjp(x, bps, dyb, "gelu")
+    check(lambda xx, pp: np.sum(dyb * batchnorm(xx, pp, "gelu")[0]), None, [(x, d_x), (bps, d_ps)])
+    run = np.concatenate([0.1 * rng.standard_normal(3), 0.5 + rng.random(3)])
+    d_x, d_ps = batchnorm_vjp(x, bps, dyb, "identity", run, False)
+    check(lambda xx, pp: np.sum(dyb * batchnorm(xx, pp, "identity", run, False)[0]), None, [(x, d_x), (bps, d_ps)])
+    _, run2 = batchnorm(x, bps, "identity", np.concatenate([np.zeros(3), np.ones(3)]), True)
+    n = x.size // 3
+    np.testing.assert_allclose(run2[:3], 0.1 * x.mean(axis=(0, 1, 3)))
+    np.testing.assert_allclose(run2[3:], 0.9 + 0.1 * x.var(axis=(0, 1, 3)) * n / (n - 1))

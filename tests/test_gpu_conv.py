@@ -247,3 +247,116 @@ def test_testmode_layer_matches_oracle(pkg):
     gdx, gdps = gnode.backward(gsol, [cot], 0.0)
     odx, odps = onode.backward(aux, [cot], np.float32(0.0), ps)
     assert rel(gdx, odx) < 1e-3 and rel(gdps, odps) < 1e-3
+
+
+# ------------------------------------------------------------------ layers either side of the cifar10 NeuralODE
+@pytest.mark.parametrize("cin,cout,act,W,H,B", [(3, 5, "identity", 32, 32, 3), (8, 1, "gelu", 32, 32, 4),
+                                                 (3, 5, "identity", 8, 8, 2), (20, 24, "tanh", 12, 5, 3)])
+def test_conv2d_layer_matches_oracle(pkg, cin, cout, act, W, H, B):
+    from oracle.lrnde_conv_oracle import conv2d, conv2d_vjp
+    rng = np.random.default_rng(11)
+    x = rng.standard_normal((W, H, cin, B)).astype(np.float32)
+    ps = (0.3 * rng.standard_normal(9 * cin * cout + cout)).astype(np.float32)
+    dy = rng.standard_normal((W, H, cout, B)).astype(np.float32)
+    y = pkg.conv2d_forward(x, ps, cout, act)
+    assert y.shape == (W, H, cout, B)
+    assert rel(y, conv2d(x.astype(np.float64), ps.astype(np.float64), cout, act)) < 2e-5
+    d_x, d_ps = pkg.conv2d_backward(x, ps, dy, act)
+    wdx, wdps = conv2d_vjp(x.astype(np.float64), ps.astype(np.float64), dy.astype(np.float64), act)
+    assert rel(d_x, wdx) < 1e-4 and rel(d_ps, wdps) < 1e-4
+
+
+@pytest.mark.parametrize("training", [True, False])
+def test_batchnorm_layer_matches_oracle(pkg, training):
+    from oracle.lrnde_conv_oracle import batchnorm, batchnorm_vjp
+    rng = np.random.default_rng(12)
+    W, H, C, B = 32, 32, 8, 5
+    x = (1.5 * rng.standard_normal((W, H, C, B)) + 0.3).astype(np.float32)
+    ps = np.concatenate([1 + 0.2 * rng.standard_normal(C), 0.2 * rng.standard_normal(C)]).astype(np.float32)
+    run = np.concatenate([0.1 * rng.standard_normal(C), 0.5 + rng.random(C)]).astype(np.float32)
+    dy = rng.standard_normal(x.shape).astype(np.float32)
+    y, st2 = pkg.batchnorm_forward(x, ps, dict(running=run, training=training))
+    wy, wrun = batchnorm(x.astype(np.float64), ps.astype(np.float64), "identity", run.astype(np.float64), training)
+    assert rel(y, wy) < 2e-5 and rel(st2["running"], wrun) < 1e-5
+    d_x, d_ps = pkg.batchnorm_backward(x, ps, dy, dict(running=run, training=training))
+    wdx, wdps = batchnorm_vjp(x.astype(np.float64), ps.astype(np.float64), dy.astype(np.float64), "identity",
+                              run.astype(np.float64), training)
+    assert rel(d_x, wdx) < 1e-4 and rel(d_ps, wdps) < 1e-4
+
+
+def test_cifar10_model_end_to_end(pkg):
+    """The whole Chain of experiments/src/construct.jl:212-227 at a reduced width (8x8 images, hidden 16):
+    AugmenterLayer(Conv 3=>5) -> BatchNorm(8) -> NeuralODE(conv core, :unbiased) -> diffeqsol_to_array ->
+    Conv(8=>1, gelu) -> Flatten -> Dense(64=>10) -> logitcrossentropy + w_reg * reg_val, forward and reverse,
+    against the oracle pipeline: loss 1e-4, every gradient block 1e-3 (regulariser term: noise-aware, see above)."""
+    from oracle.lrnde_conv_oracle import (augmenter, augmenter_vjp, batchnorm, batchnorm_vjp, conv2d, conv2d_vjp)
+    import ctypes as C
+    rng = np.random.default_rng(13)
+    W = H = 8
+    B, NC = 6, 10
+    core = [(8, 16, True, "gelu"), (16, 16, True, "gelu"), (16, 8, False, "identity")]
+    onet, chain = _pair(pkg, core, W, H, True)
+    x = rng.standard_normal((W, H, 3, B)).astype(np.float32)
+    labels = rng.integers(0, NC, B).astype(np.int32)
+    p_aug = (0.3 * rng.standard_normal(9 * 3 * 5 + 5)).astype(np.float32)
+    p_bn = np.concatenate([np.ones(8), np.zeros(8)]).astype(np.float32)
+    p_node = glorot_uniform_conv_params(onet, rng, jitter=0.1)
+    p_cls = (0.3 * rng.standard_normal(9 * 8 + 1)).astype(np.float32)
+    p_head = np.concatenate([(0.2 * rng.standard_normal(NC * W * H)), np.zeros(NC)]).astype(np.float32)
+    kw = dict(regularize="unbiased", abstol=1e-3, reltol=1e-3, maxiters=1000)
+    w_reg = 0.0      # the regulariser's own gradient is covered (noise-aware) by the layer test above
+
+    # ---- oracle pipeline
+    a0 = augmenter(x, p_aug, 5)
+    a1, _ = batchnorm(a0, p_bn)
+    onode = orc.NeuralODE(onet, **kw)
+    osol, ost2, aux = onode.forward(a1.reshape(-1, B), p_node, onode.initialstates(np.random.default_rng(5)))
+    u2 = osol.u[-1].reshape(W, H, 8, B)
+    c = conv2d(u2, p_cls, 1, "gelu")
+    flat = c.reshape(W * H, B)
+    Wh, bh = p_head[:NC * W * H].reshape((NC, W * H), order="F"), p_head[NC * W * H:]
+    logits = Wh @ flat + bh[:, None]
+    lse = np.log(np.exp(logits - logits.max(0)).sum(0)) + logits.max(0)
+    oloss = float(np.mean(lse - logits[labels, np.arange(B)]))
+    sm = np.exp(logits - lse)
+    sm[labels, np.arange(B)] -= 1
+    dlog = sm / B
+    od_head = np.concatenate([(dlog @ flat.T).ravel(order="F"), dlog.sum(1)])
+    d_c = (Wh.T @ dlog).reshape(W, H, 1, B)
+    d_u2, od_cls = conv2d_vjp(u2, p_cls, d_c, "gelu")
+    cots = [np.zeros_like(u) for u in osol.u]
+    cots[-1] = d_u2.reshape(-1, B).astype(np.float32)
+    d_a1, od_node = onode.backward(aux, cots, np.float32(w_reg), p_node)
+    d_a0, od_bn = batchnorm_vjp(a0, p_bn, d_a1.reshape(W, H, 8, B))
+    _, od_aug = augmenter_vjp(x, p_aug, d_a0)
+
+    # ---- the same Chain through libLRNDE
+    aug = pkg.AugmenterLayer(3, 5)
+    g0 = aug(x, p_aug)
+    g1, _ = pkg.batchnorm_forward(g0, p_bn, dict(running=np.concatenate([np.zeros(8), np.ones(8)]), training=True))
+    gnode = pkg.NeuralODE(chain, **kw)
+    gsol, gst2 = gnode(np.ascontiguousarray(g1.transpose(3, 2, 1, 0)).reshape(B, -1).T, p_node,
+                       gnode.initialstates(np.random.default_rng(5)))
+    assert gst2["nfe"] == ost2["nfe"]
+    gu2 = np.ascontiguousarray(np.asarray(gsol.u[-1]).T).reshape(B, 8, H, W).transpose(3, 2, 1, 0)
+    gc = pkg.conv2d_forward(gu2, p_cls, 1, "gelu")
+    gflat = np.ascontiguousarray(gc.transpose(3, 2, 1, 0)).reshape(B, W * H)      # batch-major == column-major [D, B]
+    loss = C.c_float()
+    gd_flat = np.empty((B, W * H), np.float32)
+    gd_head = np.empty(p_head.size, np.float32)
+    lib = pkg.lib()
+    ctx = gnode.ctx
+    rc = lib.lrnde_head_ce(ctx._h, p_head.ctypes.data, gflat.ctypes.data, labels.ctypes.data, B, W * H, NC, 1,
+                           C.byref(loss), gd_flat.ctypes.data, gd_head.ctypes.data)
+    assert rc == 0
+    assert abs(loss.value - oloss) < 1e-4 * abs(oloss)
+    gd_c = gd_flat.reshape(B, 1, H, W).transpose(3, 2, 1, 0)
+    gd_u2, gd_cls = pkg.conv2d_backward(gu2, p_cls, gd_c, "gelu")
+    gcot = np.ascontiguousarray(gd_u2.transpose(3, 2, 1, 0)).reshape(B, -1).T
+    gd_a1, gd_node = gnode.backward(gsol, [None] * (len(gsol.u) - 1) + [gcot], w_reg)
+    gd_a1 = np.ascontiguousarray(np.asarray(gd_a1).T).reshape(B, 8, H, W).transpose(3, 2, 1, 0)
+    gd_a0, gd_bn = pkg.batchnorm_backward(g0, p_bn, gd_a1, dict(running=None, training=True))
+    _, gd_aug = aug.backward(x, p_aug, gd_a0)
+    for name, got, want in (("head", gd_head, od_head), ("classifier conv", gd_cls, od_cls), ("node core", gd_node, od_node),
+                            ("batchnorm", gd_bn, od_bn), ("augmenter", gd_aug, od_aug)):
+        assert rel(got, want) < 1e-3, (name, rel(got, want))
