@@ -96,23 +96,31 @@ __global__ void __launch_bounds__(256) conv3x3_kernel(ConvP p) {
   for (int c0 = 0; c0 < CinTot; c0 += CK) {
     __syncthreads();
     if (p.side_desc && !side_out) side_out = xd.dst;   // xd is visible after the first barrier
-    for (int e = tid; e < CK * prow_n * pw; e += 256) {
-      const int x = e % pw, r = (e / pw) % prow_n, c = e / (pw * prow_n);
-      const int gc = c0 + c, gy = row0 + r - 1, gx = x - 1;
-      float v = 0.0f;
-      if (gc < CinTot && gy >= 0 && gy < Ht && gx >= 0 && gx < Wd) {
-        if (gc == p.Cin) v = tval;
-        else {
-          const size_t idx = gx + (size_t)Wd * (gy + (size_t)Ht * (gc + (size_t)p.Cin * b));
-          if (p.xdesc) {
-            v = lr_lincomb_at(xd, idx);
-            if (side_out && blockIdx.y == 0 && r >= 1 && r <= TR) side_out[idx] = v;
-          } else v = p.X[idx];
-          if (p.in_ab) v = fmaf(p.in_ab[gc], v, p.in_ab[p.Cin + gc]);
-          if (p.in_act != ACT_IDENTITY) v = lr_act(p.in_act, v);
+    {   // patch: one (or half a) warp per input channel, lanes over the (row, x) pairs; the row comes from a
+        // multiply-shift (exact for e < 2048 and every pw = Wd + 2 <= 34; checked exhaustively) instead of integer divisions
+      constexpr int WPC = 8 / CK;
+      const int c = (tid >> 5) / WPC;
+      const int gc = c0 + c;
+      const unsigned inv_pw = (65536u + pw - 1) / pw;
+#pragma unroll 4
+      for (int e = (tid & 31) + 32 * ((tid >> 5) % WPC); e < prow_n * pw; e += 32 * WPC) {
+        const int r = (int)(((unsigned)e * inv_pw) >> 16), x = e - r * pw;
+        const int gy = row0 + r - 1, gx = x - 1;
+        float v = 0.0f;
+        if (gc < CinTot && gy >= 0 && gy < Ht && gx >= 0 && gx < Wd) {
+          if (gc == p.Cin) v = tval;
+          else {
+            const size_t idx = gx + (size_t)Wd * (gy + (size_t)Ht * (gc + (size_t)p.Cin * b));
+            if (p.xdesc) {
+              v = lr_lincomb_at(xd, idx);
+              if (side_out && blockIdx.y == 0 && r >= 1 && r <= TR) side_out[idx] = v;
+            } else v = p.X[idx];
+            if (p.in_ab) v = fmaf(p.in_ab[gc], v, p.in_ab[p.Cin + gc]);
+            if (p.in_act != ACT_IDENTITY) v = lr_act(p.in_act, v);
+          }
         }
+        xs[c][r * RS + x] = v;
       }
-      xs[c][r * RS + x] = v;
     }
     for (int e = tid; e < 9 * CK * CB; e += 256) {
       const int j = e % CB, c = (e / CB) % CK, tap = e / (CB * CK);
@@ -257,19 +265,26 @@ __global__ void __launch_bounds__(256) conv3x3_wgrad_kernel(ConvWgP p) {
   for (int b = b0; b < b1; ++b) {
     for (int row0 = 0; row0 < Ht; row0 += SR) {
       __syncthreads();
-      for (int e = tid; e < ncl * (SR + 2) * pw; e += 256) {
-        const int x = e % pw, r = (e / pw) % (SR + 2), c = e / (pw * (SR + 2));
-        const int gy = row0 + r - 1, gx = x - 1;
-        float v = 0.0f;
-        if (gy >= 0 && gy < Ht && gx >= 0 && gx < Wd) v = conv_wg_load(p.P, c0 + c, gx + (size_t)Wd * gy, b, HW, tval);
-        xs[c][r * RS + x] = v;
+      for (int c = tid >> 5; c < ncl; c += 8) {        // patch operand: a warp per channel, lanes along x
+        for (int r = 0; r < SR + 2; ++r) {
+          const int gy = row0 + r - 1;
+          const bool row_ok = gy >= 0 && gy < Ht;
+          for (int x = tid & 31; x < pw; x += 32) {
+            const int gx = x - 1;
+            float v = 0.0f;
+            if (row_ok && gx >= 0 && gx < Wd) v = conv_wg_load(p.P, c0 + c, gx + (size_t)Wd * gy, b, HW, tval);
+            xs[c][r * RS + x] = v;
+          }
+        }
       }
-      for (int e = tid; e < 64 * NPX; e += 256) {
-        const int px = e % NPX, c = e / NPX;
-        const int gy = row0 + px / Wd;
-        float v = 0.0f;
-        if (q0 + c < QT && gy < Ht) v = conv_wg_load(p.Q, q0 + c, (size_t)row0 * Wd + px, b, HW, tval);
-        qs[px * CWG_QS + c] = v;
+      for (int c = tid >> 5; c < 64; c += 8) {         // tile operand: lanes along the pixels of the strip
+        const bool ch_ok = q0 + c < QT;
+        for (int px = tid & 31; px < NPX; px += 32) {
+          const size_t pix = (size_t)row0 * Wd + px;
+          float v = 0.0f;
+          if (ch_ok && pix < HW) v = conv_wg_load(p.Q, q0 + c, pix, b, HW, tval);
+          qs[px * CWG_QS + c] = v;
+        }
       }
       __syncthreads();
       if (pc_l < ncl && qactive) {

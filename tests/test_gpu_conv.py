@@ -310,10 +310,10 @@ def test_cifar10_model_end_to_end(pkg):
     a0 = augmenter(x, p_aug, 5)
     a1, _ = batchnorm(a0, p_bn)
     onode = orc.NeuralODE(onet, **kw)
-    osol, ost2, aux = onode.forward(a1.reshape(-1, B), p_node, onode.initialstates(np.random.default_rng(5)))
-    u2 = osol.u[-1].reshape(W, H, 8, B)
+    osol, ost2, aux = onode.forward(a1.reshape((-1, B), order="F"), p_node, onode.initialstates(np.random.default_rng(5)))
+    u2 = osol.u[-1].reshape((W, H, 8, B), order="F")     # Julia reshapes are column-major
     c = conv2d(u2, p_cls, 1, "gelu")
-    flat = c.reshape(W * H, B)
+    flat = c.reshape((W * H, B), order="F")                # FlattenLayer
     Wh, bh = p_head[:NC * W * H].reshape((NC, W * H), order="F"), p_head[NC * W * H:]
     logits = Wh @ flat + bh[:, None]
     lse = np.log(np.exp(logits - logits.max(0)).sum(0)) + logits.max(0)
@@ -322,12 +322,12 @@ def test_cifar10_model_end_to_end(pkg):
     sm[labels, np.arange(B)] -= 1
     dlog = sm / B
     od_head = np.concatenate([(dlog @ flat.T).ravel(order="F"), dlog.sum(1)])
-    d_c = (Wh.T @ dlog).reshape(W, H, 1, B)
+    d_c = (Wh.T @ dlog).reshape((W, H, 1, B), order="F")
     d_u2, od_cls = conv2d_vjp(u2, p_cls, d_c, "gelu")
     cots = [np.zeros_like(u) for u in osol.u]
-    cots[-1] = d_u2.reshape(-1, B).astype(np.float32)
+    cots[-1] = d_u2.reshape((-1, B), order="F").astype(np.float32)
     d_a1, od_node = onode.backward(aux, cots, np.float32(w_reg), p_node)
-    d_a0, od_bn = batchnorm_vjp(a0, p_bn, d_a1.reshape(W, H, 8, B))
+    d_a0, od_bn = batchnorm_vjp(a0, p_bn, d_a1.reshape((W, H, 8, B), order="F"))
     _, od_aug = augmenter_vjp(x, p_aug, d_a0)
 
     # ---- the same Chain through libLRNDE
