@@ -360,3 +360,34 @@ def test_cifar10_model_end_to_end(pkg):
     for name, got, want in (("head", gd_head, od_head), ("classifier conv", gd_cls, od_cls), ("node core", gd_node, od_node),
                             ("batchnorm", gd_bn, od_bn), ("augmenter", gd_aug, od_aug)):
         assert rel(got, want) < 1e-3, (name, rel(got, want))
+
+
+def test_device_resident_tensors_match_host_buffers(pkg):
+    """Zero-copy path (torch CUDA tensors, host_buffers = 0) of the conv dynamics and the side layers gives the
+    results of the host-buffer path bit for bit, including st'.model."""
+    import torch
+    onet, chain, ps, x, rng = _bn_case(pkg)
+    dev = torch.device("cuda", 0)
+    node = pkg.NeuralODE(chain, regularize="unbiased", abstol=1e-3, reltol=1e-3, maxiters=1000)
+    st = node.initialstates(np.random.default_rng(5))
+    sol_h, st_h = node(x, ps, st)
+    cot = rng.standard_normal(sol_h.u[-1].shape).astype(np.float32)
+    dx_h, dps_h = node.backward(sol_h, [None, cot], 1.0)
+    xt, pt = torch.from_numpy(x).to(dev), torch.from_numpy(ps).to(dev)
+    sol_d, st_d = node(xt, pt, st)
+    dx_d, dps_d = node.backward(sol_d, [None, torch.from_numpy(cot).to(dev)], 1.0)
+    assert st_d["nfe"] == st_h["nfe"] and float(st_d["reg_val"]) == float(st_h["reg_val"])
+    assert np.array_equal(sol_d.u[-1].cpu().numpy(), np.asarray(sol_h.u[-1]))
+    assert np.array_equal(st_d["model"]["running"].cpu().numpy(), st_h["model"]["running"])
+    assert np.array_equal(dps_d.cpu().numpy(), np.asarray(dps_h)) and np.array_equal(dx_d.cpu().numpy(), np.asarray(dx_h))
+    # side layers
+    xi = rng.standard_normal((8, 8, 3, 4)).astype(np.float32)
+    pa = (0.3 * rng.standard_normal(9 * 3 * 5 + 5)).astype(np.float32)
+    y_h = pkg.conv2d_forward(xi, pa, 5)
+    y_d = pkg.conv2d_forward(torch.from_numpy(xi).to(dev), torch.from_numpy(pa).to(dev), 5)
+    assert np.array_equal(y_d.cpu().numpy(), y_h)
+    bn_ps = np.concatenate([np.ones(3), np.zeros(3)]).astype(np.float32)
+    state = dict(running=np.concatenate([np.zeros(3), np.ones(3)]).astype(np.float32), training=True)
+    b_h, s_h = pkg.batchnorm_forward(xi, bn_ps, state)
+    b_d, s_d = pkg.batchnorm_forward(torch.from_numpy(xi).to(dev), torch.from_numpy(bn_ps).to(dev), state)
+    assert np.array_equal(b_d.cpu().numpy(), b_h) and np.array_equal(s_d["running"].cpu().numpy(), s_h["running"])
