@@ -15,7 +15,8 @@ import numpy as np
 
 from . import _lib
 from ._lib import check, lib
-from .layers import Chain, Context, Dense, NeuralODE, TDChain, nparams
+from .layers import (AugmenterLayer, Chain, Context, Conv, ConvChain, Dense, NeuralODE, TDChain, TDConvChain, _whcn,
+                     batchnorm_backward, batchnorm_forward, conv2d_backward, conv2d_forward, glorot_uniform, nparams)
 
 
 # ------------------------------------------------------------------ schedules (experiments/src/utils.jl:1-68)
@@ -186,5 +187,99 @@ class MnistODETrainer:
         nfe = int(st2["nfe"])
         sol.free()
         self.st = st2
+        return [self.step, time.perf_counter() - t_batch, data_time, t_fwd, t_bwd, t_opt, float(loss.value), reg,
+                float(loss.value) + w_reg * reg, nfe, acc1, acc5]
+
+
+# ------------------------------------------------------------------ CIFAR10 conv neural-ODE trainer
+class Cifar10ODETrainer:
+    """AugmenterLayer(Conv 3=>5) -> BatchNorm(8) -> NeuralODE(TDChain(Conv 9=>h + BN gelu, Conv h+1=>h + BN gelu,
+    Conv h+1=>8)) -> sol.u[end] -> Conv(8=>1, gelu) -> Flatten -> Dense(W*H => 10) with logitcrossentropy +
+    w_reg * reg_val (experiments/src/construct.jl:212-227, :19-33), Adam, scheduled learning rate and w_reg.
+    Images are (B, 3, H, W) CUDA tensors: that memory IS the reference's column-major (W, H, 3, B) array."""
+
+    def __init__(self, *, hidden: int = 64, image: int = 32, lr: float = 1e-3, scheduler: str = "inverse",
+                 w_reg_start: float = 100.0, w_reg_end: float = 10.0, total_steps: int = 1000, abstol: float = 1e-4,
+                 reltol: float = 1e-4, regularize: str = "unbiased", seed: int = 0, ctx: Optional[Context] = None,
+                 device: int = 0):
+        import torch
+        self.torch = torch
+        self.dev = torch.device("cuda", device)
+        self.ctx = ctx or Context(device, torch.cuda.current_stream(self.dev).cuda_stream)
+        self.W = self.H = int(image)
+        self.C = 10
+        self.aug = AugmenterLayer(3, 5)
+        self.chain = TDConvChain(ConvChain(Conv(8, hidden, True, "gelu"), Conv(hidden, hidden, True, "gelu"),
+                                           Conv(hidden, 8), width=self.W, height=self.H))
+        self.node = NeuralODE(self.chain, regularize=regularize, save_start=False, abstol=abstol, reltol=reltol,
+                              maxiters=10_000, ctx=self.ctx)
+        rng = np.random.default_rng(seed)
+
+        def conv_init(cin, cout):          # Lux Conv: Glorot-uniform weight, zero bias
+            a = math.sqrt(6.0 / (9 * cin + 9 * cout))
+            return np.concatenate([rng.uniform(-a, a, 9 * cin * cout), np.zeros(cout)]).astype(np.float32)
+
+        D = self.W * self.H
+        a = math.sqrt(6.0 / (D + self.C))
+        params = dict(augment=conv_init(3, 5), bn=np.concatenate([np.ones(8), np.zeros(8)]).astype(np.float32),
+                      node=glorot_uniform(self.chain, rng), cls_conv=conv_init(8, 1),
+                      head=np.concatenate([rng.uniform(-a, a, self.C * D), np.zeros(self.C)]).astype(np.float32))
+        self.ps = {k: torch.from_numpy(v).to(self.dev) for k, v in params.items()}
+        self.opt = {k: (torch.zeros_like(v), torch.zeros_like(v)) for k, v in self.ps.items()}
+        self.st = self.node.initialstates(rng)
+        self.bn_state = dict(running=torch.cat([torch.zeros(8), torch.ones(8)]).to(self.dev), training=True)
+        self.lr_sched = lr_scheduler(scheduler, lr, total_steps=total_steps)
+        self.w_reg_sched = ExponentialDecay(w_reg_start, w_reg_end, total_steps)
+        self.step = 0
+
+    def train_step(self, x, y, data_time: float = 0.0):
+        """x: (B, 3, H, W) float32 CUDA tensor, y: (B,) int32 labels.  Returns the CSV row of this step."""
+        torch, L = self.torch, lib()
+        t_batch = time.perf_counter()
+        self.step += 1
+        w_reg, lr = self.w_reg_sched(self.step), self.lr_sched(self.step)
+        B, W, H, ps = x.shape[0], self.W, self.H, self.ps
+        t0 = time.perf_counter()
+        xl = x.permute(3, 2, 1, 0)                                       # logical (W, H, 3, B)
+        a0 = self.aug(xl, ps["augment"], self.ctx)
+        a1, bn_state = batchnorm_forward(a0, ps["bn"], self.bn_state, "identity", self.ctx)
+        sol, st2 = self.node(_whcn(a1).reshape(B, -1).t(), ps["node"], self.st)
+        u2 = sol.u[-1].t().reshape(B, 8, H, W).permute(3, 2, 1, 0)
+        c = conv2d_forward(u2, ps["cls_conv"], 1, "gelu", True, self.ctx)
+        flat = _whcn(c).reshape(B, W * H)                                # FlattenLayer: column-major [W*H, B]
+        loss = C.c_float()
+        d_flat = torch.empty_like(flat)
+        grads = {"head": torch.empty_like(ps["head"])}
+        check(L.lrnde_head_ce(self.ctx._h, ps["head"].data_ptr(), flat.data_ptr(), y.data_ptr(), B, W * H, self.C, 0,
+                              C.byref(loss), d_flat.data_ptr(), grads["head"].data_ptr()))
+        torch.cuda.synchronize(self.dev)
+        t_fwd = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        d_u2, grads["cls_conv"] = conv2d_backward(u2, ps["cls_conv"], d_flat.reshape(B, 1, H, W).permute(3, 2, 1, 0),
+                                                  "gelu", True, True, self.ctx)
+        cot = _whcn(d_u2).reshape(B, -1).t()
+        d_a1, grads["node"] = self.node.backward(sol, [None] * (len(sol.u) - 1) + [cot], w_reg)
+        d_a0, grads["bn"] = batchnorm_backward(a0, ps["bn"], d_a1.t().reshape(B, 8, H, W).permute(3, 2, 1, 0),
+                                               dict(running=None, training=True), "identity", self.ctx)
+        _, grads["augment"] = self.aug.backward(xl, ps["augment"], d_a0, self.ctx)
+        torch.cuda.synchronize(self.dev)
+        t_bwd = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        for k, p in ps.items():
+            m, v = self.opt[k]
+            g = grads[k].contiguous()
+            check(L.lrnde_adam_step(self.ctx._h, p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(),
+                                    float(lr), 0.9, 0.999, 1e-8, self.step))
+        torch.cuda.synchronize(self.dev)
+        t_opt = time.perf_counter() - t0
+        Wh = ps["head"][: self.C * W * H].view(W * H, self.C)             # column-major [C x D]
+        logits = flat @ Wh + ps["head"][self.C * W * H:]
+        top5 = logits.topk(5, dim=1).indices
+        yl = y.long()
+        acc1 = float((top5[:, 0] == yl).float().mean())
+        acc5 = float((top5 == yl[:, None]).any(dim=1).float().mean())
+        reg, nfe = float(st2["reg_val"]), int(st2["nfe"])
+        sol.free()
+        self.st, self.bn_state = st2, bn_state
         return [self.step, time.perf_counter() - t_batch, data_time, t_fwd, t_bwd, t_opt, float(loss.value), reg,
                 float(loss.value) + w_reg * reg, nfe, acc1, acc5]

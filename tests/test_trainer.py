@@ -64,3 +64,24 @@ def test_training_iterations_reduce_the_loss(tr, tmp_path):
     assert all(np.isfinite(ce)) and ce[-1] < ce[0] - 0.05, ce            # memorising a fixed batch
     assert rows[0][0] == 1 and rows[-1][0] == 8 and rows[-1][9] > 0 and 0.0 <= rows[-1][10] <= rows[-1][11] <= 1.0
     assert len(open(tmp_path / "results_train.csv").read().strip().splitlines()) == 9
+
+
+@pytest.mark.gpu
+def test_cifar10_training_iterations_reduce_the_loss(tr):
+    """The cifar10 Chain (construct.jl:212-227) at a reduced size, trained on one fixed synthetic batch through the
+    C-ABI calls only: the cross-entropy goes down, the BatchNorm running statistics move, NFE is reported."""
+    import torch
+    t = tr.Cifar10ODETrainer(hidden=16, image=16, lr=3e-3, scheduler="constant", w_reg_start=1.0, w_reg_end=0.1,
+                             total_steps=10, abstol=1e-3, reltol=1e-3, seed=0)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.randn((32, 3, 16, 16), device="cuda", generator=g)
+    y = torch.randint(0, 10, (32,), device="cuda", generator=g, dtype=torch.int32)
+    r0 = t.st["model"]["running"].copy()
+    rows = [t.train_step(x, y) for _ in range(8)]
+    ce = [r[6] for r in rows]
+    assert all(np.isfinite(ce)) and ce[-1] < ce[0] - 0.05, ce
+    assert rows[-1][9] > 0 and 0.0 <= rows[-1][10] <= rows[-1][11] <= 1.0
+    r1 = t.st["model"]["running"]
+    r1 = r1.cpu().numpy() if hasattr(r1, "cpu") else np.asarray(r1)
+    assert np.abs(r1 - r0).max() > 1e-3
+    assert float((t.bn_state["running"][:8]).abs().max()) > 0
