@@ -793,7 +793,12 @@ def run_cifar10(args):
                       "gpu_launches": int(info["launches"] * args.steps), "clocks": clk,
                       "roofline": {"bound": "tensor", "kernel": "one f evaluation: conv3x3_kernel x 3 (FP32 SIMT direct convolution, "
                                    "not yet on the tensor cores) + bn_finalize x 2", "achieved": ach, "peak": tf32_peak,
-                                   "unit": "TFLOP/s", "frac": ach / tf32_peak, "traffic": None, "us_per_feval": us_f,
+                                   "unit": "TFLOP/s", "frac": ach / tf32_peak,
+                                   # dram read + write of the three convolutions of one evaluation at batch 256, ncu --set full
+                                   # (profiles/r1_cifar10_conv_ncu_full.txt); algorithmic: u in, z1 / z2 out and in, du out
+                                   "traffic": (259.0e6 if B == 256 else None),
+                                   "algorithmic_bytes_per_feval": 4.0 * 1024 * B * (8 + 64 + 64 + 64 + 64 + 8),
+                                   "us_per_feval": us_f,
                                    "peak_source": peaks["source"] + " (bf16 burst / 2 = TF32 dense)"},
                       "cpu_baseline": cpu}))
 
