@@ -439,6 +439,27 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(float* g, const float
                                                            const float* stat, const float* coef, int act, int C,
                                                            size_t HW, size_t n, const int* done) {
   if (done && *done) return;
+  // HW is a multiple of 4 (width % 4 == 0) and the buffers are 16-byte aligned: one float4 never straddles a channel
+  const bool vec = ((HW & 3) == 0) && ((((uintptr_t)g) & 15) == 0) && ((((uintptr_t)z) & 15) == 0);
+  if (vec) {
+    const size_t n4 = n >> 2, hw4 = HW >> 2;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+      const int c = (int)((i / hw4) % C);
+      const float4 zz = __ldcg(reinterpret_cast<const float4*>(z) + i);
+      float4 gg = reinterpret_cast<float4*>(g)[i];
+      if (coef) {
+        const float a = ab[c], b = ab[C + c], mean = stat[c], invstd = stat[C + c], m1 = coef[c], m2 = coef[C + c];
+        gg.x = a * (gg.x * lr_dact(act, fmaf(a, zz.x, b)) - m1 - (zz.x - mean) * invstd * m2);
+        gg.y = a * (gg.y * lr_dact(act, fmaf(a, zz.y, b)) - m1 - (zz.y - mean) * invstd * m2);
+        gg.z = a * (gg.z * lr_dact(act, fmaf(a, zz.z, b)) - m1 - (zz.z - mean) * invstd * m2);
+        gg.w = a * (gg.w * lr_dact(act, fmaf(a, zz.w, b)) - m1 - (zz.w - mean) * invstd * m2);
+      } else {
+        gg.x *= lr_dact(act, zz.x); gg.y *= lr_dact(act, zz.y); gg.z *= lr_dact(act, zz.z); gg.w *= lr_dact(act, zz.w);
+      }
+      reinterpret_cast<float4*>(g)[i] = gg;
+    }
+    return;
+  }
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const int c = (int)((i / HW) % C);
     const float zz = z[i];
