@@ -41,18 +41,44 @@ def _sources():
     return out
 
 
+def _deps(path, seen=None):
+    """The file and every quoted #include it reaches (object files are rebuilt only when these change)."""
+    seen = seen if seen is not None else set()
+    if path in seen or not os.path.exists(path):
+        return seen
+    seen.add(path)
+    for line in open(path, errors="ignore"):
+        line = line.strip()
+        if line.startswith("#include \""):
+            inc = line.split("\"")[1]
+            _deps(os.path.normpath(os.path.join(os.path.dirname(path), inc)), seen)
+    return seen
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     srcs = _sources()
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    if force or not _newer(LIB, srcs):
-        cus = [s for s in srcs if s.endswith(".cu")]
-        cmd = [nvcc, *NVCC_FLAGS, "-o", LIB, *cus, "-lcuda"]
-        if os.environ.get("LRNDE_TRACE"):
-            cmd.insert(1, "-DLRNDE_UMMA_TRACE")
-        if verbose:
-            cmd.insert(1, "-Xptxas")
-            cmd.insert(2, "-v")
-        subprocess.run(cmd, check=True, cwd=CSRC)
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    cus = [s for s in srcs if s.endswith(".cu")]
+    flags = [f for f in NVCC_FLAGS if f != "-shared"]
+    if os.environ.get("LRNDE_TRACE"):
+        flags.append("-DLRNDE_UMMA_TRACE")
+    if os.environ.get("LRNDE_WATCHDOG"):
+        flags.append("-DLRNDE_WATCHDOG")
+    if verbose:
+        flags += ["-Xptxas", "-v"]
+    procs, objs = [], []
+    for cu in cus:  # one translation unit per .cu, compiled in parallel
+        obj = os.path.join(objdir, os.path.basename(cu)[:-3] + ".o")
+        objs.append(obj)
+        if force or not _newer(obj, sorted(_deps(cu)) + [os.path.abspath(__file__)]):
+            procs.append((cu, subprocess.Popen([nvcc, *flags, "-c", "-o", obj, cu], cwd=CSRC)))
+    failed = [cu for cu, pr in procs if pr.wait() != 0]
+    if failed:
+        raise subprocess.CalledProcessError(1, "nvcc " + " ".join(failed))
+    if force or procs or not _newer(LIB, objs):
+        subprocess.run([nvcc, "-shared", "-o", LIB, *objs, "-lcuda"], check=True, cwd=CSRC)
     if force or not _newer(HOSTCHECK, srcs):
         cpps = [s for s in srcs if s.endswith(".cpp")]
         cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-o", HOSTCHECK, *cpps]

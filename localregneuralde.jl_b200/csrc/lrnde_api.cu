@@ -21,6 +21,7 @@
 #include "lrnde_umma.cuh"
 #include "lrnde_smem_mlp.cuh"
 #include "lrnde_conv.cuh"
+#include "lrnde_fused.h"
 
 // ------------------------------------------------------------------------------------------
 // errors
@@ -555,6 +556,8 @@ struct MlpEval {
   float* delta[2] = {nullptr, nullptr};
   float* part = nullptr;
   std::unique_ptr<ConvEval> conv;  // conv dynamics: every call below is forwarded
+  std::unique_ptr<FusedEngine> fe; // latent-space engine (lrnde_fused.h): forward attempts of 2-layer TD-MLPs
+  float* packW1x = nullptr;        // images of W1[:, :D] alone: Z(x) = W1[:, :D] x
   std::vector<int> wS, wChunk;    // SIMT weight-gradient split
   std::vector<int> uS, uChunk;    // tcgen05 weight-gradient split (0 = layer not eligible)
 
@@ -573,6 +576,11 @@ struct MlpEval {
     use_lean = (getenv("LRNDE_NO_LEAN") == nullptr);
     use_wide = (getenv("LRNDE_NO_WIDE") == nullptr);
     passes = (precision == LRNDE_PREC_TF32) ? 1 : 3;
+    if (use_umma && !vjp && FusedEngine::eligible(m) && !getenv("LRNDE_NO_FUSED")) {
+      fe = std::make_unique<FusedEngine>(ctx, m, ps, B, passes);
+      packW1x = (float*)ctx->alloc(sizeof(float) * 2 * umma::kAChunkFloats * umma::kReplicas *
+                                   (size_t)tiles_m(m->layers[0].out) * chunks_k(m->layers[0].in));
+    }
     act.assign(L, nullptr);
     packW.assign(L, nullptr);
     packWT.assign(L, nullptr);
@@ -637,6 +645,7 @@ struct MlpEval {
     ctx->release(delta[1]);
     ctx->release(part);
     ctx->release(s_gpart);
+    ctx->release(packW1x);
   }
 
   // once per call: transposed weights for the data-gradient GEMMs, and (tcgen05 path) the
@@ -695,6 +704,13 @@ struct MlpEval {
   void prepare() {
     if (conv) { conv->prepare(); return; }
     if (use_small) return;
+    if (fe) {
+      fe->prepare();
+      const LayerInfo& L1 = m->layers[0];
+      umma::pack_weights_kernel<<<dim3(tiles_m(L1.out) * chunks_k(L1.in), umma::kReplicas), 256, 0, ctx->stream>>>(
+          ps + L1.w_off, L1.out, L1.out, L1.in, chunks_k(L1.in), packW1x, passes);
+      LR_COUNT(ctx);
+    }
     for (size_t l = 0; l < m->layers.size(); ++l) {
       const LayerInfo& Li = m->layers[l];
       if (with_vjp) {
@@ -799,6 +815,18 @@ struct MlpEval {
 #undef LR_LAUNCH_DENSE
 #undef LR_LAUNCH_WIDE
     LR_COUNT(ctx);
+  }
+
+  // z[B][LR_ZROW] <- W1[:, :D] u   (the latent image of a state array, lrnde_fused.h)
+  void latent_of(const float* u, float* z) {
+    const LayerInfo& L1 = m->layers[0];
+    DenseP p;
+    memset(&p, 0, sizeof(p));
+    p.A = ps + L1.w_off; p.lda = L1.out; p.M = L1.out; p.K = L1.in; p.td = 0; p.bias = 0;
+    p.X = u; p.ldx = L1.in; p.N = (int)B;
+    p.Y = z; p.ldy = LR_ZROW; p.act = ACT_IDENTITY; p.dact = -1; p.out_scale = 1.0f;
+    dense(p, packW1x);
+    LR_CHECK_LAUNCH();
   }
 
   DenseP layer_fwd(int l, const LinComb* in, const float* xplain) const {
@@ -987,6 +1015,7 @@ struct Solver {
   double* partials = nullptr;
   unsigned int* counters = nullptr;
   float* muglob = nullptr;
+  float* ztape = nullptr;
   cudaGraph_t while_graph = nullptr, body_graph = nullptr;
   cudaGraphExec_t while_exec = nullptr, body_exec = nullptr;
   long body_nodes = 0;
@@ -1032,6 +1061,14 @@ struct Solver {
     ctx->release(partials);
     ctx->release(counters);
     ctx->release(muglob);
+    ctx->release(ztape);
+  }
+
+  // latent tape of the fused engine: one [B][LR_ZROW] image per tape array
+  void enable_latent(size_t zlen) {
+    ztape = (float*)ctx->alloc(sizeof(float) * 7 * zlen * (size_t)h.cap);
+    h.ztape = ztape;
+    h.zlen = zlen;
   }
 
   // adjoint in a data-parallel group: buffers of the mu-vector exchange
@@ -1279,6 +1316,15 @@ static void lr_grow_tape(Solver& S) {
   S.ts = nts;
   S.h.tape = nt;
   S.h.ts = nts;
+  if (S.ztape) {
+    float* nz = (float*)ctx->alloc(sizeof(float) * 7 * S.h.zlen * (size_t)newcap);
+    LR_CUDA(cudaMemcpyAsync(nz, S.ztape, sizeof(float) * 7 * S.h.zlen * (size_t)(S.h.slot + 1), cudaMemcpyDeviceToDevice, st));
+    LR_CUDA(cudaStreamSynchronize(st));
+    ctx->release(S.ztape);
+    S.ztape = nz;
+    S.h.ztape = nz;
+    LR_CUDA(cudaMemcpyAsync(&S.dev->ztape, &S.h.ztape, sizeof(float*), cudaMemcpyHostToDevice, st));
+  }
   S.h.cap = newcap;
   // patch the three fields in the device image
   LR_CUDA(cudaMemcpyAsync(&S.dev->tape, &S.h.tape, sizeof(float*), cudaMemcpyHostToDevice, st));
@@ -1385,6 +1431,19 @@ extern "C" int lrnde_dynamics_eval(lrnde_ctx* ctx, const lrnde_model* m, const l
   ev.prepare();
   DevBuf dstate(ctx, ev.conv ? std::max<int64_t>(1, ev.conv->nstate) : 1);
   if (ev.conv) ev.conv->attach_state(o, dstate.p);
+  if (ev.fe) {   // the same two kernels a solve uses for f(u0, t0): Z(u) by the layer-1 GEMM, then chain + kgemm
+    Solver tmp(ctx, DB, DB, 2, 1, 1);
+    tmp.init_ctrl(t, t + 1.0f, t + 1.0f, 10, 0, 1e-6f, 1e-6f);
+    tmp.enable_latent(ev.fe->zlen());
+    tmp.upload();
+    LR_CUDA(cudaMemcpyAsync(tmp.tape, ud, 4 * DB, cudaMemcpyDeviceToDevice, st));
+    ev.latent_of(tmp.tape, tmp.ztape);
+    k1_desc_kernel<<<1, 32, 0, st>>>(tmp.dev);
+    LR_COUNT(ctx);
+    ev.fe->eval(tmp.dev, &tmp.dev->st[6], nullptr, nullptr, 1);
+    LR_CUDA(cudaMemcpyAsync(outd, lr_slot_k(&tmp.h, 0, 1), 4 * DB, cudaMemcpyDeviceToDevice, st));
+    LR_CUDA(cudaStreamSynchronize(st));
+  } else
   ev.forward((const LinComb*)ddesc.p, nullptr);
   if (ev.conv) ev.conv->return_state(o);
   if (host) LR_CUDA(cudaMemcpyAsync(du, outd, 4 * DB, cudaMemcpyDeviceToHost, st));
@@ -1490,10 +1549,25 @@ extern "C" int lrnde_ode_forward(lrnde_ctx* ctx, const lrnde_model* m, const lrn
       LR_CUDA(cudaMemcpyAsync(T->bn_state, used, 4 * ev.conv->nstate, cudaMemcpyDeviceToDevice, st));
   }
   const long tq3 = lr_now_us();
+  // latent-space engine (lrnde_fused.h): stage chain in H dimensions + one GEMM per attempt for k_2..k_7
+  FusedEngine* fe = ev.fe.get();
+  const int write_z = 0;   // Z(k_2..k_6) are not read back by anything yet (the adjoint interpolates the k's)
+  if (fe) {
+    F.enable_latent(fe->zlen());
+    ev.latent_of(F.tape, F.ztape);
+  }
   auto eval = [&](const LinComb* in, const LinComb*, const int* done, const LinComb* out, bool side) {
-    ev.forward(in, done, out, side);
+    if (fe) fe->eval(F.dev, in, out, done, 1);
+    else ev.forward(in, done, out, side);
   };
-  F.body = [&]() { lr_step_body(F, eval, /*fuse_unew=*/true); };
+  F.body = [&]() {
+    if (fe) {
+      fe->step(F.dev, write_z);
+      controller_kernel<<<1, 32, 0, st>>>(F.dev);
+      LR_COUNT(ctx);
+      LR_CHECK_LAUNCH();
+    } else lr_step_body(F, eval, /*fuse_unew=*/true);
+  };
   F.build_graphs(o->loop_mode);
   F.upload();
   const long t_start = lr_now_us();
@@ -1598,17 +1672,27 @@ extern "C" int lrnde_ode_forward(lrnde_ctx* ctx, const lrnde_model* m, const lrn
     Solver& R = *T->reg;
     if (ctx->nranks > 1) R.h.total_len = F.h.total_len;
     R.init_ctrl(t1, o->t2, o->t2, o->maxiters, o->pow_mode, o->abstol, o->reltol);
+    if (fe) R.enable_latent(fe->zlen());
     R.upload();
     LinComb u1 = lr_host_interp(F, T->fts, std::min(t1, t_last));
     DevBuf dd(ctx, sizeof(LinComb) / 4 + 1);
     LR_CUDA(cudaMemcpyAsync(dd.p, &u1, sizeof(LinComb), cudaMemcpyHostToDevice, st));
     lincomb_kernel<<<lr_ew_blocks(DB), 256, 0, st>>>((const LinComb*)dd.p, R.tape, DB, nullptr);
     LR_COUNT(ctx);
-    lr_solver_start(R, eval, 0);
-    for (int j = 0; j < 5; ++j) eval(&R.dev->st[j], nullptr, &R.dev->failed, nullptr, false);
-    eval(&R.dev->st[5], nullptr, &R.dev->failed, &R.dev->st[6], true);   // u and k7 in one pass
-    err_norm_kernel<<<LR_ERR_BLOCKS, 256, 0, st>>>(R.dev);
-    LR_COUNT(ctx);
+    if (fe) {
+      ev.latent_of(R.tape, R.ztape);
+      auto evalR = [&](const LinComb* in, const LinComb*, const int* done, const LinComb* out, bool) {
+        fe->eval(R.dev, in, out, done, 1);
+      };
+      lr_solver_start(R, evalR, 0);
+      fe->step(R.dev, 0);   // the six stages, u, k7 and the residual partial sums (perform_step.jl:10-27)
+    } else {
+      lr_solver_start(R, eval, 0);
+      for (int j = 0; j < 5; ++j) eval(&R.dev->st[j], nullptr, &R.dev->failed, nullptr, false);
+      eval(&R.dev->st[5], nullptr, &R.dev->failed, &R.dev->st[6], true);   // u and k7 in one pass
+      err_norm_kernel<<<LR_ERR_BLOCKS, 256, 0, st>>>(R.dev);
+      LR_COUNT(ctx);
+    }
     if (o->reg_type == LRNDE_REGTYPE_STIFFNESS) {
       reg_stiff_sums_kernel<<<LR_ERR_BLOCKS, 256, 0, st>>>(R.dev);
       LR_COUNT(ctx);

@@ -94,7 +94,16 @@ struct SolveDev {
   float* muglob;                 // [3][mu_len]: globally summed mu vectors of the current exchange
   unsigned int* mucounter;       // blocks-finished counter of mu_publish_kernel
   size_t mu_len;                 // P
+  // latent-space engine (lrnde_fused.cu): Z(x) = W1[:, :D] x for every array x of the tape, same slot layout
+  // ([B][LR_ZROW] floats per array)
+  float* ztape;
+  size_t zlen;
 };
+#define LR_ZROW 128
+// the latent image of a tape array (p must point at the start of an array of this solve's tape)
+__host__ __device__ inline float* lr_zof(const SolveDev* S, const float* p) {
+  return S->ztape + ((size_t)(p - S->tape) / S->len) * S->zlen;
+}
 
 __host__ __device__ inline float* lr_slot_u(const SolveDev* S, int s) {
   return S->tape + (size_t)s * 7 * S->len;

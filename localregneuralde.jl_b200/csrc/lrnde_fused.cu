@@ -1,0 +1,735 @@
+// Latent-space engine (see lrnde_fused.h): chain_kernel + kgemm_kernel, hand-written tcgen05 / TMEM / bulk-copy
+// code for sm_100a.  Reference arithmetic: src/perform_step.jl:10-27 (stages, u, utilde), :34-38 and :208-212
+// (residual, RMS), src/layers/common.jl:19-33 (TDChain time row), through the identities in the header.
+#include "lrnde_fused.h"
+
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "lrnde_act.cuh"
+#include "lrnde_tc.cuh"
+
+namespace fused {
+using namespace umma;
+
+constexpr int kNT = 64;                         // samples per tile
+constexpr int kEpiWarps = 8;                    // warps 2..9: compute / epilogue (two per TMEM lane quarter)
+constexpr int kThreads = 64 + 32 * kEpiWarps;   // warp 0: bulk copies, warp 1: tcgen05.mma issue
+constexpr int kPieceBytes = 2 * 128 * 128;      // kgemm ring stage: [hi | lo] of a 128-row x 32-float chunk
+constexpr int kTailBytes = 2 * 128 * 32;        // [hi | lo] of a 128-row x 8-float K-step
+
+// shared-memory matrix descriptors (cute::UMMA::SmemDescriptor), K-major:
+//   SWIZZLE_128B: rows of 128 B, 8-row atoms of 1024 B (SBO), 16-byte chunks XOR-ed with (row & 7)
+//   SWIZZLE_32B : rows of  32 B, 8-row atoms of  256 B (SBO), 16-byte halves XOR-ed with ((row >> 2) & 1)
+constexpr uint32_t kHi128 = (1024u >> 4) | (1u << 14) | (2u << 29);
+constexpr uint32_t kHi32 = (256u >> 4) | (1u << 14) | (6u << 29);
+
+template <int COLL>
+__device__ __forceinline__ void mma(uint32_t d_tmem, uint32_t a_lo32, uint32_t b_lo32, uint32_t hi32, uint32_t idesc,
+                                    uint32_t accumulate) {
+#define LR_FMMA(QUAL)                                                                                \
+  asm volatile(                                                                                      \
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"                                                \
+      "setp.ne.b32 p, %4, 0;\n\t"                                                                    \
+      "mov.b64 da, {%1, %5};\n\t"                                                                    \
+      "mov.b64 db, {%2, %5};\n\t"                                                                    \
+      "tcgen05.mma.cta_group::1.kind::tf32" QUAL " [%0], da, db, %3, p;\n\t}"                         \
+      ::"r"(d_tmem), "r"(a_lo32), "r"(b_lo32), "r"(idesc), "r"(accumulate), "r"(hi32)                \
+      : "memory")
+  if (COLL == 1) LR_FMMA(".collector::a::fill");
+  else if (COLL == 2) LR_FMMA(".collector::a::lastuse");
+  else LR_FMMA("");
+#undef LR_FMMA
+}
+
+// one K-step (8 tf32) of D += A B^T in 3xTF32 (A_lo B_hi + A_hi B_lo + A_hi B_hi) or plain TF32
+__device__ __forceinline__ void mma_kstep(uint32_t d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
+                                          uint32_t hi32, uint32_t idesc, uint32_t acc_first, int passes) {
+  if (passes == 3) {
+    mma<0>(d, a_lo, b_hi, hi32, idesc, acc_first);
+    mma<1>(d, a_hi, b_lo, hi32, idesc, 1u);
+    mma<2>(d, a_hi, b_hi, hi32, idesc, 1u);
+  } else {
+    mma<0>(d, a_hi, b_hi, hi32, idesc, acc_first);
+  }
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, "
+      "%13, %14, %15}, [%16];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, "
+      "%14, %15, %16};"
+      ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+        "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])),
+        "r"(__float_as_uint(v[7])), "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])),
+        "r"(__float_as_uint(v[11])), "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])),
+        "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void bulk_s2g(void* gdst, const void* ssrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+
+// byte offset of element (row r, column k) inside the hi image of an R-row operand: nfull SWIZZLE_128B chunks of
+// 32 floats followed by SWIZZLE_32B K-steps of 8 floats
+__host__ __device__ inline uint32_t img_off(int R, int nfull, int r, int k) {
+  if (k < nfull * 32) {
+    const int c = k >> 5, kk = k & 31;
+    return (uint32_t)(c * R * 128 + (r >> 3) * 1024 + (r & 7) * 128 + (((kk >> 2) ^ (r & 7)) << 4) + (kk & 3) * 4);
+  }
+  const int s = (k - nfull * 32) >> 3, kk = k & 7;
+  return (uint32_t)(nfull * R * 128 + s * R * 32 + r * 32 + ((((kk >> 2) & 1) ^ ((r >> 2) & 1)) << 4) + (kk & 3) * 4);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// weight images (once per call: the parameters change every training iteration)
+// ---------------------------------------------------------------------------------------------------------
+// Mz = W1[:, :D] * W2a  ([H x Kaug], accumulated in double), as the 128-row A operand of the chain kernel
+__global__ void mz_pack_kernel(const float* __restrict__ W1, const float* __restrict__ W2a, int D, int H, int Kaug,
+                               int nfull, float* __restrict__ img, uint32_t img_bytes, int passes) {
+  const int r = threadIdx.x, k = blockIdx.x;
+  float v = 0.0f;
+  if (r < H && k < Kaug) {
+    double acc = 0.0;
+    for (int d = 0; d < D; ++d) acc += (double)W1[(size_t)d * H + r] * (double)W2a[(size_t)k * D + d];
+    v = (float)acc;
+  }
+  const float hi = (passes == 1) ? v : tf32_rna(v);
+  const float lo = (passes == 1) ? 0.0f : tf32_rna(v - hi);
+  const uint32_t o = img_off(128, nfull, r, k);
+  *reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(img) + o) = hi;
+  *reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(img) + img_bytes + o) = lo;
+}
+// W2a = [W2 | w2t | b2] split into n_mt tiles of MT output features: the A operands of the kgemm kernel
+__global__ void w2_pack_kernel(const float* __restrict__ W2a, int D, int Kaug, int nfull, int MT, float* __restrict__ img,
+                               uint32_t img_bytes, int passes) {
+  const int r = threadIdx.x, k = blockIdx.x, mt = blockIdx.y;
+  if (r >= MT) return;
+  const int mrow = mt * MT + r;
+  const float v = (mrow < D && k < Kaug) ? W2a[(size_t)k * D + mrow] : 0.0f;
+  const float hi = (passes == 1) ? v : tf32_rna(v);
+  const float lo = (passes == 1) ? 0.0f : tf32_rna(v - hi);
+  uint8_t* base = reinterpret_cast<uint8_t*>(img) + (size_t)mt * 2 * img_bytes;
+  const uint32_t o = img_off(MT, nfull, r, k);
+  *reinterpret_cast<float*>(base + o) = hi;
+  *reinterpret_cast<float*>(base + img_bytes + o) = lo;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// (1) chain kernel: the stages of one attempt as a recurrence in latent space, one CTA per 64 samples
+// ---------------------------------------------------------------------------------------------------------
+struct ChainP {
+  SolveDev* S;
+  const LinComb* single;      // nullptr: the six stages of S->st[0..6]; else: one evaluation of this descriptor
+  const LinComb* single_out;  // single mode: descriptor whose dst receives the result (nullptr: single->dst)
+  const int* done;
+  const float* Mimg;
+  uint32_t imgM;
+  const float* w1t;  // layer-1 time column (nullptr without TDChain)
+  const float* b1;
+  float* hbuf;
+  uint32_t pair_bytes;
+  int B, H, td, act, KS, nfull, ntail, passes, nbuf, write_z;
+};
+
+__global__ void __launch_bounds__(kThreads, 1) chain_kernel(ChainP p) {
+  if (p.done && *p.done) return;
+  if (!p.single && p.S->done) return;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t abar, bfull[2], bfree[2], zdone;
+  __shared__ uint32_t tmem_slot;
+  __shared__ LinComb sd[7];
+  __shared__ float* s_tape;
+  __shared__ float* s_ztape;
+  __shared__ size_t s_len, s_zlen;
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * kNT;
+  const int nst = p.single ? 1 : 6;
+  const uint32_t tileB = (uint32_t)kNT * p.KS * 32 * 2;
+  uint8_t* smA = smem;
+  uint8_t* smB = smem + 2 * (size_t)p.imgM;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&abar, 1u);
+    for (int b = 0; b < 2; ++b) { mbar_init(&bfull[b], (uint32_t)kEpiWarps); mbar_init(&bfree[b], 1u); }
+    mbar_init(&zdone, 1u);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (p.single) sd[0] = *p.single;
+    else for (int j = 0; j < 7; ++j) sd[j] = p.S->st[j];
+    if (p.single) sd[1] = p.single_out ? *p.single_out : *p.single;
+    s_tape = p.S->tape; s_ztape = p.S->ztape; s_len = p.S->len; s_zlen = p.S->zlen;
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  auto zof = [&](const float* ptr) -> float* { return s_ztape + ((size_t)(ptr - s_tape) / s_len) * s_zlen; };
+
+  if (warp == 0) {
+    // ---------------- Mz images in, operand images out (one elected lane; converged warp)
+    if (elect_one_sync()) {
+      mbar_arrive_expect_tx(&abar, 2 * p.imgM);
+      bulk_g2s(smA, p.Mimg, 2 * p.imgM, &abar);
+    }
+    __syncwarp();
+    for (int st = 0; st < nst; ++st) {
+      const int b = st % p.nbuf;
+      mbar_wait(&bfull[b], (uint32_t)((st / p.nbuf) & 1));
+      if (elect_one_sync()) {
+        // stage `st` of the attempt = half (st & 1) of operand pair (st >> 1) of this tile (kgemm layout: 128 rows)
+        const int pair = p.single ? 0 : (st >> 1), half = p.single ? 0 : (st & 1);
+        uint8_t* g = reinterpret_cast<uint8_t*>(p.hbuf) + ((size_t)blockIdx.x * 3 + pair) * p.pair_bytes;
+        const uint8_t* s = smB + (size_t)b * tileB;
+        for (int c = 0; c < p.nfull; ++c)
+          for (int lo = 0; lo < 2; ++lo)
+            bulk_s2g(g + (size_t)c * kPieceBytes + lo * (128 * 128) + half * (kNT * 128),
+                     s + (size_t)c * (2 * kNT * 128) + lo * (kNT * 128), kNT * 128);
+        for (int t = 0; t < p.ntail; ++t)
+          for (int lo = 0; lo < 2; ++lo)
+            bulk_s2g(g + (size_t)p.nfull * kPieceBytes + (size_t)t * kTailBytes + lo * (128 * 32) + half * (kNT * 32),
+                     s + (size_t)p.nfull * (2 * kNT * 128) + (size_t)t * (2 * kNT * 32) + lo * (kNT * 32), kNT * 32);
+        bulk_commit();
+        bulk_wait_read0();
+        mbar_arrive(&bfree[b]);
+      }
+      __syncwarp();
+    }
+    if (elect_one_sync()) bulk_wait0();
+    __syncwarp();
+  } else if (warp == 1) {
+    // ---------------- tcgen05.mma issue: Z(k_j) = Mz [h_j ; t_j ; 1]   (M = 128 latent rows x N = 64 samples)
+    constexpr uint32_t idesc = make_idesc(128, kNT);
+    mbar_wait(&abar, 0);
+    const uint32_t a0 = smem_u32(smA);
+    for (int st = 0; st < nst; ++st) {
+      const int b = st % p.nbuf;
+      mbar_wait(&bfull[b], (uint32_t)((st / p.nbuf) & 1));
+      tc_fence_after();
+      const uint32_t b0 = smem_u32(smB + (size_t)b * tileB);
+      const uint32_t d = tmem_base + (uint32_t)((p.single ? 7 : 2 + st) * kNT);
+      if (elect_one_sync()) {
+        uint32_t first = 0u;
+        for (int c = 0; c < p.nfull; ++c) {
+          const uint32_t ah = desc_lo(a0 + c * (128 * 128)), al = desc_lo(a0 + p.imgM + c * (128 * 128));
+          const uint32_t bh = desc_lo(b0 + c * (2 * kNT * 128)), bl = desc_lo(b0 + c * (2 * kNT * 128) + kNT * 128);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            mma_kstep(d, ah + 2 * k, al + 2 * k, bh + 2 * k, bl + 2 * k, kHi128, idesc, first, p.passes);
+            first = 1u;
+          }
+        }
+        for (int t = 0; t < p.ntail; ++t) {
+          const uint32_t ao = p.nfull * (128 * 128) + t * (128 * 32);
+          const uint32_t bo = p.nfull * (2 * kNT * 128) + t * (2 * kNT * 32);
+          mma_kstep(d, desc_lo(a0 + ao), desc_lo(a0 + p.imgM + ao), desc_lo(b0 + bo), desc_lo(b0 + bo + kNT * 32), kHi32,
+                    idesc, first, p.passes);
+          first = 1u;
+        }
+        mma_commit(&zdone);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ---------------- stage arithmetic: lane = latent row, registers = samples
+    const int q = warp & 3, cg = (warp - 2) >> 2;
+    const int hrow = q * 32 + lane;
+    const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
+    const int col0 = cg * 32;
+    const bool rowv = hrow < p.H;
+    const float w1t = (p.td && rowv && p.w1t) ? p.w1t[hrow] : 0.0f;
+    const float b1 = rowv ? p.b1[hrow] : 0.0f;
+    // inputs computed earlier: Z(uprev) -> slot 0, Z(sources) -> slots 1..
+    const int next = p.single ? 1 + sd[0].n : 2;
+    if (p.single && sd[0].n > 6) asm volatile("trap;");
+    for (int e = 0; e < next; ++e) {
+      const float* src = (e == 0) ? sd[0].base : sd[0].src[e - 1];
+      const float* zp = src ? zof(src) : nullptr;
+#pragma unroll
+      for (int blk = 0; blk < 2; ++blk) {
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int n = n0 + col0 + blk * 16 + i;
+          v[i] = (zp && rowv && n < p.B) ? __ldcg(zp + (size_t)n * LR_ZROW + hrow) : 0.0f;
+        }
+        tmem_st16(tlane + (uint32_t)(e * kNT + col0 + blk * 16), v);
+      }
+    }
+    tmem_st_wait();
+    // operand-image position of (sample row, k = hrow): chunk q of the tile when hrow is inside a full chunk
+    const bool in_full = hrow < p.nfull * 32;
+    const bool in_img = hrow < p.KS * 8;
+    for (int st = 0; st < nst; ++st) {
+      const int b = st % p.nbuf;
+      const LinComb& d = sd[st];
+      const bool last_full = (!p.single && st == 5);
+      const float tstage = last_full ? sd[6].t : d.t;
+      const int nsrc = d.n;
+      float* zlin = last_full ? zof(d.dst) : nullptr;   // Z(u_{n+1}) = Z(uprev) + dt * sum a_7i Z(k_i)
+      if (st >= p.nbuf) mbar_wait(&bfree[b], (uint32_t)(((st / p.nbuf) - 1) & 1));
+      uint8_t* tile = smB + (size_t)b * tileB;
+#pragma unroll 1
+      for (int blk = 0; blk < 2; ++blk) {
+        const int col = col0 + blk * 16;
+        float inner[16], v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) inner[i] = 0.0f;
+        for (int s = 0; s < nsrc; ++s) {
+          tmem_ld16(tlane + (uint32_t)((1 + s) * kNT + col), v);
+          const float cf = d.coef[s];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) inner[i] = fmaf(cf, v[i], inner[i]);
+        }
+        tmem_ld16(tlane + (uint32_t)col, v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int row = col + i;          // sample row of the operand tile
+          const int n = n0 + row;
+          float pre = nsrc ? fmaf(d.scale, inner[i], v[i]) : v[i];
+          if (zlin && rowv && n < p.B) zlin[(size_t)n * LR_ZROW + hrow] = pre;
+          float x = p.td ? fmaf(w1t, tstage, pre) : pre;
+          x += b1;
+          float h = lr_act(p.act, x);
+          if (!rowv) h = (p.td && hrow == p.H) ? tstage : ((hrow == p.H + p.td) ? 1.0f : 0.0f);
+          if (in_img) {
+            float hi, lo;
+            if (p.passes == 3) { hi = tf32_rna(h); lo = tf32_rna(h - hi); }
+            else { hi = h; lo = 0.0f; }
+            uint32_t o;
+            if (in_full)
+              o = (uint32_t)(q * (2 * kNT * 128) + (row >> 3) * 1024 + (row & 7) * 128 + (((lane >> 2) ^ (row & 7)) << 4) +
+                             (lane & 3) * 4);
+            else {
+              const int kt = hrow - p.nfull * 32, t = kt >> 3, kk = kt & 7;
+              o = (uint32_t)(p.nfull * (2 * kNT * 128) + t * (2 * kNT * 32) + row * 32 +
+                             ((((kk >> 2) & 1) ^ ((row >> 2) & 1)) << 4) + (kk & 3) * 4);
+            }
+            const uint32_t lo_off = in_full ? (uint32_t)(kNT * 128) : (uint32_t)(kNT * 32);
+            *reinterpret_cast<float*>(tile + o) = hi;
+            *reinterpret_cast<float*>(tile + o + lo_off) = lo;
+          }
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bfull[b]);
+      mbar_wait(&zdone, (uint32_t)(st & 1));
+      tc_fence_after();
+      // Z(k_j) to the latent tape
+      const float* kdst = p.single ? sd[1].dst : (last_full ? sd[6].dst : d.dst);
+      if (p.write_z || last_full) {
+        float* zo = zof(kdst);
+        const int slot = p.single ? 7 : 2 + st;
+#pragma unroll 1
+        for (int blk = 0; blk < 2; ++blk) {
+          float v[16];
+          tmem_ld16(tlane + (uint32_t)(slot * kNT + col0 + blk * 16), v);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int n = n0 + col0 + blk * 16 + i;
+            if (rowv && n < p.B) zo[(size_t)n * LR_ZROW + hrow] = v[i];
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// (2) kgemm kernel: k_j = W2a [h_j ; t_j ; 1] for all stages of the attempt, epilogue = tape + u_{n+1} + residual
+// ---------------------------------------------------------------------------------------------------------
+struct KgemmP {
+  SolveDev* S;
+  const LinComb* single;
+  const LinComb* single_out;
+  const int* done;
+  const float* W2img;
+  uint32_t imgW;
+  const float* hbuf;
+  uint32_t pair_bytes;
+  int B, D, MT, n_mt, KS, nfull, ntail, passes, ntiles, nclusters, ring;
+};
+
+__global__ void __launch_bounds__(kThreads, 1) kgemm_kernel(KgemmP p) {
+  if (p.done && *p.done) return;
+  if (!p.single && p.S->done) return;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t abar, full_bar[8], empty_bar[8], acc_full[2], epi_done[2];
+  __shared__ uint32_t tmem_slot;
+  __shared__ LinComb s_err, s_un;
+  __shared__ double s_red[kEpiWarps];
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const uint32_t csize = cluster_nctarank();
+  const uint32_t crank = (csize > 1) ? cluster_ctarank() : 0u;
+  const uint16_t cmask = (uint16_t)((1u << csize) - 1u);
+  const int mt = (int)(blockIdx.x % (unsigned)p.n_mt);
+  const int cid = (int)(blockIdx.x / (unsigned)p.n_mt);
+  const int npairs = p.single ? 1 : 3;
+  const int npieces = p.nfull + p.ntail;
+  uint8_t* smA = smem;
+  uint8_t* smR = smem + 2 * (size_t)p.imgW;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&abar, 1u);
+    for (int s = 0; s < p.ring; ++s) { mbar_init(&full_bar[s], 1u); mbar_init(&empty_bar[s], csize); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1u); mbar_init(&epi_done[b], (uint32_t)kEpiWarps); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (p.single) { s_err = *p.single; s_un = p.single_out ? *p.single_out : *p.single; }
+    else { s_err = p.S->err; s_un = p.S->st[5]; }
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (csize > 1) cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    // ---------------- bulk copies: this tile's W2a images once, then the operand pieces of every unit (each CTA of
+    // the cluster fetches a slice and multicasts it: the CTAs of a cluster share the sample tile)
+    if (elect_one_sync()) {
+      mbar_arrive_expect_tx(&abar, 2 * p.imgW);
+      bulk_g2s(smA, reinterpret_cast<const uint8_t*>(p.W2img) + (size_t)mt * 2 * p.imgW, 2 * p.imgW, &abar);
+    }
+    __syncwarp();
+    int it = 0;
+    for (int T = cid; T < p.ntiles; T += p.nclusters) {
+      for (int pr = 0; pr < npairs; ++pr) {
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(p.hbuf) + ((size_t)T * 3 + pr) * p.pair_bytes;
+        for (int pc = 0; pc < npieces; ++pc, ++it) {
+          const int s = it % p.ring, ph = (it / p.ring) & 1;
+          mbar_wait(&empty_bar[s], (uint32_t)(ph ^ 1));
+          const uint32_t bytes = (pc < p.nfull) ? (uint32_t)kPieceBytes : (uint32_t)kTailBytes;
+          const size_t off = (pc < p.nfull) ? (size_t)pc * kPieceBytes : (size_t)p.nfull * kPieceBytes + (size_t)(pc - p.nfull) * kTailBytes;
+          uint8_t* dst = smR + (size_t)s * kPieceBytes;
+          if (elect_one_sync()) {
+            mbar_arrive_expect_tx(&full_bar[s], bytes);
+            if (csize > 1) {
+              const uint32_t sl = (((bytes + csize - 1) / csize) + 15u) & ~15u;
+              const uint32_t o = crank * sl;
+              if (o < bytes) bulk_g2s_mc(dst + o, src + off + o, min(sl, bytes - o), &full_bar[s], cmask);
+            } else {
+              bulk_g2s(dst, src + off, bytes, &full_bar[s]);
+            }
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------- tcgen05.mma issue: D[128 features x (2 stages x 64 samples)] per operand pair
+    const uint32_t idesc = p.single ? make_idesc(128, kNT) : make_idesc(128, 2 * kNT);
+    mbar_wait(&abar, 0);
+    const uint32_t a0 = smem_u32(smA);
+    const int R = p.MT;
+    int it = 0, u = 0;
+    for (int T = cid; T < p.ntiles; T += p.nclusters, ++u) {
+      for (int pr = 0; pr < npairs; ++pr) {
+        // TMEM pair slot and the unit whose epilogue must have drained it
+        const int slot = p.single ? ((2 * u) & 3) : ((3 * u + pr) & 3);
+        const int dep = (p.single || pr == 0) ? u - 2 : u - 1;
+        if (dep >= 0) { mbar_wait(&epi_done[dep & 1], (uint32_t)((dep >> 1) & 1)); tc_fence_after(); }
+        const uint32_t d = tmem_base + (uint32_t)(slot * 2 * kNT);
+        uint32_t first = 0u;
+        for (int pc = 0; pc < npieces; ++pc, ++it) {
+          const int s = it % p.ring, ph = (it / p.ring) & 1;
+          mbar_wait(&full_bar[s], (uint32_t)ph);
+          tc_fence_after();
+          const uint32_t b0 = smem_u32(smR + (size_t)s * kPieceBytes);
+          if (elect_one_sync()) {
+            if (pc < p.nfull) {
+              const uint32_t ah = desc_lo(a0 + pc * (R * 128)), al = desc_lo(a0 + p.imgW + pc * (R * 128));
+              const uint32_t bh = desc_lo(b0), bl = desc_lo(b0 + 128 * 128);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                mma_kstep(d, ah + 2 * k, al + 2 * k, bh + 2 * k, bl + 2 * k, kHi128, idesc, first, p.passes);
+                first = 1u;
+              }
+            } else {
+              const uint32_t ao = p.nfull * (R * 128) + (pc - p.nfull) * (R * 32);
+              mma_kstep(d, desc_lo(a0 + ao), desc_lo(a0 + p.imgW + ao), desc_lo(b0), desc_lo(b0 + 128 * 32), kHi32, idesc,
+                        first, p.passes);
+              first = 1u;
+            }
+            if (csize > 1) mma_commit_mc(&empty_bar[s], cmask);
+            else mma_commit(&empty_bar[s]);
+            if (pr == npairs - 1 && pc == npieces - 1) mma_commit(&acc_full[u & 1]);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    // ---------------- epilogue: lane = output feature (coalesced global access), registers = samples
+    const int q = warp & 3, cg = (warp - 2) >> 2;
+    const int mloc = q * 32 + lane;
+    const int m = mt * p.MT + mloc;
+    const bool mv = (mloc < p.MT) && (m < p.D);
+    const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
+    const float abstol = p.S->abstol, reltol = p.S->reltol;
+    double acc = 0.0;
+    int u = 0;
+    for (int T = cid; T < p.ntiles; T += p.nclusters, ++u) {
+      mbar_wait(&acc_full[u & 1], (uint32_t)((u >> 1) & 1));
+      tc_fence_after();
+#pragma unroll 1
+      for (int blk = 0; blk < 2; ++blk) {
+        const int c0 = cg * 32 + blk * 16;
+        const int nb = T * kNT + c0;
+        if (p.single) {
+          float v[16];
+          tmem_ld16(tlane + (uint32_t)(((2 * u) & 3) * 2 * kNT + c0), v);
+          float* out = s_un.dst;
+          if (mv) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (nb + i < p.B) out[(size_t)(nb + i) * p.D + m] = v[i];
+          }
+        } else {
+          float up[16], k1[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const bool ok = mv && (nb + i < p.B);
+            up[i] = ok ? __ldcg(s_err.base + (size_t)(nb + i) * p.D + m) : 0.0f;
+            k1[i] = ok ? __ldcg(s_err.src[0] + (size_t)(nb + i) * p.D + m) : 0.0f;
+          }
+          float un[16], ut[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) { un[i] = s_un.coef[0] * k1[i]; ut[i] = s_err.coef[0] * k1[i]; }
+#pragma unroll
+          for (int jj = 0; jj < 6; ++jj) {   // stage jj + 2
+            float v[16];
+            const int slot = (3 * u + (jj >> 1)) & 3;
+            tmem_ld16(tlane + (uint32_t)(slot * 2 * kNT + (jj & 1) * kNT + c0), v);
+            float* kout = const_cast<float*>(s_err.src[jj + 1]);
+            if (mv) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (nb + i < p.B) kout[(size_t)(nb + i) * p.D + m] = v[i];
+            }
+            if (jj < 5) {
+              const float ca = s_un.coef[jj + 1];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) un[i] = fmaf(ca, v[i], un[i]);
+            }
+            const float cb = s_err.coef[jj + 1];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) ut[i] = fmaf(cb, v[i], ut[i]);
+          }
+          float* uout = s_err.dst;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float unew = fmaf(s_un.scale, un[i], up[i]);
+            if (mv && nb + i < p.B) {
+              uout[(size_t)(nb + i) * p.D + m] = unew;
+              const float r = (s_err.scale * ut[i]) / (abstol + fmaxf(fabsf(up[i]), fabsf(unew)) * reltol);
+              acc += (double)(r * r);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&epi_done[u & 1]);
+    }
+    if (!p.single) {
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+      if (lane == 0) s_red[warp - 2] = acc;
+      asm volatile("bar.sync 1, %0;" ::"r"(kEpiWarps * 32) : "memory");
+      if (warp == 2 && lane == 0) {
+        double s = 0.0;
+        for (int w = 0; w < kEpiWarps; ++w) s += s_red[w];
+        p.S->partials[blockIdx.x] = s;
+        for (unsigned i = blockIdx.x + gridDim.x; i < (unsigned)LR_ERR_BLOCKS; i += gridDim.x) p.S->partials[i] = 0.0;
+      }
+    }
+  }
+  __syncthreads();
+  if (csize > 1) cluster_sync_all();   // peers may still multicast into this CTA / signal its barriers
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+}  // namespace fused
+
+// ---------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------
+#define LRF_COUNT(ctx) do { if ((ctx)->capturing) (ctx)->captured++; else (ctx)->launches++; } while (0)
+
+static size_t lrf_round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static bool lrf_shape(const lrnde_model* m, FusedShape* out) {
+  if (!m->conv.empty() || m->layers.size() != 2) return false;
+  if (m->input_act != ACT_IDENTITY) return false;
+  const LayerInfo& L1 = m->layers[0];
+  const LayerInfo& L2 = m->layers[1];
+  if (L2.act != ACT_IDENTITY) return false;
+  FusedShape s;
+  s.D = m->D; s.H = L1.out; s.td = m->td; s.act = L1.act;
+  s.Kaug = s.H + s.td + 1;
+  if (s.Kaug > 128) return false;
+  s.KS = (s.Kaug + 7) / 8;
+  s.nfull = s.KS / 4;
+  s.ntail = s.KS % 4;
+  s.n_mt = (s.D + 127) / 128;
+  s.MT = (int)lrf_round_up((size_t)(s.D + s.n_mt - 1) / s.n_mt, 16);
+  if (out) *out = s;
+  return true;
+}
+
+bool FusedEngine::eligible(const lrnde_model* m) { return lrf_shape(m, nullptr); }
+
+FusedEngine::FusedEngine(lrnde_ctx* c, const lrnde_model* mm, const float* p, int64_t b, int npasses)
+    : ctx(c), m(mm), ps(p), B(b), passes(npasses) {
+  lrf_shape(m, &sh);
+  ntiles = (int)((B + fused::kNT - 1) / fused::kNT);
+  imgM = lrf_round_up((size_t)128 * sh.KS * 32, 1024);
+  imgW = lrf_round_up((size_t)sh.MT * sh.KS * 32, 1024);
+  pair_bytes = (size_t)sh.nfull * fused::kPieceBytes + (size_t)sh.ntail * fused::kTailBytes;
+  nbuf = (2 * imgM + 2 * (size_t)fused::kNT * sh.KS * 64 + 2048 <= 226 * 1024) ? 2 : 1;
+  Mimg = (float*)ctx->alloc(2 * imgM);
+  W2img = (float*)ctx->alloc(2 * imgW * sh.n_mt);
+  hbuf = (float*)ctx->alloc((size_t)ntiles * 3 * pair_bytes);
+  // kgemm launch geometry: one cluster = the n_mt feature tiles of a sample tile (operand pieces multicast)
+  cluster = (sh.n_mt <= 8 && !getenv("LRNDE_FUSED_NO_CLUSTER")) ? sh.n_mt : 1;
+  const size_t smem_k = 2 * imgW + 4 * (size_t)fused::kPieceBytes + 1024;
+  const size_t smem_c = 2 * imgM + (size_t)nbuf * fused::kNT * sh.KS * 64 + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    LR_CUDA(cudaFuncSetAttribute(fused::chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    LR_CUDA(cudaFuncSetAttribute(fused::kgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    attr_set = true;
+  }
+  (void)smem_c;
+  int maxc = 0;
+  if (cluster > 1) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(cluster * 64);
+    cfg.blockDim = dim3(fused::kThreads);
+    cfg.dynamicSmemBytes = smem_k;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaError_t e = cudaOccupancyMaxActiveClusters(&maxc, fused::kgemm_kernel, &cfg);
+    if (e != cudaSuccess || maxc < 1) { cudaGetLastError(); cluster = 1; }
+  }
+  if (cluster == 1) maxc = 148 / sh.n_mt > 0 ? 148 / sh.n_mt : 1;
+  if (const char* e = getenv("LRNDE_FUSED_MAXC")) maxc = std::max(1, atoi(e));
+  const int rounds = (ntiles + maxc - 1) / maxc;
+  nclusters = (ntiles + rounds - 1) / rounds;
+}
+
+FusedEngine::~FusedEngine() {
+  ctx->release(Mimg);
+  ctx->release(W2img);
+  ctx->release(hbuf);
+}
+
+void FusedEngine::prepare() {
+  const LayerInfo& L1 = m->layers[0];
+  const LayerInfo& L2 = m->layers[1];
+  const float* W1 = ps + L1.w_off;
+  const float* W2a = ps + L2.w_off;   // [D x (H + td)] followed by the bias: one [D x Kaug] column-major block
+  fused::mz_pack_kernel<<<sh.KS * 8, 128, 0, ctx->stream>>>(W1, W2a, sh.D, sh.H, sh.Kaug, sh.nfull, Mimg, (uint32_t)imgM, passes);
+  LRF_COUNT(ctx);
+  fused::w2_pack_kernel<<<dim3(sh.KS * 8, sh.n_mt), 128, 0, ctx->stream>>>(W2a, sh.D, sh.Kaug, sh.nfull, sh.MT, W2img,
+                                                                         (uint32_t)imgW, passes);
+  LRF_COUNT(ctx);
+  LR_CUDA(cudaGetLastError());
+}
+
+static void lrf_launch(FusedEngine& E, SolveDev* S, const LinComb* single, const LinComb* single_out, const int* done,
+                       int write_z) {
+  const FusedShape& sh = E.sh;
+  const LayerInfo& L1 = E.m->layers[0];
+  fused::ChainP cp;
+  memset(&cp, 0, sizeof(cp));
+  cp.S = S; cp.single = single; cp.single_out = single_out; cp.done = done;
+  cp.Mimg = E.Mimg; cp.imgM = (uint32_t)E.imgM;
+  cp.w1t = sh.td ? E.ps + L1.w_off + (size_t)sh.D * sh.H : nullptr;
+  cp.b1 = E.ps + L1.b_off;
+  cp.hbuf = E.hbuf; cp.pair_bytes = (uint32_t)E.pair_bytes;
+  cp.B = (int)E.B; cp.H = sh.H; cp.td = sh.td; cp.act = sh.act; cp.KS = sh.KS; cp.nfull = sh.nfull; cp.ntail = sh.ntail;
+  cp.passes = E.passes; cp.nbuf = E.nbuf; cp.write_z = write_z;
+  const size_t smem_c = 2 * E.imgM + (size_t)E.nbuf * fused::kNT * sh.KS * 64 + 1024;
+  fused::chain_kernel<<<E.ntiles, fused::kThreads, smem_c, E.ctx->stream>>>(cp);
+  LRF_COUNT(E.ctx);
+
+  fused::KgemmP kp;
+  memset(&kp, 0, sizeof(kp));
+  kp.S = S; kp.single = single; kp.single_out = single_out; kp.done = done;
+  kp.W2img = E.W2img; kp.imgW = (uint32_t)E.imgW; kp.hbuf = E.hbuf; kp.pair_bytes = (uint32_t)E.pair_bytes;
+  kp.B = (int)E.B; kp.D = sh.D; kp.MT = sh.MT; kp.n_mt = sh.n_mt; kp.KS = sh.KS; kp.nfull = sh.nfull; kp.ntail = sh.ntail;
+  kp.passes = E.passes; kp.ntiles = E.ntiles; kp.nclusters = E.nclusters; kp.ring = 4;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(sh.n_mt * E.nclusters);
+  cfg.blockDim = dim3(fused::kThreads);
+  cfg.dynamicSmemBytes = 2 * E.imgW + 4 * (size_t)fused::kPieceBytes + 1024;
+  cfg.stream = E.ctx->stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = E.cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  LR_CUDA(cudaLaunchKernelEx(&cfg, fused::kgemm_kernel, kp));
+  LRF_COUNT(E.ctx);
+  LR_CUDA(cudaGetLastError());
+}
+
+void FusedEngine::step(SolveDev* S, int write_z) { lrf_launch(*this, S, nullptr, nullptr, nullptr, write_z); }
+
+void FusedEngine::eval(SolveDev* S, const LinComb* in, const LinComb* out, const int* done, int write_z) {
+  lrf_launch(*this, S, in, out, done, write_z);
+}
