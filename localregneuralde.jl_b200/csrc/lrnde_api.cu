@@ -1926,6 +1926,52 @@ extern "C" int lrnde_ode_backward(lrnde_ctx* ctx, const lrnde_model* m, lrnde_ta
   LR_API_END
 }
 
+// ------------------------------------------------------------------------------------------
+// profiling hook: one Tsit5 attempt of the latent-space engine, repeated (same descriptors: the controller
+// does not run), timed with CUDA events on the library's stream.  us[0] = chain kernel, us[1] = kgemm kernel,
+// us[2] = the attempt as the solve loop runs it (chain + kgemm + controller arithmetic excluded)
+// ------------------------------------------------------------------------------------------
+extern "C" int lrnde_profile_step(lrnde_ctx* ctx, const lrnde_model* m, const lrnde_opts* o, const float* ps,
+                                  const float* x, int64_t B, int32_t iters, float* us) {
+  LR_API_BEGIN
+  if (!ctx || !m || !o || !ps || !x || !us || B < 1 || iters < 1) lr_fail(LRNDE_EINVAL, "lrnde_profile_step: bad args");
+  LR_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const size_t DB = (size_t)m->D * B;
+  MlpEval ev(ctx, m, ps, B, o->precision, false);
+  if (!ev.fe) lr_fail(LRNDE_EINVAL, "lrnde_profile_step: the model / precision does not use the latent-space engine");
+  ev.prepare();
+  Solver F(ctx, DB, DB, 3, 0, 8);
+  F.init_ctrl(o->t0, o->t2, o->t2, o->maxiters, o->pow_mode, o->abstol, o->reltol);
+  F.enable_latent(ev.fe->zlen());
+  LR_CUDA(cudaMemcpyAsync(F.tape, x, sizeof(float) * DB, cudaMemcpyDeviceToDevice, st));
+  F.h.use_cond = 0;
+  F.upload();
+  ev.latent_of(F.tape, F.ztape);
+  auto eval = [&](const LinComb* in, const LinComb*, const int* done, const LinComb* out, bool) {
+    ev.fe->eval(F.dev, in, out, done, 1);
+  };
+  lr_solver_start(F, eval, 1);
+  cudaEvent_t e[4];
+  for (auto& ev_ : e) LR_CUDA(cudaEventCreate(&ev_));
+  for (int w = 0; w < 2; ++w) ev.fe->step(F.dev, 0);
+  LR_CUDA(cudaEventRecord(e[0], st));
+  for (int i = 0; i < iters; ++i) ev.fe->step_chain(F.dev, 0);
+  LR_CUDA(cudaEventRecord(e[1], st));
+  for (int i = 0; i < iters; ++i) ev.fe->step_kgemm(F.dev);
+  LR_CUDA(cudaEventRecord(e[2], st));
+  for (int i = 0; i < iters; ++i) ev.fe->step(F.dev, 0);
+  LR_CUDA(cudaEventRecord(e[3], st));
+  LR_CUDA(cudaEventSynchronize(e[3]));
+  for (int k = 0; k < 3; ++k) {
+    float ms = 0.0f;
+    LR_CUDA(cudaEventElapsedTime(&ms, e[k], e[k + 1]));
+    us[k] = 1000.0f * ms / (float)iters;
+  }
+  for (auto& ev_ : e) cudaEventDestroy(ev_);
+  LR_API_END
+}
+
 #include "lrnde_extra.cuh"
 #include "lrnde_sde.cuh"
 #include "lrnde_latent.cuh"

@@ -12,14 +12,27 @@
 #include "lrnde_act.cuh"
 #include "lrnde_tc.cuh"
 
+#ifdef LRNDE_UMMA_TRACE
+__device__ long long g_fused_trace[4096];
+// kernel 0 = chain, 1 = kgemm; CTA `blk` only; rows of 64 stamps
+#define FTRACE(kern, blk, row, it) do { if ((int)blockIdx.x == (blk) && (it) < 64) g_fused_trace[(kern) * 2048 + (row) * 64 + (it)] = clock64(); } while (0)
+extern "C" int lrnde_debug_trace_fused(long long* out, int n) {
+  cudaMemcpyFromSymbol(out, g_fused_trace, sizeof(long long) * (size_t)n);
+  return 0;
+}
+#else
+#define FTRACE(kern, blk, row, it) do { } while (0)
+#endif
+
 namespace fused {
 using namespace umma;
 
 constexpr int kNT = 64;                         // samples per tile
-constexpr int kEpiWarps = 8;                    // warps 2..9: compute / epilogue (two per TMEM lane quarter)
+constexpr int kEpiWarps = 16;                   // warps 2..17: compute / epilogue (four per TMEM lane quarter)
 constexpr int kThreads = 64 + 32 * kEpiWarps;   // warp 0: bulk copies, warp 1: tcgen05.mma issue
-constexpr int kPieceBytes = 2 * 128 * 128;      // kgemm ring stage: [hi | lo] of a 128-row x 32-float chunk
-constexpr int kTailBytes = 2 * 128 * 32;        // [hi | lo] of a 128-row x 8-float K-step
+constexpr int kUR = 96;                         // rows of a kgemm operand unit: 6 stages x 16 samples
+constexpr int kPieceBytes = 2 * kUR * 128;      // kgemm ring stage: [hi | lo] of a 96-row x 32-float chunk
+constexpr int kTailBytes = 2 * kUR * 32;        // [hi | lo] of a 96-row x 8-float K-step
 
 // shared-memory matrix descriptors (cute::UMMA::SmemDescriptor), K-major:
 //   SWIZZLE_128B: rows of 128 B, 8-row atoms of 1024 B (SBO), 16-byte chunks XOR-ed with (row & 7)
@@ -126,23 +139,11 @@ __global__ void mz_pack_kernel(const float* __restrict__ W1, const float* __rest
   *reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(img) + o) = hi;
   *reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(img) + img_bytes + o) = lo;
 }
-// W2a = [W2 | w2t | b2] split into n_mt tiles of MT output features: the A operands of the kgemm kernel
-__global__ void w2_pack_kernel(const float* __restrict__ W2a, int D, int Kaug, int nfull, int MT, float* __restrict__ img,
-                               uint32_t img_bytes, int passes) {
-  const int r = threadIdx.x, k = blockIdx.x, mt = blockIdx.y;
-  if (r >= MT) return;
-  const int mrow = mt * MT + r;
-  const float v = (mrow < D && k < Kaug) ? W2a[(size_t)k * D + mrow] : 0.0f;
-  const float hi = (passes == 1) ? v : tf32_rna(v);
-  const float lo = (passes == 1) ? 0.0f : tf32_rna(v - hi);
-  uint8_t* base = reinterpret_cast<uint8_t*>(img) + (size_t)mt * 2 * img_bytes;
-  const uint32_t o = img_off(MT, nfull, r, k);
-  *reinterpret_cast<float*>(base + o) = hi;
-  *reinterpret_cast<float*>(base + img_bytes + o) = lo;
-}
-
 // ---------------------------------------------------------------------------------------------------------
-// (1) chain kernel: the stages of one attempt as a recurrence in latent space, one CTA per 64 samples
+// (1) chain kernel: the stages of one attempt as a recurrence in latent space, one CTA per 64 samples.
+// The 64 samples are two independent halves of 32 (column group cg): while the tensor core multiplies one
+// half's hidden activations by Mz, the other half's warps compute their next activation.
+// Operand images leave in the layout the kgemm kernel reads: units of 16 samples, 96 rows = 6 stages x 16.
 // ---------------------------------------------------------------------------------------------------------
 struct ChainP {
   SolveDev* S;
@@ -154,16 +155,17 @@ struct ChainP {
   const float* w1t;  // layer-1 time column (nullptr without TDChain)
   const float* b1;
   float* hbuf;
-  uint32_t pair_bytes;
-  int B, H, td, act, KS, nfull, ntail, passes, nbuf, write_z;
+  uint32_t unit_bytes;
+  int B, H, td, KS, nfull, ntail, passes, nbuf, write_z;
 };
 
+template <int ACT>
 __global__ void __launch_bounds__(kThreads, 1) chain_kernel(ChainP p) {
   if (p.done && *p.done) return;
   if (!p.single && p.S->done) return;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  __shared__ uint64_t abar, bfull[2], bfree[2], zdone;
+  __shared__ uint64_t abar, bfull[2][2], bfree[2], zdone[2];
   __shared__ uint32_t tmem_slot;
   __shared__ LinComb sd[7];
   __shared__ float* s_tape;
@@ -180,8 +182,12 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(ChainP p) {
 
   if (threadIdx.x == 0) {
     mbar_init(&abar, 1u);
-    for (int b = 0; b < 2; ++b) { mbar_init(&bfull[b], (uint32_t)kEpiWarps); mbar_init(&bfree[b], 1u); }
-    mbar_init(&zdone, 1u);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&bfull[0][b], (uint32_t)(kEpiWarps / 2));
+      mbar_init(&bfull[1][b], (uint32_t)(kEpiWarps / 2));
+      mbar_init(&bfree[b], 1u);
+      mbar_init(&zdone[b], 1u);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     if (p.single) sd[0] = *p.single;
     else for (int j = 0; j < 7; ++j) sd[j] = p.S->st[j];
@@ -197,6 +203,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(ChainP p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
+  if (threadIdx.x == 0) FTRACE(0, 1, 0, 0);
   auto zof = [&](const float* ptr) -> float* { return s_ztape + ((size_t)(ptr - s_tape) / s_len) * s_zlen; };
 
   if (warp == 0) {
@@ -208,20 +215,24 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(ChainP p) {
     __syncwarp();
     for (int st = 0; st < nst; ++st) {
       const int b = st % p.nbuf;
-      mbar_wait(&bfull[b], (uint32_t)((st / p.nbuf) & 1));
+      const uint32_t ph = (uint32_t)((st / p.nbuf) & 1);
+      mbar_wait(&bfull[0][b], ph);
+      mbar_wait(&bfull[1][b], ph);
       if (elect_one_sync()) {
-        // stage `st` of the attempt = half (st & 1) of operand pair (st >> 1) of this tile (kgemm layout: 128 rows)
-        const int pair = p.single ? 0 : (st >> 1), half = p.single ? 0 : (st & 1);
-        uint8_t* g = reinterpret_cast<uint8_t*>(p.hbuf) + ((size_t)blockIdx.x * 3 + pair) * p.pair_bytes;
+        // the 64 rows of this stage = rows [16 j, 16 j + 16) of four 16-sample unit tiles
+        const int j = p.single ? 0 : st;
         const uint8_t* s = smB + (size_t)b * tileB;
-        for (int c = 0; c < p.nfull; ++c)
-          for (int lo = 0; lo < 2; ++lo)
-            bulk_s2g(g + (size_t)c * kPieceBytes + lo * (128 * 128) + half * (kNT * 128),
-                     s + (size_t)c * (2 * kNT * 128) + lo * (kNT * 128), kNT * 128);
-        for (int t = 0; t < p.ntail; ++t)
-          for (int lo = 0; lo < 2; ++lo)
-            bulk_s2g(g + (size_t)p.nfull * kPieceBytes + (size_t)t * kTailBytes + lo * (128 * 32) + half * (kNT * 32),
-                     s + (size_t)p.nfull * (2 * kNT * 128) + (size_t)t * (2 * kNT * 32) + lo * (kNT * 32), kNT * 32);
+        for (int sg = 0; sg < 4; ++sg) {
+          uint8_t* g = reinterpret_cast<uint8_t*>(p.hbuf) + ((size_t)blockIdx.x * 4 + sg) * p.unit_bytes;
+          for (int c = 0; c < p.nfull; ++c)
+            for (int lo = 0; lo < 2; ++lo)
+              bulk_s2g(g + (size_t)c * kPieceBytes + lo * (kUR * 128) + j * 2048,
+                       s + (size_t)c * (2 * kNT * 128) + lo * (kNT * 128) + sg * 2048, 2048);
+          for (int t = 0; t < p.ntail; ++t)
+            for (int lo = 0; lo < 2; ++lo)
+              bulk_s2g(g + (size_t)p.nfull * kPieceBytes + (size_t)t * kTailBytes + lo * (kUR * 32) + j * 512,
+                       s + (size_t)p.nfull * (2 * kNT * 128) + (size_t)t * (2 * kNT * 32) + lo * (kNT * 32) + sg * 512, 512);
+        }
         bulk_commit();
         bulk_wait_read0();
         mbar_arrive(&bfree[b]);
@@ -231,68 +242,83 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(ChainP p) {
     if (elect_one_sync()) bulk_wait0();
     __syncwarp();
   } else if (warp == 1) {
-    // ---------------- tcgen05.mma issue: Z(k_j) = Mz [h_j ; t_j ; 1]   (M = 128 latent rows x N = 64 samples)
-    constexpr uint32_t idesc = make_idesc(128, kNT);
+    // ---------------- tcgen05.mma issue: Z(k_j) = Mz [h_j ; t_j ; 1]   (M = 128 latent rows x N = 32 samples per half)
+    constexpr uint32_t idesc = make_idesc(128, kNT / 2);
     mbar_wait(&abar, 0);
+    if (lane == 0) FTRACE(0, 1, 0, 1);
     const uint32_t a0 = smem_u32(smA);
     for (int st = 0; st < nst; ++st) {
       const int b = st % p.nbuf;
-      mbar_wait(&bfull[b], (uint32_t)((st / p.nbuf) & 1));
-      tc_fence_after();
-      const uint32_t b0 = smem_u32(smB + (size_t)b * tileB);
-      const uint32_t d = tmem_base + (uint32_t)((p.single ? 7 : 2 + st) * kNT);
-      if (elect_one_sync()) {
-        uint32_t first = 0u;
-        for (int c = 0; c < p.nfull; ++c) {
-          const uint32_t ah = desc_lo(a0 + c * (128 * 128)), al = desc_lo(a0 + p.imgM + c * (128 * 128));
-          const uint32_t bh = desc_lo(b0 + c * (2 * kNT * 128)), bl = desc_lo(b0 + c * (2 * kNT * 128) + kNT * 128);
+      for (int cg = 0; cg < 2; ++cg) {
+        mbar_wait(&bfull[cg][b], (uint32_t)((st / p.nbuf) & 1));
+        tc_fence_after();
+        if (lane == 0) FTRACE(0, 1, 1, 2 * st + cg);
+        const uint32_t b0 = smem_u32(smB + (size_t)b * tileB);
+        const uint32_t d = tmem_base + (uint32_t)((p.single ? 7 : 2 + st) * kNT + cg * (kNT / 2));
+        if (elect_one_sync()) {
+          uint32_t first = 0u;
+          for (int c = 0; c < p.nfull; ++c) {
+            const uint32_t ah = desc_lo(a0 + c * (128 * 128)), al = desc_lo(a0 + p.imgM + c * (128 * 128));
+            const uint32_t bb = b0 + c * (2 * kNT * 128) + cg * (kNT / 2) * 128;
+            const uint32_t bh = desc_lo(bb), bl = desc_lo(bb + kNT * 128);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            mma_kstep(d, ah + 2 * k, al + 2 * k, bh + 2 * k, bl + 2 * k, kHi128, idesc, first, p.passes);
+            for (int k = 0; k < 4; ++k) {
+              mma_kstep(d, ah + 2 * k, al + 2 * k, bh + 2 * k, bl + 2 * k, kHi128, idesc, first, p.passes);
+              first = 1u;
+            }
+          }
+          for (int t = 0; t < p.ntail; ++t) {
+            const uint32_t ao = p.nfull * (128 * 128) + t * (128 * 32);
+            const uint32_t bb = b0 + p.nfull * (2 * kNT * 128) + t * (2 * kNT * 32) + cg * (kNT / 2) * 32;
+            mma_kstep(d, desc_lo(a0 + ao), desc_lo(a0 + p.imgM + ao), desc_lo(bb), desc_lo(bb + kNT * 32), kHi32, idesc,
+                      first, p.passes);
             first = 1u;
           }
+          mma_commit(&zdone[cg]);
+          FTRACE(0, 1, 2, 2 * st + cg);
         }
-        for (int t = 0; t < p.ntail; ++t) {
-          const uint32_t ao = p.nfull * (128 * 128) + t * (128 * 32);
-          const uint32_t bo = p.nfull * (2 * kNT * 128) + t * (2 * kNT * 32);
-          mma_kstep(d, desc_lo(a0 + ao), desc_lo(a0 + p.imgM + ao), desc_lo(b0 + bo), desc_lo(b0 + bo + kNT * 32), kHi32,
-                    idesc, first, p.passes);
-          first = 1u;
-        }
-        mma_commit(&zdone);
+        __syncwarp();
       }
-      __syncwarp();
     }
   } else {
-    // ---------------- stage arithmetic: lane = latent row, registers = samples
-    const int q = warp & 3, cg = (warp - 2) >> 2;
+    // ---------------- stage arithmetic: lane = latent row, registers = 16 samples
+    const int q = warp & 3, sub = (warp - 2) >> 2;
+    const int cg = sub >> 1;
     const int hrow = q * 32 + lane;
     const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
-    const int col0 = cg * 32;
+    const int col = sub * 16;
     const bool rowv = hrow < p.H;
     const float w1t = (p.td && rowv && p.w1t) ? p.w1t[hrow] : 0.0f;
     const float b1 = rowv ? p.b1[hrow] : 0.0f;
+    const bool tr = (threadIdx.x == 64);
     // inputs computed earlier: Z(uprev) -> slot 0, Z(sources) -> slots 1..
     const int next = p.single ? 1 + sd[0].n : 2;
     if (p.single && sd[0].n > 6) asm volatile("trap;");
     for (int e = 0; e < next; ++e) {
       const float* src = (e == 0) ? sd[0].base : sd[0].src[e - 1];
       const float* zp = src ? zof(src) : nullptr;
+      float v[16];
 #pragma unroll
-      for (int blk = 0; blk < 2; ++blk) {
-        float v[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int n = n0 + col0 + blk * 16 + i;
-          v[i] = (zp && rowv && n < p.B) ? __ldcg(zp + (size_t)n * LR_ZROW + hrow) : 0.0f;
-        }
-        tmem_st16(tlane + (uint32_t)(e * kNT + col0 + blk * 16), v);
+      for (int i = 0; i < 16; ++i) {
+        const int n = n0 + col + i;
+        v[i] = (zp && rowv && n < p.B) ? __ldcg(zp + (size_t)n * LR_ZROW + hrow) : 0.0f;
       }
+      tmem_st16(tlane + (uint32_t)(e * kNT + col), v);
     }
     tmem_st_wait();
+    if (tr) FTRACE(0, 1, 0, 2);
     // operand-image position of (sample row, k = hrow): chunk q of the tile when hrow is inside a full chunk
     const bool in_full = hrow < p.nfull * 32;
     const bool in_img = hrow < p.KS * 8;
+    uint32_t obase, ostep_lo;
+    if (in_full) {
+      obase = (uint32_t)(q * (2 * kNT * 128) + (lane & 3) * 4);
+      ostep_lo = (uint32_t)(kNT * 128);
+    } else {
+      const int kt = hrow - p.nfull * 32, t = kt >> 3, kk = kt & 7;
+      obase = (uint32_t)(p.nfull * (2 * kNT * 128) + t * (2 * kNT * 32) + (kk & 3) * 4) | (uint32_t)(((kk >> 2) & 1) << 30);
+      ostep_lo = (uint32_t)(kNT * 32);
+    }
     for (int st = 0; st < nst; ++st) {
       const int b = st % p.nbuf;
       const LinComb& d = sd[st];
@@ -300,75 +326,78 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(ChainP p) {
       const float tstage = last_full ? sd[6].t : d.t;
       const int nsrc = d.n;
       float* zlin = last_full ? zof(d.dst) : nullptr;   // Z(u_{n+1}) = Z(uprev) + dt * sum a_7i Z(k_i)
+      if (tr) FTRACE(0, 1, 3, st);
       if (st >= p.nbuf) mbar_wait(&bfree[b], (uint32_t)(((st / p.nbuf) - 1) & 1));
+      if (tr) FTRACE(0, 1, 4, st);
       uint8_t* tile = smB + (size_t)b * tileB;
-#pragma unroll 1
-      for (int blk = 0; blk < 2; ++blk) {
-        const int col = col0 + blk * 16;
-        float inner[16], v[16];
+      float inner[16], v[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) inner[i] = 0.0f;
-        for (int s = 0; s < nsrc; ++s) {
-          tmem_ld16(tlane + (uint32_t)((1 + s) * kNT + col), v);
-          const float cf = d.coef[s];
+      for (int i = 0; i < 16; ++i) inner[i] = 0.0f;
+      for (int s = 0; s < nsrc; ++s) {
+        tmem_ld16(tlane + (uint32_t)((1 + s) * kNT + col), v);
+        const float cf = d.coef[s];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) inner[i] = fmaf(cf, v[i], inner[i]);
-        }
-        tmem_ld16(tlane + (uint32_t)col, v);
+        for (int i = 0; i < 16; ++i) inner[i] = fmaf(cf, v[i], inner[i]);
+      }
+      tmem_ld16(tlane + (uint32_t)col, v);
+      const float scale = d.scale;
+      if (nsrc) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = fmaf(scale, inner[i], v[i]);
+      }
+      if (zlin && rowv) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (n0 + col + i < p.B) zlin[(size_t)(n0 + col + i) * LR_ZROW + hrow] = v[i];
+      }
+      // activation (branch-free over the 16 samples: the compiler interleaves the dependent chains)
+      const float hconst = (p.td && hrow == p.H) ? tstage : ((hrow == p.H + p.td) ? 1.0f : 0.0f);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        float x = p.td ? fmaf(w1t, tstage, v[i]) : v[i];
+        x += b1;
+        const float h = lr_act(ACT, x);
+        v[i] = rowv ? h : hconst;
+      }
+      if (in_img) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const int row = col + i;          // sample row of the operand tile
-          const int n = n0 + row;
-          float pre = nsrc ? fmaf(d.scale, inner[i], v[i]) : v[i];
-          if (zlin && rowv && n < p.B) zlin[(size_t)n * LR_ZROW + hrow] = pre;
-          float x = p.td ? fmaf(w1t, tstage, pre) : pre;
-          x += b1;
-          float h = lr_act(p.act, x);
-          if (!rowv) h = (p.td && hrow == p.H) ? tstage : ((hrow == p.H + p.td) ? 1.0f : 0.0f);
-          if (in_img) {
-            float hi, lo;
-            if (p.passes == 3) { hi = tf32_rna(h); lo = tf32_rna(h - hi); }
-            else { hi = h; lo = 0.0f; }
-            uint32_t o;
-            if (in_full)
-              o = (uint32_t)(q * (2 * kNT * 128) + (row >> 3) * 1024 + (row & 7) * 128 + (((lane >> 2) ^ (row & 7)) << 4) +
-                             (lane & 3) * 4);
-            else {
-              const int kt = hrow - p.nfull * 32, t = kt >> 3, kk = kt & 7;
-              o = (uint32_t)(p.nfull * (2 * kNT * 128) + t * (2 * kNT * 32) + row * 32 +
-                             ((((kk >> 2) & 1) ^ ((row >> 2) & 1)) << 4) + (kk & 3) * 4);
-            }
-            const uint32_t lo_off = in_full ? (uint32_t)(kNT * 128) : (uint32_t)(kNT * 32);
-            *reinterpret_cast<float*>(tile + o) = hi;
-            *reinterpret_cast<float*>(tile + o + lo_off) = lo;
-          }
+          const int row = col + i;
+          float hi, lo;
+          if (p.passes == 3) { hi = tf32_rna(v[i]); lo = tf32_rna(v[i] - hi); }
+          else { hi = v[i]; lo = 0.0f; }
+          uint32_t o;
+          if (in_full) o = obase + (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + (((lane >> 2) ^ (row & 7)) << 4));
+          else o = (obase & 0x3FFFFFFFu) + (uint32_t)(row * 32 + ((((obase >> 30) & 1) ^ ((row >> 2) & 1)) << 4));
+          *reinterpret_cast<float*>(tile + o) = hi;
+          *reinterpret_cast<float*>(tile + o + ostep_lo) = lo;
         }
       }
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bfull[b]);
-      mbar_wait(&zdone, (uint32_t)(st & 1));
+      if (lane == 0) mbar_arrive(&bfull[cg][b]);
+      if (tr) FTRACE(0, 1, 5, st);
+      mbar_wait(&zdone[cg], (uint32_t)(st & 1));
       tc_fence_after();
+      if (tr) FTRACE(0, 1, 6, st);
       // Z(k_j) to the latent tape
       const float* kdst = p.single ? sd[1].dst : (last_full ? sd[6].dst : d.dst);
       if (p.write_z || last_full) {
         float* zo = zof(kdst);
         const int slot = p.single ? 7 : 2 + st;
-#pragma unroll 1
-        for (int blk = 0; blk < 2; ++blk) {
-          float v[16];
-          tmem_ld16(tlane + (uint32_t)(slot * kNT + col0 + blk * 16), v);
+        tmem_ld16(tlane + (uint32_t)(slot * kNT + col), v);
+        if (rowv) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int n = n0 + col0 + blk * 16 + i;
-            if (rowv && n < p.B) zo[(size_t)n * LR_ZROW + hrow] = v[i];
-          }
+          for (int i = 0; i < 16; ++i)
+            if (n0 + col + i < p.B) zo[(size_t)(n0 + col + i) * LR_ZROW + hrow] = v[i];
         }
       }
     }
     tc_fence_before();
+    if (tr) FTRACE(0, 1, 0, 3);
   }
   __syncthreads();
+  if (threadIdx.x == 0) FTRACE(0, 1, 0, 4);
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
@@ -376,26 +405,60 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(ChainP p) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// (2) kgemm kernel: k_j = W2a [h_j ; t_j ; 1] for all stages of the attempt, epilogue = tape + u_{n+1} + residual
+// (2) kgemm kernel: k_j = W2a [h_j ; t_j ; 1] for all stages of the attempt, epilogue = tape + u_{n+1} + residual.
+// One CTA = one tile of MT output features; W2a (tf32 hi / lo) sits in TENSOR MEMORY as the A operand for the whole
+// launch (the MMAs read only the activation operand from shared memory: N = 96 runs at the tensor floor), the
+// CTAs of a cluster are the feature tiles of the same samples, so the operand pieces are fetched once per
+// cluster and multicast.  A unit = 16 samples x 6 stages = 96 accumulator columns, double-buffered in TMEM.
 // ---------------------------------------------------------------------------------------------------------
 struct KgemmP {
   SolveDev* S;
   const LinComb* single;
   const LinComb* single_out;
   const int* done;
-  const float* W2img;
-  uint32_t imgW;
+  const float* W2a;   // [D x Kaug] column-major block of the parameter vector (weight | time column | bias)
   const float* hbuf;
-  uint32_t pair_bytes;
-  int B, D, MT, n_mt, KS, nfull, ntail, passes, ntiles, nclusters, ring;
+  uint32_t unit_bytes;
+  int B, D, MT, n_mt, Kaug, KS, nfull, ntail, passes, nunits, nclusters, ring;
 };
+
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+  uint32_t r[8];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+      : "r"(taddr)
+      : "memory");
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j]);
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
+               "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+               "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
+               : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem]^T : A = 128 lanes x 8 columns (tf32 in 32-bit cells)
+__device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo32, uint32_t hi32, uint32_t idesc,
+                                       uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], db, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "r"(b_lo32), "r"(idesc), "r"(accumulate), "r"(hi32)
+      : "memory");
+}
+
+constexpr int kDCol = 256;      // accumulator buffers at TMEM columns 256 and 384 (A operand in columns [0, 2 * 8 * KS))
 
 __global__ void __launch_bounds__(kThreads, 1) kgemm_kernel(KgemmP p) {
   if (p.done && *p.done) return;
   if (!p.single && p.S->done) return;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  __shared__ uint64_t abar, full_bar[8], empty_bar[8], acc_full[2], epi_done[2];
+  uint8_t* smR = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t a_ready, full_bar[8], empty_bar[8], acc_full[2], tmem_free[2];
   __shared__ uint32_t tmem_slot;
   __shared__ LinComb s_err, s_un;
   __shared__ double s_red[kEpiWarps];
@@ -407,15 +470,13 @@ __global__ void __launch_bounds__(kThreads, 1) kgemm_kernel(KgemmP p) {
   const uint16_t cmask = (uint16_t)((1u << csize) - 1u);
   const int mt = (int)(blockIdx.x % (unsigned)p.n_mt);
   const int cid = (int)(blockIdx.x / (unsigned)p.n_mt);
-  const int npairs = p.single ? 1 : 3;
   const int npieces = p.nfull + p.ntail;
-  uint8_t* smA = smem;
-  uint8_t* smR = smem + 2 * (size_t)p.imgW;
+  const int lo_col = p.KS * 8;
 
   if (threadIdx.x == 0) {
-    mbar_init(&abar, 1u);
+    mbar_init(&a_ready, (uint32_t)kEpiWarps);
     for (int s = 0; s < p.ring; ++s) { mbar_init(&full_bar[s], 1u); mbar_init(&empty_bar[s], csize); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1u); mbar_init(&epi_done[b], (uint32_t)kEpiWarps); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1u); mbar_init(&tmem_free[b], (uint32_t)(kEpiWarps / 2)); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     if (p.single) { s_err = *p.single; s_un = p.single_out ? *p.single_out : *p.single; }
     else { s_err = p.S->err; s_un = p.S->st[5]; }
@@ -430,154 +491,195 @@ __global__ void __launch_bounds__(kThreads, 1) kgemm_kernel(KgemmP p) {
   if (csize > 1) cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
+  if (threadIdx.x == 0) FTRACE(1, 0, 0, 0);
 
   if (warp == 0) {
-    // ---------------- bulk copies: this tile's W2a images once, then the operand pieces of every unit (each CTA of
-    // the cluster fetches a slice and multicasts it: the CTAs of a cluster share the sample tile)
-    if (elect_one_sync()) {
-      mbar_arrive_expect_tx(&abar, 2 * p.imgW);
-      bulk_g2s(smA, reinterpret_cast<const uint8_t*>(p.W2img) + (size_t)mt * 2 * p.imgW, 2 * p.imgW, &abar);
-    }
-    __syncwarp();
+    // ---------------- operand pieces of every unit: each CTA of the cluster fetches a slice and multicasts it
     int it = 0;
-    for (int T = cid; T < p.ntiles; T += p.nclusters) {
-      for (int pr = 0; pr < npairs; ++pr) {
-        const uint8_t* src = reinterpret_cast<const uint8_t*>(p.hbuf) + ((size_t)T * 3 + pr) * p.pair_bytes;
-        for (int pc = 0; pc < npieces; ++pc, ++it) {
-          const int s = it % p.ring, ph = (it / p.ring) & 1;
-          mbar_wait(&empty_bar[s], (uint32_t)(ph ^ 1));
-          const uint32_t bytes = (pc < p.nfull) ? (uint32_t)kPieceBytes : (uint32_t)kTailBytes;
-          const size_t off = (pc < p.nfull) ? (size_t)pc * kPieceBytes : (size_t)p.nfull * kPieceBytes + (size_t)(pc - p.nfull) * kTailBytes;
-          uint8_t* dst = smR + (size_t)s * kPieceBytes;
-          if (elect_one_sync()) {
-            mbar_arrive_expect_tx(&full_bar[s], bytes);
-            if (csize > 1) {
-              const uint32_t sl = (((bytes + csize - 1) / csize) + 15u) & ~15u;
-              const uint32_t o = crank * sl;
-              if (o < bytes) bulk_g2s_mc(dst + o, src + off + o, min(sl, bytes - o), &full_bar[s], cmask);
-            } else {
-              bulk_g2s(dst, src + off, bytes, &full_bar[s]);
-            }
+    for (int g = cid; g < p.nunits; g += p.nclusters) {
+      const uint8_t* src = reinterpret_cast<const uint8_t*>(p.hbuf) + (size_t)g * p.unit_bytes;
+      for (int pc = 0; pc < npieces; ++pc, ++it) {
+        const int s = it % p.ring, ph = (it / p.ring) & 1;
+        mbar_wait(&empty_bar[s], (uint32_t)(ph ^ 1));
+        const uint32_t bytes = (pc < p.nfull) ? (uint32_t)kPieceBytes : (uint32_t)kTailBytes;
+        const size_t off = (pc < p.nfull) ? (size_t)pc * kPieceBytes : (size_t)p.nfull * kPieceBytes + (size_t)(pc - p.nfull) * kTailBytes;
+        uint8_t* dst = smR + (size_t)s * kPieceBytes;
+        if (elect_one_sync()) {
+          FTRACE(1, 0, 1, it);
+          mbar_arrive_expect_tx(&full_bar[s], bytes);
+          if (csize > 1) {
+            const uint32_t sl = (((bytes + csize - 1) / csize) + 15u) & ~15u;
+            const uint32_t o = crank * sl;
+            if (o < bytes) bulk_g2s_mc(dst + o, src + off + o, min(sl, bytes - o), &full_bar[s], cmask);
+          } else {
+            bulk_g2s(dst, src + off, bytes, &full_bar[s]);
           }
-          __syncwarp();
         }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
-    // ---------------- tcgen05.mma issue: D[128 features x (2 stages x 64 samples)] per operand pair
-    const uint32_t idesc = p.single ? make_idesc(128, kNT) : make_idesc(128, 2 * kNT);
-    mbar_wait(&abar, 0);
-    const uint32_t a0 = smem_u32(smA);
-    const int R = p.MT;
+    // ---------------- tcgen05.mma issue: D[128 features x (6 stages x 16 samples)] = A (TMEM) x operand pieces
+    const uint32_t idesc = p.single ? make_idesc(128, 16) : make_idesc(128, kUR);
+    mbar_wait(&a_ready, 0);
+    tc_fence_after();
+    if (lane == 0) FTRACE(1, 0, 0, 1);
     int it = 0, u = 0;
-    for (int T = cid; T < p.ntiles; T += p.nclusters, ++u) {
-      for (int pr = 0; pr < npairs; ++pr) {
-        // TMEM pair slot and the unit whose epilogue must have drained it
-        const int slot = p.single ? ((2 * u) & 3) : ((3 * u + pr) & 3);
-        const int dep = (p.single || pr == 0) ? u - 2 : u - 1;
-        if (dep >= 0) { mbar_wait(&epi_done[dep & 1], (uint32_t)((dep >> 1) & 1)); tc_fence_after(); }
-        const uint32_t d = tmem_base + (uint32_t)(slot * 2 * kNT);
-        uint32_t first = 0u;
-        for (int pc = 0; pc < npieces; ++pc, ++it) {
-          const int s = it % p.ring, ph = (it / p.ring) & 1;
-          mbar_wait(&full_bar[s], (uint32_t)ph);
-          tc_fence_after();
-          const uint32_t b0 = smem_u32(smR + (size_t)s * kPieceBytes);
-          if (elect_one_sync()) {
-            if (pc < p.nfull) {
-              const uint32_t ah = desc_lo(a0 + pc * (R * 128)), al = desc_lo(a0 + p.imgW + pc * (R * 128));
-              const uint32_t bh = desc_lo(b0), bl = desc_lo(b0 + 128 * 128);
+    for (int g = cid; g < p.nunits; g += p.nclusters, ++u) {
+      const int db = u & 1;
+      if (u >= 2) { mbar_wait(&tmem_free[db], (uint32_t)(((u >> 1) - 1) & 1)); tc_fence_after(); }
+      const uint32_t d = tmem_base + (uint32_t)(kDCol + db * 128);
+      uint32_t first = 0u;
+      for (int pc = 0; pc < npieces; ++pc, ++it) {
+        const int s = it % p.ring, ph = (it / p.ring) & 1;
+        mbar_wait(&full_bar[s], (uint32_t)ph);
+        tc_fence_after();
+        if (lane == 0) FTRACE(1, 0, 2, it);
+        const uint32_t b0 = smem_u32(smR + (size_t)s * kPieceBytes);
+        if (elect_one_sync()) {
+          if (pc < p.nfull) {
+            const uint32_t bh = desc_lo(b0), bl = desc_lo(b0 + kUR * 128);
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                mma_kstep(d, ah + 2 * k, al + 2 * k, bh + 2 * k, bl + 2 * k, kHi128, idesc, first, p.passes);
-                first = 1u;
-              }
-            } else {
-              const uint32_t ao = p.nfull * (R * 128) + (pc - p.nfull) * (R * 32);
-              mma_kstep(d, desc_lo(a0 + ao), desc_lo(a0 + p.imgW + ao), desc_lo(b0), desc_lo(b0 + 128 * 32), kHi32, idesc,
-                        first, p.passes);
+            for (int k = 0; k < 4; ++k) {
+              const uint32_t ah = tmem_base + (uint32_t)((pc * 4 + k) * 8), al = ah + (uint32_t)lo_col;
+              if (p.passes == 3) {
+                mma_ts(d, al, bh + 2 * k, kHi128, idesc, first);
+                mma_ts(d, ah, bl + 2 * k, kHi128, idesc, 1u);
+                mma_ts(d, ah, bh + 2 * k, kHi128, idesc, 1u);
+              } else mma_ts(d, ah, bh + 2 * k, kHi128, idesc, first);
               first = 1u;
             }
-            if (csize > 1) mma_commit_mc(&empty_bar[s], cmask);
-            else mma_commit(&empty_bar[s]);
-            if (pr == npairs - 1 && pc == npieces - 1) mma_commit(&acc_full[u & 1]);
+          } else {
+            const uint32_t bh = desc_lo(b0), bl = desc_lo(b0 + kUR * 32);
+            const uint32_t ah = tmem_base + (uint32_t)((p.nfull * 4 + (pc - p.nfull)) * 8), al = ah + (uint32_t)lo_col;
+            if (p.passes == 3) {
+              mma_ts(d, al, bh, kHi32, idesc, first);
+              mma_ts(d, ah, bl, kHi32, idesc, 1u);
+              mma_ts(d, ah, bh, kHi32, idesc, 1u);
+            } else mma_ts(d, ah, bh, kHi32, idesc, first);
+            first = 1u;
           }
-          __syncwarp();
+          if (csize > 1) mma_commit_mc(&empty_bar[s], cmask);
+          else mma_commit(&empty_bar[s]);
+          if (pc == npieces - 1) mma_commit(&acc_full[db]);
+          FTRACE(1, 0, 3, it);
         }
+        __syncwarp();
       }
     }
   } else {
-    // ---------------- epilogue: lane = output feature (coalesced global access), registers = samples
-    const int q = warp & 3, cg = (warp - 2) >> 2;
+    // ---------------- warps 2..17: lane = output feature (coalesced global access), registers = 8 samples
+    const int q = warp & 3, sub = (warp - 2) >> 2;
+    const int par = sub >> 1, half = sub & 1;
     const int mloc = q * 32 + lane;
     const int m = mt * p.MT + mloc;
     const bool mv = (mloc < p.MT) && (m < p.D);
     const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
+    const bool tr = (threadIdx.x == 64);
+    // W2a tile -> tensor memory, tf32 hi / lo (every warp writes the K-steps ks = sub, sub + 4, ...)
+    for (int ks = sub; ks < p.KS; ks += 4) {
+      float hi[8], lo[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int k = ks * 8 + e;
+        const float w = (mv && k < p.Kaug) ? __ldg(p.W2a + (size_t)k * p.D + m) : 0.0f;
+        if (p.passes == 3) { hi[e] = tf32_rna(w); lo[e] = tf32_rna(w - hi[e]); }
+        else { hi[e] = w; lo[e] = 0.0f; }
+      }
+      tmem_st8(tlane + (uint32_t)(ks * 8), hi);
+      tmem_st8(tlane + (uint32_t)(lo_col + ks * 8), lo);
+    }
+    tmem_st_wait();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&a_ready);
+
     const float abstol = p.S->abstol, reltol = p.S->reltol;
+    const int D = p.D;
     double acc = 0.0;
     int u = 0;
-    for (int T = cid; T < p.ntiles; T += p.nclusters, ++u) {
-      mbar_wait(&acc_full[u & 1], (uint32_t)((u >> 1) & 1));
-      tc_fence_after();
-#pragma unroll 1
-      for (int blk = 0; blk < 2; ++blk) {
-        const int c0 = cg * 32 + blk * 16;
-        const int nb = T * kNT + c0;
-        if (p.single) {
-          float v[16];
-          tmem_ld16(tlane + (uint32_t)(((2 * u) & 3) * 2 * kNT + c0), v);
-          float* out = s_un.dst;
-          if (mv) {
+    for (int g = cid; g < p.nunits; g += p.nclusters, ++u) {
+      if ((u & 1) != par) continue;
+      const int db = u & 1;
+      const int nb = g * 16 + half * 8;                 // first sample of this thread's 8
+      const bool full = mv && (nb + 8 <= p.B);
+      const size_t e0 = (size_t)nb * D + m;             // element offset of (sample nb, feature m)
+      const uint32_t dcol = tlane + (uint32_t)(kDCol + db * 128 + half * 8);
+      if (p.single) {
+        if (tr) FTRACE(1, 0, 4, 2 * (u >> 1));
+        mbar_wait(&acc_full[db], (uint32_t)((u >> 1) & 1));
+        tc_fence_after();
+        float v[8];
+        tmem_ld8(dcol, v);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_free[db]);
+        float* out = s_un.dst + e0;
+        if (mv) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i)
-              if (nb + i < p.B) out[(size_t)(nb + i) * p.D + m] = v[i];
-          }
-        } else {
-          float up[16], k1[16];
+          for (int i = 0; i < 8; ++i)
+            if (nb + i < p.B) out[(size_t)i * D] = v[i];
+        }
+        continue;
+      }
+      // uprev and k1 = fsalfirst: the only arrays the attempt reads (issued before the accumulators are waited for)
+      float up[8], k1[8];
+      {
+        const float* pu = s_err.base + e0;
+        const float* pk = s_err.src[0] + e0;
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const bool ok = mv && (nb + i < p.B);
-            up[i] = ok ? __ldcg(s_err.base + (size_t)(nb + i) * p.D + m) : 0.0f;
-            k1[i] = ok ? __ldcg(s_err.src[0] + (size_t)(nb + i) * p.D + m) : 0.0f;
-          }
-          float un[16], ut[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) { un[i] = s_un.coef[0] * k1[i]; ut[i] = s_err.coef[0] * k1[i]; }
-#pragma unroll
-          for (int jj = 0; jj < 6; ++jj) {   // stage jj + 2
-            float v[16];
-            const int slot = (3 * u + (jj >> 1)) & 3;
-            tmem_ld16(tlane + (uint32_t)(slot * 2 * kNT + (jj & 1) * kNT + c0), v);
-            float* kout = const_cast<float*>(s_err.src[jj + 1]);
-            if (mv) {
-#pragma unroll
-              for (int i = 0; i < 16; ++i)
-                if (nb + i < p.B) kout[(size_t)(nb + i) * p.D + m] = v[i];
-            }
-            if (jj < 5) {
-              const float ca = s_un.coef[jj + 1];
-#pragma unroll
-              for (int i = 0; i < 16; ++i) un[i] = fmaf(ca, v[i], un[i]);
-            }
-            const float cb = s_err.coef[jj + 1];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) ut[i] = fmaf(cb, v[i], ut[i]);
-          }
-          float* uout = s_err.dst;
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float unew = fmaf(s_un.scale, un[i], up[i]);
-            if (mv && nb + i < p.B) {
-              uout[(size_t)(nb + i) * p.D + m] = unew;
-              const float r = (s_err.scale * ut[i]) / (abstol + fmaxf(fabsf(up[i]), fabsf(unew)) * reltol);
-              acc += (double)(r * r);
-            }
-          }
+        for (int i = 0; i < 8; ++i) {
+          const bool ok = full || (mv && nb + i < p.B);
+          up[i] = ok ? __ldcg(pu + (size_t)i * D) : 0.0f;
+          k1[i] = ok ? __ldcg(pk + (size_t)i * D) : 0.0f;
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&epi_done[u & 1]);
+      if (tr) FTRACE(1, 0, 4, 2 * (u >> 1));
+      mbar_wait(&acc_full[db], (uint32_t)((u >> 1) & 1));
+      tc_fence_after();
+      if (tr) FTRACE(1, 0, 4, 2 * (u >> 1) + 1);
+      float un[8], ut[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { un[i] = s_un.coef[0] * k1[i]; ut[i] = s_err.coef[0] * k1[i]; }
+#pragma unroll
+      for (int jj = 0; jj < 6; ++jj) {   // stage jj + 2
+        float v[8];
+        tmem_ld8(dcol + (uint32_t)(jj * 16), v);
+        if (jj == 5) {   // every accumulator of this thread has been read: the MMAs of unit u + 2 may overwrite them
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_free[db]);
+        }
+        float* kout = const_cast<float*>(s_err.src[jj + 1]) + e0;
+        if (full) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) __stcg(kout + (size_t)i * D, v[i]);
+        } else if (mv) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (nb + i < p.B) kout[(size_t)i * D] = v[i];
+        }
+        if (jj < 5) {
+          const float ca = s_un.coef[jj + 1];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) un[i] = fmaf(ca, v[i], un[i]);
+        }
+        const float cb = s_err.coef[jj + 1];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ut[i] = fmaf(cb, v[i], ut[i]);
+      }
+      float* uout = s_err.dst + e0;
+      const float sdt = s_un.scale, edt = s_err.scale;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float unew = fmaf(sdt, un[i], up[i]);
+        if (full || (mv && nb + i < p.B)) {
+          __stcg(uout + (size_t)i * D, unew);
+          const float r = (edt * ut[i]) / (abstol + fmaxf(fabsf(up[i]), fabsf(unew)) * reltol);
+          acc += (double)(r * r);
+        }
+      }
+      if (tr) FTRACE(1, 0, 5, u >> 1);
     }
     if (!p.single) {
       for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
@@ -590,6 +692,7 @@ __global__ void __launch_bounds__(kThreads, 1) kgemm_kernel(KgemmP p) {
         for (unsigned i = blockIdx.x + gridDim.x; i < (unsigned)LR_ERR_BLOCKS; i += gridDim.x) p.S->partials[i] = 0.0;
       }
     }
+    tc_fence_before();
   }
   __syncthreads();
   if (csize > 1) cluster_sync_all();   // peers may still multicast into this CTA / signal its barriers
@@ -633,31 +736,32 @@ FusedEngine::FusedEngine(lrnde_ctx* c, const lrnde_model* mm, const float* p, in
     : ctx(c), m(mm), ps(p), B(b), passes(npasses) {
   lrf_shape(m, &sh);
   ntiles = (int)((B + fused::kNT - 1) / fused::kNT);
+  nunits = (int)((B + 15) / 16);
   imgM = lrf_round_up((size_t)128 * sh.KS * 32, 1024);
-  imgW = lrf_round_up((size_t)sh.MT * sh.KS * 32, 1024);
-  pair_bytes = (size_t)sh.nfull * fused::kPieceBytes + (size_t)sh.ntail * fused::kTailBytes;
+  unit_bytes = (size_t)sh.nfull * fused::kPieceBytes + (size_t)sh.ntail * fused::kTailBytes;
   nbuf = (2 * imgM + 2 * (size_t)fused::kNT * sh.KS * 64 + 2048 <= 226 * 1024) ? 2 : 1;
   Mimg = (float*)ctx->alloc(2 * imgM);
-  W2img = (float*)ctx->alloc(2 * imgW * sh.n_mt);
-  hbuf = (float*)ctx->alloc((size_t)ntiles * 3 * pair_bytes);
-  // kgemm launch geometry: one cluster = the n_mt feature tiles of a sample tile (operand pieces multicast)
+  hbuf = (float*)ctx->alloc((size_t)ntiles * 4 * unit_bytes);
+  // kgemm launch geometry: one cluster = the n_mt feature tiles of the same samples (operand pieces multicast)
   cluster = (sh.n_mt <= 8 && !getenv("LRNDE_FUSED_NO_CLUSTER")) ? sh.n_mt : 1;
-  const size_t smem_k = 2 * imgW + 4 * (size_t)fused::kPieceBytes + 1024;
-  const size_t smem_c = 2 * imgM + (size_t)nbuf * fused::kNT * sh.KS * 64 + 1024;
+  ring = 8;
   static bool attr_set = false;
   if (!attr_set) {
-    LR_CUDA(cudaFuncSetAttribute(fused::chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    LR_CUDA(cudaFuncSetAttribute(fused::chain_kernel<ACT_IDENTITY>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    LR_CUDA(cudaFuncSetAttribute(fused::chain_kernel<ACT_TANH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    LR_CUDA(cudaFuncSetAttribute(fused::chain_kernel<ACT_GELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    LR_CUDA(cudaFuncSetAttribute(fused::chain_kernel<ACT_SIGMOID>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    LR_CUDA(cudaFuncSetAttribute(fused::chain_kernel<ACT_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     LR_CUDA(cudaFuncSetAttribute(fused::kgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     attr_set = true;
   }
-  (void)smem_c;
   int maxc = 0;
   if (cluster > 1) {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(cluster * 64);
     cfg.blockDim = dim3(fused::kThreads);
-    cfg.dynamicSmemBytes = smem_k;
+    cfg.dynamicSmemBytes = (size_t)ring * fused::kPieceBytes + 1024;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
@@ -667,13 +771,12 @@ FusedEngine::FusedEngine(lrnde_ctx* c, const lrnde_model* mm, const float* p, in
   }
   if (cluster == 1) maxc = 148 / sh.n_mt > 0 ? 148 / sh.n_mt : 1;
   if (const char* e = getenv("LRNDE_FUSED_MAXC")) maxc = std::max(1, atoi(e));
-  const int rounds = (ntiles + maxc - 1) / maxc;
-  nclusters = (ntiles + rounds - 1) / rounds;
+  const int rounds = (nunits + maxc - 1) / maxc;
+  nclusters = (nunits + rounds - 1) / rounds;
 }
 
 FusedEngine::~FusedEngine() {
   ctx->release(Mimg);
-  ctx->release(W2img);
   ctx->release(hbuf);
 }
 
@@ -684,14 +787,11 @@ void FusedEngine::prepare() {
   const float* W2a = ps + L2.w_off;   // [D x (H + td)] followed by the bias: one [D x Kaug] column-major block
   fused::mz_pack_kernel<<<sh.KS * 8, 128, 0, ctx->stream>>>(W1, W2a, sh.D, sh.H, sh.Kaug, sh.nfull, Mimg, (uint32_t)imgM, passes);
   LRF_COUNT(ctx);
-  fused::w2_pack_kernel<<<dim3(sh.KS * 8, sh.n_mt), 128, 0, ctx->stream>>>(W2a, sh.D, sh.Kaug, sh.nfull, sh.MT, W2img,
-                                                                         (uint32_t)imgW, passes);
-  LRF_COUNT(ctx);
   LR_CUDA(cudaGetLastError());
 }
 
-static void lrf_launch(FusedEngine& E, SolveDev* S, const LinComb* single, const LinComb* single_out, const int* done,
-                       int write_z) {
+static void lrf_launch_chain(FusedEngine& E, SolveDev* S, const LinComb* single, const LinComb* single_out, const int* done,
+                             int write_z) {
   const FusedShape& sh = E.sh;
   const LayerInfo& L1 = E.m->layers[0];
   fused::ChainP cp;
@@ -700,24 +800,36 @@ static void lrf_launch(FusedEngine& E, SolveDev* S, const LinComb* single, const
   cp.Mimg = E.Mimg; cp.imgM = (uint32_t)E.imgM;
   cp.w1t = sh.td ? E.ps + L1.w_off + (size_t)sh.D * sh.H : nullptr;
   cp.b1 = E.ps + L1.b_off;
-  cp.hbuf = E.hbuf; cp.pair_bytes = (uint32_t)E.pair_bytes;
-  cp.B = (int)E.B; cp.H = sh.H; cp.td = sh.td; cp.act = sh.act; cp.KS = sh.KS; cp.nfull = sh.nfull; cp.ntail = sh.ntail;
+  cp.hbuf = E.hbuf; cp.unit_bytes = (uint32_t)E.unit_bytes;
+  cp.B = (int)E.B; cp.H = sh.H; cp.td = sh.td; cp.KS = sh.KS; cp.nfull = sh.nfull; cp.ntail = sh.ntail;
   cp.passes = E.passes; cp.nbuf = E.nbuf; cp.write_z = write_z;
   const size_t smem_c = 2 * E.imgM + (size_t)E.nbuf * fused::kNT * sh.KS * 64 + 1024;
-  fused::chain_kernel<<<E.ntiles, fused::kThreads, smem_c, E.ctx->stream>>>(cp);
+  cudaStream_t st = E.ctx->stream;
+  switch (sh.act) {
+    case ACT_TANH: fused::chain_kernel<ACT_TANH><<<E.ntiles, fused::kThreads, smem_c, st>>>(cp); break;
+    case ACT_GELU: fused::chain_kernel<ACT_GELU><<<E.ntiles, fused::kThreads, smem_c, st>>>(cp); break;
+    case ACT_SIGMOID: fused::chain_kernel<ACT_SIGMOID><<<E.ntiles, fused::kThreads, smem_c, st>>>(cp); break;
+    case ACT_RELU: fused::chain_kernel<ACT_RELU><<<E.ntiles, fused::kThreads, smem_c, st>>>(cp); break;
+    default: fused::chain_kernel<ACT_IDENTITY><<<E.ntiles, fused::kThreads, smem_c, st>>>(cp); break;
+  }
   LRF_COUNT(E.ctx);
+  LR_CUDA(cudaGetLastError());
+}
 
+static void lrf_launch_kgemm(FusedEngine& E, SolveDev* S, const LinComb* single, const LinComb* single_out, const int* done) {
+  const FusedShape& sh = E.sh;
+  const LayerInfo& L2 = E.m->layers[1];
   fused::KgemmP kp;
   memset(&kp, 0, sizeof(kp));
   kp.S = S; kp.single = single; kp.single_out = single_out; kp.done = done;
-  kp.W2img = E.W2img; kp.imgW = (uint32_t)E.imgW; kp.hbuf = E.hbuf; kp.pair_bytes = (uint32_t)E.pair_bytes;
-  kp.B = (int)E.B; kp.D = sh.D; kp.MT = sh.MT; kp.n_mt = sh.n_mt; kp.KS = sh.KS; kp.nfull = sh.nfull; kp.ntail = sh.ntail;
-  kp.passes = E.passes; kp.ntiles = E.ntiles; kp.nclusters = E.nclusters; kp.ring = 4;
+  kp.W2a = E.ps + L2.w_off; kp.hbuf = E.hbuf; kp.unit_bytes = (uint32_t)E.unit_bytes;
+  kp.B = (int)E.B; kp.D = sh.D; kp.MT = sh.MT; kp.n_mt = sh.n_mt; kp.Kaug = sh.Kaug; kp.KS = sh.KS; kp.nfull = sh.nfull;
+  kp.ntail = sh.ntail; kp.passes = E.passes; kp.nunits = E.nunits; kp.nclusters = E.nclusters; kp.ring = E.ring;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(sh.n_mt * E.nclusters);
   cfg.blockDim = dim3(fused::kThreads);
-  cfg.dynamicSmemBytes = 2 * E.imgW + 4 * (size_t)fused::kPieceBytes + 1024;
+  cfg.dynamicSmemBytes = (size_t)E.ring * fused::kPieceBytes + 1024;
   cfg.stream = E.ctx->stream;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
@@ -727,6 +839,15 @@ static void lrf_launch(FusedEngine& E, SolveDev* S, const LinComb* single, const
   LRF_COUNT(E.ctx);
   LR_CUDA(cudaGetLastError());
 }
+
+static void lrf_launch(FusedEngine& E, SolveDev* S, const LinComb* single, const LinComb* single_out, const int* done,
+                       int write_z) {
+  lrf_launch_chain(E, S, single, single_out, done, write_z);
+  lrf_launch_kgemm(E, S, single, single_out, done);
+}
+
+void FusedEngine::step_chain(SolveDev* S, int write_z) { lrf_launch_chain(*this, S, nullptr, nullptr, nullptr, write_z); }
+void FusedEngine::step_kgemm(SolveDev* S) { lrf_launch_kgemm(*this, S, nullptr, nullptr, nullptr); }
 
 void FusedEngine::step(SolveDev* S, int write_z) { lrf_launch(*this, S, nullptr, nullptr, nullptr, write_z); }
 

@@ -34,14 +34,15 @@ struct FusedEngine {
   int64_t B;
   int passes;
   FusedShape sh;
-  int ntiles = 0;        // 64-sample tiles
+  int ntiles = 0;        // 64-sample tiles of the chain kernel
+  int nunits = 0;        // 16-sample units of the kgemm kernel
   int nbuf = 2;          // chain kernel: operand tile buffers
   int cluster = 1;       // kgemm: CTAs per cluster (= n_mt when the multicast path is usable)
   int nclusters = 1;     // kgemm: persistent clusters
+  int ring = 8;          // kgemm: operand pieces in flight
   float* Mimg = nullptr;   // chain A operand: [hi | lo] images of Mz, 128 rows
-  float* W2img = nullptr;  // kgemm A operands: n_mt x [hi | lo] images of W2a, MT rows
-  float* hbuf = nullptr;   // B operand images written by the chain kernel
-  size_t imgM = 0, imgW = 0, pair_bytes = 0;
+  float* hbuf = nullptr;   // operand images written by the chain kernel: per 16-sample unit, 96 rows = 6 stages x 16
+  size_t imgM = 0, unit_bytes = 0;
 
   static bool eligible(const lrnde_model* m);
   FusedEngine(lrnde_ctx* c, const lrnde_model* mm, const float* p, int64_t b, int npasses);
@@ -50,6 +51,8 @@ struct FusedEngine {
   void prepare();
   // one Tsit5 attempt from the descriptors of S (st[0..6], err): launches (1) and (2)
   void step(SolveDev* S, int write_z);
+  void step_chain(SolveDev* S, int write_z);   // the two launches of step(), separately (profiling)
+  void step_kgemm(SolveDev* S);
   // dst <- f(lincomb(in)) for a descriptor whose arrays live on S's tape; (out ? out : in)->dst receives k
   void eval(SolveDev* S, const LinComb* in, const LinComb* out, const int* done, int write_z);
 };
