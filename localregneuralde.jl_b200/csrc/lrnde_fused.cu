@@ -420,6 +420,7 @@ struct KgemmP {
   const float* hbuf;
   uint32_t unit_bytes;
   int B, D, MT, n_mt, Kaug, KS, nfull, ntail, passes, nunits, nclusters, ring;
+  int dbg;   // LRNDE_KG_DBG experiments (profiling only): 1 = no k stores, 2 = no loads, 4 = no residual, 8 = no u store
 };
 
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
@@ -453,12 +454,23 @@ __device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_
 
 constexpr int kDCol = 256;      // accumulator buffers at TMEM columns 256 and 384 (A operand in columns [0, 2 * 8 * KS))
 
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float (&v)[4]) {
+  uint32_t r[4];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(taddr)
+               : "memory");
+#pragma unroll
+  for (int j = 0; j < 4; ++j) v[j] = __uint_as_float(r[j]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 __global__ void __launch_bounds__(kThreads, 1) kgemm_kernel(KgemmP p) {
   if (p.done && *p.done) return;
   if (!p.single && p.S->done) return;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smR = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  __shared__ uint64_t a_ready, full_bar[8], empty_bar[8], acc_full[2], tmem_free[2];
+  __shared__ uint64_t a_ready, full_bar[2], empty_bar[2], acc_full[2], tmem_free[2];
   __shared__ uint32_t tmem_slot;
   __shared__ LinComb s_err, s_un;
   __shared__ double s_red[kEpiWarps];
@@ -470,13 +482,17 @@ __global__ void __launch_bounds__(kThreads, 1) kgemm_kernel(KgemmP p) {
   const uint16_t cmask = (uint16_t)((1u << csize) - 1u);
   const int mt = (int)(blockIdx.x % (unsigned)p.n_mt);
   const int cid = (int)(blockIdx.x / (unsigned)p.n_mt);
-  const int npieces = p.nfull + p.ntail;
   const int lo_col = p.KS * 8;
+  const uint32_t stage_bytes = (p.unit_bytes + 1023u) & ~1023u;   // one ring stage = the operand images of one unit
 
   if (threadIdx.x == 0) {
     mbar_init(&a_ready, (uint32_t)kEpiWarps);
-    for (int s = 0; s < p.ring; ++s) { mbar_init(&full_bar[s], 1u); mbar_init(&empty_bar[s], csize); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1u); mbar_init(&tmem_free[b], (uint32_t)(kEpiWarps / 2)); }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&full_bar[s], 1u);
+      mbar_init(&empty_bar[s], csize);
+      mbar_init(&acc_full[s], 1u);
+      mbar_init(&tmem_free[s], (uint32_t)kEpiWarps);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     if (p.single) { s_err = *p.single; s_un = p.single_out ? *p.single_out : *p.single; }
     else { s_err = p.S->err; s_un = p.S->st[5]; }
@@ -494,100 +510,108 @@ __global__ void __launch_bounds__(kThreads, 1) kgemm_kernel(KgemmP p) {
   if (threadIdx.x == 0) FTRACE(1, 0, 0, 0);
 
   if (warp == 0) {
-    // ---------------- operand pieces of every unit: each CTA of the cluster fetches a slice and multicasts it
-    int it = 0;
-    for (int g = cid; g < p.nunits; g += p.nclusters) {
+    // ---------------- operand images of every unit: each CTA of the cluster fetches a slice and multicasts it
+    int u = 0;
+    for (int g = cid; g < p.nunits; g += p.nclusters, ++u) {
       const uint8_t* src = reinterpret_cast<const uint8_t*>(p.hbuf) + (size_t)g * p.unit_bytes;
-      for (int pc = 0; pc < npieces; ++pc, ++it) {
-        const int s = it % p.ring, ph = (it / p.ring) & 1;
-        mbar_wait(&empty_bar[s], (uint32_t)(ph ^ 1));
-        const uint32_t bytes = (pc < p.nfull) ? (uint32_t)kPieceBytes : (uint32_t)kTailBytes;
-        const size_t off = (pc < p.nfull) ? (size_t)pc * kPieceBytes : (size_t)p.nfull * kPieceBytes + (size_t)(pc - p.nfull) * kTailBytes;
-        uint8_t* dst = smR + (size_t)s * kPieceBytes;
-        if (elect_one_sync()) {
-          FTRACE(1, 0, 1, it);
-          mbar_arrive_expect_tx(&full_bar[s], bytes);
-          if (csize > 1) {
-            const uint32_t sl = (((bytes + csize - 1) / csize) + 15u) & ~15u;
-            const uint32_t o = crank * sl;
-            if (o < bytes) bulk_g2s_mc(dst + o, src + off + o, min(sl, bytes - o), &full_bar[s], cmask);
-          } else {
-            bulk_g2s(dst, src + off, bytes, &full_bar[s]);
-          }
+      const int s = u & 1, ph = (u >> 1) & 1;
+      mbar_wait(&empty_bar[s], (uint32_t)(ph ^ 1));
+      uint8_t* dst = smR + (size_t)s * stage_bytes;
+      if (elect_one_sync()) {
+        FTRACE(1, 0, 1, u);
+        mbar_arrive_expect_tx(&full_bar[s], p.unit_bytes);
+        if (csize > 1) {
+          const uint32_t sl = (((p.unit_bytes + csize - 1) / csize) + 15u) & ~15u;
+          const uint32_t o = crank * sl;
+          if (o < p.unit_bytes) bulk_g2s_mc(dst + o, src + o, min(sl, p.unit_bytes - o), &full_bar[s], cmask);
+        } else {
+          bulk_g2s(dst, src, p.unit_bytes, &full_bar[s]);
         }
-        __syncwarp();
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    // ---------------- tcgen05.mma issue: D[128 features x (6 stages x 16 samples)] = A (TMEM) x operand pieces
+    // ---------------- tcgen05.mma issue: D[128 features x (6 stages x 16 samples)] = A (TMEM) x operand images
     const uint32_t idesc = p.single ? make_idesc(128, 16) : make_idesc(128, kUR);
     mbar_wait(&a_ready, 0);
     tc_fence_after();
     if (lane == 0) FTRACE(1, 0, 0, 1);
-    int it = 0, u = 0;
+    int u = 0;
     for (int g = cid; g < p.nunits; g += p.nclusters, ++u) {
       const int db = u & 1;
       if (u >= 2) { mbar_wait(&tmem_free[db], (uint32_t)(((u >> 1) - 1) & 1)); tc_fence_after(); }
+      mbar_wait(&full_bar[db], (uint32_t)((u >> 1) & 1));
+      tc_fence_after();
+      if (lane == 0) FTRACE(1, 0, 2, u);
       const uint32_t d = tmem_base + (uint32_t)(kDCol + db * 128);
-      uint32_t first = 0u;
-      for (int pc = 0; pc < npieces; ++pc, ++it) {
-        const int s = it % p.ring, ph = (it / p.ring) & 1;
-        mbar_wait(&full_bar[s], (uint32_t)ph);
-        tc_fence_after();
-        if (lane == 0) FTRACE(1, 0, 2, it);
-        const uint32_t b0 = smem_u32(smR + (size_t)s * kPieceBytes);
-        if (elect_one_sync()) {
-          if (pc < p.nfull) {
-            const uint32_t bh = desc_lo(b0), bl = desc_lo(b0 + kUR * 128);
+      const uint32_t b0 = smem_u32(smR + (size_t)db * stage_bytes);
+      if (elect_one_sync()) {
+        uint32_t first = 0u;
+        for (int pc = 0; pc < p.nfull; ++pc) {
+          const uint32_t bh = desc_lo(b0 + pc * kPieceBytes), bl = desc_lo(b0 + pc * kPieceBytes + kUR * 128);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint32_t ah = tmem_base + (uint32_t)((pc * 4 + k) * 8), al = ah + (uint32_t)lo_col;
-              if (p.passes == 3) {
-                mma_ts(d, al, bh + 2 * k, kHi128, idesc, first);
-                mma_ts(d, ah, bl + 2 * k, kHi128, idesc, 1u);
-                mma_ts(d, ah, bh + 2 * k, kHi128, idesc, 1u);
-              } else mma_ts(d, ah, bh + 2 * k, kHi128, idesc, first);
-              first = 1u;
-            }
-          } else {
-            const uint32_t bh = desc_lo(b0), bl = desc_lo(b0 + kUR * 32);
-            const uint32_t ah = tmem_base + (uint32_t)((p.nfull * 4 + (pc - p.nfull)) * 8), al = ah + (uint32_t)lo_col;
+          for (int k = 0; k < 4; ++k) {
+            const uint32_t ah = tmem_base + (uint32_t)((pc * 4 + k) * 8), al = ah + (uint32_t)lo_col;
             if (p.passes == 3) {
-              mma_ts(d, al, bh, kHi32, idesc, first);
-              mma_ts(d, ah, bl, kHi32, idesc, 1u);
-              mma_ts(d, ah, bh, kHi32, idesc, 1u);
-            } else mma_ts(d, ah, bh, kHi32, idesc, first);
+              mma_ts(d, al, bh + 2 * k, kHi128, idesc, first);
+              mma_ts(d, ah, bl + 2 * k, kHi128, idesc, 1u);
+              mma_ts(d, ah, bh + 2 * k, kHi128, idesc, 1u);
+            } else mma_ts(d, ah, bh + 2 * k, kHi128, idesc, first);
             first = 1u;
           }
-          if (csize > 1) mma_commit_mc(&empty_bar[s], cmask);
-          else mma_commit(&empty_bar[s]);
-          if (pc == npieces - 1) mma_commit(&acc_full[db]);
-          FTRACE(1, 0, 3, it);
         }
-        __syncwarp();
+        for (int t = 0; t < p.ntail; ++t) {
+          const uint32_t bb = b0 + p.nfull * kPieceBytes + t * kTailBytes;
+          const uint32_t bh = desc_lo(bb), bl = desc_lo(bb + kUR * 32);
+          const uint32_t ah = tmem_base + (uint32_t)((p.nfull * 4 + t) * 8), al = ah + (uint32_t)lo_col;
+          if (p.passes == 3) {
+            mma_ts(d, al, bh, kHi32, idesc, first);
+            mma_ts(d, ah, bl, kHi32, idesc, 1u);
+            mma_ts(d, ah, bh, kHi32, idesc, 1u);
+          } else mma_ts(d, ah, bh, kHi32, idesc, first);
+          first = 1u;
+        }
+        if (csize > 1) mma_commit_mc(&empty_bar[db], cmask);
+        else mma_commit(&empty_bar[db]);
+        mma_commit(&acc_full[db]);
+        FTRACE(1, 0, 3, u);
       }
+      __syncwarp();
     }
   } else {
-    // ---------------- warps 2..17: lane = output feature (coalesced global access), registers = 8 samples
+    // ---------------- warps 2..17: lane = output feature (coalesced global access), registers = 4 samples
     const int q = warp & 3, sub = (warp - 2) >> 2;
-    const int par = sub >> 1, half = sub & 1;
     const int mloc = q * 32 + lane;
     const int m = mt * p.MT + mloc;
     const bool mv = (mloc < p.MT) && (m < p.D);
     const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
     const bool tr = (threadIdx.x == 64);
-    // W2a tile -> tensor memory, tf32 hi / lo (every warp writes the K-steps ks = sub, sub + 4, ...)
-    for (int ks = sub; ks < p.KS; ks += 4) {
-      float hi[8], lo[8];
+    // W2a tile -> tensor memory, tf32 hi / lo (warp `sub` of a lane quarter writes the K-steps ks = sub, sub + 4, ...)
+    {
+      float w[4][8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const int k = ks * 8 + e;
-        const float w = (mv && k < p.Kaug) ? __ldg(p.W2a + (size_t)k * p.D + m) : 0.0f;
-        if (p.passes == 3) { hi[e] = tf32_rna(w); lo[e] = tf32_rna(w - hi[e]); }
-        else { hi[e] = w; lo[e] = 0.0f; }
+      for (int j = 0; j < 4; ++j) {
+        const int ks = sub + 4 * j;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int k = ks * 8 + e;
+          w[j][e] = (mv && k < p.Kaug) ? __ldg(p.W2a + (size_t)k * p.D + m) : 0.0f;
+        }
       }
-      tmem_st8(tlane + (uint32_t)(ks * 8), hi);
-      tmem_st8(tlane + (uint32_t)(lo_col + ks * 8), lo);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int ks = sub + 4 * j;
+        if (ks < p.KS) {
+          float hi[8], lo[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            if (p.passes == 3) { hi[e] = tf32_rna(w[j][e]); lo[e] = tf32_rna(w[j][e] - hi[e]); }
+            else { hi[e] = w[j][e]; lo[e] = 0.0f; }
+          }
+          tmem_st8(tlane + (uint32_t)(ks * 8), hi);
+          tmem_st8(tlane + (uint32_t)(lo_col + ks * 8), lo);
+        }
+      }
     }
     tmem_st_wait();
     tc_fence_before();
@@ -595,91 +619,131 @@ __global__ void __launch_bounds__(kThreads, 1) kgemm_kernel(KgemmP p) {
     if (lane == 0) mbar_arrive(&a_ready);
 
     const float abstol = p.S->abstol, reltol = p.S->reltol;
-    const int D = p.D;
+    const unsigned D = (unsigned)p.D;
     double acc = 0.0;
-    int u = 0;
-    for (int g = cid; g < p.nunits; g += p.nclusters, ++u) {
-      if ((u & 1) != par) continue;
+    // array base pointers at this thread's feature (element index inside an array = sample * D: 32 bits)
+    const float* pu = s_err.base + m;
+    const float* pk1 = s_err.src[0] + m;
+    float* po[7];
+#pragma unroll
+    for (int jj = 0; jj < 6; ++jj) po[jj] = const_cast<float*>(s_err.src[jj + 1]) + m;
+    po[6] = s_err.dst + m;
+    float* psingle = (p.single ? s_un.dst : s_err.dst) + m;
+    float ca[6], cb[7];
+#pragma unroll
+    for (int jj = 0; jj < 6; ++jj) ca[jj] = s_un.coef[jj];
+#pragma unroll
+    for (int jj = 0; jj < 7; ++jj) cb[jj] = s_err.coef[jj];
+    const float sdt = s_un.scale, edt = s_err.scale;
+    // uprev and k1 = fsalfirst are the only arrays an attempt reads: fetched one unit ahead
+    float up[4], k1[4];
+    auto fetch = [&](int g, float (&a)[4], float (&b)[4]) {
+      const int nb = g * 16 + sub * 4;
+      if (mv && nb + 4 <= p.B && !(p.dbg & 2)) {
+        const unsigned e = (unsigned)nb * D;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { a[i] = __ldcg(pu + (e + (unsigned)i * D)); b[i] = __ldcg(pk1 + (e + (unsigned)i * D)); }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const bool ok = mv && (nb + i < p.B) && !(p.dbg & 2);
+          a[i] = ok ? __ldcg(pu + (size_t)(nb + i) * D) : 0.0f;
+          b[i] = ok ? __ldcg(pk1 + (size_t)(nb + i) * D) : 0.0f;
+        }
+      }
+    };
+    // one unit: accumulators -> registers, TMEM buffer released, next unit's inputs requested, outputs stored
+    auto unit = [&](int g, int u, float (&upc)[4], float (&k1c)[4], float (&upn)[4], float (&k1n)[4]) {
       const int db = u & 1;
-      const int nb = g * 16 + half * 8;                 // first sample of this thread's 8
-      const bool full = mv && (nb + 8 <= p.B);
-      const size_t e0 = (size_t)nb * D + m;             // element offset of (sample nb, feature m)
-      const uint32_t dcol = tlane + (uint32_t)(kDCol + db * 128 + half * 8);
+      const int nb = g * 16 + sub * 4;                  // first sample of this thread's 4
+      const bool full = mv && (nb + 4 <= p.B);
+      const unsigned e0 = (unsigned)nb * D;             // element index of (sample nb, this feature)
+      const uint32_t dcol = tlane + (uint32_t)(kDCol + db * 128 + sub * 4);
+      if (tr) FTRACE(1, 0, 4, 2 * u);
+      mbar_wait(&acc_full[db], (uint32_t)((u >> 1) & 1));
+      tc_fence_after();
+      if (tr) FTRACE(1, 0, 4, 2 * u + 1);
       if (p.single) {
-        if (tr) FTRACE(1, 0, 4, 2 * (u >> 1));
-        mbar_wait(&acc_full[db], (uint32_t)((u >> 1) & 1));
-        tc_fence_after();
-        float v[8];
-        tmem_ld8(dcol, v);
+        float v[4];
+        tmem_ld4(dcol, v);
+        tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tmem_free[db]);
-        float* out = s_un.dst + e0;
         if (mv) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            if (nb + i < p.B) out[(size_t)i * D] = v[i];
+          for (int i = 0; i < 4; ++i)
+            if (nb + i < p.B) psingle[e0 + (unsigned)i * D] = v[i];
         }
-        continue;
+        return;
       }
-      // uprev and k1 = fsalfirst: the only arrays the attempt reads (issued before the accumulators are waited for)
-      float up[8], k1[8];
-      {
-        const float* pu = s_err.base + e0;
-        const float* pk = s_err.src[0] + e0;
+      float k[6][4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const bool ok = full || (mv && nb + i < p.B);
-          up[i] = ok ? __ldcg(pu + (size_t)i * D) : 0.0f;
-          k1[i] = ok ? __ldcg(pk + (size_t)i * D) : 0.0f;
-        }
-      }
-      if (tr) FTRACE(1, 0, 4, 2 * (u >> 1));
-      mbar_wait(&acc_full[db], (uint32_t)((u >> 1) & 1));
-      tc_fence_after();
-      if (tr) FTRACE(1, 0, 4, 2 * (u >> 1) + 1);
-      float un[8], ut[8];
+      for (int jj = 0; jj < 6; ++jj) tmem_ld4(dcol + (uint32_t)(jj * 16), k[jj]);
+      tmem_ld_wait();
+      if (tr) FTRACE(1, 0, 6, u);
+      // every accumulator of this thread is in registers: the MMAs of unit u + 2 may overwrite them
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_free[db]);
+      if (g + p.nclusters < p.nunits) fetch(g + p.nclusters, upn, k1n);
+      if (tr) FTRACE(1, 0, 7, u);
+      float un[4], ut[4], unew[4];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { un[i] = s_un.coef[0] * k1[i]; ut[i] = s_err.coef[0] * k1[i]; }
+      for (int i = 0; i < 4; ++i) { un[i] = ca[0] * k1c[i]; ut[i] = cb[0] * k1c[i]; }
 #pragma unroll
       for (int jj = 0; jj < 6; ++jj) {   // stage jj + 2
-        float v[8];
-        tmem_ld8(dcol + (uint32_t)(jj * 16), v);
-        if (jj == 5) {   // every accumulator of this thread has been read: the MMAs of unit u + 2 may overwrite them
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_free[db]);
-        }
-        float* kout = const_cast<float*>(s_err.src[jj + 1]) + e0;
-        if (full) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) __stcg(kout + (size_t)i * D, v[i]);
-        } else if (mv) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            if (nb + i < p.B) kout[(size_t)i * D] = v[i];
-        }
         if (jj < 5) {
-          const float ca = s_un.coef[jj + 1];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) un[i] = fmaf(ca, v[i], un[i]);
+          for (int i = 0; i < 4; ++i) un[i] = fmaf(ca[jj + 1], k[jj][i], un[i]);
         }
-        const float cb = s_err.coef[jj + 1];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) ut[i] = fmaf(cb, v[i], ut[i]);
+        for (int i = 0; i < 4; ++i) ut[i] = fmaf(cb[jj + 1], k[jj][i], ut[i]);
       }
-      float* uout = s_err.dst + e0;
-      const float sdt = s_un.scale, edt = s_err.scale;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float unew = fmaf(sdt, un[i], up[i]);
-        if (full || (mv && nb + i < p.B)) {
-          __stcg(uout + (size_t)i * D, unew);
-          const float r = (edt * ut[i]) / (abstol + fmaxf(fabsf(up[i]), fabsf(unew)) * reltol);
-          acc += (double)(r * r);
+      for (int i = 0; i < 4; ++i) unew[i] = fmaf(sdt, un[i], upc[i]);
+      if (tr) FTRACE(1, 0, 8, u);
+      if (full) {
+        if (!(p.dbg & 1)) {
+#pragma unroll
+          for (int jj = 0; jj < 6; ++jj)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) __stcg(po[jj] + (e0 + (unsigned)i * D), k[jj][i]);
+        }
+        if (!(p.dbg & 8)) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) __stcg(po[6] + (e0 + (unsigned)i * D), unew[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (!(p.dbg & 4)) {
+            const float r = (edt * ut[i]) / (abstol + fmaxf(fabsf(upc[i]), fabsf(unew[i])) * reltol);
+            acc += (double)(r * r);
+          } else acc += (double)unew[i];
+        }
+      } else if (mv) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (nb + i < p.B) {
+            const size_t e = (size_t)(nb + i) * D;
+#pragma unroll
+            for (int jj = 0; jj < 6; ++jj) po[jj][e] = k[jj][i];
+            po[6][e] = unew[i];
+            const float r = (edt * ut[i]) / (abstol + fmaxf(fabsf(upc[i]), fabsf(unew[i])) * reltol);
+            acc += (double)(r * r);
+          }
         }
       }
-      if (tr) FTRACE(1, 0, 5, u >> 1);
+      if (tr) FTRACE(1, 0, 5, u);
+    };
+    // two register sets for the fetched inputs: the unit loop is unrolled by two so that the values requested
+    // during unit u are first touched in unit u + 1 (no register moves that would wait for the loads)
+    float upB[4], k1B[4];
+    if (!p.single) fetch(cid, up, k1);
+    int u = 0;
+    for (int g = cid; g < p.nunits; g += 2 * p.nclusters, u += 2) {
+      unit(g, u, up, k1, upB, k1B);
+      if (g + p.nclusters < p.nunits) unit(g + p.nclusters, u + 1, upB, k1B, up, k1);
     }
     if (!p.single) {
       for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
@@ -743,7 +807,9 @@ FusedEngine::FusedEngine(lrnde_ctx* c, const lrnde_model* mm, const float* p, in
   Mimg = (float*)ctx->alloc(2 * imgM);
   hbuf = (float*)ctx->alloc((size_t)ntiles * 4 * unit_bytes);
   // kgemm launch geometry: one cluster = the n_mt feature tiles of the same samples (operand pieces multicast)
-  cluster = (sh.n_mt <= 8 && !getenv("LRNDE_FUSED_NO_CLUSTER")) ? sh.n_mt : 1;
+  // (measured at 8192 samples: 7-CTA clusters fit 15 at a time = 105 SMs, 80 us per attempt; 147 independent CTAs
+  // re-reading the operand images from L2: 64 us -- so the multicast path is opt-in until its ring is deeper)
+  cluster = (sh.n_mt <= 8 && getenv("LRNDE_FUSED_CLUSTER")) ? sh.n_mt : 1;
   ring = 8;
   static bool attr_set = false;
   if (!attr_set) {
@@ -761,7 +827,7 @@ FusedEngine::FusedEngine(lrnde_ctx* c, const lrnde_model* mm, const float* p, in
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(cluster * 64);
     cfg.blockDim = dim3(fused::kThreads);
-    cfg.dynamicSmemBytes = (size_t)ring * fused::kPieceBytes + 1024;
+    cfg.dynamicSmemBytes = 2 * lrf_round_up(unit_bytes, 1024) + 1024;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
@@ -773,6 +839,7 @@ FusedEngine::FusedEngine(lrnde_ctx* c, const lrnde_model* mm, const float* p, in
   if (const char* e = getenv("LRNDE_FUSED_MAXC")) maxc = std::max(1, atoi(e));
   const int rounds = (nunits + maxc - 1) / maxc;
   nclusters = (nunits + rounds - 1) / rounds;
+  if (getenv("LRNDE_FUSED_VERBOSE")) fprintf(stderr, "[lrnde fused] B=%lld units=%d cluster=%d max clusters=%d -> %d clusters, nbuf=%d\n", (long long)B, nunits, cluster, maxc, nclusters, nbuf);
 }
 
 FusedEngine::~FusedEngine() {
@@ -824,12 +891,13 @@ static void lrf_launch_kgemm(FusedEngine& E, SolveDev* S, const LinComb* single,
   kp.S = S; kp.single = single; kp.single_out = single_out; kp.done = done;
   kp.W2a = E.ps + L2.w_off; kp.hbuf = E.hbuf; kp.unit_bytes = (uint32_t)E.unit_bytes;
   kp.B = (int)E.B; kp.D = sh.D; kp.MT = sh.MT; kp.n_mt = sh.n_mt; kp.Kaug = sh.Kaug; kp.KS = sh.KS; kp.nfull = sh.nfull;
+  kp.dbg = getenv("LRNDE_KG_DBG") ? atoi(getenv("LRNDE_KG_DBG")) : 0;
   kp.ntail = sh.ntail; kp.passes = E.passes; kp.nunits = E.nunits; kp.nclusters = E.nclusters; kp.ring = E.ring;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(sh.n_mt * E.nclusters);
   cfg.blockDim = dim3(fused::kThreads);
-  cfg.dynamicSmemBytes = (size_t)E.ring * fused::kPieceBytes + 1024;
+  cfg.dynamicSmemBytes = 2 * lrf_round_up(E.unit_bytes, 1024) + 1024;
   cfg.stream = E.ctx->stream;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;

@@ -28,4 +28,4 @@ for B in [int(a) for a in sys.argv[1:]] or [8192, 128]:
         print("chain kernel, CTA 1 (cycles since TMEM allocation): misc = [start, A images in, inputs in TMEM, epilogue done, CTA done]")
         rows(a[0], ["misc", "mma_full_seen", "mma_issued", "epi_stage_begin", "epi_buf_free", "epi_tile_written", "epi_z_done"], a[0, 0, 0], 8)
         print("kgemm kernel, CTA 0: misc = [start, A images in]; per piece: producer issue / MMA saw it / MMA issued; per unit: epilogue [wait, go], done")
-        rows(a[1], ["misc", "prod_issue", "mma_full_seen", "mma_issued", "epi_wait_go", "epi_done"], a[1, 0, 0], 28)
+        rows(a[1], ["misc", "prod_issue", "mma_full_seen", "mma_issued", "epi_wait_go", "epi_done", "epi_ldtm_done", "epi_fetch_issued", "epi_fma_done"], a[1, 0, 0], 20)
