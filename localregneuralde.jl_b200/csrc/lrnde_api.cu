@@ -22,6 +22,7 @@
 #include "lrnde_smem_mlp.cuh"
 #include "lrnde_conv.cuh"
 #include "lrnde_fused.h"
+#include "lrnde_adjoint.h"
 
 // ------------------------------------------------------------------------------------------
 // errors
@@ -1016,6 +1017,7 @@ struct Solver {
   unsigned int* counters = nullptr;
   float* muglob = nullptr;
   float* ztape = nullptr;
+  float* htape = nullptr;
   cudaGraph_t while_graph = nullptr, body_graph = nullptr;
   cudaGraphExec_t while_exec = nullptr, body_exec = nullptr;
   long body_nodes = 0;
@@ -1062,13 +1064,18 @@ struct Solver {
     ctx->release(counters);
     ctx->release(muglob);
     ctx->release(ztape);
+    ctx->release(htape);
   }
 
-  // latent tape of the fused engine: one [B][LR_ZROW] image per tape array
-  void enable_latent(size_t zlen) {
+  // latent tape of the fused engine: one [B][LR_ZROW] image per tape array (+ the hidden tape when the adjoint follows)
+  void enable_latent(size_t zlen, bool hidden = false) {
     ztape = (float*)ctx->alloc(sizeof(float) * 7 * zlen * (size_t)h.cap);
     h.ztape = ztape;
     h.zlen = zlen;
+    if (hidden) {
+      htape = (float*)ctx->alloc(sizeof(float) * 7 * zlen * (size_t)h.cap);
+      h.htape = htape;
+    }
   }
 
   // adjoint in a data-parallel group: buffers of the mu-vector exchange
@@ -1324,6 +1331,15 @@ static void lr_grow_tape(Solver& S) {
     S.ztape = nz;
     S.h.ztape = nz;
     LR_CUDA(cudaMemcpyAsync(&S.dev->ztape, &S.h.ztape, sizeof(float*), cudaMemcpyHostToDevice, st));
+    if (S.htape) {
+      float* nh = (float*)ctx->alloc(sizeof(float) * 7 * S.h.zlen * (size_t)newcap);
+      LR_CUDA(cudaMemcpyAsync(nh, S.htape, sizeof(float) * 7 * S.h.zlen * (size_t)(S.h.slot + 1), cudaMemcpyDeviceToDevice, st));
+      LR_CUDA(cudaStreamSynchronize(st));
+      ctx->release(S.htape);
+      S.htape = nh;
+      S.h.htape = nh;
+      LR_CUDA(cudaMemcpyAsync(&S.dev->htape, &S.h.htape, sizeof(float*), cudaMemcpyHostToDevice, st));
+    }
   }
   S.h.cap = newcap;
   // patch the three fields in the device image
@@ -1525,6 +1541,8 @@ extern "C" int lrnde_ode_forward(lrnde_ctx* ctx, const lrnde_model* m, const lrn
 
   // ---- dense tape
   size_t slot_bytes = sizeof(float) * 7 * DB;
+  if (FusedEngine::eligible(m) && o->precision != LRNDE_PREC_FP32_SIMT)   // latent (+ hidden) tape of the fused engine
+    slot_bytes += sizeof(float) * 7 * (size_t)LR_ZROW * (size_t)B * (o->keep_tape ? 2 : 1);
   size_t budget_slots = std::max<size_t>(3, lr_tape_budget(ctx) / slot_bytes);
   const long tq1 = lr_now_us();
   int cap = (int)std::min<size_t>({(size_t)o->maxiters + 2, (size_t)96, budget_slots});
@@ -1551,13 +1569,16 @@ extern "C" int lrnde_ode_forward(lrnde_ctx* ctx, const lrnde_model* m, const lrn
   const long tq3 = lr_now_us();
   // latent-space engine (lrnde_fused.h): stage chain in H dimensions + one GEMM per attempt for k_2..k_7
   FusedEngine* fe = ev.fe.get();
-  const int write_z = 0;   // Z(k_2..k_6) are not read back by anything yet (the adjoint interpolates the k's)
+  // Z(k_j) and the hidden activations of every stage go to the latent / hidden tapes when a pullback will follow
+  // (the latent-space adjoint interpolates them instead of the D-dimensional k's)
+  const int write_z = o->keep_tape ? 1 : 0;
   if (fe) {
-    F.enable_latent(fe->zlen());
+    F.enable_latent(fe->zlen(), write_z != 0);
     ev.latent_of(F.tape, F.ztape);
+    if (F.htape) LR_CUDA(cudaMemsetAsync(F.htape, 0, sizeof(float) * fe->zlen(), st));   // C_0 = 0: u_0 = x + W2a C_0
   }
   auto eval = [&](const LinComb* in, const LinComb*, const int* done, const LinComb* out, bool side) {
-    if (fe) fe->eval(F.dev, in, out, done, 1);
+    if (fe) fe->eval(F.dev, in, out, done, 1);   // Z(k1) is always needed (next attempt), H(k1) when the tape is kept
     else ev.forward(in, done, out, side);
   };
   F.body = [&]() {
@@ -1805,13 +1826,46 @@ extern "C" int lrnde_ode_backward(lrnde_ctx* ctx, const lrnde_model* m, lrnde_ta
   int retcode_bwd = 0, nacc_b = 0, nrej_b = 0;
   long body_launches = 0;
   if (nsteps >= 1) {
+    const bool timing = getenv("LRNDE_TIMING") != nullptr;
+    long tmark = lr_now_us();
+    auto mark = [&](const char* what) {
+      if (!timing) return;
+      cudaStreamSynchronize(st);
+      const long now = lr_now_us();
+      fprintf(stderr, "[lrnde] bwd %-14s %8ld us\n", what, now - tmark);
+      tmark = now;
+    };
     Solver A(ctx, len, DB, 2, 1, o.maxiters + 1);
+    mark("solver alloc");
     A.h.is_adjoint = 1;
     A.h.fts = F.ts;
     A.h.ftape = F.tape;
     A.h.flen = DB;
     A.h.fnsteps = nsteps;
     A.h.ftdir = 1;
+    // latent-space adjoint (lrnde_adjoint.h): the forward solve kept its hidden tape
+    std::unique_ptr<LatentAdjoint> la;
+    if (F.htape && ev.use_umma && ctx->nranks == 1 && LatentAdjoint::eligible(m) && !getenv("LRNDE_NO_LATENT_ADJ")) {
+      la = std::make_unique<LatentAdjoint>(ctx, m, T->ps, B, ev.passes);
+      la->W1T = ev.WT[0]; la->Zx = F.ztape; la->x = F.tape;
+      la->prepare();
+      A.h.fhtape = F.htape;
+      A.h.fztape = F.ztape;
+      A.h.fzlen = F.h.zlen;
+      A.h.lat_mu_row = 1;
+    }
+    // alpha = W2^T lambda of the current state (start of a segment), then the stage-1 quantities
+    auto latent_begin = [&]() {
+      const LayerInfo& L2 = m->layers[1];
+      DenseP p;
+      memset(&p, 0, sizeof(p));
+      p.A = ev.WT[1]; p.lda = L2.in; p.M = L2.in; p.K = L2.out; p.td = 0; p.bias = 0;
+      p.xdesc = &A.dev->cur; p.ldx = L2.out; p.N = (int)B;
+      p.Y = la->alpha_in; p.ldy = LR_ZROW; p.act = ACT_IDENTITY; p.dact = -1; p.out_scale = 1.0f;
+      p.done = &A.dev->failed;
+      ev.dense(p, ev.packWT[1]);
+      la->begin(A.dev);
+    };
     if (ctx->nranks > 1) {
       A.h.total_len = (unsigned long long)D * (unsigned long long)ctx->total_batch + P;
       A.enable_mu_exchange(P);
@@ -1828,9 +1882,18 @@ extern "C" int lrnde_ode_backward(lrnde_ctx* ctx, const lrnde_model* m, lrnde_ta
     auto rhs = [&](const LinComb* in, const LinComb* y, const int* done, const LinComb*, bool) {
       ev.vjp(y, in, nullptr, in, -1.0f, nullptr, in, DB, -1.0f, 0.0f, done);
     };
-    A.body = [&]() { lr_step_body(A, rhs); };
+    A.body = [&]() {
+      if (la) {
+        la->attempt(A.dev);
+        controller_kernel<<<1, 32, 0, st>>>(A.dev);
+        LR_COUNT(ctx);
+        LR_CHECK_LAUNCH();
+      } else lr_step_body(A, rhs);
+    };
+    mark("latent setup");
     A.build_graphs(o.loop_mode);
     A.upload();
+    mark("graphs");
     // z(t2) = [dL/du(t2); 0]
     LR_CUDA(cudaMemsetAsync(A.tape, 0, sizeof(float) * len, st));
     std::vector<const float*> blocks;
@@ -1840,8 +1903,12 @@ extern "C" int lrnde_ode_backward(lrnde_ctx* ctx, const lrnde_model* m, lrnde_ta
       LR_COUNT(ctx);
     }
     lr_solver_start(A, rhs, 1);
+    mark("solver start");
+    if (la) latent_begin();
+    mark("latent begin");
     for (size_t si = 0; si < stops.size(); ++si) {
       A.run_segment();
+      mark("segment");
       if (si + 1 < stops.size()) {
         cot_blocks(stops[si], blocks);
         for (auto b : blocks) {
@@ -1850,7 +1917,8 @@ extern "C" int lrnde_ode_backward(lrnde_ctx* ctx, const lrnde_model* m, lrnde_ta
         }
         k1_desc_kernel<<<1, 32, 0, st>>>(A.dev);
         LR_COUNT(ctx);
-        rhs(&A.dev->st[6], &A.dev->yint[6], &A.dev->failed, nullptr, false);
+        if (la) latent_begin();
+        else rhs(&A.dev->st[6], &A.dev->yint[6], &A.dev->failed, nullptr, false);
         segment_begin_kernel<<<1, 32, 0, st>>>(A.dev, stops[si + 1], 1);
         LR_COUNT(ctx);
         nbwd_stops++;

@@ -98,11 +98,21 @@ struct SolveDev {
   // ([B][LR_ZROW] floats per array)
   float* ztape;
   size_t zlen;
+  float* htape;   // forward: hidden activations h of every k (H(k) = act(W1a [g; t; 1])); adjoint: delta_1 of every k
+  // adjoint: the latent / hidden tapes of the forward solve it interpolates (same slot layout as ftape)
+  const float* fztape;
+  const float* fhtape;
+  size_t fzlen;
+  LinComb cur;      // the current state as a descriptor (base = U(slot), t = c.t): written by k1_desc_kernel
+  int lat_mu_row;   // latent-space adjoint: the mu block's residual partial sums sit in partials[LR_ERR_BLOCKS ...]
 };
 #define LR_ZROW 128
 // the latent image of a tape array (p must point at the start of an array of this solve's tape)
 __host__ __device__ inline float* lr_zof(const SolveDev* S, const float* p) {
   return S->ztape + ((size_t)(p - S->tape) / S->len) * S->zlen;
+}
+__host__ __device__ inline float* lr_hof(const SolveDev* S, const float* p) {
+  return S->htape + ((size_t)(p - S->tape) / S->len) * S->zlen;
 }
 
 __host__ __device__ inline float* lr_slot_u(const SolveDev* S, int s) {

@@ -9,8 +9,7 @@
 
 #include <algorithm>
 
-#include "lrnde_act.cuh"
-#include "lrnde_tc.cuh"
+#include "lrnde_fused_dev.cuh"
 
 #ifdef LRNDE_UMMA_TRACE
 __device__ long long g_fused_trace[4096];
@@ -26,99 +25,6 @@ extern "C" int lrnde_debug_trace_fused(long long* out, int n) {
 
 namespace fused {
 using namespace umma;
-
-constexpr int kNT = 64;                         // samples per tile
-constexpr int kEpiWarps = 16;                   // warps 2..17: compute / epilogue (four per TMEM lane quarter)
-constexpr int kThreads = 64 + 32 * kEpiWarps;   // warp 0: bulk copies, warp 1: tcgen05.mma issue
-constexpr int kUR = 96;                         // rows of a kgemm operand unit: 6 stages x 16 samples
-constexpr int kPieceBytes = 2 * kUR * 128;      // kgemm ring stage: [hi | lo] of a 96-row x 32-float chunk
-constexpr int kTailBytes = 2 * kUR * 32;        // [hi | lo] of a 96-row x 8-float K-step
-
-// shared-memory matrix descriptors (cute::UMMA::SmemDescriptor), K-major:
-//   SWIZZLE_128B: rows of 128 B, 8-row atoms of 1024 B (SBO), 16-byte chunks XOR-ed with (row & 7)
-//   SWIZZLE_32B : rows of  32 B, 8-row atoms of  256 B (SBO), 16-byte halves XOR-ed with ((row >> 2) & 1)
-constexpr uint32_t kHi128 = (1024u >> 4) | (1u << 14) | (2u << 29);
-constexpr uint32_t kHi32 = (256u >> 4) | (1u << 14) | (6u << 29);
-
-template <int COLL>
-__device__ __forceinline__ void mma(uint32_t d_tmem, uint32_t a_lo32, uint32_t b_lo32, uint32_t hi32, uint32_t idesc,
-                                    uint32_t accumulate) {
-#define LR_FMMA(QUAL)                                                                                \
-  asm volatile(                                                                                      \
-      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"                                                \
-      "setp.ne.b32 p, %4, 0;\n\t"                                                                    \
-      "mov.b64 da, {%1, %5};\n\t"                                                                    \
-      "mov.b64 db, {%2, %5};\n\t"                                                                    \
-      "tcgen05.mma.cta_group::1.kind::tf32" QUAL " [%0], da, db, %3, p;\n\t}"                         \
-      ::"r"(d_tmem), "r"(a_lo32), "r"(b_lo32), "r"(idesc), "r"(accumulate), "r"(hi32)                \
-      : "memory")
-  if (COLL == 1) LR_FMMA(".collector::a::fill");
-  else if (COLL == 2) LR_FMMA(".collector::a::lastuse");
-  else LR_FMMA("");
-#undef LR_FMMA
-}
-
-// one K-step (8 tf32) of D += A B^T in 3xTF32 (A_lo B_hi + A_hi B_lo + A_hi B_hi) or plain TF32
-__device__ __forceinline__ void mma_kstep(uint32_t d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
-                                          uint32_t hi32, uint32_t idesc, uint32_t acc_first, int passes) {
-  if (passes == 3) {
-    mma<0>(d, a_lo, b_hi, hi32, idesc, acc_first);
-    mma<1>(d, a_hi, b_lo, hi32, idesc, 1u);
-    mma<2>(d, a_hi, b_hi, hi32, idesc, 1u);
-  } else {
-    mma<0>(d, a_hi, b_hi, hi32, idesc, acc_first);
-  }
-}
-
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
-  uint32_t r[16];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, "
-      "%13, %14, %15}, [%16];\n\t"
-      "tcgen05.wait::ld.sync.aligned;"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-#pragma unroll
-  for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
-}
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, "
-      "%14, %15, %16};"
-      ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
-        "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])),
-        "r"(__float_as_uint(v[7])), "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])),
-        "r"(__float_as_uint(v[11])), "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])),
-        "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-
-__device__ __forceinline__ void bulk_s2g(void* gdst, const void* ssrc, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ uint32_t cluster_nctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
-  return r;
-}
-
-// byte offset of element (row r, column k) inside the hi image of an R-row operand: nfull SWIZZLE_128B chunks of
-// 32 floats followed by SWIZZLE_32B K-steps of 8 floats
-__host__ __device__ inline uint32_t img_off(int R, int nfull, int r, int k) {
-  if (k < nfull * 32) {
-    const int c = k >> 5, kk = k & 31;
-    return (uint32_t)(c * R * 128 + (r >> 3) * 1024 + (r & 7) * 128 + (((kk >> 2) ^ (r & 7)) << 4) + (kk & 3) * 4);
-  }
-  const int s = (k - nfull * 32) >> 3, kk = k & 7;
-  return (uint32_t)(nfull * R * 128 + s * R * 32 + r * 32 + ((((kk >> 2) & 1) ^ ((r >> 2) & 1)) << 4) + (kk & 3) * 4);
-}
 
 // ---------------------------------------------------------------------------------------------------------
 // weight images (once per call: the parameters change every training iteration)
@@ -170,6 +76,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(ChainP p) {
   __shared__ LinComb sd[7];
   __shared__ float* s_tape;
   __shared__ float* s_ztape;
+  __shared__ float* s_htape;
   __shared__ size_t s_len, s_zlen;
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
@@ -192,7 +99,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(ChainP p) {
     if (p.single) sd[0] = *p.single;
     else for (int j = 0; j < 7; ++j) sd[j] = p.S->st[j];
     if (p.single) sd[1] = p.single_out ? *p.single_out : *p.single;
-    s_tape = p.S->tape; s_ztape = p.S->ztape; s_len = p.S->len; s_zlen = p.S->zlen;
+    s_tape = p.S->tape; s_ztape = p.S->ztape; s_htape = p.S->htape; s_len = p.S->len; s_zlen = p.S->zlen;
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512u)
@@ -205,6 +112,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(ChainP p) {
   const uint32_t tmem_base = tmem_slot;
   if (threadIdx.x == 0) FTRACE(0, 1, 0, 0);
   auto zof = [&](const float* ptr) -> float* { return s_ztape + ((size_t)(ptr - s_tape) / s_len) * s_zlen; };
+  auto hof = [&](const float* ptr) -> float* { return s_htape + ((size_t)(ptr - s_tape) / s_len) * s_zlen; };
 
   if (warp == 0) {
     // ---------------- Mz images in, operand images out (one elected lane; converged warp)
@@ -359,6 +267,14 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(ChainP p) {
         const float h = lr_act(ACT, x);
         v[i] = rowv ? h : hconst;
       }
+      const float* kdst = p.single ? sd[1].dst : (last_full ? sd[6].dst : d.dst);
+      if (p.write_z && s_htape && hrow < p.H + p.td + 1) {
+        // hidden tape for the latent-space adjoint (lrnde_adjoint.cu): H(k_j) = [h_j ; t_j ; 1]
+        float* ho = hof(kdst);
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (n0 + col + i < p.B) ho[(size_t)(n0 + col + i) * LR_ZROW + hrow] = v[i];
+      }
       if (in_img) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
@@ -381,7 +297,6 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(ChainP p) {
       tc_fence_after();
       if (tr) FTRACE(0, 1, 6, st);
       // Z(k_j) to the latent tape
-      const float* kdst = p.single ? sd[1].dst : (last_full ? sd[6].dst : d.dst);
       if (p.write_z || last_full) {
         float* zo = zof(kdst);
         const int slot = p.single ? 7 : 2 + st;
@@ -392,6 +307,30 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(ChainP p) {
             if (n0 + col + i < p.B) zo[(size_t)(n0 + col + i) * LR_ZROW + hrow] = v[i];
         }
       }
+    }
+    if (!p.single && p.write_z && s_htape && hrow < p.H + p.td + 1) {
+      // cumulative hidden image of the state: u_{n+1} = x + W2a C_{n+1},  C_{n+1} = C_n + dt sum_i a_7i H(k_i)
+      // (H(k_2..6) were stored above by this very thread, H(k_1) by an earlier launch)
+      const LinComb& d = sd[5];
+      float cs[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) cs[i] = 0.0f;
+      for (int s = 0; s < d.n; ++s) {
+        const float* hs = hof(d.src[s]);
+        const float cf = d.coef[s];
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (n0 + col + i < p.B) cs[i] = fmaf(cf, __ldcg(hs + (size_t)(n0 + col + i) * LR_ZROW + hrow), cs[i]);
+      }
+      const float* c0 = hof(d.base);
+      float* c1 = hof(d.dst);
+      const float scale = d.scale;
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        if (n0 + col + i < p.B) {
+          const size_t e = (size_t)(n0 + col + i) * LR_ZROW + hrow;
+          c1[e] = fmaf(scale, cs[i], __ldcg(c0 + e));
+        }
     }
     tc_fence_before();
     if (tr) FTRACE(0, 1, 0, 3);
@@ -423,49 +362,12 @@ struct KgemmP {
   int dbg;   // LRNDE_KG_DBG experiments (profiling only): 1 = no k stores, 2 = no loads, 4 = no residual, 8 = no u store
 };
 
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
-  uint32_t r[8];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n\t"
-      "tcgen05.wait::ld.sync.aligned;"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-      : "r"(taddr)
-      : "memory");
-#pragma unroll
-  for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j]);
-}
-__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
-               "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
-               "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
-               : "memory");
-}
-// D[tmem] (+)= A[tmem] * B[smem]^T : A = 128 lanes x 8 columns (tf32 in 32-bit cells)
-__device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo32, uint32_t hi32, uint32_t idesc,
-                                       uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "mov.b64 db, {%2, %5};\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], db, %3, p;\n\t}"
-      ::"r"(d_tmem), "r"(a_tmem), "r"(b_lo32), "r"(idesc), "r"(accumulate), "r"(hi32)
-      : "memory");
-}
-
-constexpr int kDCol = 256;      // accumulator buffers at TMEM columns 256 and 384 (A operand in columns [0, 2 * 8 * KS))
-
-__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float (&v)[4]) {
-  uint32_t r[4];
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
-               : "r"(taddr)
-               : "memory");
-#pragma unroll
-  for (int j = 0; j < 4; ++j) v[j] = __uint_as_float(r[j]);
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
+// NSTG = stage columns per sample (6: k_2..k_7 of a forward attempt; 2: the b / btilde combinations of an adjoint attempt);
+// ADJ: A = W1[:, :D]^T (features x hidden), epilogue = lambda_{n+1} and its residual (lrnde_adjoint.cu)
+template <int NSTG, bool ADJ>
 __global__ void __launch_bounds__(kThreads, 1) kgemm_kernel(KgemmP p) {
+  constexpr int UR = NSTG * 16;                   // rows of an operand unit
+  constexpr int PIECE = 2 * UR * 128, TAIL = 2 * UR * 32;
   if (p.done && *p.done) return;
   if (!p.single && p.S->done) return;
   extern __shared__ uint8_t smem_raw[];
@@ -532,7 +434,7 @@ __global__ void __launch_bounds__(kThreads, 1) kgemm_kernel(KgemmP p) {
     }
   } else if (warp == 1) {
     // ---------------- tcgen05.mma issue: D[128 features x (6 stages x 16 samples)] = A (TMEM) x operand images
-    const uint32_t idesc = p.single ? make_idesc(128, 16) : make_idesc(128, kUR);
+    const uint32_t idesc = p.single ? make_idesc(128, 16) : make_idesc(128, UR);
     mbar_wait(&a_ready, 0);
     tc_fence_after();
     if (lane == 0) FTRACE(1, 0, 0, 1);
@@ -548,7 +450,7 @@ __global__ void __launch_bounds__(kThreads, 1) kgemm_kernel(KgemmP p) {
       if (elect_one_sync()) {
         uint32_t first = 0u;
         for (int pc = 0; pc < p.nfull; ++pc) {
-          const uint32_t bh = desc_lo(b0 + pc * kPieceBytes), bl = desc_lo(b0 + pc * kPieceBytes + kUR * 128);
+          const uint32_t bh = desc_lo(b0 + pc * PIECE), bl = desc_lo(b0 + pc * PIECE + UR * 128);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const uint32_t ah = tmem_base + (uint32_t)((pc * 4 + k) * 8), al = ah + (uint32_t)lo_col;
@@ -561,8 +463,8 @@ __global__ void __launch_bounds__(kThreads, 1) kgemm_kernel(KgemmP p) {
           }
         }
         for (int t = 0; t < p.ntail; ++t) {
-          const uint32_t bb = b0 + p.nfull * kPieceBytes + t * kTailBytes;
-          const uint32_t bh = desc_lo(bb), bl = desc_lo(bb + kUR * 32);
+          const uint32_t bb = b0 + p.nfull * PIECE + t * TAIL;
+          const uint32_t bh = desc_lo(bb), bl = desc_lo(bb + UR * 32);
           const uint32_t ah = tmem_base + (uint32_t)((p.nfull * 4 + t) * 8), al = ah + (uint32_t)lo_col;
           if (p.passes == 3) {
             mma_ts(d, al, bh, kHi32, idesc, first);
@@ -595,7 +497,8 @@ __global__ void __launch_bounds__(kThreads, 1) kgemm_kernel(KgemmP p) {
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           const int k = ks * 8 + e;
-          w[j][e] = (mv && k < p.Kaug) ? __ldg(p.W2a + (size_t)k * p.D + m) : 0.0f;
+          if (ADJ) w[j][e] = (mv && k < p.Kaug) ? __ldg(p.W2a + (size_t)m * p.Kaug + k) : 0.0f;   // W1[k, m]: [H x D] column-major, Kaug = H here
+          else w[j][e] = (mv && k < p.Kaug) ? __ldg(p.W2a + (size_t)k * p.D + m) : 0.0f;
         }
       }
 #pragma unroll
@@ -626,7 +529,7 @@ __global__ void __launch_bounds__(kThreads, 1) kgemm_kernel(KgemmP p) {
     const float* pk1 = s_err.src[0] + m;
     float* po[7];
 #pragma unroll
-    for (int jj = 0; jj < 6; ++jj) po[jj] = const_cast<float*>(s_err.src[jj + 1]) + m;
+    for (int jj = 0; jj < 6; ++jj) po[jj] = ADJ ? nullptr : const_cast<float*>(s_err.src[jj + 1]) + m;
     po[6] = s_err.dst + m;
     float* psingle = (p.single ? s_un.dst : s_err.dst) + m;
     float ca[6], cb[7];
@@ -642,13 +545,13 @@ __global__ void __launch_bounds__(kThreads, 1) kgemm_kernel(KgemmP p) {
       if (mv && nb + 4 <= p.B && !(p.dbg & 2)) {
         const unsigned e = (unsigned)nb * D;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { a[i] = __ldcg(pu + (e + (unsigned)i * D)); b[i] = __ldcg(pk1 + (e + (unsigned)i * D)); }
+        for (int i = 0; i < 4; ++i) { a[i] = __ldcg(pu + (e + (unsigned)i * D)); b[i] = ADJ ? 0.0f : __ldcg(pk1 + (e + (unsigned)i * D)); }
       } else {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const bool ok = mv && (nb + i < p.B) && !(p.dbg & 2);
           a[i] = ok ? __ldcg(pu + (size_t)(nb + i) * D) : 0.0f;
-          b[i] = ok ? __ldcg(pk1 + (size_t)(nb + i) * D) : 0.0f;
+          b[i] = (ok && !ADJ) ? __ldcg(pk1 + (size_t)(nb + i) * D) : 0.0f;
         }
       }
     };
@@ -677,9 +580,9 @@ __global__ void __launch_bounds__(kThreads, 1) kgemm_kernel(KgemmP p) {
         }
         return;
       }
-      float k[6][4];
+      float k[NSTG][4];
 #pragma unroll
-      for (int jj = 0; jj < 6; ++jj) tmem_ld4(dcol + (uint32_t)(jj * 16), k[jj]);
+      for (int jj = 0; jj < NSTG; ++jj) tmem_ld4(dcol + (uint32_t)(jj * 16), k[jj]);
       tmem_ld_wait();
       if (tr) FTRACE(1, 0, 6, u);
       // every accumulator of this thread is in registers: the MMAs of unit u + 2 may overwrite them
@@ -689,24 +592,31 @@ __global__ void __launch_bounds__(kThreads, 1) kgemm_kernel(KgemmP p) {
       if (g + p.nclusters < p.nunits) fetch(g + p.nclusters, upn, k1n);
       if (tr) FTRACE(1, 0, 7, u);
       float un[4], ut[4], unew[4];
+      if constexpr (ADJ) {
+        // accumulators = W1^T Delta_b, W1^T Delta_btilde: lambda' = -W1^T delta  =>  lambda_{n+1} = lambda_n - dt (W1^T Delta_b),
+        // utilde = -dt (W1^T Delta_btilde)   (perform_step.jl:18-27 on the lambda block of the adjoint state)
 #pragma unroll
-      for (int i = 0; i < 4; ++i) { un[i] = ca[0] * k1c[i]; ut[i] = cb[0] * k1c[i]; }
+        for (int i = 0; i < 4; ++i) { unew[i] = fmaf(-edt, k[0][i], upc[i]); ut[i] = -k[NSTG - 1][i]; }
+      } else {
 #pragma unroll
-      for (int jj = 0; jj < 6; ++jj) {   // stage jj + 2
-        if (jj < 5) {
+        for (int i = 0; i < 4; ++i) { un[i] = ca[0] * k1c[i]; ut[i] = cb[0] * k1c[i]; }
 #pragma unroll
-          for (int i = 0; i < 4; ++i) un[i] = fmaf(ca[jj + 1], k[jj][i], un[i]);
+        for (int jj = 0; jj < NSTG; ++jj) {   // stage jj + 2
+          if (jj < NSTG - 1) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) un[i] = fmaf(ca[jj + 1], k[jj][i], un[i]);
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) ut[i] = fmaf(cb[jj + 1], k[jj][i], ut[i]);
         }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) ut[i] = fmaf(cb[jj + 1], k[jj][i], ut[i]);
+        for (int i = 0; i < 4; ++i) unew[i] = fmaf(sdt, un[i], upc[i]);
       }
-#pragma unroll
-      for (int i = 0; i < 4; ++i) unew[i] = fmaf(sdt, un[i], upc[i]);
       if (tr) FTRACE(1, 0, 8, u);
       if (full) {
-        if (!(p.dbg & 1)) {
+        if (!ADJ && !(p.dbg & 1)) {
 #pragma unroll
-          for (int jj = 0; jj < 6; ++jj)
+          for (int jj = 0; jj < NSTG; ++jj)
 #pragma unroll
             for (int i = 0; i < 4; ++i) __stcg(po[jj] + (e0 + (unsigned)i * D), k[jj][i]);
         }
@@ -726,8 +636,10 @@ __global__ void __launch_bounds__(kThreads, 1) kgemm_kernel(KgemmP p) {
         for (int i = 0; i < 4; ++i) {
           if (nb + i < p.B) {
             const size_t e = (size_t)(nb + i) * D;
+            if (!ADJ) {
 #pragma unroll
-            for (int jj = 0; jj < 6; ++jj) po[jj][e] = k[jj][i];
+              for (int jj = 0; jj < NSTG; ++jj) po[jj][e] = k[jj][i];
+            }
             po[6][e] = unew[i];
             const float r = (edt * ut[i]) / (abstol + fmaxf(fabsf(upc[i]), fabsf(unew[i])) * reltol);
             acc += (double)(r * r);
@@ -775,7 +687,7 @@ __global__ void __launch_bounds__(kThreads, 1) kgemm_kernel(KgemmP p) {
 
 static size_t lrf_round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-static bool lrf_shape(const lrnde_model* m, FusedShape* out) {
+bool lrf_shape(const lrnde_model* m, FusedShape* out) {
   if (!m->conv.empty() || m->layers.size() != 2) return false;
   if (m->input_act != ACT_IDENTITY) return false;
   const LayerInfo& L1 = m->layers[0];
@@ -792,6 +704,20 @@ static bool lrf_shape(const lrnde_model* m, FusedShape* out) {
   s.MT = (int)lrf_round_up((size_t)(s.D + s.n_mt - 1) / s.n_mt, 16);
   if (out) *out = s;
   return true;
+}
+
+static void lrf_set_attrs() {
+  static bool attr_set = false;
+  if (!attr_set) {
+    LR_CUDA(cudaFuncSetAttribute(fused::chain_kernel<ACT_IDENTITY>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    LR_CUDA(cudaFuncSetAttribute(fused::chain_kernel<ACT_TANH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    LR_CUDA(cudaFuncSetAttribute(fused::chain_kernel<ACT_GELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    LR_CUDA(cudaFuncSetAttribute(fused::chain_kernel<ACT_SIGMOID>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    LR_CUDA(cudaFuncSetAttribute(fused::chain_kernel<ACT_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    LR_CUDA(cudaFuncSetAttribute(fused::kgemm_kernel<6, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    LR_CUDA(cudaFuncSetAttribute(fused::kgemm_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    attr_set = true;
+  }
 }
 
 bool FusedEngine::eligible(const lrnde_model* m) { return lrf_shape(m, nullptr); }
@@ -811,16 +737,7 @@ FusedEngine::FusedEngine(lrnde_ctx* c, const lrnde_model* mm, const float* p, in
   // re-reading the operand images from L2: 64 us -- so the multicast path is opt-in until its ring is deeper)
   cluster = (sh.n_mt <= 8 && getenv("LRNDE_FUSED_CLUSTER")) ? sh.n_mt : 1;
   ring = 8;
-  static bool attr_set = false;
-  if (!attr_set) {
-    LR_CUDA(cudaFuncSetAttribute(fused::chain_kernel<ACT_IDENTITY>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-    LR_CUDA(cudaFuncSetAttribute(fused::chain_kernel<ACT_TANH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-    LR_CUDA(cudaFuncSetAttribute(fused::chain_kernel<ACT_GELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-    LR_CUDA(cudaFuncSetAttribute(fused::chain_kernel<ACT_SIGMOID>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-    LR_CUDA(cudaFuncSetAttribute(fused::chain_kernel<ACT_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-    LR_CUDA(cudaFuncSetAttribute(fused::kgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-    attr_set = true;
-  }
+  lrf_set_attrs();
   int maxc = 0;
   if (cluster > 1) {
     cudaLaunchConfig_t cfg;
@@ -832,7 +749,7 @@ FusedEngine::FusedEngine(lrnde_ctx* c, const lrnde_model* mm, const float* p, in
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    cudaError_t e = cudaOccupancyMaxActiveClusters(&maxc, fused::kgemm_kernel, &cfg);
+    cudaError_t e = cudaOccupancyMaxActiveClusters(&maxc, fused::kgemm_kernel<6, false>, &cfg);
     if (e != cudaSuccess || maxc < 1) { cudaGetLastError(); cluster = 1; }
   }
   if (cluster == 1) maxc = 148 / sh.n_mt > 0 ? 148 / sh.n_mt : 1;
@@ -903,8 +820,32 @@ static void lrf_launch_kgemm(FusedEngine& E, SolveDev* S, const LinComb* single,
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = E.cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
-  LR_CUDA(cudaLaunchKernelEx(&cfg, fused::kgemm_kernel, kp));
+  LR_CUDA(cudaLaunchKernelEx(&cfg, fused::kgemm_kernel<6, false>, kp));
   LRF_COUNT(E.ctx);
+  LR_CUDA(cudaGetLastError());
+}
+
+void lrf_launch_kgemm_adj(lrnde_ctx* ctx, SolveDev* S, const FusedShape& sh, const float* W1, const float* hbuf,
+                          size_t unit_bytes, int64_t B, int passes, int nunits, int nclusters) {
+  lrf_set_attrs();
+  fused::KgemmP kp;
+  memset(&kp, 0, sizeof(kp));
+  kp.S = S;
+  kp.W2a = W1; kp.hbuf = hbuf; kp.unit_bytes = (uint32_t)unit_bytes;
+  kp.B = (int)B; kp.D = sh.D; kp.MT = sh.MT; kp.n_mt = sh.n_mt; kp.Kaug = sh.H; kp.KS = sh.KS; kp.nfull = sh.nfull;
+  kp.ntail = sh.ntail; kp.passes = passes; kp.nunits = nunits; kp.nclusters = nclusters; kp.ring = 2;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(sh.n_mt * nclusters);
+  cfg.blockDim = dim3(fused::kThreads);
+  cfg.dynamicSmemBytes = 2 * lrf_round_up(unit_bytes, 1024) + 1024;
+  cfg.stream = ctx->stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  LR_CUDA(cudaLaunchKernelEx(&cfg, fused::kgemm_kernel<2, true>, kp));
+  LRF_COUNT(ctx);
   LR_CUDA(cudaGetLastError());
 }
 

@@ -27,6 +27,12 @@ struct FusedShape {
   int n_mt;    // number of feature tiles
 };
 
+// shape of an eligible model (false: the model is not a 2-layer TD-MLP the latent-space engines handle)
+bool lrf_shape(const lrnde_model* m, FusedShape* out);
+// lambda GEMM of the latent-space adjoint (lrnde_adjoint.h): kgemm_kernel<2, true> over units of 16 samples
+void lrf_launch_kgemm_adj(lrnde_ctx* ctx, SolveDev* S, const FusedShape& sh, const float* W1, const float* hbuf,
+                          size_t unit_bytes, int64_t B, int passes, int nunits, int nclusters);
+
 struct FusedEngine {
   lrnde_ctx* ctx;
   const lrnde_model* m;

@@ -685,6 +685,7 @@ __device__ inline void lr_write_interp(const SolveDev* S, LinComb& d, float tval
   d.scale = dt;
   d.n = 7;
   d.t = tval;
+  d.pad_ = __float_as_int(S->fts[n]);   // start time of the forward interval (latent-space adjoint: stage times)
 }
 
 // Stage descriptors of the attempt about to run from (slot, c.t, c.dt).
@@ -755,7 +756,14 @@ __global__ void k1_desc_kernel(SolveDev* S) {
   d.base = lr_slot_u(S, S->slot);
   d.t = S->c.t;
   d.dst = lr_slot_k(S, S->slot, 1);
-  if (S->is_adjoint) lr_write_interp(S, S->yint[6], S->c.t);
+  LinComb& c = S->cur;
+  lr_desc_clear(c);
+  c.base = lr_slot_u(S, S->slot);
+  c.t = S->c.t;
+  if (S->is_adjoint) {
+    lr_write_interp(S, S->yint[6], S->c.t);
+    lr_write_interp(S, S->yint[0], S->c.t);   // kept until the next call (latent-space adjoint: stage 1 of the segment)
+  }
 }
 
 // initdt part A (after initdt_norm1): dt0 and the Euler probe descriptor (st[0])
@@ -836,6 +844,11 @@ __global__ void controller_kernel(SolveDev* S) {
   v[1] = (S->reduce_mu && S->nranks > 1) ? lr_sum_partials(S->partials + 3 * LR_ERR_BLOCKS) : 0.0;
   if (threadIdx.x != 0) return;
   v[2] = v[3] = 0.0;
+  if (S->lat_mu_row) {   // latent-space adjoint: the mu block's partial sums (adj_mu_kernel)
+    double mu = 0.0;
+    for (int i = 0; i < LR_ERR_BLOCKS; ++i) mu += S->partials[LR_ERR_BLOCKS + i];
+    v[0] += mu;
+  }
   if (!(S->reduce_mu && S->nranks > 1)) lr_group_sum(S, v);
   else { double w[4] = {v[0], 0, 0, 0}; lr_group_sum(S, w); v[0] = w[0] + v[1]; }
   float EEst = sqrtf((float)v[0] / (float)(double)S->total_len);

@@ -163,6 +163,34 @@ __device__ __forceinline__ float tf32_rna(float x) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return __uint_as_float(r);
 }
+// ---- MN-major operands (both GEMM operands stored feature-contiguous per sample, K = samples): for tf32 the
+// only MN-major shared-memory layout is SWIZZLE_128B_BASE32B (cute Layout_MN_SW128_32B_Atom): atoms of 4 samples x
+// 128 bytes (32 rows), 32-byte chunks XOR-ed with the sample index; a_major = b_major = MN in the instruction descriptor
+__host__ __device__ constexpr uint32_t make_idesc_mn(int M, int N) {
+  return make_idesc(M, N) | (1u << 15) | (1u << 16);
+}
+// MN-major descriptor: atom (g, k4) of 512 B at ((k4 * 4 + g) * 512): LBO = 512 B between 32-row
+// groups, SBO = 2048 B between 4-sample groups, layout type 1 = SWIZZLE_128B_BASE32B
+constexpr uint32_t kDescHiMN = (2048u >> 4) | (1u << 14) | (1u << 29);
+__device__ __forceinline__ uint32_t desc_lo_mn(uint32_t saddr) { return ((saddr >> 4) & 0x3FFFu) | ((512u >> 4) << 16); }
+template <int COLL = 0>
+__device__ __forceinline__ void mma_tf32_mn(uint32_t d_tmem, uint32_t a_lo32, uint32_t b_lo32, uint32_t idesc,
+                                            uint32_t accumulate) {
+#define LR_MMA_MN(QUAL)                                                                              \
+  asm volatile(                                                                                      \
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"                                                \
+      "setp.ne.b32 p, %4, 0;\n\t"                                                                    \
+      "mov.b64 da, {%1, %5};\n\t"                                                                    \
+      "mov.b64 db, {%2, %5};\n\t"                                                                    \
+      "tcgen05.mma.cta_group::1.kind::tf32" QUAL " [%0], da, db, %3, p;\n\t}"                         \
+      ::"r"(d_tmem), "r"(a_lo32), "r"(b_lo32), "r"(idesc), "r"(accumulate), "r"(kDescHiMN)           \
+      : "memory")
+  if (COLL == 1) LR_MMA_MN(".collector::a::fill");
+  else if (COLL == 2) LR_MMA_MN(".collector::a::lastuse");
+  else LR_MMA_MN("");
+#undef LR_MMA_MN
+}
+
 // byte offset of (row, 16-byte chunk c) inside a K-major SWIZZLE_128B tile of 128-byte rows
 __device__ __forceinline__ uint32_t swz_off(int row, int c) {
   return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((c ^ (row & 7)) << 4));
