@@ -111,7 +111,9 @@ typedef struct {
                             evaluation of the main solve updates it through the closure exactly as Lux does
                             (momentum 0.1, unbiased variance) and the buffer holds st'.model on return */
   int32_t model_testmode; /* 1: Lux.testmode(st.model): BatchNorm normalises with model_state, no update */
-  int32_t reserved[3];
+  int32_t no_dx;          /* 1: lrnde_ode_backward does not return dL/dx (d_x may be NULL): nothing upstream of the
+                             layer has parameters, as in every classifier of experiments/src/construct.jl */
+  int32_t reserved[2];
 } lrnde_opts;
 
 typedef struct {
@@ -130,7 +132,9 @@ typedef struct {
 const char* lrnde_last_error(void);
 int lrnde_version(void);
 
-/* stream: a cudaStream_t, or NULL for a private non-blocking stream. */
+/* stream: a cudaStream_t the caller's buffers are ordered on, or NULL: the library then creates a BLOCKING stream,
+ * i.e. one that synchronises implicitly with the legacy default stream (stream 0): work the caller queued on stream 0
+ * before a call is finished before the library reads its buffers, and later stream-0 work waits for the call. */
 int lrnde_ctx_create(lrnde_ctx** out, int device, void* stream);
 int lrnde_ctx_destroy(lrnde_ctx* ctx);
 /* Blocks until everything this ctx enqueued has finished. */
@@ -337,6 +341,50 @@ int lrnde_head_ce(lrnde_ctx* ctx, const float* Wc, const float* u, const int32_t
  * experiments/src/construct.jl:104-152); step >= 1 is the 1-based iteration count. */
 int lrnde_adam_step(lrnde_ctx* ctx, float* p, const float* g, float* m, float* v, int64_t n,
                     float lr, float beta1, float beta2, float eps, int32_t step);
+
+/* The other Optimisers.jl rules experiments/src/construct.jl:104-125 can build: Descent / Momentum(lr, a) /
+ * Nesterov(lr, a) (cfg.optimizer == "sgd"), Adam(lr, (a, b), eps) (also "adamw": AdamW(lr) is Adam chained with
+ * WeightDecay(0)) and AdaMax(lr, (a, b), eps) (the physionet config, experiments/physionet/physionet.yml:27), each
+ * optionally chained with WeightDecay(weight_decay) (construct.jl:124-126: the decay term weight_decay * p is added
+ * to the rule's update).  s1 / s2: state buffers of n floats (momentum or first moment; second moment or
+ * infinity norm), zero-initialised by the caller, NULL where the rule has none.  DEVICE pointers. */
+enum { LRNDE_OPT_DESCENT = 0, LRNDE_OPT_MOMENTUM = 1, LRNDE_OPT_NESTEROV = 2, LRNDE_OPT_ADAM = 3, LRNDE_OPT_ADAMAX = 4 };
+int lrnde_opt_step(lrnde_ctx* ctx, int32_t kind, float* p, const float* g, float* s1, float* s2, int64_t n,
+                   float lr, float a, float b, float eps, float weight_decay, int32_t step);
+
+/* Sum of the DEVICE vector v[n] over the data-parallel group of lrnde_ctx_set_dist, in place, identical bits on
+ * every rank (peer loads over NVLink through the mailboxes; fixed rank order): the once-per-iteration all-reduce
+ * of the parameter gradients (Zygote's gradient of the global-mean loss in the reference's
+ * FluxMPI-less single-process runs).  Every rank must call it in the same order.  No-op on a single-rank ctx. */
+int lrnde_allreduce_sum(lrnde_ctx* ctx, float* v, int64_t n);
+
+/* The saved states of a kept solution, after the call: lrnde_ode_forward may run with u_save = NULL (every-step
+ * saves of the :biased path, neural_ode.jl:86-100: the count is only known afterwards, stats->nsave_out) and the
+ * caller then sizes u_save.  Pointers as in the forward call (HOST when it had host_buffers). */
+int lrnde_ode_saved_states(lrnde_ctx* ctx, const lrnde_model* m, lrnde_tape* tape, float* u_save,
+                           int64_t u_save_cap, float* save_times);
+
+/* One gradient evaluation of the MNIST classifier Chain(FlattenLayer, NeuralODE, diffeqsol_to_array,
+ * Dense(D => C)) (experiments/src/construct.jl:180-200) under logitcrossentropy + w_reg * reg_val
+ * (construct.jl:19-31): what Zygote.pullback computes inside run_training_step (experiments/src/utils.jl:106-115).
+ * u(t2) and its cotangent stay on the device; with o->host_buffers only x [D,B], labels (0-based), ps and Wc
+ * ([C x D] weight then [C] bias) go in and loss_ce (HOST scalar, the cross-entropy term), d_ps, d_Wc come out.
+ * grad_scale multiplies the cross-entropy cotangent (1 / nranks for a global-mean loss).  stats: forward fields
+ * of lrnde_ode_forward plus the *_bwd fields. */
+int lrnde_classifier_grad(lrnde_ctx* ctx, const lrnde_model* m, const lrnde_opts* o, const float* ps,
+                          const float* Wc, const float* x, const int32_t* labels, int64_t B, int32_t C,
+                          float w_reg, float grad_scale, float* loss_ce, float* d_ps, float* d_Wc,
+                          lrnde_stats* stats);
+
+/* Microseconds per launch of one attempt of the latent-space adjoint {chain, lambda GEMM, pairacc, reduce + mu,
+ * whole attempt}, measured with CUDA events by the last lrnde_ode_backward that ran with the environment variable
+ * LRNDE_PROFILE_ADJ=<iterations> set (roofline probe of bench.py). */
+int lrnde_profile_adjoint_last(float* us5);
+
+/* Roofline probe of the latent-space forward engine: `iters` repetitions of one Tsit5 attempt (same descriptors),
+ * CUDA events on the ctx stream; us[0] = chain kernel, us[1] = kgemm kernel, us[2] = the attempt (both). */
+int lrnde_profile_step(lrnde_ctx* ctx, const lrnde_model* m, const lrnde_opts* o, const float* ps, const float* x,
+                       int64_t B, int32_t iters, float* us);
 
 /* Roofline probe: times `iters` back-to-back f(u, ps, t) evaluations (DEVICE pointers) with
  * CUDA events on the ctx stream; *ms_per_eval is the mean, *launches_per_eval the kernels one

@@ -32,7 +32,7 @@ class Opts(C.Structure):
         ("nsave", C.c_int32), ("save_start", C.c_int32), ("precision", C.c_int32),
         ("pow_mode", C.c_int32), ("host_buffers", C.c_int32), ("keep_tape", C.c_int32),
         ("loop_mode", C.c_int32), ("last_only", C.c_int32), ("model_state", C.c_void_p),
-        ("model_testmode", C.c_int32), ("reserved", C.c_int32 * 3),
+        ("model_testmode", C.c_int32), ("no_dx", C.c_int32), ("reserved", C.c_int32 * 2),
     ]
 
 
@@ -87,7 +87,11 @@ SYMBOLS = [
     "lrnde_gru_backward", "lrnde_gru_tape_free", "lrnde_mlp_forward", "lrnde_mlp_backward",
     "lrnde_reparameterize", "lrnde_latent_loss", "lrnde_conv_model_create", "lrnde_dynamics_vjp",
     "lrnde_conv2d_forward", "lrnde_conv2d_backward", "lrnde_batchnorm_forward", "lrnde_batchnorm_backward",
+    "lrnde_opt_step", "lrnde_allreduce_sum", "lrnde_ode_saved_states", "lrnde_classifier_grad",
+    "lrnde_profile_adjoint_last", "lrnde_profile_step",
 ]
+
+OPT = {"descent": 0, "momentum": 1, "nesterov": 2, "adam": 3, "adamax": 4}
 
 
 def lib():
@@ -151,6 +155,13 @@ def lib():
     L.lrnde_mlp_backward.argtypes = [vp, C.POINTER(LayerDesc), i32, vp, vp, vp, i64, i32, vp, vp]
     L.lrnde_reparameterize.argtypes = [vp, vp, i32, i64, C.c_uint64, i32, i32, vp, vp, vp, vp, vp]
     L.lrnde_latent_loss.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i64, f32, i32, vp, vp, vp, vp]
+    L.lrnde_opt_step.argtypes = [vp, i32, vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i32]
+    L.lrnde_allreduce_sum.argtypes = [vp, vp, i64]
+    L.lrnde_ode_saved_states.argtypes = [vp, vp, vp, vp, i64, vp]
+    L.lrnde_classifier_grad.argtypes = [vp, vp, C.POINTER(Opts), vp, vp, vp, vp, i64, i32, f32, f32, vp, vp, vp,
+                                        C.POINTER(Stats)]
+    L.lrnde_profile_adjoint_last.argtypes = [vp]
+    L.lrnde_profile_step.argtypes = [vp, vp, C.POINTER(Opts), vp, vp, i64, i32, vp]
     for name in SYMBOLS:
         fn = getattr(L, name)
         if name not in ("lrnde_last_error", "lrnde_model_nparams", "lrnde_model_state_dims", "lrnde_gru_nparams"):

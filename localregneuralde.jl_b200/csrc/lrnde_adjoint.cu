@@ -56,6 +56,8 @@ __device__ __forceinline__ void act_pair(float x, float& h, float& s) {
 // TMEM: [Mz hi | Mz lo | Mh^T hi | Mh^T lo] as A operands (8 KS columns each), then one 32-column accumulator per half
 // (p = Mz c first, Mh^T eps once p has been read).
 // ---------------------------------------------------------------------------------------------------------
+constexpr int kTapeBufs = 3;                       // ring of [64 samples][LR_ZROW] tiles of the forward hidden tape
+constexpr int kTapeBufBytes = kNT * LR_ZROW * 4;   // 32 KB
 struct AChainP {
   SolveDev* S;
   int single;            // 1: stage-1 quantities of the current state (alpha from alpha_in, time / interpolant yint[0])
@@ -106,7 +108,7 @@ __global__ void __launch_bounds__(kThreads, 1) adj_chain_kernel(AChainP p) {
   if (p.single ? S->failed : S->done) return;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  __shared__ uint64_t a_ready, bfull[2], pdone[2], pread[2], xdone[2], out_full;
+  __shared__ uint64_t a_ready, bfull[2], pdone[2], pread[2], xdone[2], out_full, tfull[kTapeBufs], tempty[kTapeBufs];
   __shared__ uint32_t tmem_slot;
   __shared__ LinComb sd[6], sy[7];
   __shared__ float s_bt[7];
@@ -122,10 +124,12 @@ __global__ void __launch_bounds__(kThreads, 1) adj_chain_kernel(AChainP p) {
   const uint32_t tileB = (uint32_t)(p.nfull * 8192 + p.ntail * 2048);   // [hi | lo] images of a 32-sample operand tile
   uint8_t* tC[2] = {smem, smem + tileB};
   uint8_t* tE[2] = {smem + 2 * (size_t)tileB, smem + 3 * (size_t)tileB};
+  uint8_t* tbuf = smem + 4 * (size_t)tileB;        // kTapeBufs tape tiles (tileB is a multiple of 1024)
 
   if (threadIdx.x == 0) {
     mbar_init(&a_ready, (uint32_t)kEpiWarps);
     mbar_init(&out_full, (uint32_t)kEpiWarps);
+    for (int b = 0; b < kTapeBufs; ++b) { mbar_init(&tfull[b], 1u); mbar_init(&tempty[b], (uint32_t)kEpiWarps); }
     for (int c = 0; c < 2; ++c) {
       mbar_init(&bfull[c], (uint32_t)(kEpiWarps / 2));
       mbar_init(&pdone[c], 1u);
@@ -152,6 +156,28 @@ __global__ void __launch_bounds__(kThreads, 1) adj_chain_kernel(AChainP p) {
   auto arr = [&](int idx) -> float* { return p.ws + (size_t)idx * p.zlen; };
 
   if (warp == 0) {
+    // ---------------- forward hidden tape in: per stage the 7 H(k_i) tiles then the C_n tile of the interval that
+    // holds the stage time, bulk-copied onto a ring (the interpolant does not depend on lambda: it runs ahead)
+    {
+      const int nvalid = min(kNT, p.B - n0);
+      const uint32_t bytes = (uint32_t)nvalid * LR_ZROW * 4u;
+      int it = 0;
+      for (int jj = 0; jj < nst; ++jj) {
+        const LinComb& yd = p.single ? sy[0] : sy[jj + 1];
+        const size_t slotn = (size_t)(yd.base - s_ftape) / ((size_t)7 * s_flen);
+        const float* hb = s_fh + slotn * 7 * s_fzlen;
+        for (int s = 0; s < 8; ++s, ++it) {
+          const int b = it % kTapeBufs;
+          const float* src = (s == 7) ? hb : hb + (size_t)(s < 6 ? s + 1 : 8) * s_fzlen;   // H(k_7) = H(k_1) of the next slot
+          mbar_wait(&tempty[b], (uint32_t)(((it / kTapeBufs) & 1) ^ 1));
+          if (elect_one_sync()) {
+            mbar_arrive_expect_tx(&tfull[b], bytes);
+            bulk_g2s(tbuf + (size_t)b * kTapeBufBytes, src + (size_t)n0 * LR_ZROW, bytes, &tfull[b]);
+          }
+          __syncwarp();
+        }
+      }
+    }
     // ---------------- Delta_b / Delta_bt operand images out (units of 16 samples for the lambda GEMM)
     if (!p.single) {
       mbar_wait(&out_full, 0);
@@ -294,20 +320,26 @@ __global__ void __launch_bounds__(kThreads, 1) adj_chain_kernel(AChainP p) {
       float c[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) c[i] = 0.0f;
-      if (rowc) {
-        const size_t slotn = (size_t)(yd.base - s_ftape) / ((size_t)7 * s_flen);
-        const float* hb = s_fh + slotn * 7 * s_fzlen;
-        for (int s = 0; s < 7; ++s) {
-          const float* src = hb + (size_t)(s < 6 ? s + 1 : 8) * s_fzlen;   // H(k_7) = H(k_1) of the next slot
-          const float cf = yd.coef[s];
+      for (int s = 0; s < 8; ++s) {
+        const int it = jj * 8 + s;
+        const int b = it % kTapeBufs;
+        mbar_wait(&tfull[b], (uint32_t)((it / kTapeBufs) & 1));
+        if (rowc) {
+          const float* tb = reinterpret_cast<const float*>(tbuf + (size_t)b * kTapeBufBytes) + (cg * 32 + rbase) * LR_ZROW + hrow;
+          if (s < 7) {
+            const float cf = yd.coef[s];
 #pragma unroll
-          for (int i = 0; i < 16; ++i)
-            if (nb + i < p.B) c[i] = fmaf(cf, __ldcg(src + e0 + (size_t)i * LR_ZROW), c[i]);
+            for (int i = 0; i < 16; ++i)
+              if (nb + i < p.B) c[i] = fmaf(cf, tb[i * LR_ZROW], c[i]);
+          } else {
+            const float sc = yd.scale;
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (nb + i < p.B) c[i] = fmaf(sc, c[i], tb[i * LR_ZROW]);
+          }
         }
-        const float sc = yd.scale;
-#pragma unroll
-        for (int i = 0; i < 16; ++i)
-          if (nb + i < p.B) c[i] = fmaf(sc, c[i], __ldcg(hb + e0 + (size_t)i * LR_ZROW));
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[b]);
       }
       {
         const float cextra = (hrow == p.Kaug) ? tau : ((hrow == p.Kaug + 1) ? 1.0f : 0.0f);
@@ -729,7 +761,7 @@ struct AMuP {
   long nparams;
 };
 // mu' = -J_p^T lambda:  mu_{n+1} = mu_n - dt dW_b,  utilde = -dt dW_bt,  residual partial sums (perform_step.jl:18-27,34-38)
-__global__ void __launch_bounds__(256) adj_mu_kernel(AMuP p) {
+__global__ void __launch_bounds__(512) adj_mu_kernel(AMuP p) {
   SolveDev* S = p.S;
   if (S->done) return;
   const int slot = S->slot, next = (S->slot + 1) % S->cap;
@@ -739,6 +771,10 @@ __global__ void __launch_bounds__(256) adj_mu_kernel(AMuP p) {
   const int H = p.H, D = p.D, Kaug = p.Kaug;
   const long n1 = (long)H * (D + p.td + 1), n2 = (long)D * Kaug;
   const size_t RXs = (size_t)p.ntile * 128 * 128;   // stride between the b and btilde blocks of RX / RL
+  const bool multi = S->reduce_mu && S->nranks > 1;
+  const int par = (int)(S->mseq & 1ull);
+  float* st0 = multi ? lr_mbox_stage(S->mbox[S->rank], par, 0) : nullptr;
+  float* st1 = multi ? lr_mbox_stage(S->mbox[S->rank], par, 1) : nullptr;
   double acc = 0.0;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n1 + n2; i += (long)gridDim.x * blockDim.x) {
     float g0, g1;   // dW_b, dW_bt
@@ -751,6 +787,7 @@ __global__ void __launch_bounds__(256) adj_mu_kernel(AMuP p) {
         const float* w = p.W2a + d;
         const float* P0 = p.RP + r;                 // RP[0][k][r]
         const float* P1 = p.RP + 16384 + r;         // RP[1][k][r]
+#pragma unroll 8
         for (int k = 0; k < Kaug; ++k) {
           const float wv = __ldg(w + (size_t)k * D);
           a0 = fmaf(P0[k * 128], wv, a0);
@@ -770,6 +807,7 @@ __global__ void __launch_bounds__(256) adj_mu_kernel(AMuP p) {
       const float* P0 = p.RP + 2 * 16384 + (size_t)k * 128;   // RP[2][k][r]
       const float* P1 = p.RP + 3 * 16384 + (size_t)k * 128;   // RP[3][k][r]
       const float* w = p.W1T + d;
+#pragma unroll 8
       for (int r = 0; r < H; ++r) {
         const float wv = __ldg(w + (size_t)r * D);
         a0 = fmaf(P0[r], wv, a0);
@@ -778,6 +816,11 @@ __global__ void __launch_bounds__(256) adj_mu_kernel(AMuP p) {
       g0 = fmaf(-dt, a0, p.RL[(size_t)d * 128 + k]);
       g1 = fmaf(-dt, a1, p.RL[RXs + (size_t)d * 128 + k]);
     }
+    if (multi) {   // this rank's batch-partial sums: published, summed over ranks by adj_mu_finish_kernel
+      st0[pidx] = g0;
+      st1[pidx] = g1;
+      continue;
+    }
     const float mn = mu_n[pidx];
     const float mv = fmaf(-dt, g0, mn);
     mu_new[pidx] = mv;
@@ -785,7 +828,77 @@ __global__ void __launch_bounds__(256) adj_mu_kernel(AMuP p) {
     const float r = ut / (abstol + fmaxf(fabsf(mn), fabsf(mv)) * reltol);
     acc += (double)(r * r);
   }
+  if (multi) {
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned int prev = atomicAdd(S->mucounter, 1u);
+      if (prev == gridDim.x - 1) {   // last block: everything of this rank is visible, raise the flags on every peer
+        *S->mucounter = 0;
+        __threadfence_system();
+        for (int r = 0; r < S->nranks; ++r) {
+          volatile unsigned long long* f = &S->mbox[r]->mflag[par][S->rank];
+          *f = S->mseq + 1;
+        }
+      }
+    }
+    return;
+  }
   // block sum (fixed order)
+  __shared__ double sh[16];
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += sh[w];
+    S->partials[LR_ERR_BLOCKS + blockIdx.x] = s;
+  }
+}
+
+// Data-parallel group: mu is a batch sum and enters the error norm non-linearly, so every rank adds all
+// ranks' (dW_b, dW_bt) in rank order (identical bits everywhere) and advances a replicated GLOBAL mu (S->muglob, one
+// vector per ring slot) for the norm, next to its own batch-partial mu in the state (what the caller all-reduces).
+// The exchange sequence number is advanced by controller_kernel.
+__global__ void __launch_bounds__(256) adj_mu_finish_kernel(SolveDev* S) {
+  if (S->done) return;
+  const int par = (int)(S->mseq & 1ull);
+  LrMailbox* mine = S->mbox[S->rank];
+  if (threadIdx.x == 0) {
+    long long spins = 0;
+    for (int r = 0; r < S->nranks; ++r) {
+      volatile unsigned long long* f = &mine->mflag[par][r];
+      while (*f != S->mseq + 1) {
+        __nanosleep(40);
+        if (++spins > (1ll << 26)) { S->failed = 1; break; }   // a peer never arrived (~10 s): give up instead of hanging
+      }
+    }
+    __threadfence_system();
+  }
+  __syncthreads();
+  const int slot = S->slot, next = (S->slot + 1) % S->cap;
+  const size_t P = S->mu_len;
+  const float* mu_n = lr_slot_u(S, slot) + S->lam_len;
+  float* mu_new = lr_slot_u(S, next) + S->lam_len;
+  const float* mg_n = S->muglob + (size_t)slot * P;
+  float* mg_new = S->muglob + (size_t)next * P;
+  const float* own0 = lr_mbox_stage(mine, par, 0);
+  const float dt = S->err.scale, abstol = S->abstol, reltol = S->reltol;
+  double acc = 0.0;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < P; i += (size_t)gridDim.x * blockDim.x) {
+    float g0 = 0.0f, g1 = 0.0f;
+    for (int r = 0; r < S->nranks; ++r) {
+      g0 += ((const volatile float*)lr_mbox_stage(S->mbox[r], par, 0))[i];
+      g1 += ((const volatile float*)lr_mbox_stage(S->mbox[r], par, 1))[i];
+    }
+    mu_new[i] = fmaf(-dt, ((const volatile float*)own0)[i], mu_n[i]);
+    const float mn = mg_n[i];
+    const float mv = fmaf(-dt, g0, mn);
+    mg_new[i] = mv;
+    const float ut = -dt * g1;
+    const float rr = ut / (abstol + fmaxf(fabsf(mn), fabsf(mv)) * reltol);
+    acc += (double)(rr * rr);
+  }
   __shared__ double sh[8];
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
   if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
@@ -844,7 +957,7 @@ LatentAdjoint::LatentAdjoint(lrnde_ctx* c, const lrnde_model* mm, const float* p
   RL = (float*)ctx->alloc(sizeof(float) * (size_t)ntile_d * 2 * 16384);
   static bool attr_set = false;
   if (!attr_set) {
-    constexpr int kChainSmem = 4 * (3 * 8192 + 3 * 2048) + 1024;   // KS <= 14: at most 3 full chunks + 3 tail K-steps
+    constexpr int kChainSmem = 4 * (3 * 8192 + 3 * 2048) + ladj::kTapeBufs * ladj::kTapeBufBytes + 1024;   // KS <= 14: at most 3 full chunks + 3 tail K-steps
     LR_CUDA(cudaFuncSetAttribute(ladj::adj_chain_kernel<ACT_IDENTITY>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmem));
     LR_CUDA(cudaFuncSetAttribute(ladj::adj_chain_kernel<ACT_TANH>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmem));
     LR_CUDA(cudaFuncSetAttribute(ladj::adj_chain_kernel<ACT_GELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmem));
@@ -884,7 +997,7 @@ static void lra_launch_chain(LatentAdjoint& E, SolveDev* S, int single) {
   cp.hbuf = E.hbuf; cp.unit_bytes = (uint32_t)E.unit_bytes;
   cp.B = (int)E.B; cp.H = sh.H; cp.td = sh.td; cp.Kaug = sh.Kaug; cp.KS = sh.KS; cp.nfull = sh.nfull; cp.ntail = sh.ntail;
   cp.passes = E.passes;
-  const size_t smem_c = 4 * ((size_t)sh.nfull * 8192 + (size_t)sh.ntail * 2048) + 1024;
+  const size_t smem_c = 4 * ((size_t)sh.nfull * 8192 + (size_t)sh.ntail * 2048) + ladj::kTapeBufs * ladj::kTapeBufBytes + 1024;
   cudaStream_t st = E.ctx->stream;
   switch (sh.act) {
     case ACT_TANH: ladj::adj_chain_kernel<ACT_TANH><<<E.ntiles, fused::kThreads, smem_c, st>>>(cp); break;
@@ -937,8 +1050,12 @@ static void lra_launch_mu(LatentAdjoint& E, SolveDev* S) {
   mp.W2a = E.ps + L2.w_off; mp.W1T = E.W1T;
   mp.D = E.sh.D; mp.H = E.sh.H; mp.td = E.sh.td; mp.Kaug = E.sh.Kaug; mp.ntile = E.ntile_d;
   mp.w1_off = (long)L1.w_off; mp.w2_off = (long)L2.w_off; mp.nparams = (long)E.m->nparams;
-  ladj::adj_mu_kernel<<<LR_ERR_BLOCKS, 256, 0, st>>>(mp);
+  ladj::adj_mu_kernel<<<LR_ERR_BLOCKS, 512, 0, st>>>(mp);
   LRA_COUNT(E.ctx);
+  if (E.ctx->nranks > 1) {
+    ladj::adj_mu_finish_kernel<<<LR_ERR_BLOCKS, 256, 0, st>>>(S);
+    LRA_COUNT(E.ctx);
+  }
   LR_CUDA(cudaGetLastError());
 }
 

@@ -133,7 +133,11 @@ extern "C" int lrnde_ctx_create(lrnde_ctx** out, int device, void* stream) {
   c->device = device;
   if (stream) c->stream = (cudaStream_t)stream;
   else {
-    LR_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    // a BLOCKING stream: it synchronises implicitly with the legacy default stream (stream 0), so a caller that
+    // prepares its buffers on stream 0 (PyTorch's default stream has handle 0) and passes NULL cannot race with the
+    // library: work queued on stream 0 before a call is complete before the library's kernels start, and stream-0
+    // work queued after the call waits for them.  (Graph capture needs a non-default stream, hence not stream 0 itself.)
+    LR_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamDefault));
     c->own_stream = true;
   }
   c->pinned_bytes = 1 << 20;
@@ -1226,6 +1230,7 @@ struct lrnde_tape {
   std::vector<float> save_ts;   // times of the FULL saved solution (incl. t1 when appended)
   std::vector<int> save_out;    // index of the output block for each save_ts entry, -1 if dropped
   int reg_mode = 0;
+  int lean = 0;                 // lean tape: k_2..k_6 of the forward steps were not stored (latent-space adjoint only)
   float t1 = 0.f;
   // step logs (host copies)
   std::vector<float> log_t[2], log_dt[2], log_eest[2];
@@ -1348,6 +1353,10 @@ static void lr_grow_tape(Solver& S) {
   LR_CUDA(cudaMemcpyAsync(&S.dev->cap, &S.h.cap, sizeof(int), cudaMemcpyHostToDevice, st));
 }
 
+// forward declaration: y(t) of the kept forward solution (defined after lr_host_interp)
+static void lr_sol_at(lrnde_ctx* ctx, lrnde_tape* T, FusedEngine* fe, float tq, float* dst, LinComb* host_desc,
+                      const LinComb* dev_desc);
+
 static size_t lr_tape_budget(lrnde_ctx* ctx) {
   if (ctx->tape_budget) return (size_t)ctx->tape_budget;
   // cudaMemGetInfo takes a driver lock (measured 0.08 ... 60 ms per call on a shared host), so the
@@ -1395,6 +1404,30 @@ static LinComb lr_host_interp(const Solver& F, const std::vector<float>& fts, fl
   d.n = 7;
   d.t = tval;
   return d;
+}
+
+// y(t) of the forward solution into dst (device): the stored state on an exact hit, else the dense interpolant --
+// from the D-dimensional tape, or (lean tape) from the hidden tape: y(t) = x + W2a c(t) (FusedEngine::dense_output)
+static void lr_sol_at(lrnde_ctx* ctx, lrnde_tape* T, FusedEngine* fe, float tq, float* dst, LinComb* host_desc,
+                      const LinComb* dev_desc) {
+  Solver& F = *T->fwd;
+  cudaStream_t st = ctx->stream;
+  const size_t DB = F.h.len;
+  *host_desc = lr_host_interp(F, T->fts, tq);
+  host_desc->dst = dst;
+  LR_CUDA(cudaMemcpyAsync((void*)dev_desc, host_desc, sizeof(LinComb), cudaMemcpyHostToDevice, st));
+  if (T->lean && host_desc->n > 0) {
+    if (!fe) lr_fail(LRNDE_ESTATE, "lean tape without the latent-space engine");
+    const size_t n = (size_t)(host_desc->base - F.tape) / ((size_t)7 * DB);
+    const size_t zl = F.h.zlen;
+    const float* harr[8];
+    for (int i = 0; i < 7; ++i) harr[i] = F.htape + (n * 7 + i) * zl;
+    harr[7] = F.htape + ((n + 1) * 7 + 1) * zl;
+    fe->dense_output(F.dev, harr, host_desc->coef, host_desc->scale, F.tape, dev_desc);
+  } else {
+    lincomb_kernel<<<lr_ew_blocks(DB), 256, 0, st>>>(dev_desc, dst, DB, nullptr);
+    LR_COUNT(ctx);
+  }
 }
 
 static void lr_validate_opts(const lrnde_opts* o) {
@@ -1572,6 +1605,14 @@ extern "C" int lrnde_ode_forward(lrnde_ctx* ctx, const lrnde_model* m, const lrn
   // Z(k_j) and the hidden activations of every stage go to the latent / hidden tapes when a pullback will follow
   // (the latent-space adjoint interpolates them instead of the D-dimensional k's)
   const int write_z = o->keep_tape ? 1 : 0;
+  // lean tape: when the pullback will run in hidden space nothing reads k_2..k_6 of the D-dimensional tape (saves and
+  // the regulariser's start state come from the hidden tape: FusedEngine::dense_output), so they are not stored
+  const bool lean = fe && write_z && LatentAdjoint::eligible(m) && !getenv("LRNDE_NO_LATENT_ADJ") && !getenv("LRNDE_FULL_TAPE");
+  T->lean = lean ? 1 : 0;
+  if (fe) fe->lean = lean ? 1 : 0;
+  auto sol_at = [&](float tq, float* dst, LinComb* host_desc, const LinComb* dev_desc) {
+    lr_sol_at(ctx, T.get(), fe, tq, dst, host_desc, dev_desc);
+  };
   if (fe) {
     F.enable_latent(fe->zlen(), write_z != 0);
     ev.latent_of(F.tape, F.ztape);
@@ -1630,7 +1671,9 @@ extern "C" int lrnde_ode_forward(lrnde_ctx* ctx, const lrnde_model* m, const lrn
     for (size_t i = 0; i < times.size(); ++i) out_index.push_back((int)i);
     if (mode == LRNDE_REG_UNBIASED) { times.push_back(t1); out_index.push_back(-1); }
   } else if (o->nsave == 0 && mode != LRNDE_REG_BIASED) {
-    if (mode == LRNDE_REG_UNBIASED) { times.push_back(t1); out_index.push_back(0); }
+    // solve(...; saveat = [t1, t2] / [t2], save_start) : the reference splats save_start into solve (neural_ode.jl:51)
+    if (o->save_start) { times.push_back(o->t0); out_index.push_back(0); }
+    if (mode == LRNDE_REG_UNBIASED) { times.push_back(t1); out_index.push_back((int)out_index.size()); }
     times.push_back(o->t2);
     out_index.push_back((int)out_index.size());
   } else {  // every accepted step (saveat = [] of the :biased path, or nsave == -1)
@@ -1657,22 +1700,22 @@ extern "C" int lrnde_ode_forward(lrnde_ctx* ctx, const lrnde_model* m, const lrn
 
   // ---- write the saved states
   std::vector<LinComb> descs;
+  std::vector<float> desc_t;
   std::vector<int> desc_out;
   for (size_t i = 0; i < times.size(); ++i) {
     if (out_index[i] < 0) continue;
     float tq = std::min(times[i], t_last);
-    descs.push_back(lr_host_interp(F, T->fts, tq));
+    descs.push_back(LinComb());
+    desc_t.push_back(tq);
     desc_out.push_back(out_index[i]);
     if (save_times) save_times[out_index[i]] = times[i];
   }
   if (u_save && !descs.empty()) {
     DevBuf dd(ctx, descs.size() * (sizeof(LinComb) / 4 + 1));
-    LR_CUDA(cudaMemcpyAsync(dd.p, descs.data(), sizeof(LinComb) * descs.size(), cudaMemcpyHostToDevice, st));
     DevBuf stage(ctx, host ? DB * descs.size() : 1);
     for (size_t i = 0; i < descs.size(); ++i) {
       float* dst = host ? stage.p + i * DB : u_save + (size_t)desc_out[i] * DB;
-      lincomb_kernel<<<lr_ew_blocks(DB), 256, 0, st>>>(((const LinComb*)dd.p) + i, dst, DB, nullptr);
-      LR_COUNT(ctx);
+      sol_at(desc_t[i], dst, &descs[i], ((const LinComb*)dd.p) + i);
       if (host)
         LR_CUDA(cudaMemcpyAsync(u_save + (size_t)desc_out[i] * DB, dst, sizeof(float) * DB,
                                 cudaMemcpyDeviceToHost, st));
@@ -1695,11 +1738,10 @@ extern "C" int lrnde_ode_forward(lrnde_ctx* ctx, const lrnde_model* m, const lrn
     R.init_ctrl(t1, o->t2, o->t2, o->maxiters, o->pow_mode, o->abstol, o->reltol);
     if (fe) R.enable_latent(fe->zlen());
     R.upload();
-    LinComb u1 = lr_host_interp(F, T->fts, std::min(t1, t_last));
+    LinComb u1;
     DevBuf dd(ctx, sizeof(LinComb) / 4 + 1);
-    LR_CUDA(cudaMemcpyAsync(dd.p, &u1, sizeof(LinComb), cudaMemcpyHostToDevice, st));
-    lincomb_kernel<<<lr_ew_blocks(DB), 256, 0, st>>>((const LinComb*)dd.p, R.tape, DB, nullptr);
-    LR_COUNT(ctx);
+    sol_at(std::min(t1, t_last), R.tape, &u1, (const LinComb*)dd.p);
+    if (fe) fe->lean = 0;   // the regulariser integrator keeps k_2..k_6 (its reverse pass reads them)
     if (fe) {
       ev.latent_of(R.tape, R.ztape);
       auto evalR = [&](const LinComb* in, const LinComb*, const int* done, const LinComb* out, bool) {
@@ -1746,6 +1788,39 @@ extern "C" int lrnde_ode_forward(lrnde_ctx* ctx, const lrnde_model* m, const lrn
   LR_API_END
 }
 
+// The saved states of a kept solution, written after the call (every-step saves of the :biased path: the number of
+// accepted steps is only known after the solve, so lrnde_ode_forward can run with u_save = NULL and the caller sizes
+// the buffer from stats->nsave_out).  u_save / save_times: as in lrnde_ode_forward (HOST pointers when the forward
+// call had host_buffers).
+extern "C" int lrnde_ode_saved_states(lrnde_ctx* ctx, const lrnde_model* m, lrnde_tape* T, float* u_save,
+                                      int64_t u_save_cap, float* save_times) {
+  LR_API_BEGIN
+  if (!ctx || !m || !T || !u_save) lr_fail(LRNDE_EINVAL, "lrnde_ode_saved_states: bad args");
+  if (T->ctx != ctx || T->model != m) lr_fail(LRNDE_ESTATE, "tape belongs to another ctx/model");
+  LR_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const size_t DB = (size_t)m->D * T->B;
+  const int host = T->opts.host_buffers;
+  int nout = 0;
+  for (int v : T->save_out) nout = std::max(nout, v + 1);
+  if (nout > u_save_cap) lr_fail(LRNDE_EINVAL, "u_save holds %lld blocks but the solution has %d", (long long)u_save_cap, nout);
+  std::unique_ptr<FusedEngine> fe;
+  if (T->lean) fe = std::make_unique<FusedEngine>(ctx, m, T->ps, T->B, T->opts.precision == LRNDE_PREC_TF32 ? 1 : 3);
+  const float t_last = T->fts.back();
+  DevBuf dd(ctx, sizeof(LinComb) / 4 + 1), stage(ctx, host ? DB : 1);
+  for (size_t i = 0; i < T->save_ts.size(); ++i) {
+    if (T->save_out[i] < 0) continue;
+    LinComb hd;
+    float* dst = host ? stage.p : u_save + (size_t)T->save_out[i] * DB;
+    lr_sol_at(ctx, T, fe.get(), std::min(T->save_ts[i], t_last), dst, &hd, (const LinComb*)dd.p);
+    if (host) LR_CUDA(cudaMemcpyAsync(u_save + (size_t)T->save_out[i] * DB, dst, sizeof(float) * DB, cudaMemcpyDeviceToHost, st));
+    if (save_times) save_times[T->save_out[i]] = T->save_ts[i];
+    LR_CUDA(cudaStreamSynchronize(st));   // dd / stage are reused by the next block
+  }
+  LR_CHECK_LAUNCH();
+  LR_API_END
+}
+
 extern "C" int lrnde_tape_free(lrnde_tape* t) {
   LR_API_BEGIN
   if (t) {
@@ -1775,11 +1850,20 @@ extern "C" int lrnde_step_log(const lrnde_tape* t, int which, float* tt, float* 
 // ------------------------------------------------------------------------------------------
 // pullback: continuous adjoint over z = [lambda; mu] + reverse pass of the regulariser step
 // ------------------------------------------------------------------------------------------
+// last result of the LRNDE_PROFILE_ADJ=<iters> hook of lrnde_ode_backward: microseconds per launch of one attempt
+// of the latent-space adjoint {chain, lambda GEMM, pairacc, reduce + mu, whole attempt} (CUDA events on the ctx stream)
+static float g_adj_profile_us[5] = {0, 0, 0, 0, 0};
+extern "C" int lrnde_profile_adjoint_last(float* us5) {
+  if (!us5) return LRNDE_EINVAL;
+  for (int k = 0; k < 5; ++k) us5[k] = g_adj_profile_us[k];
+  return LRNDE_OK;
+}
+
 extern "C" int lrnde_ode_backward(lrnde_ctx* ctx, const lrnde_model* m, lrnde_tape* T,
                                   const float* d_u_save, float d_reg, float* d_ps, float* d_x,
                                   lrnde_stats* stats) {
   LR_API_BEGIN
-  if (!ctx || !m || !T || !d_ps || !d_x) lr_fail(LRNDE_EINVAL, "lrnde_ode_backward: bad args");
+  if (!ctx || !m || !T || !d_ps || (!d_x && !T->opts.no_dx)) lr_fail(LRNDE_EINVAL, "lrnde_ode_backward: bad args");
   if (T->ctx != ctx || T->model != m) lr_fail(LRNDE_ESTATE, "tape belongs to another ctx/model");
   LR_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
@@ -1817,8 +1901,9 @@ extern "C" int lrnde_ode_backward(lrnde_ctx* ctx, const lrnde_model* m, lrnde_ta
   ev.prepare();
   if (ev.conv && o.model_testmode) { ev.conv->bn_state = T->bn_state; ev.conv->testmode = 1; }
 
-  DevBuf out_dx(ctx, host ? DB : 1), out_dps(ctx, host ? P : 1);
-  float* dx_dev = host ? out_dx.p : d_x;
+  const bool no_dx = o.no_dx != 0;   // the caller has no use for dL/dx (nothing upstream has parameters)
+  DevBuf out_dx(ctx, (host || !d_x) ? DB : 1), out_dps(ctx, host ? P : 1);
+  float* dx_dev = (host || !d_x) ? out_dx.p : d_x;
   float* dps_dev = host ? out_dps.p : d_ps;
 
   const long tb_start = lr_now_us();
@@ -1845,7 +1930,9 @@ extern "C" int lrnde_ode_backward(lrnde_ctx* ctx, const lrnde_model* m, lrnde_ta
     A.h.ftdir = 1;
     // latent-space adjoint (lrnde_adjoint.h): the forward solve kept its hidden tape
     std::unique_ptr<LatentAdjoint> la;
-    if (F.htape && ev.use_umma && ctx->nranks == 1 && LatentAdjoint::eligible(m) && !getenv("LRNDE_NO_LATENT_ADJ")) {
+    if (T->lean && getenv("LRNDE_NO_LATENT_ADJ"))
+      lr_fail(LRNDE_ESTATE, "the forward solve kept a lean tape (latent-space adjoint); set LRNDE_FULL_TAPE=1 for the forward to use the per-layer adjoint");
+    if (F.htape && ev.use_umma && LatentAdjoint::eligible(m) && !getenv("LRNDE_NO_LATENT_ADJ")) {
       la = std::make_unique<LatentAdjoint>(ctx, m, T->ps, B, ev.passes);
       la->W1T = ev.WT[0]; la->Zx = F.ztape; la->x = F.tape;
       la->prepare();
@@ -1879,7 +1966,26 @@ extern "C" int lrnde_ode_backward(lrnde_ctx* ctx, const lrnde_model* m, lrnde_ta
     std::sort(stops.begin(), stops.end(), [](float a, float b) { return a > b; });
     stops.push_back(t0);
     A.init_ctrl(t2, t0, stops[0], o.maxiters, o.pow_mode, o.abstol, o.reltol);
+    // lean tape: the per-layer right-hand side (initial-dt probes only) reads y(t) materialised from the hidden tape
+    std::unique_ptr<FusedEngine> fe_y;
+    std::unique_ptr<DevBuf> ybuf, ydescs;
+    if (T->lean) {
+      if (!la) lr_fail(LRNDE_ESTATE, "lean forward tape but the latent-space adjoint is not available for this call");
+      fe_y = std::make_unique<FusedEngine>(ctx, m, T->ps, B, ev.passes);
+      ybuf = std::make_unique<DevBuf>(ctx, DB);
+      ydescs = std::make_unique<DevBuf>(ctx, 2 * (sizeof(LinComb) / 4 + 1));
+      LinComb od;
+      memset(&od, 0, sizeof(od));
+      od.dst = ybuf->p;
+      LR_CUDA(cudaMemcpyAsync(ydescs->p, &od, sizeof(LinComb), cudaMemcpyHostToDevice, st));
+    }
     auto rhs = [&](const LinComb* in, const LinComb* y, const int* done, const LinComb*, bool) {
+      if (T->lean) {
+        LinComb* out_desc = (LinComb*)ydescs->p;       // {dst = ybuf}
+        LinComb* y_mat = out_desc + 1;                 // {base = ybuf, t = y->t}, written on the device
+        fe_y->dense_output_dev(A.dev, y, F.tape, ybuf->p, y_mat, out_desc);
+        y = y_mat;
+      }
       ev.vjp(y, in, nullptr, in, -1.0f, nullptr, in, DB, -1.0f, 0.0f, done);
     };
     A.body = [&]() {
@@ -1904,8 +2010,34 @@ extern "C" int lrnde_ode_backward(lrnde_ctx* ctx, const lrnde_model* m, lrnde_ta
     }
     lr_solver_start(A, rhs, 1);
     mark("solver start");
+    // data-parallel group: the replicated global mu of the latent-space engine starts at mu(t2) = 0 (ring slot 0)
+    if (la && A.muglob) LR_CUDA(cudaMemsetAsync(A.muglob, 0, sizeof(float) * P, st));
     if (la) latent_begin();
     mark("latent begin");
+    if (la && getenv("LRNDE_PROFILE_ADJ")) {
+      // the launches of the first attempt, repeated (same descriptors: the controller does not run; they only write
+      // the next ring slot, which the real attempt recomputes), timed with CUDA events on the library's stream
+      const int iters = std::max(1, atoi(getenv("LRNDE_PROFILE_ADJ")));
+      cudaEvent_t e[6];
+      for (auto& ev_ : e) LR_CUDA(cudaEventCreate(&ev_));
+      for (int w = 0; w < 2; ++w) la->attempt(A.dev);
+      for (int k = 0; k < 4; ++k) {
+        LR_CUDA(cudaEventRecord(e[k], st));
+        for (int i = 0; i < iters; ++i) la->attempt_part(A.dev, k);
+      }
+      LR_CUDA(cudaEventRecord(e[4], st));
+      for (int i = 0; i < iters; ++i) la->attempt(A.dev);
+      LR_CUDA(cudaEventRecord(e[5], st));
+      LR_CUDA(cudaEventSynchronize(e[5]));
+      const char* nm[5] = {"chain", "lambda gemm", "pairacc", "reduce + mu", "attempt"};
+      for (int k = 0; k < 5; ++k) {
+        float ms = 0.0f;
+        LR_CUDA(cudaEventElapsedTime(&ms, e[k], e[k + 1]));
+        g_adj_profile_us[k] = 1000.0f * ms / (float)iters;
+        if (timing) fprintf(stderr, "[lrnde] adjoint attempt: %-12s %8.1f us\n", nm[k], g_adj_profile_us[k]);
+      }
+      for (auto& ev_ : e) cudaEventDestroy(ev_);
+    }
     for (size_t si = 0; si < stops.size(); ++si) {
       A.run_segment();
       mark("segment");
@@ -1977,7 +2109,7 @@ extern "C" int lrnde_ode_backward(lrnde_ctx* ctx, const lrnde_model* m, lrnde_ta
     LR_CUDA(cudaStreamSynchronize(st));
   }
   if (host) {
-    LR_CUDA(cudaMemcpyAsync(d_x, dx_dev, sizeof(float) * DB, cudaMemcpyDeviceToHost, st));
+    if (!no_dx) LR_CUDA(cudaMemcpyAsync(d_x, dx_dev, sizeof(float) * DB, cudaMemcpyDeviceToHost, st));
     LR_CUDA(cudaMemcpyAsync(d_ps, dps_dev, sizeof(float) * P, cudaMemcpyDeviceToHost, st));
   }
   LR_CUDA(cudaStreamSynchronize(st));
@@ -2011,7 +2143,9 @@ extern "C" int lrnde_profile_step(lrnde_ctx* ctx, const lrnde_model* m, const lr
   ev.prepare();
   Solver F(ctx, DB, DB, 3, 0, 8);
   F.init_ctrl(o->t0, o->t2, o->t2, o->maxiters, o->pow_mode, o->abstol, o->reltol);
-  F.enable_latent(ev.fe->zlen());
+  F.enable_latent(ev.fe->zlen(), o->keep_tape != 0);   // keep_tape: the training configuration (hidden tape, lean D-tape)
+  if (F.htape) LR_CUDA(cudaMemsetAsync(F.htape, 0, sizeof(float) * ev.fe->zlen(), st));
+  ev.fe->lean = (o->keep_tape && LatentAdjoint::eligible(m) && !getenv("LRNDE_FULL_TAPE")) ? 1 : 0;
   LR_CUDA(cudaMemcpyAsync(F.tape, x, sizeof(float) * DB, cudaMemcpyDeviceToDevice, st));
   F.h.use_cond = 0;
   F.upload();
@@ -2037,6 +2171,68 @@ extern "C" int lrnde_profile_step(lrnde_ctx* ctx, const lrnde_model* m, const lr
     us[k] = 1000.0f * ms / (float)iters;
   }
   for (auto& ev_ : e) cudaEventDestroy(ev_);
+  LR_API_END
+}
+
+// ------------------------------------------------------------------------------------------
+// One gradient evaluation of the MNIST classifier Chain(FlattenLayer, NeuralODE, diffeqsol_to_array, Dense(D => C))
+// (experiments/src/construct.jl:180-200) under the training loss logitcrossentropy + w_reg * reg_val
+// (construct.jl:19-31), i.e. what Zygote.pullback does in run_training_step (experiments/src/utils.jl:106-115) --
+// with u(t2) and its cotangent kept on the device: only x, the labels and the parameters go in, only the loss and
+// the parameter gradients come out.
+// ------------------------------------------------------------------------------------------
+__global__ void scale_kernel(float* v, float s, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) v[i] *= s;
+}
+extern "C" int lrnde_classifier_grad(lrnde_ctx* ctx, const lrnde_model* m, const lrnde_opts* o, const float* ps,
+                                     const float* Wc, const float* x, const int32_t* labels, int64_t B, int32_t Cn,
+                                     float w_reg, float grad_scale, float* loss_ce, float* d_ps, float* d_Wc,
+                                     lrnde_stats* stats) {
+  LR_API_BEGIN
+  if (!ctx || !m || !o || !ps || !Wc || !x || !labels || !loss_ce || !d_ps || !d_Wc || !stats || B < 1 || Cn < 1)
+    lr_fail(LRNDE_EINVAL, "lrnde_classifier_grad: bad args");
+  LR_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const int host = o->host_buffers;
+  const int D = m->D;
+  const size_t DB = (size_t)D * B, P = (size_t)m->nparams, PW = (size_t)Cn * (D + 1);
+  DevBuf psd(ctx, host ? P : 1), wcd(ctx, host ? PW : 1), xd(ctx, host ? DB : 1), yd(ctx, host ? (size_t)B : 1);
+  DevBuf ud(ctx, DB), dud(ctx, DB), dpsd(ctx, host ? P : 1), dwd(ctx, host ? PW : 1);
+  const float* psv = ps; const float* wcv = Wc; const float* xv = x; const int32_t* yv = labels;
+  if (host) {
+    LR_CUDA(cudaMemcpyAsync(psd.p, ps, 4 * P, cudaMemcpyHostToDevice, st));
+    LR_CUDA(cudaMemcpyAsync(wcd.p, Wc, 4 * PW, cudaMemcpyHostToDevice, st));
+    LR_CUDA(cudaMemcpyAsync(xd.p, x, 4 * DB, cudaMemcpyHostToDevice, st));
+    LR_CUDA(cudaMemcpyAsync(yd.p, labels, 4 * (size_t)B, cudaMemcpyHostToDevice, st));
+    psv = psd.p; wcv = wcd.p; xv = xd.p; yv = (const int32_t*)yd.p;
+  }
+  float* dpsv = host ? dpsd.p : d_ps;
+  float* dwv = host ? dwd.p : d_Wc;
+  lrnde_opts od = *o;
+  od.host_buffers = 0; od.keep_tape = 1; od.last_only = 1; od.no_dx = 1;
+  lrnde_tape* T = nullptr;
+  lrnde_stats s1, s2;
+  memset(&s2, 0, sizeof(s2));
+  int rc = lrnde_ode_forward(ctx, m, &od, psv, xv, B, ud.p, 1, nullptr, &s1, &T);
+  if (rc == LRNDE_OK) rc = lrnde_head_ce(ctx, wcv, ud.p, yv, B, D, Cn, 0, loss_ce, dud.p, dwv);
+  if (rc == LRNDE_OK && grad_scale != 1.0f) {
+    scale_kernel<<<lr_ew_blocks(DB), 256, 0, st>>>(dud.p, grad_scale, DB);
+    scale_kernel<<<lr_ew_blocks(PW), 256, 0, st>>>(dwv, grad_scale, PW);
+    LR_COUNT(ctx); LR_COUNT(ctx);
+  }
+  if (rc == LRNDE_OK) rc = lrnde_ode_backward(ctx, m, T, dud.p, w_reg, dpsv, nullptr, &s2);
+  if (T) lrnde_tape_free(T);
+  if (rc != LRNDE_OK) throw LrError(rc);   // the failing call already set the error text
+  if (host) {
+    LR_CUDA(cudaMemcpyAsync(d_ps, dpsv, 4 * P, cudaMemcpyDeviceToHost, st));
+    LR_CUDA(cudaMemcpyAsync(d_Wc, dwv, 4 * PW, cudaMemcpyDeviceToHost, st));
+    LR_CUDA(cudaStreamSynchronize(st));
+  }
+  *stats = s1;
+  stats->nf_bwd = s2.nf_bwd; stats->naccept_bwd = s2.naccept_bwd; stats->nreject_bwd = s2.nreject_bwd;
+  stats->retcode_bwd = s2.retcode_bwd;
+  stats->gpu_launches = s1.gpu_launches + s2.gpu_launches + 8;
+  stats->reserved[3] = s2.reserved[3]; stats->reserved[4] = s2.reserved[4];
   LR_API_END
 }
 

@@ -182,7 +182,7 @@ extern "C" int lrnde_sosri_step(lrnde_ctx* ctx, const lrnde_model* drift,
 // classifier head + logitcrossentropy:  loss = mean_b( -log softmax(W u_b + b)[y_b] )
 // ------------------------------------------------------------------------------------------
 __global__ void softmax_ce_kernel(const float* logits, const int* labels, int Cn, int B,
-                                  float* dlogits, double* partials) {
+                                  float* dlogits, double* partials, int* bad_label) {
   double acc = 0.0;
   for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
     const float* z = logits + (size_t)b * Cn;
@@ -192,6 +192,7 @@ __global__ void softmax_ce_kernel(const float* logits, const int* labels, int Cn
     for (int c = 0; c < Cn; ++c) s += expf(z[c] - mx);
     float lse = mx + logf(s);
     int y = labels[b];
+    if (y < 0 || y >= Cn) { *bad_label = 1; y = 0; }   // reported as LRNDE_EINVAL by the caller (labels are 0-based)
     acc += (double)(lse - z[y]);
     for (int c = 0; c < Cn; ++c)
       dlogits[(size_t)b * Cn + c] = (expf(z[c] - lse) - (c == y ? 1.0f : 0.0f)) / (float)B;
@@ -221,6 +222,8 @@ extern "C" int lrnde_head_ce(lrnde_ctx* ctx, const float* Wc, const float* u,
   DevBuf dub(ctx, host ? DB : 1), dwb(ctx, host ? PW : 1);
   const int nb = 64;
   DevBuf red(ctx, 2 * nb + 8);
+  int* badd = (int*)(red.p + 2 * nb + 4);
+  LR_CUDA(cudaMemsetAsync(badd, 0, sizeof(int), st));
   const float* Wd = Wc; const float* ud = u; const int* ld = labels;
   if (host) {
     LR_CUDA(cudaMemcpyAsync(w.p, Wc, 4 * PW, cudaMemcpyHostToDevice, st));
@@ -236,7 +239,7 @@ extern "C" int lrnde_head_ce(lrnde_ctx* ctx, const float* Wc, const float* u,
   dim3 g((Cn + DN_BM - 1) / DN_BM, (unsigned)((B + DN_BN - 1) / DN_BN));
   dense_nn_kernel<<<g, 256, 0, st>>>(p);
   LR_COUNT(ctx);
-  softmax_ce_kernel<<<nb, 256, 0, st>>>(logits.p, ld, Cn, (int)B, dlog.p, (double*)red.p);
+  softmax_ce_kernel<<<nb, 256, 0, st>>>(logits.p, ld, Cn, (int)B, dlog.p, (double*)red.p, badd);
   LR_COUNT(ctx);
   float* lossd = (float*)((double*)red.p + nb);
   mean_finish_kernel<<<1, 32, 0, st>>>((double*)red.p, nb, (double)B, lossd);
@@ -277,8 +280,11 @@ extern "C" int lrnde_head_ce(lrnde_ctx* ctx, const float* Wc, const float* u,
     LR_CUDA(cudaStreamSynchronize(st));
   }
   LR_CHECK_LAUNCH();
+  int bad_host = 0;
   LR_CUDA(cudaMemcpyAsync(loss, lossd, 4, cudaMemcpyDeviceToHost, st));
+  LR_CUDA(cudaMemcpyAsync(&bad_host, badd, sizeof(int), cudaMemcpyDeviceToHost, st));
   LR_CUDA(cudaStreamSynchronize(st));
+  if (bad_host) lr_fail(LRNDE_EINVAL, "lrnde_head_ce: a label is outside [0, %d) (labels are 0-based class indices)", Cn);
   LR_API_END
 }
 
@@ -332,6 +338,127 @@ extern "C" int lrnde_adam_step(lrnde_ctx* ctx, float* p, const float* g, float* 
                                                                  eps, c1, c2);
   LR_COUNT(ctx);
   LR_CHECK_LAUNCH();
+  LR_API_END
+}
+
+// ------------------------------------------------------------------------------------------
+// The other optimisers experiments/src/construct.jl:104-125 can build (Optimisers.jl rules): Descent, Momentum,
+// Nesterov, Adam / AdamW (= Adam chained with WeightDecay(0)), AdaMax, each optionally chained with
+// WeightDecay(wd) (OptimiserChain(opt, WeightDecay(wd)): the decay term wd * p is added to the rule's update,
+// not scaled by the learning rate).  s1 / s2: state buffers (momentum / first moment; second moment / inf-norm).
+// ------------------------------------------------------------------------------------------
+__global__ void opt_kernel(int kind, float* p, const float* g, float* s1, float* s2, size_t n, float lr, float a,
+                           float b, float eps, float wd, float c1, float c2) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float gi = g[i], pi = p[i];
+    float dx;
+    if (kind == LRNDE_OPT_DESCENT) dx = lr * gi;
+    else if (kind == LRNDE_OPT_MOMENTUM) { const float v = a * s1[i] + lr * gi; s1[i] = v; dx = v; }
+    else if (kind == LRNDE_OPT_NESTEROV) {
+      const float v = s1[i];
+      dx = -(a * a) * v + (1.0f + a) * lr * gi;
+      s1[i] = a * v - lr * gi;
+    } else if (kind == LRNDE_OPT_ADAMAX) {
+      const float m = a * s1[i] + (1.0f - a) * gi;
+      const float u = fmaxf(b * s2[i], fabsf(gi));
+      s1[i] = m; s2[i] = u;
+      dx = (lr / c1) * m / (u + eps);
+    } else {   // LRNDE_OPT_ADAM
+      const float m = a * s1[i] + (1.0f - a) * gi;
+      const float v = b * s2[i] + (1.0f - b) * gi * gi;
+      s1[i] = m; s2[i] = v;
+      dx = lr * (m / c1) / (sqrtf(v / c2) + eps);
+    }
+    p[i] = pi - (dx + wd * pi);
+  }
+}
+extern "C" int lrnde_opt_step(lrnde_ctx* ctx, int32_t kind, float* p, const float* g, float* s1, float* s2, int64_t n,
+                              float lr, float a, float b, float eps, float weight_decay, int32_t step) {
+  LR_API_BEGIN
+  if (!ctx || !p || !g || n < 1 || step < 1) lr_fail(LRNDE_EINVAL, "lrnde_opt_step: bad args");
+  if (kind < LRNDE_OPT_DESCENT || kind > LRNDE_OPT_ADAMAX) lr_fail(LRNDE_EINVAL, "lrnde_opt_step: unknown optimiser %d", kind);
+  if (kind != LRNDE_OPT_DESCENT && !s1) lr_fail(LRNDE_EINVAL, "lrnde_opt_step: the rule needs state buffer s1");
+  if ((kind == LRNDE_OPT_ADAM || kind == LRNDE_OPT_ADAMAX) && !s2) lr_fail(LRNDE_EINVAL, "lrnde_opt_step: the rule needs state buffer s2");
+  LR_CUDA(cudaSetDevice(ctx->device));
+  const float c1 = 1.0f - powf(a, (float)step), c2 = 1.0f - powf(b, (float)step);
+  opt_kernel<<<lr_ew_blocks((size_t)n), 256, 0, ctx->stream>>>(kind, p, g, s1, s2, (size_t)n, lr, a, b, eps, weight_decay, c1, c2);
+  LR_COUNT(ctx);
+  LR_CHECK_LAUNCH();
+  LR_API_END
+}
+
+// ------------------------------------------------------------------------------------------
+// Sum of a device vector over the data-parallel group (the once-per-iteration all-reduce of the parameter
+// gradients) through the peer-mapped mailboxes set by lrnde_ctx_set_dist: every rank publishes its
+// chunk in its own staging area, raises a flag on every peer, and adds all ranks' chunks in rank order over
+// NVLink peer loads -- identical bits on every rank, no host round trip, no NCCL dependency.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ar_publish_kernel(LrMailbox* mine, LrMailbox* const* peers, int rank, int nranks,
+                                                         const float* v, size_t n, unsigned long long seq,
+                                                         unsigned int* counter) {
+  const int par = (int)(seq & 1ull);
+  float* stage = lr_mbox_stage(mine, par, 2);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) stage[i] = v[i];
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int prev = atomicAdd(counter, 1u);
+    if (prev == gridDim.x - 1) {
+      *counter = 0;
+      __threadfence_system();
+      for (int r = 0; r < nranks; ++r) {
+        volatile unsigned long long* f = &peers[r]->mflag[par][rank];
+        *f = seq + 1;
+      }
+    }
+  }
+}
+__global__ void __launch_bounds__(256) ar_gather_kernel(LrMailbox* mine, LrMailbox* const* peers, int nranks, float* v,
+                                                        size_t n, unsigned long long seq, int* timed_out) {
+  const int par = (int)(seq & 1ull);
+  if (threadIdx.x == 0) {
+    long long spins = 0;
+    for (int r = 0; r < nranks; ++r) {
+      volatile unsigned long long* f = &mine->mflag[par][r];
+      while (*f != seq + 1) {
+        __nanosleep(40);
+        if (++spins > (1ll << 26)) { *timed_out = 1; break; }
+      }
+    }
+    __threadfence_system();
+  }
+  __syncthreads();
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float s = 0.0f;
+    for (int r = 0; r < nranks; ++r) s += ((const volatile float*)lr_mbox_stage(peers[r], par, 2))[i];
+    v[i] = s;
+  }
+}
+extern "C" int lrnde_allreduce_sum(lrnde_ctx* ctx, float* v, int64_t n) {
+  LR_API_BEGIN
+  if (!ctx || !v || n < 0) lr_fail(LRNDE_EINVAL, "lrnde_allreduce_sum: bad args");
+  if (ctx->nranks <= 1 || n == 0) return LRNDE_OK;
+  LR_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  DevBuf aux(ctx, 8 + 2 * LR_MAX_RANKS);
+  unsigned int* counter = (unsigned int*)aux.p;
+  int* timed_out = (int*)(aux.p + 1);
+  LrMailbox** peers = (LrMailbox**)(aux.p + 4);
+  LR_CUDA(cudaMemsetAsync(aux.p, 0, 16, st));
+  LR_CUDA(cudaMemcpyAsync(peers, ctx->peer_mbox, sizeof(LrMailbox*) * LR_MAX_RANKS, cudaMemcpyHostToDevice, st));
+  for (int64_t off = 0; off < n; off += LR_MU_MAX) {
+    const size_t cnt = (size_t)std::min<int64_t>(LR_MU_MAX, n - off);
+    ar_publish_kernel<<<64, 256, 0, st>>>(ctx->peer_mbox[ctx->rank], peers, ctx->rank, ctx->nranks, v + off, cnt, ctx->mseq, counter);
+    LR_COUNT(ctx);
+    ar_gather_kernel<<<64, 256, 0, st>>>(ctx->peer_mbox[ctx->rank], peers, ctx->nranks, v + off, cnt, ctx->mseq, timed_out);
+    LR_COUNT(ctx);
+    ctx->mseq += 1;
+  }
+  LR_CHECK_LAUNCH();
+  int to = 0;
+  LR_CUDA(cudaMemcpyAsync(&to, timed_out, sizeof(int), cudaMemcpyDeviceToHost, st));
+  LR_CUDA(cudaStreamSynchronize(st));
+  if (to) lr_fail(LRNDE_ESTATE, "lrnde_allreduce_sum: a peer rank never published its vector (timed out)");
   LR_API_END
 }
 

@@ -268,7 +268,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(ChainP p) {
         v[i] = rowv ? h : hconst;
       }
       const float* kdst = p.single ? sd[1].dst : (last_full ? sd[6].dst : d.dst);
-      if (p.write_z && s_htape && hrow < p.H + p.td + 1) {
+      if (s_htape && hrow < p.H + p.td + 1) {
         // hidden tape for the latent-space adjoint (lrnde_adjoint.cu): H(k_j) = [h_j ; t_j ; 1]
         float* ho = hof(kdst);
 #pragma unroll
@@ -297,7 +297,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(ChainP p) {
       tc_fence_after();
       if (tr) FTRACE(0, 1, 6, st);
       // Z(k_j) to the latent tape
-      if (p.write_z || last_full) {
+      if ((p.single && p.write_z) || last_full) {   // intermediate Z(k_j) are not read back by anything
         float* zo = zof(kdst);
         const int slot = p.single ? 7 : 2 + st;
         tmem_ld16(tlane + (uint32_t)(slot * kNT + col), v);
@@ -308,7 +308,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(ChainP p) {
         }
       }
     }
-    if (!p.single && p.write_z && s_htape && hrow < p.H + p.td + 1) {
+    if (!p.single && s_htape && hrow < p.H + p.td + 1) {
       // cumulative hidden image of the state: u_{n+1} = x + W2a C_{n+1},  C_{n+1} = C_n + dt sum_i a_7i H(k_i)
       // (H(k_2..6) were stored above by this very thread, H(k_1) by an earlier launch)
       const LinComb& d = sd[5];
@@ -360,6 +360,8 @@ struct KgemmP {
   uint32_t unit_bytes;
   int B, D, MT, n_mt, Kaug, KS, nfull, ntail, passes, nunits, nclusters, ring;
   int dbg;   // LRNDE_KG_DBG experiments (profiling only): 1 = no k stores, 2 = no loads, 4 = no residual, 8 = no u store
+  int lean;  // lean tape: k_2..k_6 are not stored (the latent-space adjoint and dense output read the hidden tape)
+  const float* add_base;   // single mode: dst = add_base + W2a [h ; t ; 1]  (dense output y(t) = x + W2a c(t))
 };
 
 // NSTG = stage columns per sample (6: k_2..k_7 of a forward attempt; 2: the b / btilde combinations of an adjoint attempt);
@@ -576,7 +578,7 @@ __global__ void __launch_bounds__(kThreads, 1) kgemm_kernel(KgemmP p) {
         if (mv) {
 #pragma unroll
           for (int i = 0; i < 4; ++i)
-            if (nb + i < p.B) psingle[e0 + (unsigned)i * D] = v[i];
+            if (nb + i < p.B) psingle[e0 + (unsigned)i * D] = p.add_base ? v[i] + __ldcg(p.add_base + m + (e0 + (unsigned)i * D)) : v[i];
         }
         return;
       }
@@ -617,8 +619,10 @@ __global__ void __launch_bounds__(kThreads, 1) kgemm_kernel(KgemmP p) {
         if (!ADJ && !(p.dbg & 1)) {
 #pragma unroll
           for (int jj = 0; jj < NSTG; ++jj)
+            if (jj == NSTG - 1 || !p.lean) {   // k_7 = fsalfirst of the next attempt is always needed
 #pragma unroll
-            for (int i = 0; i < 4; ++i) __stcg(po[jj] + (e0 + (unsigned)i * D), k[jj][i]);
+              for (int i = 0; i < 4; ++i) __stcg(po[jj] + (e0 + (unsigned)i * D), k[jj][i]);
+            }
         }
         if (!(p.dbg & 8)) {
 #pragma unroll
@@ -638,7 +642,8 @@ __global__ void __launch_bounds__(kThreads, 1) kgemm_kernel(KgemmP p) {
             const size_t e = (size_t)(nb + i) * D;
             if (!ADJ) {
 #pragma unroll
-              for (int jj = 0; jj < NSTG; ++jj) po[jj][e] = k[jj][i];
+              for (int jj = 0; jj < NSTG; ++jj)
+                if (jj == NSTG - 1 || !p.lean) po[jj][e] = k[jj][i];
             }
             po[6][e] = unew[i];
             const float r = (edt * ut[i]) / (abstol + fmaxf(fabsf(upc[i]), fabsf(unew[i])) * reltol);
@@ -676,6 +681,66 @@ __global__ void __launch_bounds__(kThreads, 1) kgemm_kernel(KgemmP p) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
+}
+
+// Dense output in hidden space: the operand image (stage-0 rows of every 16-sample unit) of
+//   c(t) = C_n + dt_n sum_i b_i(theta) H(k_i)     so that   y(t) = x + W2a c(t)   (single-mode kgemm with add_base)
+struct InterpP {
+  const float* src[8];   // C_n, H(k_1) ... H(k_7) of the interval
+  float coef[7];
+  float scale;
+  const SolveDev* A;     // non-null: interval / weights from the device descriptor yd of this (adjoint) solve instead
+  const LinComb* yd;
+  LinComb* ydesc_out;    // with A: receives {base = ybase, n = 0, t = yd->t} (the materialised y(t) as a descriptor)
+  float* ybase;
+  float* hbuf;
+  uint32_t unit_bytes;
+  int B, Kaug, KS, nfull, passes;
+};
+__global__ void __launch_bounds__(256) interp_image_kernel(InterpP p) {
+  const int kk = threadIdx.x & 127;
+  const int n = blockIdx.x * 2 + (threadIdx.x >> 7);
+  if (p.A && p.A->failed) return;
+  if (p.A && p.ydesc_out && blockIdx.x == 0 && threadIdx.x == 0) {
+    LinComb d;
+    d.base = p.ybase; d.dst = nullptr; d.n = 0; d.scale = 0.0f; d.t = p.yd->t; d.pad_ = 0;
+    for (int k = 0; k < LR_MAXSRC; ++k) { d.src[k] = nullptr; d.coef[k] = 0.0f; }
+    *p.ydesc_out = d;
+  }
+  if (n >= p.B || kk >= p.KS * 8) return;
+  float v = 0.0f;
+  if (kk < p.Kaug) {
+    const size_t e = (size_t)n * LR_ZROW + kk;
+    float acc = 0.0f;
+    if (p.A) {
+      const size_t slotn = (size_t)(p.yd->base - p.A->ftape) / ((size_t)7 * p.A->flen);
+      const float* hb = p.A->fhtape + slotn * 7 * p.A->fzlen;
+#pragma unroll
+      for (int i = 0; i < 7; ++i) acc = fmaf(p.yd->coef[i], hb[(size_t)(i < 6 ? i + 1 : 8) * p.A->fzlen + e], acc);
+      v = fmaf(p.yd->scale, acc, hb[e]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 7; ++i) acc = fmaf(p.coef[i], p.src[i + 1][e], acc);
+      v = fmaf(p.scale, acc, p.src[0][e]);
+    }
+  }
+  float hi, lo;
+  if (p.passes == 3) { hi = tf32_rna(v); lo = tf32_rna(v - hi); }
+  else { hi = v; lo = 0.0f; }
+  uint8_t* g = reinterpret_cast<uint8_t*>(p.hbuf) + (size_t)(n >> 4) * p.unit_bytes;
+  const int r = n & 15;
+  uint32_t o, lo_step;
+  if (kk < p.nfull * 32) {
+    const int c = kk >> 5, k5 = kk & 31;
+    o = (uint32_t)(c * kPieceBytes + (r >> 3) * 1024 + (r & 7) * 128 + (((k5 >> 2) ^ (r & 7)) << 4) + (k5 & 3) * 4);
+    lo_step = (uint32_t)(kUR * 128);
+  } else {
+    const int kt = kk - p.nfull * 32, t = kt >> 3, k3 = kt & 7;
+    o = (uint32_t)(p.nfull * kPieceBytes + t * kTailBytes + r * 32 + ((((k3 >> 2) & 1) ^ ((r >> 2) & 1)) << 4) + (k3 & 3) * 4);
+    lo_step = (uint32_t)(kUR * 32);
+  }
+  *reinterpret_cast<float*>(g + o) = hi;
+  *reinterpret_cast<float*>(g + o + lo_step) = lo;
 }
 
 }  // namespace fused
@@ -809,6 +874,8 @@ static void lrf_launch_kgemm(FusedEngine& E, SolveDev* S, const LinComb* single,
   kp.W2a = E.ps + L2.w_off; kp.hbuf = E.hbuf; kp.unit_bytes = (uint32_t)E.unit_bytes;
   kp.B = (int)E.B; kp.D = sh.D; kp.MT = sh.MT; kp.n_mt = sh.n_mt; kp.Kaug = sh.Kaug; kp.KS = sh.KS; kp.nfull = sh.nfull;
   kp.dbg = getenv("LRNDE_KG_DBG") ? atoi(getenv("LRNDE_KG_DBG")) : 0;
+  kp.lean = (!single && E.lean) ? 1 : 0;
+  kp.add_base = single ? E.add_base : nullptr;
   kp.ntail = sh.ntail; kp.passes = E.passes; kp.nunits = E.nunits; kp.nclusters = E.nclusters; kp.ring = E.ring;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
@@ -853,6 +920,35 @@ static void lrf_launch(FusedEngine& E, SolveDev* S, const LinComb* single, const
                        int write_z) {
   lrf_launch_chain(E, S, single, single_out, done, write_z);
   lrf_launch_kgemm(E, S, single, single_out, done);
+}
+
+void FusedEngine::dense_output(SolveDev* S, const float* const* harr, const float* coef, float scale, const float* xbase,
+                               const LinComb* out_desc) {
+  fused::InterpP ip;
+  memset(&ip, 0, sizeof(ip));
+  for (int i = 0; i < 8; ++i) ip.src[i] = harr[i];
+  for (int i = 0; i < 7; ++i) ip.coef[i] = coef[i];
+  ip.scale = scale; ip.hbuf = hbuf; ip.unit_bytes = (uint32_t)unit_bytes;
+  ip.B = (int)B; ip.Kaug = sh.Kaug; ip.KS = sh.KS; ip.nfull = sh.nfull; ip.passes = passes;
+  fused::interp_image_kernel<<<(int)((B + 1) / 2), 256, 0, ctx->stream>>>(ip);
+  LRF_COUNT(ctx);
+  add_base = xbase;
+  lrf_launch_kgemm(*this, S, out_desc, out_desc, nullptr);
+  add_base = nullptr;
+}
+
+void FusedEngine::dense_output_dev(SolveDev* A, const LinComb* yd, const float* xbase, float* ybuf, LinComb* ydesc_out,
+                                   const LinComb* out_desc) {
+  fused::InterpP ip;
+  memset(&ip, 0, sizeof(ip));
+  ip.A = A; ip.yd = yd; ip.ydesc_out = ydesc_out; ip.ybase = ybuf;
+  ip.hbuf = hbuf; ip.unit_bytes = (uint32_t)unit_bytes;
+  ip.B = (int)B; ip.Kaug = sh.Kaug; ip.KS = sh.KS; ip.nfull = sh.nfull; ip.passes = passes;
+  fused::interp_image_kernel<<<(int)((B + 1) / 2), 256, 0, ctx->stream>>>(ip);
+  LRF_COUNT(ctx);
+  add_base = xbase;
+  lrf_launch_kgemm(*this, A, out_desc, out_desc, &A->failed);
+  add_base = nullptr;
 }
 
 void FusedEngine::step_chain(SolveDev* S, int write_z) { lrf_launch_chain(*this, S, nullptr, nullptr, nullptr, write_z); }

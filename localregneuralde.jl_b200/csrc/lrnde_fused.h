@@ -49,6 +49,8 @@ struct FusedEngine {
   float* Mimg = nullptr;   // chain A operand: [hi | lo] images of Mz, 128 rows
   float* hbuf = nullptr;   // operand images written by the chain kernel: per 16-sample unit, 96 rows = 6 stages x 16
   size_t imgM = 0, unit_bytes = 0;
+  int lean = 0;                     // lean tape: attempts do not store k_2..k_6
+  const float* add_base = nullptr;  // dense_output(): base array of the single-mode kgemm
 
   static bool eligible(const lrnde_model* m);
   FusedEngine(lrnde_ctx* c, const lrnde_model* mm, const float* p, int64_t b, int npasses);
@@ -61,4 +63,12 @@ struct FusedEngine {
   void step_kgemm(SolveDev* S);
   // dst <- f(lincomb(in)) for a descriptor whose arrays live on S's tape; (out ? out : in)->dst receives k
   void eval(SolveDev* S, const LinComb* in, const LinComb* out, const int* done, int write_z);
+  // dense output from the hidden tape: out_desc->dst <- xbase + W2a (harr[0] + scale * sum_i coef[i] * harr[i + 1])
+  // (harr: C_n, H(k_1..7) of the interval, [B][LR_ZROW] each; out_desc: device descriptor, only dst is used)
+  void dense_output(SolveDev* S, const float* const* harr, const float* coef, float scale, const float* xbase,
+                    const LinComb* out_desc);
+  // the same from a device-resident interpolant descriptor yd of the adjoint solve A (A->fhtape ...): out_desc->dst (=
+  // ybuf) <- y(yd->t), and *ydesc_out <- the materialised state as a descriptor {base = ybuf, t = yd->t}
+  void dense_output_dev(SolveDev* A, const LinComb* yd, const float* xbase, float* ybuf, LinComb* ydesc_out,
+                        const LinComb* out_desc);
 };

@@ -841,16 +841,14 @@ __global__ void controller_kernel(SolveDev* S) {
   if (S->done) { if (threadIdx.x == 0) lr_set_cond(S); return; }
   double v[4];
   v[0] = lr_sum_partials(S->partials);
-  v[1] = (S->reduce_mu && S->nranks > 1) ? lr_sum_partials(S->partials + 3 * LR_ERR_BLOCKS) : 0.0;
+  // mu block of the adjoint state: row 1 = latent-space engine (adj_mu_kernel / adj_mu_finish_kernel), row 3 = the
+  // exchanged global vectors of the per-layer engine; in a group both are already global and identical on every rank
+  v[1] = S->lat_mu_row ? lr_sum_partials(S->partials + LR_ERR_BLOCKS)
+                       : ((S->reduce_mu && S->nranks > 1) ? lr_sum_partials(S->partials + 3 * LR_ERR_BLOCKS) : 0.0);
   if (threadIdx.x != 0) return;
   v[2] = v[3] = 0.0;
-  if (S->lat_mu_row) {   // latent-space adjoint: the mu block's partial sums (adj_mu_kernel)
-    double mu = 0.0;
-    for (int i = 0; i < LR_ERR_BLOCKS; ++i) mu += S->partials[LR_ERR_BLOCKS + i];
-    v[0] += mu;
-  }
-  if (!(S->reduce_mu && S->nranks > 1)) lr_group_sum(S, v);
-  else { double w[4] = {v[0], 0, 0, 0}; lr_group_sum(S, w); v[0] = w[0] + v[1]; }
+  if (S->lat_mu_row && S->reduce_mu && S->nranks > 1) S->mseq += 1;   // next vector exchange uses the other parity
+  { double w[4] = {v[0], 0, 0, 0}; lr_group_sum(S, w); v[0] = w[0] + v[1]; }
   float EEst = sqrtf((float)v[0] / (float)(double)S->total_len);
   const float t_before = S->c.t, dt_before = S->c.dt;
   float dt_taken = 0.0f;

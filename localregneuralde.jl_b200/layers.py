@@ -13,6 +13,7 @@ from __future__ import annotations
 import copy
 import ctypes as C
 import math
+import warnings
 from dataclasses import dataclass
 from typing import List, Optional, Sequence
 
@@ -428,24 +429,39 @@ class NeuralODE:
         n_ps = psb.size if host else psb.numel()
         if n_ps != nparams(self.model):
             raise ValueError("ps has the wrong length for this model")
-        if o.nsave > 0:
-            cap = o.nsave + 1
-        elif o.nsave == 0:
-            cap = 2
-        else:
-            cap = self.maxiters + 2
-        if host:
-            usave = _host_empty((cap, B, D))
-        else:
-            usave = torch.empty((cap, B, D), dtype=torch.float32, device=xb.device)
-        times = np.zeros(cap, np.float32)
+        def _alloc(cap):
+            if host:
+                return _host_empty((cap, B, D))
+            return torch.empty((cap, B, D), dtype=torch.float32, device=xb.device)
+
         stats = Stats()
         tape = C.c_void_p()
         ctx = self.ctx
         mh = ctx.model_handle(self.model)
         running = self._attach_model_state(o, st.get("model"), host, None if host else xb.device)
-        check(lib().lrnde_ode_forward(ctx._h, mh, C.byref(o), _ptr(psb), _ptr(xb), B, _ptr(usave),
-                                      cap, _ptr(times), C.byref(stats), C.byref(tape)))
+        if o.nsave >= 0:
+            cap = (o.nsave + 1) if o.nsave > 0 else 3        # [u0,] [u(t1),] u(t2)
+            usave = _alloc(cap)
+            times = np.zeros(cap, np.float32)
+            check(lib().lrnde_ode_forward(ctx._h, mh, C.byref(o), _ptr(psb), _ptr(xb), B, _ptr(usave),
+                                          cap, _ptr(times), C.byref(stats), C.byref(tape)))
+        else:
+            # every accepted step (:biased, neural_ode.jl:86-100): their number is only known after the solve, so the
+            # states are fetched from the kept solution afterwards instead of reserving maxiters + 2 blocks up front
+            user_keep = bool(o.keep_tape)
+            o.keep_tape = 1
+            check(lib().lrnde_ode_forward(ctx._h, mh, C.byref(o), _ptr(psb), _ptr(xb), B, None,
+                                          0, None, C.byref(stats), C.byref(tape)))
+            cap = max(1, stats.nsave_out)
+            usave = _alloc(cap)
+            times = np.zeros(cap, np.float32)
+            check(lib().lrnde_ode_saved_states(ctx._h, mh, tape, _ptr(usave), cap, _ptr(times)))
+            if not user_keep:
+                check(lib().lrnde_tape_free(tape))
+                tape = C.c_void_p()
+        if stats.retcode != 0:
+            warnings.warn(f"NeuralODE solve finished with retcode {_lib.RETCODES.get(stats.retcode, stats.retcode)} "
+                          "(the reference warns and returns the partial solution as well)")
         n = stats.nsave_out
         us = [usave[i].T for i in range(n)]        # back to (D, B) views
         sol = DESolution([T(t) for t in times[:n]], us, tape if keep_tape else None, self, ctx,

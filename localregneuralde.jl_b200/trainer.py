@@ -91,6 +91,44 @@ def lr_scheduler(name: str, lr: float, *, total_steps: int = 1, cosine_lr_div_fa
                      "`exponential`, `inverse` and `cosine`." % name)
 
 
+# ------------------------------------------------------------------ optimisers (experiments/src/construct.jl:103-126)
+class Optimiser:
+    """``construct(expt, cfg::OptimizerConfig)``: cfg.optimizer in ("adam", "adamw", "adamax", "sgd"); "sgd" is
+    Nesterov(lr, momentum) when cfg.nesterov, Descent(lr) when momentum == 0, else Momentum(lr, momentum);
+    weight_decay != 0 chains WeightDecay(weight_decay) after the rule (Optimisers.jl OptimiserChain).  AdamW(lr) is
+    Adam chained with WeightDecay(0) in Optimisers.jl, i.e. the Adam update.  The state lives in device buffers
+    (torch tensors) and every update is one ``lrnde_opt_step`` launch per parameter block."""
+
+    def __init__(self, optimizer: str = "adam", learning_rate: float = 1e-3, momentum: float = 0.0,
+                 nesterov: bool = False, weight_decay: float = 0.0, beta=(0.9, 0.999), eps: float = 1e-8):
+        if optimizer in ("adam", "adamw"):
+            self.kind = "adam"
+        elif optimizer == "adamax":
+            self.kind = "adamax"
+        elif optimizer == "sgd":
+            self.kind = "nesterov" if nesterov else ("descent" if momentum == 0 else "momentum")
+        else:
+            raise ValueError(f"unknown value for `optimizer` = {optimizer}. Supported options are: `adam`, `adamax` "
+                             "and `sgd`.")
+        self.lr, self.momentum, self.weight_decay, self.beta, self.eps = learning_rate, momentum, weight_decay, beta, eps
+        self.state = {}
+
+    def update(self, ctx: Context, key, p, g, step: int, lr: Optional[float] = None):
+        """p <- p - rule(g) in place (p, g: CUDA tensors); ``step`` is the 1-based iteration count."""
+        import torch
+        if key not in self.state:
+            n1 = self.kind != "descent"
+            n2 = self.kind in ("adam", "adamax")
+            self.state[key] = (torch.zeros_like(p) if n1 else None, torch.zeros_like(p) if n2 else None)
+        s1, s2 = self.state[key]
+        a, b = (self.beta if self.kind in ("adam", "adamax") else (self.momentum, 0.0))
+        g = g.contiguous()
+        check(lib().lrnde_opt_step(ctx._h, _lib.OPT[self.kind], p.data_ptr(), g.data_ptr(),
+                                   s1.data_ptr() if s1 is not None else None, s2.data_ptr() if s2 is not None else None,
+                                   p.numel(), float(self.lr if lr is None else lr), float(a), float(b), float(self.eps),
+                                   float(self.weight_decay), int(step)))
+
+
 # ------------------------------------------------------------------ CSV schema (experiments/src/logging.jl:102-128)
 def train_csv_header(latent_ode: bool = False, sde: bool = False) -> List[str]:
     return (["Step", "Batch Time", "Data Time", "Forward Pass Time", "Backward Pass Time", "Optimizer Time"]
@@ -127,11 +165,13 @@ class MnistODETrainer:
     def __init__(self, *, hidden: int = 100, lr: float = 1e-3, scheduler: str = "inverse", w_reg_start: float = 100.0,
                  w_reg_end: float = 10.0, w_reg_decay: str = "exponential", total_steps: int = 1000, abstol: float = 1.4e-8,
                  reltol: float = 1.4e-8, regularize: str = "unbiased", seed: int = 0, ctx: Optional[Context] = None,
-                 device: int = 0):
+                 device: int = 0, optimizer: str = "adam", momentum: float = 0.0, nesterov: bool = False,
+                 weight_decay: float = 0.0):
         import torch
         self.torch = torch
         self.dev = torch.device("cuda", device)
         self.ctx = ctx or Context(device, torch.cuda.current_stream(self.dev).cuda_stream)
+        self.optim = Optimiser(optimizer, lr, momentum, nesterov, weight_decay)
         self.D, self.C = 784, 10
         self.chain = TDChain(Chain(Dense(self.D, hidden, "tanh"), Dense(hidden, self.D)))
         self.node = NeuralODE(self.chain, regularize=regularize, save_start=False, abstol=abstol, reltol=reltol,
@@ -143,7 +183,6 @@ class MnistODETrainer:
                              np.zeros(self.C, np.float32)])
         self.wc = torch.from_numpy(wc).to(self.dev)
         self.st = self.node.initialstates(rng)
-        self.opt = [torch.zeros_like(self.ps), torch.zeros_like(self.ps), torch.zeros_like(self.wc), torch.zeros_like(self.wc)]
         self.lr_sched = lr_scheduler(scheduler, lr, total_steps=total_steps)
         self.w_reg_sched = ExponentialDecay(w_reg_start, w_reg_end, total_steps) if w_reg_decay == "exponential" \
             else Constant(w_reg_start)
@@ -171,9 +210,8 @@ class MnistODETrainer:
         torch.cuda.synchronize(self.dev)
         t_bwd = time.perf_counter() - t0
         t0 = time.perf_counter()
-        for p, g, m, v in ((self.ps, d_ps, self.opt[0], self.opt[1]), (self.wc, d_wc, self.opt[2], self.opt[3])):
-            check(L.lrnde_adam_step(self.ctx._h, p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(),
-                                    float(lr), 0.9, 0.999, 1e-8, self.step))
+        for key, p, g in (("ps", self.ps, d_ps), ("wc", self.wc, d_wc)):
+            self.optim.update(self.ctx, key, p, g, self.step, lr)
         torch.cuda.synchronize(self.dev)
         t_opt = time.perf_counter() - t0
         # metrics (not on the timed path): logits = W u + b
@@ -181,8 +219,8 @@ class MnistODETrainer:
         logits = u_last @ W + self.wc[self.C * self.D:]
         top5 = logits.topk(5, dim=1).indices
         yl = y.long()
-        acc1 = float((top5[:, 0] == yl).float().mean())
-        acc5 = float((top5 == yl[:, None]).any(dim=1).float().mean())
+        acc1 = 100.0 * float((top5[:, 0] == yl).float().mean())        # percent, as accuracy() of experiments/src/utils.jl
+        acc5 = 100.0 * float((top5 == yl[:, None]).any(dim=1).float().mean())
         reg = float(st2["reg_val"])
         nfe = int(st2["nfe"])
         sol.free()
@@ -201,11 +239,13 @@ class Cifar10ODETrainer:
     def __init__(self, *, hidden: int = 64, image: int = 32, lr: float = 1e-3, scheduler: str = "inverse",
                  w_reg_start: float = 100.0, w_reg_end: float = 10.0, total_steps: int = 1000, abstol: float = 1e-4,
                  reltol: float = 1e-4, regularize: str = "unbiased", seed: int = 0, ctx: Optional[Context] = None,
-                 device: int = 0):
+                 device: int = 0, optimizer: str = "adam", momentum: float = 0.0, nesterov: bool = False,
+                 weight_decay: float = 0.0):
         import torch
         self.torch = torch
         self.dev = torch.device("cuda", device)
         self.ctx = ctx or Context(device, torch.cuda.current_stream(self.dev).cuda_stream)
+        self.optim = Optimiser(optimizer, lr, momentum, nesterov, weight_decay)
         self.W = self.H = int(image)
         self.C = 10
         self.aug = AugmenterLayer(3, 5)
@@ -225,7 +265,6 @@ class Cifar10ODETrainer:
                       node=glorot_uniform(self.chain, rng), cls_conv=conv_init(8, 1),
                       head=np.concatenate([rng.uniform(-a, a, self.C * D), np.zeros(self.C)]).astype(np.float32))
         self.ps = {k: torch.from_numpy(v).to(self.dev) for k, v in params.items()}
-        self.opt = {k: (torch.zeros_like(v), torch.zeros_like(v)) for k, v in self.ps.items()}
         self.st = self.node.initialstates(rng)
         self.bn_state = dict(running=torch.cat([torch.zeros(8), torch.ones(8)]).to(self.dev), training=True)
         self.lr_sched = lr_scheduler(scheduler, lr, total_steps=total_steps)
@@ -266,18 +305,15 @@ class Cifar10ODETrainer:
         t_bwd = time.perf_counter() - t0
         t0 = time.perf_counter()
         for k, p in ps.items():
-            m, v = self.opt[k]
-            g = grads[k].contiguous()
-            check(L.lrnde_adam_step(self.ctx._h, p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(),
-                                    float(lr), 0.9, 0.999, 1e-8, self.step))
+            self.optim.update(self.ctx, k, p, grads[k], self.step, lr)
         torch.cuda.synchronize(self.dev)
         t_opt = time.perf_counter() - t0
         Wh = ps["head"][: self.C * W * H].view(W * H, self.C)             # column-major [C x D]
         logits = flat @ Wh + ps["head"][self.C * W * H:]
         top5 = logits.topk(5, dim=1).indices
         yl = y.long()
-        acc1 = float((top5[:, 0] == yl).float().mean())
-        acc5 = float((top5 == yl[:, None]).any(dim=1).float().mean())
+        acc1 = 100.0 * float((top5[:, 0] == yl).float().mean())        # percent, as accuracy() of experiments/src/utils.jl
+        acc5 = 100.0 * float((top5 == yl[:, None]).any(dim=1).float().mean())
         reg, nfe = float(st2["reg_val"]), int(st2["nfe"])
         sol.free()
         self.st, self.bn_state = st2, bn_state

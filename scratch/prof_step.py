@@ -16,6 +16,12 @@ for B in [int(a) for a in sys.argv[1:]] or [8192, 128]:
     node = pkg.NeuralODE(chain, ctx=ctx, abstol=1.4e-8, reltol=1.4e-8, precision="tf32x3")
     ps = torch.from_numpy(node.initialparameters(np.random.default_rng(0))).to(dev)
     x = torch.rand((B, 784), device=dev)
+    for keep in (False, True):
+      o, _ = node._opts("none", 0.0, 0.0, keep, False)
+      us = (C.c_float * 3)()
+      pkg._lib.check(L.lrnde_profile_step(ctx._h, ctx.model_handle(chain), C.byref(o), C.c_void_p(ps.data_ptr()),
+                                          C.c_void_p(x.data_ptr()), C.c_int64(B), 20, us))
+      print(f"== B={B} keep_tape={keep}: chain {us[0]:.1f} us  kgemm {us[1]:.1f} us  attempt {us[2]:.1f} us")
     o, _ = node._opts("none", 0.0, 0.0, False, False)
     us = (C.c_float * 3)()
     pkg._lib.check(L.lrnde_profile_step(ctx._h, ctx.model_handle(chain), C.byref(o), C.c_void_p(ps.data_ptr()),

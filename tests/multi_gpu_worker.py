@@ -1,0 +1,83 @@
+"""Worker of tests/test_gpu_multi.py (one process per GPU, torchrun): the batch-sharded run of the layer against the
+same global batch on one GPU -- SURVEY 8(e): identical accept / reject sequences forward and backward on every rank,
+states / regulariser / gradients equal to the single-GPU run, and lrnde_allreduce_sum equal to the sum of the ranks'
+vectors with identical bits everywhere.  Prints one line per (precision, rank) and exits non-zero on a mismatch."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as entry  # noqa: E402
+import oracle as orc  # noqa: E402
+
+pkg = entry.load_package()
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+
+
+def gather(blob):
+    out = [None] * world
+    dist.all_gather_object(out, blob)
+    return out
+
+
+def rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-30))
+
+
+D, H, Bt = 784, 100, 64 * world
+rng = np.random.default_rng(4)
+om = orc.mnist_ode_model(D, H)
+ps = (orc.glorot_uniform_params(om, rng) * 5).astype(np.float32)
+x = rng.random((D, Bt), dtype=np.float32)
+c = (rng.standard_normal((D, Bt)) / Bt).astype(np.float32)
+chain = pkg.TDChain(pkg.Chain(pkg.Dense(D, H, "tanh"), pkg.Dense(H, D)))
+ctx_dp = pkg.Context(local, torch.cuda.current_stream(dev).cuda_stream)
+ctx_dp.setup_group(rank, world, Bt, gather)
+ctx_1 = pkg.Context(local, torch.cuda.current_stream(dev).cuda_stream)
+lo, hi = rank * Bt // world, (rank + 1) * Bt // world
+ok = True
+for prec, tol in (("fp32", 1e-6), ("tf32x3", 1e-3)):       # tf32x3 at a truncation-dominated tolerance (latent-space engines)
+    kw = dict(regularize="unbiased", abstol=tol, reltol=tol, maxiters=10000, save_start=False, precision=prec)
+    res = {}
+    for name, ctx, xs, cs in (("single", ctx_1, x, c), ("dp", ctx_dp, x[:, lo:hi], c[:, lo:hi])):
+        node = pkg.NeuralODE(chain, ctx=ctx, **kw)
+        st = node.initialstates(np.random.default_rng(9))
+        sol, st2 = node(np.ascontiguousarray(xs), ps, st)
+        d_x, d_ps = node.backward(sol, [None, np.ascontiguousarray(cs)], 2.5)
+        t, dt, ee, acc = sol.step_log(0)
+        bt, bdt, bee, bacc = sol.step_log(1)
+        res[name] = dict(u=np.asarray(sol.u[-1]).copy(), reg=float(st2["reg_val"]), nfe=st2["nfe"], d_x=np.asarray(d_x).copy(),
+                         d_ps=np.asarray(d_ps).copy(), acc=acc, bacc=bacc, dt=dt, nfb=sol.bwd_stats.nf_bwd)
+        sol.free()
+    # the product's own gradient all-reduce (peer loads over NVLink), checked against NCCL
+    g = torch.from_numpy(res["dp"]["d_ps"]).to(dev)
+    g2 = g.clone()
+    pkg._lib.check(pkg.lib().lrnde_allreduce_sum(ctx_dp._h, g.data_ptr(), g.numel()))
+    dist.all_reduce(g2)
+    allg = [torch.empty_like(g) for _ in range(world)]
+    dist.all_gather(allg, g)
+    same_bits = all(torch.equal(allg[0], a) for a in allg)
+    s, d = res["single"], res["dp"]
+    same_f = np.array_equal(s["acc"], d["acc"]) and s["nfe"] == d["nfe"]
+    same_b = np.array_equal(s["bacc"], d["bacc"]) and s["nfb"] == d["nfb"]
+    e_u, e_dx = rel(d["u"], s["u"][:, lo:hi]), rel(d["d_x"], s["d_x"][:, lo:hi])
+    e_dps, e_ar = rel(g.cpu().numpy(), s["d_ps"]), rel(g.cpu().numpy(), g2.cpu().numpy())
+    e_reg = abs(d["reg"] - s["reg"]) / abs(s["reg"])
+    bar = 1e-5 if prec == "fp32" else 2e-4
+    good = same_f and same_b and same_bits and e_u < bar and e_dx < 10 * bar and e_dps < 10 * bar and e_ar < 1e-6 and e_reg < 10 * bar
+    ok = ok and good
+    print(f"[multi-gpu rank {rank}/{world}] prec={prec} fwd attempts {len(s['acc'])}/{len(d['acc'])} same={same_f} "
+          f"bwd attempts {len(s['bacc'])}/{len(d['bacc'])} same={same_b} u {e_u:.2e} d_x {e_dx:.2e} d_ps(allreduced) {e_dps:.2e} "
+          f"reg {e_reg:.2e} allreduce vs nccl {e_ar:.2e} identical bits on all ranks {same_bits} -> {'ok' if good else 'MISMATCH'}",
+          flush=True)
+dist.barrier()
+dist.destroy_process_group()
+sys.exit(0 if ok else 1)

@@ -18,6 +18,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLD = os.path.join(ROOT, "tests", "golden")
 PRECS = ["fp32", "tf32x3"]
 PRECS_SMALL = ["fp32", "tf32x3", "smem"]     # "smem": the shared-memory engine (networks that fit one SM)
+NOISE_TF32X3 = 1.0    # measured on B200: |reg_gpu - reg32| / |reg32 - reg64| <= 2.8 on every fixture for tf32x3 (fp32: <= 3.7), inside the 10x allowance of the fp32 engine: the 3xTF32 engines need no extra factor
 
 
 @pytest.fixture(scope="module")
@@ -125,7 +126,9 @@ def test_layer_matches_golden(pkg, name, loop_mode, prec):
     strict_bwd = strict and int(g["n_bwd64"]) == len(g["bwd_step_log"])
     # 3xTF32 keeps fp32-level products but drops the lo*lo term and rounds the lo parts: its
     # rounding noise is a few times the FP32 FMA's, so noise-regime allowances scale with it
-    noise = 1.0 if prec in ("fp32", "smem") else 30.0
+    # measured on B200 (LRNDE_TEST_VERBOSE=1 prints the ratios): |reg_gpu - reg32| / |reg32 - reg64| stays below
+    # NOISE_TF32X3 on every noise-regime fixture; fp32 / smem do the oracle's arithmetic and get 1
+    noise = 1.0 if prec in ("fp32", "smem") else NOISE_TF32X3
     layer = pkg.NeuralODE(_chain(pkg, layers, td, input_act), precision=prec, loop_mode=loop_mode, **kw)
     st = layer.initialstates(np.random.default_rng(seed + 100))
     if name == "eval_mode":
@@ -161,6 +164,9 @@ def test_layer_matches_golden(pkg, name, loop_mode, prec):
     reg32, reg64 = float(g["reg_val"]), float(g["reg_val64"])
     if name != "eval_mode":
         tol = 1e-4 * abs(reg32) + 10 * noise * abs(reg32 - reg64) + 1e-12   # 2nd term: pure-noise regime
+        if os.environ.get("LRNDE_TEST_VERBOSE"):
+            print(f"[noise] {name} {prec} loop{loop_mode}: |reg_gpu-reg32|/|reg32-reg64| = "
+                  f"{abs(float(st2['reg_val']) - reg32) / (abs(reg32 - reg64) + 1e-30):.3g} strict={strict}")
         assert abs(float(st2["reg_val"]) - reg32) <= tol, (float(st2["reg_val"]), reg32, reg64)
         if kw.get("regularize") != "biased" or strict:
             assert abs(sol.stats.t1_used - float(g["t1"])) < 1e-4
@@ -187,7 +193,7 @@ def test_layer_matches_golden(pkg, name, loop_mode, prec):
     d_x, d_ps = layer.backward(sol, cots, float(g["d_reg"]))
     bt, bdt, beest, bacc = sol.step_log(1)
     bw = g["bwd_step_log"]
-    if strict_bwd and prec == "fp32":
+    if strict_bwd and prec in ("fp32", "tf32x3"):     # tf32x3: the latent-space adjoint on the two-layer fixtures
         assert len(bt) == len(bw), (len(bt), len(bw))
         assert np.array_equal(bacc, bw[:, 3].astype(bool))
         assert sol.bwd_stats.nf_bwd == int(g["nf_bwd"])
@@ -313,7 +319,18 @@ def test_mnist_ode_b128_reference_tolerance(pkg, prec):
     d_x0, d_ps0 = node.backward(sol, [None, c], 0.0)
     o_dx0, o_dps0 = on.backward(aux, [None, c], 0.0, ps)
     assert rel(d_ps0, o_dps0) < 1e-3, rel(d_ps0, o_dps0)
-    print("reg gpu/oracle", float(st2["reg_val"]), float(ost2["reg_val"]), "d_ps rel", rel(d_ps, o_dps))
+    # the regulariser value and the total gradient against the Float64 twin of the oracle, within the measured
+    # Float32-vs-Float64 gap of the oracle itself (both are rounding noise of the same step at this tolerance)
+    on64 = orc.NeuralODE(om, regularize="unbiased", save_start=False, dtype=np.float64, **kw)
+    osol64, ost64, aux64 = on64.forward(x.astype(np.float64), ps.astype(np.float64), on64.initialstates(np.random.default_rng(7)))
+    _, o_dps64 = on64.backward(aux64, [None, c.astype(np.float64)], 2.5, ps.astype(np.float64))
+    reg_gpu, reg32, reg64 = float(st2["reg_val"]), float(ost2["reg_val"]), float(ost64["reg_val"])
+    gap_reg = abs(reg32 - reg64)
+    gap_dps = rel(o_dps, o_dps64)
+    noise = 1.0 if prec == "fp32" else NOISE_TF32X3
+    print("reg gpu/oracle32/oracle64", reg_gpu, reg32, reg64, "d_ps rel vs f64: gpu", rel(d_ps, o_dps64), "oracle32", gap_dps)
+    assert abs(reg_gpu - reg64) <= 10 * noise * gap_reg + 1e-4 * abs(reg64), (reg_gpu, reg32, reg64)
+    assert rel(d_ps, o_dps64) <= 1e-3 + 10 * noise * gap_dps, (rel(d_ps, o_dps64), gap_dps)
 
 
 # ------------------------------------------------------------------ full-size properties
@@ -512,3 +529,175 @@ def test_return_last_only_is_the_fused_sol_to_arr(pkg):
     dx2, dp2 = last.backward(s2, [cot], 0.7)
     assert np.asarray(dx1).tobytes() == np.asarray(dx2).tobytes() and np.asarray(dp1).tobytes() == np.asarray(dp2).tobytes()
     s1.free(); s2.free()
+
+
+# ------------------------------------------------------------------ latent-space engines vs the per-layer engines
+@pytest.mark.parametrize("shape", [(16, 12, 37), (784, 100, 96)])
+def test_latent_space_engines_match_the_layer_engines(pkg, shape):
+    """The hidden-space schedule (csrc/lrnde_fused.cu forward attempts with the lean tape, csrc/lrnde_adjoint.cu
+    adjoint attempts) against the per-layer tcgen05 kernels (LRNDE_NO_FUSED=1: one GEMM per layer, D-dimensional
+    tape and adjoint) on a truncation-dominated case: same accept / reject sequences forward and backward, same NFE,
+    states, regulariser and gradients."""
+    Dd, Hh, B = shape
+    layers = [(Dd, Hh, "tanh"), (Hh, Dd, "identity")]
+    om = _omodel(layers, True, None)
+    rng = np.random.default_rng(11)
+    ps = (orc.glorot_uniform_params(om, rng) * (3 if Dd < 100 else 5)).astype(np.float32)
+    x = (rng.standard_normal((Dd, B)) if Dd < 100 else rng.random((Dd, B))).astype(np.float32)
+    cot = [(rng.standard_normal((Dd, B)) / B).astype(np.float32) for _ in range(2)]
+    kw = dict(regularize="unbiased", abstol=1e-3, reltol=1e-3, save_start=False, precision="tf32x3")
+    out = {}
+    for mode in ("latent", "layers"):
+        if mode == "layers":
+            os.environ["LRNDE_NO_FUSED"] = "1"
+        try:
+            node = pkg.NeuralODE(_chain(pkg, layers, True, None), **kw)
+            sol, st2 = node(x, ps, node.initialstates(np.random.default_rng(3)))
+            d_x, d_ps = node.backward(sol, cot, 0.9)
+            out[mode] = dict(u=[np.asarray(u).copy() for u in sol.u], reg=float(st2["reg_val"]), nfe=st2["nfe"],
+                             log=sol.step_log(0), blog=sol.step_log(1), d_x=np.asarray(d_x).copy(),
+                             d_ps=np.asarray(d_ps).copy(), nfb=sol.bwd_stats.nf_bwd)
+            sol.free()
+        finally:
+            os.environ.pop("LRNDE_NO_FUSED", None)
+    a, b = out["latent"], out["layers"]
+    assert a["nfe"] == b["nfe"] and a["nfb"] == b["nfb"]
+    assert np.array_equal(a["log"][3], b["log"][3]) and np.array_equal(a["blog"][3], b["blog"][3])
+    np.testing.assert_allclose(a["log"][1], b["log"][1], rtol=2e-3)          # dt sequence
+    for ua, ub in zip(a["u"], b["u"]):
+        assert rel(ua, ub) < 2e-5, rel(ua, ub)
+    assert abs(a["reg"] - b["reg"]) <= 2e-3 * abs(b["reg"]), (a["reg"], b["reg"])
+    assert rel(a["d_x"], b["d_x"]) < 3e-4 and rel(a["d_ps"], b["d_ps"]) < 3e-4, (rel(a["d_x"], b["d_x"]), rel(a["d_ps"], b["d_ps"]))
+
+
+def test_save_start_in_unbiased_mode_prepends_u0(pkg):
+    """NeuralODE(...; save_start = true) splats into solve (neural_ode.jl:51): sol.u = [u0, u(t1), u(t2)], and a
+    cotangent on u0 flows straight into d_x."""
+    layers = [(16, 12, "tanh"), (12, 16, "identity")]
+    om = _omodel(layers, True, None)
+    rng = np.random.default_rng(5)
+    ps = (orc.glorot_uniform_params(om, rng) * 3).astype(np.float32)
+    x = rng.standard_normal((16, 9)).astype(np.float32)
+    kw = dict(regularize="unbiased", abstol=1e-3, reltol=1e-3, save_start=True)
+    node = pkg.NeuralODE(_chain(pkg, layers, True, None), precision="tf32x3", **kw)
+    on = orc.NeuralODE(om, **kw)
+    sol, st2 = node(x, ps, node.initialstates(np.random.default_rng(2)))
+    osol, ost2, aux = on.forward(x, ps, on.initialstates(np.random.default_rng(2)))
+    assert len(sol.u) == len(osol.u) == 3 and float(sol.t[0]) == 0.0
+    assert np.array_equal(np.asarray(sol.u[0]), x)
+    for i in range(3):
+        assert rel(sol.u[i], osol.u[i]) < 1e-4
+    cots = [(rng.standard_normal((16, 9)) / 9).astype(np.float32) for _ in range(3)]
+    d_x, d_ps = node.backward(sol, cots, 0.0)
+    o_dx, o_dps = on.backward(aux, cots, 0.0, ps)
+    assert rel(d_x, o_dx) < 1e-3 and rel(d_ps, o_dps) < 1e-3
+    sol.free()
+
+
+def test_biased_mode_sizes_the_states_from_the_solve(pkg):
+    """:biased with the experiments' maxiters = 10_000: the saved states are fetched after the solve
+    (lrnde_ode_saved_states), one block per accepted step, instead of reserving maxiters + 2 blocks."""
+    layers = [(784, 100, "tanh"), (100, 784, "identity")]
+    om = _omodel(layers, True, None)
+    rng = np.random.default_rng(0)
+    ps = (orc.glorot_uniform_params(om, rng) * 5).astype(np.float32)
+    B = 512
+    x = rng.random((784, B), dtype=np.float32)
+    node = pkg.NeuralODE(_chain(pkg, layers, True, None), regularize="biased", abstol=1e-4, reltol=1e-4,
+                         maxiters=10_000, precision="tf32x3")
+    sol, st2 = node(x, ps, node.initialstates(np.random.default_rng(1)))
+    assert len(sol.u) == sol.stats.naccept + 1 and sol.stats.naccept < 200        # u0 and every accepted step
+    assert np.array_equal(np.asarray(sol.u[0]), x) and float(sol.t[-1]) == 1.0
+    assert any(abs(float(t) - sol.stats.t1_used) < 1e-7 for t in sol.t[:-1])      # t1 is one of the step times
+    d_x, d_ps = node.backward(sol, [None] * (len(sol.u) - 1) + [np.ones_like(x) / B], 1.0)
+    assert np.isfinite(np.asarray(d_ps)).all() and float(np.abs(np.asarray(d_ps)).max()) > 0
+    sol.free()
+
+
+def test_default_stream_work_is_ordered_before_the_library(pkg):
+    """buffers prepared on torch's default stream right before the call.  The ctx of a NULL stream
+    handle runs on a blocking stream (ordered with stream 0), so a pending host-to-device copy behind a long kernel
+    queue must be complete when the library reads x."""
+    import torch
+    dev = torch.device("cuda", 0)
+    layers = [(784, 100, "tanh"), (100, 784, "identity")]
+    om = _omodel(layers, True, None)
+    rng = np.random.default_rng(0)
+    ps = torch.from_numpy((orc.glorot_uniform_params(om, rng) * 3).astype(np.float32)).to(dev)
+    B = 2048
+    xh = torch.from_numpy(rng.random((B, 784), dtype=np.float32)).pin_memory()
+    ctx = pkg.Context(0, torch.cuda.current_stream(dev).cuda_stream)     # handle 0 -> NULL -> the library's own stream
+    node = pkg.NeuralODE(_chain(pkg, layers, True, None), regularize="none", abstol=1e-3, reltol=1e-3, precision="tf32x3",
+                         ctx=ctx)
+    st = node.initialstates(np.random.default_rng(1))
+    xd = xh.to(dev)
+    torch.cuda.synchronize()
+    ref, _ = node(xd.t(), ps, st)
+    want = ref.u[-1].clone()
+    big = torch.randn((8192, 8192), device=dev)
+    xd2 = torch.zeros_like(xd)
+    torch.cuda.synchronize()
+    for _ in range(8):
+        big = big @ big * 1e-4            # ~100 ms of queued work on stream 0
+    xd2.copy_(xh, non_blocking=True)      # queued behind it
+    sol, _ = node(xd2.t(), ps, st)        # must not read xd2 before the copy has landed
+    torch.cuda.synchronize()
+    assert torch.equal(sol.u[-1], want)
+
+
+def test_head_ce_rejects_labels_outside_the_class_range(pkg):
+    import ctypes as C
+    import torch
+    dev = torch.device("cuda", 0)
+    ctx = pkg.default_context(0)
+    B, Dd, Cn = 16, 8, 10
+    Wc = torch.randn(Cn * Dd + Cn, device=dev)
+    u = torch.randn((B, Dd), device=dev)
+    y = torch.arange(1, B + 1, device=dev, dtype=torch.int32)      # 1-based labels as Julia's onecold gives: 10 is out of range
+    loss = C.c_float()
+    rc = pkg.lib().lrnde_head_ce(ctx._h, Wc.data_ptr(), u.data_ptr(), y.data_ptr(), B, Dd, Cn, 0, C.byref(loss), None, None)
+    assert rc == -1 and b"0-based" in pkg.lib().lrnde_last_error()
+
+
+def test_classifier_grad_is_the_layer_by_layer_iteration(pkg):
+    """lrnde_classifier_grad (host buffers: x, labels, ps, Wc in; loss, d_ps, d_Wc out) against the same iteration
+    assembled from lrnde_ode_forward + lrnde_head_ce + lrnde_ode_backward on device buffers."""
+    import ctypes as C
+    import torch
+    dev = torch.device("cuda", 0)
+    ctx = pkg.default_context(0)
+    Dd, Hh, Cn, B = 784, 100, 10, 256
+    layers = [(Dd, Hh, "tanh"), (Hh, Dd, "identity")]
+    om = _omodel(layers, True, None)
+    rng = np.random.default_rng(2)
+    ps = (orc.glorot_uniform_params(om, rng) * 3).astype(np.float32)
+    Wc = np.concatenate([rng.uniform(-0.1, 0.1, Cn * Dd), np.zeros(Cn)]).astype(np.float32)
+    x = rng.random((B, Dd), dtype=np.float32)
+    y = rng.integers(0, Cn, B).astype(np.int32)
+    chain = _chain(pkg, layers, True, None)
+    node = pkg.NeuralODE(chain, regularize="unbiased", save_start=False, abstol=1e-3, reltol=1e-3, precision="tf32x3",
+                         return_last_only=True, ctx=ctx)
+    st = node.initialstates(np.random.default_rng(4))
+    # layer by layer on the device
+    pst, Wct, xt, yt = (torch.from_numpy(a).to(dev) for a in (ps, Wc, x, y))
+    sol, st2 = node(xt.t(), pst, st)
+    loss = C.c_float()
+    d_u = torch.empty((B, Dd), device=dev)
+    d_Wc = torch.empty_like(Wct)
+    pkg._lib.check(pkg.lib().lrnde_head_ce(ctx._h, Wct.data_ptr(), sol.u[-1].t().data_ptr(), yt.data_ptr(), B, Dd, Cn, 0,
+                                           C.byref(loss), d_u.data_ptr(), d_Wc.data_ptr()))
+    d_x, d_ps = node.backward(sol, [d_u.t()], 2.5)
+    # fused, host buffers
+    import copy
+    o, _ = node._opts("unbiased", 0.0, 0.0, True, True)
+    o.t1 = float(np.float32(copy.deepcopy(st["rng"]).random(dtype=np.float32)))
+    stats = pkg._lib.Stats()
+    loss2 = C.c_float()
+    g_ps, g_wc = np.empty_like(ps), np.empty_like(Wc)
+    pkg._lib.check(pkg.lib().lrnde_classifier_grad(ctx._h, ctx.model_handle(chain), C.byref(o), ps.ctypes.data, Wc.ctypes.data,
+                                                   x.ctypes.data, y.ctypes.data, B, Cn, 2.5, 1.0, C.byref(loss2),
+                                                   g_ps.ctypes.data, g_wc.ctypes.data, C.byref(stats)))
+    assert stats.nfe == st2["nfe"] and abs(loss2.value - loss.value) <= 1e-6 * abs(loss.value)
+    assert abs(stats.reg_val - float(st2["reg_val"])) <= 1e-6 * abs(float(st2["reg_val"]))
+    assert rel(g_ps, d_ps.cpu().numpy()) < 1e-6 and rel(g_wc, d_Wc.cpu().numpy()) < 1e-6
+    sol.free()
