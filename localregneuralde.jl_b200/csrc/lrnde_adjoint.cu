@@ -27,6 +27,18 @@ enum {
   LA_NARR = 32
 };
 
+#ifdef LRNDE_UMMA_TRACE
+__device__ long long g_adj_trace[1024];
+// CTA 1 only; rows of 16 stamps (row = event kind, column = stage)
+#define ATRACE(row, it) do { if ((int)blockIdx.x == 1 && (it) < 16) g_adj_trace[(row) * 16 + (it)] = clock64(); } while (0)
+extern "C" int lrnde_debug_trace_adj(long long* out, int n) {
+  cudaMemcpyFromSymbol(out, g_adj_trace, sizeof(long long) * (size_t)n);
+  return 0;
+}
+#else
+#define ATRACE(row, it) do { } while (0)
+#endif
+
 namespace ladj {
 using namespace umma;
 using namespace fused;
@@ -154,6 +166,8 @@ __global__ void __launch_bounds__(kThreads, 1) adj_chain_kernel(AChainP p) {
   const uint32_t tmem_base = tmem_slot;
   const uint32_t c_acc = tmem_base + (uint32_t)(32 * p.KS);
   auto arr = [&](int idx) -> float* { return p.ws + (size_t)idx * p.zlen; };
+  const bool tr = (threadIdx.x == 64) && !p.single;
+  if (tr) ATRACE(0, 0);
 
   if (warp == 0) {
     // ---------------- forward hidden tape in: per stage the 7 H(k_i) tiles then the C_n tile of the interval that
@@ -215,8 +229,10 @@ __global__ void __launch_bounds__(kThreads, 1) adj_chain_kernel(AChainP p) {
         mbar_wait(&bfull[cg], ph);
         tc_fence_after();
         if (elect_one_sync()) {
+          if (cg == 0 && !p.single) ATRACE(7, st);
           issue_group(c_acc + (uint32_t)(cg * 32), mz_hi, mz_lo, smem_u32(tC[cg]), p.nfull, p.ntail, p.passes, idesc);
           mma_commit(&pdone[cg]);
+          if (cg == 0 && !p.single) ATRACE(8, st);
         }
         __syncwarp();
       }
@@ -276,6 +292,7 @@ __global__ void __launch_bounds__(kThreads, 1) adj_chain_kernel(AChainP p) {
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(&a_ready);
+    if (tr) ATRACE(0, 1);
 
     // operand-image position of (tile row, k = hrow)
     const bool in_full = hrow < p.nfull * 32;
@@ -307,17 +324,11 @@ __global__ void __launch_bounds__(kThreads, 1) adj_chain_kernel(AChainP p) {
     const float dt = sd[0].scale;
     const float* alpha_n = p.single ? p.alpha_in : arr(LA_ALPHA + slot);
     const size_t e0 = (size_t)nb * LR_ZROW + hrow;     // element of (first sample, this row) in a [B][LR_ZROW] array
-    float dlast[16], hlast[16];                        // delta / [h;tau;1] of the last stage (stage 7)
-
-    for (int jj = 0; jj < nst; ++jj) {
+    // c_j = C_n + dt_n sum_i b_i(theta) H(k_i): dense interpolant of the forward solution in hidden space, from the
+    // tape ring (the 7 H(k_i) tiles, then the C_n tile).  Does not depend on lambda: stage jj + 1's runs while the
+    // tensor core works on stage jj.
+    auto compute_c = [&](int jj, float (&c)[16]) {
       const LinComb& yd = p.single ? sy[0] : sy[jj + 1];
-      const float tau = yd.t;
-      const bool last = (!p.single && jj == 5);
-      float* dst_del = p.single ? arr(LA_S1 + 3 * slot + 0) : (last ? arr(LA_S1 + 3 * next + 0) : arr(LA_DEL + jj));
-      float* dst_hh = p.single ? arr(LA_S1 + 3 * slot + 1) : (last ? arr(LA_S1 + 3 * next + 1) : arr(LA_HH + jj));
-      float* dst_cc = p.single ? arr(LA_S1 + 3 * slot + 2) : (last ? arr(LA_S1 + 3 * next + 2) : arr(LA_CC + jj));
-      // ---- c_j = C_n + dt_n sum_i b_i(theta) H(k_i): dense interpolant of the forward solution in hidden space
-      float c[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) c[i] = 0.0f;
       for (int s = 0; s < 8; ++s) {
@@ -341,47 +352,79 @@ __global__ void __launch_bounds__(kThreads, 1) adj_chain_kernel(AChainP p) {
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty[b]);
       }
+    };
+    float c[16], ep[16], dprev[16];
+    compute_c(0, c);
+    if (tr) ATRACE(0, 2);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { ep[i] = 0.0f; dprev[i] = 0.0f; }
+    if (!p.single && rowv) {   // delta_1 (FSAL) of the current state
+      const float* d1 = arr(LA_S1 + 3 * slot + 0);
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        if (nb + i < p.B) dprev[i] = __ldcg(d1 + e0 + (size_t)i * LR_ZROW);
+    }
+
+    for (int jj = 0; jj < nst; ++jj) {
+      const LinComb& yd = p.single ? sy[0] : sy[jj + 1];
+      const float tau = yd.t;
+      const bool last = (!p.single && jj == 5);
+      if (tr) ATRACE(1, jj);
+      float* dst_del = p.single ? arr(LA_S1 + 3 * slot + 0) : (last ? arr(LA_S1 + 3 * next + 0) : arr(LA_DEL + jj));
+      float* dst_hh = p.single ? arr(LA_S1 + 3 * slot + 1) : (last ? arr(LA_S1 + 3 * next + 1) : arr(LA_HH + jj));
+      float* dst_cc = p.single ? arr(LA_S1 + 3 * slot + 2) : (last ? arr(LA_S1 + 3 * next + 2) : arr(LA_CC + jj));
+      // ---- operand tiles of this stage: c_j (rows Kaug, Kaug + 1 of the stored copy = tau_j, 1) and
+      //      eps_j = sum_{i<j} a_ji delta_i = (partial sum prefetched during the previous stage) + a_{j,j-1} delta_{j-1}
       {
         const float cextra = (hrow == p.Kaug) ? tau : ((hrow == p.Kaug + 1) ? 1.0f : 0.0f);
 #pragma unroll
         for (int i = 0; i < 16; ++i)
           if (nb + i < p.B) dst_cc[e0 + (size_t)i * LR_ZROW] = rowc ? c[i] : cextra;
       }
+      if (tr) ATRACE(9, jj);
       if (in_img) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) tile_put(tC[cg], i, c[i]);
       }
-      // ---- eps_j = sum_{i<j} a_ji delta_i
-      float e[16];
+      if (tr) ATRACE(10, jj);
       if (!p.single) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) e[i] = 0.0f;
-        if (rowv) {
-          const LinComb& d = sd[jj];
-          for (int s = 0; s <= jj; ++s) {
-            const float* src = (s == 0) ? arr(LA_S1 + 3 * slot + 0) : arr(LA_DEL + s - 1);
-            const float cf = d.coef[s];
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-              if (nb + i < p.B) e[i] = fmaf(cf, __ldcg(src + e0 + (size_t)i * LR_ZROW), e[i]);
-          }
-        }
+        const float cl = sd[jj].coef[jj];
         float* dst_eps = arr(LA_EPS + jj);
 #pragma unroll
-        for (int i = 0; i < 16; ++i)
-          if (nb + i < p.B) dst_eps[e0 + (size_t)i * LR_ZROW] = e[i];
-        if (in_img) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) tile_put(tE[cg], i, e[i]);
+        for (int i = 0; i < 16; ++i) {
+          const float e = fmaf(cl, dprev[i], ep[i]);
+          if (nb + i < p.B) dst_eps[e0 + (size_t)i * LR_ZROW] = e;
+          if (in_img) tile_put(tE[cg], i, e);
         }
       }
+      if (tr) ATRACE(11, jj);
       tc_fence_before();
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bfull[cg]);
-      // ---- p_j = Zx + Mz c_j + w1t tau_j + b1
-      float v[16], hh[16], ss[16];
+      if (tr) ATRACE(2, jj);
+      // ---- while the tensor core forms p_j = Mz c_j: next stage's interpolant and the known part of its eps
+      if (jj + 1 < nst) {
+        compute_c(jj + 1, c);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) ep[i] = sd[jj + 1].coef[jj] * dprev[i];
+        if (rowv) {
+          for (int s = 0; s < jj; ++s) {
+            const float* src = (s == 0) ? arr(LA_S1 + 3 * slot + 0) : arr(LA_DEL + s - 1);
+            const float cf = sd[jj + 1].coef[s];
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (nb + i < p.B) ep[i] = fmaf(cf, __ldcg(src + e0 + (size_t)i * LR_ZROW), ep[i]);
+          }
+        }
+      }
+      if (tr) ATRACE(3, jj);
+      float v[16], ss[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) ss[i] = (rowv && nb + i < p.B) ? __ldcg(p.Zx + e0 + (size_t)i * LR_ZROW) : 0.0f;   // Zx
+      // ---- p_j = Zx + Mz c_j + w1t tau_j + b1 ; h_j, s_j
       mbar_wait(&pdone[cg], (uint32_t)(jj & 1));
+      if (tr) ATRACE(4, jj);
       tc_fence_after();
       tmem_ld16(c_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(cg * 32 + rbase), v);
       tc_fence_before();
@@ -390,18 +433,22 @@ __global__ void __launch_bounds__(kThreads, 1) adj_chain_kernel(AChainP p) {
       const float hconst = (p.td && hrow == p.H) ? tau : ((hrow == p.H + p.td) ? 1.0f : 0.0f);
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-        const float zx = (rowv && nb + i < p.B) ? __ldcg(p.Zx + e0 + (size_t)i * LR_ZROW) : 0.0f;
-        float x = v[i] + zx;
+        float x = v[i] + ss[i];
         x = p.td ? fmaf(w1t, tau, x) : x;
         x += b1;
-        float h, s;
-        act_pair<ACT>(x, h, s);
-        hh[i] = rowv ? h : hconst;
-        ss[i] = rowv ? s : 0.0f;
+        float h, sg;
+        act_pair<ACT>(x, h, sg);
+        ss[i] = rowv ? sg : 0.0f;
+        if (nb + i < p.B) dst_hh[e0 + (size_t)i * LR_ZROW] = rowv ? h : hconst;
       }
       // ---- alpha_j = alpha_n - dt Mh^T eps_j ; delta_j = s_j .* alpha_j
+      float an[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) an[i] = (rowv && nb + i < p.B) ? __ldcg(alpha_n + e0 + (size_t)i * LR_ZROW) : 0.0f;
+      if (tr) ATRACE(5, jj);
       if (!p.single) {
         mbar_wait(&xdone[cg], (uint32_t)(jj & 1));
+        if (tr) ATRACE(6, jj);
         tc_fence_after();
         tmem_ld16(c_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(cg * 32 + rbase), v);
         tc_fence_before();
@@ -409,32 +456,42 @@ __global__ void __launch_bounds__(kThreads, 1) adj_chain_kernel(AChainP p) {
       float* dst_alpha = p.single ? arr(LA_ALPHA + slot) : arr(LA_ALPHA + next);
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-        const bool ok = nb + i < p.B;
-        const float an = (rowv && ok) ? __ldcg(alpha_n + e0 + (size_t)i * LR_ZROW) : 0.0f;
-        const float aj = p.single ? an : fmaf(-dt, v[i], an);
+        const float aj = p.single ? an[i] : fmaf(-dt, v[i], an[i]);
         const float del = ss[i] * aj;
-        if (ok) {
+        if (nb + i < p.B) {
           dst_del[e0 + (size_t)i * LR_ZROW] = del;
-          dst_hh[e0 + (size_t)i * LR_ZROW] = hh[i];
           if (p.single || last) dst_alpha[e0 + (size_t)i * LR_ZROW] = rowv ? aj : 0.0f;
         }
-        dlast[i] = del;
-        hlast[i] = hh[i];
+        dprev[i] = del;
       }
     }
+    if (tr) ATRACE(0, 3);
     if (!p.single) {
-      // ---- Delta_bt = sum_j btilde_j delta_j ; sum_j b_j H_j ; sum_j btilde_j H_j   (stages 1..6 re-read, stage 7 in registers)
+      // ---- Delta_bt = sum_j btilde_j delta_j ; sum_j b_j H_j ; sum_j btilde_j H_j  (stage 7 in registers / own stores)
       const LinComb& d7 = sd[5];   // coef = a_7i = b_i
       float acc[16], acc2[16];
+      // three source arrays per round trip (the loop-carried registers of the stages are free here)
+      auto gather3 = [&](int s0, int ns, int which, float (&t)[3][16]) {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) acc[i] = s_bt[6] * dlast[i];
-      if (rowv) {
-        for (int s = 0; s < 6; ++s) {
-          const float* src = (s == 0) ? arr(LA_S1 + 3 * slot + 0) : arr(LA_DEL + s - 1);
-          const float cf = s_bt[s];
+        for (int k = 0; k < 3; ++k) {
+          const int s = s0 + k;
+          const float* src = (s == 0) ? arr(LA_S1 + 3 * slot + which)
+                                      : (s == 6 ? arr(LA_S1 + 3 * next + which) : arr((which ? LA_HH : LA_DEL) + s - 1));
 #pragma unroll
           for (int i = 0; i < 16; ++i)
-            if (nb + i < p.B) acc[i] = fmaf(cf, __ldcg(src + e0 + (size_t)i * LR_ZROW), acc[i]);
+            t[k][i] = (k < ns && nb + i < p.B) ? __ldcg(src + e0 + (size_t)i * LR_ZROW) : 0.0f;
+        }
+      };
+#pragma unroll
+      for (int i = 0; i < 16; ++i) acc[i] = s_bt[6] * dprev[i];
+      if (rowv) {
+        float t[3][16];
+        for (int s0 = 0; s0 < 6; s0 += 3) {
+          gather3(s0, 3, 0, t);
+#pragma unroll
+          for (int k = 0; k < 3; ++k)
+#pragma unroll
+            for (int i = 0; i < 16; ++i) acc[i] = fmaf(s_bt[s0 + k], t[k][i], acc[i]);
         }
       }
       {
@@ -451,20 +508,22 @@ __global__ void __launch_bounds__(kThreads, 1) adj_chain_kernel(AChainP p) {
       __syncwarp();
       if (lane == 0) mbar_arrive(&out_full);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) { acc[i] = 0.0f; acc2[i] = s_bt[6] * hlast[i]; }
+      for (int i = 0; i < 16; ++i) { acc[i] = 0.0f; acc2[i] = 0.0f; }
       if (rowc) {
-        for (int s = 0; s < 6; ++s) {
-          const float* src = (s == 0) ? arr(LA_S1 + 3 * slot + 1) : arr(LA_HH + s - 1);
-          const float cb = d7.coef[s], ct = s_bt[s];
+        float t[3][16];
+        for (int s0 = 0; s0 < 7; s0 += 3) {
+          const int ns = min(3, 7 - s0);
+          gather3(s0, ns, 1, t);
 #pragma unroll
-          for (int i = 0; i < 16; ++i)
-            if (nb + i < p.B) {
-              const float hv = __ldcg(src + e0 + (size_t)i * LR_ZROW);
-              acc[i] = fmaf(cb, hv, acc[i]);
-              acc2[i] = fmaf(ct, hv, acc2[i]);
-            }
+          for (int k = 0; k < 3; ++k) {
+            const int s = s0 + k;
+            const float cb = (k < ns && s < 6) ? d7.coef[s] : 0.0f, ct = (k < ns) ? s_bt[s] : 0.0f;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { acc[i] = fmaf(cb, t[k][i], acc[i]); acc2[i] = fmaf(ct, t[k][i], acc2[i]); }
+          }
         }
       }
+      if (tr) ATRACE(0, 4);
       float* hbb = arr(LA_HBB);
       float* hbt = arr(LA_HBT);
 #pragma unroll
@@ -477,6 +536,7 @@ __global__ void __launch_bounds__(kThreads, 1) adj_chain_kernel(AChainP p) {
     tc_fence_before();
   }
   __syncthreads();
+  if (threadIdx.x == 0 && !p.single) ATRACE(0, 5);
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");

@@ -227,6 +227,19 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(ChainP p) {
       obase = (uint32_t)(p.nfull * (2 * kNT * 128) + t * (2 * kNT * 32) + (kk & 3) * 4) | (uint32_t)(((kk >> 2) & 1) << 30);
       ostep_lo = (uint32_t)(kNT * 32);
     }
+    // cumulative hidden image of the state: u_{n+1} = x + W2a C_{n+1},  C_{n+1} = C_n + dt sum_i a_7i H(k_i)
+    // (hidden tape of the latent-space adjoint); H(k_1) comes from the tape, H(k_2..6) from the stages below
+    const bool write_c = !p.single && s_htape && hrow < p.H + p.td + 1;
+    float csum[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) csum[i] = 0.0f;
+    if (write_c) {
+      const float* h1 = hof(sd[5].src[0]);
+      const float cf = sd[5].coef[0];
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        if (n0 + col + i < p.B) csum[i] = cf * __ldcg(h1 + (size_t)(n0 + col + i) * LR_ZROW + hrow);
+    }
     for (int st = 0; st < nst; ++st) {
       const int b = st % p.nbuf;
       const LinComb& d = sd[st];
@@ -266,6 +279,23 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(ChainP p) {
         x += b1;
         const float h = lr_act(ACT, x);
         v[i] = rowv ? h : hconst;
+      }
+      if (write_c) {
+        if (!last_full) {
+          const float cf = sd[5].coef[st + 1];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) csum[i] = fmaf(cf, v[i], csum[i]);
+        } else {
+          const float* c0 = hof(sd[5].base);
+          float* c1 = hof(sd[5].dst);
+          const float sc = sd[5].scale;
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (n0 + col + i < p.B) {
+              const size_t e = (size_t)(n0 + col + i) * LR_ZROW + hrow;
+              c1[e] = fmaf(sc, csum[i], __ldcg(c0 + e));
+            }
+        }
       }
       const float* kdst = p.single ? sd[1].dst : (last_full ? sd[6].dst : d.dst);
       if (s_htape && hrow < p.H + p.td + 1) {
@@ -307,30 +337,6 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(ChainP p) {
             if (n0 + col + i < p.B) zo[(size_t)(n0 + col + i) * LR_ZROW + hrow] = v[i];
         }
       }
-    }
-    if (!p.single && s_htape && hrow < p.H + p.td + 1) {
-      // cumulative hidden image of the state: u_{n+1} = x + W2a C_{n+1},  C_{n+1} = C_n + dt sum_i a_7i H(k_i)
-      // (H(k_2..6) were stored above by this very thread, H(k_1) by an earlier launch)
-      const LinComb& d = sd[5];
-      float cs[16];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) cs[i] = 0.0f;
-      for (int s = 0; s < d.n; ++s) {
-        const float* hs = hof(d.src[s]);
-        const float cf = d.coef[s];
-#pragma unroll
-        for (int i = 0; i < 16; ++i)
-          if (n0 + col + i < p.B) cs[i] = fmaf(cf, __ldcg(hs + (size_t)(n0 + col + i) * LR_ZROW + hrow), cs[i]);
-      }
-      const float* c0 = hof(d.base);
-      float* c1 = hof(d.dst);
-      const float scale = d.scale;
-#pragma unroll
-      for (int i = 0; i < 16; ++i)
-        if (n0 + col + i < p.B) {
-          const size_t e = (size_t)(n0 + col + i) * LR_ZROW + hrow;
-          c1[e] = fmaf(scale, cs[i], __ldcg(c0 + e));
-        }
     }
     tc_fence_before();
     if (tr) FTRACE(0, 1, 0, 3);

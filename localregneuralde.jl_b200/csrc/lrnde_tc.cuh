@@ -158,10 +158,11 @@ __device__ __forceinline__ void mma_commit_mc(uint64_t* bar, uint16_t mask) {
       ::"r"(smem_u32(bar)), "h"(mask)
       : "memory");
 }
+// round to nearest tf32, ties away from zero -- the result of cvt.rna.tf32.f32 for every finite value, as two
+// full-rate integer instructions: the cvt form issues at a few results per clock per SM and was the largest single
+// cost of every kernel that splits operands into hi / lo parts on the fly (in-kernel clock64 timeline, profiles/r2)
 __device__ __forceinline__ float tf32_rna(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
 // ---- MN-major operands (both GEMM operands stored feature-contiguous per sample, K = samples): for tf32 the
 // only MN-major shared-memory layout is SWIZZLE_128B_BASE32B (cute Layout_MN_SW128_32B_Atom): atoms of 4 samples x

@@ -44,7 +44,7 @@ ctx_dp.setup_group(rank, world, Bt, gather)
 ctx_1 = pkg.Context(local, torch.cuda.current_stream(dev).cuda_stream)
 lo, hi = rank * Bt // world, (rank + 1) * Bt // world
 ok = True
-for prec, tol in (("fp32", 1e-6), ("tf32x3", 1e-3)):       # tf32x3 at a truncation-dominated tolerance (latent-space engines)
+for prec, tol in (("fp32", 1e-6), ("tf32x3", 1e-5)):       # tf32x3: the latent-space engines (forward, lean tape, adjoint)
     kw = dict(regularize="unbiased", abstol=tol, reltol=tol, maxiters=10000, save_start=False, precision=prec)
     res = {}
     for name, ctx, xs, cs in (("single", ctx_1, x, c), ("dp", ctx_dp, x[:, lo:hi], c[:, lo:hi])):
@@ -71,7 +71,7 @@ for prec, tol in (("fp32", 1e-6), ("tf32x3", 1e-3)):       # tf32x3 at a truncat
     e_u, e_dx = rel(d["u"], s["u"][:, lo:hi]), rel(d["d_x"], s["d_x"][:, lo:hi])
     e_dps, e_ar = rel(g.cpu().numpy(), s["d_ps"]), rel(g.cpu().numpy(), g2.cpu().numpy())
     e_reg = abs(d["reg"] - s["reg"]) / abs(s["reg"])
-    bar = 1e-5 if prec == "fp32" else 2e-4
+    bar = 1e-5 if prec == "fp32" else 1e-4      # tolerance-level agreement: the dt sequence follows EEst, whose partial sums add up in a different order
     good = same_f and same_b and same_bits and e_u < bar and e_dx < 10 * bar and e_dps < 10 * bar and e_ar < 1e-6 and e_reg < 10 * bar
     ok = ok and good
     print(f"[multi-gpu rank {rank}/{world}] prec={prec} fwd attempts {len(s['acc'])}/{len(d['acc'])} same={same_f} "
