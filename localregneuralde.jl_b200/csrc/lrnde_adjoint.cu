@@ -43,19 +43,6 @@ namespace ladj {
 using namespace umma;
 using namespace fused;
 
-// Mz = W1[:, :D] * W2a as a plain zero-padded [128][128] matrix (double accumulation)
-__global__ void mz_plain_kernel(const float* __restrict__ W1, const float* __restrict__ W2a, int D, int H, int Kaug,
-                                float* __restrict__ out) {
-  const int r = threadIdx.x, k = blockIdx.x;
-  float v = 0.0f;
-  if (r < H && k < Kaug) {
-    double acc = 0.0;
-    for (int d = 0; d < D; ++d) acc += (double)W1[(size_t)d * H + r] * (double)W2a[(size_t)k * D + d];
-    v = (float)acc;
-  }
-  out[r * 128 + k] = v;
-}
-
 template <int ACT>
 __device__ __forceinline__ void act_pair(float x, float& h, float& s) {
   if (ACT == ACT_TANH) { h = tanhf(x); s = 1.0f - h * h; }
@@ -114,10 +101,10 @@ __device__ __forceinline__ void issue_group(uint32_t d, uint32_t a_hi, uint32_t 
   }
 }
 
-template <int ACT>
+template <int ACT, bool SINGLE>
 __global__ void __launch_bounds__(kThreads, 1) adj_chain_kernel(AChainP p) {
   SolveDev* S = p.S;
-  if (p.single ? S->failed : S->done) return;
+  if (SINGLE ? S->failed : S->done) return;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   __shared__ uint64_t a_ready, bfull[2], pdone[2], pread[2], xdone[2], out_full, tfull[kTapeBufs], tempty[kTapeBufs];
@@ -132,7 +119,7 @@ __global__ void __launch_bounds__(kThreads, 1) adj_chain_kernel(AChainP p) {
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * kNT;
-  const int nst = p.single ? 1 : 6;
+  const int nst = SINGLE ? 1 : 6;
   const uint32_t tileB = (uint32_t)(p.nfull * 8192 + p.ntail * 2048);   // [hi | lo] images of a 32-sample operand tile
   uint8_t* tC[2] = {smem, smem + tileB};
   uint8_t* tE[2] = {smem + 2 * (size_t)tileB, smem + 3 * (size_t)tileB};
@@ -166,7 +153,7 @@ __global__ void __launch_bounds__(kThreads, 1) adj_chain_kernel(AChainP p) {
   const uint32_t tmem_base = tmem_slot;
   const uint32_t c_acc = tmem_base + (uint32_t)(32 * p.KS);
   auto arr = [&](int idx) -> float* { return p.ws + (size_t)idx * p.zlen; };
-  const bool tr = (threadIdx.x == 64) && !p.single;
+  const bool tr = (threadIdx.x == 64) && !SINGLE;
   if (tr) ATRACE(0, 0);
 
   if (warp == 0) {
@@ -177,7 +164,7 @@ __global__ void __launch_bounds__(kThreads, 1) adj_chain_kernel(AChainP p) {
       const uint32_t bytes = (uint32_t)nvalid * LR_ZROW * 4u;
       int it = 0;
       for (int jj = 0; jj < nst; ++jj) {
-        const LinComb& yd = p.single ? sy[0] : sy[jj + 1];
+        const LinComb& yd = SINGLE ? sy[0] : sy[jj + 1];
         const size_t slotn = (size_t)(yd.base - s_ftape) / ((size_t)7 * s_flen);
         const float* hb = s_fh + slotn * 7 * s_fzlen;
         for (int s = 0; s < 8; ++s, ++it) {
@@ -193,7 +180,7 @@ __global__ void __launch_bounds__(kThreads, 1) adj_chain_kernel(AChainP p) {
       }
     }
     // ---------------- Delta_b / Delta_bt operand images out (units of 16 samples for the lambda GEMM)
-    if (!p.single) {
+    if (!SINGLE) {
       mbar_wait(&out_full, 0);
       if (elect_one_sync()) {
         for (int sg = 0; sg < 4; ++sg) {
@@ -229,14 +216,14 @@ __global__ void __launch_bounds__(kThreads, 1) adj_chain_kernel(AChainP p) {
         mbar_wait(&bfull[cg], ph);
         tc_fence_after();
         if (elect_one_sync()) {
-          if (cg == 0 && !p.single) ATRACE(7, st);
+          if (cg == 0 && !SINGLE) ATRACE(7, st);
           issue_group(c_acc + (uint32_t)(cg * 32), mz_hi, mz_lo, smem_u32(tC[cg]), p.nfull, p.ntail, p.passes, idesc);
           mma_commit(&pdone[cg]);
-          if (cg == 0 && !p.single) ATRACE(8, st);
+          if (cg == 0 && !SINGLE) ATRACE(8, st);
         }
         __syncwarp();
       }
-      if (!p.single) {
+      if (!SINGLE) {
         for (int cg = 0; cg < 2; ++cg) {
           mbar_wait(&pread[cg], ph);
           tc_fence_after();
@@ -294,249 +281,219 @@ __global__ void __launch_bounds__(kThreads, 1) adj_chain_kernel(AChainP p) {
     if (lane == 0) mbar_arrive(&a_ready);
     if (tr) ATRACE(0, 1);
 
-    // operand-image position of (tile row, k = hrow)
+    // operand-image position of (tile row r, k = hrow): byte offset = oA + r * oS + ((osw ^ m(r)) << 4) with
+    // m(r) = r & 7 (SWIZZLE_128B chunks of 32 k) or (r >> 2) & 1 (SWIZZLE_32B K-steps of the tail); lo image at + oLo
     const bool in_full = hrow < p.nfull * 32;
     const bool in_img = hrow < p.KS * 8;
-    uint32_t obase, ostep_lo, tail_hb = 0u;
+    uint32_t oA, oS, oLo, osw;
     if (in_full) {
-      obase = (uint32_t)(q * 8192 + (lane & 3) * 4);
-      ostep_lo = 4096u;
+      oS = 128u; oLo = 4096u; osw = (uint32_t)(lane >> 2);
+      oA = (uint32_t)(q * 8192 + (lane & 3) * 4) + (uint32_t)rbase * oS;
     } else {
       const int kt = hrow - p.nfull * 32, t = kt >> 3, kk = kt & 7;
-      obase = (uint32_t)(p.nfull * 8192 + t * 2048 + (kk & 3) * 4);
-      tail_hb = (uint32_t)((kk >> 2) & 1);
-      ostep_lo = 1024u;
+      oS = 32u; oLo = 1024u; osw = (uint32_t)((kk >> 2) & 1);
+      oA = (uint32_t)(p.nfull * 8192 + t * 2048 + (kk & 3) * 4) + (uint32_t)rbase * oS;
     }
-    auto tile_put = [&](uint8_t* tile, int i, float val) {
-      const int row = rbase + i;
-      float hi, lo;
-      if (p.passes == 3) { hi = tf32_rna(val); lo = tf32_rna(val - hi); }
-      else { hi = val; lo = 0.0f; }
-      uint32_t o;
-      if (in_full) o = obase + (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + (((lane >> 2) ^ (row & 7)) << 4));
-      else o = obase + (uint32_t)(row * 32 + ((tail_hb ^ (uint32_t)((row >> 2) & 1)) << 4));
-      *reinterpret_cast<float*>(tile + o) = hi;
-      *reinterpret_cast<float*>(tile + o + ostep_lo) = lo;
+    // tf32 split without branches: passes == 1 keeps the value (no rounding, lo = 0)
+    const uint32_t rnd = (p.passes == 3) ? 0x1000u : 0u, msk = (p.passes == 3) ? 0xFFFFE000u : 0xFFFFFFFFu;
+    auto tile_put16 = [&](uint8_t* tile, const float (&val)[16]) {
+      if (!in_img) return;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const uint32_t m = in_full ? (uint32_t)(i & 7) : (uint32_t)((i >> 2) & 1);
+        const uint32_t o = oA + (uint32_t)i * oS + ((osw ^ m) << 4);
+        const float hi = __uint_as_float((__float_as_uint(val[i]) + rnd) & msk);
+        const float lo = __uint_as_float((__float_as_uint(val[i] - hi) + rnd) & msk);
+        *reinterpret_cast<float*>(tile + o) = hi;
+        *reinterpret_cast<float*>(tile + o + oLo) = lo;
+      }
     };
     const float w1t = (p.td && rowv && p.w1t) ? p.w1t[hrow] : 0.0f;
     const float b1 = rowv ? p.b1[hrow] : 0.0f;
     const int slot = s_slot, next = s_next;
     const float dt = sd[0].scale;
-    const float* alpha_n = p.single ? p.alpha_in : arr(LA_ALPHA + slot);
-    const size_t e0 = (size_t)nb * LR_ZROW + hrow;     // element of (first sample, this row) in a [B][LR_ZROW] array
-    // c_j = C_n + dt_n sum_i b_i(theta) H(k_i): dense interpolant of the forward solution in hidden space, from the
-    // tape ring (the 7 H(k_i) tiles, then the C_n tile).  Does not depend on lambda: stage jj + 1's runs while the
-    // tensor core works on stage jj.
-    auto compute_c = [&](int jj, float (&c)[16]) {
-      const LinComb& yd = p.single ? sy[0] : sy[jj + 1];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) c[i] = 0.0f;
-      for (int s = 0; s < 8; ++s) {
-        const int it = jj * 8 + s;
-        const int b = it % kTapeBufs;
-        mbar_wait(&tfull[b], (uint32_t)((it / kTapeBufs) & 1));
-        if (rowc) {
-          const float* tb = reinterpret_cast<const float*>(tbuf + (size_t)b * kTapeBufBytes) + (cg * 32 + rbase) * LR_ZROW + hrow;
-          if (s < 7) {
-            const float cf = yd.coef[s];
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-              if (nb + i < p.B) c[i] = fmaf(cf, tb[i * LR_ZROW], c[i]);
-          } else {
-            const float sc = yd.scale;
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-              if (nb + i < p.B) c[i] = fmaf(sc, c[i], tb[i * LR_ZROW]);
-          }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty[b]);
-      }
-    };
-    float c[16], ep[16], dprev[16];
-    compute_c(0, c);
-    if (tr) ATRACE(0, 2);
-#pragma unroll
-    for (int i = 0; i < 16; ++i) { ep[i] = 0.0f; dprev[i] = 0.0f; }
-    if (!p.single && rowv) {   // delta_1 (FSAL) of the current state
-      const float* d1 = arr(LA_S1 + 3 * slot + 0);
-#pragma unroll
-      for (int i = 0; i < 16; ++i)
-        if (nb + i < p.B) dprev[i] = __ldcg(d1 + e0 + (size_t)i * LR_ZROW);
-    }
+    const float* alpha_n = SINGLE ? p.alpha_in : arr(LA_ALPHA + slot);
+    // element of (first sample, this row) in a [Bpad][LR_ZROW] array.  The work arrays are padded to whole 64-sample
+    // tiles, so samples beyond B are computed and stored like the others (never read back): no bounds tests below
+    const size_t e0 = (size_t)nb * LR_ZROW + hrow;
+    uint8_t* const tCc = tC[cg];
+    uint8_t* const tEc = tE[cg];
+    const float* tape_row = reinterpret_cast<const float*>(tbuf) + (cg * 32 + rbase) * LR_ZROW + hrow;
 
-    for (int jj = 0; jj < nst; ++jj) {
-      const LinComb& yd = p.single ? sy[0] : sy[jj + 1];
+    float c[16], ep[16], dprev[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { c[i] = 0.0f; ep[i] = 0.0f; dprev[i] = 0.0f; }
+    if (!SINGLE && rowv) {   // delta_1 (FSAL) of the current state
+      const float* d1 = arr(LA_S1 + 3 * slot + 0) + e0;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) dprev[i] = __ldcg(d1 + (size_t)i * LR_ZROW);
+    }
+    float v[16], ss[16];
+    // software pipeline: iteration jj runs the front of stage jj (operand tiles), then the lambda-independent part of
+    // stage jj + 1 (interpolant c from the tape ring, known part of eps) while the tensor core works, then the back of
+    // stage jj (p, activation, alpha, delta).  jj = -1 only prefetches.
+    for (int jj = -1; jj < nst; ++jj) {
+      const LinComb& yd = SINGLE ? sy[0] : sy[jj < 0 ? 1 : jj + 1];
       const float tau = yd.t;
-      const bool last = (!p.single && jj == 5);
-      if (tr) ATRACE(1, jj);
-      float* dst_del = p.single ? arr(LA_S1 + 3 * slot + 0) : (last ? arr(LA_S1 + 3 * next + 0) : arr(LA_DEL + jj));
-      float* dst_hh = p.single ? arr(LA_S1 + 3 * slot + 1) : (last ? arr(LA_S1 + 3 * next + 1) : arr(LA_HH + jj));
-      float* dst_cc = p.single ? arr(LA_S1 + 3 * slot + 2) : (last ? arr(LA_S1 + 3 * next + 2) : arr(LA_CC + jj));
-      // ---- operand tiles of this stage: c_j (rows Kaug, Kaug + 1 of the stored copy = tau_j, 1) and
-      //      eps_j = sum_{i<j} a_ji delta_i = (partial sum prefetched during the previous stage) + a_{j,j-1} delta_{j-1}
-      {
+      const bool last = (!SINGLE && jj == 5);
+      float* dst_del = SINGLE ? arr(LA_S1 + 3 * slot + 0) : (last ? arr(LA_S1 + 3 * next + 0) : arr(LA_DEL + max(jj, 0)));
+      float* dst_hh = SINGLE ? arr(LA_S1 + 3 * slot + 1) : (last ? arr(LA_S1 + 3 * next + 1) : arr(LA_HH + max(jj, 0)));
+      float* dst_cc = SINGLE ? arr(LA_S1 + 3 * slot + 2) : (last ? arr(LA_S1 + 3 * next + 2) : arr(LA_CC + max(jj, 0)));
+      if (jj >= 0) {
+        if (tr) ATRACE(1, jj);
+        // ---- operand tiles: c_j (rows Kaug, Kaug + 1 of the stored copy = tau_j, 1) and
+        //      eps_j = (partial sum prefetched during the previous stage) + a_{j,j-1} delta_{j-1}
         const float cextra = (hrow == p.Kaug) ? tau : ((hrow == p.Kaug + 1) ? 1.0f : 0.0f);
 #pragma unroll
-        for (int i = 0; i < 16; ++i)
-          if (nb + i < p.B) dst_cc[e0 + (size_t)i * LR_ZROW] = rowc ? c[i] : cextra;
-      }
-      if (tr) ATRACE(9, jj);
-      if (in_img) {
+        for (int i = 0; i < 16; ++i) dst_cc[e0 + (size_t)i * LR_ZROW] = rowc ? c[i] : cextra;
+        tile_put16(tCc, c);
+        if (!SINGLE) {
+          const float cl = sd[jj].coef[jj];
+          float* dst_eps = arr(LA_EPS + jj) + e0;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) tile_put(tC[cg], i, c[i]);
-      }
-      if (tr) ATRACE(10, jj);
-      if (!p.single) {
-        const float cl = sd[jj].coef[jj];
-        float* dst_eps = arr(LA_EPS + jj);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float e = fmaf(cl, dprev[i], ep[i]);
-          if (nb + i < p.B) dst_eps[e0 + (size_t)i * LR_ZROW] = e;
-          if (in_img) tile_put(tE[cg], i, e);
+          for (int i = 0; i < 16; ++i) { v[i] = fmaf(cl, dprev[i], ep[i]); dst_eps[(size_t)i * LR_ZROW] = v[i]; }
+          tile_put16(tEc, v);
         }
+        tc_fence_before();
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bfull[cg]);
+        if (tr) ATRACE(2, jj);
       }
-      if (tr) ATRACE(11, jj);
-      tc_fence_before();
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bfull[cg]);
-      if (tr) ATRACE(2, jj);
-      // ---- while the tensor core forms p_j = Mz c_j: next stage's interpolant and the known part of its eps
       if (jj + 1 < nst) {
-        compute_c(jj + 1, c);
+        // ---- c_{j+1} = C_n + dt_n sum_i b_i(theta) H(k_i): dense interpolant of the forward solution in hidden space,
+        //      from the tape ring (the 7 H(k_i) tiles, then the C_n tile)
+        const LinComb& yn = SINGLE ? sy[0] : sy[jj + 2];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) ep[i] = sd[jj + 1].coef[jj] * dprev[i];
-        if (rowv) {
-          for (int s = 0; s < jj; ++s) {
-            const float* src = (s == 0) ? arr(LA_S1 + 3 * slot + 0) : arr(LA_DEL + s - 1);
-            const float cf = sd[jj + 1].coef[s];
+        for (int i = 0; i < 16; ++i) c[i] = 0.0f;
+        for (int s = 0; s < 8; ++s) {
+          const int it = (jj + 1) * 8 + s;
+          const int b = it % kTapeBufs;
+          mbar_wait(&tfull[b], (uint32_t)((it / kTapeBufs) & 1));
+          if (rowc) {
+            const float* tb = tape_row + (size_t)b * (kTapeBufBytes / 4);
+            const float cf = (s < 7) ? yn.coef[s] : 1.0f, sc = (s < 7) ? 1.0f : yn.scale;
 #pragma unroll
-            for (int i = 0; i < 16; ++i)
-              if (nb + i < p.B) ep[i] = fmaf(cf, __ldcg(src + e0 + (size_t)i * LR_ZROW), ep[i]);
+            for (int i = 0; i < 16; ++i) c[i] = fmaf(cf, tb[i * LR_ZROW], sc * c[i]);
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[b]);
+        }
+        if (!SINGLE && jj >= 0) {   // known part of eps_{j+1}: delta_1 .. delta_j (the newest one is in registers)
+#pragma unroll
+          for (int i = 0; i < 16; ++i) ep[i] = sd[jj + 1].coef[jj] * dprev[i];
+          if (rowv) {
+            for (int s = 0; s < jj; ++s) {
+              const float* src = ((s == 0) ? arr(LA_S1 + 3 * slot + 0) : arr(LA_DEL + s - 1)) + e0;
+              const float cf = sd[jj + 1].coef[s];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) ep[i] = fmaf(cf, __ldcg(src + (size_t)i * LR_ZROW), ep[i]);
+            }
           }
         }
       }
-      if (tr) ATRACE(3, jj);
-      float v[16], ss[16];
+      if (jj >= 0) {
+        if (tr) ATRACE(3, jj);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) ss[i] = (rowv && nb + i < p.B) ? __ldcg(p.Zx + e0 + (size_t)i * LR_ZROW) : 0.0f;   // Zx
-      // ---- p_j = Zx + Mz c_j + w1t tau_j + b1 ; h_j, s_j
-      mbar_wait(&pdone[cg], (uint32_t)(jj & 1));
-      if (tr) ATRACE(4, jj);
-      tc_fence_after();
-      tmem_ld16(c_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(cg * 32 + rbase), v);
-      tc_fence_before();
-      __syncwarp();
-      if (!p.single && lane == 0) mbar_arrive(&pread[cg]);
-      const float hconst = (p.td && hrow == p.H) ? tau : ((hrow == p.H + p.td) ? 1.0f : 0.0f);
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        float x = v[i] + ss[i];
-        x = p.td ? fmaf(w1t, tau, x) : x;
-        x += b1;
-        float h, sg;
-        act_pair<ACT>(x, h, sg);
-        ss[i] = rowv ? sg : 0.0f;
-        if (nb + i < p.B) dst_hh[e0 + (size_t)i * LR_ZROW] = rowv ? h : hconst;
-      }
-      // ---- alpha_j = alpha_n - dt Mh^T eps_j ; delta_j = s_j .* alpha_j
-      float an[16];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) an[i] = (rowv && nb + i < p.B) ? __ldcg(alpha_n + e0 + (size_t)i * LR_ZROW) : 0.0f;
-      if (tr) ATRACE(5, jj);
-      if (!p.single) {
-        mbar_wait(&xdone[cg], (uint32_t)(jj & 1));
-        if (tr) ATRACE(6, jj);
+        for (int i = 0; i < 16; ++i) ss[i] = rowv ? __ldcg(p.Zx + e0 + (size_t)i * LR_ZROW) : 0.0f;   // Zx
+        // ---- p_j = Zx + Mz c_j + w1t tau_j + b1 ; h_j, s_j
+        mbar_wait(&pdone[cg], (uint32_t)(jj & 1));
+        if (tr) ATRACE(4, jj);
         tc_fence_after();
         tmem_ld16(c_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(cg * 32 + rbase), v);
         tc_fence_before();
-      }
-      float* dst_alpha = p.single ? arr(LA_ALPHA + slot) : arr(LA_ALPHA + next);
+        __syncwarp();
+        if (!SINGLE && lane == 0) mbar_arrive(&pread[cg]);
+        const float hconst = (p.td && hrow == p.H) ? tau : ((hrow == p.H + p.td) ? 1.0f : 0.0f);
+        const float pb = p.td ? fmaf(w1t, tau, b1) : b1;
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const float aj = p.single ? an[i] : fmaf(-dt, v[i], an[i]);
-        const float del = ss[i] * aj;
-        if (nb + i < p.B) {
-          dst_del[e0 + (size_t)i * LR_ZROW] = del;
-          if (p.single || last) dst_alpha[e0 + (size_t)i * LR_ZROW] = rowv ? aj : 0.0f;
+        for (int i = 0; i < 16; ++i) {
+          float h, sg;
+          act_pair<ACT>(v[i] + ss[i] + pb, h, sg);
+          ss[i] = rowv ? sg : 0.0f;
+          dst_hh[e0 + (size_t)i * LR_ZROW] = rowv ? h : hconst;
         }
-        dprev[i] = del;
+        // ---- alpha_j = alpha_n - dt Mh^T eps_j ; delta_j = s_j .* alpha_j
+        float an[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) an[i] = rowv ? __ldcg(alpha_n + e0 + (size_t)i * LR_ZROW) : 0.0f;
+        if (tr) ATRACE(5, jj);
+        if (!SINGLE) {
+          mbar_wait(&xdone[cg], (uint32_t)(jj & 1));
+          if (tr) ATRACE(6, jj);
+          tc_fence_after();
+          tmem_ld16(c_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(cg * 32 + rbase), v);
+          tc_fence_before();
+        }
+        float* dst_alpha = (SINGLE ? arr(LA_ALPHA + slot) : arr(LA_ALPHA + next)) + e0;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float aj = SINGLE ? an[i] : fmaf(-dt, v[i], an[i]);
+          dprev[i] = ss[i] * aj;
+          dst_del[e0 + (size_t)i * LR_ZROW] = dprev[i];
+          if (SINGLE || last) dst_alpha[(size_t)i * LR_ZROW] = rowv ? aj : 0.0f;
+        }
       }
     }
     if (tr) ATRACE(0, 3);
-    if (!p.single) {
+    if (!SINGLE) {
       // ---- Delta_bt = sum_j btilde_j delta_j ; sum_j b_j H_j ; sum_j btilde_j H_j  (stage 7 in registers / own stores)
       const LinComb& d7 = sd[5];   // coef = a_7i = b_i
-      float acc[16], acc2[16];
-      // three source arrays per round trip (the loop-carried registers of the stages are free here)
+      // which = 0: delta_j, 1: [h_j;tau_j;1]; three source arrays per round trip
       auto gather3 = [&](int s0, int ns, int which, float (&t)[3][16]) {
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-          const int s = s0 + k;
-          const float* src = (s == 0) ? arr(LA_S1 + 3 * slot + which)
-                                      : (s == 6 ? arr(LA_S1 + 3 * next + which) : arr((which ? LA_HH : LA_DEL) + s - 1));
+          const int s = min(s0 + k, 6);
+          const float* src = ((s == 0) ? arr(LA_S1 + 3 * slot + which)
+                                       : (s == 6 ? arr(LA_S1 + 3 * next + which) : arr((which ? LA_HH : LA_DEL) + s - 1))) + e0;
 #pragma unroll
-          for (int i = 0; i < 16; ++i)
-            t[k][i] = (k < ns && nb + i < p.B) ? __ldcg(src + e0 + (size_t)i * LR_ZROW) : 0.0f;
+          for (int i = 0; i < 16; ++i) t[k][i] = (k < ns) ? __ldcg(src + (size_t)i * LR_ZROW) : 0.0f;
         }
       };
+      float t[3][16];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) acc[i] = s_bt[6] * dprev[i];
-      if (rowv) {
-        float t[3][16];
-        for (int s0 = 0; s0 < 6; s0 += 3) {
-          gather3(s0, 3, 0, t);
-#pragma unroll
-          for (int k = 0; k < 3; ++k)
-#pragma unroll
-            for (int i = 0; i < 16; ++i) acc[i] = fmaf(s_bt[s0 + k], t[k][i], acc[i]);
-        }
-      }
-      {
-        float* dbt = arr(LA_DBT);
-#pragma unroll
-        for (int i = 0; i < 16; ++i)
-          if (nb + i < p.B) dbt[e0 + (size_t)i * LR_ZROW] = acc[i];
-      }
-      if (in_img) {   // the p accumulator of stage 7 has been read: tile C is free
-#pragma unroll
-        for (int i = 0; i < 16; ++i) tile_put(tC[cg], i, (nb + i < p.B) ? acc[i] : 0.0f);
-      }
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&out_full);
-#pragma unroll
-      for (int i = 0; i < 16; ++i) { acc[i] = 0.0f; acc2[i] = 0.0f; }
-      if (rowc) {
-        float t[3][16];
-        for (int s0 = 0; s0 < 7; s0 += 3) {
-          const int ns = min(3, 7 - s0);
-          gather3(s0, ns, 1, t);
+      for (int i = 0; i < 16; ++i) { v[i] = s_bt[6] * dprev[i]; ss[i] = 0.0f; c[i] = 0.0f; }
+      for (int round = 0; round < 5; ++round) {     // rounds 0, 1: delta_1..6 ; rounds 2..4: H_1..7
+        const int which = round < 2 ? 0 : 1;
+        const int s0 = which ? (round - 2) * 3 : round * 3;
+        const int ns = which ? min(3, 7 - s0) : 3;
+        if (which ? rowc : rowv) {
+          gather3(s0, ns, which, t);
 #pragma unroll
           for (int k = 0; k < 3; ++k) {
-            const int s = s0 + k;
-            const float cb = (k < ns && s < 6) ? d7.coef[s] : 0.0f, ct = (k < ns) ? s_bt[s] : 0.0f;
+            const int s = min(s0 + k, 6);
+            const float ct = (k < ns) ? s_bt[s] : 0.0f;
+            const float cb = (k < ns && s < 6) ? d7.coef[s] : 0.0f;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) { acc[i] = fmaf(cb, t[k][i], acc[i]); acc2[i] = fmaf(ct, t[k][i], acc2[i]); }
+            for (int i = 0; i < 16; ++i) {
+              if (which) { c[i] = fmaf(cb, t[k][i], c[i]); ss[i] = fmaf(ct, t[k][i], ss[i]); }
+              else v[i] = fmaf(ct, t[k][i], v[i]);
+            }
           }
+        }
+        if (round == 1) {    // Delta_bt complete: stored, and its operand image (tile C is free: p of stage 7 has been read)
+          float* dbt = arr(LA_DBT) + e0;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) dbt[(size_t)i * LR_ZROW] = v[i];
+          tile_put16(tCc, v);
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&out_full);
         }
       }
       if (tr) ATRACE(0, 4);
-      float* hbb = arr(LA_HBB);
-      float* hbt = arr(LA_HBT);
+      float* hbb = arr(LA_HBB) + e0;
+      float* hbt = arr(LA_HBT) + e0;
 #pragma unroll
-      for (int i = 0; i < 16; ++i)
-        if (nb + i < p.B) {
-          hbb[e0 + (size_t)i * LR_ZROW] = rowc ? acc[i] : 0.0f;
-          hbt[e0 + (size_t)i * LR_ZROW] = rowc ? acc2[i] : 0.0f;
-        }
+      for (int i = 0; i < 16; ++i) {
+        hbb[(size_t)i * LR_ZROW] = rowc ? c[i] : 0.0f;
+        hbt[(size_t)i * LR_ZROW] = rowc ? ss[i] : 0.0f;
+      }
     }
     tc_fence_before();
   }
   __syncthreads();
-  if (threadIdx.x == 0 && !p.single) ATRACE(0, 5);
+  if (threadIdx.x == 0 && !SINGLE) ATRACE(0, 5);
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
@@ -986,8 +943,8 @@ bool LatentAdjoint::eligible(const lrnde_model* m) {
 LatentAdjoint::LatentAdjoint(lrnde_ctx* c, const lrnde_model* mm, const float* p, int64_t b, int npasses)
     : ctx(c), m(mm), ps(p), B(b), passes(npasses) {
   lrf_shape(m, &sh);
-  zlen = (size_t)LR_ZROW * (size_t)B;
   ntiles = (int)((B + fused::kNT - 1) / fused::kNT);
+  zlen = (size_t)LR_ZROW * (size_t)ntiles * fused::kNT;   // work arrays padded to whole 64-sample tiles (adj_chain_kernel)
   nunits = (int)((B + 15) / 16);
   unit_bytes = (size_t)sh.nfull * 8192 + (size_t)sh.ntail * 2048;
   const int maxc = std::max(1, 148 / sh.n_mt);
@@ -1018,11 +975,16 @@ LatentAdjoint::LatentAdjoint(lrnde_ctx* c, const lrnde_model* mm, const float* p
   static bool attr_set = false;
   if (!attr_set) {
     constexpr int kChainSmem = 4 * (3 * 8192 + 3 * 2048) + ladj::kTapeBufs * ladj::kTapeBufBytes + 1024;   // KS <= 14: at most 3 full chunks + 3 tail K-steps
-    LR_CUDA(cudaFuncSetAttribute(ladj::adj_chain_kernel<ACT_IDENTITY>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmem));
-    LR_CUDA(cudaFuncSetAttribute(ladj::adj_chain_kernel<ACT_TANH>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmem));
-    LR_CUDA(cudaFuncSetAttribute(ladj::adj_chain_kernel<ACT_GELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmem));
-    LR_CUDA(cudaFuncSetAttribute(ladj::adj_chain_kernel<ACT_SIGMOID>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmem));
-    LR_CUDA(cudaFuncSetAttribute(ladj::adj_chain_kernel<ACT_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmem));
+    LR_CUDA(cudaFuncSetAttribute(ladj::adj_chain_kernel<ACT_IDENTITY, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmem));
+    LR_CUDA(cudaFuncSetAttribute(ladj::adj_chain_kernel<ACT_IDENTITY, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmem));
+    LR_CUDA(cudaFuncSetAttribute(ladj::adj_chain_kernel<ACT_TANH, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmem));
+    LR_CUDA(cudaFuncSetAttribute(ladj::adj_chain_kernel<ACT_TANH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmem));
+    LR_CUDA(cudaFuncSetAttribute(ladj::adj_chain_kernel<ACT_GELU, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmem));
+    LR_CUDA(cudaFuncSetAttribute(ladj::adj_chain_kernel<ACT_GELU, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmem));
+    LR_CUDA(cudaFuncSetAttribute(ladj::adj_chain_kernel<ACT_SIGMOID, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmem));
+    LR_CUDA(cudaFuncSetAttribute(ladj::adj_chain_kernel<ACT_SIGMOID, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmem));
+    LR_CUDA(cudaFuncSetAttribute(ladj::adj_chain_kernel<ACT_RELU, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmem));
+    LR_CUDA(cudaFuncSetAttribute(ladj::adj_chain_kernel<ACT_RELU, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmem));
     LR_CUDA(cudaFuncSetAttribute(ladj::pairacc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ladj::pairacc_smem()));
     attr_set = true;
   }
@@ -1037,12 +999,10 @@ LatentAdjoint::~LatentAdjoint() {
   ctx->release(RP); ctx->release(RX); ctx->release(RL);
 }
 
-void LatentAdjoint::prepare() {
-  const LayerInfo& L1 = m->layers[0];
-  const LayerInfo& L2 = m->layers[1];
-  ladj::mz_plain_kernel<<<128, 128, 0, ctx->stream>>>(ps + L1.w_off, ps + L2.w_off, sh.D, sh.H, sh.Kaug, Mz);
+void LatentAdjoint::prepare(const float* mz_plain) {
+  if (mz_plain) { Mz_ext = mz_plain; return; }   // kept by the forward call (lrnde_tape)
+  lrf_mz_plain(ctx, m, ps, Mz);
   LRA_COUNT(ctx);
-  LR_CUDA(cudaGetLastError());
 }
 
 static void lra_launch_chain(LatentAdjoint& E, SolveDev* S, int single) {
@@ -1050,7 +1010,7 @@ static void lra_launch_chain(LatentAdjoint& E, SolveDev* S, int single) {
   const LayerInfo& L1 = E.m->layers[0];
   ladj::AChainP cp;
   memset(&cp, 0, sizeof(cp));
-  cp.S = S; cp.single = single; cp.Mz = E.Mz;
+  cp.S = S; cp.single = single; cp.Mz = E.Mz_ext ? E.Mz_ext : E.Mz;
   cp.w1t = sh.td ? E.ps + L1.w_off + (size_t)sh.D * sh.H : nullptr;
   cp.b1 = E.ps + L1.b_off;
   cp.Zx = E.Zx; cp.alpha_in = E.alpha_in; cp.ws = E.ws; cp.zlen = E.zlen;
@@ -1059,13 +1019,16 @@ static void lra_launch_chain(LatentAdjoint& E, SolveDev* S, int single) {
   cp.passes = E.passes;
   const size_t smem_c = 4 * ((size_t)sh.nfull * 8192 + (size_t)sh.ntail * 2048) + ladj::kTapeBufs * ladj::kTapeBufBytes + 1024;
   cudaStream_t st = E.ctx->stream;
+#define LRA_CHAIN(A) do { if (single) ladj::adj_chain_kernel<A, true><<<E.ntiles, fused::kThreads, smem_c, st>>>(cp); \
+                         else ladj::adj_chain_kernel<A, false><<<E.ntiles, fused::kThreads, smem_c, st>>>(cp); } while (0)
   switch (sh.act) {
-    case ACT_TANH: ladj::adj_chain_kernel<ACT_TANH><<<E.ntiles, fused::kThreads, smem_c, st>>>(cp); break;
-    case ACT_GELU: ladj::adj_chain_kernel<ACT_GELU><<<E.ntiles, fused::kThreads, smem_c, st>>>(cp); break;
-    case ACT_SIGMOID: ladj::adj_chain_kernel<ACT_SIGMOID><<<E.ntiles, fused::kThreads, smem_c, st>>>(cp); break;
-    case ACT_RELU: ladj::adj_chain_kernel<ACT_RELU><<<E.ntiles, fused::kThreads, smem_c, st>>>(cp); break;
-    default: ladj::adj_chain_kernel<ACT_IDENTITY><<<E.ntiles, fused::kThreads, smem_c, st>>>(cp); break;
+    case ACT_TANH: LRA_CHAIN(ACT_TANH); break;
+    case ACT_GELU: LRA_CHAIN(ACT_GELU); break;
+    case ACT_SIGMOID: LRA_CHAIN(ACT_SIGMOID); break;
+    case ACT_RELU: LRA_CHAIN(ACT_RELU); break;
+    default: LRA_CHAIN(ACT_IDENTITY); break;
   }
+#undef LRA_CHAIN
   LRA_COUNT(E.ctx);
   LR_CUDA(cudaGetLastError());
 }

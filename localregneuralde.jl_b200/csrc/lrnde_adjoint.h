@@ -33,6 +33,7 @@ struct LatentAdjoint {
   int nP = 1, chunkP = 32;    // pairacc: CTAs / samples per CTA of the hidden-space terms
   int nD = 1, chunkD = 32;    // pairacc: batch splits / samples per split of the D-dimensional terms
   float* Mz = nullptr;        // [128][128] plain fp32 (zero padded)
+  const float* Mz_ext = nullptr;   // the copy the forward call kept, when there is one
   float* ws = nullptr;        // LA_NARR hidden-space arrays of [B][LR_ZROW]
   float* alpha_in = nullptr;  // W2^T lambda of the current state (written by the caller's GEMM before begin())
   float* hbuf = nullptr;      // operand images of the lambda GEMM: units of 16 samples x {Delta_b, Delta_bt}
@@ -46,7 +47,7 @@ struct LatentAdjoint {
   static bool eligible(const lrnde_model* m);
   LatentAdjoint(lrnde_ctx* c, const lrnde_model* mm, const float* p, int64_t b, int npasses);
   ~LatentAdjoint();
-  void prepare();
+  void prepare(const float* mz_plain = nullptr);
   // stage-1 quantities (delta_1, [h_1;t;1], c_1) of the current state from alpha_in and S->yint[0]
   void begin(SolveDev* S);
   // one Tsit5 attempt of the adjoint from the descriptors of S (st, yint, err): launches (1) - (4)

@@ -563,6 +563,7 @@ struct MlpEval {
   std::unique_ptr<ConvEval> conv;  // conv dynamics: every call below is forwarded
   std::unique_ptr<FusedEngine> fe; // latent-space engine (lrnde_fused.h): forward attempts of 2-layer TD-MLPs
   float* packW1x = nullptr;        // images of W1[:, :D] alone: Z(x) = W1[:, :D] x
+  float* mz_plain_out = nullptr;   // where prepare() leaves the plain copy of Mz = W1 W2a (kept in the tape for the pullback)
   std::vector<int> wS, wChunk;    // SIMT weight-gradient split
   std::vector<int> uS, uChunk;    // tcgen05 weight-gradient split (0 = layer not eligible)
 
@@ -710,7 +711,7 @@ struct MlpEval {
     if (conv) { conv->prepare(); return; }
     if (use_small) return;
     if (fe) {
-      fe->prepare();
+      fe->prepare(mz_plain_out);
       const LayerInfo& L1 = m->layers[0];
       umma::pack_weights_kernel<<<dim3(tiles_m(L1.out) * chunks_k(L1.in), umma::kReplicas), 256, 0, ctx->stream>>>(
           ps + L1.w_off, L1.out, L1.out, L1.in, chunks_k(L1.in), packW1x, passes);
@@ -1224,6 +1225,7 @@ struct lrnde_tape {
   int64_t B;
   float* ps = nullptr;  // device copy of the parameters the forward used
   float* bn_state = nullptr;  // conv dynamics: device copy of st.model the forward normalised with (testmode)
+  float* Mz = nullptr;        // latent-space engines: W1 W2a of the parameters the forward used ([128][128])
   std::unique_ptr<Solver> fwd;
   std::unique_ptr<Solver> reg;  // regulariser integrator (2-slot ring), reg modes only
   std::vector<float> fts;       // host copy of accepted times
@@ -1235,7 +1237,7 @@ struct lrnde_tape {
   // step logs (host copies)
   std::vector<float> log_t[2], log_dt[2], log_eest[2];
   std::vector<unsigned char> log_acc[2];
-  ~lrnde_tape() { ctx->release(ps); ctx->release(bn_state); }
+  ~lrnde_tape() { ctx->release(ps); ctx->release(bn_state); ctx->release(Mz); }
 };
 
 static void lr_copy_log(Solver& S, lrnde_tape* T, int which) {
@@ -1590,6 +1592,10 @@ extern "C" int lrnde_ode_forward(lrnde_ctx* ctx, const lrnde_model* m, const lrn
 
   const bool need_vjp = false;
   MlpEval ev(ctx, m, T->ps, B, o->precision, need_vjp);
+  if (ev.fe && o->keep_tape) {
+    T->Mz = (float*)ctx->alloc(sizeof(float) * 128 * 128);
+    ev.mz_plain_out = T->Mz;
+  }
   ev.prepare();
   if (ev.conv) {   // st.model: tracked by the main solve's f evaluations only (the closure's st_ at the time
                    // _solve_neuralode_generic returns, neural_ode.jl:44-53)
@@ -1935,7 +1941,7 @@ extern "C" int lrnde_ode_backward(lrnde_ctx* ctx, const lrnde_model* m, lrnde_ta
     if (F.htape && ev.use_umma && LatentAdjoint::eligible(m) && !getenv("LRNDE_NO_LATENT_ADJ")) {
       la = std::make_unique<LatentAdjoint>(ctx, m, T->ps, B, ev.passes);
       la->W1T = ev.WT[0]; la->Zx = F.ztape; la->x = F.tape;
-      la->prepare();
+      la->prepare(T->Mz);
       A.h.fhtape = F.htape;
       A.h.fztape = F.ztape;
       A.h.fzlen = F.h.zlen;

@@ -29,16 +29,31 @@ using namespace umma;
 // ---------------------------------------------------------------------------------------------------------
 // weight images (once per call: the parameters change every training iteration)
 // ---------------------------------------------------------------------------------------------------------
-// Mz = W1[:, :D] * W2a  ([H x Kaug], accumulated in double), as the 128-row A operand of the chain kernel
-__global__ void mz_pack_kernel(const float* __restrict__ W1, const float* __restrict__ W2a, int D, int H, int Kaug,
-                               int nfull, float* __restrict__ img, uint32_t img_bytes, int passes) {
-  const int r = threadIdx.x, k = blockIdx.x;
-  float v = 0.0f;
+// Mz = W1[:, :D] * W2a  ([H x Kaug], accumulated in double) as a plain zero-padded [128][128] matrix: one block per
+// column k, thread = (row r, slice of the D-long dot product), fixed-order sum of the four slices
+__global__ void __launch_bounds__(512) mz_plain_kernel(const float* __restrict__ W1, const float* __restrict__ W2a, int D, int H,
+                                                       int Kaug, float* __restrict__ out) {
+  __shared__ double part[4][128];
+  const int r = threadIdx.x & 127, sl = threadIdx.x >> 7, k = blockIdx.x;
+  double acc0 = 0.0, acc1 = 0.0;
   if (r < H && k < Kaug) {
-    double acc = 0.0;
-    for (int d = 0; d < D; ++d) acc += (double)W1[(size_t)d * H + r] * (double)W2a[(size_t)k * D + d];
-    v = (float)acc;
+    const float* w2 = W2a + (size_t)k * D;
+    int d = sl;
+    for (; d + 4 < D; d += 8) {
+      acc0 += (double)W1[(size_t)d * H + r] * (double)w2[d];
+      acc1 += (double)W1[(size_t)(d + 4) * H + r] * (double)w2[d + 4];
+    }
+    for (; d < D; d += 4) acc0 += (double)W1[(size_t)d * H + r] * (double)w2[d];
   }
+  part[sl][r] = acc0 + acc1;
+  __syncthreads();
+  if (sl == 0) out[r * 128 + k] = (float)(((part[0][r] + part[1][r]) + part[2][r]) + part[3][r]);
+}
+// ... and as the 128-row tf32 hi / lo A-operand image of the chain kernel
+__global__ void mz_image_kernel(const float* __restrict__ plain, int Kaug, int nfull, float* __restrict__ img, uint32_t img_bytes,
+                                int passes) {
+  const int r = threadIdx.x, k = blockIdx.x;
+  const float v = (k < 128) ? plain[r * 128 + k] : 0.0f;
   const float hi = (passes == 1) ? v : tf32_rna(v);
   const float lo = (passes == 1) ? 0.0f : tf32_rna(v - hi);
   const uint32_t o = img_off(128, nfull, r, k);
@@ -63,6 +78,8 @@ struct ChainP {
   float* hbuf;
   uint32_t unit_bytes;
   int B, H, td, KS, nfull, ntail, passes, nbuf, write_z;
+  int combo;   // lean attempt: export only the operand images of sum_i a_7i H(k_i) and sum_i btilde_i H(k_i) (units of
+               // 16 samples x 2 row groups) for kgemm_kernel<2, false>: u_{n+1} and the residual need nothing else
 };
 
 template <int ACT>
@@ -74,6 +91,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(ChainP p) {
   __shared__ uint64_t abar, bfull[2][2], bfree[2], zdone[2];
   __shared__ uint32_t tmem_slot;
   __shared__ LinComb sd[7];
+  __shared__ float s_bt[7];
   __shared__ float* s_tape;
   __shared__ float* s_ztape;
   __shared__ float* s_htape;
@@ -99,6 +117,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(ChainP p) {
     if (p.single) sd[0] = *p.single;
     else for (int j = 0; j < 7; ++j) sd[j] = p.S->st[j];
     if (p.single) sd[1] = p.single_out ? *p.single_out : *p.single;
+    for (int j = 0; j < 7; ++j) s_bt[j] = p.S->err.coef[j];
     s_tape = p.S->tape; s_ztape = p.S->ztape; s_htape = p.S->htape; s_len = p.S->len; s_zlen = p.S->zlen;
   }
   if (warp == 1) {
@@ -126,6 +145,11 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(ChainP p) {
       const uint32_t ph = (uint32_t)((st / p.nbuf) & 1);
       mbar_wait(&bfull[0][b], ph);
       mbar_wait(&bfull[1][b], ph);
+      if (p.combo) {          // nothing to export per stage; the MMA of this stage has its own barrier (zdone)
+        if (elect_one_sync()) mbar_arrive(&bfree[b]);
+        __syncwarp();
+        continue;
+      }
       if (elect_one_sync()) {
         // the 64 rows of this stage = rows [16 j, 16 j + 16) of four 16-sample unit tiles
         const int j = p.single ? 0 : st;
@@ -144,6 +168,30 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(ChainP p) {
         bulk_commit();
         bulk_wait_read0();
         mbar_arrive(&bfree[b]);
+      }
+      __syncwarp();
+    }
+    if (p.combo) {
+      // the two combination tiles (buffer 0: sum a_7i H(k_i), buffer 1: sum btilde_i H(k_i)) as row groups 0 / 1 of
+      // units of 16 samples x 2 groups (the operand layout of kgemm_kernel<2, *>)
+      const uint32_t ph = (uint32_t)((6 / p.nbuf) & 1);
+      for (int b = 0; b < 2; ++b) { mbar_wait(&bfull[0][b], ph); mbar_wait(&bfull[1][b], ph); }
+      if (elect_one_sync()) {
+        for (int j = 0; j < 2; ++j) {
+          const uint8_t* s = smB + (size_t)j * tileB;
+          for (int sg = 0; sg < 4; ++sg) {
+            uint8_t* g = reinterpret_cast<uint8_t*>(p.hbuf) + ((size_t)blockIdx.x * 4 + sg) * p.unit_bytes;
+            for (int c = 0; c < p.nfull; ++c)
+              for (int lo = 0; lo < 2; ++lo)
+                bulk_s2g(g + (size_t)c * 8192 + lo * 4096 + j * 2048,
+                         s + (size_t)c * (2 * kNT * 128) + lo * (kNT * 128) + sg * 2048, 2048);
+            for (int t = 0; t < p.ntail; ++t)
+              for (int lo = 0; lo < 2; ++lo)
+                bulk_s2g(g + (size_t)p.nfull * 8192 + (size_t)t * 2048 + lo * 1024 + j * 512,
+                         s + (size_t)p.nfull * (2 * kNT * 128) + (size_t)t * (2 * kNT * 32) + lo * (kNT * 32) + sg * 512, 512);
+          }
+        }
+        bulk_commit();
       }
       __syncwarp();
     }
@@ -230,16 +278,35 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(ChainP p) {
     // cumulative hidden image of the state: u_{n+1} = x + W2a C_{n+1},  C_{n+1} = C_n + dt sum_i a_7i H(k_i)
     // (hidden tape of the latent-space adjoint); H(k_1) comes from the tape, H(k_2..6) from the stages below
     const bool write_c = !p.single && s_htape && hrow < p.H + p.td + 1;
-    float csum[16];
+    float csum[16], bsum[16];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) csum[i] = 0.0f;
+    for (int i = 0; i < 16; ++i) { csum[i] = 0.0f; bsum[i] = 0.0f; }
     if (write_c) {
       const float* h1 = hof(sd[5].src[0]);
-      const float cf = sd[5].coef[0];
+      const float cf = sd[5].coef[0], cb = s_bt[0];
 #pragma unroll
       for (int i = 0; i < 16; ++i)
-        if (n0 + col + i < p.B) csum[i] = cf * __ldcg(h1 + (size_t)(n0 + col + i) * LR_ZROW + hrow);
+        if (n0 + col + i < p.B) {
+          const float h1v = __ldcg(h1 + (size_t)(n0 + col + i) * LR_ZROW + hrow);
+          csum[i] = cf * h1v;
+          if (p.combo) bsum[i] = cb * h1v;
+        }
     }
+    auto tile_put16 = [&](uint8_t* tile, const float (&val)[16]) {
+      if (!in_img) return;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int row = col + i;
+        float hi, lo;
+        if (p.passes == 3) { hi = tf32_rna(val[i]); lo = tf32_rna(val[i] - hi); }
+        else { hi = val[i]; lo = 0.0f; }
+        uint32_t o;
+        if (in_full) o = obase + (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + (((lane >> 2) ^ (row & 7)) << 4));
+        else o = (obase & 0x3FFFFFFFu) + (uint32_t)(row * 32 + ((((obase >> 30) & 1) ^ ((row >> 2) & 1)) << 4));
+        *reinterpret_cast<float*>(tile + o) = hi;
+        *reinterpret_cast<float*>(tile + o + ostep_lo) = lo;
+      }
+    };
     for (int st = 0; st < nst; ++st) {
       const int b = st % p.nbuf;
       const LinComb& d = sd[st];
@@ -281,6 +348,11 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(ChainP p) {
         v[i] = rowv ? h : hconst;
       }
       if (write_c) {
+        if (p.combo) {
+          const float cb = s_bt[st + 1];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) bsum[i] = fmaf(cb, v[i], bsum[i]);
+        }
         if (!last_full) {
           const float cf = sd[5].coef[st + 1];
 #pragma unroll
@@ -305,20 +377,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(ChainP p) {
         for (int i = 0; i < 16; ++i)
           if (n0 + col + i < p.B) ho[(size_t)(n0 + col + i) * LR_ZROW + hrow] = v[i];
       }
-      if (in_img) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int row = col + i;
-          float hi, lo;
-          if (p.passes == 3) { hi = tf32_rna(v[i]); lo = tf32_rna(v[i] - hi); }
-          else { hi = v[i]; lo = 0.0f; }
-          uint32_t o;
-          if (in_full) o = obase + (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + (((lane >> 2) ^ (row & 7)) << 4));
-          else o = (obase & 0x3FFFFFFFu) + (uint32_t)(row * 32 + ((((obase >> 30) & 1) ^ ((row >> 2) & 1)) << 4));
-          *reinterpret_cast<float*>(tile + o) = hi;
-          *reinterpret_cast<float*>(tile + o + ostep_lo) = lo;
-        }
-      }
+      tile_put16(tile, v);
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bfull[cg][b]);
@@ -337,6 +396,16 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(ChainP p) {
             if (n0 + col + i < p.B) zo[(size_t)(n0 + col + i) * LR_ZROW + hrow] = v[i];
         }
       }
+    }
+    if (p.combo) {
+      // every MMA has read its tile (zdone of the last stage): both buffers are free for the two combination tiles
+#pragma unroll
+      for (int i = 0; i < 16; ++i) { if (n0 + col + i >= p.B) { csum[i] = 0.0f; bsum[i] = 0.0f; } }
+      tile_put16(smB, csum);
+      tile_put16(smB + (size_t)tileB, bsum);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(&bfull[cg][0]); mbar_arrive(&bfull[cg][1]); }
     }
     tc_fence_before();
     if (tr) FTRACE(0, 1, 0, 3);
@@ -537,7 +606,7 @@ __global__ void __launch_bounds__(kThreads, 1) kgemm_kernel(KgemmP p) {
     const float* pk1 = s_err.src[0] + m;
     float* po[7];
 #pragma unroll
-    for (int jj = 0; jj < 6; ++jj) po[jj] = ADJ ? nullptr : const_cast<float*>(s_err.src[jj + 1]) + m;
+    for (int jj = 0; jj < 6; ++jj) po[jj] = (ADJ || NSTG == 2) ? nullptr : const_cast<float*>(s_err.src[jj + 1]) + m;
     po[6] = s_err.dst + m;
     float* psingle = (p.single ? s_un.dst : s_err.dst) + m;
     float ca[6], cb[7];
@@ -553,13 +622,13 @@ __global__ void __launch_bounds__(kThreads, 1) kgemm_kernel(KgemmP p) {
       if (mv && nb + 4 <= p.B && !(p.dbg & 2)) {
         const unsigned e = (unsigned)nb * D;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { a[i] = __ldcg(pu + (e + (unsigned)i * D)); b[i] = ADJ ? 0.0f : __ldcg(pk1 + (e + (unsigned)i * D)); }
+        for (int i = 0; i < 4; ++i) { a[i] = __ldcg(pu + (e + (unsigned)i * D)); b[i] = (ADJ || NSTG == 2) ? 0.0f : __ldcg(pk1 + (e + (unsigned)i * D)); }
       } else {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const bool ok = mv && (nb + i < p.B) && !(p.dbg & 2);
           a[i] = ok ? __ldcg(pu + (size_t)(nb + i) * D) : 0.0f;
-          b[i] = (ok && !ADJ) ? __ldcg(pk1 + (size_t)(nb + i) * D) : 0.0f;
+          b[i] = (ok && !ADJ && NSTG != 2) ? __ldcg(pk1 + (size_t)(nb + i) * D) : 0.0f;
         }
       }
     };
@@ -605,6 +674,11 @@ __global__ void __launch_bounds__(kThreads, 1) kgemm_kernel(KgemmP p) {
         // utilde = -dt (W1^T Delta_btilde)   (perform_step.jl:18-27 on the lambda block of the adjoint state)
 #pragma unroll
         for (int i = 0; i < 4; ++i) { unew[i] = fmaf(-edt, k[0][i], upc[i]); ut[i] = -k[NSTG - 1][i]; }
+      } else if constexpr (NSTG == 2) {
+        // lean forward attempt: accumulators = W2a sum_i a_7i H(k_i) and W2a sum_i btilde_i H(k_i) (k_1 included), i.e.
+        // sum_i a_7i k_i and sum_i btilde_i k_i of perform_step.jl:18-27 by linearity of the output layer
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { unew[i] = fmaf(sdt, k[0][i], upc[i]); ut[i] = k[1][i]; }
       } else {
 #pragma unroll
         for (int i = 0; i < 4; ++i) { un[i] = ca[0] * k1c[i]; ut[i] = cb[0] * k1c[i]; }
@@ -622,7 +696,7 @@ __global__ void __launch_bounds__(kThreads, 1) kgemm_kernel(KgemmP p) {
       }
       if (tr) FTRACE(1, 0, 8, u);
       if (full) {
-        if (!ADJ && !(p.dbg & 1)) {
+        if (!ADJ && NSTG != 2 && !(p.dbg & 1)) {
 #pragma unroll
           for (int jj = 0; jj < NSTG; ++jj)
             if (jj == NSTG - 1 || !p.lean) {   // k_7 = fsalfirst of the next attempt is always needed
@@ -646,7 +720,7 @@ __global__ void __launch_bounds__(kThreads, 1) kgemm_kernel(KgemmP p) {
         for (int i = 0; i < 4; ++i) {
           if (nb + i < p.B) {
             const size_t e = (size_t)(nb + i) * D;
-            if (!ADJ) {
+            if (!ADJ && NSTG != 2) {
 #pragma unroll
               for (int jj = 0; jj < NSTG; ++jj)
                 if (jj == NSTG - 1 || !p.lean) po[jj][e] = k[jj][i];
@@ -787,6 +861,7 @@ static void lrf_set_attrs() {
     LR_CUDA(cudaFuncSetAttribute(fused::chain_kernel<ACT_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     LR_CUDA(cudaFuncSetAttribute(fused::kgemm_kernel<6, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     LR_CUDA(cudaFuncSetAttribute(fused::kgemm_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    LR_CUDA(cudaFuncSetAttribute(fused::kgemm_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     attr_set = true;
   }
 }
@@ -800,8 +875,10 @@ FusedEngine::FusedEngine(lrnde_ctx* c, const lrnde_model* mm, const float* p, in
   nunits = (int)((B + 15) / 16);
   imgM = lrf_round_up((size_t)128 * sh.KS * 32, 1024);
   unit_bytes = (size_t)sh.nfull * fused::kPieceBytes + (size_t)sh.ntail * fused::kTailBytes;
+  unit_bytes2 = (size_t)sh.nfull * 8192 + (size_t)sh.ntail * 2048;   // units of 16 samples x 2 row groups (combo attempts)
   nbuf = (2 * imgM + 2 * (size_t)fused::kNT * sh.KS * 64 + 2048 <= 226 * 1024) ? 2 : 1;
   Mimg = (float*)ctx->alloc(2 * imgM);
+  Mplain = (float*)ctx->alloc(sizeof(float) * 128 * 128);
   hbuf = (float*)ctx->alloc((size_t)ntiles * 4 * unit_bytes);
   // kgemm launch geometry: one cluster = the n_mt feature tiles of the same samples (operand pieces multicast)
   // (measured at 8192 samples: 7-CTA clusters fit 15 at a time = 105 SMs, 80 us per attempt; 147 independent CTAs
@@ -832,15 +909,24 @@ FusedEngine::FusedEngine(lrnde_ctx* c, const lrnde_model* mm, const float* p, in
 
 FusedEngine::~FusedEngine() {
   ctx->release(Mimg);
+  ctx->release(Mplain);
   ctx->release(hbuf);
 }
 
-void FusedEngine::prepare() {
+void lrf_mz_plain(lrnde_ctx* ctx, const lrnde_model* m, const float* ps, float* out) {
+  FusedShape sh;
+  lrf_shape(m, &sh);
   const LayerInfo& L1 = m->layers[0];
-  const LayerInfo& L2 = m->layers[1];
-  const float* W1 = ps + L1.w_off;
-  const float* W2a = ps + L2.w_off;   // [D x (H + td)] followed by the bias: one [D x Kaug] column-major block
-  fused::mz_pack_kernel<<<sh.KS * 8, 128, 0, ctx->stream>>>(W1, W2a, sh.D, sh.H, sh.Kaug, sh.nfull, Mimg, (uint32_t)imgM, passes);
+  const LayerInfo& L2 = m->layers[1];   // [D x (H + td)] followed by the bias: one [D x Kaug] column-major block
+  fused::mz_plain_kernel<<<128, 512, 0, ctx->stream>>>(ps + L1.w_off, ps + L2.w_off, sh.D, sh.H, sh.Kaug, out);
+  LRF_COUNT(ctx);
+  LR_CUDA(cudaGetLastError());
+}
+
+void FusedEngine::prepare(float* mz_plain_out) {
+  float* plain = mz_plain_out ? mz_plain_out : Mplain;
+  lrf_mz_plain(ctx, m, ps, plain);
+  fused::mz_image_kernel<<<sh.KS * 8, 128, 0, ctx->stream>>>(plain, sh.Kaug, sh.nfull, Mimg, (uint32_t)imgM, passes);
   LRF_COUNT(ctx);
   LR_CUDA(cudaGetLastError());
 }
@@ -858,6 +944,8 @@ static void lrf_launch_chain(FusedEngine& E, SolveDev* S, const LinComb* single,
   cp.hbuf = E.hbuf; cp.unit_bytes = (uint32_t)E.unit_bytes;
   cp.B = (int)E.B; cp.H = sh.H; cp.td = sh.td; cp.KS = sh.KS; cp.nfull = sh.nfull; cp.ntail = sh.ntail;
   cp.passes = E.passes; cp.nbuf = E.nbuf; cp.write_z = write_z;
+  cp.combo = (!single && E.combo()) ? 1 : 0;
+  if (cp.combo) cp.unit_bytes = (uint32_t)E.unit_bytes2;
   const size_t smem_c = 2 * E.imgM + (size_t)E.nbuf * fused::kNT * sh.KS * 64 + 1024;
   cudaStream_t st = E.ctx->stream;
   switch (sh.act) {
@@ -882,18 +970,21 @@ static void lrf_launch_kgemm(FusedEngine& E, SolveDev* S, const LinComb* single,
   kp.dbg = getenv("LRNDE_KG_DBG") ? atoi(getenv("LRNDE_KG_DBG")) : 0;
   kp.lean = (!single && E.lean) ? 1 : 0;
   kp.add_base = single ? E.add_base : nullptr;
+  const bool combo = !single && E.combo();
+  if (combo) kp.unit_bytes = (uint32_t)E.unit_bytes2;
   kp.ntail = sh.ntail; kp.passes = E.passes; kp.nunits = E.nunits; kp.nclusters = E.nclusters; kp.ring = E.ring;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(sh.n_mt * E.nclusters);
   cfg.blockDim = dim3(fused::kThreads);
-  cfg.dynamicSmemBytes = 2 * lrf_round_up(E.unit_bytes, 1024) + 1024;
+  cfg.dynamicSmemBytes = 2 * lrf_round_up(combo ? E.unit_bytes2 : E.unit_bytes, 1024) + 1024;
   cfg.stream = E.ctx->stream;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = E.cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
-  LR_CUDA(cudaLaunchKernelEx(&cfg, fused::kgemm_kernel<6, false>, kp));
+  if (combo) LR_CUDA(cudaLaunchKernelEx(&cfg, fused::kgemm_kernel<2, false>, kp));
+  else LR_CUDA(cudaLaunchKernelEx(&cfg, fused::kgemm_kernel<6, false>, kp));
   LRF_COUNT(E.ctx);
   LR_CUDA(cudaGetLastError());
 }

@@ -15,6 +15,8 @@
 //   (3) controller_kernel (unchanged).
 // Every k_j is still materialised, so the tape, the interpolant, the saves and the adjoint are unchanged.
 #pragma once
+#include <stdlib.h>
+
 #include "lrnde_host.h"
 
 struct FusedShape {
@@ -33,6 +35,9 @@ bool lrf_shape(const lrnde_model* m, FusedShape* out);
 void lrf_launch_kgemm_adj(lrnde_ctx* ctx, SolveDev* S, const FusedShape& sh, const float* W1, const float* hbuf,
                           size_t unit_bytes, int64_t B, int passes, int nunits, int nclusters);
 
+// Mz = W1[:, :D] W2a as a plain zero-padded [128][128] matrix (device), accumulated in double
+void lrf_mz_plain(lrnde_ctx* ctx, const lrnde_model* m, const float* ps, float* out);
+
 struct FusedEngine {
   lrnde_ctx* ctx;
   const lrnde_model* m;
@@ -47,16 +52,20 @@ struct FusedEngine {
   int nclusters = 1;     // kgemm: persistent clusters
   int ring = 8;          // kgemm: operand pieces in flight
   float* Mimg = nullptr;   // chain A operand: [hi | lo] images of Mz, 128 rows
+  float* Mplain = nullptr; // Mz as a plain zero-padded [128][128] matrix
   float* hbuf = nullptr;   // operand images written by the chain kernel: per 16-sample unit, 96 rows = 6 stages x 16
-  size_t imgM = 0, unit_bytes = 0;
-  int lean = 0;                     // lean tape: attempts do not store k_2..k_6
+  size_t imgM = 0, unit_bytes = 0, unit_bytes2 = 0;
+  int lean = 0;                     // lean tape: attempts store u_{n+1} only (the hidden tape carries everything else)
+  // lean attempts run the two-column GEMM (sum a_7i k_i, sum btilde_i k_i) when both operand buffers exist
+  bool combo() const { return lean && nbuf == 2 && !getenv("LRNDE_NO_COMBO"); }
   const float* add_base = nullptr;  // dense_output(): base array of the single-mode kgemm
 
   static bool eligible(const lrnde_model* m);
   FusedEngine(lrnde_ctx* c, const lrnde_model* mm, const float* p, int64_t b, int npasses);
   ~FusedEngine();
   size_t zlen() const { return (size_t)LR_ZROW * (size_t)B; }
-  void prepare();
+  // Mz = W1 W2a (double accumulation) and its operand image; mz_plain_out (optional): where the plain [128][128] copy goes
+  void prepare(float* mz_plain_out = nullptr);
   // one Tsit5 attempt from the descriptors of S (st[0..6], err): launches (1) and (2)
   void step(SolveDev* S, int write_z);
   void step_chain(SolveDev* S, int write_z);   // the two launches of step(), separately (profiling)

@@ -14,7 +14,7 @@ node = pkg.NeuralODE(chain, ctx=ctx, abstol=1.4e-8, reltol=1.4e-8, precision="tf
                      loop_mode=int(os.environ.get("LOOP_MODE", "2")))
 ps = torch.from_numpy(node.initialparameters(np.random.default_rng(0)) * scale).to(dev)
 x = torch.rand((B, 784), device=dev).t()
-for it in range(2):
+for it in range(int(os.environ.get("ITERS", "2"))):
     sol, st2 = node(x, ps, node.initialstates(np.random.default_rng(1)))
     cots = [(torch.randn((B, 784), device=dev) / B).t() for _ in sol.u]
     torch.cuda.synchronize(); t0 = time.perf_counter()
