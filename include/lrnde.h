@@ -59,7 +59,8 @@ enum { LRNDE_PREC_AUTO = 0, LRNDE_PREC_FP32_SIMT = 1, LRNDE_PREC_TF32X3 = 2, LRN
        LRNDE_PREC_SMEM = 4 /* FP32, whole network out of shared memory: one launch per evaluation (small nets) */ };
 /* solver retcodes (OrdinaryDiffEq ReturnCode subset the loop can produce) */
 enum { LRNDE_RET_SUCCESS = 0, LRNDE_RET_MAXITERS = 1, LRNDE_RET_DTMIN = 2, LRNDE_RET_UNSTABLE = 3,
-       LRNDE_RET_TAPEFULL = 4 };
+       LRNDE_RET_TAPEFULL = 4,
+       LRNDE_RET_PEERTIMEOUT = 5 /* data-parallel group: a rank did not reach a norm / mu exchange within ~10 s */ };
 /* controller power function */
 enum { LRNDE_POW_FASTPOW2023 = 0, LRNDE_POW_EXACT = 1 };
 

@@ -13,7 +13,7 @@ REG = {"none": 0, "unbiased": 1, "biased": 2}
 REGTYPE = {"error_estimate": 0, "stiffness_estimate": 1}
 PREC = {"auto": 0, "fp32": 1, "tf32x3": 2, "tf32": 3, "smem": 4}
 POW = {"fastpow_2023": 0, "exact": 1}
-RETCODES = {0: "Success", 1: "MaxIters", 2: "DtLessThanMin", 3: "Unstable", 4: "TapeFull"}
+RETCODES = {0: "Success", 1: "MaxIters", 2: "DtLessThanMin", 3: "Unstable", 4: "TapeFull", 5: "PeerTimeout"}
 
 
 class LayerDesc(C.Structure):

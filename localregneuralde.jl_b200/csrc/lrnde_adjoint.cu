@@ -887,7 +887,7 @@ __global__ void __launch_bounds__(256) adj_mu_finish_kernel(SolveDev* S) {
       volatile unsigned long long* f = &mine->mflag[par][r];
       while (*f != S->mseq + 1) {
         __nanosleep(40);
-        if (++spins > (1ll << 26)) { S->failed = 1; break; }   // a peer never arrived (~10 s): give up instead of hanging
+        if (++spins > (1ll << 26)) { lr_peer_timeout(S); break; }   // a peer never arrived (~10 s): give up instead of hanging
       }
     }
     __threadfence_system();

@@ -153,6 +153,7 @@ extern "C" int lrnde_ctx_destroy(lrnde_ctx* c) {
   cudaStreamSynchronize(c->stream);
   for (auto& b : c->pool) cudaFree(b.p);
   if (c->mailbox) cudaFree(c->mailbox);
+  if (c->bn_seq) cudaFree(c->bn_seq);
   if (c->pinned) cudaFreeHost(c->pinned);
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
@@ -199,9 +200,33 @@ extern "C" int lrnde_ctx_set_dist(lrnde_ctx* c, int rank, int nranks, void* cons
   c->nranks = nranks;
   c->total_batch = total_batch;
   for (int r = 0; r < nranks && nranks > 1; ++r) c->peer_mbox[r] = (LrMailbox*)mailboxes[r];
-  c->seq = 0;
-  c->mseq = 0;
+  // the exchange sequence numbers (seq, mseq, bn_seq) are NOT reset: the mailbox flags of earlier exchanges stay in
+  // place, and every rank of the group calls this the same number of times, so the counters stay in step
+  LR_CUDA(cudaSetDevice(c->device));
+  if (!c->bn_seq) {
+    LR_CUDA(cudaMalloc((void**)&c->bn_seq, sizeof(unsigned long long) * (LR_BN_MAXC + 1)));
+    LR_CUDA(cudaMemset(c->bn_seq, 0, sizeof(unsigned long long) * (LR_BN_MAXC + 1)));
+  }
   LR_API_END
+}
+
+BnDist lrnde_ctx::bn_dist() {
+  BnDist d;
+  memset(&d, 0, sizeof(d));
+  d.rank = rank;
+  d.nranks = bn_seq ? nranks : 1;
+  for (int r = 0; r < LR_MAX_RANKS; ++r) d.mbox[r] = peer_mbox[r];
+  d.seq = bn_seq;
+  d.timed_out = bn_seq ? (int*)(bn_seq + LR_BN_MAXC) : nullptr;
+  return d;
+}
+
+void lrnde_ctx::bn_check() {
+  if (nranks <= 1 || !bn_seq) return;
+  int flag = 0;
+  LR_CUDA(cudaMemcpyAsync(&flag, bn_seq + LR_BN_MAXC, sizeof(int), cudaMemcpyDeviceToHost, stream));
+  LR_CUDA(cudaStreamSynchronize(stream));
+  if (flag) lr_fail(LRNDE_ESTATE, "BatchNorm statistics exchange: a rank of the data-parallel group did not arrive within ~10 s");
 }
 
 // ------------------------------------------------------------------------------------------
@@ -326,9 +351,9 @@ struct ConvEval {
 
   ConvEval(lrnde_ctx* c, const lrnde_model* mm, const float* p, int64_t b, bool vjp)
       : ctx(c), m(mm), ps(p), B(b), with_vjp(vjp) {
-    if (ctx->nranks > 1)
-      for (auto& Li : m->conv)
-        if (Li.bn) lr_fail(LRNDE_EINVAL, "conv dynamics with BatchNorm: batch statistics are not exchanged across ranks (single-GPU ctx only)");
+    for (auto& Li : m->conv)
+      if (Li.bn && Li.cout > LR_BN_MAXC && ctx->nranks > 1)
+        lr_fail(LRNDE_EINVAL, "BatchNorm with %d channels on a multi-rank ctx (the statistics exchange holds %d)", Li.cout, LR_BN_MAXC);
     L = (int)m->conv.size();
     HW = (size_t)m->Wd * m->Ht;
     z.assign(L, nullptr); ab.assign(L, nullptr); stat.assign(L, nullptr); pack.assign(L, nullptr); packT.assign(L, nullptr);
@@ -452,7 +477,7 @@ struct ConvEval {
         bn_finalize_kernel<<<Li.cout, 128, 0, ctx->stream>>>(spart, conv_nblk(Li.cout), Li.cout, (double)HW * (double)B,
                                                            ps + Li.g_off, 1e-5f, ab[l], stat[l],
                                                            bn_state ? bn_state + s_off[l] : nullptr, testmode,
-                                                           (update_state && bn_update) ? ncalls : 0, done);
+                                                           (update_state && bn_update) ? ncalls : 0, done, ctx->bn_dist());
         LR_COUNT(ctx);
       }
     }
@@ -512,7 +537,7 @@ struct ConvEval {
           bn_bwd_stats_kernel<<<dim3(Lp.cout, bnS), 256, 0, st>>>(G[cur], z[l - 1], ab[l - 1], stat[l - 1], Lp.act, Lp.cout, HW,
                                                                 (int)B, bnImg, bpart, done);
           LR_COUNT(ctx);
-          bn_bwd_finalize_kernel<<<(Lp.cout + 63) / 64, 64, 0, st>>>(bpart, bnS, Lp.cout, (double)HW * (double)B, coef, dgb, testmode, done);
+          bn_bwd_finalize_kernel<<<(Lp.cout + 63) / 64, 64, 0, st>>>(bpart, bnS, Lp.cout, (double)HW * (double)B, coef, dgb, testmode, done, ctx->bn_dist());
           LR_COUNT(ctx);
           wgrad_reduce_kernel<<<1, 256, 0, st>>>(dgb, 1, (size_t)2 * Lp.cout, dps_ptr ? dps_ptr + Lp.g_off : nullptr, dps_desc,
                                                dps_off + (size_t)Lp.g_off, p_scale, p_beta, done);
@@ -1775,6 +1800,7 @@ extern "C" int lrnde_ode_forward(lrnde_ctx* ctx, const lrnde_model* m, const lrn
     nf_reg = 9;  // 6 + integrator.sol.destats.nf (perform_step.jl:31)
   }
 
+  if (ev.conv) ctx->bn_check();
   stats->naccept = naccept;
   stats->nreject = nreject;
   stats->retcode = F.h.c.retcode;
@@ -2119,6 +2145,7 @@ extern "C" int lrnde_ode_backward(lrnde_ctx* ctx, const lrnde_model* m, lrnde_ta
     LR_CUDA(cudaMemcpyAsync(d_ps, dps_dev, sizeof(float) * P, cudaMemcpyDeviceToHost, st));
   }
   LR_CUDA(cudaStreamSynchronize(st));
+  if (ev.conv) ctx->bn_check();
   if (stats) {
     stats->nf_bwd = (nsteps >= 1) ? 3 + 6 * (nacc_b + nrej_b) + nbwd_stops : 0;
     stats->naccept_bwd = nacc_b;

@@ -134,7 +134,8 @@ LR_HD void lr_tsit5_interp(float th, float* b) {
 }
 
 // ---------------------------------------------------------------- controller state
-enum { LR_RET_SUCCESS = 0, LR_RET_MAXITERS = 1, LR_RET_DTMIN = 2, LR_RET_UNSTABLE = 3, LR_RET_TAPEFULL = 4 };
+enum { LR_RET_SUCCESS = 0, LR_RET_MAXITERS = 1, LR_RET_DTMIN = 2, LR_RET_UNSTABLE = 3, LR_RET_TAPEFULL = 4,
+       LR_RET_PEERTIMEOUT = 5 };
 
 struct LrCtrl {
   float t, dt, dtpropose, qold, q11, tstop, dtmax, dtmin;

@@ -337,7 +337,7 @@ __global__ void __launch_bounds__(256) conv3x3_wgrad_kernel(ConvWgP p) {
 __global__ void __launch_bounds__(128) bn_finalize_kernel(const float2* part, int nblk, int C, double count,
                                                           const float* gamma_beta, float eps, float* ab,
                                                           float* stat, float* running, int testmode, int update,
-                                                          const int* done) {
+                                                          const int* done, BnDist dist) {
   if (done && *done) return;
   __shared__ double s1[128], s2[128];
   const int c = blockIdx.x, tid = threadIdx.x;
@@ -363,6 +363,9 @@ __global__ void __launch_bounds__(128) bn_finalize_kernel(const float2* part, in
     __syncthreads();
   }
   if (tid == 0) {
+    // data-parallel group: the two sums and the element count are exchanged, so every rank
+    // normalises with (and tracks) the statistics of the whole batch
+    lr_bn_group_sum(dist, c, s1[0], s2[0], count);
     const double mean = s1[0] / count;
     double var = s2[0] / count - mean * mean;
     if (var < 0.0) var = 0.0;
@@ -422,16 +425,17 @@ __global__ void __launch_bounds__(256) bn_bwd_stats_kernel(const float* g, const
 
 // coef = [mean(ghat) ; mean(ghat xhat)], dgb = [d_gamma ; d_beta]
 __global__ void bn_bwd_finalize_kernel(const double2* part, int S, int C, double count, float* coef, float* dgb,
-                                       int testmode, const int* done) {
+                                       int testmode, const int* done, BnDist dist) {
   if (done && *done) return;
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   double t1 = 0.0, t2 = 0.0;
   for (int s = 0; s < S; ++s) { t1 += part[(size_t)c * S + s].x; t2 += part[(size_t)c * S + s].y; }
+  dgb[c] = (float)t2;            // parameter gradients stay per-rank partial sums (all-reduced once per iteration)
+  dgb[C + c] = (float)t1;
+  if (!testmode) lr_bn_group_sum(dist, c, t1, t2, count);   // the means are over the GLOBAL batch
   coef[c] = testmode ? 0.0f : (float)(t1 / count);          // testmode: the statistics are constants
   coef[C + c] = testmode ? 0.0f : (float)(t2 / count);
-  dgb[c] = (float)t2;
-  dgb[C + c] = (float)t1;
 }
 
 // g <- gamma invstd (ghat - m1 - xhat m2) in place; coef == nullptr: plain activation pullback g <- g act'(z)

@@ -150,7 +150,7 @@ static void bn_statistics(lrnde_ctx* ctx, int C, size_t HW, int64_t B, const flo
     LR_COUNT(ctx);
   }
   bn_finalize_kernel<<<C, 128, 0, st>>>((const float2*)part.p, S, C, (double)HW * (double)B, psd, 1e-5f, ab, stat, state,
-                                        testmode, update, nullptr);
+                                        testmode, update, nullptr, ctx->bn_dist());
   LR_COUNT(ctx);
 }
 }  // namespace convops
@@ -159,6 +159,7 @@ extern "C" int lrnde_batchnorm_forward(lrnde_ctx* ctx, int32_t C, int64_t HW, in
                                        int64_t B, float* state, int32_t testmode, int32_t host_buffers, float* y) {
   LR_API_BEGIN
   if (!ctx || !ps || !x || !y || C < 1 || HW < 1 || B < 1) lr_fail(LRNDE_EINVAL, "lrnde_batchnorm_forward: bad args");
+  if (ctx->nranks > 1 && C > LR_BN_MAXC) lr_fail(LRNDE_EINVAL, "BatchNorm with %d channels on a multi-rank ctx (max %d)", C, LR_BN_MAXC);
   if (testmode && !state) lr_fail(LRNDE_EINVAL, "lrnde_batchnorm_forward: testmode needs the running statistics");
   LR_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
@@ -182,6 +183,7 @@ extern "C" int lrnde_batchnorm_forward(lrnde_ctx* ctx, int32_t C, int64_t HW, in
     if (state && !testmode) LR_CUDA(cudaMemcpyAsync(state, sd, 8 * C, cudaMemcpyDeviceToHost, st));
   }
   LR_CUDA(cudaStreamSynchronize(st));
+  ctx->bn_check();
   LR_API_END
 }
 
@@ -217,7 +219,7 @@ extern "C" int lrnde_batchnorm_backward(lrnde_ctx* ctx, int32_t C, int64_t HW, i
   bn_bwd_stats_kernel<<<dim3(C, S), 256, 0, st>>>(gd, xd, ab.p, stat.p, a, C, (size_t)HW, (int)B, img, (double2*)bpart.p, nullptr);
   LR_COUNT(ctx);
   bn_bwd_finalize_kernel<<<(C + 63) / 64, 64, 0, st>>>((const double2*)bpart.p, S, C, (double)HW * (double)B, coef.p, dgbd,
-                                                     testmode, nullptr);
+                                                     testmode, nullptr, ctx->bn_dist());
   LR_COUNT(ctx);
   bn_bwd_apply_kernel<<<lr_ew_blocks(n), 256, 0, st>>>(gd, xd, ab.p, stat.p, coef.p, a, C, (size_t)HW, n, nullptr);
   LR_COUNT(ctx);
@@ -227,5 +229,6 @@ extern "C" int lrnde_batchnorm_backward(lrnde_ctx* ctx, int32_t C, int64_t HW, i
     LR_CUDA(cudaMemcpyAsync(d_ps, dgbd, 8 * C, cudaMemcpyDeviceToHost, st));
   }
   LR_CUDA(cudaStreamSynchronize(st));
+  ctx->bn_check();
   LR_API_END
 }

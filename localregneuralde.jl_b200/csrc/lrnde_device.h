@@ -38,10 +38,64 @@ struct LrMailbox {
 // stage[parity][3][LR_MU_MAX] floats: per-rank partial batch sums of the mu block that the
 // adjoint's error norm needs as GLOBAL values.
 #define LR_MU_MAX (1 << 20)
-#define LR_MAILBOX_BYTES (sizeof(LrMailbox) + sizeof(float) * 2 * 3 * (size_t)LR_MU_MAX)
+// ... followed by the BatchNorm area: per-channel pairs of batch sums (sum x, sum x^2 of the forward; sum ghat,
+// sum ghat xhat of the pullback) that conv dynamics with BatchNorm need as GLOBAL values (SURVEY 8e (4),
+// experiments/src/construct.jl:213-216).  val[seq & 1][r][c], flag[seq & 1][r][c] = seq + 1 once visible; every channel
+// counts its own exchanges (lrnde_ctx::bn_seq), so the C blocks of a finalize kernel exchange independently.
+#define LR_BN_MAXC 256
+struct LrBnBox {
+  double val[2][LR_MAX_RANKS][LR_BN_MAXC][4];   // (sum 1, sum 2, element count of the rank, unused)
+  unsigned long long flag[2][LR_MAX_RANKS][LR_BN_MAXC];
+};
+#define LR_MU_STAGE_BYTES (sizeof(float) * 2 * 3 * (size_t)LR_MU_MAX)
+#define LR_MAILBOX_BYTES (sizeof(LrMailbox) + LR_MU_STAGE_BYTES + sizeof(LrBnBox))
 __host__ __device__ inline float* lr_mbox_stage(LrMailbox* m, int parity, int vec) {
   return reinterpret_cast<float*>(m + 1) + ((size_t)parity * 3 + vec) * LR_MU_MAX;
 }
+__host__ __device__ inline LrBnBox* lr_mbox_bn(LrMailbox* m) {
+  return reinterpret_cast<LrBnBox*>(reinterpret_cast<char*>(m + 1) + LR_MU_STAGE_BYTES);
+}
+// the data-parallel group as a kernel argument of the BatchNorm finalize kernels (nranks <= 1: no exchange)
+struct BnDist {
+  LrMailbox* mbox[LR_MAX_RANKS];
+  int rank, nranks;
+  unsigned long long* seq;   // [LR_BN_MAXC] exchanges done per channel (device memory of this rank)
+  int* timed_out;            // set when a peer never arrived (~10 s): the host call fails with LRNDE_ESTATE
+};
+#ifdef __CUDACC__
+// (a, b, count) <- sums over ranks in rank order (identical bits on every rank).  One calling thread per channel.
+__device__ inline void lr_bn_group_sum(const BnDist& d, int c, double& a, double& b, double& count) {
+  if (d.nranks <= 1) return;
+  const unsigned long long seq = d.seq[c];
+  d.seq[c] = seq + 1;
+  const int par = (int)(seq & 1ull);
+  for (int r = 0; r < d.nranks; ++r) {
+    volatile double* dst = lr_mbox_bn(d.mbox[r])->val[par][d.rank][c];
+    dst[0] = a; dst[1] = b; dst[2] = count;
+  }
+  __threadfence_system();
+  for (int r = 0; r < d.nranks; ++r) {
+    volatile unsigned long long* f = &lr_mbox_bn(d.mbox[r])->flag[par][d.rank][c];
+    *f = seq + 1;
+  }
+  LrBnBox* mine = lr_mbox_bn(d.mbox[d.rank]);
+  for (int r = 0; r < d.nranks; ++r) {
+    volatile unsigned long long* f = &mine->flag[par][r][c];
+    long long spins = 0;
+    while (*f != seq + 1) {
+      __nanosleep(40);
+      if (++spins > (1ll << 26)) { if (d.timed_out) *d.timed_out = 1; break; }
+    }
+  }
+  __threadfence_system();
+  double sa = 0.0, sb = 0.0, sc = 0.0;
+  for (int r = 0; r < d.nranks; ++r) {
+    const volatile double* src = mine->val[par][r][c];
+    sa += src[0]; sb += src[1]; sc += src[2];
+  }
+  a = sa; b = sb; count = sc;
+}
+#endif
 
 struct SolveDev {
   LrCtrl c;
@@ -106,6 +160,16 @@ struct SolveDev {
   LinComb cur;      // the current state as a descriptor (base = U(slot), t = c.t): written by k1_desc_kernel
   int lat_mu_row;   // latent-space adjoint: the mu block's residual partial sums sit in partials[LR_ERR_BLOCKS ...]
 };
+// a rank of the group never published its value: the solve ends with retcode PeerTimeout on this rank (the
+// controller sees `failed`, closes the WHILE loop, and the host reports the retcode) instead of spinning forever
+#ifdef __CUDACC__
+__device__ inline void lr_peer_timeout(SolveDev* S) {
+  S->failed = 1;
+  S->done = 1;
+  if (S->c.retcode == LR_RET_SUCCESS) S->c.retcode = LR_RET_PEERTIMEOUT;
+}
+#endif
+
 #define LR_ZROW 128
 // the latent image of a tape array (p must point at the start of an array of this solve's tape)
 __host__ __device__ inline float* lr_zof(const SolveDev* S, const float* p) {

@@ -49,6 +49,9 @@ struct lrnde_ctx {
   LrMailbox* peer_mbox[LR_MAX_RANKS] = {nullptr};
   unsigned long long seq = 0;                 // next collective sequence number
   unsigned long long mseq = 0;                // next vector-exchange sequence number
+  unsigned long long* bn_seq = nullptr;       // device: per-channel BatchNorm exchange counters + the time-out flag
+  BnDist bn_dist();                           // kernel argument of the BatchNorm finalize kernels
+  void bn_check();                            // after a sync: fails the call when an exchange timed out
 
   void* alloc(size_t bytes);
   void release(void* p);

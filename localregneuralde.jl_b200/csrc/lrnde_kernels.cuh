@@ -549,7 +549,12 @@ __device__ inline void lr_group_sum(SolveDev* S, double* v) {
   LrMailbox* mine = S->mbox[me];
   for (int r = 0; r < S->nranks; ++r) {
     volatile unsigned long long* f = &mine->flag[par][r];
-    while (*f != seq + 1) { __nanosleep(20); }
+    long long spins = 0;
+    while (*f != seq + 1) {
+      __nanosleep(20);
+      if (++spins > (1ll << 27)) { lr_peer_timeout(S); break; }   // a peer never arrived (~10 s): fail the solve instead of hanging
+    }
+    if (S->failed) break;
   }
   __threadfence_system();
   for (int k = 0; k < 4; ++k) {
@@ -613,7 +618,12 @@ __global__ void __launch_bounds__(256) mu_gather_kernel(SolveDev* S, int nvec, c
   if (threadIdx.x == 0) {
     for (int r = 0; r < S->nranks; ++r) {
       volatile unsigned long long* f = &mine->mflag[par][r];
-      while (*f != S->mseq + 1) { __nanosleep(40); }
+      long long spins = 0;
+      while (*f != S->mseq + 1) {
+        __nanosleep(40);
+        if (++spins > (1ll << 26)) { lr_peer_timeout(S); break; }
+      }
+      if (S->failed) break;
     }
     __threadfence_system();
   }
@@ -849,6 +859,7 @@ __global__ void controller_kernel(SolveDev* S) {
   v[2] = v[3] = 0.0;
   if (S->lat_mu_row && S->reduce_mu && S->nranks > 1) S->mseq += 1;   // next vector exchange uses the other parity
   { double w[4] = {v[0], 0, 0, 0}; lr_group_sum(S, w); v[0] = w[0] + v[1]; }
+  if (S->failed) { S->done = 1; lr_set_cond(S); return; }   // peer timeout (or a failure flagged by a step kernel)
   float EEst = sqrtf((float)v[0] / (float)(double)S->total_len);
   const float t_before = S->c.t, dt_before = S->c.dt;
   float dt_taken = 0.0f;

@@ -78,6 +78,45 @@ for prec, tol in (("fp32", 1e-6), ("tf32x3", 1e-5)):       # tf32x3: the latent-
           f"bwd attempts {len(s['bacc'])}/{len(d['bacc'])} same={same_b} u {e_u:.2e} d_x {e_dx:.2e} d_ps(allreduced) {e_dps:.2e} "
           f"reg {e_reg:.2e} allreduce vs nccl {e_ar:.2e} identical bits on all ranks {same_bits} -> {'ok' if good else 'MISMATCH'}",
           flush=True)
+
+# ---- conv dynamics with BatchNorm (experiments/src/construct.jl:213-216): the batch statistics of every
+# BatchNorm evaluation (forward sums, pullback sums, running statistics) are exchanged through the peer mailbox, so the
+# sharded run normalises with the statistics of the whole batch exactly like the single-GPU run
+from oracle.lrnde_conv_oracle import ConvLayer, ConvNet, glorot_uniform_conv_params  # noqa: E402
+
+cl = [(2, 5, True, "gelu"), (5, 4, True, "gelu"), (4, 2, False, "identity")]
+Wd, Ht, Bc = 8, 4, 3 * world
+onet = ConvNet([ConvLayer(*l) for l in cl], Wd, Ht, time_dependent=True)
+cchain = pkg.TDConvChain(pkg.ConvChain(*[pkg.Conv(*l) for l in cl], width=Wd, height=Ht))
+rng = np.random.default_rng(11)
+cps = glorot_uniform_conv_params(onet, rng, jitter=0.2)
+cx = rng.standard_normal((onet.state_dims, Bc)).astype(np.float32)
+cc = (rng.standard_normal((onet.state_dims, Bc)) / Bc).astype(np.float32)
+ctx_dp.setup_group(rank, world, Bc, gather)
+lo, hi = rank * Bc // world, (rank + 1) * Bc // world
+res = {}
+for name, ctx, xs, cs in (("single", ctx_1, cx, cc), ("dp", ctx_dp, cx[:, lo:hi], cc[:, lo:hi])):
+    node = pkg.NeuralODE(cchain, ctx=ctx, regularize="unbiased", abstol=1e-3, reltol=1e-3, maxiters=1000, save_start=False)
+    sol, st2 = node(np.ascontiguousarray(xs), cps, node.initialstates(np.random.default_rng(5)))
+    d_x, d_ps = node.backward(sol, [None, np.ascontiguousarray(cs)], 1.5)
+    t, dt, ee, acc = sol.step_log(0)
+    bt, bdt, bee, bacc = sol.step_log(1)
+    res[name] = dict(u=np.asarray(sol.u[-1]).copy(), reg=float(st2["reg_val"]), nfe=st2["nfe"], d_x=np.asarray(d_x).copy(),
+                     d_ps=np.asarray(d_ps).copy(), acc=acc, bacc=bacc, running=np.asarray(st2["model"]["running"]).copy())
+    sol.free()
+g = torch.from_numpy(res["dp"]["d_ps"]).to(dev)
+pkg._lib.check(pkg.lib().lrnde_allreduce_sum(ctx_dp._h, g.data_ptr(), g.numel()))
+s, d = res["single"], res["dp"]
+same_f = np.array_equal(s["acc"], d["acc"]) and s["nfe"] == d["nfe"]
+same_b = np.array_equal(s["bacc"], d["bacc"])
+e_u, e_dx = rel(d["u"], s["u"][:, lo:hi]), rel(d["d_x"], s["d_x"][:, lo:hi])
+e_dps, e_run = rel(g.cpu().numpy(), s["d_ps"]), rel(d["running"], s["running"])
+e_reg = abs(d["reg"] - s["reg"]) / abs(s["reg"])
+good = same_f and same_b and e_u < 1e-4 and e_dx < 1e-3 and e_dps < 1e-3 and e_run < 1e-4 and e_reg < 1e-3
+ok = ok and good
+print(f"[multi-gpu rank {rank}/{world}] conv+BatchNorm fwd attempts {len(s['acc'])}/{len(d['acc'])} same={same_f} bwd attempts "
+      f"{len(s['bacc'])}/{len(d['bacc'])} same={same_b} u {e_u:.2e} d_x {e_dx:.2e} d_ps(allreduced) {e_dps:.2e} running stats "
+      f"{e_run:.2e} reg {e_reg:.2e} -> {'ok' if good else 'MISMATCH'}", flush=True)
 dist.barrier()
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)
