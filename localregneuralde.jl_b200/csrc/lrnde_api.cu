@@ -23,6 +23,9 @@
 #include "lrnde_conv.cuh"
 #include "lrnde_fused.h"
 #include "lrnde_adjoint.h"
+#include "lrnde_regrev.cuh"
+
+static bool lr_reg_hidden_eligible(const lrnde_model* m, int reg_type);
 
 // ------------------------------------------------------------------------------------------
 // errors
@@ -1251,6 +1254,7 @@ struct lrnde_tape {
   float* ps = nullptr;  // device copy of the parameters the forward used
   float* bn_state = nullptr;  // conv dynamics: device copy of st.model the forward normalised with (testmode)
   float* Mz = nullptr;        // latent-space engines: W1 W2a of the parameters the forward used ([128][128])
+  int reg_hidden = 0;         // the regulariser integrator kept its hidden images: its reverse pass runs in hidden space
   std::unique_ptr<Solver> fwd;
   std::unique_ptr<Solver> reg;  // regulariser integrator (2-slot ring), reg modes only
   std::vector<float> fts;       // host copy of accepted times
@@ -1767,7 +1771,10 @@ extern "C" int lrnde_ode_forward(lrnde_ctx* ctx, const lrnde_model* m, const lrn
     Solver& R = *T->reg;
     if (ctx->nranks > 1) R.h.total_len = F.h.total_len;
     R.init_ctrl(t1, o->t2, o->t2, o->maxiters, o->pow_mode, o->abstol, o->reltol);
-    if (fe) R.enable_latent(fe->zlen());
+    // hidden images [h_j ; t_j ; 1] of the regulariser's stages for the hidden-space reverse pass (lrnde_regrev.cuh)
+    const bool reg_hidden = fe && o->keep_tape && T->Mz && lr_reg_hidden_eligible(m, o->reg_type);
+    if (fe) R.enable_latent(fe->zlen(), reg_hidden);
+    T->reg_hidden = reg_hidden ? 1 : 0;
     R.upload();
     LinComb u1;
     DevBuf dd(ctx, sizeof(LinComb) / 4 + 1);
@@ -1890,6 +1897,139 @@ extern "C" int lrnde_profile_adjoint_last(float* us5) {
   for (int k = 0; k < 5; ++k) us5[k] = g_adj_profile_us[k];
   return LRNDE_OK;
 }
+
+// ------------------------------------------------------------------------------------------
+// Reverse pass of the regulariser step in hidden space (lrnde_regrev.cuh): 2-layer TD-MLP with tanh,
+// regularize_type = :error_estimate.  dps += d_reg * d reg_val / d ps.
+// ------------------------------------------------------------------------------------------
+static bool lr_reg_hidden_eligible(const lrnde_model* m, int reg_type) {
+  if (getenv("LRNDE_NO_HIDDEN_REG")) return false;
+  FusedShape sh;
+  if (reg_type != LRNDE_REGTYPE_ERROR || !lrf_shape(m, &sh)) return false;
+  if (m->layers.size() != 2 || m->layers[0].act != ACT_TANH || m->layers[1].act != ACT_IDENTITY) return false;
+  if (m->input_act != ACT_IDENTITY) return false;
+  const LayerInfo &L1 = m->layers[0], &L2 = m->layers[1];
+  // the layer blocks must be [weight | bias] back to back (ComponentArray order), D a multiple of 4 (16-byte rows)
+  if (L1.b_off != L1.w_off + (int64_t)L1.out * (L1.in + m->td) || L2.b_off != L2.w_off + (int64_t)L2.out * (L2.in + m->td)) return false;
+  return sh.D % 4 == 0 && sh.H % 4 == 0 && sh.Kaug + m->td + 1 <= 104;
+}
+
+static void lr_wgrad_launch(lrnde_ctx* ctx, const umma::WgOperand& P, const umma::WgOperand& Q, int transposed, int ldo, int64_t N,
+                            float* part, size_t block, int nsplit, int chunk, int passes, const int* done) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    LR_CUDA(cudaFuncSetAttribute(umma::wgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, umma::wgrad_smem()));
+    LR_CUDA(cudaFuncSetAttribute(umma::wgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, umma::wgrad_smem()));
+    attr_set = true;
+  }
+  umma::WgradUP w;
+  memset(&w, 0, sizeof(w));
+  w.P = P; w.Q = Q; w.transposed = transposed; w.ldo = ldo;
+  w.B = (int)N; w.chunk = chunk; w.part = part; w.block = block; w.passes = passes; w.tdesc = nullptr; w.done = done;
+  dim3 g((P.rows + 127) / 128, nsplit);
+  const bool lean = P.rows % 4 == 0 && Q.rows % 4 == 0 && P.ld % 4 == 0 && Q.ld % 4 == 0 &&
+                    (((uintptr_t)P.ptr) & 15) == 0 && (((uintptr_t)Q.ptr) & 15) == 0;
+  if (lean) umma::wgrad_kernel<false><<<g, umma::kThreads, umma::wgrad_smem(), ctx->stream>>>(w);
+  else umma::wgrad_kernel<true><<<g, umma::kThreads, umma::wgrad_smem(), ctx->stream>>>(w);
+  LR_COUNT(ctx);
+}
+// batch split of a contraction over N samples with n_mt row tiles: one wave of CTAs, chunks of a multiple of 32
+static void lr_wgrad_split(int64_t N, int n_mt, int* nsplit, int* chunk) {
+  int us = std::max(1, std::min(64, 148 / n_mt));
+  int uc = (int)((N + us - 1) / us);
+  uc = std::max(32, ((uc + 31) / 32) * 32);
+  *nsplit = (int)((N + uc - 1) / uc);
+  *chunk = uc;
+}
+
+static void lr_reg_pullback_hidden(lrnde_ctx* ctx, const lrnde_model* m, lrnde_tape* T, MlpEval& ev, float d_reg, float* dps_dev) {
+  cudaStream_t st = ctx->stream;
+  Solver& R = *T->reg;
+  const int64_t B = T->B;
+  FusedShape sh;
+  lrf_shape(m, &sh);
+  const int D = sh.D, H = sh.H, Kaug = sh.Kaug, td = m->td;
+  const int KP = 104;                         // rows of the padded hidden operands (multiple of 4 >= Kaug + td + 1)
+  const size_t DB = (size_t)D * B, ZB = (size_t)LR_ZROW * B;
+  const LayerInfo &L1 = m->layers[0], &L2 = m->layers[1];
+  const int* done = nullptr;
+
+  // (1) G, Q
+  DevBuf gq(ctx, 2 * DB);
+  RegSeedGQP sp;
+  sp.R = R.dev; sp.d_reg = d_reg; sp.gq = gq.p; sp.DB = DB;
+  reg_seed_gq_kernel<<<lr_ew_blocks(DB), 256, 0, st>>>(sp);
+  LR_COUNT(ctx);
+  // (2) A = W2^T G, Bq = W2^T Q: one GEMM over 2B columns
+  DevBuf ab(ctx, 2 * ZB);
+  {
+    DenseP p;
+    memset(&p, 0, sizeof(p));
+    p.A = ev.WT[1]; p.lda = L2.in; p.M = L2.in; p.K = L2.out; p.td = 0; p.bias = 0;
+    p.X = gq.p; p.ldx = L2.out; p.N = (int)(2 * B);
+    p.Y = ab.p; p.ldy = LR_ZROW; p.act = ACT_IDENTITY; p.dact = -1; p.out_scale = 1.0f; p.done = done;
+    ev.dense(p, ev.use_umma ? ev.packWT[1] : nullptr);
+  }
+  // (3) the stage cotangents in hidden space
+  DevBuf work(ctx, (6 + 6 + 1 + 1 + 2) * ZB);
+  RegRevP rp;
+  memset(&rp, 0, sizeof(rp));
+  rp.R = R.dev; rp.Mz = T->Mz; rp.ab = ab.p;
+  for (int j = 1; j <= 6; ++j) rp.hh[j - 1] = R.htape + (size_t)j * R.h.zlen;     // K(0, j)
+  rp.hh[6] = R.htape + (size_t)8 * R.h.zlen;                                       // k7 = K(1, 1)
+  rp.del = work.p; rp.cc = work.p + 6 * ZB; rp.dsum = work.p + 12 * ZB; rp.uv = work.p + 13 * ZB; rp.hba = work.p + 14 * ZB;
+  rp.B = (int)B; rp.H = H; rp.Kaug = Kaug; rp.td = td;
+  for (int r = 0; r < 6; ++r) for (int i = 0; i < 6; ++i) rp.a[r][i] = lr_tsit5_a(r, i);
+  for (int i = 0; i < 7; ++i) rp.bt[i] = lr_tsit5_btilde(i);
+  {
+    const size_t smem = sizeof(float) * ((size_t)H * 128 + 2 * 128 * 4);
+    static bool attr_set = false;
+    if (!attr_set) {
+      LR_CUDA(cudaFuncSetAttribute(reg_rev_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 128 * 4 + 4096));
+      attr_set = true;
+    }
+    const int npairs = (int)((B + 2 * kRegRevS - 1) / (2 * kRegRevS));
+    reg_rev_chain_kernel<<<std::min(npairs, 2 * 148), 256, smem, st>>>(rp);
+    LR_COUNT(ctx);
+  }
+  // (4) the four batch contractions on the tensor cores (fixed split, fixed-order reduce in (5))
+  int s1, c1, s2, c2, s3, c3, s4, c4;
+  lr_wgrad_split(2 * B, (D + 127) / 128, &s1, &c1);
+  lr_wgrad_split(B, (D + 127) / 128, &s2, &c2);
+  lr_wgrad_split(6 * B, 1, &s3, &c3);
+  lr_wgrad_split(B, 1, &s4, &c4);
+  const size_t b1 = (size_t)D * KP, b2 = (size_t)H * D, b3 = (size_t)H * KP;
+  DevBuf part(ctx, s1 * b1 + s2 * b2 + (size_t)(s3 + s4) * b3 + 2 * (size_t)H * Kaug);
+  float* t1 = part.p; float* t2 = t1 + s1 * b1; float* ssb = t2 + s2 * b2; float* uhb = ssb + s3 * b3; float* smb = uhb + s4 * b3;
+  const float* uprev = R.tape;   // U(0) of the regulariser integrator
+  {
+    umma::WgOperand oG = {gq.p, D, D, 0, 0, 0};
+    umma::WgOperand oHBA = {rp.hba, LR_ZROW, KP, 0, 0, 0};
+    lr_wgrad_launch(ctx, oG, oHBA, 0, D, 2 * B, t1, b1, s1, c1, ev.passes, done);
+    umma::WgOperand oU = {uprev, D, D, 0, 0, 0};
+    umma::WgOperand oDS = {rp.dsum, LR_ZROW, H, 0, 0, 0};
+    lr_wgrad_launch(ctx, oU, oDS, 1, H, B, t2, b2, s2, c2, ev.passes, done);
+    umma::WgOperand oCC = {rp.cc, LR_ZROW, KP, 0, 0, 0};
+    umma::WgOperand oDEL = {rp.del, LR_ZROW, H, 0, 0, 0};
+    lr_wgrad_launch(ctx, oCC, oDEL, 1, H, 6 * B, ssb, b3, s3, c3, ev.passes, done);
+    umma::WgOperand oH1 = {rp.hh[0], LR_ZROW, KP, 0, 0, 0};
+    umma::WgOperand oUV = {rp.uv, LR_ZROW, H, 0, 0, 0};
+    lr_wgrad_launch(ctx, oH1, oUV, 1, H, B, uhb, b3, s4, c4, ev.passes, done);
+  }
+  // (5) d_ps += ...
+  RegAsmP ap;
+  memset(&ap, 0, sizeof(ap));
+  ap.R = R.dev; ap.ps = T->ps; ap.dps = dps_dev; ap.t1 = t1; ap.t2 = t2; ap.ss = ssb; ap.uh = uhb; ap.sm = smb;
+  ap.S1 = s1; ap.S2 = s2; ap.S3 = s3; ap.S4 = s4; ap.D = D; ap.H = H; ap.Kaug = Kaug; ap.td = td; ap.KP = KP;
+  ap.w1_off = (long)L1.w_off; ap.w2_off = (long)L2.w_off;
+  reg_ss_kernel<<<(H * Kaug + 255) / 256, 256, 0, st>>>(ap);
+  LR_COUNT(ctx);
+  reg_assemble_kernel<<<lr_ew_blocks((size_t)D * Kaug + (size_t)H * D), 256, 0, st>>>(ap);
+  LR_COUNT(ctx);
+  LR_CHECK_LAUNCH();
+  LR_CUDA(cudaStreamSynchronize(st));   // the scratch buffers go back to the pool
+}
+
 
 extern "C" int lrnde_ode_backward(lrnde_ctx* ctx, const lrnde_model* m, lrnde_tape* T,
                                   const float* d_u_save, float d_reg, float* d_ps, float* d_x,
@@ -2111,7 +2251,9 @@ extern "C" int lrnde_ode_backward(lrnde_ctx* ctx, const lrnde_model* m, lrnde_ta
 
   const long tb_adj = lr_now_us();
   // ---- reverse pass of the regulariser step: gradient w.r.t. ps only
-  if (T->reg && d_reg != 0.0f) {
+  if (T->reg && d_reg != 0.0f && T->reg_hidden && ev.use_umma && !getenv("LRNDE_NO_HIDDEN_REG")) {
+    lr_reg_pullback_hidden(ctx, m, T, ev, d_reg, dps_dev);
+  } else if (T->reg && d_reg != 0.0f) {
     Solver& R = *T->reg;
     DevBuf work(ctx, 9 * DB);
     RegSeedP sp;
