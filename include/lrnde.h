@@ -377,6 +377,15 @@ int lrnde_classifier_grad(lrnde_ctx* ctx, const lrnde_model* m, const lrnde_opts
                           float w_reg, float grad_scale, float* loss_ce, float* d_ps, float* d_Wc,
                           lrnde_stats* stats);
 
+/* Input pipeline of lrnde_classifier_grad with host buffers: starts the host -> device copy of a batch (x [D,B] and
+ * its 0-based labels, PINNED host memory for the copy to overlap) on the library's copy stream and returns at once
+ * (the copy is queued behind the next lrnde_classifier_grad's own small parameter copies, or at the next prefetch).
+ * A later lrnde_classifier_grad called with the same host pointers and B uses the staged device copy instead of
+ * copying inside the call.  Two batches can be in flight (the one being consumed and the next one); the host
+ * buffers must stay unchanged until the consuming call returns.  The reference's counterpart is the DataLoader
+ * batch moved with `gpu` before run_training_step (experiments/src/utils.jl:106-115). */
+int lrnde_prefetch_inputs(lrnde_ctx* ctx, const float* x, const int32_t* labels, int64_t B, int32_t D);
+
 /* Microseconds per launch of one attempt of the latent-space adjoint {chain, lambda GEMM, pairacc, reduce + mu,
  * whole attempt}, measured with CUDA events by the last lrnde_ode_backward that ran with the environment variable
  * LRNDE_PROFILE_ADJ=<iterations> set (roofline probe of bench.py). */

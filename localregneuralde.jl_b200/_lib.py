@@ -87,7 +87,7 @@ SYMBOLS = [
     "lrnde_gru_backward", "lrnde_gru_tape_free", "lrnde_mlp_forward", "lrnde_mlp_backward",
     "lrnde_reparameterize", "lrnde_latent_loss", "lrnde_conv_model_create", "lrnde_dynamics_vjp",
     "lrnde_conv2d_forward", "lrnde_conv2d_backward", "lrnde_batchnorm_forward", "lrnde_batchnorm_backward",
-    "lrnde_opt_step", "lrnde_allreduce_sum", "lrnde_ode_saved_states", "lrnde_classifier_grad",
+    "lrnde_opt_step", "lrnde_allreduce_sum", "lrnde_ode_saved_states", "lrnde_classifier_grad", "lrnde_prefetch_inputs",
     "lrnde_profile_adjoint_last", "lrnde_profile_step",
 ]
 
@@ -158,6 +158,7 @@ def lib():
     L.lrnde_opt_step.argtypes = [vp, i32, vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i32]
     L.lrnde_allreduce_sum.argtypes = [vp, vp, i64]
     L.lrnde_ode_saved_states.argtypes = [vp, vp, vp, vp, i64, vp]
+    L.lrnde_prefetch_inputs.argtypes = [vp, vp, vp, i64, i32]
     L.lrnde_classifier_grad.argtypes = [vp, vp, C.POINTER(Opts), vp, vp, vp, vp, i64, i32, f32, f32, vp, vp, vp,
                                         C.POINTER(Stats)]
     L.lrnde_profile_adjoint_last.argtypes = [vp]

@@ -53,6 +53,18 @@ struct lrnde_ctx {
   BnDist bn_dist();                           // kernel argument of the BatchNorm finalize kernels
   void bn_check();                            // after a sync: fails the call when an exchange timed out
 
+  // input prefetch of lrnde_classifier_grad (lrnde_prefetch_inputs): two device slots filled on a copy stream
+  struct Staged {
+    float* x = nullptr; int32_t* y = nullptr; size_t cap_x = 0, cap_y = 0;
+    const void* key_x = nullptr; const void* key_y = nullptr; size_t nx = 0, ny = 0;
+    unsigned long long seq = 0; bool ready = false; cudaEvent_t ev = nullptr;
+  } staged[2];
+  cudaStream_t copy_stream = nullptr;
+  unsigned long long staged_seq = 0;
+  // a prefetch request whose copy has not been issued yet: the copy engine is FIFO across streams, so the big copy
+  // is queued AFTER the consuming call's own small parameter copies (lrnde_classifier_grad flushes it)
+  struct { const float* x = nullptr; const int32_t* y = nullptr; int64_t B = 0; int32_t D = 0; bool valid = false; } pending;
+
   void* alloc(size_t bytes);
   void release(void* p);
   void release_all_unused();

@@ -707,3 +707,13 @@ def test_classifier_grad_is_the_layer_by_layer_iteration(pkg):
     assert abs(stats.reg_val - float(st2["reg_val"])) <= 1e-6 * abs(float(st2["reg_val"]))
     assert rel(g_ps, d_ps.cpu().numpy()) < 1e-6 and rel(g_wc, d_Wc.cpu().numpy()) < 1e-6
     sol.free()
+    # input pipeline: the batch staged by lrnde_prefetch_inputs (pinned host memory, copy stream) gives the same bits
+    xp = torch.from_numpy(x).pin_memory()
+    yp = torch.from_numpy(y).pin_memory()
+    pkg._lib.check(pkg.lib().lrnde_prefetch_inputs(ctx._h, xp.data_ptr(), yp.data_ptr(), B, Dd))
+    g_ps2, g_wc2 = np.empty_like(ps), np.empty_like(Wc)
+    loss3 = C.c_float()
+    pkg._lib.check(pkg.lib().lrnde_classifier_grad(ctx._h, ctx.model_handle(chain), C.byref(o), ps.ctypes.data, Wc.ctypes.data,
+                                                   xp.data_ptr(), yp.data_ptr(), B, Cn, 2.5, 1.0, C.byref(loss3),
+                                                   g_ps2.ctypes.data, g_wc2.ctypes.data, C.byref(stats)))
+    assert loss3.value == loss2.value and np.array_equal(g_ps2, g_ps) and np.array_equal(g_wc2, g_wc)
