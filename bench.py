@@ -308,10 +308,11 @@ def _native_loop(pkg, torch, dist, args, B, world, rank, dev, ctx, steps, warmup
         st_e = step(0, st, False)                           # warm
         ms_e, _, _ = timed(e2e_steps, st_e, False, 1)
         ms_e /= e2e_steps
+    e2e_info = dict(info) if e2e_steps else {}
     PW = NCLS * D + NCLS
     h2d = 4 * (B * D + B + P + PW) + 4 * (P + PW)            # x, labels, ps, Wc in; the host gradients back up for the optimiser
     d2h = 4 * (P + PW + 1) + 4 * (P + PW)                    # d_ps, d_Wc, loss out; the updated parameters
-    return dict(ms=ms_total / steps, ms_total=ms_total, ms_e2e=ms_e, info=fwd_info, launches=n_launch, nfe_sum=nfe_sum,
+    return dict(ms=ms_total / steps, ms_total=ms_total, ms_e2e=ms_e, info=fwd_info, e2e_info=e2e_info, launches=n_launch, nfe_sum=nfe_sum,
                 h2d=h2d, d2h=d2h, node=node, chain=chain, ps=ps, xb=xb, P=P)
 
 
@@ -359,6 +360,7 @@ def run_native(args):
     value = B * world / (ms / 1e3)
     e2e = {"value": B * world / (ms_e / 1e3), "unit": "samples/s", "h2d_bytes_per_step": r["h2d"],
            "d2h_bytes_per_step": r["d2h"], "ms_per_step": ms_e, "steps": e2e_steps,
+           "last_step": {k: r["e2e_info"].get(k) for k in ("naccept", "nacc_b", "nfe", "phases_us")},
            "call": "lrnde_classifier_grad with host buffers (x, labels, ps, Wc in; loss, d_ps, d_Wc out) + gradient "
                    "all-reduce + Adam; pinned host memory; every step also issues lrnde_prefetch_inputs for the next batch "
                    "(one x + labels host-to-device copy per step, on the library's copy stream, overlapped with the step)"}
@@ -888,7 +890,7 @@ def main():
     ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "tf32x3", "tf32"])
     ap.add_argument("--loop-mode", type=int, default=0)
     ap.add_argument("--ref-batch", type=int, default=512, help="bounded sample for the CPU reference")
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the batch-128 (BASELINE configs[0]) block")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],

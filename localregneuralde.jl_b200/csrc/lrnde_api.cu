@@ -163,6 +163,7 @@ extern "C" int lrnde_ctx_destroy(lrnde_ctx* c) {
     if (sg.ev) cudaEventDestroy(sg.ev);
   }
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  for (auto& cg : c->graph_cache) { cudaGraphExecDestroy(cg.exec); cudaGraphDestroy(cg.graph); }
   if (c->pinned) cudaFreeHost(c->pinned);
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
@@ -1060,6 +1061,7 @@ struct Solver {
   cudaGraph_t while_graph = nullptr, body_graph = nullptr;
   cudaGraphExec_t while_exec = nullptr, body_exec = nullptr;
   long body_nodes = 0;
+  bool graph_cached = false;   // while_graph / while_exec belong to ctx->graph_cache
   std::function<void()> body;
 
   Solver(lrnde_ctx* c, size_t len, size_t lam_len, int cap, int ring, int logcap) : ctx(c) {
@@ -1090,9 +1092,9 @@ struct Solver {
     for (int r = 0; r < LR_MAX_RANKS; ++r) h.mbox[r] = ctx->peer_mbox[r];
   }
   ~Solver() {
-    if (while_exec) cudaGraphExecDestroy(while_exec);
+    if (while_exec && !graph_cached) cudaGraphExecDestroy(while_exec);
     if (body_exec) cudaGraphExecDestroy(body_exec);
-    if (while_graph) cudaGraphDestroy(while_graph);
+    if (while_graph && !graph_cached) cudaGraphDestroy(while_graph);
     if (body_graph) cudaGraphDestroy(body_graph);
     ctx->release(dev);
     ctx->release(tape);
@@ -1157,10 +1159,74 @@ struct Solver {
     h.tape_full = 0;
   }
 
+  // signature of the body: a throw-away capture, then every kernel node's function, launch shape and parameter bytes
+  void body_signature(std::vector<lrnde_ctx::GraphNodeSig>& sig) {
+    cudaStream_t st = ctx->stream;
+    cudaGraph_t probe = nullptr;
+    ctx->capturing = true;
+    const long before = ctx->captured;
+    cudaError_t e = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
+    if (e != cudaSuccess) { ctx->capturing = false; LR_CUDA(e); }
+    try { body(); } catch (...) {
+      cudaGraph_t dummy; cudaStreamEndCapture(st, &dummy); ctx->capturing = false; ctx->captured = before; throw;
+    }
+    e = cudaStreamEndCapture(st, &probe);
+    ctx->capturing = false;
+    ctx->captured = before;
+    LR_CUDA(e);
+    size_t n = 0;
+    LR_CUDA(cudaGraphGetNodes(probe, nullptr, &n));
+    std::vector<cudaGraphNode_t> nodes(n);
+    if (n) LR_CUDA(cudaGraphGetNodes(probe, nodes.data(), &n));
+    sig.clear();
+    bool ok = true;
+    for (size_t i = 0; i < n && ok; ++i) {
+      cudaGraphNodeType ty;
+      LR_CUDA(cudaGraphNodeGetType(nodes[i], &ty));
+      if (ty != cudaGraphNodeTypeKernel) { ok = false; break; }
+      cudaKernelNodeParams kp;
+      LR_CUDA(cudaGraphKernelNodeGetParams(nodes[i], &kp));
+      lrnde_ctx::GraphNodeSig s;
+      s.func = kp.func;
+      s.g[0] = kp.gridDim.x; s.g[1] = kp.gridDim.y; s.g[2] = kp.gridDim.z;
+      s.b[0] = kp.blockDim.x; s.b[1] = kp.blockDim.y; s.b[2] = kp.blockDim.z;
+      s.smem = kp.sharedMemBytes;
+      if (!kp.kernelParams) { ok = false; break; }
+      for (size_t pi = 0;; ++pi) {
+        size_t off = 0, sz = 0;
+        if (cudaFuncGetParamInfo(kp.func, pi, &off, &sz) != cudaSuccess) { cudaGetLastError(); break; }
+        const char* src = (const char*)kp.kernelParams[pi];
+        s.params.insert(s.params.end(), src, src + sz);
+      }
+      sig.push_back(std::move(s));
+    }
+    cudaGraphDestroy(probe);
+    if (!ok) sig.clear();   // something other than kernel nodes: no caching
+  }
+
   // one step attempt = body(); captured once, then looped on the device
   void build_graphs(int loop_mode) {
     cudaStream_t st = ctx->stream;
     if (loop_mode == 0) {
+      std::vector<lrnde_ctx::GraphNodeSig> sig;
+      const bool use_cache = getenv("LRNDE_NO_GRAPH_CACHE") == nullptr;
+      if (use_cache) {
+        body_signature(sig);
+        for (auto& cg : ctx->graph_cache) {
+          if (cg.dev != (void*)dev || cg.sig.size() != sig.size()) continue;
+          bool same = true;
+          for (size_t i = 0; i < sig.size() && same; ++i) {
+            const auto &a = cg.sig[i], &b = sig[i];
+            same = a.func == b.func && memcmp(a.g, b.g, sizeof(a.g)) == 0 && memcmp(a.b, b.b, sizeof(a.b)) == 0 &&
+                   a.smem == b.smem && a.params == b.params;
+          }
+          if (!same) continue;
+          while_graph = cg.graph; while_exec = cg.exec; graph_cached = true;
+          h.cond_handle = cg.handle; h.use_cond = 1; body_nodes = cg.body_nodes;
+          cg.last_use = ++ctx->graph_clock;
+          return;
+        }
+      }
       LR_CUDA(cudaGraphCreate(&while_graph, 0));
       cudaGraphConditionalHandle handle;
       LR_CUDA(cudaGraphConditionalHandleCreate(&handle, while_graph, 0, 0));
@@ -1198,6 +1264,22 @@ struct Solver {
       LR_CUDA(e);
       body_nodes = ctx->captured - before;
       LR_CUDA(cudaGraphInstantiate(&while_exec, while_graph, 0));
+      if (use_cache && !sig.empty()) {
+        if (ctx->graph_cache.size() >= 8) {   // evict the least recently used entry (no live solver launches it again:
+                                              // solvers only launch their graph inside the call that built it)
+          size_t lru = 0;
+          for (size_t i = 1; i < ctx->graph_cache.size(); ++i)
+            if (ctx->graph_cache[i].last_use < ctx->graph_cache[lru].last_use) lru = i;
+          cudaGraphExecDestroy(ctx->graph_cache[lru].exec);
+          cudaGraphDestroy(ctx->graph_cache[lru].graph);
+          ctx->graph_cache.erase(ctx->graph_cache.begin() + lru);
+        }
+        lrnde_ctx::CachedGraph cg;
+        cg.graph = while_graph; cg.exec = while_exec; cg.handle = h.cond_handle; cg.body_nodes = body_nodes;
+        cg.dev = (void*)dev; cg.sig = std::move(sig); cg.last_use = ++ctx->graph_clock;
+        ctx->graph_cache.push_back(std::move(cg));
+        graph_cached = true;
+      }
     } else if (loop_mode == 2) {
       // no graph at all (profilers that cannot see into graphs): body() is launched directly
       h.use_cond = 0;

@@ -65,6 +65,17 @@ struct lrnde_ctx {
   // is queued AFTER the consuming call's own small parameter copies (lrnde_classifier_grad flushes it)
   struct { const float* x = nullptr; const int32_t* y = nullptr; int64_t B = 0; int32_t D = 0; bool valid = false; } pending;
 
+  // instantiated WHILE graphs of earlier calls, keyed by the full signature of their body (every kernel node's
+  // function, launch shape and parameter bytes): a training loop allocates the same pool blocks every iteration,
+  // so the captured body is usually identical and the 130-170 us of cudaGraphInstantiate are spent once
+  struct GraphNodeSig { void* func; unsigned g[3], b[3], smem; std::vector<char> params; };
+  struct CachedGraph {
+    cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr; unsigned long long handle = 0; long body_nodes = 0;
+    void* dev = nullptr; std::vector<GraphNodeSig> sig; unsigned long long last_use = 0;
+  };
+  std::vector<CachedGraph> graph_cache;
+  unsigned long long graph_clock = 0;
+
   void* alloc(size_t bytes);
   void release(void* p);
   void release_all_unused();
