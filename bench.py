@@ -299,14 +299,30 @@ def _native_loop(pkg, torch, dist, args, B, world, rank, dev, ctx, steps, warmup
     for i in range(warmup):
         st = step(i, st, True)
     launches["n"] = 0
+    # the e2e leg below repeats exactly these iterations (same parameters, optimiser state and t1 stream), so that the
+    # two legs take the same solver steps and differ only in where the buffers live
+    import copy
+    snap = dict(ps=ps.clone(), Wc=Wc.clone(), opt={k: v.clone() for k, v in opt.items()}, st=copy.deepcopy(st))
+
+    def restore():
+        ps.copy_(snap["ps"])
+        Wc.copy_(snap["Wc"])
+        for k, v in opt.items():
+            v.copy_(snap["opt"][k])
+        hb["ps"].copy_(ps)
+        hb["Wc"].copy_(Wc)
+        torch.cuda.synchronize(dev)
+        return copy.deepcopy(snap["st"])
+
     ms_total, st, nfe_sum = timed(steps, st, True, warmup)
     n_launch = launches["n"]
     fwd_info = dict(info)
     ms_e = float("nan")
     if e2e_steps:
-        chk(lib.lrnde_prefetch_inputs(ctx._h, hbufs[0][0].data_ptr(), hbufs[0][1].data_ptr(), B, D))   # batch of the warm step
-        st_e = step(0, st, False)                           # warm
-        ms_e, _, _ = timed(e2e_steps, st_e, False, 1)
+        i_w = warmup - 1 if warmup > 0 else 1
+        chk(lib.lrnde_prefetch_inputs(ctx._h, hbufs[i_w % 2][0].data_ptr(), hbufs[i_w % 2][1].data_ptr(), B, D))   # batch of the warm step
+        step(i_w, restore(), False)                         # warm (leaves the batch of iteration `warmup` staged)
+        ms_e, _, _ = timed(e2e_steps, restore(), False, warmup)
         ms_e /= e2e_steps
     e2e_info = dict(info) if e2e_steps else {}
     PW = NCLS * D + NCLS
@@ -394,11 +410,20 @@ def run_native(args):
     fwd_t, adj_t = us[2] * 1e-6, (ua[4] * 1e-6 if ua[4] > 0 else float("nan"))
     fwd_bytes, fwd_flops = 9.0 * arr, 6.0 * Ff
     adj_bytes, adj_flops = 22.0 * arr + 14.0 * 4.0 * P, 18.0 * Ff
-    traffic = None
-    tr_path = os.path.join(ROOT, "profiles", "r2_kernel_traffic.json")       # ncu --set full of this build (profiles/)
-    kern_traffic = json.load(open(tr_path)) if os.path.exists(tr_path) else {}
-    if str(B) in kern_traffic.get("kgemm_fwd", {}):
-        traffic = kern_traffic["kgemm_fwd"][str(B)]
+    # DRAM bytes per launch from the committed ncu --set full captures of this build at 8192 samples
+    # (profiles/r2_traffic.json, made by scratch/ncu_traffic.py from profiles/r2_*_ncu_full.txt's reports):
+    # the forward attempt = chain_kernel + kgemm_kernel<2,0> (lean tape)
+    traffic, traffic_detail = None, None
+    tr_path = os.path.join(ROOT, "profiles", "r2_traffic.json")
+    if os.path.exists(tr_path) and B == 8192:
+        kt = json.load(open(tr_path))
+        get = lambda name: next((v["dram_bytes_per_launch"] for k, v in kt.items() if name in k), None)
+        parts = {n: get(n) for n in ("chain_kernel<1>", "kgemm_kernel<2, 0>", "adj_chain_kernel", "pairacc_kernel",
+                                     "adj_reduce_kernel", "adj_mu_kernel")}
+        if parts["chain_kernel<1>"] and parts["kgemm_kernel<2, 0>"]:
+            traffic = parts["chain_kernel<1>"] + parts["kgemm_kernel<2, 0>"]
+        traffic_detail = {"source": "profiles/r2_traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch)",
+                          "per_kernel": parts}
     # per-kernel figures with the bytes each launch really has to move in this design
     zarr = 4.0 * 128 * B                                         # one hidden-space array [B][128]
     kern = {
@@ -426,7 +451,7 @@ def run_native(args):
                       "events; algorithmic work of SURVEY 8(d): 6 F_f flop, 9 * 4 * D * B bytes",
             "achieved": (fwd_bytes / fwd_t / 1e9) if bound == "hbm" else fwd_flops / fwd_t / 1e12,
             "peak": hbm_peak if bound == "hbm" else tf32_peak, "unit": "GB/s" if bound == "hbm" else "TFLOP/s",
-            "frac": max(hbm_frac, ten_frac), "traffic": traffic,
+            "frac": max(hbm_frac, ten_frac), "traffic": traffic, "traffic_detail": traffic_detail,
             "peak_source": ("MEASURED_PEAKS.json (STREAM copy; bf16 burst / 2 = TF32 dense)" if peaks else "fallback"),
             "forward_step": {"us": round(us[2], 2), "us_solve_loop": round(fwd_info["phases_us"]["fwd_solve"] /
                                                                         max(1, fwd_info["naccept"] + fwd_info["nreject"]), 2),

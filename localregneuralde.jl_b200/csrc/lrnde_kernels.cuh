@@ -668,8 +668,18 @@ __global__ void __launch_bounds__(256) mu_norm_kernel(SolveDev* S, int mode, con
 
 // fixed-order sum of LR_ERR_BLOCKS partials by one warp
 __device__ __forceinline__ double lr_sum_partials(const double* p) {
+  // all loads in flight before the (order-preserving) adds: the controller is a single warp on the critical path
+  constexpr int NV = (LR_ERR_BLOCKS + 31) / 32;
+  double v[NV];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int i = (int)threadIdx.x + 32 * k;
+    v[k] = (i < LR_ERR_BLOCKS) ? __ldcg(p + i) : 0.0;
+  }
   double s = 0.0;
-  for (int i = threadIdx.x; i < LR_ERR_BLOCKS; i += 32) s += p[i];
+#pragma unroll
+  for (int k = 0; k < NV; ++k)
+    if ((int)threadIdx.x + 32 * k < LR_ERR_BLOCKS) s += v[k];
   for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
   return __shfl_sync(0xffffffffu, s, 0);
 }
