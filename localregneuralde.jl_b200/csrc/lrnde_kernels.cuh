@@ -477,7 +477,16 @@ __global__ void __launch_bounds__(256) err_norm_kernel(SolveDev* S) {
   if (threadIdx.x == 0) S->partials[blockIdx.x] = s;
 }
 
-// initdt norms, pass 1: sum (u0/sk)^2, sum (f0/sk)^2, count of non-finite f0
+// initdt norms, pass 1: sum (u0/sk)^2, sum (f0/sk)^2, count of non-finite f0.  16-byte loads, two groups in flight
+// per thread (the scalar grid-stride loop was latency-bound: 55 us for 51 MB); scalar path for unaligned slots.
+__device__ __forceinline__ void lr_initdt1_elem(float u, float f, float abstol, float reltol, double& a0, double& a1,
+                                                unsigned int& bad) {
+  const float sk = abstol + fabsf(u) * reltol;
+  const float q0 = u / sk, q1 = f / sk;
+  a0 += (double)(q0 * q0);
+  a1 += (double)(q1 * q1);
+  if (!isfinite(f)) bad++;
+}
 __global__ void __launch_bounds__(256) initdt_norm1_kernel(SolveDev* S) {
   if (S->failed) return;
   const float* u0 = lr_slot_u(S, S->slot);
@@ -486,15 +495,28 @@ __global__ void __launch_bounds__(256) initdt_norm1_kernel(SolveDev* S) {
   double a0 = 0.0, a1 = 0.0;
   unsigned int bad = 0;
   const size_t nloc = (S->reduce_mu && S->nranks > 1) ? S->lam_len : S->len;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nloc;
-       i += (size_t)gridDim.x * blockDim.x) {
-    float u = u0[i], f = f0[i];
-    float sk = abstol + fabsf(u) * reltol;
-    float q0 = u / sk, q1 = f / sk;
-    a0 += (double)(q0 * q0);
-    a1 += (double)(q1 * q1);
-    if (!isfinite(f)) bad++;
+  const size_t tid = blockIdx.x * (size_t)blockDim.x + threadIdx.x, nthr = (size_t)gridDim.x * blockDim.x;
+  size_t done = 0;
+  if (((((uintptr_t)u0) | ((uintptr_t)f0)) & 15) == 0) {
+    const size_t n4 = nloc >> 2;
+    const float4* u4 = reinterpret_cast<const float4*>(u0);
+    const float4* f4 = reinterpret_cast<const float4*>(f0);
+    size_t i = tid;
+    for (; i + nthr < n4; i += 2 * nthr) {
+      const float4 ua = __ldcg(u4 + i), fa = __ldcg(f4 + i), ub = __ldcg(u4 + i + nthr), fb = __ldcg(f4 + i + nthr);
+      lr_initdt1_elem(ua.x, fa.x, abstol, reltol, a0, a1, bad); lr_initdt1_elem(ua.y, fa.y, abstol, reltol, a0, a1, bad);
+      lr_initdt1_elem(ua.z, fa.z, abstol, reltol, a0, a1, bad); lr_initdt1_elem(ua.w, fa.w, abstol, reltol, a0, a1, bad);
+      lr_initdt1_elem(ub.x, fb.x, abstol, reltol, a0, a1, bad); lr_initdt1_elem(ub.y, fb.y, abstol, reltol, a0, a1, bad);
+      lr_initdt1_elem(ub.z, fb.z, abstol, reltol, a0, a1, bad); lr_initdt1_elem(ub.w, fb.w, abstol, reltol, a0, a1, bad);
+    }
+    for (; i < n4; i += nthr) {
+      const float4 ua = __ldcg(u4 + i), fa = __ldcg(f4 + i);
+      lr_initdt1_elem(ua.x, fa.x, abstol, reltol, a0, a1, bad); lr_initdt1_elem(ua.y, fa.y, abstol, reltol, a0, a1, bad);
+      lr_initdt1_elem(ua.z, fa.z, abstol, reltol, a0, a1, bad); lr_initdt1_elem(ua.w, fa.w, abstol, reltol, a0, a1, bad);
+    }
+    done = n4 << 2;
   }
+  for (size_t i = done + tid; i < nloc; i += nthr) lr_initdt1_elem(u0[i], f0[i], abstol, reltol, a0, a1, bad);
   double s0 = lr_block_sum(a0);
   double s1 = lr_block_sum(a1);
   if (threadIdx.x == 0) {
@@ -505,6 +527,13 @@ __global__ void __launch_bounds__(256) initdt_norm1_kernel(SolveDev* S) {
 }
 
 // pass 2: sum ((f1-f0)/sk)^2 and count of f1 != f0; f1 sits in K(slot, 2)
+__device__ __forceinline__ void lr_initdt2_elem(float u, float f0v, float f1v, float abstol, float reltol, double& a2,
+                                                unsigned int& neq) {
+  const float sk = abstol + fabsf(u) * reltol;
+  const float q = (f1v - f0v) / sk;
+  a2 += (double)(q * q);
+  if (!(f1v == f0v)) neq++;
+}
 __global__ void __launch_bounds__(256) initdt_norm2_kernel(SolveDev* S) {
   if (S->failed) return;
   const float* u0 = lr_slot_u(S, S->slot);
@@ -514,13 +543,30 @@ __global__ void __launch_bounds__(256) initdt_norm2_kernel(SolveDev* S) {
   double a2 = 0.0;
   unsigned int neq = 0;
   const size_t nloc = (S->reduce_mu && S->nranks > 1) ? S->lam_len : S->len;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nloc;
-       i += (size_t)gridDim.x * blockDim.x) {
-    float sk = abstol + fabsf(u0[i]) * reltol;
-    float q = (f1[i] - f0[i]) / sk;
-    a2 += (double)(q * q);
-    if (!(f1[i] == f0[i])) neq++;
+  const size_t tid = blockIdx.x * (size_t)blockDim.x + threadIdx.x, nthr = (size_t)gridDim.x * blockDim.x;
+  size_t done = 0;
+  if (((((uintptr_t)u0) | ((uintptr_t)f0) | ((uintptr_t)f1)) & 15) == 0) {
+    const size_t n4 = nloc >> 2;
+    const float4* u4 = reinterpret_cast<const float4*>(u0);
+    const float4* p4 = reinterpret_cast<const float4*>(f0);
+    const float4* q4 = reinterpret_cast<const float4*>(f1);
+    size_t i = tid;
+    for (; i + nthr < n4; i += 2 * nthr) {
+      const float4 ua = __ldcg(u4 + i), pa = __ldcg(p4 + i), qa = __ldcg(q4 + i);
+      const float4 ub = __ldcg(u4 + i + nthr), pb = __ldcg(p4 + i + nthr), qb = __ldcg(q4 + i + nthr);
+      lr_initdt2_elem(ua.x, pa.x, qa.x, abstol, reltol, a2, neq); lr_initdt2_elem(ua.y, pa.y, qa.y, abstol, reltol, a2, neq);
+      lr_initdt2_elem(ua.z, pa.z, qa.z, abstol, reltol, a2, neq); lr_initdt2_elem(ua.w, pa.w, qa.w, abstol, reltol, a2, neq);
+      lr_initdt2_elem(ub.x, pb.x, qb.x, abstol, reltol, a2, neq); lr_initdt2_elem(ub.y, pb.y, qb.y, abstol, reltol, a2, neq);
+      lr_initdt2_elem(ub.z, pb.z, qb.z, abstol, reltol, a2, neq); lr_initdt2_elem(ub.w, pb.w, qb.w, abstol, reltol, a2, neq);
+    }
+    for (; i < n4; i += nthr) {
+      const float4 ua = __ldcg(u4 + i), pa = __ldcg(p4 + i), qa = __ldcg(q4 + i);
+      lr_initdt2_elem(ua.x, pa.x, qa.x, abstol, reltol, a2, neq); lr_initdt2_elem(ua.y, pa.y, qa.y, abstol, reltol, a2, neq);
+      lr_initdt2_elem(ua.z, pa.z, qa.z, abstol, reltol, a2, neq); lr_initdt2_elem(ua.w, pa.w, qa.w, abstol, reltol, a2, neq);
+    }
+    done = n4 << 2;
   }
+  for (size_t i = done + tid; i < nloc; i += nthr) lr_initdt2_elem(u0[i], f0[i], f1[i], abstol, reltol, a2, neq);
   double s2 = lr_block_sum(a2);
   if (threadIdx.x == 0) S->partials[2 * LR_ERR_BLOCKS + blockIdx.x] = s2;
   if (neq) atomicAdd(&S->counters[1], neq);

@@ -33,19 +33,46 @@ __global__ void __launch_bounds__(256) reg_seed_gq_kernel(RegSeedGQP p) {
   const float* u = e.dst;
   const float root = R->reg_ss_root;
   const float c = (root == 0.0f || R->failed) ? 0.0f : p.d_reg * dt / (n * root);
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < p.DB; i += (size_t)gridDim.x * blockDim.x) {
-    float inner = 0.0f;
-#pragma unroll
-    for (int k = 0; k < 7; ++k) inner = fmaf(e.coef[k], __ldcg(e.src[k] + i), inner);
+  auto elem = [&](float inner, float uu, float up, float& g, float& q) {
     const float ut = dt * inner;
-    const float uu = u[i];
-    const float au = fabsf(uu), ap = fabsf(uprev[i]);
+    const float au = fabsf(uu), ap = fabsf(up);
     const float denom = abstol + fmaxf(ap, au) * reltol;
     const float r = ut / denom;
     const float dr = c * r;
     const float sg = (uu > 0.0f) ? 1.0f : ((uu < 0.0f) ? -1.0f : 0.0f);
-    p.gq[i] = dr / denom;
-    p.gq[p.DB + i] = (-dr * ut / (denom * denom)) * reltol * sg * ((au > ap) ? 1.0f : 0.0f);
+    g = dr / denom;
+    q = (-dr * ut / (denom * denom)) * reltol * sg * ((au > ap) ? 1.0f : 0.0f);
+  };
+  const size_t tid = blockIdx.x * (size_t)blockDim.x + threadIdx.x, nthr = (size_t)gridDim.x * blockDim.x;
+  // 16-byte groups (every array of the regulariser's ring starts at a multiple of D * B floats, D % 4 == 0)
+  uintptr_t al = ((uintptr_t)uprev) | ((uintptr_t)u) | ((uintptr_t)p.gq) | (uintptr_t)(p.DB & 3);
+#pragma unroll
+  for (int k = 0; k < 7; ++k) al |= (uintptr_t)e.src[k];
+  size_t done = 0;
+  if ((al & 15) == 0) {
+    const size_t n4 = p.DB >> 2;
+    for (size_t i = tid; i < n4; i += nthr) {
+      float4 in = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < 7; ++k) {
+        const float4 v = __ldcg(reinterpret_cast<const float4*>(e.src[k]) + i);
+        in.x = fmaf(e.coef[k], v.x, in.x); in.y = fmaf(e.coef[k], v.y, in.y);
+        in.z = fmaf(e.coef[k], v.z, in.z); in.w = fmaf(e.coef[k], v.w, in.w);
+      }
+      const float4 uu = __ldcg(reinterpret_cast<const float4*>(u) + i), up = __ldcg(reinterpret_cast<const float4*>(uprev) + i);
+      float4 g, q;
+      elem(in.x, uu.x, up.x, g.x, q.x); elem(in.y, uu.y, up.y, g.y, q.y);
+      elem(in.z, uu.z, up.z, g.z, q.z); elem(in.w, uu.w, up.w, g.w, q.w);
+      reinterpret_cast<float4*>(p.gq)[i] = g;
+      reinterpret_cast<float4*>(p.gq + p.DB)[i] = q;
+    }
+    done = n4 << 2;
+  }
+  for (size_t i = done + tid; i < p.DB; i += nthr) {
+    float inner = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) inner = fmaf(e.coef[k], __ldcg(e.src[k] + i), inner);
+    elem(inner, u[i], uprev[i], p.gq[i], p.gq[p.DB + i]);
   }
 }
 
