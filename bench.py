@@ -280,29 +280,44 @@ def _native_loop(pkg, torch, dist, args, B, world, rank, dev, ctx, steps, warmup
 
     def timed(nsteps, st, resident, i0):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(nsteps)]
         sync_all()
         e0.record()
         nfe_sum = 0
         for i in range(nsteps):
             st = step(i0 + i, st, resident)
             nfe_sum += info["nfe"]
+            marks[i].record()
         e1.record()
         sync_all()
         ms = e0.elapsed_time(e1)
+        prev = e0
+        per_step = []
+        for m in marks:
+            per_step.append(round(prev.elapsed_time(m), 3))
+            prev = m
+        info["per_step_ms"] = per_step
         if world > 1:
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
         return ms, st, nfe_sum
 
+    import copy
+    # buffers of the state snapshot taken at the start of the timed region (allocated before the warm-up so that the
+    # timed steps see a settled allocator)
+    snap = dict(ps=torch.empty_like(ps), Wc=torch.empty_like(Wc), opt={k: torch.empty_like(v) for k, v in opt.items()}, st=None)
     st = st0
     for i in range(warmup):
         st = step(i, st, True)
     launches["n"] = 0
     # the e2e leg below repeats exactly these iterations (same parameters, optimiser state and t1 stream), so that the
     # two legs take the same solver steps and differ only in where the buffers live
-    import copy
-    snap = dict(ps=ps.clone(), Wc=Wc.clone(), opt={k: v.clone() for k, v in opt.items()}, st=copy.deepcopy(st))
+    for k, v in (("ps", ps), ("Wc", Wc)):
+        snap[k].copy_(v)
+    for k, v in opt.items():
+        snap["opt"][k].copy_(v)
+    snap["st"] = copy.deepcopy(st)
 
     def restore():
         ps.copy_(snap["ps"])
@@ -317,6 +332,7 @@ def _native_loop(pkg, torch, dist, args, B, world, rank, dev, ctx, steps, warmup
     ms_total, st, nfe_sum = timed(steps, st, True, warmup)
     n_launch = launches["n"]
     fwd_info = dict(info)
+    per_step_ms = list(info.get("per_step_ms", []))
     ms_e = float("nan")
     if e2e_steps:
         i_w = warmup - 1 if warmup > 0 else 1
@@ -329,6 +345,7 @@ def _native_loop(pkg, torch, dist, args, B, world, rank, dev, ctx, steps, warmup
     h2d = 4 * (B * D + B + P + PW) + 4 * (P + PW)            # x, labels, ps, Wc in; the host gradients back up for the optimiser
     d2h = 4 * (P + PW + 1) + 4 * (P + PW)                    # d_ps, d_Wc, loss out; the updated parameters
     return dict(ms=ms_total / steps, ms_total=ms_total, ms_e2e=ms_e, info=fwd_info, e2e_info=e2e_info, launches=n_launch, nfe_sum=nfe_sum,
+                per_step_ms=per_step_ms,
                 h2d=h2d, d2h=d2h, node=node, chain=chain, ps=ps, xb=xb, P=P)
 
 
@@ -485,7 +502,7 @@ def run_native(args):
                    "nfe": int(nfe_c)}
         line = {
             "metric": "mnist_ode_train_samples_per_s", "value": value, "unit": "samples/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "per_step_ms": r["per_step_ms"], "higher_is_better": True,
             "scaling": args.scaling, "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "tf32x3",
             "data": "synthetic", "config": workload_config(args, world),
             "parity_regime": "noise (abstol = reltol = 1.4e-8 sits below Float32 resolution: the embedded error estimate "
