@@ -200,6 +200,75 @@ __global__ void softmax_ce_kernel(const float* logits, const int* labels, int Cn
   double r = lr_block_sum(acc);
   if (threadIdx.x == 0) partials[blockIdx.x] = r;
 }
+// Fused head for small class counts (Cn <= 16): one warp per sample reads u_b once, forms the Cn logits (weights in
+// shared memory), the cross entropy, dlogits (kept for the weight gradient) and d_u[:, b] = W^T dlogits[:, b].
+// Same arithmetic as dense_nn_kernel + softmax_ce_kernel + dense_nn_kernel, in 2 * 4 * D * B bytes of traffic.
+constexpr int kHeadMaxC = 16;
+__global__ void __launch_bounds__(256) head_fused_kernel(const float* __restrict__ Wc, const float* __restrict__ u,
+                                                         const int* __restrict__ labels, int Cn, int D, int B,
+                                                         float* __restrict__ dlogits, float* __restrict__ d_u,
+                                                         double* partials, int* bad_label) {
+  extern __shared__ float hw[];                 // W [Cn x D] column-major (as in ps), then the bias [Cn]
+  for (int i = threadIdx.x; i < Cn * (D + 1); i += blockDim.x) hw[i] = Wc[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  double acc = 0.0;
+  for (int b = blockIdx.x * nwarp + warp; b < B; b += gridDim.x * nwarp) {
+    const float* ub = u + (size_t)b * D;
+    float z[kHeadMaxC];
+#pragma unroll
+    for (int c = 0; c < kHeadMaxC; ++c) z[c] = 0.0f;
+    for (int d = lane; d < D; d += 32) {
+      const float x = __ldcg(ub + d);
+#pragma unroll
+      for (int c = 0; c < kHeadMaxC; ++c)
+        if (c < Cn) z[c] = fmaf(hw[c + d * Cn], x, z[c]);
+    }
+#pragma unroll
+    for (int c = 0; c < kHeadMaxC; ++c) {
+      if (c < Cn) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) z[c] += __shfl_xor_sync(0xffffffffu, z[c], o);
+        z[c] += hw[Cn * D + c];
+      }
+    }
+    float mx = z[0];
+#pragma unroll
+    for (int c = 1; c < kHeadMaxC; ++c) if (c < Cn) mx = fmaxf(mx, z[c]);
+    float sum = 0.0f;
+#pragma unroll
+    for (int c = 0; c < kHeadMaxC; ++c) if (c < Cn) sum += expf(z[c] - mx);
+    const float lse = mx + logf(sum);
+    int y = labels[b];
+    if (y < 0 || y >= Cn) { if (lane == 0) *bad_label = 1; y = 0; }
+    float zy = 0.0f;
+    float dl[kHeadMaxC];
+#pragma unroll
+    for (int c = 0; c < kHeadMaxC; ++c) {
+      dl[c] = 0.0f;
+      if (c < Cn) {
+        if (c == y) zy = z[c];
+        dl[c] = (expf(z[c] - lse) - (c == y ? 1.0f : 0.0f)) / (float)B;
+      }
+    }
+    if (lane == 0) {
+      acc += (double)(lse - zy);
+      for (int c = 0; c < Cn; ++c) dlogits[(size_t)b * Cn + c] = dl[c];
+    }
+    if (d_u) {
+      float* out = d_u + (size_t)b * D;
+      for (int d = lane; d < D; d += 32) {
+        float v = 0.0f;
+#pragma unroll
+        for (int c = 0; c < kHeadMaxC; ++c)
+          if (c < Cn) v = fmaf(hw[c + d * Cn], dl[c], v);
+        out[d] = v;
+      }
+    }
+  }
+  double r = lr_block_sum(acc);
+  if (threadIdx.x == 0) partials[blockIdx.x] = r;
+}
 __global__ void mean_finish_kernel(const double* partials, int nb, double n, float* out) {
   double s = 0.0;
   for (int i = threadIdx.x; i < nb; i += 32) s += partials[i];
@@ -220,7 +289,7 @@ extern "C" int lrnde_head_ce(lrnde_ctx* ctx, const float* Wc, const float* u,
   DevBuf w(ctx, host ? PW : 1), ub(ctx, host ? DB : 1), lb(ctx, host ? (size_t)B : 1);
   DevBuf logits(ctx, CB), dlog(ctx, CB), wt(ctx, (size_t)D * Cn);
   DevBuf dub(ctx, host ? DB : 1), dwb(ctx, host ? PW : 1);
-  const int nb = 64;
+  const int nb = 296;
   DevBuf red(ctx, 2 * nb + 8);
   int* badd = (int*)(red.p + 2 * nb + 4);
   LR_CUDA(cudaMemsetAsync(badd, 0, sizeof(int), st));
@@ -231,6 +300,24 @@ extern "C" int lrnde_head_ce(lrnde_ctx* ctx, const float* Wc, const float* u,
     LR_CUDA(cudaMemcpyAsync(lb.p, labels, 4 * (size_t)B, cudaMemcpyHostToDevice, st));
     Wd = w.p; ud = ub.p; ld = (const int*)lb.p;
   }
+  const size_t head_smem = sizeof(float) * (size_t)Cn * (D + 1);
+  const bool fused_head = Cn <= kHeadMaxC && head_smem <= 160 * 1024 && !getenv("LRNDE_NO_FUSED_HEAD");
+  float* lossd = (float*)((double*)red.p + nb);
+  if (fused_head) {
+    static size_t attr_bytes = 0;
+    if (head_smem > attr_bytes) {
+      LR_CUDA(cudaFuncSetAttribute(head_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)head_smem));
+      attr_bytes = head_smem;
+    }
+    LR_CUDA(cudaMemsetAsync(red.p, 0, sizeof(double) * nb, st));
+    const int hb = (int)std::min<int64_t>(nb, (B + 7) / 8);   // at most nb blocks (the partial sums), 8 warps each
+    head_fused_kernel<<<hb, 256, head_smem, st>>>(Wd, ud, ld, Cn, D, (int)B, dlog.p, d_u ? (host ? dub.p : d_u) : nullptr,
+                                                  (double*)red.p, badd);
+    LR_COUNT(ctx);
+    mean_finish_kernel<<<1, 32, 0, st>>>((double*)red.p, nb, (double)B, lossd);
+    LR_COUNT(ctx);
+    if (d_u && host) LR_CUDA(cudaMemcpyAsync(d_u, dub.p, 4 * DB, cudaMemcpyDeviceToHost, st));
+  } else {
   DenseP p;
   memset(&p, 0, sizeof(p));
   p.A = Wd; p.lda = Cn; p.M = Cn; p.K = D; p.td = 0; p.bias = 1;
@@ -241,10 +328,10 @@ extern "C" int lrnde_head_ce(lrnde_ctx* ctx, const float* Wc, const float* u,
   LR_COUNT(ctx);
   softmax_ce_kernel<<<nb, 256, 0, st>>>(logits.p, ld, Cn, (int)B, dlog.p, (double*)red.p, badd);
   LR_COUNT(ctx);
-  float* lossd = (float*)((double*)red.p + nb);
   mean_finish_kernel<<<1, 32, 0, st>>>((double*)red.p, nb, (double)B, lossd);
   LR_COUNT(ctx);
-  if (d_u) {
+  }
+  if (d_u && !fused_head) {
     dim3 tg((Cn + 31) / 32, (D + 31) / 32), tb(32, 8);
     transpose_kernel<<<tg, tb, 0, st>>>(Wd, Cn, D, wt.p);
     LR_COUNT(ctx);
