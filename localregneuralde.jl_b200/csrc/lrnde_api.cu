@@ -21,6 +21,7 @@
 #include "lrnde_umma.cuh"
 #include "lrnde_smem_mlp.cuh"
 #include "lrnde_conv.cuh"
+#include "lrnde_conv_tc.h"
 #include "lrnde_fused.h"
 #include "lrnde_adjoint.h"
 #include "lrnde_regrev.cuh"
@@ -351,6 +352,20 @@ struct ConvEval {
   bool bn_update = false;
   bool first_call_twice = false;  // OrdinaryDiffEq calls f(u0, t0) twice (initialize! and the initial-dt heuristic);
                                   // the library evaluates it once, the running statistics see two closure calls
+  // tensor-core engine (lrnde_conv_tc.h): every layer has channel counts that are multiples of 8 and at most 64
+  bool tc = false;
+  ConvTcGeom geo;
+  float* Fhi = nullptr; float* Flo = nullptr;           // (F) operand of the convolution about to run
+  std::vector<uint8_t*> wimg, wimgT;                    // weight images: forward / data-gradient convolution
+  std::vector<float*> tsum;                             // time-channel tables
+
+  static bool tc_eligible(const lrnde_model* m) {
+    const char* e = getenv("LRNDE_CONV_TC");
+    if (e && e[0] == '0') return false;
+    for (auto& Li : m->conv)
+      if ((Li.cin & 7) || (Li.cout & 7) || Li.cin > 64 || Li.cout > 64) return false;
+    return m->Wd + 3 <= kCtGuard;
+  }
 
   static int tile_rows(int PT, int Wd, int Ht) { return std::min(PT / (Wd >> 2), Ht); }
   static bool narrow(int cout) { return cout <= 16; }   // <8,8,4> instantiation (whole-image tiles)
@@ -366,11 +381,20 @@ struct ConvEval {
         lr_fail(LRNDE_EINVAL, "BatchNorm with %d channels on a multi-rank ctx (the statistics exchange holds %d)", Li.cout, LR_BN_MAXC);
     L = (int)m->conv.size();
     HW = (size_t)m->Wd * m->Ht;
+    tc = tc_eligible(m);
+    if (tc) geo.set(m->Wd, m->Ht, (int)B);
     z.assign(L, nullptr); ab.assign(L, nullptr); stat.assign(L, nullptr); pack.assign(L, nullptr); packT.assign(L, nullptr);
+    wimg.assign(L, nullptr); wimgT.assign(L, nullptr); tsum.assign(L, nullptr);
     for (int l = 0; l < L; ++l) {
       const ConvLayerInfo& Li = m->conv[l];
       maxC = std::max(maxC, std::max(Li.cin, Li.cout));
       nblk_max = std::max(nblk_max, conv_nblk(Li.cout) * Li.cout);
+      if (tc) {
+        nblk_max = std::max(nblk_max, geo.ngroups * 4 * Li.cout);
+        wimg[l] = (uint8_t*)ctx->alloc(convtc_wimg_bytes(Li.cin, convtc_nout(Li.cout)));
+        if (m->td) tsum[l] = (float*)ctx->alloc(4 * 64 * (size_t)convtc_nout(Li.cout));
+        if (vjp) wimgT[l] = (uint8_t*)ctx->alloc(convtc_wimg_bytes(Li.cout, convtc_nout(Li.cin)));
+      }
       const size_t nw = (size_t)9 * (Li.cin + m->td) * Li.cout;
       pack[l] = (float*)ctx->alloc(4 * nw);
       if (l < L - 1) z[l] = (float*)ctx->alloc(4 * HW * Li.cout * B);
@@ -380,6 +404,13 @@ struct ConvEval {
       if (vjp) packT[l] = (float*)ctx->alloc(4 * (size_t)9 * Li.cin * Li.cout);
     }
     spart = (float2*)ctx->alloc(sizeof(float2) * (size_t)nblk_max);
+    if (tc) {
+      // the guard positions and the tail of the last tile group are read by the bulk copies and never written
+      const size_t nf = geo.f_floats(maxC);
+      Fhi = (float*)ctx->alloc(4 * nf); Flo = (float*)ctx->alloc(4 * nf);
+      LR_CUDA(cudaMemsetAsync(Fhi, 0, 4 * nf, ctx->stream));
+      LR_CUDA(cudaMemsetAsync(Flo, 0, 4 * nf, ctx->stream));
+    }
     if (vjp) {
       int n_sm = 148;
       ybuf = (float*)ctx->alloc(4 * (size_t)m->D * B);
@@ -416,6 +447,10 @@ struct ConvEval {
     for (auto p : stat) ctx->release(p);
     for (auto p : pack) ctx->release(p);
     for (auto p : packT) ctx->release(p);
+    for (auto p : wimg) ctx->release(p);
+    for (auto p : wimgT) ctx->release(p);
+    for (auto p : tsum) ctx->release(p);
+    ctx->release(Fhi); ctx->release(Flo);
     ctx->release(spart); ctx->release(ybuf); ctx->release(lbuf); ctx->release(G[0]); ctx->release(G[1]);
     ctx->release(part); ctx->release(bpart); ctx->release(coef); ctx->release(dgb);
   }
@@ -452,8 +487,23 @@ struct ConvEval {
         conv_pack_kernel<<<lr_ew_blocks((size_t)9 * Li.cin * Li.cout), 256, 0, ctx->stream>>>(ps + Li.w_off, cintot, Li.cout, 1, Li.cin, packT[l]);
         LR_COUNT(ctx);
       }
+      if (tc) {
+        convtc_wpack(ctx, ps + Li.w_off, cintot, Li.cout, 0, 0, m->td, wimg[l], tsum[l]);
+        if (with_vjp) convtc_wpack(ctx, ps + Li.w_off, cintot, Li.cout, 1, Li.cin, m->td, wimgT[l], nullptr);
+      }
     }
     LR_CHECK_LAUNCH();
+  }
+
+  int stat_nblk(int cout) const { return tc ? geo.ngroups * 4 : conv_nblk(cout); }
+  // tensor-core convolution of (F): packed operand -> [W,H,Cout,B]
+  void launch_tc(const uint8_t* img, int K, const float* ts, const LinComb* tdesc, float* Y, const LinComb* ydesc, float scale,
+                 int cout, float2* sp, const int* done) {
+    ConvTcP q;
+    memset(&q, 0, sizeof(q));
+    q.Fhi = Fhi; q.Flo = Flo; q.Wimg = img; q.K = K; q.tsum = ts; q.tdesc = tdesc; q.Y = Y; q.ydesc = ydesc;
+    q.out_scale = scale; q.Cout = cout; q.stat_part = sp; q.done = done;
+    convtc_conv(ctx, geo, q);
   }
 
   void launch(ConvP& q) {
@@ -472,6 +522,16 @@ struct ConvEval {
     if (update_state) first_call_twice = false;
     for (int l = 0; l < upto; ++l) {
       const ConvLayerInfo& Li = m->conv[l];
+      if (tc) {
+        ConvTcPackP pk;
+        memset(&pk, 0, sizeof(pk));
+        if (l == 0) { pk.xdesc = in; pk.side_to_desc_dst = side_to_in_dst ? 1 : 0; pk.side = side; pk.in_act = ACT_IDENTITY; }
+        else { pk.X = z[l - 1]; pk.in_ab = m->conv[l - 1].bn ? ab[l - 1] : nullptr; pk.in_act = m->conv[l - 1].act; }
+        pk.Fhi = Fhi; pk.Flo = Flo; pk.C = Li.cin; pk.done = done;
+        convtc_pack(ctx, geo, pk);
+        launch_tc(wimg[l], Li.cin, m->td ? tsum[l] : nullptr, m->td ? in : nullptr, l == L - 1 ? nullptr : z[l],
+                  l == L - 1 ? (out ? out : in) : nullptr, 1.0f, Li.cout, (Li.bn && !testmode) ? spart : nullptr, done);
+      } else {
       ConvP q;
       memset(&q, 0, sizeof(q));
       if (l == 0) {
@@ -483,8 +543,9 @@ struct ConvEval {
       if (l == L - 1) q.ydesc = out ? out : in; else q.Y = z[l];
       if (Li.bn && !testmode) q.stat_part = spart;
       launch(q);
+      }
       if (Li.bn) {
-        bn_finalize_kernel<<<Li.cout, 128, 0, ctx->stream>>>(spart, conv_nblk(Li.cout), Li.cout, (double)HW * (double)B,
+        bn_finalize_kernel<<<Li.cout, 128, 0, ctx->stream>>>(spart, stat_nblk(Li.cout), Li.cout, (double)HW * (double)B,
                                                            ps + Li.g_off, 1e-5f, ab[l], stat[l],
                                                            bn_state ? bn_state + s_off[l] : nullptr, testmode,
                                                            (update_state && bn_update) ? ncalls : 0, done, ctx->bn_dist());
@@ -534,13 +595,21 @@ struct ConvEval {
       ConvP q;
       memset(&q, 0, sizeof(q));
       q.X = delta; q.in_act = ACT_IDENTITY; q.td = 0; q.Wp = packT[l]; q.Cin = Li.cout; q.Cout = Li.cin; q.done = done;
+      if (tc) {   // (F) image of the cotangent, then the data-gradient convolution on the tensor cores
+        ConvTcPackP pk;
+        memset(&pk, 0, sizeof(pk));
+        pk.X = delta; pk.in_act = ACT_IDENTITY; pk.Fhi = Fhi; pk.Flo = Flo; pk.C = Li.cout; pk.done = done;
+        convtc_pack(ctx, geo, pk);
+      }
       if (l == 0) {
         q.out_scale = a_scale;
         if (out_a) q.Y = out_a; else q.ydesc = out_desc;
-        launch(q);
+        if (tc) launch_tc(wimgT[l], Li.cout, nullptr, nullptr, q.Y, q.ydesc, a_scale, Li.cin, nullptr, done);
+        else launch(q);
       } else {
         q.out_scale = 1.0f; q.Y = G[cur];
-        launch(q);
+        if (tc) launch_tc(wimgT[l], Li.cout, nullptr, nullptr, G[cur], nullptr, 1.0f, Li.cin, nullptr, done);
+        else launch(q);
         const ConvLayerInfo& Lp = m->conv[l - 1];
         const size_t n = HW * Lp.cout * B;
         if (Lp.bn) {

@@ -1,0 +1,88 @@
+// Tensor-core engine of the conv dynamics (BASELINE configs[3] "cifar10", "implicit-GEMM Conv stages"):
+//
+//   TDChain(Chain(Chain(Conv((3,3), 9 => 64; pad=1, use_bias=false), BatchNorm(64, gelu)),
+//                 Chain(Conv((3,3), 65 => 64; pad=1, use_bias=false), BatchNorm(64, gelu)),
+//                 Conv((3,3), 65 => 8; pad=1, use_bias=false)))      experiments/src/construct.jl:212-218
+//
+// Every 3x3 convolution (forward, its transposed twin of the reverse pass, and the weight gradient) is an implicit
+// GEMM on tcgen05 in 3xTF32.  No im2col matrix exists anywhere:
+//
+//   * convtc_pack_kernel applies whatever sits between two convolutions (stage combination of perform_step.jl:11-18,
+//     BatchNorm scale / shift + activation, or the BatchNorm pullback) ONCE per element, splits the result into tf32
+//     hi / lo parts and writes it
+//       (F) channel-interleaved with a zero halo: F[c / 4][guard + b * (W+2)(H+2) + (y+1)(W+2) + (x+1)][c % 4], which
+//           is the K-major no-swizzle UMMA layout with a uniform 16-byte row stride: rows = positions, K = channels.
+//           A tap (dy, dx) of the convolution is the SAME shared-memory patch read through a descriptor whose start
+//           address is moved by (dy (W+2) + dx) rows -- nine taps, one copy of the patch, plain bulk copies;
+//       (P) plain [W, H, C, B] hi / lo arrays, the operands of the weight gradient (K = pixels of an image row):
+//           tensor-map TMA delivers the dx-shifted, zero-padded row tiles in the K-major SWIZZLE_128B layout.
+//   * convtc_kernel<NOUT>: persistent CTAs, M = 128 consecutive (haloed) positions, N = output channels, K = 8 input
+//     channels per MMA; a group of four M tiles shares every weight stage, accumulators double-buffered in TMEM
+//     (2 x 4 x NOUT columns), epilogue = time-channel term + scale + coalesced [W,H,C,B] stores + BatchNorm partial
+//     sums.  The TDChain time channel (common.jl:19-33: t inside the image, 0 in the padding) never enters the GEMM:
+//     its contribution t * sum_{taps inside} w[tap, time, co] depends only on the border class of the pixel.
+//   * convtc_wgrad_kernel: dW[tap, ci, co] = sum_p X[p + d_tap, ci] Delta[p, co]; see lrnde_conv_tc.cu.
+#pragma once
+#include "lrnde_host.h"
+
+constexpr int kCtGuard = 36;     // positions in front of / behind the packed arrays (>= W + 3)
+constexpr int kCtGroup = 512;    // positions per tile group (4 M tiles of 128)
+
+struct ConvTcGeom {
+  int Wd = 0, Ht = 0, B = 0, PW = 0, PH = 0, IMG = 0;
+  long NP = 0, NPA = 0;   // haloed positions of the batch; allocated positions per channel chunk
+  int ngroups = 0;
+  void set(int wd, int ht, int b) {
+    Wd = wd; Ht = ht; B = b; PW = wd + 2; PH = ht + 2; IMG = PW * PH;
+    NP = (long)b * IMG;
+    ngroups = (int)((NP + kCtGroup - 1) / kCtGroup);
+    NPA = (long)ngroups * kCtGroup + 2 * kCtGuard;
+  }
+  size_t f_floats(int C) const { return (size_t)(C / 4) * (size_t)NPA * 4; }   // one of the hi / lo arrays
+};
+
+// what convtc_pack_kernel computes per element before the hi / lo split
+struct ConvTcPackP {
+  const float* X; const LinComb* xdesc;     // source [W,H,C,B]: plain array or stage combination
+  float* side; int side_to_desc_dst;        // also store the combined source (u_{n+1} / y(t)): plain pointer or xdesc->dst
+  const float* in_ab; int in_act;           // v <- act(a[c] v + b[c])  (BatchNorm scale / shift + activation)
+  // BatchNorm + activation pullback (X = z, the raw conv output the statistics were taken on):
+  //   v <- a (g act'(a z + b) - m1 - (z - mean) invstd m2); coef == nullptr: v <- g act'(z)
+  const float* bwd_g; const float* bwd_stat; const float* bwd_coef; int bwd_act;
+  float* Fhi; float* Flo;                   // (F) layout (may be null)
+  float* Phi; float* Plo;                   // plain hi / lo (may be null)
+  int C;
+  const int* done;
+};
+void convtc_pack(lrnde_ctx* ctx, const ConvTcGeom& g, const ConvTcPackP& p);
+
+// weight image of one convolution: [stage of 8 input channels][hi | lo][tap][k4][NOUT rows][4] + the time-channel table
+size_t convtc_wimg_bytes(int K, int NOUT);
+inline int convtc_nout(int cout) { return cout <= 16 ? 16 : 64; }
+// w: Lux weight [3,3,CinTot,Cout]; transposed = 0: out channels = Cout, K = first `K` input channels, tsum = table of the
+// channel CinTot - 1 when td; transposed = 1: the data-gradient convolution (K = Cout, out channels = first `keep` inputs)
+void convtc_wpack(lrnde_ctx* ctx, const float* w, int CinTot, int Cout, int transposed, int keep, int td, uint8_t* img,
+                  float* tsum);
+
+struct ConvTcP {
+  const float* Fhi; const float* Flo;
+  const uint8_t* Wimg; int K;               // input channels (multiple of 8)
+  const float* tsum; const LinComb* tdesc;  // time channel (null: none)
+  float* Y; const LinComb* ydesc; float out_scale; int Cout;
+  float2* stat_part;                        // [ngroups * 4][Cout] (sum, sum of squares) of the raw output, or null
+  const int* done;
+};
+void convtc_conv(lrnde_ctx* ctx, const ConvTcGeom& g, const ConvTcP& p);
+
+// weight gradient on the tensor cores (Wd == 32 only): part[split][Lux weight layout], splits = convtc_wgrad_splits()
+struct ConvTcWgP {
+  const float* Xhi; const float* Xlo; int Cx;     // input of the convolution [W,H,Cx,B] (time channel excluded)
+  const float* Dhi; const float* Dlo; int Cd;     // cotangent of its output [W,H,Cd,B]
+  int CinTot;                                     // Cx + td: layout of the result
+  float* part; size_t block;
+  const LinComb* tdesc;                           // time channel: its weight gradient t * (masked sums of Delta)
+  const float* Dplain;                            // (unused when tdesc == null)
+  const int* done;
+};
+int convtc_wgrad_splits(const ConvTcGeom& g);
+void convtc_wgrad(lrnde_ctx* ctx, const ConvTcGeom& g, const ConvTcWgP& p);
