@@ -358,6 +358,10 @@ struct ConvEval {
   float* Fhi = nullptr; float* Flo = nullptr;           // (F) operand of the convolution about to run
   std::vector<uint8_t*> wimg, wimgT;                    // weight images: forward / data-gradient convolution
   std::vector<float*> tsum;                             // time-channel tables
+  bool wg_tc = false;                                   // weight gradients on the tensor cores as well (Wd == 32)
+  std::vector<float*> Phi, Plo;                         // plain tf32 hi / lo input of every layer (operands of its weight gradient)
+  float* PDhi = nullptr; float* PDlo = nullptr;         // ... and of the cotangent of the layer at hand
+  float* rowsum = nullptr;                              // per-row sums of that cotangent (time channel's weight gradient)
 
   static bool tc_eligible(const lrnde_model* m) {
     const char* e = getenv("LRNDE_CONV_TC");
@@ -383,6 +387,8 @@ struct ConvEval {
     HW = (size_t)m->Wd * m->Ht;
     tc = tc_eligible(m);
     if (tc) geo.set(m->Wd, m->Ht, (int)B);
+    wg_tc = tc && vjp && convtc_wgrad_ok(geo) && !getenv("LRNDE_CONV_WG_SIMT");
+    Phi.assign(m->conv.size(), nullptr); Plo.assign(m->conv.size(), nullptr);
     z.assign(L, nullptr); ab.assign(L, nullptr); stat.assign(L, nullptr); pack.assign(L, nullptr); packT.assign(L, nullptr);
     wimg.assign(L, nullptr); wimgT.assign(L, nullptr); tsum.assign(L, nullptr);
     for (int l = 0; l < L; ++l) {
@@ -390,10 +396,11 @@ struct ConvEval {
       maxC = std::max(maxC, std::max(Li.cin, Li.cout));
       nblk_max = std::max(nblk_max, conv_nblk(Li.cout) * Li.cout);
       if (tc) {
-        nblk_max = std::max(nblk_max, geo.ngroups * 4 * Li.cout);
+        nblk_max = std::max(nblk_max, geo.ngroups * 8 * std::max(Li.cout, Li.cin));
         wimg[l] = (uint8_t*)ctx->alloc(convtc_wimg_bytes(Li.cin, convtc_nout(Li.cout)));
         if (m->td) tsum[l] = (float*)ctx->alloc(4 * 64 * (size_t)convtc_nout(Li.cout));
         if (vjp) wimgT[l] = (uint8_t*)ctx->alloc(convtc_wimg_bytes(Li.cout, convtc_nout(Li.cin)));
+        if (wg_tc) { Phi[l] = (float*)ctx->alloc(4 * HW * Li.cin * B); Plo[l] = (float*)ctx->alloc(4 * HW * Li.cin * B); }
       }
       const size_t nw = (size_t)9 * (Li.cin + m->td) * Li.cout;
       pack[l] = (float*)ctx->alloc(4 * nw);
@@ -431,6 +438,11 @@ struct ConvEval {
         S = (int)((B + img - 1) / img);
         wS.push_back(S); wImg.push_back(img); wCic.push_back(cic); wChunks.push_back(chunks); wSwap.push_back(swapped ? 1 : 0);
         maxpart = std::max(maxpart, (size_t)S * 9 * cintot * Li.cout);
+        if (wg_tc) maxpart = std::max(maxpart, (size_t)convtc_wgrad_splits(geo) * 9 * cintot * Li.cout);
+      }
+      if (wg_tc) {
+        PDhi = (float*)ctx->alloc(4 * HW * maxC * B); PDlo = (float*)ctx->alloc(4 * HW * maxC * B);
+        rowsum = (float*)ctx->alloc(4 * (size_t)3 * m->Ht * maxC * B);
       }
       part = (float*)ctx->alloc(4 * maxpart);
       bnS = std::max(1, std::min((int)B, 16));
@@ -451,6 +463,9 @@ struct ConvEval {
     for (auto p : wimgT) ctx->release(p);
     for (auto p : tsum) ctx->release(p);
     ctx->release(Fhi); ctx->release(Flo);
+    for (auto p : Phi) ctx->release(p);
+    for (auto p : Plo) ctx->release(p);
+    ctx->release(PDhi); ctx->release(PDlo); ctx->release(rowsum);
     ctx->release(spart); ctx->release(ybuf); ctx->release(lbuf); ctx->release(G[0]); ctx->release(G[1]);
     ctx->release(part); ctx->release(bpart); ctx->release(coef); ctx->release(dgb);
   }
@@ -495,7 +510,7 @@ struct ConvEval {
     LR_CHECK_LAUNCH();
   }
 
-  int stat_nblk(int cout) const { return tc ? geo.ngroups * 4 : conv_nblk(cout); }
+  int stat_nblk(int cout) const { return tc ? convtc_stat_rows(geo, cout) : conv_nblk(cout); }
   // tensor-core convolution of (F): packed operand -> [W,H,Cout,B]
   void launch_tc(const uint8_t* img, int K, const float* ts, const LinComb* tdesc, float* Y, const LinComb* ydesc, float scale,
                  int cout, float2* sp, const int* done) {
@@ -517,7 +532,7 @@ struct ConvEval {
 
   // layers 0..upto-1 of the dynamics on lincomb(in); `side` / `side_desc`: keep the combined input
   void run_layers(const LinComb* in, const int* done, int upto, const LinComb* out, bool side_to_in_dst, float* side,
-                  bool update_state) {
+                  bool update_state, bool plain = false) {
     const int ncalls = (update_state && first_call_twice) ? 2 : 1;
     if (update_state) first_call_twice = false;
     for (int l = 0; l < upto; ++l) {
@@ -528,6 +543,7 @@ struct ConvEval {
         if (l == 0) { pk.xdesc = in; pk.side_to_desc_dst = side_to_in_dst ? 1 : 0; pk.side = side; pk.in_act = ACT_IDENTITY; }
         else { pk.X = z[l - 1]; pk.in_ab = m->conv[l - 1].bn ? ab[l - 1] : nullptr; pk.in_act = m->conv[l - 1].act; }
         pk.Fhi = Fhi; pk.Flo = Flo; pk.C = Li.cin; pk.done = done;
+        if (plain) { pk.Phi = Phi[l]; pk.Plo = Plo[l]; }
         convtc_pack(ctx, geo, pk);
         launch_tc(wimg[l], Li.cin, m->td ? tsum[l] : nullptr, m->td ? in : nullptr, l == L - 1 ? nullptr : z[l],
                   l == L - 1 ? (out ? out : in) : nullptr, 1.0f, Li.cout, (Li.bn && !testmode) ? spart : nullptr, done);
@@ -559,8 +575,81 @@ struct ConvEval {
     LR_CHECK_LAUNCH();
   }
 
+
+  // the reverse pass with every contraction on the tensor cores: the pack kernel writes each activation and each
+  // cotangent once as the (F) operand of the next convolution and as the plain hi / lo operand of the weight gradient
+  void vjp_tc(const LinComb* y, const LinComb* lamd, float* out_a, const LinComb* out_desc, float a_scale,
+              float* dps_ptr, const LinComb* dps_desc, size_t dps_off, float p_scale, float p_beta, const int* done) {
+    cudaStream_t st = ctx->stream;
+    if (L > 1) run_layers(y, done, L - 1, nullptr, false, nullptr, false, true);   // recompute, operands of dW_0..L-2 kept
+    {   // input of the last layer: only its plain image is needed (the forward convolution is not recomputed)
+      ConvTcPackP pk;
+      memset(&pk, 0, sizeof(pk));
+      if (L == 1) { pk.xdesc = y; pk.in_act = ACT_IDENTITY; }
+      else { pk.X = z[L - 2]; pk.in_ab = m->conv[L - 2].bn ? ab[L - 2] : nullptr; pk.in_act = m->conv[L - 2].act; }
+      pk.Phi = Phi[L - 1]; pk.Plo = Plo[L - 1]; pk.C = m->conv[L - 1].cin; pk.done = done;
+      convtc_pack(ctx, geo, pk);
+    }
+    {   // cotangent of the output
+      ConvTcPackP pk;
+      memset(&pk, 0, sizeof(pk));
+      pk.xdesc = lamd; pk.in_act = ACT_IDENTITY; pk.Fhi = Fhi; pk.Flo = Flo; pk.Phi = PDhi; pk.Plo = PDlo;
+      pk.rowsum = m->td ? rowsum : nullptr;
+      pk.C = m->conv[L - 1].cout; pk.done = done;
+      convtc_pack(ctx, geo, pk);
+    }
+    const int S = convtc_wgrad_splits(geo);
+    int cur = 0;
+    for (int l = L - 1; l >= 0; --l) {
+      const ConvLayerInfo& Li = m->conv[l];
+      const int cintot = Li.cin + m->td;
+      const size_t nw = (size_t)9 * cintot * Li.cout;
+      ConvTcWgP w;
+      memset(&w, 0, sizeof(w));
+      w.Xhi = Phi[l]; w.Xlo = Plo[l]; w.Cx = Li.cin; w.Dhi = PDhi; w.Dlo = PDlo; w.Cd = Li.cout; w.CinTot = cintot;
+      w.part = part; w.block = nw; w.tdesc = m->td ? y : nullptr; w.Drowsum = rowsum; w.done = done;
+      convtc_wgrad(ctx, geo, w);
+      wgrad_reduce_kernel<<<lr_ew_blocks(nw), 256, 0, st>>>(part, S, nw, dps_ptr ? dps_ptr + Li.w_off : nullptr, dps_desc,
+                                                           dps_off + (size_t)Li.w_off, p_scale, p_beta, done);
+      LR_COUNT(ctx);
+      if (l == 0) {
+        launch_tc(wimgT[l], Li.cout, nullptr, nullptr, out_a, out_a ? nullptr : out_desc, a_scale, Li.cin, nullptr, done);
+      } else {
+        const ConvLayerInfo& Lp = m->conv[l - 1];
+        {
+          ConvTcP q;
+          memset(&q, 0, sizeof(q));
+          q.Fhi = Fhi; q.Flo = Flo; q.Wimg = wimgT[l]; q.K = Li.cout; q.Y = G[cur]; q.out_scale = 1.0f; q.Cout = Li.cin; q.done = done;
+          if (Lp.bn) { q.stat_part = spart; q.bwd_z = z[l - 1]; q.bwd_ab = ab[l - 1]; q.bwd_stat = stat[l - 1]; q.bwd_act = Lp.act; }
+          convtc_conv(ctx, geo, q);
+        }
+        ConvTcPackP pk;
+        memset(&pk, 0, sizeof(pk));
+        pk.Fhi = Fhi; pk.Flo = Flo; pk.Phi = PDhi; pk.Plo = PDlo; pk.C = Lp.cout; pk.done = done; pk.in_act = ACT_IDENTITY;
+        pk.rowsum = m->td ? rowsum : nullptr;
+        if (Lp.bn) {
+          bn_bwd_finalize_tc_kernel<<<Lp.cout, 128, 0, st>>>(spart, convtc_stat_rows(geo, Lp.cout), Lp.cout, (double)HW * (double)B, coef, dgb, testmode,
+                                                            done, ctx->bn_dist());
+          LR_COUNT(ctx);
+          wgrad_reduce_kernel<<<1, 256, 0, st>>>(dgb, 1, (size_t)2 * Lp.cout, dps_ptr ? dps_ptr + Lp.g_off : nullptr, dps_desc,
+                                               dps_off + (size_t)Lp.g_off, p_scale, p_beta, done);
+          LR_COUNT(ctx);
+          pk.X = z[l - 1]; pk.bwd_g = G[cur]; pk.in_ab = ab[l - 1]; pk.bwd_stat = stat[l - 1]; pk.bwd_coef = coef; pk.bwd_act = Lp.act;
+        } else if (Lp.act != ACT_IDENTITY) {
+          pk.X = z[l - 1]; pk.bwd_g = G[cur]; pk.bwd_act = Lp.act;
+        } else {
+          pk.X = G[cur];
+        }
+        convtc_pack(ctx, geo, pk);
+        cur ^= 1;
+      }
+    }
+    LR_CHECK_LAUNCH();
+  }
+
   void vjp(const LinComb* y, const LinComb* lamd, float* out_a, const LinComb* out_desc, float a_scale,
            float* dps_ptr, const LinComb* dps_desc, size_t dps_off, float p_scale, float p_beta, const int* done) {
+    if (wg_tc) { vjp_tc(y, lamd, out_a, out_desc, a_scale, dps_ptr, dps_desc, dps_off, p_scale, p_beta, done); return; }
     cudaStream_t st = ctx->stream;
     const size_t DB = (size_t)m->D * B;
     if (L > 1) run_layers(y, done, L - 1, nullptr, false, ybuf, false);     // recompute; y(t) kept for dW_1

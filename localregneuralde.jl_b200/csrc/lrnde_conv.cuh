@@ -438,6 +438,34 @@ __global__ void bn_bwd_finalize_kernel(const double2* part, int S, int C, double
   coef[C + c] = testmode ? 0.0f : (float)(t2 / count);
 }
 
+// the same from the (sum ghat, sum ghat xhat) partials of the tensor-core data-gradient convolution's epilogue
+// (part[block][C] float2, like bn_finalize_kernel); grid = C blocks of 128 threads
+__global__ void __launch_bounds__(128) bn_bwd_finalize_tc_kernel(const float2* part, int nblk, int C, double count, float* coef,
+                                                                 float* dgb, int testmode, const int* done, BnDist dist) {
+  if (done && *done) return;
+  __shared__ double s1[128], s2[128];
+  const int c = blockIdx.x, tid = threadIdx.x;
+  double a1 = 0.0, a2 = 0.0;
+  for (int i = tid; i < nblk; i += 128) {
+    const float2 v = part[(size_t)i * C + c];
+    a1 += (double)v.x; a2 += (double)v.y;
+  }
+  s1[tid] = a1; s2[tid] = a2;
+  __syncthreads();
+  for (int o = 64; o > 0; o >>= 1) {
+    if (tid < o) { s1[tid] += s1[tid + o]; s2[tid] += s2[tid + o]; }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    double t1 = s1[0], t2 = s2[0];
+    dgb[c] = (float)t2;
+    dgb[C + c] = (float)t1;
+    if (!testmode) lr_bn_group_sum(dist, c, t1, t2, count);
+    coef[c] = testmode ? 0.0f : (float)(t1 / count);
+    coef[C + c] = testmode ? 0.0f : (float)(t2 / count);
+  }
+}
+
 // g <- gamma invstd (ghat - m1 - xhat m2) in place; coef == nullptr: plain activation pullback g <- g act'(z)
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(float* g, const float* z, const float* ab,
                                                            const float* stat, const float* coef, int act, int C,

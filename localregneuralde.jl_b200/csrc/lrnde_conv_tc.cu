@@ -42,14 +42,35 @@ __host__ __device__ constexpr int stage_bytes(int NOUT) { return 4 * kRunB + wst
 
 // ---------------------------------------------------------------------------------------------------------
 // pack: one pass over an activation, everything element-wise between two convolutions, hi / lo split
-// grid (B * (Ht + 2), 1), block 256 = 64 haloed columns x 4 channel-chunk lanes
 // ---------------------------------------------------------------------------------------------------------
+// derivative of the activation in the pullback epilogue: ONE out-of-line body (sixteen call sites per loop: inlining the
+// five-way switch with its tanhf / expf sixty-four times made the kernel instruction-fetch bound, 100 -> 750 us)
+__device__ __noinline__ float dact_call(int act, float x) {
+  if (act == ACT_GELU) {   // tanh through exp: absolute error ~2e-7
+    const float inner = 0.7978845608028654f * (x + 0.044715f * x * x * x);
+    const float th = 1.0f - __fdividef(2.0f, __expf(2.0f * inner) + 1.0f);
+    const float dinner = 0.7978845608028654f * (1.0f + 3.0f * 0.044715f * x * x);
+    return 0.5f * (1.0f + th) + 0.5f * x * (1.0f - th * th) * dinner;
+  }
+  return lr_dact(act, x);
+}
+
+__device__ __noinline__ float act_call(int act, float x) {
+  if (act == ACT_GELU) {
+    const float inner = 0.7978845608028654f * (x + 0.044715f * x * x * x);
+    return x * (1.0f - __fdividef(1.0f, __expf(2.0f * inner) + 1.0f));   // 0.5 x (1 + tanh(inner)) = x (1 - 1 / (e^{2 inner} + 1))
+  }
+  return lr_act(act, x);
+}
+
 struct PackK {
   ConvTcPackP p;
   int Wd, Ht, PW, PH, IMG;
   long NPA;
 };
 
+// one block = one image row (b, y); warp w owns the channel chunks c4 = w, w + 8, ...; lane = x (two passes when Wd > 32).
+// The halo positions of (F) are zero from the allocation on and no pack ever writes them.
 __global__ void __launch_bounds__(256) pack_kernel(PackK k) {
   const ConvTcPackP& p = k.p;
   if (p.done && *p.done) return;
@@ -58,47 +79,61 @@ __global__ void __launch_bounds__(256) pack_kernel(PackK k) {
     if (threadIdx.x == 0) xd = *p.xdesc;
     __syncthreads();
   }
-  const int xh = threadIdx.x & 63, cl = threadIdx.x >> 6;
-  if (xh >= k.PW) return;
-  const int b = blockIdx.x / k.PH, yh = blockIdx.x % k.PH;
-  const bool inside = xh >= 1 && xh <= k.Wd && yh >= 1 && yh <= k.Ht;
-  const int x = xh - 1, y = yh - 1;
-  const size_t pos = (size_t)kCtGuard + (size_t)b * k.IMG + (size_t)yh * k.PW + xh;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x / k.Ht, y = blockIdx.x % k.Ht;
   float* side = p.side_to_desc_dst ? xd.dst : p.side;
   const int C4 = p.C >> 2;
-  for (int c4 = cl; c4 < C4; c4 += 4) {
-    float hi[4] = {0.0f, 0.0f, 0.0f, 0.0f}, lo[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-    if (inside) {
+  const size_t HW = (size_t)k.Wd * k.Ht;
+  for (int x = lane; x < k.Wd; x += 32) {
+    const size_t pos = (size_t)kCtGuard + (size_t)b * k.IMG + (size_t)(y + 1) * k.PW + (x + 1);
+    const size_t pix = x + (size_t)k.Wd * y;
+#pragma unroll 1
+    for (int c4 = warp; c4 < C4; c4 += 8) {
+      const size_t idx0 = pix + HW * ((size_t)c4 * 4 + (size_t)p.C * b);
+      float v[4], g[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const size_t idx = idx0 + HW * j;
+        v[j] = p.xdesc ? lr_lincomb_at_tc(xd, idx) : __ldcg(p.X + idx);
+        g[j] = p.bwd_g ? __ldcg(p.bwd_g + idx) : 0.0f;
+      }
+      float hi[4], lo[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int c = c4 * 4 + j;
-        const size_t idx = x + (size_t)k.Wd * (y + (size_t)k.Ht * (c + (size_t)p.C * b));
-        float v;
-        if (p.xdesc) {
-          v = lr_lincomb_at_tc(xd, idx);
-          if (side) side[idx] = v;
-        } else v = __ldcg(p.X + idx);
+        const size_t idx = idx0 + HW * j;
+        float r = v[j];
+        if (p.xdesc && side) side[idx] = r;
         if (p.bwd_g) {
-          const float g = __ldcg(p.bwd_g + idx);
           if (p.bwd_coef) {
             const float a = p.in_ab[c], bb = p.in_ab[p.C + c];
-            const float gh = g * lr_dact(p.bwd_act, fmaf(a, v, bb));
-            const float xhat = (v - p.bwd_stat[c]) * p.bwd_stat[p.C + c];
-            v = a * (gh - p.bwd_coef[c] - xhat * p.bwd_coef[p.C + c]);
-          } else v = g * lr_dact(p.bwd_act, v);
+            const float gh = g[j] * dact_call(p.bwd_act, fmaf(a, r, bb));
+            const float xhat = (r - p.bwd_stat[c]) * p.bwd_stat[p.C + c];
+            r = a * (gh - p.bwd_coef[c] - xhat * p.bwd_coef[p.C + c]);
+          } else r = g[j] * dact_call(p.bwd_act, r);
         } else {
-          if (p.in_ab) v = fmaf(p.in_ab[c], v, p.in_ab[p.C + c]);
-          if (p.in_act != ACT_IDENTITY) v = lr_act(p.in_act, v);
+          if (p.in_ab) r = fmaf(p.in_ab[c], r, p.in_ab[p.C + c]);
+          if (p.in_act != ACT_IDENTITY) r = act_call(p.in_act, r);
         }
-        hi[j] = tf32_rna(v);
-        lo[j] = tf32_rna(v - hi[j]);
+        hi[j] = tf32_rna(r);
+        lo[j] = tf32_rna(r - hi[j]);
         if (p.Phi) { p.Phi[idx] = hi[j]; p.Plo[idx] = lo[j]; }
+        if (p.rowsum) {   // (Wd == 32) sum over the image row, its first and last pixel: the time channel's weight gradient
+          float sum = r;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+          const float last = __shfl_sync(0xffffffffu, r, 31);
+          if (lane == 0) {
+            float* dst = p.rowsum + ((size_t)blockIdx.x * p.C + c) * 3;
+            dst[0] = sum; dst[1] = r; dst[2] = last;
+          }
+        }
       }
-    }
-    if (p.Fhi) {
-      const size_t o = ((size_t)c4 * (size_t)k.NPA + pos) * 4;
-      *reinterpret_cast<float4*>(p.Fhi + o) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-      *reinterpret_cast<float4*>(p.Flo + o) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+      if (p.Fhi) {
+        const size_t o = ((size_t)c4 * (size_t)k.NPA + pos) * 4;
+        *reinterpret_cast<float4*>(p.Fhi + o) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<float4*>(p.Flo + o) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+      }
     }
   }
 }
@@ -169,8 +204,10 @@ __device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
   return v[0];
 }
 
-template <int NOUT>
-__global__ void __launch_bounds__(kThreads, 1) conv_kernel(ConvK k) {
+constexpr int kConvThreads = 64 + 256;   // warp 0: bulk copies, warp 1: tcgen05.mma, warps 2..9: epilogue (two per TMEM lane quarter)
+// MODE 0: plain epilogue; 1: + (sum, sum of squares) of the raw output; 2: + the two sums of the BatchNorm pullback
+template <int NOUT, int MODE>
+__global__ void __launch_bounds__(kConvThreads, 1) conv_kernel(ConvK k) {
   const ConvTcP& p = k.p;
   if (p.done && *p.done) return;
   constexpr int STB = stage_bytes(NOUT), WSB = wstage_bytes(NOUT);
@@ -186,7 +223,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_kernel(ConvK k) {
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1u); mbar_init(&empty_bar[s], 1u); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1u); mbar_init(&tmem_free[s], 4u); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1u); mbar_init(&tmem_free[s], 8u); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -260,59 +297,63 @@ __global__ void __launch_bounds__(kThreads, 1) conv_kernel(ConvK k) {
       }
     }
   } else {
-    // ---------------- epilogue: lane = position (coalesced along x), registers = 16 output channels at a time
-    const int q = warp & 3;
+    // ---------------- epilogue: lane = position (coalesced along x), registers = 16 output channels at a time;
+    // the two warps of a lane quarter take alternate 16-channel chunks (NOUT = 16: alternate tiles)
+    const int q = warp & 3, half = (warp - 2) >> 2;
     const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
     float* out = p.ydesc ? p.ydesc->dst : p.Y;
     const float tval = p.tdesc ? p.tdesc->t : 0.0f;
     const size_t HW = (size_t)k.Wd * k.Ht;
+    constexpr int NCC = NOUT / 16;
     int it = 0;
     for (int g = blockIdx.x; g < k.ngroups; g += gridDim.x, ++it) {
       const int db = it & 1;
-      size_t obase[kTiles];
-      int cls[kTiles];
-      bool valid[kTiles];
-#pragma unroll
-      for (int i = 0; i < kTiles; ++i) {
-        const long pp = (long)g * kCtGroup + i * 128 + q * 32 + lane;
-        const int b = (int)(pp / k.IMG), r = (int)(pp % k.IMG);
-        const int yh = r / k.PW, xh = r % k.PW;
-        valid[i] = pp < k.NP && xh >= 1 && xh <= k.Wd && yh >= 1 && yh <= k.Ht;
-        const int x = xh - 1, y = yh - 1;
-        obase[i] = (size_t)x + (size_t)k.Wd * ((size_t)y + (size_t)k.Ht * ((size_t)p.Cout * b));
-        const int ym = (y > 0 ? 1 : 0) | 2 | (y < k.Ht - 1 ? 4 : 0), xm = (x > 0 ? 1 : 0) | 2 | (x < k.Wd - 1 ? 4 : 0);
-        cls[i] = (ym * 8 + xm) * NOUT;
-      }
       mbar_wait(&acc_full[db], (uint32_t)((it >> 1) & 1));
       tc_fence_after();
 #pragma unroll 1
-      for (int cc = 0; cc < NOUT / 16; ++cc) {
+      for (int cc = (NCC > 1 ? half : 0); cc < NCC; cc += (NCC > 1 ? 2 : 1)) {
         float st[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) st[j] = 0.0f;
-#pragma unroll
-        for (int i = 0; i < kTiles; ++i) {
+#pragma unroll 1
+        for (int i = (NCC > 1 ? 0 : half); i < kTiles; i += (NCC > 1 ? 1 : 2)) {
+          const long pp = (long)g * kCtGroup + i * 128 + q * 32 + lane;
+          const int b = (int)(pp / k.IMG), r0 = (int)(pp % k.IMG);
+          const int yh = r0 / k.PW, xh = r0 % k.PW;
+          const bool valid = pp < k.NP && xh >= 1 && xh <= k.Wd && yh >= 1 && yh <= k.Ht;
+          const int x = xh - 1, y = yh - 1;
+          const size_t obase = (size_t)x + (size_t)k.Wd * ((size_t)y + (size_t)k.Ht * ((size_t)p.Cout * b)) + (size_t)(cc * 16) * HW;
+          const int ym = (y > 0 ? 1 : 0) | 2 | (y < k.Ht - 1 ? 4 : 0), xm = (x > 0 ? 1 : 0) | 2 | (x < k.Wd - 1 ? 4 : 0);
+          const float* ts = p.tsum ? p.tsum + (ym * 8 + xm) * NOUT + cc * 16 : nullptr;
           float v[16];
           tmem_ld16(tlane + (uint32_t)(db * kTiles * NOUT + i * NOUT + cc * 16), v);
-          if (valid[i]) {
+          if (valid) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const int co = cc * 16 + j;
               if (co < p.Cout) {
                 float r = v[j];
-                if (p.tsum) r = fmaf(tval, __ldg(p.tsum + cls[i] + co), r);
-                st[j] += r;
-                st[16 + j] = fmaf(r, r, st[16 + j]);
-                out[obase[i] + (size_t)co * HW] = r * p.out_scale;
+                if (ts) r = fmaf(tval, __ldg(ts + j), r);
+                if (MODE == 1) {
+                  st[j] += r;
+                  st[16 + j] = fmaf(r, r, st[16 + j]);
+                } else if (MODE == 2) {
+                  const float zz = __ldcg(p.bwd_z + obase + (size_t)j * HW);
+                  const float gh = r * dact_call(p.bwd_act, fmaf(__ldg(p.bwd_ab + co), zz, __ldg(p.bwd_ab + p.Cout + co)));
+                  st[j] += gh;
+                  st[16 + j] = fmaf(gh, (zz - __ldg(p.bwd_stat + co)) * __ldg(p.bwd_stat + p.Cout + co), st[16 + j]);
+                }
+                out[obase + (size_t)j * HW] = r * p.out_scale;
               }
             }
           }
         }
-        if (p.stat_part) {
+        if (MODE != 0) {
           const float tot = warp_transpose_sum(st, lane);
           const int co = cc * 16 + (lane & 15);
-          if (co < p.Cout)
-            reinterpret_cast<float*>(p.stat_part + ((size_t)g * 4 + q) * p.Cout + co)[lane >> 4] = tot;
+          // NOUT = 16: the two warps of a quarter saw different tiles of the same channels -> separate partial rows
+          const size_t row = (NCC > 1) ? ((size_t)g * 4 + q) : (((size_t)g * 4 + q) * 2 + half);
+          if (co < p.Cout) reinterpret_cast<float*>(p.stat_part + row * p.Cout + co)[lane >> 4] = tot;
         }
       }
       tc_fence_before();
@@ -328,6 +369,267 @@ __global__ void __launch_bounds__(kThreads, 1) conv_kernel(ConvK k) {
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// weight gradient (Wd == 32): see lrnde_conv_tc.h
+//   step i of a CTA = P row t = t0 + i (flattened (image, row) index): tensor-map TMA delivers the tile [64 channels]
+//   [32 pixels] (K-major SWIZZLE_128B, hi and lo); warps 2..5 write its two dx-shifted, zero-padded copies next to it
+//   (a TMA box cannot start at a pixel that is not a multiple of 16 bytes: measured, scratch/mb/tma_test.cu); Q rows
+//   t - 1, t, t + 1 of the same image are the B operands of the taps dy = +1, 0, -1.
+//   A (M = 128) = two adjacent P tiles: (dx = -1, dx = 0) and (dx = +1, whatever follows: rows 64..127 are ignored)
+//   TMEM: accumulator (dy, mt) at columns (dy * 2 + mt) * NB
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kWgXS = 3, kWgQS = 4;                 // ring slots: P rows, Q rows
+constexpr int kWgPTile = 64 * 128;                  // one P tile (hi or lo)
+constexpr int kWgXSlot = 6 * kWgPTile;              // [hi dx-1 | hi dx0 | hi dx+1 | lo dx-1 | lo dx0 | lo dx+1]
+
+struct WgK {
+  int Ht, nrows_total, rows_per_cta;
+  int Pc, Qc, swapped, CinTot, Cd;
+  float* part; size_t block;
+  const int* done;
+  int dbg;   // LRNDE_WG_DBG (bring-up): 1 = no TMA / MMA, 2 = TMA but no MMA
+};
+
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+template <int NB>
+__global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constant__ CUtensorMap mPhi, const __grid_constant__ CUtensorMap mPlo,
+                                                            const __grid_constant__ CUtensorMap mQhi, const __grid_constant__ CUtensorMap mQlo,
+                                                            WgK k) {
+  if (k.done && *k.done) return;
+  constexpr int QT = NB * 128;           // one Q tile (hi or lo)
+  constexpr int QSLOT = 2 * QT;
+  constexpr uint32_t TCOLS = (6 * NB <= 128) ? 128u : 512u;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* sm = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smQ = sm + kWgXS * kWgXSlot;
+  __shared__ uint64_t x_full[kWgXS], s_full[kWgXS], x_empty[kWgXS], q_full[kWgQS], q_empty[kWgQS], acc_done;
+  __shared__ uint32_t tmem_slot;
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const int t0 = blockIdx.x * k.rows_per_cta;
+  const int n = min(k.rows_per_cta, k.nrows_total - t0);   // >= 1 by construction of the grid
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kWgXS; ++s) { mbar_init(&x_full[s], 1u); mbar_init(&s_full[s], 4u); mbar_init(&x_empty[s], 1u); }
+    for (int s = 0; s < kWgQS; ++s) { mbar_init(&q_full[s], 1u); mbar_init(&q_empty[s], 1u); }
+    mbar_init(&acc_done, 1u);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(TCOLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (k.dbg & 1) {
+    if (warp >= 2) {
+      float* out = k.part + (size_t)blockIdx.x * k.block;
+      for (size_t e = threadIdx.x - 64; e < k.block; e += 128) out[e] = 0.0f;
+    }
+  } else if (warp == 0) {
+    // ---------------- TMA: Q row j <-> flattened row u = t0 - 1 + j; P row i <-> t0 + i
+    auto load_q = [&](int j) {
+      const int slot = j % kWgQS;
+      if (j >= kWgQS) mbar_wait(&q_empty[slot], (uint32_t)(((j / kWgQS) - 1) & 1));
+      if (elect_one_sync()) {
+        const int u = t0 - 1 + j;
+        // rows in front of / behind the batch: coordinates outside the tensor (zero fill); they are never multiplied
+        const int b = (u < 0) ? -1 : u / k.Ht, y = (u < 0) ? 0 : u % k.Ht;
+        uint8_t* dst = smQ + (size_t)slot * QSLOT;
+        mbar_arrive_expect_tx(&q_full[slot], (uint32_t)QSLOT);
+        tma_load_4d(dst, &mQhi, 0, y, 0, b, &q_full[slot]);
+        tma_load_4d(dst + QT, &mQlo, 0, y, 0, b, &q_full[slot]);
+      }
+      __syncwarp();
+    };
+    load_q(0);
+    load_q(1);
+    for (int i = 0; i < n; ++i) {
+      const int slot = i % kWgXS;
+      if (i >= kWgXS) mbar_wait(&x_empty[slot], (uint32_t)(((i / kWgXS) - 1) & 1));
+      if (elect_one_sync()) {
+        const int t = t0 + i, b = t / k.Ht, y = t % k.Ht;
+        uint8_t* dst = sm + (size_t)slot * kWgXSlot;
+        mbar_arrive_expect_tx(&x_full[slot], (uint32_t)(2 * kWgPTile));
+        tma_load_4d(dst + 1 * kWgPTile, &mPhi, 0, y, 0, b, &x_full[slot]);
+        tma_load_4d(dst + 4 * kWgPTile, &mPlo, 0, y, 0, b, &x_full[slot]);
+      }
+      __syncwarp();
+      load_q(i + 2);
+    }
+  } else if (warp == 1) {
+    // ---------------- tcgen05.mma issue
+    const uint32_t idesc = make_idesc(128, NB);
+    uint32_t touched = 0;
+    int q_arrived = 0;
+    for (int i = 0; i < n; ++i) {
+      const int xs = i % kWgXS;
+      mbar_wait(&s_full[xs], (uint32_t)((i / kWgXS) & 1));
+      while (q_arrived <= i + 2) {
+        mbar_wait(&q_full[q_arrived % kWgQS], (uint32_t)((q_arrived / kWgQS) & 1));
+        ++q_arrived;
+      }
+      tc_fence_after();
+      const int yy = (t0 + i) % k.Ht;
+      if (elect_one_sync()) {
+        const uint32_t xb = smem_u32(sm + (size_t)xs * kWgXSlot);
+#pragma unroll 1
+        for (int dyi = 0; dyi < 3; ++dyi) {
+          const int dy = dyi - 1, y = yy - dy;
+          if (y < 0 || y >= k.Ht || (k.dbg & 2)) continue;
+          const int j = i + 1 - dy;
+          const uint32_t qb = smem_u32(smQ + (size_t)(j % kWgQS) * QSLOT);
+          const uint32_t qh = desc_lo(qb), ql = desc_lo(qb + QT);
+          const uint32_t fresh = ((touched >> dyi) & 1u) ? 1u : 0u;
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt) {
+            const uint32_t ah = desc_lo(xb + mt * 2 * kWgPTile), al = desc_lo(xb + 3 * kWgPTile + mt * 2 * kWgPTile);
+            const uint32_t d = tmem_base + (uint32_t)((dyi * 2 + mt) * NB);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              mma<0>(d, al + 2 * ks, qh + 2 * ks, fused::kHi128, idesc, (ks > 0) ? 1u : fresh);
+              mma<1>(d, ah + 2 * ks, ql + 2 * ks, fused::kHi128, idesc, 1u);
+              mma<2>(d, ah + 2 * ks, qh + 2 * ks, fused::kHi128, idesc, 1u);
+            }
+          }
+          touched |= 1u << dyi;
+        }
+        mma_commit(&x_empty[xs]);
+        mma_commit(&q_empty[i % kWgQS]);      // Q row j = i (flattened row t - 1): its last use was this step
+        if (i == n - 1) mma_commit(&acc_done);
+      }
+      touched = __shfl_sync(0xffffffffu, touched, 0) | touched;   // (the elected lane may change between steps)
+      touched = __reduce_or_sync(0xffffffffu, touched);
+      __syncwarp();
+    }
+  } else {
+    // ---------------- the dx = -1 / +1 copies of every P tile: thread = (hi | lo, channel row), conflict-free 16-byte accesses
+    {
+      const int tt = threadIdx.x - 64, c = tt & 63, sw = c & 7;
+      for (int i = 0; i < n; ++i) {
+        const int slot = i % kWgXS;
+        mbar_wait(&x_full[slot], (uint32_t)((i / kWgXS) & 1));
+        uint8_t* base = sm + (size_t)slot * kWgXSlot + (size_t)(tt >> 6) * 3 * kWgPTile + c * 128;
+        float f[34];
+        f[0] = 0.0f; f[33] = 0.0f;
+#pragma unroll
+        for (int qq = 0; qq < 8; ++qq) {
+          const float4 r = *reinterpret_cast<const float4*>(base + kWgPTile + ((qq ^ sw) << 4));
+          f[1 + 4 * qq] = r.x; f[2 + 4 * qq] = r.y; f[3 + 4 * qq] = r.z; f[4 + 4 * qq] = r.w;
+        }
+#pragma unroll
+        for (int qq = 0; qq < 8; ++qq) {   // f[1 + x] = P[x]: the dx = -1 tile holds P[x - 1], the dx = +1 tile P[x + 1]
+          *reinterpret_cast<float4*>(base + ((qq ^ sw) << 4)) = make_float4(f[4 * qq], f[4 * qq + 1], f[4 * qq + 2], f[4 * qq + 3]);
+          *reinterpret_cast<float4*>(base + 2 * kWgPTile + ((qq ^ sw) << 4)) =
+              make_float4(f[4 * qq + 2], f[4 * qq + 3], f[4 * qq + 4], f[4 * qq + 5]);
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_full[slot]);
+      }
+    }
+    // ---------------- epilogue: accumulators -> part[split][Lux layout]
+    const int q = warp & 3;
+    const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
+    float* out = k.part + (size_t)blockIdx.x * k.block;
+    if (k.CinTot > (k.swapped ? k.Qc : k.Pc))   // time channel: its entries of this split are zero (time_wgrad_kernel fills split 0)
+      for (int e = threadIdx.x - 64; e < 9 * k.Cd; e += 128)
+        out[(e % 9) + 9 * ((k.CinTot - 1) + (size_t)k.CinTot * (e / 9))] = 0.0f;
+    mbar_wait(&acc_done, 0u);
+    tc_fence_after();
+    const int m = q * 32 + lane;
+    const int pc = m & 63;
+#pragma unroll 1
+    for (int dyi = 0; dyi < 3; ++dyi) {
+      // a tap whose rows never met inside this CTA's range has an untouched accumulator: it contributes zero
+      bool met = false;
+      for (int i = 0; i < n && !met; ++i) { const int y = (t0 + i) % k.Ht - (dyi - 1); met = (y >= 0 && y < k.Ht); }
+#pragma unroll 1
+      for (int mt = 0; mt < 2; ++mt) {
+        const int dxi = mt * 2 + (m >> 6);
+#pragma unroll 1
+        for (int cc = 0; cc < NB / 16; ++cc) {
+          float v[16];
+          tmem_ld16(tlane + (uint32_t)((dyi * 2 + mt) * NB + cc * 16), v);
+          if (dxi < 3 && pc < k.Pc) {
+            // normal : P = X (ci = pc), Q = Delta (co = qc): accumulator (dy, dx) is the tap itself -> w[2 - dx, 2 - dy]
+            // swapped: P = Delta (co = pc) shifted by s, Q = X (ci = qc): tap d = -s -> w[dx, dy]
+            const int kx = k.swapped ? dxi : 2 - dxi, ky = k.swapped ? dyi : 2 - dyi;
+#pragma unroll
+            for (int jn = 0; jn < 16; ++jn) {
+              const int qc = cc * 16 + jn;
+              if (qc < k.Qc) {
+                const int ci = k.swapped ? qc : pc, co = k.swapped ? pc : qc;
+                out[kx + 3 * (ky + 3 * (ci + (size_t)k.CinTot * co))] = met ? v[jn] : 0.0f;
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TCOLS) : "memory");
+  }
+}
+
+// weight gradient of the time channel: dW[tap, time, co] = t * sum_{b, pixels p with p + d_tap inside the image} Delta[p, co]
+// = t * (T - [dy=-1] Top - [dy=+1] Bottom - [dx=-1] Left - [dx=+1] Right + the excluded corner), from the per-row
+// (sum, first, last) triples the pack kernel wrote while it formed Delta.  grid = Cd blocks; fixed-order tree: deterministic.
+// Written into split 0 of `part` (wgrad_kernel zero-fills the time entries of every split).
+__global__ void __launch_bounds__(256) time_wgrad_kernel(const float* __restrict__ rowsum, int Cd, int Ht, int nrows_total,
+                                                         const LinComb* tdesc, int Cx, int CinTot, float* part, const int* done) {
+  if (done && *done) return;
+  __shared__ double red[9][256];
+  const int c = blockIdx.x, tid = threadIdx.x;
+  double a[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};   // T, top, bottom, left, right, tl, tr, bl, br
+  for (int r = tid; r < nrows_total; r += 256) {
+    const float* src = rowsum + ((size_t)r * Cd + c) * 3;
+    const float s = src[0], v0 = src[1], v31 = src[2];
+    const int y = r % Ht;
+    a[0] += s; a[3] += v0; a[4] += v31;
+    if (y == 0) { a[1] += s; a[5] += v0; a[6] += v31; }
+    if (y == Ht - 1) { a[2] += s; a[7] += v0; a[8] += v31; }
+  }
+#pragma unroll
+  for (int q = 0; q < 9; ++q) red[q][tid] = a[q];
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (tid < o)
+#pragma unroll
+      for (int q = 0; q < 9; ++q) red[q][tid] += red[q][tid + o];
+    __syncthreads();
+  }
+  if (tid < 9) {
+    const int dy = tid / 3 - 1, dx = tid % 3 - 1;
+    double r = red[0][0];
+    if (dy == -1) r -= red[1][0];
+    if (dy == 1) r -= red[2][0];
+    if (dx == -1) r -= red[3][0];
+    if (dx == 1) r -= red[4][0];
+    if (dy == -1 && dx == -1) r += red[5][0];
+    if (dy == -1 && dx == 1) r += red[6][0];
+    if (dy == 1 && dx == -1) r += red[7][0];
+    if (dy == 1 && dx == 1) r += red[8][0];
+    part[(1 - dx) + 3 * ((1 - dy) + 3 * (Cx + (size_t)CinTot * c))] = tdesc->t * (float)r;   // w[2 - (dx + 1), 2 - (dy + 1), time, co]
+  }
+}
+
 }  // namespace convtc
 
 // ---------------------------------------------------------------------------------------------------------
@@ -336,17 +638,20 @@ __global__ void __launch_bounds__(kThreads, 1) conv_kernel(ConvK k) {
 void convtc_pack(lrnde_ctx* ctx, const ConvTcGeom& g, const ConvTcPackP& p) {
   convtc::PackK k;
   k.p = p; k.Wd = g.Wd; k.Ht = g.Ht; k.PW = g.PW; k.PH = g.PH; k.IMG = g.IMG; k.NPA = g.NPA;
-  convtc::pack_kernel<<<g.B * g.PH, 256, 0, ctx->stream>>>(k);
+  convtc::pack_kernel<<<g.B * g.Ht, 256, 0, ctx->stream>>>(k);
   LCT_COUNT(ctx);
 }
 
 static void convtc_attrs() {   // outside stream capture: the first call is prepare() -> convtc_wpack
   static bool attr_set = false;
   if (attr_set) return;
-  LR_CUDA(cudaFuncSetAttribute(convtc::conv_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               convtc::kStages * convtc::stage_bytes(64) + 256));
-  LR_CUDA(cudaFuncSetAttribute(convtc::conv_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               convtc::kStages * convtc::stage_bytes(16) + 256));
+  const int s64 = convtc::kStages * convtc::stage_bytes(64) + 256, s16 = convtc::kStages * convtc::stage_bytes(16) + 256;
+  LR_CUDA(cudaFuncSetAttribute(convtc::conv_kernel<64, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, s64));
+  LR_CUDA(cudaFuncSetAttribute(convtc::conv_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, s64));
+  LR_CUDA(cudaFuncSetAttribute(convtc::conv_kernel<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, s64));
+  LR_CUDA(cudaFuncSetAttribute(convtc::conv_kernel<16, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, s16));
+  LR_CUDA(cudaFuncSetAttribute(convtc::conv_kernel<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, s16));
+  LR_CUDA(cudaFuncSetAttribute(convtc::conv_kernel<16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, s16));
   attr_set = true;
 }
 
@@ -371,7 +676,69 @@ void convtc_conv(lrnde_ctx* ctx, const ConvTcGeom& g, const ConvTcP& p) {
   convtc::ConvK k;
   k.p = p; k.Wd = g.Wd; k.Ht = g.Ht; k.PW = g.PW; k.IMG = g.IMG; k.ngroups = g.ngroups; k.NP = g.NP; k.NPA = g.NPA;
   const int grid = std::min(g.ngroups, 148);
-  if (NOUT == 64) convtc::conv_kernel<64><<<grid, convtc::kThreads, smem64, ctx->stream>>>(k);
-  else convtc::conv_kernel<16><<<grid, convtc::kThreads, smem16, ctx->stream>>>(k);
+  const int mode = !p.stat_part ? 0 : (p.bwd_z ? 2 : 1);
+  const int T = convtc::kConvThreads;
+  if (NOUT == 64) {
+    if (mode == 0) convtc::conv_kernel<64, 0><<<grid, T, smem64, ctx->stream>>>(k);
+    else if (mode == 1) convtc::conv_kernel<64, 1><<<grid, T, smem64, ctx->stream>>>(k);
+    else convtc::conv_kernel<64, 2><<<grid, T, smem64, ctx->stream>>>(k);
+  } else {
+    if (mode == 0) convtc::conv_kernel<16, 0><<<grid, T, smem16, ctx->stream>>>(k);
+    else if (mode == 1) convtc::conv_kernel<16, 1><<<grid, T, smem16, ctx->stream>>>(k);
+    else convtc::conv_kernel<16, 2><<<grid, T, smem16, ctx->stream>>>(k);
+  }
   LCT_COUNT(ctx);
+}
+
+// ---- weight gradient
+bool convtc_wgrad_ok(const ConvTcGeom& g) { return g.Wd == 32; }
+static int wg_rows_per_cta(const ConvTcGeom& g) { return std::max(1, (g.B * g.Ht + 147) / 148); }
+int convtc_wgrad_splits(const ConvTcGeom& g) {
+  const int rows = g.B * g.Ht, rpc = wg_rows_per_cta(g);
+  return (rows + rpc - 1) / rpc;
+}
+static CUtensorMap wg_map(const float* base, const ConvTcGeom& g, int C, int boxC) {
+  CUtensorMap m;
+  const cuuint64_t dims[4] = {(cuuint64_t)g.Wd, (cuuint64_t)g.Ht, (cuuint64_t)C, (cuuint64_t)g.B};
+  const cuuint64_t strides[3] = {(cuuint64_t)g.Wd * 4, (cuuint64_t)g.Wd * g.Ht * 4, (cuuint64_t)g.Wd * g.Ht * C * 4};
+  const cuuint32_t box[4] = {32, 1, (cuuint32_t)boxC, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUresult r = cuTensorMapEncodeTiled(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, estr,
+                                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    lr_set_error("cuTensorMapEncodeTiled failed (%d) for a [%d,%d,%d,%d] tensor", (int)r, g.Wd, g.Ht, C, g.B);
+    throw LrError(LRNDE_ECUDA);
+  }
+  return m;
+}
+void convtc_wgrad(lrnde_ctx* ctx, const ConvTcGeom& g, const ConvTcWgP& p) {
+  static bool attr_set = false;
+  const int smem64 = convtc::kWgXS * convtc::kWgXSlot + convtc::kWgQS * 2 * 64 * 128 + 1024 + 8192;   // + the ignored rows of the last A tile
+  const int smem16 = convtc::kWgXS * convtc::kWgXSlot + convtc::kWgQS * 2 * 16 * 128 + 1024 + 8192;
+  if (!attr_set) {
+    LR_CUDA(cudaFuncSetAttribute(convtc::wgrad_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem64));
+    LR_CUDA(cudaFuncSetAttribute(convtc::wgrad_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem16));
+    attr_set = true;
+  }
+  const bool swapped = p.Cx < p.Cd;                 // the operand with fewer channels is Q
+  const int Pc = swapped ? p.Cd : p.Cx, Qc = swapped ? p.Cx : p.Cd;
+  const int NB = convtc_nout(Qc);
+  const CUtensorMap mPhi = wg_map(swapped ? p.Dhi : p.Xhi, g, Pc, 64), mPlo = wg_map(swapped ? p.Dlo : p.Xlo, g, Pc, 64);
+  const CUtensorMap mQhi = wg_map(swapped ? p.Xhi : p.Dhi, g, Qc, NB), mQlo = wg_map(swapped ? p.Xlo : p.Dlo, g, Qc, NB);
+  convtc::WgK k;
+  k.Ht = g.Ht; k.nrows_total = g.B * g.Ht; k.rows_per_cta = wg_rows_per_cta(g);
+  k.Pc = Pc; k.Qc = Qc; k.swapped = swapped ? 1 : 0; k.CinTot = p.CinTot; k.Cd = p.Cd;
+  k.part = p.part; k.block = p.block; k.done = p.done;
+  const char* dbg = getenv("LRNDE_WG_DBG");
+  k.dbg = dbg ? atoi(dbg) : 0;
+  const int grid = convtc_wgrad_splits(g);
+  if (k.dbg & 8) return;
+  if (NB == 64) convtc::wgrad_kernel<64><<<grid, convtc::kThreads, smem64, ctx->stream>>>(mPhi, mPlo, mQhi, mQlo, k);
+  else convtc::wgrad_kernel<16><<<grid, convtc::kThreads, smem16, ctx->stream>>>(mPhi, mPlo, mQhi, mQlo, k);
+  LCT_COUNT(ctx);
+  if (p.tdesc && !(k.dbg & 4)) {
+    convtc::time_wgrad_kernel<<<p.Cd, 256, 0, ctx->stream>>>(p.Drowsum, p.Cd, g.Ht, k.nrows_total, p.tdesc, p.Cx, p.CinTot, p.part, p.done);
+    LCT_COUNT(ctx);
+  }
 }

@@ -51,6 +51,7 @@ struct ConvTcPackP {
   const float* bwd_g; const float* bwd_stat; const float* bwd_coef; int bwd_act;
   float* Fhi; float* Flo;                   // (F) layout (may be null)
   float* Phi; float* Plo;                   // plain hi / lo (may be null)
+  float* rowsum;                            // [B * Ht][C][3]: (sum, first, last) of every image row of the result (Wd == 32; may be null)
   int C;
   const int* done;
 };
@@ -69,20 +70,30 @@ struct ConvTcP {
   const uint8_t* Wimg; int K;               // input channels (multiple of 8)
   const float* tsum; const LinComb* tdesc;  // time channel (null: none)
   float* Y; const LinComb* ydesc; float out_scale; int Cout;
-  float2* stat_part;                        // [ngroups * 4][Cout] (sum, sum of squares) of the raw output, or null
+  float2* stat_part;                        // [convtc_stat_rows(g, Cout)][Cout] (sum, sum of squares) of the raw output, or null
+  // data-gradient convolution followed by a BatchNorm + activation pullback: the statistics are the two sums of that
+  // pullback instead, (sum ghat, sum ghat xhat) with ghat = g act'(a z + b), xhat = (z - mean) invstd  (z: [W,H,Cout,B])
+  const float* bwd_z; const float* bwd_ab; const float* bwd_stat; int bwd_act;
   const int* done;
 };
 void convtc_conv(lrnde_ctx* ctx, const ConvTcGeom& g, const ConvTcP& p);
+inline int convtc_stat_rows(const ConvTcGeom& g, int cout) { return g.ngroups * (cout <= 16 ? 8 : 4); }
 
-// weight gradient on the tensor cores (Wd == 32 only): part[split][Lux weight layout], splits = convtc_wgrad_splits()
+// weight gradient on the tensor cores (Wd == 32): dW[tap, ci, co] = sum_{b,y,x} X[x + dx, y + dy, ci, b] Delta[x, y, co, b]
+// as GEMMs over the pixels of an image row (K = 32): the operand with more channels is "P" (M = 64 channels x 2 dx shifts
+// per MMA, tensor-map TMA delivers the three dx-shifted, zero-padded copies of a row), the other one "Q" (N = its
+// channels); the dy taps pair P row yy with Q rows yy - dy.  The image rows of the batch are split over the CTAs;
+// part[split][Lux weight layout] is summed by wgrad_reduce_kernel in fixed order.  The time channel's weight gradient
+// t * sum_{pixels whose tap stays inside the image} Delta is formed from nine masked sums by convtc_time_wgrad_kernel.
 struct ConvTcWgP {
-  const float* Xhi; const float* Xlo; int Cx;     // input of the convolution [W,H,Cx,B] (time channel excluded)
-  const float* Dhi; const float* Dlo; int Cd;     // cotangent of its output [W,H,Cd,B]
+  const float* Xhi; const float* Xlo; int Cx;     // input of the convolution [W,H,Cx,B] (time channel excluded), hi / lo
+  const float* Dhi; const float* Dlo; int Cd;     // cotangent of its output [W,H,Cd,B], hi / lo
   int CinTot;                                     // Cx + td: layout of the result
-  float* part; size_t block;
-  const LinComb* tdesc;                           // time channel: its weight gradient t * (masked sums of Delta)
-  const float* Dplain;                            // (unused when tdesc == null)
+  float* part; size_t block;                      // block = 9 * CinTot * Cd floats per split
+  const LinComb* tdesc;                           // time channel (null: none)
+  const float* Drowsum;                           // per-row sums of Delta written by the pack kernel (time channel only)
   const int* done;
 };
+bool convtc_wgrad_ok(const ConvTcGeom& g);         // Wd == 32
 int convtc_wgrad_splits(const ConvTcGeom& g);
 void convtc_wgrad(lrnde_ctx* ctx, const ConvTcGeom& g, const ConvTcWgP& p);
