@@ -14,6 +14,13 @@
 
 #define LCT_COUNT(ctx) do { if ((ctx)->capturing) (ctx)->captured++; else (ctx)->launches++; } while (0)
 
+// in-kernel timeline of CTA 0 (LRNDE_CT_DBG & 32): rows of 16 clock64 stamps
+__device__ long long g_ct_trace[8 * 16];
+#define CTRACE(row, it) do { if (ctrace_on && (it) < 16) g_ct_trace[(row) * 16 + (it)] = clock64(); } while (0)
+extern "C" int lrnde_debug_trace_convtc(long long* out, int n) {
+  return (int)cudaMemcpyFromSymbol(out, g_ct_trace, sizeof(long long) * (size_t)n);
+}
+
 namespace convtc {
 using namespace umma;
 using fused::mma;
@@ -45,23 +52,20 @@ __host__ __device__ constexpr int stage_bytes(int NOUT) { return 4 * kRunB + wst
 // ---------------------------------------------------------------------------------------------------------
 // derivative of the activation in the pullback epilogue: ONE out-of-line body (sixteen call sites per loop: inlining the
 // five-way switch with its tanhf / expf sixty-four times made the kernel instruction-fetch bound, 100 -> 750 us)
-__device__ __noinline__ float dact_call(int act, float x) {
-  if (act == ACT_GELU) {   // tanh through exp: absolute error ~2e-7
-    const float inner = 0.7978845608028654f * (x + 0.044715f * x * x * x);
-    const float th = 1.0f - __fdividef(2.0f, __expf(2.0f * inner) + 1.0f);
-    const float dinner = 0.7978845608028654f * (1.0f + 3.0f * 0.044715f * x * x);
-    return 0.5f * (1.0f + th) + 0.5f * x * (1.0f - th * th) * dinner;
-  }
-  return lr_dact(act, x);
+// gelu (tanh form, the Lux default of the cifar10 config) inline: sixteen independent chains per loop body
+__device__ __forceinline__ float gelu_d(float x) {   // tanh through exp: absolute error ~2e-7
+  const float inner = 0.7978845608028654f * (x + 0.044715f * x * x * x);
+  const float th = 1.0f - __fdividef(2.0f, __expf(2.0f * inner) + 1.0f);
+  const float dinner = 0.7978845608028654f * (1.0f + 3.0f * 0.044715f * x * x);
+  return 0.5f * (1.0f + th) + 0.5f * x * (1.0f - th * th) * dinner;
 }
+__device__ __forceinline__ float gelu_f(float x) {
+  const float inner = 0.7978845608028654f * (x + 0.044715f * x * x * x);
+  return x * (1.0f - __fdividef(1.0f, __expf(2.0f * inner) + 1.0f));   // 0.5 x (1 + tanh(inner)) = x (1 - 1 / (e^{2 inner} + 1))
+}
+__device__ __noinline__ float dact_call(int act, float x) { return act == ACT_GELU ? gelu_d(x) : lr_dact(act, x); }
 
-__device__ __noinline__ float act_call(int act, float x) {
-  if (act == ACT_GELU) {
-    const float inner = 0.7978845608028654f * (x + 0.044715f * x * x * x);
-    return x * (1.0f - __fdividef(1.0f, __expf(2.0f * inner) + 1.0f));   // 0.5 x (1 + tanh(inner)) = x (1 - 1 / (e^{2 inner} + 1))
-  }
-  return lr_act(act, x);
-}
+__device__ __noinline__ float act_call(int act, float x) { return act == ACT_GELU ? gelu_f(x) : lr_act(act, x); }
 
 struct PackK {
   ConvTcPackP p;
@@ -88,51 +92,63 @@ __global__ void __launch_bounds__(256) pack_kernel(PackK k) {
     const size_t pos = (size_t)kCtGuard + (size_t)b * k.IMG + (size_t)(y + 1) * k.PW + (x + 1);
     const size_t pix = x + (size_t)k.Wd * y;
 #pragma unroll 1
-    for (int c4 = warp; c4 < C4; c4 += 8) {
-      const size_t idx0 = pix + HW * ((size_t)c4 * 4 + (size_t)p.C * b);
-      float v[4], g[4];
+    for (int c4a = warp; c4a < C4; c4a += 16) {
+      // two chunks per pass (c4a, c4a + 8): every load of the pass is issued before the first out-of-line activation call
+      float v[2][4], g[2][4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const size_t idx = idx0 + HW * j;
-        v[j] = p.xdesc ? lr_lincomb_at_tc(xd, idx) : __ldcg(p.X + idx);
-        g[j] = p.bwd_g ? __ldcg(p.bwd_g + idx) : 0.0f;
-      }
-      float hi[4], lo[4];
+      for (int u = 0; u < 2; ++u) {
+        const int c4 = c4a + 8 * u;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int c = c4 * 4 + j;
-        const size_t idx = idx0 + HW * j;
-        float r = v[j];
-        if (p.xdesc && side) side[idx] = r;
-        if (p.bwd_g) {
-          if (p.bwd_coef) {
-            const float a = p.in_ab[c], bb = p.in_ab[p.C + c];
-            const float gh = g[j] * dact_call(p.bwd_act, fmaf(a, r, bb));
-            const float xhat = (r - p.bwd_stat[c]) * p.bwd_stat[p.C + c];
-            r = a * (gh - p.bwd_coef[c] - xhat * p.bwd_coef[p.C + c]);
-          } else r = g[j] * dact_call(p.bwd_act, r);
-        } else {
-          if (p.in_ab) r = fmaf(p.in_ab[c], r, p.in_ab[p.C + c]);
-          if (p.in_act != ACT_IDENTITY) r = act_call(p.in_act, r);
+        for (int j = 0; j < 4; ++j) {
+          const size_t idx = pix + HW * ((size_t)c4 * 4 + j + (size_t)p.C * b);
+          const bool ok = c4 < C4;
+          v[u][j] = !ok ? 0.0f : (p.xdesc ? lr_lincomb_at_tc(xd, idx) : __ldcg(p.X + idx));
+          g[u][j] = (ok && p.bwd_g) ? __ldcg(p.bwd_g + idx) : 0.0f;
         }
-        hi[j] = tf32_rna(r);
-        lo[j] = tf32_rna(r - hi[j]);
-        if (p.Phi) { p.Phi[idx] = hi[j]; p.Plo[idx] = lo[j]; }
-        if (p.rowsum) {   // (Wd == 32) sum over the image row, its first and last pixel: the time channel's weight gradient
-          float sum = r;
+      }
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-          const float last = __shfl_sync(0xffffffffu, r, 31);
-          if (lane == 0) {
-            float* dst = p.rowsum + ((size_t)blockIdx.x * p.C + c) * 3;
-            dst[0] = sum; dst[1] = r; dst[2] = last;
+      for (int u = 0; u < 2; ++u) {
+        const int c4 = c4a + 8 * u;
+        if (c4 >= C4) break;
+        float hi[4], lo[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int c = c4 * 4 + j;
+          const size_t idx = pix + HW * ((size_t)c + (size_t)p.C * b);
+          float r = v[u][j];
+          if (p.xdesc && side) side[idx] = r;
+          if (p.bwd_g) {
+            if (p.bwd_coef) {
+              const float a = p.in_ab[c], bb = p.in_ab[p.C + c];
+              const float pre = fmaf(a, r, bb);
+              const float gh = g[u][j] * (p.bwd_act == ACT_GELU ? gelu_d(pre) : dact_call(p.bwd_act, pre));
+              const float xhat = (r - p.bwd_stat[c]) * p.bwd_stat[p.C + c];
+              r = a * (gh - p.bwd_coef[c] - xhat * p.bwd_coef[p.C + c]);
+            } else r = g[u][j] * dact_call(p.bwd_act, r);
+          } else {
+            if (p.in_ab) r = fmaf(p.in_ab[c], r, p.in_ab[p.C + c]);
+            if (p.in_act == ACT_GELU) r = gelu_f(r);
+            else if (p.in_act != ACT_IDENTITY) r = act_call(p.in_act, r);
+          }
+          hi[j] = tf32_rna(r);
+          lo[j] = tf32_rna(r - hi[j]);
+          if (p.Phi) { p.Phi[idx] = hi[j]; p.Plo[idx] = lo[j]; }
+          if (p.rowsum) {   // (Wd == 32) sum over the image row, its first and last pixel: the time channel's weight gradient
+            float sum = r;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            const float last = __shfl_sync(0xffffffffu, r, 31);
+            if (lane == 0) {
+              float* dst = p.rowsum + ((size_t)blockIdx.x * p.C + c) * 3;
+              dst[0] = sum; dst[1] = r; dst[2] = last;
+            }
           }
         }
-      }
-      if (p.Fhi) {
-        const size_t o = ((size_t)c4 * (size_t)k.NPA + pos) * 4;
-        *reinterpret_cast<float4*>(p.Fhi + o) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<float4*>(p.Flo + o) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+        if (p.Fhi) {
+          const size_t o = ((size_t)c4 * (size_t)k.NPA + pos) * 4;
+          *reinterpret_cast<float4*>(p.Fhi + o) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<float4*>(p.Flo + o) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+        }
       }
     }
   }
@@ -187,6 +203,7 @@ struct ConvK {
   ConvTcP p;
   int Wd, Ht, PW, IMG, ngroups;
   long NP, NPA;
+  int dbg;   // LRNDE_CT_DBG (profiling only): 1 = no output stores, 2 = no time-channel term
 };
 
 // sum over the warp of 32 per-lane values; lane L returns the total of value L (31 shuffles)
@@ -236,6 +253,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_kernel(ConvK k) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
+  // LRNDE_CT_DBG: 32 = trace CTA 0; + 64: only the K = 8 convolution into 64 channels; + 128: only K = 64 into 64
+  const bool ctrace_on = (k.dbg & 32) && blockIdx.x == 0 && (!(k.dbg & 64) || (p.K == 8 && NOUT == 64)) &&
+                         (!(k.dbg & 128) || (p.K == 64 && NOUT == 64));
+  if (threadIdx.x == 0) CTRACE(0, 0);
 
   if (warp == 0) {
     // ---------------- bulk copies: per stage of 8 input channels, [hi k4=0 | hi k4=1 | lo k4=0 | lo k4=1] runs + weights
@@ -246,6 +267,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_kernel(ConvK k) {
         mbar_wait(&empty_bar[slot], ph ^ 1u);
         if (elect_one_sync()) {
           uint8_t* dst = sm + (size_t)slot * STB;
+          if (s == 0) CTRACE(1, (int)(ks / nst));
           mbar_arrive_expect_tx(&full_bar[slot], (uint32_t)STB);
 #pragma unroll
           for (int part = 0; part < 2; ++part)
@@ -272,6 +294,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_kernel(ConvK k) {
         mbar_wait(&full_bar[slot], ph);
         tc_fence_after();
         if (elect_one_sync()) {
+          if (s == 0) CTRACE(2, it);
           const uint32_t base = smem_u32(sm + (size_t)slot * STB);
           const uint32_t wb = base + 4 * kRunB;
 #pragma unroll 1
@@ -291,74 +314,110 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_kernel(ConvK k) {
             }
           }
           mma_commit(&empty_bar[slot]);
-          if (s == nst - 1) mma_commit(&acc_full[db]);
+          if (s == nst - 1) { mma_commit(&acc_full[db]); CTRACE(3, it); }
         }
         __syncwarp();
       }
     }
   } else {
     // ---------------- epilogue: lane = position (coalesced along x), registers = 16 output channels at a time;
-    // the two warps of a lane quarter take alternate 16-channel chunks (NOUT = 16: alternate tiles)
+    // the two warps of a lane quarter take alternate 16-channel chunks (NOUT = 16: alternate tiles).  The position is
+    // decoded once per tile in 32-bit arithmetic (a 64-bit division per chunk was half of the epilogue's latency).
     const int q = warp & 3, half = (warp - 2) >> 2;
     const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
     float* out = p.ydesc ? p.ydesc->dst : p.Y;
     const float tval = p.tdesc ? p.tdesc->t : 0.0f;
     const size_t HW = (size_t)k.Wd * k.Ht;
     constexpr int NCC = NOUT / 16;
+    constexpr int NCW = (NCC > 1) ? NCC / 2 : 1;     // chunks per warp
+    const bool gelu_bwd = (MODE == 2) && p.bwd_act == ACT_GELU;
+    const float oscale = p.out_scale;
+    const bool no_store = (k.dbg & 1) != 0, no_ts = (k.dbg & 2) != 0;
+    const uint32_t uIMG = (uint32_t)k.IMG, uPW = (uint32_t)k.PW, uNP = (uint32_t)k.NP;
     int it = 0;
     for (int g = blockIdx.x; g < k.ngroups; g += gridDim.x, ++it) {
       const int db = it & 1;
+      float st[NCW][32];
+#pragma unroll
+      for (int h2 = 0; h2 < NCW; ++h2)
+#pragma unroll
+        for (int j = 0; j < 32; ++j) st[h2][j] = 0.0f;
+      if (threadIdx.x == 64) CTRACE(4, it);
       mbar_wait(&acc_full[db], (uint32_t)((it >> 1) & 1));
       tc_fence_after();
+      if (threadIdx.x == 64) CTRACE(5, it);
 #pragma unroll 1
-      for (int cc = (NCC > 1 ? half : 0); cc < NCC; cc += (NCC > 1 ? 2 : 1)) {
-        float st[32];
+      for (int i = (NCC > 1 ? 0 : half); i < ((k.dbg & 4) ? 0 : kTiles); i += (NCC > 1 ? 1 : 2)) {
+        const uint32_t pp = (uint32_t)g * kCtGroup + (uint32_t)(i * 128 + q * 32 + lane);
+        const uint32_t b = pp / uIMG, r0 = pp - b * uIMG;
+        const uint32_t yh = r0 / uPW, xh = r0 - yh * uPW;
+        const bool valid = pp < uNP && xh >= 1 && xh <= (uint32_t)k.Wd && yh >= 1 && yh <= (uint32_t)k.Ht;
+        const int x = (int)xh - 1, y = (int)yh - 1;
+        const size_t obase0 = (size_t)x + (size_t)k.Wd * ((size_t)y + (size_t)k.Ht * ((size_t)p.Cout * b));
+        const int ym = (y > 0 ? 1 : 0) | 2 | (y < k.Ht - 1 ? 4 : 0), xm = (x > 0 ? 1 : 0) | 2 | (x < k.Wd - 1 ? 4 : 0);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) st[j] = 0.0f;
-#pragma unroll 1
-        for (int i = (NCC > 1 ? 0 : half); i < kTiles; i += (NCC > 1 ? 1 : 2)) {
-          const long pp = (long)g * kCtGroup + i * 128 + q * 32 + lane;
-          const int b = (int)(pp / k.IMG), r0 = (int)(pp % k.IMG);
-          const int yh = r0 / k.PW, xh = r0 % k.PW;
-          const bool valid = pp < k.NP && xh >= 1 && xh <= k.Wd && yh >= 1 && yh <= k.Ht;
-          const int x = xh - 1, y = yh - 1;
-          const size_t obase = (size_t)x + (size_t)k.Wd * ((size_t)y + (size_t)k.Ht * ((size_t)p.Cout * b)) + (size_t)(cc * 16) * HW;
-          const int ym = (y > 0 ? 1 : 0) | 2 | (y < k.Ht - 1 ? 4 : 0), xm = (x > 0 ? 1 : 0) | 2 | (x < k.Wd - 1 ? 4 : 0);
-          const float* ts = p.tsum ? p.tsum + (ym * 8 + xm) * NOUT + cc * 16 : nullptr;
+        for (int h2 = 0; h2 < NCW; ++h2) {
+          const int cc = (NCC > 1) ? half + 2 * h2 : 0;
+          const size_t obase = obase0 + (size_t)(cc * 16) * HW;
+          const float* ts = (p.tsum && !no_ts) ? p.tsum + (ym * 8 + xm) * NOUT + cc * 16 : nullptr;
           float v[16];
           tmem_ld16(tlane + (uint32_t)(db * kTiles * NOUT + i * NOUT + cc * 16), v);
-          if (valid) {
+          if (valid && !(k.dbg & 16)) {
+            // every load of the chunk is issued before the arithmetic (one basic block: no per-element branches; the
+            // channels >= Cout of a partial chunk have zero weights, so their accumulators and table entries are zero)
+            constexpr int JB = (MODE == 2) ? 8 : 16;     // elements per batch (register pressure of the pullback constants)
+            float* o = out + obase;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const int co = cc * 16 + j;
-              if (co < p.Cout) {
-                float r = v[j];
-                if (ts) r = fmaf(tval, __ldg(ts + j), r);
-                if (MODE == 1) {
-                  st[j] += r;
-                  st[16 + j] = fmaf(r, r, st[16 + j]);
-                } else if (MODE == 2) {
-                  const float zz = __ldcg(p.bwd_z + obase + (size_t)j * HW);
-                  const float gh = r * dact_call(p.bwd_act, fmaf(__ldg(p.bwd_ab + co), zz, __ldg(p.bwd_ab + p.Cout + co)));
-                  st[j] += gh;
-                  st[16 + j] = fmaf(gh, (zz - __ldg(p.bwd_stat + co)) * __ldg(p.bwd_stat + p.Cout + co), st[16 + j]);
+            for (int j0 = 0; j0 < 16; j0 += JB) {
+              float tsv[JB], zz[JB], ca[JB], cb[JB], cm[JB], ci[JB];
+              if (MODE != 2) {
+#pragma unroll
+                for (int j = 0; j < JB; ++j) tsv[j] = ts ? __ldg(ts + j0 + j) : 0.0f;
+              } else {
+#pragma unroll
+                for (int j = 0; j < JB; ++j) {
+                  const int co = min(cc * 16 + j0 + j, p.Cout - 1);
+                  zz[j] = __ldcg(p.bwd_z + obase0 + (size_t)co * HW);
+                  ca[j] = __ldg(p.bwd_ab + co); cb[j] = __ldg(p.bwd_ab + p.Cout + co);
+                  cm[j] = __ldg(p.bwd_stat + co); ci[j] = __ldg(p.bwd_stat + p.Cout + co);
                 }
-                out[obase + (size_t)j * HW] = r * p.out_scale;
+              }
+#pragma unroll
+              for (int j = 0; j < JB; ++j) {
+                const int jj = j0 + j;
+                float r = v[jj];
+                if (MODE != 2) r = fmaf(tval, tsv[j], r);
+                if (MODE == 1) {
+                  st[h2][jj] += r;
+                  st[h2][16 + jj] = fmaf(r, r, st[h2][16 + jj]);
+                } else if (MODE == 2) {
+                  const float pre = fmaf(ca[j], zz[j], cb[j]);
+                  const float gh = r * (gelu_bwd ? gelu_d(pre) : dact_call(p.bwd_act, pre));
+                  st[h2][jj] += gh;
+                  st[h2][16 + jj] = fmaf(gh, (zz[j] - cm[j]) * ci[j], st[h2][16 + jj]);
+                }
+                if (cc * 16 + jj < p.Cout && !no_store) o[(size_t)jj * HW] = r * oscale;
               }
             }
           }
         }
-        if (MODE != 0) {
-          const float tot = warp_transpose_sum(st, lane);
+      }
+      // every accumulator of this warp has been read: the MMAs of the group after next may overwrite the buffer
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_free[db]);
+      if (threadIdx.x == 64) CTRACE(6, it);
+      if (MODE != 0 && !(k.dbg & 8)) {
+#pragma unroll
+        for (int h2 = 0; h2 < NCW; ++h2) {
+          const int cc = (NCC > 1) ? half + 2 * h2 : 0;
+          const float tot = warp_transpose_sum(st[h2], lane);
           const int co = cc * 16 + (lane & 15);
           // NOUT = 16: the two warps of a quarter saw different tiles of the same channels -> separate partial rows
           const size_t row = (NCC > 1) ? ((size_t)g * 4 + q) : (((size_t)g * 4 + q) * 2 + half);
           if (co < p.Cout) reinterpret_cast<float*>(p.stat_part + row * p.Cout + co)[lane >> 4] = tot;
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_free[db]);
     }
   }
   tc_fence_before();
@@ -675,6 +734,8 @@ void convtc_conv(lrnde_ctx* ctx, const ConvTcGeom& g, const ConvTcP& p) {
   convtc_attrs();
   convtc::ConvK k;
   k.p = p; k.Wd = g.Wd; k.Ht = g.Ht; k.PW = g.PW; k.IMG = g.IMG; k.ngroups = g.ngroups; k.NP = g.NP; k.NPA = g.NPA;
+  static const char* dbg_env = getenv("LRNDE_CT_DBG");
+  k.dbg = dbg_env ? atoi(dbg_env) : 0;
   const int grid = std::min(g.ngroups, 148);
   const int mode = !p.stat_part ? 0 : (p.bwd_z ? 2 : 1);
   const int T = convtc::kConvThreads;
