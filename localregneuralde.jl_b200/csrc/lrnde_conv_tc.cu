@@ -73,7 +73,8 @@ struct PackK {
   long NPA;
 };
 
-// one block = one image row (b, y); warp w owns the channel chunks c4 = w, w + 8, ...; lane = x (two passes when Wd > 32).
+// one block = one image row (b, y) and min(8, C / 4) warps; warp w owns the channel chunks c4 = w, w + nw, ...; lane = x
+// (two passes when Wd > 32).
 // The halo positions of (F) are zero from the allocation on and no pack ever writes them.
 __global__ void __launch_bounds__(256) pack_kernel(PackK k) {
   const ConvTcPackP& p = k.p;
@@ -83,7 +84,7 @@ __global__ void __launch_bounds__(256) pack_kernel(PackK k) {
     if (threadIdx.x == 0) xd = *p.xdesc;
     __syncthreads();
   }
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   const int b = blockIdx.x / k.Ht, y = blockIdx.x % k.Ht;
   float* side = p.side_to_desc_dst ? xd.dst : p.side;
   const int C4 = p.C >> 2;
@@ -92,12 +93,12 @@ __global__ void __launch_bounds__(256) pack_kernel(PackK k) {
     const size_t pos = (size_t)kCtGuard + (size_t)b * k.IMG + (size_t)(y + 1) * k.PW + (x + 1);
     const size_t pix = x + (size_t)k.Wd * y;
 #pragma unroll 1
-    for (int c4a = warp; c4a < C4; c4a += 16) {
-      // two chunks per pass (c4a, c4a + 8): every load of the pass is issued before the first out-of-line activation call
+    for (int c4a = warp; c4a < C4; c4a += 2 * nw) {
+      // two chunks per pass (c4a, c4a + nw): every load of the pass is issued before the first out-of-line activation call
       float v[2][4], g[2][4];
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
-        const int c4 = c4a + 8 * u;
+        const int c4 = c4a + nw * u;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const size_t idx = pix + HW * ((size_t)c4 * 4 + j + (size_t)p.C * b);
@@ -108,7 +109,7 @@ __global__ void __launch_bounds__(256) pack_kernel(PackK k) {
       }
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
-        const int c4 = c4a + 8 * u;
+        const int c4 = c4a + nw * u;
         if (c4 >= C4) break;
         float hi[4], lo[4];
 #pragma unroll
@@ -697,7 +698,7 @@ __global__ void __launch_bounds__(256) time_wgrad_kernel(const float* __restrict
 void convtc_pack(lrnde_ctx* ctx, const ConvTcGeom& g, const ConvTcPackP& p) {
   convtc::PackK k;
   k.p = p; k.Wd = g.Wd; k.Ht = g.Ht; k.PW = g.PW; k.PH = g.PH; k.IMG = g.IMG; k.NPA = g.NPA;
-  convtc::pack_kernel<<<g.B * g.Ht, 256, 0, ctx->stream>>>(k);
+  convtc::pack_kernel<<<g.B * g.Ht, 32 * std::max(1, std::min(8, p.C / 4)), 0, ctx->stream>>>(k);
   LCT_COUNT(ctx);
 }
 

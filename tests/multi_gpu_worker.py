@@ -84,39 +84,54 @@ for prec, tol in (("fp32", 1e-6), ("tf32x3", 1e-5)):       # tf32x3: the latent-
 # sharded run normalises with the statistics of the whole batch exactly like the single-GPU run
 from oracle.lrnde_conv_oracle import ConvLayer, ConvNet, glorot_uniform_conv_params  # noqa: E402
 
-cl = [(2, 5, True, "gelu"), (5, 4, True, "gelu"), (4, 2, False, "identity")]
-Wd, Ht, Bc = 8, 4, 3 * world
-onet = ConvNet([ConvLayer(*l) for l in cl], Wd, Ht, time_dependent=True)
-cchain = pkg.TDConvChain(pkg.ConvChain(*[pkg.Conv(*l) for l in cl], width=Wd, height=Ht))
-rng = np.random.default_rng(11)
-cps = glorot_uniform_conv_params(onet, rng, jitter=0.2)
-cx = rng.standard_normal((onet.state_dims, Bc)).astype(np.float32)
-cc = (rng.standard_normal((onet.state_dims, Bc)) / Bc).astype(np.float32)
-ctx_dp.setup_group(rank, world, Bc, gather)
-lo, hi = rank * Bc // world, (rank + 1) * Bc // world
-res = {}
-for name, ctx, xs, cs in (("single", ctx_1, cx, cc), ("dp", ctx_dp, cx[:, lo:hi], cc[:, lo:hi])):
-    node = pkg.NeuralODE(cchain, ctx=ctx, regularize="unbiased", abstol=1e-3, reltol=1e-3, maxiters=1000, save_start=False)
-    sol, st2 = node(np.ascontiguousarray(xs), cps, node.initialstates(np.random.default_rng(5)))
-    d_x, d_ps = node.backward(sol, [None, np.ascontiguousarray(cs)], 1.5)
-    t, dt, ee, acc = sol.step_log(0)
-    bt, bdt, bee, bacc = sol.step_log(1)
-    res[name] = dict(u=np.asarray(sol.u[-1]).copy(), reg=float(st2["reg_val"]), nfe=st2["nfe"], d_x=np.asarray(d_x).copy(),
-                     d_ps=np.asarray(d_ps).copy(), acc=acc, bacc=bacc, running=np.asarray(st2["model"]["running"]).copy())
-    sol.free()
-g = torch.from_numpy(res["dp"]["d_ps"]).to(dev)
-pkg._lib.check(pkg.lib().lrnde_allreduce_sum(ctx_dp._h, g.data_ptr(), g.numel()))
-s, d = res["single"], res["dp"]
-same_f = np.array_equal(s["acc"], d["acc"]) and s["nfe"] == d["nfe"]
-same_b = np.array_equal(s["bacc"], d["bacc"])
-e_u, e_dx = rel(d["u"], s["u"][:, lo:hi]), rel(d["d_x"], s["d_x"][:, lo:hi])
-e_dps, e_run = rel(g.cpu().numpy(), s["d_ps"]), rel(d["running"], s["running"])
-e_reg = abs(d["reg"] - s["reg"]) / abs(s["reg"])
-good = same_f and same_b and e_u < 1e-4 and e_dx < 1e-3 and e_dps < 1e-3 and e_run < 1e-4 and e_reg < 1e-3
-ok = ok and good
-print(f"[multi-gpu rank {rank}/{world}] conv+BatchNorm fwd attempts {len(s['acc'])}/{len(d['acc'])} same={same_f} bwd attempts "
-      f"{len(s['bacc'])}/{len(d['bacc'])} same={same_b} u {e_u:.2e} d_x {e_dx:.2e} d_ps(allreduced) {e_dps:.2e} running stats "
-      f"{e_run:.2e} reg {e_reg:.2e} -> {'ok' if good else 'MISMATCH'}", flush=True)
+CONV_CASES = (
+    ("SIMT", [(2, 5, True, "gelu"), (5, 4, True, "gelu"), (4, 2, False, "identity")], 8, 4, 3),
+    # channel counts that are multiples of 8, width 32: the tcgen05 engine (csrc/lrnde_conv_tc.cu), BatchNorm statistics of the
+    # forward epilogue and of the data-gradient convolution's pullback epilogue exchanged between the ranks
+    ("tcgen05", [(8, 16, True, "gelu"), (16, 16, True, "gelu"), (16, 8, False, "identity")], 32, 4, 2),
+)
+for ctag, cl, Wd, Ht, per_rank in CONV_CASES:
+    Bc = per_rank * world
+    onet = ConvNet([ConvLayer(*l) for l in cl], Wd, Ht, time_dependent=True)
+    cchain = pkg.TDConvChain(pkg.ConvChain(*[pkg.Conv(*l) for l in cl], width=Wd, height=Ht))
+    rng = np.random.default_rng(11)
+    cps = glorot_uniform_conv_params(onet, rng, jitter=0.2)
+    cx = rng.standard_normal((onet.state_dims, Bc)).astype(np.float32)
+    cc = (rng.standard_normal((onet.state_dims, Bc)) / Bc).astype(np.float32)
+    ctx_dp.setup_group(rank, world, Bc, gather)
+    lo, hi = rank * Bc // world, (rank + 1) * Bc // world
+    res = {}
+    for name, ctx, xs, cs in (("single", ctx_1, cx, cc), ("dp", ctx_dp, cx[:, lo:hi], cc[:, lo:hi])):
+        node = pkg.NeuralODE(cchain, ctx=ctx, regularize="unbiased", abstol=1e-3, reltol=1e-3, maxiters=1000, save_start=False)
+        sol, st2 = node(np.ascontiguousarray(xs), cps, node.initialstates(np.random.default_rng(5)))
+        d_x, d_ps = node.backward(sol, [None, np.ascontiguousarray(cs)], 1.5)
+        t, dt, ee, acc = sol.step_log(0)
+        bt, bdt, bee, bacc = sol.step_log(1)
+        res[name] = dict(u=np.asarray(sol.u[-1]).copy(), reg=float(st2["reg_val"]), nfe=st2["nfe"], d_x=np.asarray(d_x).copy(),
+                         d_ps=np.asarray(d_ps).copy(), acc=acc, bacc=bacc, running=np.asarray(st2["model"]["running"]).copy())
+        sol.free()
+    g = torch.from_numpy(res["dp"]["d_ps"]).to(dev)
+    pkg._lib.check(pkg.lib().lrnde_allreduce_sum(ctx_dp._h, g.data_ptr(), g.numel()))
+    s, d = res["single"], res["dp"]
+    same_f = np.array_equal(s["acc"], d["acc"]) and s["nfe"] == d["nfe"]
+    same_b = np.array_equal(s["bacc"], d["bacc"])
+    e_u, e_dx = rel(d["u"], s["u"][:, lo:hi]), rel(d["d_x"], s["d_x"][:, lo:hi])
+    e_dps, e_run = rel(g.cpu().numpy(), s["d_ps"]), rel(d["running"], s["running"])
+    e_reg = abs(d["reg"] - s["reg"]) / abs(s["reg"])
+    # SIMT engine: per-image partial sums, the sharded run is bit-identical.  tcgen05 engine: the 512-position tile groups
+    # straddle the images differently on every rank, the norms differ in the last bits, the step sizes (a cancellation) at
+    # ~1e-4, and the layer-1 statistics move with the stage times through the time channel: the bar of the single-GPU test
+    # of the same quantity against the oracle (tests/test_gpu_conv.py::test_layer_returns_the_state_of_the_closure)
+    run_tol = 1e-4 if ctag == "SIMT" else 5e-3
+    good = same_f and same_b and e_u < 1e-4 and e_dx < 1e-3 and e_dps < 1e-3 and e_run < run_tol and e_reg < 1e-3
+    ok = ok and good
+    if not good and rank == 0:
+        dd = np.abs(d["running"] - s["running"])
+        print("running stats: worst entries", np.argsort(-dd)[:6], dd[np.argsort(-dd)[:6]], "single", s["running"][np.argsort(-dd)[:6]],
+              "dp", d["running"][np.argsort(-dd)[:6]], "nfe", s["nfe"], d["nfe"], flush=True)
+    print(f"[multi-gpu rank {rank}/{world}] conv+BatchNorm ({ctag}) fwd attempts {len(s['acc'])}/{len(d['acc'])} same={same_f} bwd attempts "
+          f"{len(s['bacc'])}/{len(d['bacc'])} same={same_b} u {e_u:.2e} d_x {e_dx:.2e} d_ps(allreduced) {e_dps:.2e} running stats "
+          f"{e_run:.2e} reg {e_reg:.2e} -> {'ok' if good else 'MISMATCH'}", flush=True)
 dist.barrier()
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)

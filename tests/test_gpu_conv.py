@@ -36,6 +36,14 @@ SHAPES = [
     ([(3, 24, True, "gelu"), (24, 20, False, "tanh"), (20, 3, False, "identity")], 12, 7, True, 5),   # 64-wide tiles, masks
     ([(8, 64, True, "gelu"), (64, 64, True, "gelu"), (64, 8, False, "identity")], 32, 32, True, 2),  # the cifar10 core
     ([(2, 17, True, "gelu"), (17, 2, False, "identity")], 16, 40, False, 2),                 # several row tiles
+    # tensor-core engine (csrc/lrnde_conv_tc.cu: channel counts multiples of 8, <= 64): partial 16-channel chunks, the
+    # 16-wide instantiation with statistics, swapped / narrow weight-gradient operands, a row count that is not a
+    # multiple of the split
+    ([(8, 16, True, "gelu"), (16, 24, True, "tanh"), (24, 8, False, "identity")], 32, 6, True, 3),
+    ([(8, 64, True, "gelu"), (64, 64, True, "gelu"), (64, 8, False, "identity")], 32, 32, True, 5),  # images split over CTAs
+    ([(8, 32, False, "tanh"), (32, 8, False, "identity")], 32, 8, False, 2),                 # no BatchNorm, no time channel
+    ([(8, 64, True, "gelu"), (64, 8, False, "identity")], 16, 16, True, 2),                  # width 16: SIMT weight gradient
+    ([(16, 16, False, "identity")], 32, 3, True, 2),                                         # one layer, time channel
 ]
 
 
@@ -68,6 +76,26 @@ def test_conv_vjp_matches_oracle(pkg, layers, W, H, td, B):
         assert rel(dps[wo:wo + n], wdps[wo:wo + n]) < 1e-4
         if L.batchnorm:
             assert rel(dps[go:go + 2 * L.out_ch], wdps[go:go + 2 * L.out_ch]) < 1e-4
+
+
+def test_tensor_core_and_simt_conv_engines_agree(pkg, monkeypatch):
+    """The tcgen05 engine (3xTF32) against the FP32 SIMT direct convolutions of the same library on the cifar10 core:
+    f, the data gradient and every parameter gradient (LRNDE_CONV_TC=0 selects the SIMT engine per call)."""
+    rng = np.random.default_rng(11)
+    layers, W, H, B = [(8, 64, True, "gelu"), (64, 64, True, "gelu"), (64, 8, False, "identity")], 32, 32, 7
+    onet, chain = _pair(pkg, layers, W, H, True)
+    ps = glorot_uniform_conv_params(onet, rng, jitter=0.2)
+    u = rng.standard_normal((onet.state_dims, B)).astype(np.float32)
+    lam = rng.standard_normal((onet.state_dims, B)).astype(np.float32)
+    layer = pkg.NeuralODE(chain)
+    f_tc = layer.dynamics(u, ps, 0.3)
+    a_tc, d_tc = layer.dynamics_vjp(u, ps, 0.3, lam)
+    monkeypatch.setenv("LRNDE_CONV_TC", "0")
+    f_si = layer.dynamics(u, ps, 0.3)
+    a_si, d_si = layer.dynamics_vjp(u, ps, 0.3, lam)
+    assert rel(f_tc, f_si) < 1e-5, rel(f_tc, f_si)
+    assert rel(a_tc, a_si) < 1e-5, rel(a_tc, a_si)
+    assert rel(d_tc, d_si) < 1e-5, rel(d_tc, d_si)
 
 
 def test_conv_model_validation(pkg):

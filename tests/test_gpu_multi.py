@@ -30,4 +30,4 @@ def test_sharded_run_matches_the_single_gpu_run(n):
     lines = [l for l in r.stdout.splitlines() if l.startswith("[multi-gpu")]
     print("\n".join(lines))
     assert r.returncode == 0, (r.stdout[-3000:], r.stderr[-3000:])
-    assert len(lines) == 3 * n and all(l.endswith("ok") for l in lines)
+    assert len(lines) == 4 * n and all(l.endswith("ok") for l in lines)
