@@ -884,10 +884,27 @@ def run_cifar10(args):
         layer.dynamics(xt, pt, 0.5)
     e1.record()
     torch.cuda.synchronize()
-    us_f = 1e3 * e0.elapsed_time(e1) / 10
+    us_f_call = 1e3 * e0.elapsed_time(e1) / 10      # through the C ABI: includes the per-call setup (weight images, buffers)
+    # ... and inside a solve: the forward pass of the layer (main solve + regulariser step: nfe evaluations with their
+    # stage combinations, BatchNorm reductions, error norms and controller launches), CUDA events around 3 passes
+    nfe_f = []
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(3):
+        sol, st2 = layer(xt, pt, st)
+        nfe_f.append(int(st2["nfe"]))
+        sol.free()
+    e1.record()
+    torch.cuda.synchronize()
+    us_f = 1e3 * e0.elapsed_time(e1) / float(sum(nfe_f))
     peaks = measured_peaks()
     tf32_peak = peaks["bf16_burst"] / 2.0
     ach = F_f * B / (us_f * 1e-6) / 1e12
+    traffic = None
+    tr_path = os.path.join(ROOT, "profiles", "r2_traffic_cifar10.json")
+    if B == 256 and os.path.exists(tr_path):   # ncu --set full of the same kernels at batch 256 (scratch/ncu_traffic.py)
+        tr = json.load(open(tr_path))
+        traffic = tr.get("dram_bytes_per_feval")
     cpu = None
     if not args.no_cpu_baseline:
         Bs = args.cifar_ref_batch
@@ -901,7 +918,7 @@ def run_cifar10(args):
                "sample": f"1 iteration at batch {Bs} ({dt:.1f} s), numpy float32 oracle", "nfe": int(st2["nfe"])}
     print(json.dumps({"metric": "cifar10_train_samples_per_s", "value": B / (ms / 1e3), "unit": "samples/s", "n_gpus": 1,
                       "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-                      "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                      "scaling": "weak", "vs_baseline": None, "dtype": "tf32x3", "data": "synthetic",
                       "config": {"workload": wl, "batch": B,
                                  "l2": "hidden activations 2 x 67 MB per f evaluation at batch 256: larger than L2"},
                       "nfe_per_step": info["nfe"], "nfe_per_s": info["nfe"] / (ms / 1e3), "nf_bwd_per_step": info["nf_bwd"],
@@ -910,14 +927,17 @@ def run_cifar10(args):
                       "e2e": {"value": B / (ms_e / 1e3), "unit": "samples/s", "ms_per_step": ms_e,
                               "h2d_bytes_per_step": 4 * (2 * D * B + ps.size), "d2h_bytes_per_step": 4 * (2 * D * B + ps.size)},
                       "gpu_launches": int(info["launches"] * args.steps), "clocks": clk,
-                      "roofline": {"bound": "tensor", "kernel": "one f evaluation: conv3x3_kernel x 3 (FP32 SIMT direct convolution, "
-                                   "not yet on the tensor cores) + bn_finalize x 2", "achieved": ach, "peak": tf32_peak,
+                      "roofline": {"bound": "tensor", "kernel": "one f evaluation inside the forward solve: convtc::pack_kernel x 3 (stage "
+                                   "combination / BatchNorm + gelu, tf32 hi/lo split) + convtc::conv_kernel x 3 (tcgen05 implicit GEMM, "
+                                   "3xTF32; the three MMAs per algorithmic one are NOT counted as work) + bn_finalize x 2; time = "
+                                   "forward pass of the layer / nfe", "achieved": ach, "peak": tf32_peak,
                                    "unit": "TFLOP/s", "frac": ach / tf32_peak,
-                                   # dram read + write of the three convolutions of one evaluation at batch 256, ncu --set full
-                                   # (profiles/r1_cifar10_conv_ncu_full.txt); algorithmic: u in, z1 / z2 out and in, du out
-                                   "traffic": (259.0e6 if B == 256 else None),
+                                   "frac_of_3xtf32_issue_capacity": 3.0 * ach / tf32_peak,
+                                   # dram read + write of the pack / conv kernels of one evaluation at batch 256, ncu --set full
+                                   # (profiles/r2_traffic_cifar10.json); algorithmic: u in, z1 / z2 out and in, du out
+                                   "traffic": traffic,
                                    "algorithmic_bytes_per_feval": 4.0 * 1024 * B * (8 + 64 + 64 + 64 + 64 + 8),
-                                   "us_per_feval": us_f,
+                                   "us_per_feval": us_f, "us_per_feval_through_the_c_abi": us_f_call,
                                    "peak_source": peaks["source"] + " (bf16 burst / 2 = TF32 dense)"},
                       "cpu_baseline": cpu}))
 

@@ -359,8 +359,7 @@ struct ConvEval {
   std::vector<uint8_t*> wimg, wimgT;                    // weight images: forward / data-gradient convolution
   std::vector<float*> tsum;                             // time-channel tables
   bool wg_tc = false;                                   // weight gradients on the tensor cores as well (Wd == 32)
-  std::vector<float*> Phi, Plo;                         // plain tf32 hi / lo input of every layer (operands of its weight gradient)
-  float* PDhi = nullptr; float* PDlo = nullptr;         // ... and of the cotangent of the layer at hand
+  float* PD = nullptr;                                  // plain fp32 cotangent of the layer at hand (operand of its weight gradient)
   float* rowsum = nullptr;                              // per-row sums of that cotangent (time channel's weight gradient)
 
   static bool tc_eligible(const lrnde_model* m) {
@@ -388,7 +387,6 @@ struct ConvEval {
     tc = tc_eligible(m);
     if (tc) geo.set(m->Wd, m->Ht, (int)B);
     wg_tc = tc && vjp && convtc_wgrad_ok(geo) && !getenv("LRNDE_CONV_WG_SIMT");
-    Phi.assign(m->conv.size(), nullptr); Plo.assign(m->conv.size(), nullptr);
     z.assign(L, nullptr); ab.assign(L, nullptr); stat.assign(L, nullptr); pack.assign(L, nullptr); packT.assign(L, nullptr);
     wimg.assign(L, nullptr); wimgT.assign(L, nullptr); tsum.assign(L, nullptr);
     for (int l = 0; l < L; ++l) {
@@ -400,7 +398,6 @@ struct ConvEval {
         wimg[l] = (uint8_t*)ctx->alloc(convtc_wimg_bytes(Li.cin, convtc_nout(Li.cout)));
         if (m->td) tsum[l] = (float*)ctx->alloc(4 * 64 * (size_t)convtc_nout(Li.cout));
         if (vjp) wimgT[l] = (uint8_t*)ctx->alloc(convtc_wimg_bytes(Li.cout, convtc_nout(Li.cin)));
-        if (wg_tc) { Phi[l] = (float*)ctx->alloc(4 * HW * Li.cin * B); Plo[l] = (float*)ctx->alloc(4 * HW * Li.cin * B); }
       }
       const size_t nw = (size_t)9 * (Li.cin + m->td) * Li.cout;
       pack[l] = (float*)ctx->alloc(4 * nw);
@@ -441,7 +438,7 @@ struct ConvEval {
         if (wg_tc) maxpart = std::max(maxpart, (size_t)convtc_wgrad_splits(geo) * 9 * cintot * Li.cout);
       }
       if (wg_tc) {
-        PDhi = (float*)ctx->alloc(4 * HW * maxC * B); PDlo = (float*)ctx->alloc(4 * HW * maxC * B);
+        PD = (float*)ctx->alloc(4 * HW * maxC * B);
         rowsum = (float*)ctx->alloc(4 * (size_t)3 * m->Ht * maxC * B);
       }
       part = (float*)ctx->alloc(4 * maxpart);
@@ -463,9 +460,7 @@ struct ConvEval {
     for (auto p : wimgT) ctx->release(p);
     for (auto p : tsum) ctx->release(p);
     ctx->release(Fhi); ctx->release(Flo);
-    for (auto p : Phi) ctx->release(p);
-    for (auto p : Plo) ctx->release(p);
-    ctx->release(PDhi); ctx->release(PDlo); ctx->release(rowsum);
+    ctx->release(PD); ctx->release(rowsum);
     ctx->release(spart); ctx->release(ybuf); ctx->release(lbuf); ctx->release(G[0]); ctx->release(G[1]);
     ctx->release(part); ctx->release(bpart); ctx->release(coef); ctx->release(dgb);
   }
@@ -532,7 +527,7 @@ struct ConvEval {
 
   // layers 0..upto-1 of the dynamics on lincomb(in); `side` / `side_desc`: keep the combined input
   void run_layers(const LinComb* in, const int* done, int upto, const LinComb* out, bool side_to_in_dst, float* side,
-                  bool update_state, bool plain = false) {
+                  bool update_state) {
     const int ncalls = (update_state && first_call_twice) ? 2 : 1;
     if (update_state) first_call_twice = false;
     for (int l = 0; l < upto; ++l) {
@@ -543,7 +538,6 @@ struct ConvEval {
         if (l == 0) { pk.xdesc = in; pk.side_to_desc_dst = side_to_in_dst ? 1 : 0; pk.side = side; pk.in_act = ACT_IDENTITY; }
         else { pk.X = z[l - 1]; pk.in_ab = m->conv[l - 1].bn ? ab[l - 1] : nullptr; pk.in_act = m->conv[l - 1].act; }
         pk.Fhi = Fhi; pk.Flo = Flo; pk.C = Li.cin; pk.done = done;
-        if (plain) { pk.Phi = Phi[l]; pk.Plo = Plo[l]; }
         convtc_pack(ctx, geo, pk);
         launch_tc(wimg[l], Li.cin, m->td ? tsum[l] : nullptr, m->td ? in : nullptr, l == L - 1 ? nullptr : z[l],
                   l == L - 1 ? (out ? out : in) : nullptr, 1.0f, Li.cout, (Li.bn && !testmode) ? spart : nullptr, done);
@@ -581,19 +575,18 @@ struct ConvEval {
   void vjp_tc(const LinComb* y, const LinComb* lamd, float* out_a, const LinComb* out_desc, float a_scale,
               float* dps_ptr, const LinComb* dps_desc, size_t dps_off, float p_scale, float p_beta, const int* done) {
     cudaStream_t st = ctx->stream;
-    if (L > 1) run_layers(y, done, L - 1, nullptr, false, nullptr, false, true);   // recompute, operands of dW_0..L-2 kept
-    {   // input of the last layer: only its plain image is needed (the forward convolution is not recomputed)
+    // recompute z_0..z_{L-2} (the weight gradients read them, and y(t) = ybuf, through TMA and transform on the fly)
+    if (L > 1) run_layers(y, done, L - 1, nullptr, false, ybuf, false);
+    else {
       ConvTcPackP pk;
       memset(&pk, 0, sizeof(pk));
-      if (L == 1) { pk.xdesc = y; pk.in_act = ACT_IDENTITY; }
-      else { pk.X = z[L - 2]; pk.in_ab = m->conv[L - 2].bn ? ab[L - 2] : nullptr; pk.in_act = m->conv[L - 2].act; }
-      pk.Phi = Phi[L - 1]; pk.Plo = Plo[L - 1]; pk.C = m->conv[L - 1].cin; pk.done = done;
+      pk.xdesc = y; pk.side = ybuf; pk.in_act = ACT_IDENTITY; pk.C = m->conv[0].cin; pk.done = done;
       convtc_pack(ctx, geo, pk);
     }
     {   // cotangent of the output
       ConvTcPackP pk;
       memset(&pk, 0, sizeof(pk));
-      pk.xdesc = lamd; pk.in_act = ACT_IDENTITY; pk.Fhi = Fhi; pk.Flo = Flo; pk.Phi = PDhi; pk.Plo = PDlo;
+      pk.xdesc = lamd; pk.in_act = ACT_IDENTITY; pk.Fhi = Fhi; pk.Flo = Flo; pk.Pv = PD;
       pk.rowsum = m->td ? rowsum : nullptr;
       pk.C = m->conv[L - 1].cout; pk.done = done;
       convtc_pack(ctx, geo, pk);
@@ -606,7 +599,9 @@ struct ConvEval {
       const size_t nw = (size_t)9 * cintot * Li.cout;
       ConvTcWgP w;
       memset(&w, 0, sizeof(w));
-      w.Xhi = Phi[l]; w.Xlo = Plo[l]; w.Cx = Li.cin; w.Dhi = PDhi; w.Dlo = PDlo; w.Cd = Li.cout; w.CinTot = cintot;
+      if (l == 0) { w.X = ybuf; w.x_act = ACT_IDENTITY; }
+      else { w.X = z[l - 1]; w.x_ab = m->conv[l - 1].bn ? ab[l - 1] : nullptr; w.x_act = m->conv[l - 1].act; }
+      w.Cx = Li.cin; w.D = PD; w.Cd = Li.cout; w.CinTot = cintot;
       w.part = part; w.block = nw; w.tdesc = m->td ? y : nullptr; w.Drowsum = rowsum; w.done = done;
       convtc_wgrad(ctx, geo, w);
       wgrad_reduce_kernel<<<lr_ew_blocks(nw), 256, 0, st>>>(part, S, nw, dps_ptr ? dps_ptr + Li.w_off : nullptr, dps_desc,
@@ -625,7 +620,7 @@ struct ConvEval {
         }
         ConvTcPackP pk;
         memset(&pk, 0, sizeof(pk));
-        pk.Fhi = Fhi; pk.Flo = Flo; pk.Phi = PDhi; pk.Plo = PDlo; pk.C = Lp.cout; pk.done = done; pk.in_act = ACT_IDENTITY;
+        pk.Fhi = Fhi; pk.Flo = Flo; pk.Pv = PD; pk.C = Lp.cout; pk.done = done; pk.in_act = ACT_IDENTITY;
         pk.rowsum = m->td ? rowsum : nullptr;
         if (Lp.bn) {
           bn_bwd_finalize_tc_kernel<<<Lp.cout, 128, 0, st>>>(spart, convtc_stat_rows(geo, Lp.cout), Lp.cout, (double)HW * (double)B, coef, dgb, testmode,

@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(256) pack_kernel(PackK k) {
           }
           hi[j] = tf32_rna(r);
           lo[j] = tf32_rna(r - hi[j]);
-          if (p.Phi) { p.Phi[idx] = hi[j]; p.Plo[idx] = lo[j]; }
+          if (p.Pv) p.Pv[idx] = r;
           if (p.rowsum) {   // (Wd == 32) sum over the image row, its first and last pixel: the time channel's weight gradient
             float sum = r;
 #pragma unroll
@@ -432,10 +432,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_kernel(ConvK k) {
 
 // ---------------------------------------------------------------------------------------------------------
 // weight gradient (Wd == 32): see lrnde_conv_tc.h
-//   step i of a CTA = P row t = t0 + i (flattened (image, row) index): tensor-map TMA delivers the tile [64 channels]
-//   [32 pixels] (K-major SWIZZLE_128B, hi and lo); warps 2..5 write its two dx-shifted, zero-padded copies next to it
-//   (a TMA box cannot start at a pixel that is not a multiple of 16 bytes: measured, scratch/mb/tma_test.cu); Q rows
-//   t - 1, t, t + 1 of the same image are the B operands of the taps dy = +1, 0, -1.
+//   step i of a CTA = P row t = t0 + i (flattened (image, row) index): tensor-map TMA delivers the fp32 tile [64 channels]
+//   [32 pixels] (K-major SWIZZLE_128B) of the STORED array; warps 2 and 3 (a thread per channel row) apply BatchNorm +
+//   activation, split into tf32 hi / lo and write the tile and its two dx-shifted, zero-padded copies (a TMA box cannot
+//   start at a pixel that is not a multiple of 16 bytes: measured, scratch/mb/tma_test.cu); warps 4 and 5 do the same
+//   (without shifts) for the Q rows; Q rows t - 1, t, t + 1 of the same image are the B operands of the taps dy = +1, 0, -1.
 //   A (M = 128) = two adjacent P tiles: (dx = -1, dx = 0) and (dx = +1, whatever follows: rows 64..127 are ignored)
 //   TMEM: accumulator (dy, mt) at columns (dy * 2 + mt) * NB
 // ---------------------------------------------------------------------------------------------------------
@@ -449,7 +450,25 @@ struct WgK {
   float* part; size_t block;
   const int* done;
   int dbg;   // LRNDE_WG_DBG (bring-up): 1 = no TMA / MMA, 2 = TMA but no MMA
+  const float* p_ab; const float* q_ab; int p_act, q_act;   // v <- act(a[c] v + b[c]) applied to the rows of P / Q
 };
+
+// one operand row of 32 pixels: BatchNorm scale / shift + activation (rows >= C of the box are zero fill: left alone)
+__device__ __forceinline__ void wg_transform(float (&f)[34], const float* ab, int act, int c, int C) {
+  if (c >= C) return;
+  if (ab) {
+    const float a = __ldg(ab + c), b = __ldg(ab + C + c);
+#pragma unroll
+    for (int x = 1; x <= 32; ++x) f[x] = fmaf(a, f[x], b);
+  }
+  if (act == ACT_GELU) {
+#pragma unroll
+    for (int x = 1; x <= 32; ++x) f[x] = gelu_f(f[x]);
+  } else if (act != ACT_IDENTITY) {
+#pragma unroll
+    for (int x = 1; x <= 32; ++x) f[x] = act_call(act, f[x]);
+  }
+}
 
 __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint64_t* bar) {
   asm volatile(
@@ -459,9 +478,7 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
 }
 
 template <int NB>
-__global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constant__ CUtensorMap mPhi, const __grid_constant__ CUtensorMap mPlo,
-                                                            const __grid_constant__ CUtensorMap mQhi, const __grid_constant__ CUtensorMap mQlo,
-                                                            WgK k) {
+__global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constant__ CUtensorMap mP, const __grid_constant__ CUtensorMap mQ, WgK k) {
   if (k.done && *k.done) return;
   constexpr int QT = NB * 128;           // one Q tile (hi or lo)
   constexpr int QSLOT = 2 * QT;
@@ -469,7 +486,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
   extern __shared__ uint8_t smem_raw[];
   uint8_t* sm = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* smQ = sm + kWgXS * kWgXSlot;
-  __shared__ uint64_t x_full[kWgXS], s_full[kWgXS], x_empty[kWgXS], q_full[kWgQS], q_empty[kWgQS], acc_done;
+  __shared__ uint64_t x_full[kWgXS], s_full[kWgXS], x_empty[kWgXS], q_full[kWgQS], qs_full[kWgQS], q_empty[kWgQS], acc_done;
   __shared__ uint32_t tmem_slot;
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
@@ -478,8 +495,8 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
   const int n = min(k.rows_per_cta, k.nrows_total - t0);   // >= 1 by construction of the grid
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kWgXS; ++s) { mbar_init(&x_full[s], 1u); mbar_init(&s_full[s], 4u); mbar_init(&x_empty[s], 1u); }
-    for (int s = 0; s < kWgQS; ++s) { mbar_init(&q_full[s], 1u); mbar_init(&q_empty[s], 1u); }
+    for (int s = 0; s < kWgXS; ++s) { mbar_init(&x_full[s], 1u); mbar_init(&s_full[s], 2u); mbar_init(&x_empty[s], 1u); }
+    for (int s = 0; s < kWgQS; ++s) { mbar_init(&q_full[s], 1u); mbar_init(&qs_full[s], 2u); mbar_init(&q_empty[s], 1u); }
     mbar_init(&acc_done, 1u);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -508,9 +525,8 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
         // rows in front of / behind the batch: coordinates outside the tensor (zero fill); they are never multiplied
         const int b = (u < 0) ? -1 : u / k.Ht, y = (u < 0) ? 0 : u % k.Ht;
         uint8_t* dst = smQ + (size_t)slot * QSLOT;
-        mbar_arrive_expect_tx(&q_full[slot], (uint32_t)QSLOT);
-        tma_load_4d(dst, &mQhi, 0, y, 0, b, &q_full[slot]);
-        tma_load_4d(dst + QT, &mQlo, 0, y, 0, b, &q_full[slot]);
+        mbar_arrive_expect_tx(&q_full[slot], (uint32_t)QT);
+        tma_load_4d(dst, &mQ, 0, y, 0, b, &q_full[slot]);
       }
       __syncwarp();
     };
@@ -522,9 +538,8 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
       if (elect_one_sync()) {
         const int t = t0 + i, b = t / k.Ht, y = t % k.Ht;
         uint8_t* dst = sm + (size_t)slot * kWgXSlot;
-        mbar_arrive_expect_tx(&x_full[slot], (uint32_t)(2 * kWgPTile));
-        tma_load_4d(dst + 1 * kWgPTile, &mPhi, 0, y, 0, b, &x_full[slot]);
-        tma_load_4d(dst + 4 * kWgPTile, &mPlo, 0, y, 0, b, &x_full[slot]);
+        mbar_arrive_expect_tx(&x_full[slot], (uint32_t)kWgPTile);
+        tma_load_4d(dst + 1 * kWgPTile, &mP, 0, y, 0, b, &x_full[slot]);
       }
       __syncwarp();
       load_q(i + 2);
@@ -538,7 +553,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
       const int xs = i % kWgXS;
       mbar_wait(&s_full[xs], (uint32_t)((i / kWgXS) & 1));
       while (q_arrived <= i + 2) {
-        mbar_wait(&q_full[q_arrived % kWgQS], (uint32_t)((q_arrived / kWgQS) & 1));
+        mbar_wait(&qs_full[q_arrived % kWgQS], (uint32_t)((q_arrived / kWgQS) & 1));
         ++q_arrived;
       }
       tc_fence_after();
@@ -575,29 +590,70 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
       __syncwarp();
     }
   } else {
-    // ---------------- the dx = -1 / +1 copies of every P tile: thread = (hi | lo, channel row), conflict-free 16-byte accesses
+    // ---------------- operand preparation in shared memory (conflict-free 16-byte accesses: a thread per 128-byte row)
     {
-      const int tt = threadIdx.x - 64, c = tt & 63, sw = c & 7;
-      for (int i = 0; i < n; ++i) {
-        const int slot = i % kWgXS;
-        mbar_wait(&x_full[slot], (uint32_t)((i / kWgXS) & 1));
-        uint8_t* base = sm + (size_t)slot * kWgXSlot + (size_t)(tt >> 6) * 3 * kWgPTile + c * 128;
-        float f[34];
-        f[0] = 0.0f; f[33] = 0.0f;
+      const int tt = threadIdx.x - 64;
+      if (tt < 64) {   // P rows: transform, split, and the dx = -1 / +1 copies
+        const int c = tt, sw = c & 7;
+        for (int i = 0; i < n; ++i) {
+          const int slot = i % kWgXS;
+          mbar_wait(&x_full[slot], (uint32_t)((i / kWgXS) & 1));
+          uint8_t* base = sm + (size_t)slot * kWgXSlot + c * 128;
+          float f[34];
+          f[0] = 0.0f; f[33] = 0.0f;
 #pragma unroll
-        for (int qq = 0; qq < 8; ++qq) {
-          const float4 r = *reinterpret_cast<const float4*>(base + kWgPTile + ((qq ^ sw) << 4));
-          f[1 + 4 * qq] = r.x; f[2 + 4 * qq] = r.y; f[3 + 4 * qq] = r.z; f[4 + 4 * qq] = r.w;
-        }
+          for (int qq = 0; qq < 8; ++qq) {
+            const float4 r = *reinterpret_cast<const float4*>(base + kWgPTile + ((qq ^ sw) << 4));
+            f[1 + 4 * qq] = r.x; f[2 + 4 * qq] = r.y; f[3 + 4 * qq] = r.z; f[4 + 4 * qq] = r.w;
+          }
+          wg_transform(f, k.p_ab, k.p_act, c, k.Pc);
+          float l[34];
 #pragma unroll
-        for (int qq = 0; qq < 8; ++qq) {   // f[1 + x] = P[x]: the dx = -1 tile holds P[x - 1], the dx = +1 tile P[x + 1]
-          *reinterpret_cast<float4*>(base + ((qq ^ sw) << 4)) = make_float4(f[4 * qq], f[4 * qq + 1], f[4 * qq + 2], f[4 * qq + 3]);
-          *reinterpret_cast<float4*>(base + 2 * kWgPTile + ((qq ^ sw) << 4)) =
-              make_float4(f[4 * qq + 2], f[4 * qq + 3], f[4 * qq + 4], f[4 * qq + 5]);
+          for (int x = 0; x < 34; ++x) { const float h = tf32_rna(f[x]); l[x] = tf32_rna(f[x] - h); f[x] = h; }
+#pragma unroll
+          for (int qq = 0; qq < 8; ++qq) {   // f[1 + x] = P[x]: the dx = -1 tile holds P[x - 1], the dx = +1 tile P[x + 1]
+            const int o = (qq ^ sw) << 4;
+            *reinterpret_cast<float4*>(base + o) = make_float4(f[4 * qq], f[4 * qq + 1], f[4 * qq + 2], f[4 * qq + 3]);
+            *reinterpret_cast<float4*>(base + kWgPTile + o) = make_float4(f[4 * qq + 1], f[4 * qq + 2], f[4 * qq + 3], f[4 * qq + 4]);
+            *reinterpret_cast<float4*>(base + 2 * kWgPTile + o) = make_float4(f[4 * qq + 2], f[4 * qq + 3], f[4 * qq + 4], f[4 * qq + 5]);
+            *reinterpret_cast<float4*>(base + 3 * kWgPTile + o) = make_float4(l[4 * qq], l[4 * qq + 1], l[4 * qq + 2], l[4 * qq + 3]);
+            *reinterpret_cast<float4*>(base + 4 * kWgPTile + o) = make_float4(l[4 * qq + 1], l[4 * qq + 2], l[4 * qq + 3], l[4 * qq + 4]);
+            *reinterpret_cast<float4*>(base + 5 * kWgPTile + o) = make_float4(l[4 * qq + 2], l[4 * qq + 3], l[4 * qq + 4], l[4 * qq + 5]);
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&s_full[slot]);
         }
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&s_full[slot]);
+      } else {         // Q rows: transform and split
+        const int c = tt - 64, sw = c & 7;
+        for (int j = 0; j < n + 2; ++j) {
+          const int slot = j % kWgQS;
+          mbar_wait(&q_full[slot], (uint32_t)((j / kWgQS) & 1));
+          if (c < NB) {
+            uint8_t* base = smQ + (size_t)slot * QSLOT + c * 128;
+            float f[34];
+            f[0] = 0.0f; f[33] = 0.0f;
+#pragma unroll
+            for (int qq = 0; qq < 8; ++qq) {
+              const float4 r = *reinterpret_cast<const float4*>(base + ((qq ^ sw) << 4));
+              f[1 + 4 * qq] = r.x; f[2 + 4 * qq] = r.y; f[3 + 4 * qq] = r.z; f[4 + 4 * qq] = r.w;
+            }
+            wg_transform(f, k.q_ab, k.q_act, c, k.Qc);
+#pragma unroll
+            for (int qq = 0; qq < 8; ++qq) {
+              const int o = (qq ^ sw) << 4;
+              float4 h, lo4;
+              h.x = tf32_rna(f[4 * qq + 1]); h.y = tf32_rna(f[4 * qq + 2]); h.z = tf32_rna(f[4 * qq + 3]); h.w = tf32_rna(f[4 * qq + 4]);
+              lo4.x = tf32_rna(f[4 * qq + 1] - h.x); lo4.y = tf32_rna(f[4 * qq + 2] - h.y);
+              lo4.z = tf32_rna(f[4 * qq + 3] - h.z); lo4.w = tf32_rna(f[4 * qq + 4] - h.w);
+              *reinterpret_cast<float4*>(base + o) = h;
+              *reinterpret_cast<float4*>(base + QT + o) = lo4;
+            }
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&qs_full[slot]);
+        }
       }
     }
     // ---------------- epilogue: accumulators -> part[split][Lux layout]
@@ -786,18 +842,19 @@ void convtc_wgrad(lrnde_ctx* ctx, const ConvTcGeom& g, const ConvTcWgP& p) {
   const bool swapped = p.Cx < p.Cd;                 // the operand with fewer channels is Q
   const int Pc = swapped ? p.Cd : p.Cx, Qc = swapped ? p.Cx : p.Cd;
   const int NB = convtc_nout(Qc);
-  const CUtensorMap mPhi = wg_map(swapped ? p.Dhi : p.Xhi, g, Pc, 64), mPlo = wg_map(swapped ? p.Dlo : p.Xlo, g, Pc, 64);
-  const CUtensorMap mQhi = wg_map(swapped ? p.Xhi : p.Dhi, g, Qc, NB), mQlo = wg_map(swapped ? p.Xlo : p.Dlo, g, Qc, NB);
+  const CUtensorMap mP = wg_map(swapped ? p.D : p.X, g, Pc, 64), mQ = wg_map(swapped ? p.X : p.D, g, Qc, NB);
   convtc::WgK k;
   k.Ht = g.Ht; k.nrows_total = g.B * g.Ht; k.rows_per_cta = wg_rows_per_cta(g);
   k.Pc = Pc; k.Qc = Qc; k.swapped = swapped ? 1 : 0; k.CinTot = p.CinTot; k.Cd = p.Cd;
   k.part = p.part; k.block = p.block; k.done = p.done;
+  k.p_ab = swapped ? nullptr : p.x_ab; k.p_act = swapped ? ACT_IDENTITY : p.x_act;
+  k.q_ab = swapped ? p.x_ab : nullptr; k.q_act = swapped ? p.x_act : ACT_IDENTITY;
   const char* dbg = getenv("LRNDE_WG_DBG");
   k.dbg = dbg ? atoi(dbg) : 0;
   const int grid = convtc_wgrad_splits(g);
   if (k.dbg & 8) return;
-  if (NB == 64) convtc::wgrad_kernel<64><<<grid, convtc::kThreads, smem64, ctx->stream>>>(mPhi, mPlo, mQhi, mQlo, k);
-  else convtc::wgrad_kernel<16><<<grid, convtc::kThreads, smem16, ctx->stream>>>(mPhi, mPlo, mQhi, mQlo, k);
+  if (NB == 64) convtc::wgrad_kernel<64><<<grid, convtc::kThreads, smem64, ctx->stream>>>(mP, mQ, k);
+  else convtc::wgrad_kernel<16><<<grid, convtc::kThreads, smem16, ctx->stream>>>(mP, mQ, k);
   LCT_COUNT(ctx);
   if (p.tdesc && !(k.dbg & 4)) {
     convtc::time_wgrad_kernel<<<p.Cd, 256, 0, ctx->stream>>>(p.Drowsum, p.Cd, g.Ht, k.nrows_total, p.tdesc, p.Cx, p.CinTot, p.part, p.done);

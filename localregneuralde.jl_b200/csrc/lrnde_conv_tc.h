@@ -14,8 +14,9 @@
 //           is the K-major no-swizzle UMMA layout with a uniform 16-byte row stride: rows = positions, K = channels.
 //           A tap (dy, dx) of the convolution is the SAME shared-memory patch read through a descriptor whose start
 //           address is moved by (dy (W+2) + dx) rows -- nine taps, one copy of the patch, plain bulk copies;
-//       (P) plain [W, H, C, B] hi / lo arrays, the operands of the weight gradient (K = pixels of an image row):
-//           tensor-map TMA delivers the dx-shifted, zero-padded row tiles in the K-major SWIZZLE_128B layout.
+//       (P) for cotangents, a plain [W, H, C, B] fp32 copy: the weight gradient (K = pixels of an image row) reads its
+//           operands -- raw conv outputs, y(t), cotangents -- through tensor-map TMA (K-major SWIZZLE_128B row tiles) and
+//           applies BatchNorm + activation, the hi / lo split and the dx shifts in shared memory.
 //   * convtc_kernel<NOUT>: persistent CTAs, M = 128 consecutive (haloed) positions, N = output channels, K = 8 input
 //     channels per MMA; a group of four M tiles shares every weight stage, accumulators double-buffered in TMEM
 //     (2 x 4 x NOUT columns), epilogue = time-channel term + scale + coalesced [W,H,C,B] stores + BatchNorm partial
@@ -50,7 +51,7 @@ struct ConvTcPackP {
   //   v <- a (g act'(a z + b) - m1 - (z - mean) invstd m2); coef == nullptr: v <- g act'(z)
   const float* bwd_g; const float* bwd_stat; const float* bwd_coef; int bwd_act;
   float* Fhi; float* Flo;                   // (F) layout (may be null)
-  float* Phi; float* Plo;                   // plain hi / lo (may be null)
+  float* Pv;                                // plain fp32 [W,H,C,B] copy of the result: operand of the weight gradient (may be null)
   float* rowsum;                            // [B * Ht][C][3]: (sum, first, last) of every image row of the result (Wd == 32; may be null)
   int C;
   const int* done;
@@ -86,8 +87,10 @@ inline int convtc_stat_rows(const ConvTcGeom& g, int cout) { return g.ngroups * 
 // part[split][Lux weight layout] is summed by wgrad_reduce_kernel in fixed order.  The time channel's weight gradient
 // t * sum_{pixels whose tap stays inside the image} Delta is formed from nine masked sums by convtc_time_wgrad_kernel.
 struct ConvTcWgP {
-  const float* Xhi; const float* Xlo; int Cx;     // input of the convolution [W,H,Cx,B] (time channel excluded), hi / lo
-  const float* Dhi; const float* Dlo; int Cd;     // cotangent of its output [W,H,Cd,B], hi / lo
+  // input of the convolution [W,H,Cx,B] (time channel excluded) = act(a[c] X + b[c]) of a stored array (x_ab / x_act as in
+  // ConvTcPackP::in_ab / in_act; null / ACT_IDENTITY: X itself)
+  const float* X; const float* x_ab; int x_act; int Cx;
+  const float* D; int Cd;                         // cotangent of its output [W,H,Cd,B], fp32
   int CinTot;                                     // Cx + td: layout of the result
   float* part; size_t block;                      // block = 9 * CinTot * Cd floats per split
   const LinComb* tdesc;                           // time channel (null: none)
