@@ -438,7 +438,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_kernel(ConvK k) {
 //   start at a pixel that is not a multiple of 16 bytes: measured, scratch/mb/tma_test.cu); warps 4 and 5 do the same
 //   (without shifts) for the Q rows; Q rows t - 1, t, t + 1 of the same image are the B operands of the taps dy = +1, 0, -1.
 //   A (M = 128) = two adjacent P tiles: (dx = -1, dx = 0) and (dx = +1, whatever follows: rows 64..127 are ignored)
-//   TMEM: accumulator (dy, mt) at columns (dy * 2 + mt) * NB
+//   TMEM: accumulator (dy, mt) at columns (dy * 2 + mt) * NB, zeroed by the epilogue warps before the first MMA.
+//   NB = 16 (few Q channels: the MMAs are bound by the 4 KB A read): the three Q rows of a step are ONE B operand of
+//   N = 48 -- their tiles are adjacent in a ring of 4 slots whose first two are mirrored behind the last -- and the
+//   accumulators of an M tile are adjacent, (mt * 3 + n) * NB with n = 1 - dy: a third of the MMAs.
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kWgXS = 3, kWgQS = 4;                 // ring slots: P rows, Q rows
 constexpr int kWgPTile = 64 * 128;                  // one P tile (hi or lo)
@@ -481,12 +484,17 @@ template <int NB>
 __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constant__ CUtensorMap mP, const __grid_constant__ CUtensorMap mQ, WgK k) {
   if (k.done && *k.done) return;
   constexpr int QT = NB * 128;           // one Q tile (hi or lo)
+  constexpr bool STACK = (NB == 16);
   constexpr int QSLOT = 2 * QT;
+  // Q ring: STACK: [hi of slots 0..5 | lo of slots 0..5] (slots 4, 5 mirror 0, 1); otherwise [hi | lo] per slot
+  auto q_hi = [&](uint8_t* smQ_, int slot) { return STACK ? smQ_ + (size_t)slot * QT : smQ_ + (size_t)slot * QSLOT; };
+  auto q_lo = [&](uint8_t* smQ_, int slot) { return STACK ? smQ_ + (size_t)(6 + slot) * QT : smQ_ + (size_t)slot * QSLOT + QT; };
+  auto acc_col = [&](int dyi, int mt) { return STACK ? (mt * 3 + (2 - dyi)) * NB : (dyi * 2 + mt) * NB; };
   constexpr uint32_t TCOLS = (6 * NB <= 128) ? 128u : 512u;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* sm = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* smQ = sm + kWgXS * kWgXSlot;
-  __shared__ uint64_t x_full[kWgXS], s_full[kWgXS], x_empty[kWgXS], q_full[kWgQS], qs_full[kWgQS], q_empty[kWgQS], acc_done;
+  __shared__ uint64_t x_full[kWgXS], s_full[kWgXS], x_empty[kWgXS], q_full[kWgQS], qs_full[kWgQS], q_empty[kWgQS], acc_done, acc_zero;
   __shared__ uint32_t tmem_slot;
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
@@ -498,6 +506,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
     for (int s = 0; s < kWgXS; ++s) { mbar_init(&x_full[s], 1u); mbar_init(&s_full[s], 2u); mbar_init(&x_empty[s], 1u); }
     for (int s = 0; s < kWgQS; ++s) { mbar_init(&q_full[s], 1u); mbar_init(&qs_full[s], 2u); mbar_init(&q_empty[s], 1u); }
     mbar_init(&acc_done, 1u);
+    mbar_init(&acc_zero, 4u);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -524,7 +533,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
         const int u = t0 - 1 + j;
         // rows in front of / behind the batch: coordinates outside the tensor (zero fill); they are never multiplied
         const int b = (u < 0) ? -1 : u / k.Ht, y = (u < 0) ? 0 : u % k.Ht;
-        uint8_t* dst = smQ + (size_t)slot * QSLOT;
+        uint8_t* dst = q_hi(smQ, slot);
         mbar_arrive_expect_tx(&q_full[slot], (uint32_t)QT);
         tma_load_4d(dst, &mQ, 0, y, 0, b, &q_full[slot]);
       }
@@ -546,9 +555,10 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
     }
   } else if (warp == 1) {
     // ---------------- tcgen05.mma issue
-    const uint32_t idesc = make_idesc(128, NB);
-    uint32_t touched = 0;
+    const uint32_t idesc1 = make_idesc(128, NB), idesc2 = make_idesc(128, 2 * NB), idesc3 = make_idesc(128, 3 * NB);
     int q_arrived = 0;
+    mbar_wait(&acc_zero, 0u);
+    tc_fence_after();
     for (int i = 0; i < n; ++i) {
       const int xs = i % kWgXS;
       mbar_wait(&s_full[xs], (uint32_t)((i / kWgXS) & 1));
@@ -558,38 +568,67 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
       }
       tc_fence_after();
       const int yy = (t0 + i) % k.Ht;
-      if (elect_one_sync()) {
+      if (elect_one_sync() && !(k.dbg & 2)) {
         const uint32_t xb = smem_u32(sm + (size_t)xs * kWgXSlot);
-#pragma unroll 1
-        for (int dyi = 0; dyi < 3; ++dyi) {
-          const int dy = dyi - 1, y = yy - dy;
-          if (y < 0 || y >= k.Ht || (k.dbg & 2)) continue;
-          const int j = i + 1 - dy;
-          const uint32_t qb = smem_u32(smQ + (size_t)(j % kWgQS) * QSLOT);
-          const uint32_t qh = desc_lo(qb), ql = desc_lo(qb + QT);
-          const uint32_t fresh = ((touched >> dyi) & 1u) ? 1u : 0u;
+        if (STACK) {
+          // Q rows i + n (n = 0, 1, 2 <-> dy = +1, 0, -1) of the same image, adjacent in the (mirrored) ring: one B operand
+          const int n0 = (yy == 0) ? 1 : 0, n1 = (yy == k.Ht - 1) ? 1 : 2, cnt = n1 - n0 + 1;
+          const int s0 = (i + n0) % kWgQS;
+          const uint32_t qh = desc_lo(smem_u32(q_hi(smQ, s0))), ql = desc_lo(smem_u32(q_lo(smQ, s0)));
+          const uint32_t idesc = cnt == 3 ? idesc3 : (cnt == 2 ? idesc2 : idesc1);
 #pragma unroll
           for (int mt = 0; mt < 2; ++mt) {
             const uint32_t ah = desc_lo(xb + mt * 2 * kWgPTile), al = desc_lo(xb + 3 * kWgPTile + mt * 2 * kWgPTile);
-            const uint32_t d = tmem_base + (uint32_t)((dyi * 2 + mt) * NB);
+            const uint32_t d = tmem_base + (uint32_t)((mt * 3 + n0) * NB);
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
-              mma<0>(d, al + 2 * ks, qh + 2 * ks, fused::kHi128, idesc, (ks > 0) ? 1u : fresh);
+              mma<0>(d, al + 2 * ks, qh + 2 * ks, fused::kHi128, idesc, 1u);
               mma<1>(d, ah + 2 * ks, ql + 2 * ks, fused::kHi128, idesc, 1u);
               mma<2>(d, ah + 2 * ks, qh + 2 * ks, fused::kHi128, idesc, 1u);
             }
           }
-          touched |= 1u << dyi;
+        } else {
+#pragma unroll 1
+          for (int dyi = 0; dyi < 3; ++dyi) {
+            const int dy = dyi - 1, y = yy - dy;
+            if (y < 0 || y >= k.Ht) continue;
+            const int j = i + 1 - dy;
+            const uint32_t qh = desc_lo(smem_u32(q_hi(smQ, j % kWgQS))), ql = desc_lo(smem_u32(q_lo(smQ, j % kWgQS)));
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+              const uint32_t ah = desc_lo(xb + mt * 2 * kWgPTile), al = desc_lo(xb + 3 * kWgPTile + mt * 2 * kWgPTile);
+              const uint32_t d = tmem_base + (uint32_t)acc_col(dyi, mt);
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {
+                mma<0>(d, al + 2 * ks, qh + 2 * ks, fused::kHi128, idesc1, 1u);
+                mma<1>(d, ah + 2 * ks, ql + 2 * ks, fused::kHi128, idesc1, 1u);
+                mma<2>(d, ah + 2 * ks, qh + 2 * ks, fused::kHi128, idesc1, 1u);
+              }
+            }
+          }
         }
+      }
+      __syncwarp();
+      if (elect_one_sync()) {
         mma_commit(&x_empty[xs]);
         mma_commit(&q_empty[i % kWgQS]);      // Q row j = i (flattened row t - 1): its last use was this step
         if (i == n - 1) mma_commit(&acc_done);
       }
-      touched = __shfl_sync(0xffffffffu, touched, 0) | touched;   // (the elected lane may change between steps)
-      touched = __reduce_or_sync(0xffffffffu, touched);
       __syncwarp();
     }
   } else {
+    // ---------------- accumulators <- 0 (every MMA accumulates; a tap whose rows never meet in this range stays zero)
+    {
+      const uint32_t tl = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+      float zero16[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) zero16[j] = 0.0f;
+      for (int c0 = 0; c0 < 6 * NB; c0 += 16) fused::tmem_st16(tl + (uint32_t)c0, zero16);
+      fused::tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_zero);
+    }
     // ---------------- operand preparation in shared memory (conflict-free 16-byte accesses: a thread per 128-byte row)
     {
       const int tt = threadIdx.x - 64;
@@ -630,7 +669,9 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
           const int slot = j % kWgQS;
           mbar_wait(&q_full[slot], (uint32_t)((j / kWgQS) & 1));
           if (c < NB) {
-            uint8_t* base = smQ + (size_t)slot * QSLOT + c * 128;
+            uint8_t* base = q_hi(smQ, slot) + c * 128;
+            uint8_t* base_lo = q_lo(smQ, slot) + c * 128;
+            const bool mirror = STACK && slot < 2;
             float f[34];
             f[0] = 0.0f; f[33] = 0.0f;
 #pragma unroll
@@ -647,7 +688,11 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
               lo4.x = tf32_rna(f[4 * qq + 1] - h.x); lo4.y = tf32_rna(f[4 * qq + 2] - h.y);
               lo4.z = tf32_rna(f[4 * qq + 3] - h.z); lo4.w = tf32_rna(f[4 * qq + 4] - h.w);
               *reinterpret_cast<float4*>(base + o) = h;
-              *reinterpret_cast<float4*>(base + QT + o) = lo4;
+              *reinterpret_cast<float4*>(base_lo + o) = lo4;
+              if (mirror) {
+                *reinterpret_cast<float4*>(base + 4 * QT + o) = h;
+                *reinterpret_cast<float4*>(base_lo + 4 * QT + o) = lo4;
+              }
             }
           }
           fence_proxy_async();
@@ -669,16 +714,13 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
     const int pc = m & 63;
 #pragma unroll 1
     for (int dyi = 0; dyi < 3; ++dyi) {
-      // a tap whose rows never met inside this CTA's range has an untouched accumulator: it contributes zero
-      bool met = false;
-      for (int i = 0; i < n && !met; ++i) { const int y = (t0 + i) % k.Ht - (dyi - 1); met = (y >= 0 && y < k.Ht); }
 #pragma unroll 1
       for (int mt = 0; mt < 2; ++mt) {
         const int dxi = mt * 2 + (m >> 6);
 #pragma unroll 1
         for (int cc = 0; cc < NB / 16; ++cc) {
           float v[16];
-          tmem_ld16(tlane + (uint32_t)((dyi * 2 + mt) * NB + cc * 16), v);
+          tmem_ld16(tlane + (uint32_t)(acc_col(dyi, mt) + cc * 16), v);
           if (dxi < 3 && pc < k.Pc) {
             // normal : P = X (ci = pc), Q = Delta (co = qc): accumulator (dy, dx) is the tap itself -> w[2 - dx, 2 - dy]
             // swapped: P = Delta (co = pc) shifted by s, Q = X (ci = qc): tap d = -s -> w[dx, dy]
@@ -688,7 +730,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
               const int qc = cc * 16 + jn;
               if (qc < k.Qc) {
                 const int ci = k.swapped ? qc : pc, co = k.swapped ? pc : qc;
-                out[kx + 3 * (ky + 3 * (ci + (size_t)k.CinTot * co))] = met ? v[jn] : 0.0f;
+                out[kx + 3 * (ky + 3 * (ci + (size_t)k.CinTot * co))] = v[jn];
               }
             }
           }
@@ -706,15 +748,18 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
 
 // weight gradient of the time channel: dW[tap, time, co] = t * sum_{b, pixels p with p + d_tap inside the image} Delta[p, co]
 // = t * (T - [dy=-1] Top - [dy=+1] Bottom - [dx=-1] Left - [dx=+1] Right + the excluded corner), from the per-row
-// (sum, first, last) triples the pack kernel wrote while it formed Delta.  grid = Cd blocks; fixed-order tree: deterministic.
-// Written into split 0 of `part` (wgrad_kernel zero-fills the time entries of every split).
+// (sum, first, last) triples the pack kernel wrote while it formed Delta.  grid (Cd, nsp): block (c, s) takes the rows
+// r = s (mod nsp) and writes into split s of `part` (wgrad_kernel zero-fills the time entries of every split; nsp <= splits).
+// Fixed partition, fixed-order tree: deterministic.
 __global__ void __launch_bounds__(256) time_wgrad_kernel(const float* __restrict__ rowsum, int Cd, int Ht, int nrows_total,
-                                                         const LinComb* tdesc, int Cx, int CinTot, float* part, const int* done) {
+                                                         const LinComb* tdesc, int Cx, int CinTot, float* part, size_t block,
+                                                         const int* done) {
   if (done && *done) return;
   __shared__ double red[9][256];
   const int c = blockIdx.x, tid = threadIdx.x;
+  part += (size_t)blockIdx.y * block;
   double a[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};   // T, top, bottom, left, right, tl, tr, bl, br
-  for (int r = tid; r < nrows_total; r += 256) {
+  for (int r = blockIdx.y + gridDim.y * tid; r < nrows_total; r += 256 * gridDim.y) {
     const float* src = rowsum + ((size_t)r * Cd + c) * 3;
     const float s = src[0], v0 = src[1], v31 = src[2];
     const int y = r % Ht;
@@ -833,7 +878,7 @@ static CUtensorMap wg_map(const float* base, const ConvTcGeom& g, int C, int box
 void convtc_wgrad(lrnde_ctx* ctx, const ConvTcGeom& g, const ConvTcWgP& p) {
   static bool attr_set = false;
   const int smem64 = convtc::kWgXS * convtc::kWgXSlot + convtc::kWgQS * 2 * 64 * 128 + 1024 + 8192;   // + the ignored rows of the last A tile
-  const int smem16 = convtc::kWgXS * convtc::kWgXSlot + convtc::kWgQS * 2 * 16 * 128 + 1024 + 8192;
+  const int smem16 = convtc::kWgXS * convtc::kWgXSlot + 12 * 16 * 128 + 1024 + 8192;   // Q ring of 4 + 2 mirrored slots, hi and lo
   if (!attr_set) {
     LR_CUDA(cudaFuncSetAttribute(convtc::wgrad_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem64));
     LR_CUDA(cudaFuncSetAttribute(convtc::wgrad_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem16));
@@ -857,7 +902,9 @@ void convtc_wgrad(lrnde_ctx* ctx, const ConvTcGeom& g, const ConvTcWgP& p) {
   else convtc::wgrad_kernel<16><<<grid, convtc::kThreads, smem16, ctx->stream>>>(mP, mQ, k);
   LCT_COUNT(ctx);
   if (p.tdesc && !(k.dbg & 4)) {
-    convtc::time_wgrad_kernel<<<p.Cd, 256, 0, ctx->stream>>>(p.Drowsum, p.Cd, g.Ht, k.nrows_total, p.tdesc, p.Cx, p.CinTot, p.part, p.done);
+    convtc::time_wgrad_kernel<<<dim3(p.Cd, std::min(8, grid)), 256, 0, ctx->stream>>>(p.Drowsum, p.Cd, g.Ht, k.nrows_total, p.tdesc, p.Cx,
+                                                                                   p.CinTot, p.part, p.block, p.done);
     LCT_COUNT(ctx);
   }
 }
+
