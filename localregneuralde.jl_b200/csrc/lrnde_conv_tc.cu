@@ -439,11 +439,12 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_kernel(ConvK k) {
 //   (without shifts) for the Q rows; Q rows t - 1, t, t + 1 of the same image are the B operands of the taps dy = +1, 0, -1.
 //   A (M = 128) = two adjacent P tiles: (dx = -1, dx = 0) and (dx = +1, whatever follows: rows 64..127 are ignored)
 //   TMEM: accumulator (dy, mt) at columns (dy * 2 + mt) * NB, zeroed by the epilogue warps before the first MMA.
-//   NB = 16 (few Q channels: the MMAs are bound by the 4 KB A read): the three Q rows of a step are ONE B operand of
-//   N = 48 -- their tiles are adjacent in a ring of 4 slots whose first two are mirrored behind the last -- and the
-//   accumulators of an M tile are adjacent, (mt * 3 + n) * NB with n = 1 - dy: a third of the MMAs.
+//   The three Q rows of a step are ONE B operand of N = 3 NB -- their tiles are adjacent in a ring of 4 slots whose first
+//   two are mirrored behind the last -- and the accumulators of an M tile are adjacent, (mt * 3 + n) * NB with n = 1 - dy:
+//   a third of the MMAs and of the A-operand reads (the separate N = NB MMAs were bound by shared-memory bandwidth).
 // ---------------------------------------------------------------------------------------------------------
-constexpr int kWgXS = 3, kWgQS = 4;                 // ring slots: P rows, Q rows
+constexpr int kWgQS = 4;                            // Q ring slots (+ 2 mirrors)
+__host__ __device__ constexpr int wg_xs(int NB) { return NB == 64 ? 2 : 3; }   // P ring slots (the mirrored Q ring of 64-row tiles takes 96 KB)
 constexpr int kWgPTile = 64 * 128;                  // one P tile (hi or lo)
 constexpr int kWgXSlot = 6 * kWgPTile;              // [hi dx-1 | hi dx0 | hi dx+1 | lo dx-1 | lo dx0 | lo dx+1]
 
@@ -484,7 +485,8 @@ template <int NB>
 __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constant__ CUtensorMap mP, const __grid_constant__ CUtensorMap mQ, WgK k) {
   if (k.done && *k.done) return;
   constexpr int QT = NB * 128;           // one Q tile (hi or lo)
-  constexpr bool STACK = (NB == 16);
+  constexpr bool STACK = true;
+  constexpr int kWgXS = wg_xs(NB);
   constexpr int QSLOT = 2 * QT;
   // Q ring: STACK: [hi of slots 0..5 | lo of slots 0..5] (slots 4, 5 mirror 0, 1); otherwise [hi | lo] per slot
   auto q_hi = [&](uint8_t* smQ_, int slot) { return STACK ? smQ_ + (size_t)slot * QT : smQ_ + (size_t)slot * QSLOT; };
@@ -877,8 +879,9 @@ static CUtensorMap wg_map(const float* base, const ConvTcGeom& g, int C, int box
 }
 void convtc_wgrad(lrnde_ctx* ctx, const ConvTcGeom& g, const ConvTcWgP& p) {
   static bool attr_set = false;
-  const int smem64 = convtc::kWgXS * convtc::kWgXSlot + convtc::kWgQS * 2 * 64 * 128 + 1024 + 8192;   // + the ignored rows of the last A tile
-  const int smem16 = convtc::kWgXS * convtc::kWgXSlot + 12 * 16 * 128 + 1024 + 8192;   // Q ring of 4 + 2 mirrored slots, hi and lo
+  // P ring + Q ring of 4 + 2 mirrored slots (hi and lo) + alignment + the ignored rows of the last A tile
+  const int smem64 = convtc::wg_xs(64) * convtc::kWgXSlot + 12 * 64 * 128 + 1024 + 8192;
+  const int smem16 = convtc::wg_xs(16) * convtc::kWgXSlot + 12 * 16 * 128 + 1024 + 8192;
   if (!attr_set) {
     LR_CUDA(cudaFuncSetAttribute(convtc::wgrad_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem64));
     LR_CUDA(cudaFuncSetAttribute(convtc::wgrad_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem16));
