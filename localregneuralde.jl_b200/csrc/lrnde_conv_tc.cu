@@ -868,9 +868,24 @@ static CUtensorMap wg_map(const float* base, const ConvTcGeom& g, int C, int box
   const cuuint64_t strides[3] = {(cuuint64_t)g.Wd * 4, (cuuint64_t)g.Wd * g.Ht * 4, (cuuint64_t)g.Wd * g.Ht * C * 4};
   const cuuint32_t box[4] = {32, 1, (cuuint32_t)boxC, 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
-  const CUresult r = cuTensorMapEncodeTiled(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, estr,
-                                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  // the driver entry point is looked up at run time: libLRNDE.so must load (and export its symbols) on a box without libcuda.so.1
+  typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeTiled encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    LR_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) {
+      lr_set_error("cuTensorMapEncodeTiled is not available from this driver");
+      throw LrError(LRNDE_ECUDA);
+    }
+    encode = reinterpret_cast<EncodeTiled>(fn);
+  }
+  const CUresult r = encode(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     lr_set_error("cuTensorMapEncodeTiled failed (%d) for a [%d,%d,%d,%d] tensor", (int)r, g.Wd, g.Ht, C, g.B);
     throw LrError(LRNDE_ECUDA);
