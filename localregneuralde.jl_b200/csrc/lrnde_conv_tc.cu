@@ -173,11 +173,20 @@ __global__ void wpack_kernel(const float* w, int CinTot, int Cout, int transpose
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n_img; e += gridDim.x * blockDim.x) {
     int r = e;
     const int j = r & 3; r >>= 2;
-    const int n = r % NOUT; r /= NOUT;
-    const int k4 = r & 1; r >>= 1;
-    const int tap = r % 9; r /= 9;
-    const int part = r & 1; r >>= 1;
-    const int s = r;
+    int n, k4, tap, part, s;
+    if (NOUT == 16) {   // [stage][tap][k4][hi rows 0..15 | lo rows 16..31][4]: [B_hi; B_lo] is ONE B operand of N = 32
+      n = r & 15; r >>= 4;
+      part = r & 1; r >>= 1;
+      k4 = r & 1; r >>= 1;
+      tap = r % 9; r /= 9;
+      s = r;
+    } else {            // [stage][hi | lo][tap][k4][NOUT rows][4]
+      n = r % NOUT; r /= NOUT;
+      k4 = r & 1; r >>= 1;
+      tap = r % 9; r /= 9;
+      part = r & 1; r >>= 1;
+      s = r;
+    }
     const int k = 8 * s + 4 * k4 + j;
     float v = 0.0f;
     if (n < Nreal) v = wl_at(w, CinTot, Cout, transposed, tap, k, n);
@@ -229,7 +238,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_kernel(ConvK k) {
   const ConvTcP& p = k.p;
   if (p.done && *p.done) return;
   constexpr int STB = stage_bytes(NOUT), WSB = wstage_bytes(NOUT);
-  constexpr int TCOLS = 2 * kTiles * NOUT;   // 512 (NOUT = 64) or 128 (NOUT = 16)
+  // NOUT = 16 (bound by MMA issue / the A read, not by N): D[:, 0:16] += A_hi B_hi + A_lo B_hi, D[:, 16:32] += A_hi B_lo with
+  // B' = [B_hi; B_lo] as one N = 32 operand: two MMAs per K-step instead of three; the epilogue adds the two halves
+  constexpr int DCOL = (NOUT == 16) ? 32 : NOUT;
+  constexpr int TCOLS = 2 * kTiles * DCOL;   // 512 (NOUT = 64) or 256 (NOUT = 16)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* sm = (uint8_t*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
   __shared__ uint64_t full_bar[kStages], empty_bar[kStages], acc_full[2], tmem_free[2];
@@ -284,7 +296,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_kernel(ConvK k) {
     }
   } else if (warp == 1) {
     // ---------------- tcgen05.mma issue: D[128 positions x NOUT] += A(patch shifted by the tap) x B(weights of the tap)
-    const uint32_t idesc = make_idesc(128, NOUT);
+    const uint32_t idesc = make_idesc(128, NOUT), idesc32 = make_idesc(128, 32);
     uint32_t ks = 0;
     int it = 0;
     for (int g = blockIdx.x; g < k.ngroups; g += gridDim.x, ++it) {
@@ -301,17 +313,22 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_kernel(ConvK k) {
 #pragma unroll 1
           for (int tap = 0; tap < 9; ++tap) {
             const int sh = (tap / 3 - 1) * k.PW + (tap % 3 - 1);
-            const uint32_t bh = dlo(wb + tap * (2 * NOUT * 16), NOUT * 16);
+            const uint32_t bh = (NOUT == 16) ? dlo(wb + tap * (2 * 32 * 16), 32 * 16) : dlo(wb + tap * (2 * NOUT * 16), NOUT * 16);
             const uint32_t bl = dlo(wb + 9 * 2 * NOUT * 16 + tap * (2 * NOUT * 16), NOUT * 16);
             const uint32_t acc = (s > 0 || tap > 0) ? 1u : 0u;
 #pragma unroll
             for (int i = 0; i < kTiles; ++i) {
               const uint32_t aoff = (uint32_t)((kCtGuard + i * 128 + sh) * 16);
               const uint32_t ah = dlo(base + aoff, kRunB), al = dlo(base + 2 * kRunB + aoff, kRunB);
-              const uint32_t d = tmem_base + (uint32_t)(db * kTiles * NOUT + i * NOUT);
-              mma<0>(d, al, bh, kHiNone, idesc, acc);
-              mma<1>(d, ah, bl, kHiNone, idesc, 1u);
-              mma<2>(d, ah, bh, kHiNone, idesc, 1u);
+              const uint32_t d = tmem_base + (uint32_t)(db * kTiles * DCOL + i * DCOL);
+              if (NOUT == 16) {
+                mma<0>(d, ah, bh, kHiNone, idesc32, acc);     // [A_hi B_hi | A_hi B_lo]
+                mma<0>(d, al, bh, kHiNone, idesc, 1u);        // A_lo B_hi into the first half
+              } else {
+                mma<0>(d, al, bh, kHiNone, idesc, acc);
+                mma<1>(d, ah, bl, kHiNone, idesc, 1u);
+                mma<2>(d, ah, bh, kHiNone, idesc, 1u);
+              }
             }
           }
           mma_commit(&empty_bar[slot]);
@@ -362,7 +379,13 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_kernel(ConvK k) {
           const size_t obase = obase0 + (size_t)(cc * 16) * HW;
           const float* ts = (p.tsum && !no_ts) ? p.tsum + (ym * 8 + xm) * NOUT + cc * 16 : nullptr;
           float v[16];
-          tmem_ld16(tlane + (uint32_t)(db * kTiles * NOUT + i * NOUT + cc * 16), v);
+          tmem_ld16(tlane + (uint32_t)(db * kTiles * DCOL + i * DCOL + cc * 16), v);
+          if (NOUT == 16) {
+            float v2[16];
+            tmem_ld16(tlane + (uint32_t)(db * kTiles * DCOL + i * DCOL + 16), v2);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] += v2[j];
+          }
           if (valid && !(k.dbg & 16)) {
             // every load of the chunk is issued before the arithmetic (one basic block: no per-element branches; the
             // channels >= Cout of a partial chunk have zero weights, so their accumulators and table entries are zero)
