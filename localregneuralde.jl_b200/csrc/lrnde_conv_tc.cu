@@ -246,6 +246,15 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_kernel(ConvK k) {
   uint8_t* sm = (uint8_t*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
   __shared__ uint64_t full_bar[kStages], empty_bar[kStages], acc_full[2], tmem_free[2];
   __shared__ uint32_t tmem_slot;
+  // per-channel constants of the BatchNorm pullback (a, b, mean, invstd): with 222 KB of shared memory there is next to no
+  // L1 left, every __ldg of them went to L2 (long-scoreboard stalls on the first FFMA were 90 % of the epilogue's samples)
+  __shared__ float s_bw[MODE == 2 ? 4 : 1][MODE == 2 ? 64 : 1];
+  if (MODE == 2 && threadIdx.x < 64) {
+    const int c = threadIdx.x;
+    const bool ok = c < p.Cout;
+    s_bw[0][c] = ok ? p.bwd_ab[c] : 0.0f; s_bw[1][c] = ok ? p.bwd_ab[p.Cout + c] : 0.0f;
+    s_bw[2][c] = ok ? p.bwd_stat[c] : 0.0f; s_bw[3][c] = ok ? p.bwd_stat[p.Cout + c] : 0.0f;
+  }
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
@@ -389,39 +398,30 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_kernel(ConvK k) {
           if (valid && !(k.dbg & 16)) {
             // every load of the chunk is issued before the arithmetic (one basic block: no per-element branches; the
             // channels >= Cout of a partial chunk have zero weights, so their accumulators and table entries are zero)
-            constexpr int JB = (MODE == 2) ? 8 : 16;     // elements per batch (register pressure of the pullback constants)
             float* o = out + obase;
+            float tsv[16], zz[16];
+            if (MODE != 2) {
 #pragma unroll
-            for (int j0 = 0; j0 < 16; j0 += JB) {
-              float tsv[JB], zz[JB], ca[JB], cb[JB], cm[JB], ci[JB];
-              if (MODE != 2) {
+              for (int j = 0; j < 16; ++j) tsv[j] = ts ? __ldg(ts + j) : 0.0f;
+            } else {
 #pragma unroll
-                for (int j = 0; j < JB; ++j) tsv[j] = ts ? __ldg(ts + j0 + j) : 0.0f;
-              } else {
+              for (int j = 0; j < 16; ++j) zz[j] = __ldcg(p.bwd_z + obase0 + (size_t)min(cc * 16 + j, p.Cout - 1) * HW);
+            }
 #pragma unroll
-                for (int j = 0; j < JB; ++j) {
-                  const int co = min(cc * 16 + j0 + j, p.Cout - 1);
-                  zz[j] = __ldcg(p.bwd_z + obase0 + (size_t)co * HW);
-                  ca[j] = __ldg(p.bwd_ab + co); cb[j] = __ldg(p.bwd_ab + p.Cout + co);
-                  cm[j] = __ldg(p.bwd_stat + co); ci[j] = __ldg(p.bwd_stat + p.Cout + co);
-                }
+            for (int j = 0; j < 16; ++j) {
+              float r = v[j];
+              if (MODE != 2) r = fmaf(tval, tsv[j], r);
+              if (MODE == 1) {
+                st[h2][j] += r;
+                st[h2][16 + j] = fmaf(r, r, st[h2][16 + j]);
+              } else if (MODE == 2) {
+                const int c = cc * 16 + j;
+                const float pre = fmaf(s_bw[0][c], zz[j], s_bw[1][c]);
+                const float gh = r * (gelu_bwd ? gelu_d(pre) : dact_call(p.bwd_act, pre));
+                st[h2][j] += gh;
+                st[h2][16 + j] = fmaf(gh, (zz[j] - s_bw[2][c]) * s_bw[3][c], st[h2][16 + j]);
               }
-#pragma unroll
-              for (int j = 0; j < JB; ++j) {
-                const int jj = j0 + j;
-                float r = v[jj];
-                if (MODE != 2) r = fmaf(tval, tsv[j], r);
-                if (MODE == 1) {
-                  st[h2][jj] += r;
-                  st[h2][16 + jj] = fmaf(r, r, st[h2][16 + jj]);
-                } else if (MODE == 2) {
-                  const float pre = fmaf(ca[j], zz[j], cb[j]);
-                  const float gh = r * (gelu_bwd ? gelu_d(pre) : dact_call(p.bwd_act, pre));
-                  st[h2][jj] += gh;
-                  st[h2][16 + jj] = fmaf(gh, (zz[j] - cm[j]) * ci[j], st[h2][16 + jj]);
-                }
-                if (cc * 16 + jj < p.Cout && !no_store) o[(size_t)jj * HW] = r * oscale;
-              }
+              if (cc * 16 + j < p.Cout && !no_store) o[(size_t)j * HW] = r * oscale;
             }
           }
         }

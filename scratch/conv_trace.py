@@ -13,7 +13,11 @@ chain = pkg.TDConvChain(pkg.ConvChain(*layers, width=32, height=32))
 layer = pkg.NeuralODE(chain)
 ps = torch.from_numpy(layer.initialparameters(np.random.default_rng(0))).cuda()
 u = torch.randn((8192, B), device="cuda")
-for _ in range(3): layer.dynamics(u, ps, 0.5)
+if len(sys.argv) > 3 and sys.argv[3] == "vjp":   # the last matching convolution of a right-hand side (data gradient, pullback epilogue)
+    un, pn = u.cpu().numpy(), ps.cpu().numpy()
+    for _ in range(3): layer.dynamics_vjp(un, pn, 0.5, un)
+else:
+    for _ in range(3): layer.dynamics(u, ps, 0.5)
 torch.cuda.synchronize()
 buf = (C.c_longlong * 128)()
 lib.lrnde_debug_trace_convtc(buf, 128)
