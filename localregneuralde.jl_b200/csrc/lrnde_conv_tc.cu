@@ -467,6 +467,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_kernel(ConvK k) {
 //   a third of the MMAs and of the A-operand reads (the separate N = NB MMAs were bound by shared-memory bandwidth).
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kWgQS = 4;                            // Q ring slots (+ 2 mirrors)
+constexpr int kWgRS = 4;                            // raw P tiles in flight (TMA staging ring: the TMA latency of ~1-2 us is not
+                                                    // part of the MMA -> operand preparation -> MMA chain of a P slot)
 __host__ __device__ constexpr int wg_xs(int NB) { return NB == 64 ? 2 : 3; }   // P ring slots (the mirrored Q ring of 64-row tiles takes 96 KB)
 constexpr int kWgPTile = 64 * 128;                  // one P tile (hi or lo)
 constexpr int kWgXSlot = 6 * kWgPTile;              // [hi dx-1 | hi dx0 | hi dx+1 | lo dx-1 | lo dx0 | lo dx+1]
@@ -481,10 +483,10 @@ struct WgK {
 };
 
 // one operand row of 32 pixels: BatchNorm scale / shift + activation (rows >= C of the box are zero fill: left alone)
-__device__ __forceinline__ void wg_transform(float (&f)[34], const float* ab, int act, int c, int C) {
+// (a, b: the row's scale / shift, fetched ONCE per thread -- the kernel has next to no L1 and a __ldg per step went to L2)
+__device__ __forceinline__ void wg_transform(float (&f)[34], bool affine, float a, float b, int act, int c, int C) {
   if (c >= C) return;
-  if (ab) {
-    const float a = __ldg(ab + c), b = __ldg(ab + C + c);
+  if (affine) {
 #pragma unroll
     for (int x = 1; x <= 32; ++x) f[x] = fmaf(a, f[x], b);
   }
@@ -519,7 +521,9 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
   extern __shared__ uint8_t smem_raw[];
   uint8_t* sm = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* smQ = sm + kWgXS * kWgXSlot;
-  __shared__ uint64_t x_full[kWgXS], s_full[kWgXS], x_empty[kWgXS], q_full[kWgQS], qs_full[kWgQS], q_empty[kWgQS], acc_done, acc_zero;
+  uint8_t* smR = smQ + 12 * QT;          // raw P tiles (after the Q ring: the ignored rows of the last A tile read into the Q ring)
+  __shared__ uint64_t r_full[kWgRS], r_empty[kWgRS], s_full[kWgXS], x_empty[kWgXS], q_full[kWgQS], qs_full[kWgQS], q_empty[kWgQS], acc_done,
+      acc_zero;
   __shared__ uint32_t tmem_slot;
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
@@ -528,7 +532,8 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
   const int n = min(k.rows_per_cta, k.nrows_total - t0);   // >= 1 by construction of the grid
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kWgXS; ++s) { mbar_init(&x_full[s], 1u); mbar_init(&s_full[s], 2u); mbar_init(&x_empty[s], 1u); }
+    for (int s = 0; s < kWgXS; ++s) { mbar_init(&s_full[s], 2u); mbar_init(&x_empty[s], 1u); }
+    for (int s = 0; s < kWgRS; ++s) { mbar_init(&r_full[s], 1u); mbar_init(&r_empty[s], 2u); }
     for (int s = 0; s < kWgQS; ++s) { mbar_init(&q_full[s], 1u); mbar_init(&qs_full[s], 2u); mbar_init(&q_empty[s], 1u); }
     mbar_init(&acc_done, 1u);
     mbar_init(&acc_zero, 4u);
@@ -543,6 +548,8 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
+  const bool ctrace_on = (k.dbg & 32) && blockIdx.x == 0 && (!(k.dbg & 64) || NB == 64);   // LRNDE_WG_DBG=32 (+64: only NB = 64)
+  if (threadIdx.x == 0) CTRACE(0, 0);
 
   if (k.dbg & 1) {
     if (warp >= 2) {
@@ -567,13 +574,13 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
     load_q(0);
     load_q(1);
     for (int i = 0; i < n; ++i) {
-      const int slot = i % kWgXS;
-      if (i >= kWgXS) mbar_wait(&x_empty[slot], (uint32_t)(((i / kWgXS) - 1) & 1));
+      const int slot = i % kWgRS;
+      if (i >= kWgRS) mbar_wait(&r_empty[slot], (uint32_t)(((i / kWgRS) - 1) & 1));
       if (elect_one_sync()) {
         const int t = t0 + i, b = t / k.Ht, y = t % k.Ht;
-        uint8_t* dst = sm + (size_t)slot * kWgXSlot;
-        mbar_arrive_expect_tx(&x_full[slot], (uint32_t)kWgPTile);
-        tma_load_4d(dst + 1 * kWgPTile, &mP, 0, y, 0, b, &x_full[slot]);
+        CTRACE(1, i);
+        mbar_arrive_expect_tx(&r_full[slot], (uint32_t)kWgPTile);
+        tma_load_4d(smR + (size_t)slot * kWgPTile, &mP, 0, y, 0, b, &r_full[slot]);
       }
       __syncwarp();
       load_q(i + 2);
@@ -594,6 +601,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
       tc_fence_after();
       const int yy = (t0 + i) % k.Ht;
       if (elect_one_sync() && !(k.dbg & 2)) {
+        CTRACE(4, i);
         const uint32_t xb = smem_u32(sm + (size_t)xs * kWgXSlot);
         if (STACK) {
           // Q rows i + n (n = 0, 1, 2 <-> dy = +1, 0, -1) of the same image, adjacent in the (mirrored) ring: one B operand
@@ -659,21 +667,29 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
       const int tt = threadIdx.x - 64;
       if (tt < 64) {   // P rows: transform, split, and the dx = -1 / +1 copies
         const int c = tt, sw = c & 7;
+        const bool aff = k.p_ab != nullptr && c < k.Pc;
+        const float ta = aff ? __ldg(k.p_ab + c) : 1.0f, tb = aff ? __ldg(k.p_ab + k.Pc + c) : 0.0f;
         for (int i = 0; i < n; ++i) {
-          const int slot = i % kWgXS;
-          mbar_wait(&x_full[slot], (uint32_t)((i / kWgXS) & 1));
+          const int slot = i % kWgXS, rs = i % kWgRS;
+          mbar_wait(&r_full[rs], (uint32_t)((i / kWgRS) & 1));
+          if (tt == 0) CTRACE(2, i);
+          const uint8_t* raw = smR + (size_t)rs * kWgPTile + c * 128;
           uint8_t* base = sm + (size_t)slot * kWgXSlot + c * 128;
           float f[34];
           f[0] = 0.0f; f[33] = 0.0f;
 #pragma unroll
           for (int qq = 0; qq < 8; ++qq) {
-            const float4 r = *reinterpret_cast<const float4*>(base + kWgPTile + ((qq ^ sw) << 4));
+            const float4 r = *reinterpret_cast<const float4*>(raw + ((qq ^ sw) << 4));
             f[1 + 4 * qq] = r.x; f[2 + 4 * qq] = r.y; f[3 + 4 * qq] = r.z; f[4 + 4 * qq] = r.w;
           }
-          wg_transform(f, k.p_ab, k.p_act, c, k.Pc);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&r_empty[rs]);        // the raw tile is in registers: the TMA may refill the stage
+          wg_transform(f, aff, ta, tb, k.p_act, c, k.Pc);
           float l[34];
 #pragma unroll
           for (int x = 0; x < 34; ++x) { const float h = tf32_rna(f[x]); l[x] = tf32_rna(f[x] - h); f[x] = h; }
+          // the MMAs that read this P slot two (three) steps ago are done
+          if (i >= kWgXS) mbar_wait(&x_empty[slot], (uint32_t)(((i / kWgXS) - 1) & 1));
 #pragma unroll
           for (int qq = 0; qq < 8; ++qq) {   // f[1 + x] = P[x]: the dx = -1 tile holds P[x - 1], the dx = +1 tile P[x + 1]
             const int o = (qq ^ sw) << 4;
@@ -686,10 +702,13 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
           }
           fence_proxy_async();
           __syncwarp();
+          if (tt == 0) CTRACE(3, i);
           if (lane == 0) mbar_arrive(&s_full[slot]);
         }
       } else {         // Q rows: transform and split
         const int c = tt - 64, sw = c & 7;
+        const bool aff = k.q_ab != nullptr && c < k.Qc;
+        const float ta = aff ? __ldg(k.q_ab + c) : 1.0f, tb = aff ? __ldg(k.q_ab + k.Qc + c) : 0.0f;
         for (int j = 0; j < n + 2; ++j) {
           const int slot = j % kWgQS;
           mbar_wait(&q_full[slot], (uint32_t)((j / kWgQS) & 1));
@@ -704,7 +723,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
               const float4 r = *reinterpret_cast<const float4*>(base + ((qq ^ sw) << 4));
               f[1 + 4 * qq] = r.x; f[2 + 4 * qq] = r.y; f[3 + 4 * qq] = r.z; f[4 + 4 * qq] = r.w;
             }
-            wg_transform(f, k.q_ab, k.q_act, c, k.Qc);
+            wg_transform(f, aff, ta, tb, k.q_act, c, k.Qc);
 #pragma unroll
             for (int qq = 0; qq < 8; ++qq) {
               const int o = (qq ^ sw) << 4;
@@ -733,8 +752,10 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
     if (k.CinTot > (k.swapped ? k.Qc : k.Pc))   // time channel: its entries of this split are zero (time_wgrad_kernel fills split 0)
       for (int e = threadIdx.x - 64; e < 9 * k.Cd; e += 128)
         out[(e % 9) + 9 * ((k.CinTot - 1) + (size_t)k.CinTot * (e / 9))] = 0.0f;
+    if (threadIdx.x == 64) CTRACE(5, 0);
     mbar_wait(&acc_done, 0u);
     tc_fence_after();
+    if (threadIdx.x == 64) CTRACE(5, 1);
     const int m = q * 32 + lane;
     const int pc = m & 63;
 #pragma unroll 1
@@ -763,6 +784,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
       }
     }
   }
+  if (threadIdx.x == 64) CTRACE(5, 2);
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -917,9 +939,9 @@ static CUtensorMap wg_map(const float* base, const ConvTcGeom& g, int C, int box
 }
 void convtc_wgrad(lrnde_ctx* ctx, const ConvTcGeom& g, const ConvTcWgP& p) {
   static bool attr_set = false;
-  // P ring + Q ring of 4 + 2 mirrored slots (hi and lo) + alignment + the ignored rows of the last A tile
-  const int smem64 = convtc::wg_xs(64) * convtc::kWgXSlot + 12 * 64 * 128 + 1024 + 8192;
-  const int smem16 = convtc::wg_xs(16) * convtc::kWgXSlot + 12 * 16 * 128 + 1024 + 8192;
+  // P ring + Q ring of 4 + 2 mirrored slots (hi and lo) + raw P staging ring + alignment
+  const int smem64 = convtc::wg_xs(64) * convtc::kWgXSlot + 12 * 64 * 128 + convtc::kWgRS * convtc::kWgPTile + 1024;
+  const int smem16 = convtc::wg_xs(16) * convtc::kWgXSlot + 12 * 16 * 128 + convtc::kWgRS * convtc::kWgPTile + 1024;
   if (!attr_set) {
     LR_CUDA(cudaFuncSetAttribute(convtc::wgrad_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem64));
     LR_CUDA(cudaFuncSetAttribute(convtc::wgrad_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem16));
