@@ -123,7 +123,18 @@ for ctag, cl, Wd, Ht, per_rank in CONV_CASES:
     # ~1e-4, and the layer-1 statistics move with the stage times through the time channel: the bar of the single-GPU test
     # of the same quantity against the oracle (tests/test_gpu_conv.py::test_layer_returns_the_state_of_the_closure)
     run_tol = 1e-4 if ctag == "SIMT" else 5e-3
-    good = same_f and same_b and e_u < 1e-4 and e_dx < 1e-3 and e_dps < 1e-3 and e_run < run_tol and e_reg < 1e-3
+    # ... and the regulariser value is the embedded error estimate of ONE step at the conservative initial dt: where it is
+    # Float32 rounding noise, two non-bit-identical Float32 evaluations agree only up to that noise.  As in
+    # tests/test_gpu_conv.py::test_conv_neural_ode_layer_matches_oracle the Float64 twin of the oracle measures it.
+    reg_tol = 1e-3
+    if ctag != "SIMT":
+        okw = dict(regularize="unbiased", abstol=1e-3, reltol=1e-3, maxiters=1000)
+        o32, o64 = orc.NeuralODE(onet, **okw), orc.NeuralODE(onet, dtype=np.float64, **okw)
+        _, ost32, _ = o32.forward(cx, cps, o32.initialstates(np.random.default_rng(5)))
+        _, ost64, _ = o64.forward(cx.astype(np.float64), cps.astype(np.float64), o64.initialstates(np.random.default_rng(5)))
+        r32, r64 = float(ost32["reg_val"]), float(ost64["reg_val"])
+        reg_tol = 1e-3 + 10 * abs(r32 - r64) / abs(s["reg"])
+    good = same_f and same_b and e_u < 1e-4 and e_dx < 1e-3 and e_dps < 1e-3 and e_run < run_tol and e_reg < reg_tol
     ok = ok and good
     if not good and rank == 0:
         dd = np.abs(d["running"] - s["running"])
@@ -131,7 +142,7 @@ for ctag, cl, Wd, Ht, per_rank in CONV_CASES:
               "dp", d["running"][np.argsort(-dd)[:6]], "nfe", s["nfe"], d["nfe"], flush=True)
     print(f"[multi-gpu rank {rank}/{world}] conv+BatchNorm ({ctag}) fwd attempts {len(s['acc'])}/{len(d['acc'])} same={same_f} bwd attempts "
           f"{len(s['bacc'])}/{len(d['bacc'])} same={same_b} u {e_u:.2e} d_x {e_dx:.2e} d_ps(allreduced) {e_dps:.2e} running stats "
-          f"{e_run:.2e} reg {e_reg:.2e} -> {'ok' if good else 'MISMATCH'}", flush=True)
+          f"{e_run:.2e} reg {e_reg:.2e} (bar {reg_tol:.1e}) -> {'ok' if good else 'MISMATCH'}", flush=True)
 dist.barrier()
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)

@@ -27,7 +27,8 @@ def test_sharded_run_matches_the_single_gpu_run(n):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
            "--master-port", str(29530 + n), os.path.join(ROOT, "tests", "multi_gpu_worker.py")]
     r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
-    lines = [l for l in r.stdout.splitlines() if l.startswith("[multi-gpu")]
+    lines = [l for l in r.stdout.splitlines() if "[multi-gpu" in l]
     print("\n".join(lines))
     assert r.returncode == 0, (r.stdout[-3000:], r.stderr[-3000:])
-    assert len(lines) == 4 * n and all(l.endswith("ok") for l in lines)
+    # (the ranks print at the same time: two reports can share a line)
+    assert r.stdout.count("[multi-gpu rank") == 4 * n and r.stdout.count("-> ok") == 4 * n and "MISMATCH" not in r.stdout
