@@ -533,6 +533,18 @@ struct ConvEval {
     for (int l = 0; l < upto; ++l) {
       const ConvLayerInfo& Li = m->conv[l];
       if (tc) {
+        static const bool fuse = !(getenv("LRNDE_CONV_FUSE") && getenv("LRNDE_CONV_FUSE")[0] == '0');
+        if (l > 0 && fuse && (Li.cin & 15) == 0) {
+          // the convolution forms its operand itself from the stored raw output of the previous layer (BatchNorm scale /
+          // shift + activation + hi / lo split by producer warps): no pack launch, no (F) round trip through HBM
+          ConvTcP q;
+          memset(&q, 0, sizeof(q));
+          q.srcZ = z[l - 1]; q.src_ab = m->conv[l - 1].bn ? ab[l - 1] : nullptr; q.src_act = m->conv[l - 1].act;
+          q.Wimg = wimg[l]; q.K = Li.cin; q.tsum = m->td ? tsum[l] : nullptr; q.tdesc = m->td ? in : nullptr;
+          q.Y = l == L - 1 ? nullptr : z[l]; q.ydesc = l == L - 1 ? (out ? out : in) : nullptr;
+          q.out_scale = 1.0f; q.Cout = Li.cout; q.stat_part = (Li.bn && !testmode) ? spart : nullptr; q.done = done;
+          convtc_conv(ctx, geo, q);
+        } else {
         ConvTcPackP pk;
         memset(&pk, 0, sizeof(pk));
         if (l == 0) { pk.xdesc = in; pk.side_to_desc_dst = side_to_in_dst ? 1 : 0; pk.side = side; pk.in_act = ACT_IDENTITY; }
@@ -541,6 +553,7 @@ struct ConvEval {
         convtc_pack(ctx, geo, pk);
         launch_tc(wimg[l], Li.cin, m->td ? tsum[l] : nullptr, m->td ? in : nullptr, l == L - 1 ? nullptr : z[l],
                   l == L - 1 ? (out ? out : in) : nullptr, 1.0f, Li.cout, (Li.bn && !testmode) ? spart : nullptr, done);
+        }
       } else {
       ConvP q;
       memset(&q, 0, sizeof(q));

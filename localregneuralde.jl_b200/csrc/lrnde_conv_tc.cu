@@ -232,9 +232,14 @@ __device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
 }
 
 constexpr int kConvThreads = 64 + 256;   // warp 0: bulk copies, warp 1: tcgen05.mma, warps 2..9: epilogue (two per TMEM lane quarter)
+constexpr int kConvProd = 256;           // SRC = 1: warps 10..17 form the A operand in shared memory
 // MODE 0: plain epilogue; 1: + (sum, sum of squares) of the raw output; 2: + the two sums of the BatchNorm pullback
-template <int NOUT, int MODE>
-__global__ void __launch_bounds__(kConvThreads, 1) conv_kernel(ConvK k) {
+// SRC 0: the A operand is the packed (F) image (bulk copies); 1: it is formed here from a stored [W,H,K,B] array: four
+// producer warps read the patch run of a stage (584 positions x 8 channels), apply BatchNorm scale / shift + activation,
+// split into tf32 hi / lo and write the (F) layout straight into the stage -- the pack kernel's work without its 151 MB
+// round trip through HBM (the weights still arrive by bulk copy)
+template <int NOUT, int MODE, int SRC>
+__global__ void __launch_bounds__(kConvThreads + SRC * kConvProd, 1) conv_kernel(ConvK k) {
   const ConvTcP& p = k.p;
   if (p.done && *p.done) return;
   constexpr int STB = stage_bytes(NOUT), WSB = wstage_bytes(NOUT);
@@ -249,6 +254,12 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_kernel(ConvK k) {
   // per-channel constants of the BatchNorm pullback (a, b, mean, invstd): with 222 KB of shared memory there is next to no
   // L1 left, every __ldg of them went to L2 (long-scoreboard stalls on the first FFMA were 90 % of the epilogue's samples)
   __shared__ float s_bw[MODE == 2 ? 4 : 1][MODE == 2 ? 64 : 1];
+  __shared__ float s_in[SRC == 1 ? 2 : 1][SRC == 1 ? 64 : 1];   // SRC = 1: scale / shift of the input channels
+  if (SRC == 1 && threadIdx.x < 64) {
+    const int c = threadIdx.x;
+    const bool ok = p.src_ab != nullptr && c < p.K;
+    s_in[0][c] = ok ? p.src_ab[c] : 1.0f; s_in[1][c] = ok ? p.src_ab[p.K + c] : 0.0f;
+  }
   if (MODE == 2 && threadIdx.x < 64) {
     const int c = threadIdx.x;
     const bool ok = c < p.Cout;
@@ -261,7 +272,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_kernel(ConvK k) {
   const int nst = p.K >> 3;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1u); mbar_init(&empty_bar[s], 1u); }
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], SRC == 1 ? 1u + kConvProd / 32 : 1u); mbar_init(&empty_bar[s], 1u); }
     for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1u); mbar_init(&tmem_free[s], 8u); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -290,14 +301,16 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_kernel(ConvK k) {
         if (elect_one_sync()) {
           uint8_t* dst = sm + (size_t)slot * STB;
           if (s == 0) CTRACE(1, (int)(ks / nst));
-          mbar_arrive_expect_tx(&full_bar[slot], (uint32_t)STB);
+          mbar_arrive_expect_tx(&full_bar[slot], (uint32_t)(SRC == 1 ? WSB : STB));
+          if (SRC == 0) {
 #pragma unroll
-          for (int part = 0; part < 2; ++part)
+            for (int part = 0; part < 2; ++part)
 #pragma unroll
-            for (int k4 = 0; k4 < 2; ++k4) {
-              const float* src = (part ? p.Flo : p.Fhi) + ((size_t)(2 * s + k4) * (size_t)k.NPA + (size_t)g * kCtGroup) * 4;
-              bulk_g2s(dst + (part * 2 + k4) * kRunB, src, (uint32_t)kRunB, &full_bar[slot]);
-            }
+              for (int k4 = 0; k4 < 2; ++k4) {
+                const float* src = (part ? p.Flo : p.Fhi) + ((size_t)(2 * s + k4) * (size_t)k.NPA + (size_t)g * kCtGroup) * 4;
+                bulk_g2s(dst + (part * 2 + k4) * kRunB, src, (uint32_t)kRunB, &full_bar[slot]);
+              }
+          }
           bulk_g2s(dst + 4 * kRunB, p.Wimg + (size_t)s * WSB, (uint32_t)WSB, &full_bar[slot]);
         }
         __syncwarp();
@@ -344,6 +357,90 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_kernel(ConvK k) {
           if (s == nst - 1) { mma_commit(&acc_full[db]); CTRACE(3, it); }
         }
         __syncwarp();
+      }
+    }
+  } else if (SRC == 1 && warp >= kConvThreads / 32) {
+    // ---------------- A-operand producers: thread pt owns the run positions r = pt + 128 m (decoded once per group)
+    const int pt = (int)threadIdx.x - kConvThreads;
+    const uint32_t uIMG = (uint32_t)k.IMG, uPW = (uint32_t)k.PW;
+    const size_t HW = (size_t)k.Wd * k.Ht;
+    constexpr int NPOS = (kRun + kConvProd - 1) / kConvProd;   // 5
+    uint32_t ks = 0;
+    for (int g = blockIdx.x; g < k.ngroups; g += gridDim.x) {
+      uint32_t poff[NPOS];
+#pragma unroll
+      for (int m = 0; m < NPOS; ++m) {
+        const int r = pt + kConvProd * m;
+        const long pp = (long)g * kCtGroup + r - kCtGuard;
+        poff[m] = 0xFFFFFFFFu;
+        if (r < kRun && pp >= 0 && pp < k.NP) {
+          const uint32_t up = (uint32_t)pp, b = up / uIMG, r0 = up - b * uIMG;
+          const uint32_t yh = r0 / uPW, xh = r0 - yh * uPW;
+          if (xh >= 1 && xh <= (uint32_t)k.Wd && yh >= 1 && yh <= (uint32_t)k.Ht)
+            poff[m] = (xh - 1) + (uint32_t)k.Wd * ((yh - 1) + (uint32_t)k.Ht * ((uint32_t)p.K * b));
+        }
+      }
+      // software pipeline over the half stages (4 channels each): the loads of the next half are in flight while the
+      // current one is transformed and stored (the kernel has no L1: every load is an L2 / HBM round trip)
+      auto issue = [&](int c0, float (&v)[NPOS][4]) {
+#pragma unroll
+        for (int m = 0; m < NPOS; ++m)
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            v[m][j] = (poff[m] != 0xFFFFFFFFu) ? __ldcg(p.srcZ + poff[m] + (size_t)(c0 + j) * HW) : 0.0f;
+      };
+      auto store = [&](uint8_t* dst, int k4, int c0, const float (&v)[NPOS][4]) {
+#pragma unroll
+        for (int m = 0; m < NPOS; ++m) {
+          const int r = pt + kConvProd * m;
+          if (r < kRun) {
+            float4 h4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f), l4 = h4;
+            if (poff[m] != 0xFFFFFFFFu) {
+              float t[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                t[j] = fmaf(s_in[0][c0 + j], v[m][j], s_in[1][c0 + j]);
+                if (p.src_act == ACT_GELU) t[j] = gelu_f(t[j]);
+                else if (p.src_act != ACT_IDENTITY) t[j] = act_call(p.src_act, t[j]);
+              }
+              h4 = make_float4(tf32_rna(t[0]), tf32_rna(t[1]), tf32_rna(t[2]), tf32_rna(t[3]));
+              l4 = make_float4(tf32_rna(t[0] - h4.x), tf32_rna(t[1] - h4.y), tf32_rna(t[2] - h4.z), tf32_rna(t[3] - h4.w));
+            }
+            *reinterpret_cast<float4*>(dst + k4 * kRunB + r * 16) = h4;
+            *reinterpret_cast<float4*>(dst + (2 + k4) * kRunB + r * 16) = l4;
+          }
+        }
+      };
+      // four half stages in flight (2 x 9.3 KB each way would bound the stream at ~0.8 TB/s): rounds r = 2 s + k4, register
+      // sets v0..v3 in rotation, two stages per trip (nst is even: the host uses this path only for K % 16 == 0)
+      float v0[NPOS][4], v1[NPOS][4], v2[NPOS][4], v3[NPOS][4];
+      const int nr = 2 * nst;
+      auto c_of = [](int r) { return 4 * r; };
+      issue(c_of(0), v0);
+      issue(c_of(1), v1);
+      issue(c_of(2), v2);
+      for (int s = 0; s < nst; s += 2, ks += 2) {
+        const int r = 2 * s;
+        const uint32_t slot0 = ks % kStages, ph0 = (ks / kStages) & 1u;
+        const uint32_t slot1 = (ks + 1) % kStages, ph1 = ((ks + 1) / kStages) & 1u;
+        uint8_t* dst0 = sm + (size_t)slot0 * STB;
+        uint8_t* dst1 = sm + (size_t)slot1 * STB;
+        issue(c_of(r + 3), v3);
+        mbar_wait(&empty_bar[slot0], ph0 ^ 1u);
+        store(dst0, 0, c_of(r), v0);
+        if (r + 4 < nr) issue(c_of(r + 4), v0);
+        store(dst0, 1, c_of(r + 1), v1);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full_bar[slot0]);
+        if (r + 5 < nr) issue(c_of(r + 5), v1);
+        mbar_wait(&empty_bar[slot1], ph1 ^ 1u);
+        store(dst1, 0, c_of(r + 2), v2);
+        if (r + 6 < nr) issue(c_of(r + 6), v2);
+        store(dst1, 1, c_of(r + 3), v3);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full_bar[slot1]);
       }
     }
   } else {
@@ -854,12 +951,16 @@ static void convtc_attrs() {   // outside stream capture: the first call is prep
   static bool attr_set = false;
   if (attr_set) return;
   const int s64 = convtc::kStages * convtc::stage_bytes(64) + 256, s16 = convtc::kStages * convtc::stage_bytes(16) + 256;
-  LR_CUDA(cudaFuncSetAttribute(convtc::conv_kernel<64, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, s64));
-  LR_CUDA(cudaFuncSetAttribute(convtc::conv_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, s64));
-  LR_CUDA(cudaFuncSetAttribute(convtc::conv_kernel<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, s64));
-  LR_CUDA(cudaFuncSetAttribute(convtc::conv_kernel<16, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, s16));
-  LR_CUDA(cudaFuncSetAttribute(convtc::conv_kernel<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, s16));
-  LR_CUDA(cudaFuncSetAttribute(convtc::conv_kernel<16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, s16));
+  LR_CUDA(cudaFuncSetAttribute(convtc::conv_kernel<64, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, s64));
+  LR_CUDA(cudaFuncSetAttribute(convtc::conv_kernel<64, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, s64));
+  LR_CUDA(cudaFuncSetAttribute(convtc::conv_kernel<64, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, s64));
+  LR_CUDA(cudaFuncSetAttribute(convtc::conv_kernel<16, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, s16));
+  LR_CUDA(cudaFuncSetAttribute(convtc::conv_kernel<16, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, s16));
+  LR_CUDA(cudaFuncSetAttribute(convtc::conv_kernel<16, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, s16));
+  LR_CUDA(cudaFuncSetAttribute(convtc::conv_kernel<64, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, s64));
+  LR_CUDA(cudaFuncSetAttribute(convtc::conv_kernel<64, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, s64));
+  LR_CUDA(cudaFuncSetAttribute(convtc::conv_kernel<16, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, s16));
+  LR_CUDA(cudaFuncSetAttribute(convtc::conv_kernel<16, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, s16));
   attr_set = true;
 }
 
@@ -887,15 +988,24 @@ void convtc_conv(lrnde_ctx* ctx, const ConvTcGeom& g, const ConvTcP& p) {
   k.dbg = dbg_env ? atoi(dbg_env) : 0;
   const int grid = std::min(g.ngroups, 148);
   const int mode = !p.stat_part ? 0 : (p.bwd_z ? 2 : 1);
-  const int T = convtc::kConvThreads;
-  if (NOUT == 64) {
-    if (mode == 0) convtc::conv_kernel<64, 0><<<grid, T, smem64, ctx->stream>>>(k);
-    else if (mode == 1) convtc::conv_kernel<64, 1><<<grid, T, smem64, ctx->stream>>>(k);
-    else convtc::conv_kernel<64, 2><<<grid, T, smem64, ctx->stream>>>(k);
+  const int T = convtc::kConvThreads, T1 = convtc::kConvThreads + convtc::kConvProd;
+  if (p.srcZ) {   // the A operand is formed inside the kernel (forward convolutions on a stored raw conv output)
+    if (mode == 2) { lr_set_error("convtc_conv: srcZ with the pullback epilogue is not instantiated"); throw LrError(LRNDE_EINVAL); }
+    if (NOUT == 64) {
+      if (mode == 0) convtc::conv_kernel<64, 0, 1><<<grid, T1, smem64, ctx->stream>>>(k);
+      else convtc::conv_kernel<64, 1, 1><<<grid, T1, smem64, ctx->stream>>>(k);
+    } else {
+      if (mode == 0) convtc::conv_kernel<16, 0, 1><<<grid, T1, smem16, ctx->stream>>>(k);
+      else convtc::conv_kernel<16, 1, 1><<<grid, T1, smem16, ctx->stream>>>(k);
+    }
+  } else if (NOUT == 64) {
+    if (mode == 0) convtc::conv_kernel<64, 0, 0><<<grid, T, smem64, ctx->stream>>>(k);
+    else if (mode == 1) convtc::conv_kernel<64, 1, 0><<<grid, T, smem64, ctx->stream>>>(k);
+    else convtc::conv_kernel<64, 2, 0><<<grid, T, smem64, ctx->stream>>>(k);
   } else {
-    if (mode == 0) convtc::conv_kernel<16, 0><<<grid, T, smem16, ctx->stream>>>(k);
-    else if (mode == 1) convtc::conv_kernel<16, 1><<<grid, T, smem16, ctx->stream>>>(k);
-    else convtc::conv_kernel<16, 2><<<grid, T, smem16, ctx->stream>>>(k);
+    if (mode == 0) convtc::conv_kernel<16, 0, 0><<<grid, T, smem16, ctx->stream>>>(k);
+    else if (mode == 1) convtc::conv_kernel<16, 1, 0><<<grid, T, smem16, ctx->stream>>>(k);
+    else convtc::conv_kernel<16, 2, 0><<<grid, T, smem16, ctx->stream>>>(k);
   }
   LCT_COUNT(ctx);
 }

@@ -68,6 +68,9 @@ void convtc_wpack(lrnde_ctx* ctx, const float* w, int CinTot, int Cout, int tran
 
 struct ConvTcP {
   const float* Fhi; const float* Flo;
+  // alternative source of the A operand: a stored [W,H,K,B] array with v <- act(a[c] v + b[c]) applied on the fly
+  // (src_ab null: identity scale / shift); the (F) image is not read then
+  const float* srcZ; const float* src_ab; int src_act;
   const uint8_t* Wimg; int K;               // input channels (multiple of 8)
   const float* tsum; const LinComb* tdesc;  // time channel (null: none)
   float* Y; const LinComb* ydesc; float out_scale; int Cout;
