@@ -369,6 +369,8 @@ struct ConvEval {
       if ((Li.cin & 7) || (Li.cout & 7) || Li.cin > 64 || Li.cout > 64) return false;
     return m->Wd + 3 <= kCtGuard;
   }
+  // haloed positions of the batch are indexed with 32 bits inside the kernels
+  static bool tc_fits(const lrnde_model* m, int64_t b) { return (double)b * (m->Wd + 2) * (m->Ht + 2) < 2.0e9; }
 
   static int tile_rows(int PT, int Wd, int Ht) { return std::min(PT / (Wd >> 2), Ht); }
   static bool narrow(int cout) { return cout <= 16; }   // <8,8,4> instantiation (whole-image tiles)
@@ -384,7 +386,7 @@ struct ConvEval {
         lr_fail(LRNDE_EINVAL, "BatchNorm with %d channels on a multi-rank ctx (the statistics exchange holds %d)", Li.cout, LR_BN_MAXC);
     L = (int)m->conv.size();
     HW = (size_t)m->Wd * m->Ht;
-    tc = tc_eligible(m);
+    tc = tc_eligible(m) && tc_fits(m, b);
     if (tc) geo.set(m->Wd, m->Ht, (int)B);
     wg_tc = tc && vjp && convtc_wgrad_ok(geo) && !getenv("LRNDE_CONV_WG_SIMT");
     z.assign(L, nullptr); ab.assign(L, nullptr); stat.assign(L, nullptr); pack.assign(L, nullptr); packT.assign(L, nullptr);
@@ -534,7 +536,8 @@ struct ConvEval {
       const ConvLayerInfo& Li = m->conv[l];
       if (tc) {
         static const bool fuse = !(getenv("LRNDE_CONV_FUSE") && getenv("LRNDE_CONV_FUSE")[0] == '0');
-        if (l > 0 && fuse && (Li.cin & 15) == 0) {
+        // (the producers address the source with 32-bit pixel offsets)
+        if (l > 0 && fuse && (Li.cin & 15) == 0 && (double)HW * Li.cin * (double)B < 4.0e9) {
           // the convolution forms its operand itself from the stored raw output of the previous layer (BatchNorm scale /
           // shift + activation + hi / lo split by producer warps): no pack launch, no (F) round trip through HBM
           ConvTcP q;
