@@ -17,12 +17,15 @@
 //       (P) for cotangents, a plain [W, H, C, B] fp32 copy: the weight gradient (K = pixels of an image row) reads its
 //           operands -- raw conv outputs, y(t), cotangents -- through tensor-map TMA (K-major SWIZZLE_128B row tiles) and
 //           applies BatchNorm + activation, the hi / lo split and the dx shifts in shared memory.
-//   * convtc_kernel<NOUT>: persistent CTAs, M = 128 consecutive (haloed) positions, N = output channels, K = 8 input
-//     channels per MMA; a group of four M tiles shares every weight stage, accumulators double-buffered in TMEM
+//   * conv_kernel<NOUT, MODE, SRC>: persistent CTAs, M = 128 consecutive (haloed) positions, N = output channels, K = 8
+//     input channels per MMA; a group of four M tiles shares every weight stage, accumulators double-buffered in TMEM
 //     (2 x 4 x NOUT columns), epilogue = time-channel term + scale + coalesced [W,H,C,B] stores + BatchNorm partial
-//     sums.  The TDChain time channel (common.jl:19-33: t inside the image, 0 in the padding) never enters the GEMM:
-//     its contribution t * sum_{taps inside} w[tap, time, co] depends only on the border class of the pixel.
-//   * convtc_wgrad_kernel: dW[tap, ci, co] = sum_p X[p + d_tap, ci] Delta[p, co]; see lrnde_conv_tc.cu.
+//     sums (MODE 1: of the raw output; MODE 2: of the BatchNorm pullback that follows a data-gradient convolution).
+//     The TDChain time channel (common.jl:19-33: t inside the image, 0 in the padding) never enters the GEMM: its
+//     contribution t * sum_{taps inside} w[tap, time, co] depends only on the border class of the pixel.  SRC = 1: the
+//     (F) operand is not read from memory at all -- eight producer warps form it in the stage from the stored raw output
+//     of the previous layer (ConvTcP::srcZ).
+//   * wgrad_kernel<NB>: dW[tap, ci, co] = sum_p X[p + d_tap, ci] Delta[p, co]; see below and lrnde_conv_tc.cu.
 #pragma once
 #include "lrnde_host.h"
 
